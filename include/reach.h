@@ -1,0 +1,164 @@
+/* libreach_sm100a -- C ABI of the B200-native linear-flowpipe hot path of JuliaReach/Reachability.jl v0.7.0.
+ *
+ * The reference has no FFI of its own (it is pure Julia); each entry point below replaces one Julia-level
+ * seam on the hot path and is what the `ccall` shim (julia/ReachSM100a.jl) binds.
+ * Citations are file:line under /root/reference/src.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = OK, 1 = invalid argument, 2 = CUDA/runtime error,
+ *     3 = unsupported on this path (the caller must raise; there is NO CPU fallback in this library);
+ *     the message is available through reach_last_error().
+ *   - all host pointers are caller-owned, column-major Float64 (Julia layout) with an explicit leading
+ *     dimension, valid only for the duration of the call; the library copies what it needs to the device
+ *     before returning and never retains host pointers.
+ *   - indices crossing the ABI are 0-based int32; sizes are int64 (Julia Int).
+ *   - one reach_ctx is bound to one CUDA device and one stream; multi-GPU runs use one process (rank) and
+ *     one context per GPU and shard rows / steps / problems across ranks (DESIGN.md "Multi-GPU").
+ */
+#ifndef REACH_SM100A_H
+#define REACH_SM100A_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define REACH_API __attribute__((visibility("default")))
+#else
+#define REACH_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REACH_OK 0
+#define REACH_EINVAL 1
+#define REACH_ECUDA 2
+#define REACH_EUNSUPPORTED 3
+
+#define REACH_FORWARD 0  /* discretize(...; algorithm="forward")  discretize.jl:654-655 */
+#define REACH_BACKWARD 1 /* discretize(...; algorithm="backward") discretize.jl:656-657 */
+
+typedef struct reach_ctx reach_ctx;
+typedef struct reach_boxplan reach_boxplan;   /* BFFPSV18 problem resident on the device */
+typedef struct reach_flowpipe reach_flowpipe; /* GLGM06 problem + zonotope flowpipe resident on the device */
+typedef struct reach_ensemble reach_ensemble; /* batched homogeneous GLGM06 flowpipes on the device */
+
+/* ---- context ----------------------------------------------------------------------------------------- */
+REACH_API int32_t reach_version(void);
+/* Module `__init__` of the Julia shim. Fails (REACH_ECUDA) when no sm_100 device is visible. */
+REACH_API int32_t reach_ctx_create(int32_t device, reach_ctx** out);
+REACH_API void reach_ctx_destroy(reach_ctx* ctx);
+/* Message of the last failure on this context (ctx == NULL: last failure of reach_ctx_create). */
+REACH_API const char* reach_last_error(const reach_ctx* ctx);
+REACH_API int32_t reach_sync(reach_ctx* ctx);
+/* Counters for `@timing` (logging.jl:80-88) and bench.py: kernels launched so far on this context. */
+REACH_API int32_t reach_launch_count(reach_ctx* ctx, uint64_t* launches);
+
+/* ---- discretisation: src/ReachSets/discretize.jl ----------------------------------------------------- */
+/* exp_Aδ(A, δ; exp_method="base") = exp(Matrix(A*δ))            discretize.jl:150-152 */
+REACH_API int32_t reach_expm(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, double* Phi, int64_t ldphi);
+/* Φ₁(A, δ) = exp(Pmatrix)[1:n, n+1:2n]   discretize.jl:221-226;  Φ₂(A, δ) = exp(Pmatrix)[1:n, 2n+1:3n]  :296-301.
+ * Computed from the block-triangular structure without forming the 3n x 3n exponential. Either output may be NULL. */
+REACH_API int32_t reach_phi12(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, double* Phi1, int64_t ld1,
+                    double* Phi2, int64_t ld2);
+/* discretize_interpolation (discretize.jl:627-675) for a box X0 = (c, r) and a constant box input U = (cU, rU)
+ * entering through B (n x m; m = 0: homogeneous; B == NULL with m == n: identity), followed by the box
+ * decomposition of the lazy Ω0 that BFFPSV18 performs (BFFPSV18/reach.jl:64-65).
+ * Outputs (each may be NULL): Phi n x n; Phi2abs = Φ₂(|A|, δ) n x n; c0, r0 (n) box of Ω0; rE (n) radius of Einit;
+ * rpsi (n) radius of Eψ0; MU = δ·B (n x m, ld n). */
+REACH_API int32_t reach_discretize_box(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm,
+                             const double* c, const double* r, int64_t m, const double* B, int64_t ldb,
+                             const double* cU, const double* rU, double* Phi, int64_t ldphi, double* Phi2abs,
+                             int64_t ldphi2, double* c0, double* r0, double* rE, double* rpsi, double* MU);
+
+/* ---- BFFPSV18: dense reach_blocks! (BFFPSV18/reach_blocks.jl:135-224) ---------------------------------- */
+/* One-shot host-buffer call = the method the shim adds for
+ *   reach_blocks!(ϕ::Matrix{Float64}, Xhat0::Vector{<:Union{Interval,Hyperrectangle}}, U, ..., res)
+ * dispatched from the registry at BFFPSV18/reach.jl:191-193.
+ *   Phi n x n; (c0, r0) decomposed Ω0 (all n coordinates, reach_blocks.jl:185-187);
+ *   inputs: MU = δB (n x m), U = box(cU, rU), rpsi (n) -- m == 0 (or MU == NULL): homogeneous (U == nothing);
+ *   rows: the nrows 0-based coordinates of the blocks in `:blocks` (compute_dimensions.jl:1-15);
+ *   N = number of reach sets (reach.jl:54).
+ * Outputs centers/radii: nrows x N column-major (column k-1 = step k; reach_blocks.jl:152-158,195-202).
+ * steps_done receives N (the `index` of the (index, skip) tuple, reach_blocks.jl:62; skip is always false for the
+ * Universe invariant, reach.jl:225-227). */
+REACH_API int32_t reach_bffpsv18_boxes(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             double* centers, double* radii, int64_t* steps_done);
+/* Same computation split into upload / device-resident run / download (what bench.py times as `value`). */
+REACH_API int32_t reach_boxplan_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             reach_boxplan** out);
+REACH_API int32_t reach_boxplan_run(reach_boxplan* plan);                      /* whole time loop on the device */
+REACH_API int32_t reach_boxplan_fetch(reach_boxplan* plan, double* centers, double* radii); /* nrows x N each */
+/* Device pointers of the result (nrows x N column-major, ld = nrows), for zero-copy consumers. */
+REACH_API int32_t reach_boxplan_device_results(reach_boxplan* plan, double** centers_dev, double** radii_dev);
+/* CUDA-event time of the last run and of its dominant kernel (the stacked DMMA GEMM), launches of each. */
+REACH_API int32_t reach_boxplan_timing(reach_boxplan* plan, double* run_ms, double* gemm_ms, int64_t* gemm_launches,
+                             double* gemm_flops);
+REACH_API void reach_boxplan_destroy(reach_boxplan* plan);
+/* check mode, dense check_blocks (BFFPSV18/check_blocks.jl:105-183) for a half-space property
+ * is_contained_in(LinearConstraint(ell, bound)) already mapped to `rows` (partitions.jl:33-46).
+ * violation: first violating step (1-based) or 0 (check_blocks.jl:116). */
+REACH_API int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             const double* ell, double bound, int32_t eager, int64_t* violation);
+/* output_function branch (reach_blocks.jl:152-155,197-199; reach.jl:73-82): stored set is
+ * box_approximation(Mout * CPA(Xhat_k)); Mout is q x nrows. centers/radii: q x N. */
+REACH_API int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                                  const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                                  const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                                  int64_t q, const double* Mout, int64_t ldm, double* centers, double* radii);
+
+/* ---- GLGM06: reach_homog! / reach_inhomog! (GLGM06/reach.jl:5-62) -------------------------------------- */
+/* flags */
+#define REACH_GLGM06_KEEP_ZERO_GENERATORS 1 /* Zonotope(c, G; remove_zero_generators=false) semantics */
+#define REACH_GLGM06_STEPWISE 2             /* force the step-by-step kernels (no batched pipeline) */
+/* Upload Ω0red = (c0, G0 n x p0) (already reduce_order'ed, GLGM06/post.jl:20 -- or call reach_reduce_order) and
+ * the discretised input V = (cV, GV n x pV); pV == 0 and cV == NULL selects reach_homog!. */
+REACH_API int32_t reach_glgm06_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
+                            const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV,
+                            int64_t ldgv, int64_t N, int64_t max_order, int32_t flags, reach_flowpipe** out);
+REACH_API int32_t reach_glgm06_run(reach_flowpipe* fp); /* whole recurrence on the device; results stay there */
+/* Number of generators of every reach set R_1..R_N. */
+REACH_API int32_t reach_flowpipe_ngens(reach_flowpipe* fp, int32_t* p /* N */);
+/* Reach set k (1-based): centre (n) and generators (n x p_k, leading dimension ldg >= n). */
+REACH_API int32_t reach_flowpipe_step(reach_flowpipe* fp, int64_t k, double* c, double* G, int64_t ldg);
+/* Order-reduction record of step k >= 2 (which = 0: reduce_order of R_k, GLGM06/reach.jl:49; which = 1: of W, :55):
+ * p_in columns went in, m were boxed; ind[0..p_in) = sortperm(h) 0-based; h[0..p_in) the scores. Outputs may be NULL.
+ * m == 0 and p_in == 0 mean "no reduction happened" (r*n >= p). */
+REACH_API int32_t reach_flowpipe_selection(reach_flowpipe* fp, int64_t k, int32_t which, int32_t* p_in, int32_t* m, int32_t* ind,
+                                 double* h);
+REACH_API int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, double* gemm_ms, int64_t* gemm_launches,
+                              double* gemm_flops, double* reduce_ms, double* reduce_bytes);
+REACH_API void reach_flowpipe_free(reach_flowpipe* fp);
+/* reduce_order(Z, r) of LazySets (Girard), call site GLGM06/post.jl:20.  Gout must hold n x max(p, r*n) doubles;
+ * p_out receives the new generator count; ind (p, may be NULL) the sortperm. */
+REACH_API int32_t reach_reduce_order(reach_ctx* ctx, int64_t n, int64_t p, const double* c, const double* G, int64_t ldg,
+                           int64_t r, int32_t flags, double* Gout, int64_t ldgo, int64_t* p_out, int32_t* ind);
+
+/* Batched homogeneous ensemble (config C5): `batch` independent initial zonotopes (c0s n x batch, G0s n x p x batch)
+ * under the same Φ; R_k = (Φ c_{k-1}, Φ G_{k-1}) for every member (GLGM06/reach.jl:15-19). */
+REACH_API int32_t reach_ensemble_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t batch, int64_t p,
+                              const double* c0s, const double* G0s, int64_t N, reach_ensemble** out);
+REACH_API int32_t reach_ensemble_run(reach_ensemble* e);
+/* Member b (0-based), step k (1-based): centre n, generators n x p (ld n). */
+REACH_API int32_t reach_ensemble_step(reach_ensemble* e, int64_t b, int64_t k, double* c, double* G);
+/* Box hull of every member at step k: lo/hi n x batch. */
+REACH_API int32_t reach_ensemble_boxes(reach_ensemble* e, int64_t k, double* lo, double* hi);
+REACH_API int32_t reach_ensemble_timing(reach_ensemble* e, double* run_ms, double* bytes_per_step);
+REACH_API void reach_ensemble_free(reach_ensemble* e);
+
+/* ---- test/bench hooks ---------------------------------------------------------------------------------- */
+/* C = A * B with the library's DMMA GEMM (all host column-major); reps > 1 re-runs the device kernel and
+ * kernel_ms receives the mean CUDA-event time of one launch. */
+REACH_API int32_t reach_dgemm(reach_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                    int64_t ldb, double* C, int64_t ldc, int32_t reps, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REACH_SM100A_H */

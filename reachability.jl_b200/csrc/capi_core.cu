@@ -1,0 +1,121 @@
+// C ABI: context management and the GEMM test hook (include/reach.h).
+#include "common.cuh"
+#include "../../include/reach.h"
+
+using namespace reach;
+
+struct reach_ctx {
+    Ctx c;
+};
+
+namespace reach {
+thread_local std::string g_create_error;
+Ctx* ctx_of(reach_ctx* h) { return &h->c; }
+}  // namespace reach
+
+#define REACH_TRY(ctxptr) try {
+#define REACH_CATCH(ctxptr)                                              \
+    }                                                                    \
+    catch (const reach::Error& e) {                                      \
+        if (ctxptr) (ctxptr)->c.last_error = e.what();                   \
+        return e.code;                                                   \
+    }                                                                    \
+    catch (const std::exception& e) {                                    \
+        if (ctxptr) (ctxptr)->c.last_error = e.what();                   \
+        return REACH_ECUDA;                                              \
+    }
+
+extern "C" {
+
+int32_t reach_version(void) { return 100; }
+
+int32_t reach_ctx_create(int32_t device, reach_ctx** out) {
+    if (!out) return REACH_EINVAL;
+    *out = nullptr;
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(REACH_ECUDA, std::string("no CUDA device visible (libreach_sm100a has no CPU path): ") +
+                                         cudaGetErrorString(e));
+        REACH_REQUIRE(device >= 0 && device < count, "reach_ctx_create: device index out of range");
+        cudaDeviceProp prop;
+        REACH_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error(REACH_EUNSUPPORTED, std::string("device '") + prop.name + "' is not sm_100 (B200)");
+        REACH_CUDA(cudaSetDevice(device));
+        reach_ctx* h = new reach_ctx();
+        h->c.device = device;
+        h->c.sm_count = prop.multiProcessorCount;
+        REACH_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+        REACH_CUDA(cudaEventCreate(&h->c.ev0));
+        REACH_CUDA(cudaEventCreate(&h->c.ev1));
+        *out = h;
+        return REACH_OK;
+    } catch (const Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    }
+}
+
+void reach_ctx_destroy(reach_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    for (void* p : ctx->c.scratch) cudaFree(p);
+    if (ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
+    if (ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
+    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+
+const char* reach_last_error(const reach_ctx* ctx) {
+    return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str();
+}
+
+int32_t reach_sync(reach_ctx* ctx) {
+    if (!ctx) return REACH_EINVAL;
+    REACH_TRY(ctx)
+    REACH_CUDA(cudaSetDevice(ctx->c.device));
+    REACH_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return REACH_OK;
+    REACH_CATCH(ctx)
+}
+
+int32_t reach_launch_count(reach_ctx* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return REACH_EINVAL;
+    *launches = ctx->c.launches;
+    return REACH_OK;
+}
+
+int32_t reach_dgemm(reach_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                    int64_t ldb, double* C, int64_t ldc, int32_t reps, double* kernel_ms) {
+    if (!ctx) return REACH_EINVAL;
+    REACH_TRY(ctx)
+    Ctx* c = &ctx->c;
+    REACH_CUDA(cudaSetDevice(c->device));
+    REACH_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "reach_dgemm: bad arguments");
+    DMat dA = dmat_alloc(c, M, K), dB = dmat_alloc(c, K, N), dBt = dmat_alloc(c, N, K), dC = dmat_alloc(c, M, N);
+    dmat_upload(c, dA, A, lda);
+    dmat_upload(c, dB, B, ldb);
+    transpose(c, K, N, dB.p, dB.ld, dBt.p, dBt.ld);
+    gemm_nt(c, M, N, K, dA.p, dA.ld, dBt.p, dBt.ld, dC.p, dC.ld);
+    if (reps > 1) {
+        REACH_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < reps; ++i) gemm_nt(c, M, N, K, dA.p, dA.ld, dBt.p, dBt.ld, dC.p, dC.ld);
+        REACH_CUDA(cudaEventRecord(c->ev1, c->stream));
+        REACH_CUDA(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        REACH_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (kernel_ms) *kernel_ms = ms / reps;
+    } else if (kernel_ms) {
+        *kernel_ms = 0;
+    }
+    dmat_download(c, dC, C, ldc);
+    REACH_CUDA(cudaStreamSynchronize(c->stream));
+    dmat_free(dA); dmat_free(dB); dmat_free(dBt); dmat_free(dC);
+    return REACH_OK;
+    REACH_CATCH(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// libreach_sm100a -- shared declarations for the CUDA translation units.
+// B200 (sm_100a) only; no CPU fallback exists anywhere in this library.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <cuda_runtime.h>
+
+namespace reach {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define REACH_CUDA(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            char _buf[512];                                                                      \
+            snprintf(_buf, sizeof(_buf), "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(_e), \
+                     __FILE__, __LINE__, #expr);                                                 \
+            throw ::reach::Error(2, _buf);                                                       \
+        }                                                                                        \
+    } while (0)
+
+#define REACH_REQUIRE(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) throw ::reach::Error(1, std::string(msg));    \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// Device matrix, column-major (Julia layout), zero-padded so that every tile the GEMM touches exists:
+//   rows_alloc = round_up(rows, 8) + 128 slack, cols_alloc = round_up(cols, 128)  (see DESIGN.md "HBM layout").
+struct DMat {
+    double* p = nullptr;
+    int64_t rows = 0, cols = 0;     // logical
+    int64_t ld = 0;                 // leading dimension (doubles), multiple of 16
+    int64_t cols_alloc = 0;
+    bool owned = false;
+    size_t bytes() const { return (size_t)ld * (size_t)cols_alloc * sizeof(double); }
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    // launch accounting (bench.py "gpu_launches") and per-phase timings
+    uint64_t launches = 0;
+    double t_discretize_ms = 0, t_loop_ms = 0, t_h2d_ms = 0, t_d2h_ms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> scratch;     // freed at destroy
+};
+
+DMat dmat_alloc(Ctx* ctx, int64_t rows, int64_t cols, int64_t extra_rows = 0);
+void dmat_free(DMat& m);
+void dmat_upload(Ctx* ctx, DMat& dst, const double* host, int64_t ld_host);      // host col-major -> device
+void dmat_download(Ctx* ctx, const DMat& src, double* host, int64_t ld_host);
+void dmat_zero(Ctx* ctx, DMat& m);
+
+// ---- primitives (each is one kernel launch on ctx->stream) -------------------------------------------
+// C[M x N] = A[M x K] * B[K x N], A and C column-major, B given TRANSPOSED (Bt[k*ldbt + j] = B[k, j]).
+// All operands zero-padded as DMat guarantees.  Fused options: see gemm_dmma.cu.
+struct GemmEpilogue {
+    // C = alpha * A*B + beta_I * I (diagonal add on global row==col), used by the Taylor/Horner expm.
+    double alpha = 1.0;
+    double diag = 0.0;
+};
+void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt,
+             int64_t ldbt, double* C, int64_t ldc, const GemmEpilogue& ep = GemmEpilogue());
+// Bt[j + i*ldt] = A[i + j*lda]   (rows x cols -> cols x rows), out-of-place
+void transpose(Ctx* ctx, int64_t rows, int64_t cols, const double* A, int64_t lda, double* At, int64_t ldt);
+
+}  // namespace reach

@@ -1,0 +1,250 @@
+// FP64 GEMM for sm_100a: persistent, warp-specialised, TMA-bulk-copy (UBLKCP) -> mbarrier ring -> DMMA.
+//
+// tcgen05 has no f64 kind, so the FP64 tensor path on B200 is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4),
+// measured at 37.06 TFLOP/s register-resident on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl).
+// This kernel is the engine of every dense contraction on the path:
+//   * BFFPSV18  P_{k+s}[R,:] = P_k[R,:] · Φ^s  on a stack of s row-blocks (reach_blocks.jl:217-218)
+//   * GLGM06    Φ^k·[G0 | c0], Φ^k·[GV | cV], Φ^k·Φ (GLGM06/reach.jl:48,54,57)
+//   * discretize  Taylor/Horner products of e^{Aδ}, Φ₁, Φ₂ (discretize.jl:150-166, 221-315), A·A (:655)
+//
+// Operands: A [M x K] column-major (M contiguous), B passed TRANSPOSED as Bt [K x N] with N contiguous,
+// C [M x N] column-major.  Both operand tiles are therefore K "rows" of 1 KB contiguous memory, each moved
+// by one cp.async.bulk (TMA engine, no tensor map needed) into a padded smem row (pitch 132 doubles) so that
+// the m8n8k4 fragment loads (lane -> (k = lane%4, row = lane/4)) hit 16 distinct 8-byte bank slots per
+// half-warp: slot = 4*(lane%4) + lane/4 (mod 16).
+#include "common.cuh"
+
+namespace reach {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int STAGES = 4;
+constexpr int PITCH_A = BM + 4;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared through the TMA engine, completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+struct GemmParams {
+    const double* A;
+    const double* Bt;
+    double* C;
+    int64_t lda, ldbt, ldc;
+    int M, N, ksteps;
+    int tiles_m, tiles_n;
+    double alpha, diag;
+};
+
+// WNT = n8 tiles per warp along N; CTA tile is 128 x (32*WNT).
+template <int WNT>
+__global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+    constexpr int BN = 32 * WNT;
+    constexpr int PITCH_B = BN + 4;
+    constexpr int A_STAGE = BK * PITCH_A;     // doubles
+    constexpr int B_STAGE = BK * PITCH_B;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    if (warp == CONSUMER_WARPS) {
+        // ===== producer warp: lanes 0..15 move A rows, lanes 16..31 move Bt rows of each k-step =====
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const double* gA = p.A + (int64_t)tm * BM;
+            const double* gB = p.Bt + (int64_t)tn * BN;
+            for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(BK * (BM + BN) * sizeof(double)));
+                __syncwarp();
+                const int k = ks * BK + (lane & 15);
+                if (lane < 16)
+                    bulk_g2s(sA + s * A_STAGE + lane * PITCH_A, gA + (int64_t)k * p.lda, BM * 8, &full[s]);
+                else
+                    bulk_g2s(sB + s * B_STAGE + (lane - 16) * PITCH_B, gB + (int64_t)k * p.ldbt, BN * 8, &full[s]);
+            }
+        }
+    } else {
+        // ===== consumer warps: 2 (M) x 4 (N); warp tile 64 x 8*WNT =====
+        const int wm = warp >> 2, wn = warp & 3;
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            double acc[8][WNT][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+            for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                const double* a_s = sA + s * A_STAGE + t * PITCH_A + wm * 64 + g;
+                const double* b_s = sB + s * B_STAGE + t * PITCH_B + wn * (8 * WNT) + g;
+#pragma unroll
+                for (int kk = 0; kk < BK / 4; ++kk) {
+                    double a[8], b[WNT];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = a_s[kk * 4 * PITCH_A + i * 8];
+#pragma unroll
+                    for (int j = 0; j < WNT; ++j) b[j] = b_s[kk * 4 * PITCH_B + j * 8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < WNT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            // ---- epilogue: masked direct stores (8 rows x 8 B = two full 32 B sectors per column) ----
+            const int row0 = tm * BM + wm * 64 + g;
+            const int col0 = tn * BN + wn * (8 * WNT) + 2 * t;
+#pragma unroll
+            for (int j = 0; j < WNT; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = col0 + j * 8 + e;
+                    if (col < p.N) {
+                        double* cptr = p.C + (int64_t)col * p.ldc;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = row0 + i * 8;
+                            if (row < p.M) {
+                                double v = p.alpha * acc[i][j][e];
+                                if (row == col) v += p.diag;
+                                cptr[row] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int WNT>
+void launch(Ctx* ctx, const GemmParams& p) {
+    constexpr int BN = 32 * WNT;
+    const size_t smem = (size_t)STAGES * BK * (PITCH_A + BN + 4) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    gemm_dmma_kernel<WNT><<<grid, THREADS, smem, ctx->stream>>>(p);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+__global__ void transpose_kernel(int rows, int cols, const double* __restrict__ A, int64_t lda, double* __restrict__ At,
+                                 int64_t ldt) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + threadIdx.x, c = c0 + j;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? A[(int64_t)c * lda + r] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + threadIdx.x, r = r0 + j;     // At[c, r] = A[r, c]
+        if (r < rows && c < cols) At[(int64_t)r * ldt + c] = tile[threadIdx.x][j];
+    }
+}
+
+}  // namespace
+
+void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt, int64_t ldbt,
+             double* C, int64_t ldc, const GemmEpilogue& ep) {
+    if (M <= 0 || N <= 0) return;
+    REACH_REQUIRE(K > 0, "gemm_nt: K must be positive");
+    REACH_REQUIRE((lda % 2) == 0 && (ldbt % 2) == 0, "gemm_nt: leading dimensions must be even (16-byte TMA rows)");
+    REACH_REQUIRE((((uintptr_t)A) & 15) == 0 && (((uintptr_t)Bt) & 15) == 0, "gemm_nt: operands must be 16-byte aligned");
+    GemmParams p;
+    p.A = A; p.Bt = Bt; p.C = C;
+    p.lda = lda; p.ldbt = ldbt; p.ldc = ldc;
+    p.M = (int)M; p.N = (int)N; p.ksteps = (int)ceil_div(K, BK);
+    p.alpha = ep.alpha; p.diag = ep.diag;
+    p.tiles_m = (int)ceil_div(M, BM);
+    // widest column tile that wastes the least padding
+    int best = 4;
+    int64_t best_cols = round_up(N, 128);
+    for (int wnt = 3; wnt >= 2; --wnt) {
+        int64_t c = round_up(N, 32 * wnt);
+        if (c < best_cols) { best_cols = c; best = wnt; }
+    }
+    p.tiles_n = (int)ceil_div(N, 32 * best);
+    switch (best) {
+        case 4: launch<4>(ctx, p); break;
+        case 3: launch<3>(ctx, p); break;
+        default: launch<2>(ctx, p); break;
+    }
+}
+
+void transpose(Ctx* ctx, int64_t rows, int64_t cols, const double* A, int64_t lda, double* At, int64_t ldt) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(cols, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>((int)rows, (int)cols, A, lda, At, ldt);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+}  // namespace reach
