@@ -1,0 +1,332 @@
+"""Thin numpy-facing wrapper over the C ABI (one Context per GPU).  Mirrors what the Julia `ccall` shim does:
+marshal column-major Float64 arrays, check the int32 status, raise on failure."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import ReachError, dptr, fmat, fvec, iptr
+
+
+class Context:
+    """`reach_ctx`: one CUDA device + stream.  Raises ReachError when no B200 is visible."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self.lib.reach_ctx_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise ReachError(rc, (self.lib.reach_last_error(None) or b"").decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.reach_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise ReachError(rc, (self.lib.reach_last_error(self._h) or b"").decode())
+
+    def sync(self):
+        self._check(self.lib.reach_sync(self._h))
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._check(self.lib.reach_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    # ---- test hook -------------------------------------------------------------------------------------
+    def dgemm(self, A, B, reps: int = 1):
+        A, B = fmat(A), fmat(B)
+        M, K = A.shape
+        K2, N = B.shape
+        assert K == K2
+        Cm = np.zeros((M, N), order="F")
+        ms = C.c_double()
+        self._check(self.lib.reach_dgemm(self._h, M, N, K, dptr(A), M, dptr(B), K, dptr(Cm), M, int(reps), C.byref(ms)))
+        return Cm, ms.value
+
+    # ---- discretisation --------------------------------------------------------------------------------
+    def expm(self, A, delta: float) -> np.ndarray:
+        A = fmat(A)
+        n = A.shape[0]
+        Phi = np.zeros((n, n), order="F")
+        self._check(self.lib.reach_expm(self._h, n, dptr(A), n, float(delta), dptr(Phi), n))
+        return Phi
+
+    def phi12(self, A, delta: float):
+        A = fmat(A)
+        n = A.shape[0]
+        P1 = np.zeros((n, n), order="F")
+        P2 = np.zeros((n, n), order="F")
+        self._check(self.lib.reach_phi12(self._h, n, dptr(A), n, float(delta), dptr(P1), n, dptr(P2), n))
+        return P1, P2
+
+    def discretize_box(self, A, delta, c, r, B=None, cU=None, rU=None, algorithm="forward", want_phi2abs=False):
+        """Returns dict(Phi, c0, r0, rE, rpsi, MU[, Phi2abs])."""
+        A = fmat(A)
+        n = A.shape[0]
+        alg = {"forward": 0, "backward": 1}.get(algorithm)
+        if alg is None:
+            raise ValueError(f"the algorithm {algorithm} is unknown")
+        c, r = fvec(c), fvec(r)
+        m = 0
+        Bm = None
+        if cU is not None:
+            cU, rU = fvec(cU), fvec(rU)
+            m = len(cU)
+            Bm = fmat(np.eye(n) if B is None else B)
+            assert Bm.shape == (n, m)
+        Phi = np.zeros((n, n), order="F")
+        P2 = np.zeros((n, n), order="F") if want_phi2abs else None
+        c0, r0, rE = np.zeros(n), np.zeros(n), np.zeros(n)
+        rpsi = np.zeros(n) if m else None
+        MU = np.zeros((n, m), order="F") if m else None
+        self._check(self.lib.reach_discretize_box(
+            self._h, n, dptr(A), n, float(delta), alg, dptr(c), dptr(r), m, dptr(Bm), n, dptr(cU), dptr(rU),
+            dptr(Phi), n, dptr(P2), n, dptr(c0), dptr(r0), dptr(rE), dptr(rpsi), dptr(MU)))
+        out = dict(Phi=Phi, c0=c0, r0=r0, rE=rE, rpsi=rpsi, MU=MU, cU=cU, rU=rU)
+        if want_phi2abs:
+            out["Phi2abs"] = P2
+        return out
+
+    # ---- BFFPSV18 --------------------------------------------------------------------------------------
+    @staticmethod
+    def _box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N):
+        Phi = fmat(Phi)
+        n = Phi.shape[0]
+        c0, r0 = fvec(c0), fvec(r0)
+        m = 0
+        if MU is not None:
+            MU = fmat(MU).reshape(n, -1, order="F")
+            m = MU.shape[1]
+            cU, rU, rpsi = fvec(cU), fvec(rU), fvec(rpsi)
+        else:
+            cU = rU = rpsi = None
+        rows = np.arange(n, dtype=np.int32) if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        keep = (Phi, c0, r0, MU, cU, rU, rpsi, rows)
+        args = (n, dptr(Phi), n, dptr(c0), dptr(r0), m, dptr(MU), n, dptr(cU), dptr(rU), dptr(rpsi), len(rows),
+                iptr(rows), int(N))
+        return keep, args, len(rows)
+
+    def bffpsv18_boxes(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None):
+        """One-shot host-buffer call.  Returns (centers, radii) as (nrows, N) Fortran arrays."""
+        keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
+        centers = np.zeros((nrows, N), order="F")
+        radii = np.zeros((nrows, N), order="F")
+        done = C.c_int64()
+        self._check(self.lib.reach_bffpsv18_boxes(self._h, *args, dptr(centers), dptr(radii), C.byref(done)))
+        return centers, radii
+
+    def boxplan(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None) -> "BoxPlan":
+        return BoxPlan(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
+
+    def bffpsv18_check(self, Phi, c0, r0, N, ell, bound, MU=None, cU=None, rU=None, rpsi=None, rows=None, eager=True):
+        keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
+        ell = fvec(ell)
+        assert len(ell) == nrows
+        v = C.c_int64()
+        self._check(self.lib.reach_bffpsv18_check(self._h, *args, dptr(ell), float(bound), int(bool(eager)), C.byref(v)))
+        return int(v.value)
+
+    def bffpsv18_output_map(self, Phi, c0, r0, N, Mout, MU=None, cU=None, rU=None, rpsi=None, rows=None):
+        keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
+        Mout = fmat(Mout)
+        q = Mout.shape[0]
+        assert Mout.shape[1] == nrows
+        centers = np.zeros((q, N), order="F")
+        radii = np.zeros((q, N), order="F")
+        self._check(self.lib.reach_bffpsv18_output_map(self._h, *args, q, dptr(Mout), q, dptr(centers), dptr(radii)))
+        return centers, radii
+
+    # ---- GLGM06 ----------------------------------------------------------------------------------------
+    def glgm06(self, Phi, c0, G0, N, max_order=10, cV=None, GV=None, flags=0) -> "Flowpipe":
+        return Flowpipe(self, Phi, c0, G0, N, max_order, cV, GV, flags)
+
+    def reduce_order(self, c, G, r, flags=0):
+        G = fmat(G)
+        n, p = G.shape
+        c = fvec(c)
+        pmax = max(p, int(r) * n)
+        Gout = np.zeros((n, pmax), order="F")
+        pout = C.c_int64()
+        ind = np.zeros(p, dtype=np.int32)
+        self._check(self.lib.reach_reduce_order(self._h, n, p, dptr(c), dptr(G), n, int(r), int(flags), dptr(Gout), n,
+                                                C.byref(pout), iptr(ind)))
+        return np.asfortranarray(Gout[:, :pout.value]), ind
+
+    def ensemble(self, Phi, c0s, G0s, N) -> "Ensemble":
+        return Ensemble(self, Phi, c0s, G0s, N)
+
+
+class BoxPlan:
+    """`reach_boxplan`: BFFPSV18 problem resident on the device (upload once, run, fetch)."""
+
+    def __init__(self, ctx: Context, Phi, c0, r0, N, MU, cU, rU, rpsi, rows):
+        self.ctx = ctx
+        keep, args, self.nrows = ctx._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
+        self.N = int(N)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.reach_boxplan_create(ctx._h, *args, C.byref(self._h)))
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.reach_boxplan_run(self._h))
+
+    def fetch(self):
+        centers = np.zeros((self.nrows, self.N), order="F")
+        radii = np.zeros((self.nrows, self.N), order="F")
+        self.ctx._check(self.ctx.lib.reach_boxplan_fetch(self._h, dptr(centers), dptr(radii)))
+        return centers, radii
+
+    def timing(self):
+        run, gemm, fl = C.c_double(), C.c_double(), C.c_double()
+        nl = C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_boxplan_timing(self._h, C.byref(run), C.byref(gemm), C.byref(nl), C.byref(fl)))
+        return dict(run_ms=run.value, gemm_ms=gemm.value, gemm_launches=nl.value, gemm_flops=fl.value)
+
+    def close(self):
+        if self._h.value:
+            self.ctx.lib.reach_boxplan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Flowpipe:
+    """`reach_flowpipe`: GLGM06 zonotope flowpipe resident on the device."""
+
+    def __init__(self, ctx: Context, Phi, c0, G0, N, max_order, cV, GV, flags):
+        self.ctx = ctx
+        Phi = fmat(Phi)
+        n = Phi.shape[0]
+        c0 = fvec(c0)
+        G0 = fmat(G0).reshape(n, -1, order="F")
+        p0 = G0.shape[1]
+        pV = 0
+        if cV is not None:
+            cV = fvec(cV)
+            GV = fmat(GV).reshape(n, -1, order="F")
+            pV = GV.shape[1]
+        self.n, self.N = n, int(N)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.reach_glgm06_create(ctx._h, n, dptr(Phi), n, p0, dptr(c0), dptr(G0), n, pV, dptr(cV),
+                                               dptr(GV) if pV else None, n, int(N), int(max_order), int(flags),
+                                               C.byref(self._h)))
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.reach_glgm06_run(self._h))
+        return self
+
+    def ngens(self) -> np.ndarray:
+        p = np.zeros(self.N, dtype=np.int32)
+        self.ctx._check(self.ctx.lib.reach_flowpipe_ngens(self._h, iptr(p)))
+        return p
+
+    def step(self, k: int, p: Optional[int] = None):
+        """Reach set k (1-based) -> (c, G)."""
+        if p is None:
+            p = int(self.ngens()[k - 1])
+        c = np.zeros(self.n)
+        G = np.zeros((self.n, max(p, 1)), order="F")
+        self.ctx._check(self.ctx.lib.reach_flowpipe_step(self._h, int(k), dptr(c), dptr(G), self.n))
+        return c, np.asfortranarray(G[:, :p])
+
+    def selection(self, k: int, which: int = 0, pmax: int = 1 << 16):
+        pin, m = C.c_int32(), C.c_int32()
+        self.ctx._check(self.ctx.lib.reach_flowpipe_selection(self._h, int(k), int(which), C.byref(pin), C.byref(m),
+                                                              None, None))
+        ind = np.zeros(max(pin.value, 1), dtype=np.int32)
+        h = np.zeros(max(pin.value, 1))
+        if pin.value:
+            self.ctx._check(self.ctx.lib.reach_flowpipe_selection(self._h, int(k), int(which), C.byref(pin),
+                                                                  C.byref(m), iptr(ind), dptr(h)))
+        return dict(p_in=pin.value, m=m.value, ind=ind[:pin.value], h=h[:pin.value])
+
+    def timing(self):
+        vals = [C.c_double() for _ in range(5)]
+        nl = C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_flowpipe_timing(self._h, C.byref(vals[0]), C.byref(vals[1]), C.byref(nl),
+                                                           C.byref(vals[2]), C.byref(vals[3]), C.byref(vals[4])))
+        return dict(run_ms=vals[0].value, gemm_ms=vals[1].value, gemm_launches=nl.value, gemm_flops=vals[2].value,
+                    reduce_ms=vals[3].value, reduce_bytes=vals[4].value)
+
+    def close(self):
+        if self._h.value:
+            self.ctx.lib.reach_flowpipe_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ensemble:
+    """`reach_ensemble`: batched homogeneous GLGM06 flowpipes (config C5)."""
+
+    def __init__(self, ctx: Context, Phi, c0s, G0s, N):
+        self.ctx = ctx
+        Phi = fmat(Phi)
+        n = Phi.shape[0]
+        c0s = fmat(c0s)                       # n x batch
+        batch = c0s.shape[1]
+        G0s = np.asfortranarray(np.asarray(G0s, dtype=np.float64))   # n x p x batch
+        assert G0s.shape[0] == n and G0s.shape[2] == batch
+        p = G0s.shape[1]
+        self.n, self.p, self.batch, self.N = n, p, batch, int(N)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.reach_ensemble_create(ctx._h, n, dptr(Phi), n, batch, p, dptr(c0s), dptr(G0s), int(N),
+                                                 C.byref(self._h)))
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.reach_ensemble_run(self._h))
+        return self
+
+    def step(self, b: int, k: int):
+        c = np.zeros(self.n)
+        G = np.zeros((self.n, self.p), order="F")
+        self.ctx._check(self.ctx.lib.reach_ensemble_step(self._h, int(b), int(k), dptr(c), dptr(G)))
+        return c, G
+
+    def boxes(self, k: int):
+        lo = np.zeros((self.n, self.batch), order="F")
+        hi = np.zeros((self.n, self.batch), order="F")
+        self.ctx._check(self.ctx.lib.reach_ensemble_boxes(self._h, int(k), dptr(lo), dptr(hi)))
+        return lo, hi
+
+    def timing(self):
+        a, b = C.c_double(), C.c_double()
+        self.ctx._check(self.ctx.lib.reach_ensemble_timing(self._h, C.byref(a), C.byref(b)))
+        return dict(run_ms=a.value, bytes_per_step=b.value)
+
+    def close(self):
+        if self._h.value:
+            self.ctx.lib.reach_ensemble_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,109 @@
+// C ABI: BFFPSV18 entry points (include/reach.h).
+#include "common.cuh"
+#include "../../include/reach.h"
+
+namespace reach {
+struct BoxPlan;
+BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0, const double* r0,
+                        int64_t m, const double* MU, int64_t ldmu, const double* cU, const double* rU,
+                        const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N);
+void boxplan_destroy(BoxPlan* P);
+void boxplan_run(BoxPlan* P);
+void boxplan_fetch(BoxPlan* P, double* centers, double* radii);
+void boxplan_results(BoxPlan* P, double** c, double** r);
+void boxplan_timing(BoxPlan* P, double* run_ms, double* gemm_ms, int64_t* launches, double* flops);
+Ctx* boxplan_ctx(BoxPlan* P);
+Ctx* ctx_of(reach_ctx* h);
+}  // namespace reach
+
+using namespace reach;
+
+struct reach_boxplan {
+    BoxPlan* p;
+    Ctx* ctx;
+};
+
+#define GUARD_BEGIN(ctx) \
+    if (!(ctx)) return REACH_EINVAL; \
+    try { \
+        REACH_CUDA(cudaSetDevice((ctx)->device));
+#define GUARD_END(ctx) \
+    } catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; } \
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+
+extern "C" {
+
+int32_t reach_boxplan_create(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             reach_boxplan** out) {
+    if (!h || !out) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    *out = nullptr;
+    GUARD_BEGIN(ctx)
+    BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+    *out = new reach_boxplan{p, ctx};
+    return REACH_OK;
+    GUARD_END(ctx)
+}
+
+int32_t reach_boxplan_run(reach_boxplan* plan) {
+    if (!plan) return REACH_EINVAL;
+    GUARD_BEGIN(plan->ctx)
+    boxplan_run(plan->p);
+    return REACH_OK;
+    GUARD_END(plan->ctx)
+}
+
+int32_t reach_boxplan_fetch(reach_boxplan* plan, double* centers, double* radii) {
+    if (!plan) return REACH_EINVAL;
+    GUARD_BEGIN(plan->ctx)
+    boxplan_fetch(plan->p, centers, radii);
+    return REACH_OK;
+    GUARD_END(plan->ctx)
+}
+
+int32_t reach_boxplan_device_results(reach_boxplan* plan, double** centers_dev, double** radii_dev) {
+    if (!plan) return REACH_EINVAL;
+    boxplan_results(plan->p, centers_dev, radii_dev);
+    return REACH_OK;
+}
+
+int32_t reach_boxplan_timing(reach_boxplan* plan, double* run_ms, double* gemm_ms, int64_t* gemm_launches,
+                             double* gemm_flops) {
+    if (!plan) return REACH_EINVAL;
+    boxplan_timing(plan->p, run_ms, gemm_ms, gemm_launches, gemm_flops);
+    return REACH_OK;
+}
+
+void reach_boxplan_destroy(reach_boxplan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    cudaStreamSynchronize(plan->ctx->stream);
+    boxplan_destroy(plan->p);
+    delete plan;
+}
+
+int32_t reach_bffpsv18_boxes(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             double* centers, double* radii, int64_t* steps_done) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    GUARD_BEGIN(ctx)
+    REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes: output buffers required");
+    BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+    try {
+        boxplan_run(p);
+        boxplan_fetch(p, centers, radii);
+    } catch (...) {
+        boxplan_destroy(p);
+        throw;
+    }
+    boxplan_destroy(p);
+    if (steps_done) *steps_done = N;
+    return REACH_OK;
+    GUARD_END(ctx)
+}
+
+}  // extern "C"

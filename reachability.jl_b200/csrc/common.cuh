@@ -73,6 +73,10 @@ struct GemmEpilogue {
     // C = alpha * A*B + beta_I * I (diagonal add on global row==col), used by the Taylor/Horner expm.
     double alpha = 1.0;
     double diag = 0.0;
+    // columns >= nsplit of the product go to C2 (ldc2) instead of C: side products such as P·[δB | c0]
+    double* C2 = nullptr;
+    int64_t ldc2 = 0;
+    int64_t nsplit = -1;
 };
 void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt,
              int64_t ldbt, double* C, int64_t ldc, const GemmEpilogue& ep = GemmEpilogue());

@@ -72,6 +72,9 @@ struct GemmParams {
     int M, N, ksteps;
     int tiles_m, tiles_n;
     double alpha, diag;
+    double* C2;      // columns >= nsplit are stored to C2[(col - nsplit) * ldc2 + row] (fused side products)
+    int64_t ldc2;
+    int nsplit;
 };
 
 // WNT = n8 tiles per warp along N; CTA tile is 128 x (32*WNT).
@@ -162,7 +165,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 for (int e = 0; e < 2; ++e) {
                     const int col = col0 + j * 8 + e;
                     if (col < p.N) {
-                        double* cptr = p.C + (int64_t)col * p.ldc;
+                        double* cptr = col < p.nsplit ? p.C + (int64_t)col * p.ldc
+                                                      : p.C2 + (int64_t)(col - p.nsplit) * p.ldc2;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = row0 + i * 8;
@@ -223,6 +227,8 @@ void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t
     p.lda = lda; p.ldbt = ldbt; p.ldc = ldc;
     p.M = (int)M; p.N = (int)N; p.ksteps = (int)ceil_div(K, BK);
     p.alpha = ep.alpha; p.diag = ep.diag;
+    p.C2 = ep.C2; p.ldc2 = ep.ldc2;
+    p.nsplit = (ep.C2 != nullptr && ep.nsplit >= 0) ? (int)ep.nsplit : (int)N;
     p.tiles_m = (int)ceil_div(M, BM);
     // widest column tile that wastes the least padding
     int best = 4;
