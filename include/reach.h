@@ -47,6 +47,9 @@ typedef struct reach_ensemble reach_ensemble; /* batched homogeneous GLGM06 flow
 REACH_API int32_t reach_version(void);
 /* Module `__init__` of the Julia shim. Fails (REACH_ECUDA) when no sm_100 device is visible. */
 REACH_API int32_t reach_ctx_create(int32_t device, reach_ctx** out);
+/* Same, but all work is issued on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream
+ * or CUDA.jl's task stream); the stream is borrowed, not owned.  stream == NULL behaves like reach_ctx_create. */
+REACH_API int32_t reach_ctx_create_on_stream(int32_t device, void* stream, reach_ctx** out);
 REACH_API void reach_ctx_destroy(reach_ctx* ctx);
 /* Message of the last failure on this context (ctx == NULL: last failure of reach_ctx_create). */
 REACH_API const char* reach_last_error(const reach_ctx* ctx);

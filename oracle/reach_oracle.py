@@ -428,12 +428,38 @@ def bffpsv18_reach(P: DiscreteBoxProblem, N: int, rows: Optional[Sequence[int]] 
     return C, R
 
 
-def bffpsv18_output_map(P: DiscreteBoxProblem, N: int, M: np.ndarray, rows: Sequence[int]):
+def _block_slices(nrows: int, block_sizes: Optional[Sequence[int]]):
+    """Slices of ``rows`` belonging to each block of ``:blocks`` (consecutive groups; None: one single block)."""
+    if block_sizes is None:
+        return [slice(0, nrows)]
+    assert sum(block_sizes) == nrows
+    out, o = [], 0
+    for b in block_sizes:
+        out.append(slice(o, o + b))
+        o += b
+    return out
+
+
+def _blockwise_abs_product(M: np.ndarray, Pk: np.ndarray, slices) -> np.ndarray:
+    """Σ_i |M[:, b_i] · P[b_i, :]|: the support function of a ``CartesianProductArray`` of lazy
+    ``MinkowskiSumArray`` blocks is separable per block, ρ(d, ×_i X_i) = Σ_i ρ(d_i, X_i), so the absolute value
+    is taken per block of rows (NOT of the full product M·P)."""
+    acc = np.zeros((M.shape[0], Pk.shape[1]))
+    for sl in slices:
+        acc += np.abs(M[:, sl] @ Pk[sl, :])
+    return acc
+
+
+def bffpsv18_output_map(P: DiscreteBoxProblem, N: int, M: np.ndarray, rows: Sequence[int],
+                        block_sizes: Optional[Sequence[int]] = None):
     """``output_function`` branch of ``reach_blocks!`` (reach_blocks.jl:152-155,191-199; reach.jl:73-82):
-    blocks stay lazy and the stored set is ``box_approximation(M * CPA(Xhatk))``: centre
-    ``M(P c0 + cW)``, radius ``|M P| r0 + |M| rW``.  ``M`` is q x len(rows)."""
+    blocks stay lazy (``MinkowskiSumArray``) and the stored set is ``box_approximation(M * CPA(Xhatk))``:
+    centre ``M(P c0 + cW)``, radius ``Σ_i |M[:,b_i] P[b_i,:]| r0 + |M| rW`` (per-block absolute value, see
+    `_blockwise_abs_product`; step 1 uses the boxed ``Xhat0``: ``|M| r0[rows]``, :152-155).
+    ``M`` is q x len(rows); ``block_sizes`` groups ``rows`` into the blocks of ``:blocks``."""
     Phi = P.Phi
     rows = np.asarray(rows, dtype=np.int64)
+    slices = _block_slices(len(rows), block_sizes)
     q = M.shape[0]
     C = np.zeros((N, q))
     R = np.zeros((N, q))
@@ -447,9 +473,8 @@ def bffpsv18_output_map(P: DiscreteBoxProblem, N: int, M: np.ndarray, rows: Sequ
         rW = (np.abs(P.MU) @ P.rU + P.rpsi)[rows]
     Pk = Phi[rows, :].copy()
     for k in range(2, N + 1):
-        MP = M @ Pk
-        c = MP @ P.c0
-        r = np.abs(MP) @ P.r0
+        c = (M @ Pk) @ P.c0
+        r = _blockwise_abs_product(M, Pk, slices) @ P.r0
         if inhomog:
             c = c + M @ cW
             r = r + np.abs(M) @ rW
@@ -465,14 +490,17 @@ def bffpsv18_output_map(P: DiscreteBoxProblem, N: int, M: np.ndarray, rows: Sequ
 
 
 def bffpsv18_check(P: DiscreteBoxProblem, N: int, ell: np.ndarray, bound: float, rows: Sequence[int],
-                   eager: bool = True) -> int:
+                   eager: bool = True, block_sizes: Optional[Sequence[int]] = None) -> int:
     """Dense ``check_blocks`` (BFFPSV18/check_blocks.jl:105-183) for the half-space property
     ``is_contained_in(LinearConstraint(ell, bound))`` after `inout_map_property` (partitions.jl:33-46):
-    states stay lazy (no per-block boxing), so ``ρ(ℓ, X_k) = (ℓᵀP)c0 + |ℓᵀP| r0 + ℓ·cW + |ℓ|·rW``
-    (SURVEY.md section 8f-1).  ``ell`` is given on the coordinates ``rows`` (0-based).  Returns the first
-    violating step index (1-based) or 0 if the property holds for all N steps."""
+    states stay lazy (no per-block boxing) and ρ of the ``CartesianProductArray`` is separable per block, so
+    ``ρ(ℓ, X_k) = (ℓᵀP)c0 + Σ_i |ℓ_iᵀP[b_i,:]| r0 + ℓ·cW + |ℓ|·rW`` (SURVEY.md section 8f-1 misses the
+    per-block absolute value; `oracle/lazysets_mini.check_blocks_dense` is the literal version).  ``ell`` is
+    given on the coordinates ``rows`` (0-based); ``block_sizes`` groups ``rows`` into the blocks of ``:blocks``.
+    Returns the first violating step index (1-based) or 0 if the property holds for all N steps."""
     rows = np.asarray(rows, dtype=np.int64)
     ell = np.asarray(ell, dtype=np.float64)
+    slices = _block_slices(len(rows), block_sizes)
     violation = 0
     if ell @ P.c0[rows] + np.abs(ell) @ P.r0[rows] > bound:   # check_blocks.jl:122-129, k = 1
         if eager:
@@ -486,8 +514,7 @@ def bffpsv18_check(P: DiscreteBoxProblem, N: int, ell: np.ndarray, bound: float,
         rW = (np.abs(P.MU) @ P.rU + P.rpsi)[rows]
     Pk = P.Phi[rows, :].copy()
     for k in range(2, N + 1):
-        lP = ell @ Pk
-        rho = lP @ P.c0 + np.abs(lP) @ P.r0
+        rho = (ell @ Pk) @ P.c0 + _blockwise_abs_product(ell[None, :], Pk, slices)[0] @ P.r0
         if inhomog:
             rho += ell @ cW + np.abs(ell) @ rW
         if rho > bound:

@@ -30,6 +30,7 @@ _BOX_ARGS = [vp, i64, c_double_p, i64, c_double_p, c_double_p, i64, c_double_p, 
 _SIGNATURES = {
     "reach_version": [],
     "reach_ctx_create": [i32, C.POINTER(vp)],
+    "reach_ctx_create_on_stream": [i32, vp, C.POINTER(vp)],
     "reach_ctx_destroy": [vp],
     "reach_last_error": [vp],
     "reach_sync": [vp],

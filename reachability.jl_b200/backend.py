@@ -14,10 +14,11 @@ from ._lib import ReachError, dptr, fmat, fvec, iptr
 class Context:
     """`reach_ctx`: one CUDA device + stream.  Raises ReachError when no B200 is visible."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        """`stream`: a cudaStream_t handle to borrow (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         self.lib = _lib.load()
         self._h = C.c_void_p()
-        rc = self.lib.reach_ctx_create(int(device), C.byref(self._h))
+        rc = self.lib.reach_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(self._h))
         if rc != 0:
             raise ReachError(rc, (self.lib.reach_last_error(None) or b"").decode())
         self.device = device
@@ -134,6 +135,16 @@ class Context:
         self._check(self.lib.reach_bffpsv18_boxes(self._h, *args, dptr(centers), dptr(radii), C.byref(done)))
         return centers, radii
 
+    def bffpsv18_boxes_into(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows, centers, radii):
+        """One-shot call writing into caller-owned (e.g. pinned) (nrows, N) Fortran arrays; no host-side copies when
+        the inputs are already column-major float64."""
+        keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
+        assert centers.shape == (nrows, N) and radii.shape == (nrows, N)
+        assert centers.flags.f_contiguous and radii.flags.f_contiguous
+        done = C.c_int64()
+        self._check(self.lib.reach_bffpsv18_boxes(self._h, *args, dptr(centers), dptr(radii), C.byref(done)))
+        return int(done.value)
+
     def boxplan(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None) -> "BoxPlan":
         return BoxPlan(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
 
@@ -193,6 +204,12 @@ class BoxPlan:
         radii = np.zeros((self.nrows, self.N), order="F")
         self.ctx._check(self.ctx.lib.reach_boxplan_fetch(self._h, dptr(centers), dptr(radii)))
         return centers, radii
+
+    def device_results(self):
+        """(centers_ptr, radii_ptr): device addresses of the nrows x N column-major results (zero-copy consumers)."""
+        cp, rp = _lib.c_double_p(), _lib.c_double_p()
+        self.ctx._check(self.ctx.lib.reach_boxplan_device_results(self._h, C.byref(cp), C.byref(rp)))
+        return C.cast(cp, C.c_void_p).value, C.cast(rp, C.c_void_p).value
 
     def timing(self):
         run, gemm, fl = C.c_double(), C.c_double(), C.c_double()

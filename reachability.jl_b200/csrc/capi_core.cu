@@ -29,7 +29,9 @@ extern "C" {
 
 int32_t reach_version(void) { return 100; }
 
-int32_t reach_ctx_create(int32_t device, reach_ctx** out) {
+int32_t reach_ctx_create(int32_t device, reach_ctx** out) { return reach_ctx_create_on_stream(device, nullptr, out); }
+
+int32_t reach_ctx_create_on_stream(int32_t device, void* stream, reach_ctx** out) {
     if (!out) return REACH_EINVAL;
     *out = nullptr;
     try {
@@ -47,7 +49,12 @@ int32_t reach_ctx_create(int32_t device, reach_ctx** out) {
         reach_ctx* h = new reach_ctx();
         h->c.device = device;
         h->c.sm_count = prop.multiProcessorCount;
-        REACH_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+        if (stream) {
+            h->c.stream = (cudaStream_t)stream;
+            h->c.owns_stream = false;
+        } else {
+            REACH_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+        }
         REACH_CUDA(cudaEventCreate(&h->c.ev0));
         REACH_CUDA(cudaEventCreate(&h->c.ev1));
         *out = h;
@@ -65,7 +72,7 @@ void reach_ctx_destroy(reach_ctx* ctx) {
     for (void* p : ctx->c.scratch) cudaFree(p);
     if (ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
     if (ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
-    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    if (ctx->c.stream && ctx->c.owns_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }
 

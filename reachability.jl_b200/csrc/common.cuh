@@ -52,6 +52,7 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     std::string last_error;
     // launch accounting (bench.py "gpu_launches") and per-phase timings
     uint64_t launches = 0;

@@ -1,0 +1,167 @@
+"""GPU parity: BFFPSV18 device path (through the C ABI) vs the CPU oracle.
+
+Tolerance (north_star): 1e-10 relative + 1e-12 absolute on every box centre and radius.
+Mirrors the shapes of /root/reference/test/Reachability/solve_continuous.jl (4x4 LCS, affine CLCCS, `:vars` subsets,
+1-D Interval and 2-D Hyperrectangle partitions) plus BASELINE.json's configs C1 and C3.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import reach_oracle as orc
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _run(ctx, D, N, rows=None):
+    C, R = ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+    return C.T, R.T       # (N, nrows) like the oracle
+
+
+def _check(ctx, D, N, rows=None):
+    Co, Ro = orc.bffpsv18_reach(D, N, rows)
+    Cg, Rg = _run(ctx, D, N, rows)
+    assert_close(Cg, Co, "centres")
+    assert_close(Rg, Ro, "radii")
+    return Cg, Rg
+
+
+@pytest.mark.parametrize("name", ["lcs4", "clccs4", "doc5"])
+@pytest.mark.parametrize("alg", ["forward", "backward"])
+def test_golden_fixtures(ctx, name, alg):
+    z = np.load(GOLDEN / f"{name}.npz")
+    N = z[f"{alg}_centers"].shape[0]
+    inh = "B" in z
+    C, R = ctx.bffpsv18_boxes(z[f"{alg}_Phi"], z[f"{alg}_c0"], z[f"{alg}_r0"], N,
+                              z[f"{alg}_MU"] if inh else None, z["cU"] if inh else None, z["rU"] if inh else None,
+                              z[f"{alg}_rpsi"] if inh else None)
+    assert_close(C.T, z[f"{alg}_centers"], "centres")
+    assert_close(R.T, z[f"{alg}_radii"], "radii")
+
+
+def _random_problem(seed, n, m):
+    g = np.random.default_rng(seed)
+    A = g.standard_normal((n, n)) / np.sqrt(n) - 1.2 * np.eye(n)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m)) if m else None
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3) if m else None
+    return orc.discretize_box(A, X0, 0.01, B, U)
+
+
+@pytest.mark.parametrize("n,m,N", [(1, 0, 5), (1, 1, 40), (2, 1, 3), (7, 3, 33), (8, 0, 64), (9, 2, 65), (33, 5, 129),
+                                   (130, 4, 257), (257, 1, 100), (300, 17, 40)])
+def test_random_systems_ragged_sizes(ctx, n, m, N):
+    _check(ctx, _random_problem(100 + n, n, m), N)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3])
+def test_tiny_step_counts(ctx, N):
+    """N == 1 returns only X_1 = Xhat0[blocks] (reach.jl:87-90, reach_blocks.jl:152-158)."""
+    D = _random_problem(5, 12, 2)
+    C, R = _check(ctx, D, N)
+    assert np.array_equal(C[0], D.c0) and np.array_equal(R[0], D.r0)
+
+
+def test_rows_subset_and_order(ctx):
+    """`:vars` -> blocks -> dimensions (compute_dimensions.jl:1-15): any subset, any order, no duplicates needed."""
+    D = _random_problem(6, 40, 3)
+    _check(ctx, D, 50, rows=[3])
+    _check(ctx, D, 50, rows=[0, 1, 38, 39])
+    _check(ctx, D, 50, rows=[39, 5, 17, 4, 20, 21, 22, 23, 24])
+    part = [[2 * i, 2 * i + 1] for i in range(20)]
+    blocks = orc.compute_blocks([1, 3, 40], [[a + 1 for a in b] for b in part])
+    rows = [d - 1 for d in orc.compute_dimensions([[a + 1 for a in b] for b in part], blocks)]
+    assert rows == [0, 1, 2, 3, 38, 39]
+    _check(ctx, D, 50, rows=rows)
+
+
+def test_zero_radius_and_singleton_inputs(ctx):
+    """Flat initial sets (r = 0) and a Singleton input (rU = 0): affine term x' = Ax + b (solve_continuous.jl:216-224)."""
+    g = np.random.default_rng(3)
+    n = 10
+    A = g.standard_normal((n, n)) - 2 * np.eye(n)
+    D = orc.discretize_box(A, orc.Box(g.standard_normal(n), np.zeros(n)), 0.02, np.eye(n),
+                           orc.Box(g.standard_normal(n), np.zeros(n)))
+    _check(ctx, D, 30)
+
+
+def test_invalid_arguments_raise(ctx):
+    import reachability_jl_b200 as rb
+    D = _random_problem(5, 6, 0)
+    with pytest.raises(rb.ReachError) as ei:
+        ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, 5, rows=[0, 6])
+    assert ei.value.code == 1 and "row index" in str(ei.value)
+    with pytest.raises(rb.ReachError):
+        ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, 0)
+
+
+def _workload_problem(w):
+    X0 = orc.Box(w.c, w.r)
+    U = orc.Box(w.cU, w.rU) if w.B is not None else None
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.phi12_series(np.abs(w.A), w.delta)[2]      # = Φ₂(|A|, δ) (tests/test_oracle_pins.py); avoids the 3n x 3n exp
+    return orc.discretize_box(w.A, X0, w.delta, w.B, U, Phi=Phi, Phi2abs=P2)
+
+
+def test_config_c1_building_full(ctx):
+    """BASELINE.json configs[0]: n = 48, 1-D Interval blocks, δ = 0.003, T = 20 -> N = 6667, all variables."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.building()
+    D = _workload_problem(w)
+    N = orc.n_steps_bffpsv18(w.T, w.delta)
+    assert N == 6667
+    _check(ctx, D, N)
+
+
+def test_config_c3_fom_prefix_and_rows(ctx):
+    """BASELINE.json configs[2]: n = 1006, 503 2-D Hyperrectangle blocks; oracle-sized prefix N = 150."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.fom()
+    D = _workload_problem(w)
+    _check(ctx, D, 150)
+    _check(ctx, D, 40, rows=list(range(100, 226)))
+
+
+def test_config_c3_full_size_properties(ctx):
+    """Full N = 6667 at n = 1006: size-independent properties instead of the (hours-long) CPU loop.
+    (a) prefix: the first 150 steps equal the oracle's; (b) closed form at sampled steps k:
+        homogeneous run  c_k = Φ^{k-1} c0,  r_k = |Φ^{k-1}| r0  with Φ^{k-1} by repeated squaring on the CPU;
+    (c) linearity: doubling (c0, r0, cU, rU, rψ) doubles every bound; (d) radii are non-negative, and the
+        inhomogeneous radii dominate the homogeneous ones."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.fom()
+    D = _workload_problem(w)
+    N = orc.n_steps_bffpsv18(w.T, w.delta)
+    Cg, Rg = _run(ctx, D, N)
+    Co, Ro = orc.bffpsv18_reach(D, 150)
+    assert_close(Cg[:150], Co, "prefix centres")
+    assert_close(Rg[:150], Ro, "prefix radii")
+    Dh = orc.DiscreteBoxProblem(D.Phi, D.c0, D.r0, None, None, None, None, D.rE, D.Phi2abs)
+    Ch, Rh = _run(ctx, Dh, N)
+    for k in (2, 500, 3333, 6667):
+        Pk = np.linalg.matrix_power(D.Phi, k - 1)
+        assert_close(Ch[k - 1], Pk @ D.c0, f"closed-form centre {k}")
+        assert_close(Rh[k - 1], np.abs(Pk) @ D.r0, f"closed-form radius {k}")
+    assert np.all(Rg >= 0) and np.all(Rg >= Rh * (1 - 1e-12))
+    D2 = orc.DiscreteBoxProblem(D.Phi, 2 * D.c0, 2 * D.r0, D.MU, 2 * D.cU, 2 * D.rU, 2 * D.rpsi, D.rE, D.Phi2abs)
+    C2, R2 = _run(ctx, D2, N)
+    assert_close(C2, 2 * Cg, "linearity centres")
+    assert_close(R2, 2 * Rg, "linearity radii")
+
+
+def test_boxplan_is_repeatable_and_counts_launches(ctx):
+    D = _random_problem(9, 64, 2)
+    before = ctx.launch_count()
+    plan = ctx.boxplan(D.Phi, D.c0, D.r0, 200, D.MU, D.cU, D.rU, D.rpsi)
+    plan.run()
+    a = plan.fetch()
+    plan.run()
+    b = plan.fetch()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])      # deterministic summation order
+    assert ctx.launch_count() > before
+    t = plan.timing()
+    assert t["run_ms"] > 0 and t["gemm_launches"] > 0
+    plan.close()
