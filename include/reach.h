@@ -119,7 +119,7 @@ REACH_API int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t n, const dou
 /* ---- GLGM06: reach_homog! / reach_inhomog! (GLGM06/reach.jl:5-62) -------------------------------------- */
 /* flags */
 #define REACH_GLGM06_KEEP_ZERO_GENERATORS 1 /* Zonotope(c, G; remove_zero_generators=false) semantics */
-#define REACH_GLGM06_STEPWISE 2             /* force the step-by-step kernels (no batched pipeline) */
+#define REACH_GLGM06_RECORD_SELECTIONS 2    /* keep sortperm + scores of every reduce_order call (reach_flowpipe_selection) */
 /* Upload Ω0red = (c0, G0 n x p0) (already reduce_order'ed, GLGM06/post.jl:20 -- or call reach_reduce_order) and
  * the discretised input V = (cV, GV n x pV); pV == 0 and cV == NULL selects reach_homog!. */
 REACH_API int32_t reach_glgm06_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
@@ -130,9 +130,16 @@ REACH_API int32_t reach_glgm06_run(reach_flowpipe* fp); /* whole recurrence on t
 REACH_API int32_t reach_flowpipe_ngens(reach_flowpipe* fp, int32_t* p /* N */);
 /* Reach set k (1-based): centre (n) and generators (n x p_k, leading dimension ldg >= n). */
 REACH_API int32_t reach_flowpipe_step(reach_flowpipe* fp, int64_t k, double* c, double* G, int64_t ldg);
+/* All reach sets at once (the `R` vector reach_inhomog! fills, GLGM06/reach.jl:30-36): centers n x N (ld n);
+ * G holds N slabs of n x pmax (ld n, slab stride n*pmax doubles), slab k-1 = generators of R_k in its first p_k columns.
+ * Either output may be NULL. */
+REACH_API int32_t reach_flowpipe_fetch(reach_flowpipe* fp, double* centers, double* G, int64_t pmax);
+/* Box hull of reach set k: lo/hi (n). */
+REACH_API int32_t reach_flowpipe_box(reach_flowpipe* fp, int64_t k, double* lo, double* hi);
 /* Order-reduction record of step k >= 2 (which = 0: reduce_order of R_k, GLGM06/reach.jl:49; which = 1: of W, :55):
  * p_in columns went in, m were boxed; ind[0..p_in) = sortperm(h) 0-based; h[0..p_in) the scores. Outputs may be NULL.
- * m == 0 and p_in == 0 mean "no reduction happened" (r*n >= p). */
+ * m == 0 and p_in == 0 mean "no reduction happened" (r*n >= p).  Needs REACH_GLGM06_RECORD_SELECTIONS.
+ * Indices refer to the concatenation after zero-generator removal, exactly like LazySets' `ind`. */
 REACH_API int32_t reach_flowpipe_selection(reach_flowpipe* fp, int64_t k, int32_t which, int32_t* p_in, int32_t* m, int32_t* ind,
                                  double* h);
 REACH_API int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, double* gemm_ms, int64_t* gemm_launches,

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "reach_glgm06_run": [vp],
     "reach_flowpipe_ngens": [vp, c_int32_p],
     "reach_flowpipe_step": [vp, i64, c_double_p, c_double_p, i64],
+    "reach_flowpipe_fetch": [vp, c_double_p, c_double_p, i64],
+    "reach_flowpipe_box": [vp, i64, c_double_p, c_double_p],
     "reach_flowpipe_selection": [vp, i64, i32, c_int32_p, c_int32_p, c_int32_p, c_double_p],
     "reach_flowpipe_timing": [vp, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p],
     "reach_flowpipe_free": [vp],

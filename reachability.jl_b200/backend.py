@@ -11,6 +11,10 @@ from . import _lib
 from ._lib import ReachError, dptr, fmat, fvec, iptr
 
 
+KEEP_ZERO_GENERATORS = 1     # REACH_GLGM06_KEEP_ZERO_GENERATORS
+RECORD_SELECTIONS = 2        # REACH_GLGM06_RECORD_SELECTIONS
+
+
 class Context:
     """`reach_ctx`: one CUDA device + stream.  Raises ReachError when no B200 is visible."""
 
@@ -267,6 +271,23 @@ class Flowpipe:
         G = np.zeros((self.n, max(p, 1)), order="F")
         self.ctx._check(self.ctx.lib.reach_flowpipe_step(self._h, int(k), dptr(c), dptr(G), self.n))
         return c, np.asfortranarray(G[:, :p])
+
+    def fetch(self, centers=None, G=None):
+        """All reach sets: centers (n, N) and G (n, pmax, N) Fortran arrays (allocated when None)."""
+        p = self.ngens()
+        pmax = int(p.max()) if G is None else G.shape[1]
+        if centers is None:
+            centers = np.zeros((self.n, self.N), order="F")
+        if G is None:
+            G = np.zeros((self.n, pmax, self.N), order="F")
+        assert centers.flags.f_contiguous and G.flags.f_contiguous and G.shape == (self.n, pmax, self.N)
+        self.ctx._check(self.ctx.lib.reach_flowpipe_fetch(self._h, dptr(centers), dptr(G), pmax))
+        return centers, G, p
+
+    def box(self, k: int):
+        lo, hi = np.zeros(self.n), np.zeros(self.n)
+        self.ctx._check(self.ctx.lib.reach_flowpipe_box(self._h, int(k), dptr(lo), dptr(hi)))
+        return lo, hi
 
     def selection(self, k: int, which: int = 0, pmax: int = 1 << 16):
         pin, m = C.c_int32(), C.c_int32()

@@ -10,13 +10,6 @@ int32_t reach_phi12(reach_ctx* ctx, int64_t, const double*, int64_t, double, dou
 int32_t reach_discretize_box(reach_ctx* ctx, int64_t, const double*, int64_t, double, int32_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, double*, int64_t, double*, int64_t, double*, double*, double*, double*, double*) { STUB(ctx, "reach_discretize_box"); }
 int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, const double*, double, int32_t, int64_t*) { STUB(ctx, "reach_bffpsv18_check"); }
 int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, int64_t, const double*, int64_t, double*, double*) { STUB(ctx, "reach_bffpsv18_output_map"); }
-int32_t reach_glgm06_create(reach_ctx* ctx, int64_t, const double*, int64_t, int64_t, const double*, const double*, int64_t, int64_t, const double*, const double*, int64_t, int64_t, int64_t, int32_t, reach_flowpipe**) { STUB(ctx, "reach_glgm06_create"); }
-int32_t reach_glgm06_run(reach_flowpipe*) { return REACH_EUNSUPPORTED; }
-int32_t reach_flowpipe_ngens(reach_flowpipe*, int32_t*) { return REACH_EUNSUPPORTED; }
-int32_t reach_flowpipe_step(reach_flowpipe*, int64_t, double*, double*, int64_t) { return REACH_EUNSUPPORTED; }
-int32_t reach_flowpipe_selection(reach_flowpipe*, int64_t, int32_t, int32_t*, int32_t*, int32_t*, double*) { return REACH_EUNSUPPORTED; }
-int32_t reach_flowpipe_timing(reach_flowpipe*, double*, double*, int64_t*, double*, double*, double*) { return REACH_EUNSUPPORTED; }
-void reach_flowpipe_free(reach_flowpipe*) {}
 int32_t reach_reduce_order(reach_ctx* ctx, int64_t, int64_t, const double*, const double*, int64_t, int64_t, int32_t, double*, int64_t, int64_t*, int32_t*) { STUB(ctx, "reach_reduce_order"); }
 int32_t reach_ensemble_create(reach_ctx* ctx, int64_t, const double*, int64_t, int64_t, int64_t, const double*, const double*, int64_t, reach_ensemble**) { STUB(ctx, "reach_ensemble_create"); }
 int32_t reach_ensemble_run(reach_ensemble*) { return REACH_EUNSUPPORTED; }

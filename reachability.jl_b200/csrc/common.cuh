@@ -81,6 +81,10 @@ struct GemmEpilogue {
 };
 void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt,
              int64_t ldbt, double* C, int64_t ldc, const GemmEpilogue& ep = GemmEpilogue());
+// Y[n x Q] = P[n x K] * X[K x Q], all column-major; X and Y are generator matrices (columns contiguous, ld a
+// multiple of 16 and zero-padded).  P must be zero-padded like a DMat.  ep.alpha / ep.diag apply (diag on Y[i,i]).
+void gemm_left(Ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64_t ldp, const double* X, int64_t ldx,
+               double* Y, int64_t ldy, const GemmEpilogue& ep = GemmEpilogue());
 // Bt[j + i*ldt] = A[i + j*lda]   (rows x cols -> cols x rows), out-of-place
 void transpose(Ctx* ctx, int64_t rows, int64_t cols, const double* A, int64_t lda, double* At, int64_t ldt);
 

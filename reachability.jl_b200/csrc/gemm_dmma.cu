@@ -78,11 +78,19 @@ struct GemmParams {
 };
 
 // WNT = n8 tiles per warp along N; CTA tile is 128 x (32*WNT).
-template <int WNT>
+// AKM = false ("NT"): A column-major (M contiguous), C column-major           -> C[row + col*ldc]
+// AKM = true  ("TN"): A given with K contiguous (row m of A = lda-strided run of K doubles), C stored with N
+//                     contiguous -> C[row*ldc + col].  With A = X^T (X n x Q column-major generators) and
+//                     Bt = Phi^s column-major this is  Y = Phi^s * X  with Y column-major again: the left
+//                     multiplication of GLGM06 (linear_map, GLGM06/reach.jl:16,48,54) with no transposes.
+//                     The A tile is moved as 128 bulk copies of 128 B into rows of pitch BK+4 = 20 doubles, so the
+//                     fragment load (row = lane/4, k = lane%4) hits slot 4*(lane/4) + lane%4 (mod 16): conflict-free.
+template <int WNT, bool AKM>
 __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
     constexpr int BN = 32 * WNT;
     constexpr int PITCH_B = BN + 4;
-    constexpr int A_STAGE = BK * PITCH_A;     // doubles
+    constexpr int PITCH_AK = BK + 4;
+    constexpr int A_STAGE = AKM ? BM * PITCH_AK : BK * PITCH_A;     // doubles
     constexpr int B_STAGE = BK * PITCH_B;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-            const double* gA = p.A + (int64_t)tm * BM;
+            const double* gA = AKM ? p.A + (int64_t)tm * BM * p.lda : p.A + (int64_t)tm * BM;
             const double* gB = p.Bt + (int64_t)tn * BN;
             for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
                 const int s = it % STAGES;
@@ -116,7 +124,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(BK * (BM + BN) * sizeof(double)));
                 __syncwarp();
                 const int k = ks * BK + (lane & 15);
-                if (lane < 16)
+                if (AKM) {
+#pragma unroll
+                    for (int rr = 0; rr < BM / 32; ++rr) {
+                        const int row = lane + rr * 32;
+                        bulk_g2s(sA + s * A_STAGE + row * PITCH_AK, gA + (int64_t)row * p.lda + ks * BK, BK * 8, &full[s]);
+                    }
+                    if (lane < 16)
+                        bulk_g2s(sB + s * B_STAGE + lane * PITCH_B, gB + (int64_t)k * p.ldbt, BN * 8, &full[s]);
+                } else if (lane < 16)
                     bulk_g2s(sA + s * A_STAGE + lane * PITCH_A, gA + (int64_t)k * p.lda, BM * 8, &full[s]);
                 else
                     bulk_g2s(sB + s * B_STAGE + (lane - 16) * PITCH_B, gB + (int64_t)k * p.ldbt, BN * 8, &full[s]);
@@ -139,13 +155,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                const double* a_s = sA + s * A_STAGE + t * PITCH_A + wm * 64 + g;
+                const double* a_s = AKM ? sA + s * A_STAGE + (wm * 64 + g) * PITCH_AK + t
+                                        : sA + s * A_STAGE + t * PITCH_A + wm * 64 + g;
                 const double* b_s = sB + s * B_STAGE + t * PITCH_B + wn * (8 * WNT) + g;
 #pragma unroll
                 for (int kk = 0; kk < BK / 4; ++kk) {
                     double a[8], b[WNT];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = a_s[kk * 4 * PITCH_A + i * 8];
+                    for (int i = 0; i < 8; ++i)
+                        a[i] = AKM ? a_s[i * 8 * PITCH_AK + kk * 4] : a_s[kk * 4 * PITCH_A + i * 8];
 #pragma unroll
                     for (int j = 0; j < WNT; ++j) b[j] = b_s[kk * 4 * PITCH_B + j * 8];
 #pragma unroll
@@ -159,6 +177,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
             // ---- epilogue: masked direct stores (8 rows x 8 B = two full 32 B sectors per column) ----
             const int row0 = tm * BM + wm * 64 + g;
             const int col0 = tn * BN + wn * (8 * WNT) + 2 * t;
+            if constexpr (AKM) {
+                // C[row*ldc + col]: each thread owns two adjacent columns -> one 16-byte store; 4 lanes cover 64 B.
+                // (col, col+1) is stored whenever col < N: for odd N the pad entry receives the exact zero of the
+                // zero-padded operand (ldc >= round_up(N, 2) by the DMat/generator layout).
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = row0 + i * 8;
+                    if (row < p.M) {
+                        double* crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                        for (int j = 0; j < WNT; ++j) {
+                            const int col = col0 + j * 8;
+                            if (col < p.N) {
+                                double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                                if (row == col) v.x += p.diag;
+                                if (row == col + 1) v.y += p.diag;
+                                *reinterpret_cast<double2*>(crow + col) = v;
+                            }
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < WNT; ++j) {
 #pragma unroll
@@ -179,22 +219,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                     }
                 }
             }
+            }
         }
     }
 }
 
-template <int WNT>
+template <int WNT, bool AKM>
 void launch(Ctx* ctx, const GemmParams& p) {
     constexpr int BN = 32 * WNT;
-    const size_t smem = (size_t)STAGES * BK * (PITCH_A + BN + 4) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+    constexpr int A_STAGE = AKM ? BM * (BK + 4) : BK * PITCH_A;
+    const size_t smem = (size_t)STAGES * (A_STAGE + BK * (BN + 4)) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-    gemm_dmma_kernel<WNT><<<grid, THREADS, smem, ctx->stream>>>(p);
+    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(p);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;
 }
@@ -239,9 +281,41 @@ void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t
     }
     p.tiles_n = (int)ceil_div(N, 32 * best);
     switch (best) {
-        case 4: launch<4>(ctx, p); break;
-        case 3: launch<3>(ctx, p); break;
-        default: launch<2>(ctx, p); break;
+        case 4: launch<4, false>(ctx, p); break;
+        case 3: launch<3, false>(ctx, p); break;
+        default: launch<2, false>(ctx, p); break;
+    }
+}
+
+// Y[n x Q] = P[n x K] * X[K x Q], everything column-major (see the AKM = true variant above).
+void gemm_left(Ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64_t ldp, const double* X, int64_t ldx,
+               double* Y, int64_t ldy, const GemmEpilogue& ep) {
+    if (n <= 0 || Q <= 0) return;
+    REACH_REQUIRE(K > 0, "gemm_left: K must be positive");
+    // The K-tail of a generator row (k in [K, round_up(K,16))) may run into the next column: it multiplies the zero
+    // pad rows of P, so it only has to be finite; the caller keeps >= 128 zeroed columns of slack behind X.
+    REACH_REQUIRE((ldp % 2) == 0 && (ldx % 2) == 0 && (ldy % 2) == 0 && ldx >= K && ldy >= round_up(n, 2),
+                  "gemm_left: leading dimensions must be even, ldx >= K, ldy >= round_up(n,2)");
+    REACH_REQUIRE((((uintptr_t)P) & 15) == 0 && (((uintptr_t)X) & 15) == 0 && (((uintptr_t)Y) & 15) == 0,
+                  "gemm_left: operands must be 16-byte aligned");
+    GemmParams p;
+    p.A = X; p.Bt = P; p.C = Y;
+    p.lda = ldx; p.ldbt = ldp; p.ldc = ldy;
+    p.M = (int)Q; p.N = (int)n; p.ksteps = (int)ceil_div(K, BK);
+    p.alpha = ep.alpha; p.diag = ep.diag;
+    p.C2 = nullptr; p.ldc2 = 0; p.nsplit = (int)n;
+    p.tiles_m = (int)ceil_div(Q, BM);
+    int best = 4;
+    int64_t best_cols = round_up(n, 128);
+    for (int wnt = 3; wnt >= 2; --wnt) {
+        int64_t c = round_up(n, 32 * wnt);
+        if (c < best_cols) { best_cols = c; best = wnt; }
+    }
+    p.tiles_n = (int)ceil_div(n, 32 * best);
+    switch (best) {
+        case 4: launch<4, true>(ctx, p); break;
+        case 3: launch<3, true>(ctx, p); break;
+        default: launch<2, true>(ctx, p); break;
     }
 }
 

@@ -1,0 +1,148 @@
+"""GPU parity: GLGM06 device path (reach_homog! / reach_inhomog!, GLGM06/reach.jl:5-62, through the C ABI) vs the
+CPU oracle.
+
+Tolerance (north_star): 1e-10 relative + 1e-12 absolute on every centre and generator entry, and IDENTICAL
+order-reduction selections (sortperm and number of boxed generators of every reduce_order call).
+Shapes mirror /root/reference/test/Reachability/solve_continuous.jl:186-196 (4x4 LCS / CLCCS with GLGM06 and
+`:max_order`) plus random dense systems with ragged sizes and BASELINE.json's C2-shaped system at reduced size.
+"""
+import numpy as np
+import pytest
+
+from oracle import reach_oracle as orc
+from tests.util import assert_close, tol_units
+
+pytestmark = pytest.mark.gpu
+
+KEEP, RECORD = 1, 2
+
+
+def _problem(seed, n, m, delta=0.01, dense=True):
+    g = np.random.default_rng(seed)
+    if dense:
+        A = g.standard_normal((n, n)) / np.sqrt(n) - 1.2 * np.eye(n)
+    else:   # block-diagonal 2x2 rotations (ISS-shaped): generators keep structural zeros
+        A = np.zeros((n, n))
+        for i in range(n // 2):
+            w = g.uniform(1.0, 30.0)
+            A[2 * i:2 * i + 2, 2 * i:2 * i + 2] = [[-0.1, w], [-w, -0.1]]
+        if n % 2:
+            A[-1, -1] = -1.0
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m)) if m else None
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3) if m else None
+    return A, X0, B, U, delta
+
+
+def _oracle(A, X0, B, U, delta, N, r, rzg):
+    D = orc.discretize_zonotope(A, X0, delta, B, U, rzg=rzg)
+    Om = orc.reduce_order(D.Omega0, r, rzg)
+    if D.V is None:
+        return D, Om, orc.glgm06_reach_homog(Om, D.Phi, N, rzg), [None] * N
+    R, sels = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, r, rzg, return_selections=True)
+    return D, Om, R, sels
+
+
+def _device(ctx, D, Om, N, r, rzg, record=True):
+    flags = (0 if rzg else KEEP) | (RECORD if record else 0)
+    V = D.V
+    fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, None if V is None else V.c, None if V is None else V.G, flags)
+    fp.run()
+    return fp
+
+
+def _compare(fp, R, sels, N, check_sel=True):
+    p = fp.ngens()
+    for k in range(1, N + 1):
+        Zo = R[k - 1]
+        assert p[k - 1] == Zo.ngens, f"step {k}: {p[k - 1]} generators, oracle {Zo.ngens}"
+        c, G = fp.step(k)
+        assert_close(c, Zo.c, f"step {k} centre")
+        if check_sel and sels[k - 1] is not None:
+            for which, sel in enumerate(sels[k - 1]):
+                got = fp.selection(k, which)
+                if sel is None:
+                    assert got["p_in"] == 0 and got["m"] == 0, f"step {k} list {which}: unexpected reduction"
+                    continue
+                h, ind, m = sel
+                assert got["p_in"] == len(h) and got["m"] == m, (k, which, got["p_in"], len(h), got["m"], m)
+                if not np.array_equal(got["ind"], ind):
+                    bad = np.nonzero(got["ind"] != ind)[0]
+                    i0 = bad[0]
+                    raise AssertionError(f"step {k} list {which}: sortperm differs at rank {i0} "
+                                         f"(got {got['ind'][i0]}, oracle {ind[i0]}; h={h[got['ind'][i0]]!r} vs {h[ind[i0]]!r})")
+                assert tol_units(got["h"], h) <= 1.0
+        assert_close(G, Zo.G, f"step {k} generators")
+
+
+@pytest.mark.parametrize("n,N", [(1, 4), (4, 20), (13, 33), (28, 65), (50, 40)])
+def test_homogeneous(ctx, n, N):
+    A, X0, _, _, delta = _problem(200 + n, n, 0)
+    D, Om, R, sels = _oracle(A, X0, None, None, delta, N, 10, True)
+    fp = _device(ctx, D, Om, N, 10, True, record=False)
+    _compare(fp, R, sels, N, check_sel=False)
+    lo, hi = fp.box(N)
+    rad = np.abs(R[-1].G).sum(axis=1)
+    assert_close(lo, R[-1].c - rad, "box lo")
+    assert_close(hi, R[-1].c + rad, "box hi")
+    fp.close()
+
+
+@pytest.mark.parametrize("rzg", [True, False])
+@pytest.mark.parametrize("n,m,N,r", [(4, 2, 30, 3), (6, 1, 40, 2), (13, 3, 25, 4), (20, 20, 20, 5), (33, 2, 30, 6),
+                                     (64, 5, 20, 3), (9, 2, 60, 1)])
+def test_inhomogeneous_dense(ctx, n, m, N, r, rzg):
+    A, X0, B, U, delta = _problem(300 + n, n, m)
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, r, rzg)
+    fp = _device(ctx, D, Om, N, r, rzg)
+    _compare(fp, R, sels, N)
+    fp.close()
+
+
+@pytest.mark.parametrize("rzg", [True, False])
+@pytest.mark.parametrize("n,m,N,r", [(8, 1, 40, 3), (20, 2, 30, 4), (54, 3, 30, 5)])
+def test_inhomogeneous_structured_zeros(ctx, n, m, N, r, rzg):
+    """Decoupled modes with the input entering few rows: box vectors d have exact zeros, so zero-generator removal
+    (`Zonotope` constructor) changes the generator counts and the number of boxed generators."""
+    A, X0, B, U, delta = _problem(400 + n, n, m, dense=False)
+    B = np.zeros((n, m))
+    B[1, 0] = 1.0
+    if m > 1:
+        B[n // 2 | 1, 1] = -0.5
+    X0.r[n // 2:] = 0.0
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, r, rzg)
+    fp = _device(ctx, D, Om, N, r, rzg)
+    _compare(fp, R, sels, N)
+    fp.close()
+
+
+def test_n_equals_one_set(ctx):
+    A, X0, B, U, delta = _problem(7, 5, 2)
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, 1, 3, True)
+    fp = _device(ctx, D, Om, 1, 3, True)
+    _compare(fp, R, sels, 1)
+    fp.close()
+
+
+def test_bulk_fetch_matches_stepwise(ctx):
+    A, X0, B, U, delta = _problem(11, 16, 2)
+    N = 25
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, 3, True)
+    fp = _device(ctx, D, Om, N, 3, True)
+    C, G, p = fp.fetch()
+    for k in range(1, N + 1):
+        c, Gk = fp.step(k)
+        assert np.array_equal(C[:, k - 1], c)
+        assert np.array_equal(G[:, :p[k - 1], k - 1], Gk)
+    fp.close()
+
+
+def test_c2_shaped_reduced(ctx):
+    """BASELINE.json config C2 (ISS-shaped modal system, GLGM06, max_order 10) at n=54, N=60."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.iss(n_modes=27, T=0.6)
+    N = orc.n_steps_glgm06(w.T, w.delta)
+    D, Om, R, sels = _oracle(w.A, orc.Box(w.c, w.r), w.B, orc.Box(w.cU, w.rU), w.delta, N, w.max_order, True)
+    fp = _device(ctx, D, Om, N, w.max_order, True)
+    _compare(fp, R, sels, N)
+    fp.close()
