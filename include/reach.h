@@ -168,6 +168,11 @@ REACH_API void reach_ensemble_free(reach_ensemble* e);
 REACH_API int32_t reach_dgemm(reach_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int32_t reps, double* kernel_ms);
 
+/* Y (n x Q) = P (n x K) * X (K x Q) with the left-multiplication variant of the same kernel (generator layout,
+ * everything column-major; the GEMM behind linear_map, GLGM06/reach.jl:16,48,54). */
+REACH_API int32_t reach_dgemm_left(reach_ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64_t ldp, const double* X,
+                         int64_t ldx, double* Y, int64_t ldy, int32_t reps, double* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "reach_ensemble_boxes": [vp, i64, c_double_p, c_double_p],
     "reach_ensemble_timing": [vp, c_double_p, c_double_p],
     "reach_ensemble_free": [vp],
+    "reach_dgemm_left": [vp, i64, i64, i64, c_double_p, i64, c_double_p, i64, c_double_p, i64, i32, c_double_p],
     "reach_dgemm": [vp, i64, i64, i64, c_double_p, i64, c_double_p, i64, c_double_p, i64, i32, c_double_p],
 }
 _RESTYPES = {

@@ -67,6 +67,17 @@ class Context:
         self._check(self.lib.reach_dgemm(self._h, M, N, K, dptr(A), M, dptr(B), K, dptr(Cm), M, int(reps), C.byref(ms)))
         return Cm, ms.value
 
+    def dgemm_left(self, P, X, reps: int = 1):
+        """Y = P @ X with the generator-layout (left multiplication) variant of the DMMA GEMM."""
+        P, X = fmat(P), fmat(X)
+        n, K = P.shape
+        K2, Q = X.shape
+        assert K == K2
+        Y = np.zeros((n, Q), order="F")
+        ms = C.c_double()
+        self._check(self.lib.reach_dgemm_left(self._h, n, Q, K, dptr(P), n, dptr(X), K, dptr(Y), n, int(reps), C.byref(ms)))
+        return Y, ms.value
+
     # ---- discretisation --------------------------------------------------------------------------------
     def expm(self, A, delta: float) -> np.ndarray:
         A = fmat(A)

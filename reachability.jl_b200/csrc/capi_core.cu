@@ -125,4 +125,41 @@ int32_t reach_dgemm(reach_ctx* ctx, int64_t M, int64_t N, int64_t K, const doubl
     REACH_CATCH(ctx)
 }
 
+int32_t reach_dgemm_left(reach_ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64_t ldp, const double* X,
+                         int64_t ldx, double* Y, int64_t ldy, int32_t reps, double* kernel_ms) {
+    if (!ctx) return REACH_EINVAL;
+    REACH_TRY(ctx)
+    Ctx* c = &ctx->c;
+    REACH_CUDA(cudaSetDevice(c->device));
+    REACH_REQUIRE(n > 0 && Q > 0 && K > 0 && P && X && Y, "reach_dgemm_left: bad arguments");
+    // generator layout: ld = round_up(rows, 4), 128 zeroed columns of slack
+    const int64_t lx = round_up(K, 4), ly = round_up(n, 4);
+    DMat dP = dmat_alloc(c, n, K);
+    double *dX = nullptr, *dY = nullptr;
+    REACH_CUDA(cudaMalloc(&dX, (size_t)(Q + 128) * lx * 8));
+    REACH_CUDA(cudaMalloc(&dY, (size_t)(Q + 128) * ly * 8));
+    REACH_CUDA(cudaMemsetAsync(dX, 0, (size_t)(Q + 128) * lx * 8, c->stream));
+    REACH_CUDA(cudaMemsetAsync(dY, 0, (size_t)(Q + 128) * ly * 8, c->stream));
+    dmat_upload(c, dP, P, ldp);
+    REACH_CUDA(cudaMemcpy2DAsync(dX, lx * 8, X, ldx * 8, K * 8, Q, cudaMemcpyHostToDevice, c->stream));
+    gemm_left(c, n, Q, K, dP.p, dP.ld, dX, lx, dY, ly);
+    if (reps > 1) {
+        REACH_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < reps; ++i) gemm_left(c, n, Q, K, dP.p, dP.ld, dX, lx, dY, ly);
+        REACH_CUDA(cudaEventRecord(c->ev1, c->stream));
+        REACH_CUDA(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        REACH_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (kernel_ms) *kernel_ms = ms / reps;
+    } else if (kernel_ms) {
+        *kernel_ms = 0;
+    }
+    REACH_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, dY, ly * 8, n * 8, Q, cudaMemcpyDeviceToHost, c->stream));
+    REACH_CUDA(cudaStreamSynchronize(c->stream));
+    dmat_free(dP);
+    cudaFree(dX); cudaFree(dY);
+    return REACH_OK;
+    REACH_CATCH(ctx)
+}
+
 }  // extern "C"

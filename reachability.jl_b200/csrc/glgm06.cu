@@ -708,7 +708,6 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
             g.st = (WState*)own(dalloc<WState>(ctx, 2));
             g.cW = (double*)own(dalloc<double>(ctx, ld));
-            REACH_CUDA(cudaMemcpyAsync(g.cW, cV, n * 8, cudaMemcpyHostToDevice, st));     // cW_1 = cV (:41-42)
             g.order_stride = F->record ? (int64_t)(g.capListR + g.capListW) : 0;
             const size_t order_len = (size_t)(g.capListR + g.capListW) * (F->record ? (size_t)(N + 1) : 1);
             g.orderR = (int*)own(dalloc<int>(ctx, order_len));
@@ -838,7 +837,8 @@ void flowpipe_run(Flowpipe* F) {
             REACH_CUDA(cudaMemsetAsync(g.cntS, 0, sizeof(int) * 2 * cnt, st));
         }
     };
-    // W_1 = V: scores / order of X's own input segment
+    // W_1 = V (GLGM06/reach.jl:41-42): cW = cV, scores / order of X's own input segment
+    REACH_CUDA(cudaMemcpyAsync(g.cW, F->X + (g.p0 + g.pV + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
     score_and_sort(F->X, 1);
     init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 8)), 256, 0, st>>>(g, F->X);
     REACH_CUDA(cudaGetLastError());
