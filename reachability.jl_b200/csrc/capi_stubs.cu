@@ -5,9 +5,6 @@
 namespace reach { Ctx* ctx_of(reach_ctx* h); }
 #define STUB(ctx, name) do { if (ctx) reach::ctx_of(ctx)->last_error = name ": not implemented in this build"; return REACH_EUNSUPPORTED; } while (0)
 extern "C" {
-int32_t reach_expm(reach_ctx* ctx, int64_t, const double*, int64_t, double, double*, int64_t) { STUB(ctx, "reach_expm"); }
-int32_t reach_phi12(reach_ctx* ctx, int64_t, const double*, int64_t, double, double*, int64_t, double*, int64_t) { STUB(ctx, "reach_phi12"); }
-int32_t reach_discretize_box(reach_ctx* ctx, int64_t, const double*, int64_t, double, int32_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, double*, int64_t, double*, int64_t, double*, double*, double*, double*, double*) { STUB(ctx, "reach_discretize_box"); }
 int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, const double*, double, int32_t, int64_t*) { STUB(ctx, "reach_bffpsv18_check"); }
 int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, int64_t, const double*, int64_t, double*, double*) { STUB(ctx, "reach_bffpsv18_output_map"); }
 int32_t reach_reduce_order(reach_ctx* ctx, int64_t, int64_t, const double*, const double*, int64_t, int64_t, int32_t, double*, int64_t, int64_t*, int32_t*) { STUB(ctx, "reach_reduce_order"); }

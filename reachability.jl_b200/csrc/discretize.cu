@@ -1,0 +1,349 @@
+// Discretisation on the device: src/ReachSets/discretize.jl of the reference.
+//
+//   exp_Aδ(A, δ)          = exp(Matrix(A*δ))                         discretize.jl:150-152
+//   Φ₁(A, δ), Φ₂(A, δ)    = blocks of exp(Pmatrix(A, δ))              discretize.jl:162-166, 221-226, 296-301
+//   discretize_interpolation (forward / backward) for box sets        discretize.jl:627-675
+//   box decomposition of the lazy Ω0 (BFFPSV18/reach.jl:64-65)
+//
+// B200 design: everything is GEMM.  The reference forms the dense 3n x 3n exponential to read off Φ₁/Φ₂ (27x the
+// flops of e^{Aδ}); here the three blocks come out of ONE Horner chain on the n x n matrix X = A δ / 2^s,
+//     R_{m+1} = I,  R_j = I + (X / j) R_{j+1}      =>   e^X = R_1,  Σ X^i/(i+1)! = R_2,  Σ X^i/(i+2)! = R_3 / 2,
+// one DMMA GEMM per term with the scale 1/j and the "+ I" fused into the epilogue, followed by s doubling steps
+//     Φ₀(2t) = Φ₀(t)²,   Φ₁(2t) = (Φ₀(t) + I) Φ₁(t),   Φ₂(2t) = (Φ₀(t) + I) Φ₂(t) + t Φ₁(t)
+// (the block rows of exp(Pmatrix)², read off the block-triangular structure).  ‖X‖₁ <= 1/2 and m = 18 terms put the
+// truncation error below 1e-20, so the result agrees with Julia's Padé-13 `exp` to rounding (tests pin both against
+// a 50-digit mpmath reference).
+#include "common.cuh"
+#include "../../include/reach.h"
+#include <cmath>
+#include <algorithm>
+
+namespace reach {
+
+namespace {
+
+constexpr int TAYLOR_TERMS = 18;
+
+__global__ void scale_copy_kernel(int n, const double* __restrict__ A, int64_t lda, double alpha, int take_abs,
+                                  double* __restrict__ X, int64_t ldx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i < n) {
+        double v = A[(int64_t)j * lda + i];
+        if (take_abs) v = fabs(v);
+        X[(int64_t)j * ldx + i] = alpha * v;
+    }
+}
+
+// out[j] = sum_i |A[i, j]|  (column sums for the 1-norm); one warp per column
+__global__ void col_abs_sums_kernel(int n, const double* __restrict__ A, int64_t lda, double* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += fabs(A[(int64_t)warp * lda + i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = s;
+}
+
+// Y = a * X + b * Z + d * I   (n x n, elementwise; Z may be NULL)
+__global__ void axpby_diag_kernel(int n, double a, const double* __restrict__ X, int64_t ldx, double b,
+                                  const double* __restrict__ Z, int64_t ldz, double d, double* __restrict__ Y, int64_t ldy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i < n) {
+        double v = a * X[(int64_t)j * ldx + i];
+        if (Z) v += b * Z[(int64_t)j * ldz + i];
+        if (i == j) v += d;
+        Y[(int64_t)j * ldy + i] = v;
+    }
+}
+
+// Row-wise products with a box (c, r):  sgn[i] = sum_j M[i,j] c[j],  mag[i] = sum_j |M[i,j]| r[j].
+// CTA = 64 rows x 4 column groups; columns in ascending order inside a group, groups combined in order.
+__global__ void __launch_bounds__(256) box_matvec_kernel(int rows, int cols, const double* __restrict__ M, int64_t ldm,
+                                                         const double* __restrict__ c, const double* __restrict__ r,
+                                                         double* __restrict__ sgn, double* __restrict__ mag) {
+    __shared__ double ss[4][64], sm[4][64];
+    const int li = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + li;
+    double a = 0.0, b = 0.0;
+    if (i < rows) {
+        for (int j = grp; j < cols; j += 4) {
+            const double v = M[(int64_t)j * ldm + i];
+            if (c) a = fma(v, c[j], a);
+            if (r) b = fma(fabs(v), r[j], b);
+        }
+    }
+    ss[grp][li] = a;
+    sm[grp][li] = b;
+    __syncthreads();
+    if (grp == 0 && i < rows) {
+        if (sgn) sgn[i] = (ss[0][li] + ss[1][li]) + (ss[2][li] + ss[3][li]);
+        if (mag) mag[i] = (sm[0][li] + sm[1][li]) + (sm[2][li] + sm[3][li]);
+    }
+}
+
+// s[i] = |a[i]| + b[i]      (symmetric_interval_hull radius of a box with centre a, radius b)
+__global__ void sih_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = fabs(a[i]) + b[i];
+}
+
+// box decomposition of Ω0 = CH(X0, Y), Y = ΦX0 ⊕ δU0 ⊕ Eψ0 ⊕ Einit   (discretize.jl:679,685)
+__global__ void omega0_box_kernel(int n, const double* __restrict__ c, const double* __restrict__ r,
+                                  const double* __restrict__ pc, const double* __restrict__ pr,
+                                  const double* __restrict__ rE, const double* __restrict__ uc,
+                                  const double* __restrict__ ur, const double* __restrict__ rpsi,
+                                  double* __restrict__ c0, double* __restrict__ r0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cY = pc[i];
+    double rY = pr[i] + rE[i];
+    if (uc) {
+        cY = cY + uc[i];
+        rY = rY + ur[i] + rpsi[i];
+    }
+    const double hi = fmax(c[i] + r[i], cY + rY);
+    const double lo = fmin(c[i] - r[i], cY - rY);
+    c0[i] = (hi + lo) / 2;
+    r0[i] = (hi - lo) / 2;
+}
+
+void launch2d(Ctx* ctx, int n, dim3& grid) { grid = dim3((unsigned)ceil_div(n, 256), (unsigned)n); (void)ctx; }
+
+}  // namespace
+
+// Horner chain + doubling.  dA: n x n on the device (ld lda).  Outputs are DMats allocated by the caller (any may
+// be NULL): P0 = e^{Aδ}, P1 = Φ₁(A, δ), P2 = Φ₂(A, δ).  take_abs: use |A| entrywise (Φ₂(abs.(A), δ), discretize.jl:652).
+void expm_family(Ctx* ctx, int64_t n, const double* dA, int64_t lda, double delta, bool take_abs, DMat* P0, DMat* P1,
+                 DMat* P2) {
+    cudaStream_t st = ctx->stream;
+    const bool need12 = (P1 != nullptr) || (P2 != nullptr);
+    // 1-norm of A δ
+    double* dsum = nullptr;
+    REACH_CUDA(cudaMalloc(&dsum, sizeof(double) * n));
+    col_abs_sums_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>((int)n, dA, lda, dsum);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    std::vector<double> hs(n);
+    REACH_CUDA(cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dsum);
+    double nrm = 0.0;
+    for (double v : hs) {
+        if (!std::isfinite(v)) throw Error(REACH_EINVAL, "expm: matrix has non-finite entries");
+        nrm = std::max(nrm, v);
+    }
+    nrm *= std::fabs(delta);
+    int s = 0;
+    if (nrm > 0.5) s = (int)std::ceil(std::log2(nrm / 0.5));
+    if (s > 60) throw Error(REACH_EINVAL, "expm: ||A delta|| too large");
+    const double h = delta / std::ldexp(1.0, s);
+
+    DMat X = dmat_alloc(ctx, n, n), Ra = dmat_alloc(ctx, n, n), Rb = dmat_alloc(ctx, n, n);
+    DMat R2 = need12 ? dmat_alloc(ctx, n, n) : DMat(), R3 = need12 ? dmat_alloc(ctx, n, n) : DMat();
+    dim3 g2;
+    launch2d(ctx, (int)n, g2);
+    scale_copy_kernel<<<g2, 256, 0, st>>>((int)n, dA, lda, h, take_abs ? 1 : 0, X.p, X.ld);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    // R_{m+1} = I
+    DMat* cur = &Ra;
+    DMat* nxt = &Rb;
+    axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, X.p, X.ld, 0.0, nullptr, 0, 1.0, cur->p, cur->ld);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    for (int j = TAYLOR_TERMS; j >= 1; --j) {
+        GemmEpilogue ep;
+        ep.alpha = 1.0 / j;
+        ep.diag = 1.0;
+        DMat* dst = nxt;
+        if (need12 && j == 3) dst = &R3;
+        if (need12 && j == 2) dst = &R2;
+        gemm_left(ctx, n, n, n, X.p, X.ld, cur->p, cur->ld, dst->p, dst->ld, ep);      // R_j = I + (X/j) R_{j+1}
+        if (dst == nxt) std::swap(cur, nxt); else cur = dst;
+    }
+    // cur = R_1 = e^X ; R2 = Σ X^i/(i+1)! ; R3/2 = Σ X^i/(i+2)!
+    DMat W = need12 ? dmat_alloc(ctx, n, n) : DMat();
+    DMat Q1, Q2, T1, T2;
+    if (need12) {
+        Q1 = dmat_alloc(ctx, n, n); Q2 = dmat_alloc(ctx, n, n); T1 = dmat_alloc(ctx, n, n); T2 = dmat_alloc(ctx, n, n);
+        axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, h, R2.p, R2.ld, 0.0, nullptr, 0, 0.0, Q1.p, Q1.ld);
+        axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.5 * h * h, R3.p, R3.ld, 0.0, nullptr, 0, 0.0, Q2.p, Q2.ld);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    // the three blocks live in: e = *cur (other of Ra/Rb is scratch), Q1, Q2
+    DMat* e = cur;
+    DMat* escr = (cur == &Ra) ? &Rb : &Ra;
+    if (cur == &R2 || cur == &R3) throw Error(REACH_ECUDA, "expm: internal buffer rotation error");
+    DMat *q1 = &Q1, *q2 = &Q2, *t1 = &T1, *t2 = &T2;
+    double t = h;
+    for (int i = 0; i < s; ++i) {
+        if (need12) {
+            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 1.0, e->p, e->ld, 0.0, nullptr, 0, 1.0, W.p, W.ld);   // W = Φ₀ + I
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches++;
+            gemm_left(ctx, n, n, n, W.p, W.ld, q1->p, q1->ld, t1->p, t1->ld);             // Φ₁(2t) = W Φ₁
+            gemm_left(ctx, n, n, n, W.p, W.ld, q2->p, q2->ld, t2->p, t2->ld);             // W Φ₂
+            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 1.0, t2->p, t2->ld, t, q1->p, q1->ld, 0.0, t2->p, t2->ld);  // + t Φ₁(t)
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches++;
+            std::swap(q1, t1);
+            std::swap(q2, t2);
+        }
+        gemm_left(ctx, n, n, n, e->p, e->ld, e->p, e->ld, escr->p, escr->ld);             // Φ₀(2t) = Φ₀²
+        std::swap(e, escr);
+        t *= 2;
+    }
+    auto give = [&](DMat* out, DMat* src) {
+        if (!out) return;
+        REACH_CUDA(cudaMemcpy2DAsync(out->p, out->ld * 8, src->p, src->ld * 8, n * 8, n, cudaMemcpyDeviceToDevice, st));
+    };
+    give(P0, e);
+    if (need12) { give(P1, q1); give(P2, q2); }
+    REACH_CUDA(cudaStreamSynchronize(st));
+    dmat_free(X); dmat_free(Ra); dmat_free(Rb);
+    if (need12) { dmat_free(R2); dmat_free(R3); dmat_free(W); dmat_free(Q1); dmat_free(Q2); dmat_free(T1); dmat_free(T2); }
+}
+
+static void box_matvec(Ctx* ctx, int64_t rows, int64_t cols, const double* M, int64_t ldm, const double* c, const double* r,
+                       double* sgn, double* mag) {
+    if (rows <= 0) return;
+    box_matvec_kernel<<<(unsigned)ceil_div(rows, 64), 256, 0, ctx->stream>>>((int)rows, (int)cols, M, ldm, c, r, sgn, mag);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+}  // namespace reach
+
+// =========================================================================================================
+namespace reach { Ctx* ctx_of(reach_ctx* h); }
+using namespace reach;
+
+#define D_BEGIN(ctx)                                      \
+    if (!(ctx)) return REACH_EINVAL;                      \
+    try {                                                 \
+        REACH_CUDA(cudaSetDevice((ctx)->device));
+#define D_END(ctx)                                                                                \
+    }                                                                                             \
+    catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+
+extern "C" {
+
+int32_t reach_expm(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, double* Phi, int64_t ldphi) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    D_BEGIN(ctx)
+    REACH_REQUIRE(n > 0 && A && Phi && lda >= n && ldphi >= n, "reach_expm: bad arguments");
+    DMat dA = dmat_alloc(ctx, n, n), dP = dmat_alloc(ctx, n, n);
+    dmat_upload(ctx, dA, A, lda);
+    expm_family(ctx, n, dA.p, dA.ld, delta, false, &dP, nullptr, nullptr);
+    dmat_download(ctx, dP, Phi, ldphi);
+    REACH_CUDA(cudaStreamSynchronize(ctx->stream));
+    dmat_free(dA); dmat_free(dP);
+    return REACH_OK;
+    D_END(ctx)
+}
+
+int32_t reach_phi12(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, double* Phi1, int64_t ld1,
+                    double* Phi2, int64_t ld2) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    D_BEGIN(ctx)
+    REACH_REQUIRE(n > 0 && A && lda >= n && (!Phi1 || ld1 >= n) && (!Phi2 || ld2 >= n), "reach_phi12: bad arguments");
+    DMat dA = dmat_alloc(ctx, n, n), d1 = dmat_alloc(ctx, n, n), d2 = dmat_alloc(ctx, n, n);
+    dmat_upload(ctx, dA, A, lda);
+    expm_family(ctx, n, dA.p, dA.ld, delta, false, nullptr, &d1, &d2);
+    if (Phi1) dmat_download(ctx, d1, Phi1, ld1);
+    if (Phi2) dmat_download(ctx, d2, Phi2, ld2);
+    REACH_CUDA(cudaStreamSynchronize(ctx->stream));
+    dmat_free(dA); dmat_free(d1); dmat_free(d2);
+    return REACH_OK;
+    D_END(ctx)
+}
+
+int32_t reach_discretize_box(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm,
+                             const double* c, const double* r, int64_t m, const double* B, int64_t ldb,
+                             const double* cU, const double* rU, double* Phi, int64_t ldphi, double* Phi2abs,
+                             int64_t ldphi2, double* c0, double* r0, double* rE, double* rpsi, double* MU) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    D_BEGIN(ctx)
+    REACH_REQUIRE(n > 0 && A && lda >= n && c && r, "reach_discretize_box: bad A / X0");
+    if (algorithm != REACH_FORWARD && algorithm != REACH_BACKWARD)
+        throw Error(REACH_EINVAL, "the algorithm is unknown");      // ArgumentError at discretize.jl:659
+    REACH_REQUIRE(m >= 0 && (m == 0 || (cU && rU)), "reach_discretize_box: inputs need cU, rU");
+    REACH_REQUIRE(!B || ldb >= n, "reach_discretize_box: bad ldb");
+    REACH_REQUIRE(B || m == 0 || m == n, "reach_discretize_box: B == NULL means identity and needs m == n");
+    cudaStream_t st = ctx->stream;
+    DMat dA = dmat_alloc(ctx, n, n), dPhi = dmat_alloc(ctx, n, n), dP2 = dmat_alloc(ctx, n, n), dM = dmat_alloc(ctx, n, n);
+    DMat dM2, dB, dAB;
+    double* vec = nullptr;     // n-vectors: c r pc pr a1 b1 s1 rE uc ur a2 b2 s2 rpsi c0 r0 ; m-vectors: cU rU
+    const int64_t NV = 16;
+    REACH_CUDA(cudaMalloc(&vec, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1))));
+    REACH_CUDA(cudaMemsetAsync(vec, 0, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1)), st));
+    auto V = [&](int i) { return vec + (int64_t)i * n; };
+    double* dcU = vec + NV * n;
+    double* drU = dcU + std::max<int64_t>(m, 1);
+    dmat_upload(ctx, dA, A, lda);
+    REACH_CUDA(cudaMemcpyAsync(V(0), c, n * 8, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(cudaMemcpyAsync(V(1), r, n * 8, cudaMemcpyHostToDevice, st));
+    expm_family(ctx, n, dA.p, dA.ld, delta, false, &dPhi, nullptr, nullptr);          // ϕ = exp_Aδ(A, δ)        :649
+    expm_family(ctx, n, dA.p, dA.ld, delta, true, nullptr, nullptr, &dP2);            // Phi2Aabs = Φ₂(|A|, δ)   :652
+    gemm_left(ctx, n, n, n, dA.p, dA.ld, dA.p, dA.ld, dM.p, dM.ld);                    // A * A                   :655
+    const DMat* Msel = &dM;
+    if (algorithm == REACH_BACKWARD) {                                                 // A * A * ϕ               :657
+        dM2 = dmat_alloc(ctx, n, n);
+        gemm_left(ctx, n, n, n, dM.p, dM.ld, dPhi.p, dPhi.ld, dM2.p, dM2.ld);
+        Msel = &dM2;
+    }
+    const unsigned gv = (unsigned)ceil_div(n, 256);
+    box_matvec(ctx, n, n, Msel->p, Msel->ld, V(0), V(1), V(4), V(5));                  // box of (A²)X0
+    sih_kernel<<<gv, 256, 0, st>>>((int)n, V(4), V(5), V(6));                          // inner sih
+    box_matvec(ctx, n, n, dP2.p, dP2.ld, nullptr, V(6), nullptr, V(7));                // Einit radius = Φ₂|A| s1
+    box_matvec(ctx, n, n, dPhi.p, dPhi.ld, V(0), V(1), V(2), V(3));                    // box of ΦX0
+    ctx->launches += 1;
+    if (m > 0) {
+        REACH_CUDA(cudaMemcpyAsync(dcU, cU, m * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(drU, rU, m * 8, cudaMemcpyHostToDevice, st));
+        dB = dmat_alloc(ctx, n, m);
+        if (B) {
+            dmat_upload(ctx, dB, B, ldb);
+        } else {
+            dim3 g2((unsigned)ceil_div(n, 256), (unsigned)n);
+            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, dA.p, dA.ld, 0.0, nullptr, 0, 1.0, dB.p, dB.ld);
+            ctx->launches++;
+        }
+        dAB = dmat_alloc(ctx, n, m);
+        gemm_left(ctx, n, m, n, dA.p, dA.ld, dB.p, dB.ld, dAB.p, dAB.ld);              // A * U0 = (A B) U        :671
+        box_matvec(ctx, n, m, dAB.p, dAB.ld, dcU, drU, V(10), V(11));
+        sih_kernel<<<gv, 256, 0, st>>>((int)n, V(10), V(11), V(12));
+        box_matvec(ctx, n, n, dP2.p, dP2.ld, nullptr, V(12), nullptr, V(13));          // Eψ0 radius
+        // δ U0: MU = δ B, box of MU * U
+        dim3 gm((unsigned)ceil_div(n, 256), (unsigned)m);
+        scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, dB.p, dB.ld, delta, 0, dAB.p, dAB.ld);   // reuse dAB as MU
+        box_matvec(ctx, n, m, dAB.p, dAB.ld, dcU, drU, V(8), V(9));
+        ctx->launches += 2;
+    }
+    omega0_box_kernel<<<gv, 256, 0, st>>>((int)n, V(0), V(1), V(2), V(3), V(7), m > 0 ? V(8) : nullptr, V(9), V(13),
+                                          V(14), V(15));
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_box: ldphi"); dmat_download(ctx, dPhi, Phi, ldphi); }
+    if (Phi2abs) { REACH_REQUIRE(ldphi2 >= n, "reach_discretize_box: ldphi2"); dmat_download(ctx, dP2, Phi2abs, ldphi2); }
+    auto down = [&](double* dst, int i) {
+        if (dst) REACH_CUDA(cudaMemcpyAsync(dst, V(i), n * 8, cudaMemcpyDeviceToHost, st));
+    };
+    down(c0, 14); down(r0, 15); down(rE, 7);
+    if (m > 0) {
+        down(rpsi, 13);
+        if (MU) dmat_download(ctx, dAB, MU, n);
+    }
+    REACH_CUDA(cudaStreamSynchronize(st));
+    dmat_free(dA); dmat_free(dPhi); dmat_free(dP2); dmat_free(dM); dmat_free(dM2); dmat_free(dB); dmat_free(dAB);
+    cudaFree(vec);
+    return REACH_OK;
+    D_END(ctx)
+}
+
+}  // extern "C"
