@@ -7,11 +7,4 @@ namespace reach { Ctx* ctx_of(reach_ctx* h); }
 extern "C" {
 int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, const double*, double, int32_t, int64_t*) { STUB(ctx, "reach_bffpsv18_check"); }
 int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, const double*, int64_t, const int32_t*, int64_t, int64_t, const double*, int64_t, double*, double*) { STUB(ctx, "reach_bffpsv18_output_map"); }
-int32_t reach_reduce_order(reach_ctx* ctx, int64_t, int64_t, const double*, const double*, int64_t, int64_t, int32_t, double*, int64_t, int64_t*, int32_t*) { STUB(ctx, "reach_reduce_order"); }
-int32_t reach_ensemble_create(reach_ctx* ctx, int64_t, const double*, int64_t, int64_t, int64_t, const double*, const double*, int64_t, reach_ensemble**) { STUB(ctx, "reach_ensemble_create"); }
-int32_t reach_ensemble_run(reach_ensemble*) { return REACH_EUNSUPPORTED; }
-int32_t reach_ensemble_step(reach_ensemble*, int64_t, int64_t, double*, double*) { return REACH_EUNSUPPORTED; }
-int32_t reach_ensemble_boxes(reach_ensemble*, int64_t, double*, double*) { return REACH_EUNSUPPORTED; }
-int32_t reach_ensemble_timing(reach_ensemble*, double*, double*) { return REACH_EUNSUPPORTED; }
-void reach_ensemble_free(reach_ensemble*) {}
 }

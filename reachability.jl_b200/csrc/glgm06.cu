@@ -591,6 +591,18 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     hi[(int64_t)b * n + i] = ci + s;
 }
 
+// Dense copy of the current W (parity par): tagged box generators are synthesised.  out: n x pW, leading dim ldo.
+__global__ void __launch_bounds__(256) materialize_w_kernel(GP g, int par, double* __restrict__ out, int ldo) {
+    const WState st = g.st[par];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= st.pW) return;
+    const int tag = g.tagW[par][warp];
+    const double val = g.valW[par][warp];
+    const double* src = g.GW[st.cur] + (int64_t)warp * g.ld;
+    double* dst = out + (int64_t)warp * ldo;
+    for (int i = lane; i < g.n; i += 32) dst[i] = tag < 0 ? src[i] : (i == tag ? val : 0.0);
+}
+
 template <typename T>
 T* dalloc(Ctx* ctx, size_t count, bool zero = true) {
     T* p = nullptr;
@@ -608,6 +620,7 @@ struct Flowpipe {
     int64_t n = 0, ld = 0, p0 = 0, pV = 0, q = 0, N = 0, r = 0, s = 1;
     int flags = 0;
     bool homog = false, record = false;
+    int64_t nc = 1;                 // homogeneous: number of centre columns (ensemble: one per member)
     GP g{};
     DMat Phi, PowA, PowB;
     double* X = nullptr;            // n x q  [G0 | GV | c0 | cV]
@@ -640,7 +653,7 @@ static int64_t pick_block(int64_t n, int64_t q, int64_t N) {
 
 Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
                           const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV, int64_t ldgv,
-                          int64_t N, int64_t max_order, int32_t flags) {
+                          int64_t N, int64_t max_order, int32_t flags, int64_t nc = 1) {
     REACH_REQUIRE(n > 0 && Phi && ldphi >= n, "glgm06: bad Phi");
     REACH_REQUIRE(p0 >= 0 && c0 && (p0 == 0 || (G0 && ldg0 >= n)), "glgm06: bad Omega0");
     REACH_REQUIRE(N >= 1, "glgm06: N must be >= 1");
@@ -658,7 +671,8 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         F->record = (flags & REACH_GLGM06_RECORD_SELECTIONS) != 0;
         F->ld = round_up(n, 4);   // 32-byte aligned columns; the GEMM's K-tail over-read hits finite data times zero pad
         const int64_t ld = F->ld;
-        F->q = homog ? p0 + 1 : p0 + pV + 2;
+        F->nc = homog ? nc : 1;
+        F->q = homog ? p0 + F->nc : p0 + pV + 2;
         const int64_t q = F->q;
         F->s = N > 2 ? pick_block(n, q, N) : 1;
         const int64_t s = F->s;
@@ -675,11 +689,20 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         g.n = (int)n; g.ld = (int)ld; g.p0 = (int)p0; g.pV = (int)pV; g.q = (int)q;
         g.strip = (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) ? 0 : 1;
         if (homog) {
-            // the flowpipe storage is the stack: slot k-1 = Phi^{k-1} [G0 | c0]
+            // the flowpipe storage is the stack: slot k-1 = Phi^{k-1} [G0 | c0]  (ensemble: [G_0 .. G_{b-1} | c_0 .. c_{b-1}])
             const size_t cols = (size_t)N * q + 256;
+            size_t free_b = 0, total_b = 0;
+            REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            if ((double)cols * ld * 8.0 > 0.92 * (double)free_b) {
+                char buf[256];
+                snprintf(buf, sizeof(buf), "glgm06: homogeneous flowpipe needs %.1f GB of HBM (N=%lld sets of %lld columns), "
+                         "%.1f GB free: shard the ensemble across GPUs or shorten the horizon",
+                         (double)cols * ld * 8.0 / 1e9, (long long)N, (long long)q, (double)free_b / 1e9);
+                throw Error(REACH_EUNSUPPORTED, buf);
+            }
             F->Hflow = (double*)own(dalloc<double>(ctx, cols * ld));
             up2d(F->Hflow, G0, ldg0, p0);
-            up2d(F->Hflow + p0 * ld, c0, n, 1);
+            up2d(F->Hflow + p0 * ld, c0, n, nc);
         } else {
             const int64_t rn = max_order * n;
             g.rn = rn; g.nkeep = n * (max_order - 1);
@@ -919,6 +942,70 @@ void flowpipe_run(Flowpipe* F) {
     F->ran = true;
 }
 
+// reduce_order(Z, r) of LazySets (Girard 2005; call site GLGM06/post.jl:20) as ONE step of the same
+// machinery: W list = [ (empty W) | the columns of G ], so scores, stable order, boxing and zero-generator removal
+// are exactly the kernels the time loop uses.
+void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const double* G, int64_t ldg, int64_t r,
+                       int32_t flags, double* Gout, int64_t ldgo, int64_t* p_out, int32_t* ind) {
+    REACH_REQUIRE(n > 0 && p >= 0 && c && (p == 0 || (G && ldg >= n)) && Gout && ldgo >= n && p_out,
+                  "reach_reduce_order: bad arguments");
+    cudaStream_t st = ctx->stream;
+    if (r < 1 || p == 0) {      // reduce_order returns Z itself
+        for (int64_t j = 0; j < p; ++j) std::memcpy(Gout + j * ldgo, G + j * ldg, sizeof(double) * n);
+        *p_out = p;
+        if (ind) for (int64_t j = 0; j < p; ++j) ind[j] = (int32_t)j;
+        return;
+    }
+    std::vector<double> zeros((size_t)n * n, 0.0);
+    Flowpipe* F = flowpipe_create(ctx, n, zeros.data(), n, 0, c, nullptr, n, p, c, G, ldg, 2, r, flags & REACH_GLGM06_KEEP_ZERO_GENERATORS);
+    double* dout = nullptr;
+    try {
+        GP g = F->g;
+        g.Y = F->X;
+        const int per = (int)p;
+        score_stack_kernel<<<(unsigned)ceil_div(per, 8), 256, 0, st>>>(g, 1);
+        dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(per, 256)), 2u);
+        sort_segments_kernel<<<grid, 256, 0, st>>>(g);
+        REACH_CUDA(cudaGetLastError());
+        REACH_CUDA(cudaMemsetAsync(g.st, 0, 2 * sizeof(WState), st));       // W empty, buffer 0
+        const int rank_threads = g.p0 + 2 * g.capW + g.pV;
+        rank_lists_kernel<<<(unsigned)ceil_div(rank_threads, 256), 256, 0, st>>>(g, 0, 2, 0);
+        const size_t apply_smem = (size_t)(APPLY_THREADS / 32) * F->ld * sizeof(double);
+        REACH_CUDA(cudaFuncSetAttribute(apply_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        apply_step_kernel<<<NBOX + 2 * (unsigned)ctx->sm_count, APPLY_THREADS, apply_smem, st>>>(g, 0, 2);
+        REACH_CUDA(cudaGetLastError());
+        const int64_t cap = g.capW;
+        REACH_CUDA(cudaMalloc(&dout, sizeof(double) * (size_t)cap * n));
+        materialize_w_kernel<<<(unsigned)ceil_div(cap, 8), 256, 0, st>>>(g, 1, dout, (int)n);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 5;
+        WState ns;
+        StepPlan pl;
+        REACH_CUDA(cudaMemcpyAsync(&ns, g.st + 1, sizeof(ns), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(&pl, g.plans + 2, sizeof(pl), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        *p_out = ns.pW;
+        if (ns.pW > 0)
+            REACH_CUDA(cudaMemcpy2DAsync(Gout, ldgo * 8, dout, n * 8, n * 8, ns.pW, cudaMemcpyDeviceToHost, st));
+        if (ind) {
+            std::vector<int> order(std::max(pl.pinW, 1));
+            std::vector<int> cpos(p);
+            REACH_CUDA(cudaMemcpyAsync(order.data(), g.orderW + 2 * g.order_stride, sizeof(int) * pl.pinW, cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaMemcpyAsync(cpos.data(), g.cposS, sizeof(int) * p, cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+            for (int sgm = 0; sgm < pl.pinW; ++sgm) ind[sgm] = cpos[order[sgm]];     // code == column (p0 = 0)
+            for (int64_t j = pl.pinW; j < p; ++j) ind[j] = -1;
+        }
+        REACH_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        if (dout) cudaFree(dout);
+        flowpipe_free(F);
+        throw;
+    }
+    cudaFree(dout);
+    flowpipe_free(F);
+}
+
 }  // namespace reach
 
 // =========================================================================================================
@@ -1135,6 +1222,101 @@ int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, double* gemm_m
     if (reduce_ms) *reduce_ms = F->reduce_ms;
     if (reduce_bytes) *reduce_bytes = F->reduce_bytes;
     return REACH_OK;
+}
+
+int32_t reach_reduce_order(reach_ctx* h, int64_t n, int64_t p, const double* c, const double* G, int64_t ldg, int64_t r,
+                           int32_t flags, double* Gout, int64_t ldgo, int64_t* p_out, int32_t* ind) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    FP_BEGIN(ctx)
+    reduce_order_once(ctx, n, p, c, G, ldg, r, flags, Gout, ldgo, p_out, ind);
+    return REACH_OK;
+    FP_END(ctx)
+}
+
+// ---- batched homogeneous ensemble (config C5): the same homogeneous recurrence over batch * (p + 1) columns ----
+struct reach_ensemble {
+    Flowpipe* f;
+    Ctx* ctx;
+    int64_t batch, p;
+    double* stage;
+};
+
+int32_t reach_ensemble_create(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, int64_t batch, int64_t p,
+                              const double* c0s, const double* G0s, int64_t N, reach_ensemble** out) {
+    if (!h || !out) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    *out = nullptr;
+    FP_BEGIN(ctx)
+    REACH_REQUIRE(batch >= 1 && p >= 0 && c0s && (p == 0 || G0s), "reach_ensemble_create: bad arguments");
+    Flowpipe* f = flowpipe_create(ctx, n, Phi, ldphi, batch * p, c0s, G0s, n, 0, nullptr, nullptr, n, N, 1, 0, batch);
+    *out = new reach_ensemble{f, ctx, batch, p, nullptr};
+    return REACH_OK;
+    FP_END(ctx)
+}
+
+int32_t reach_ensemble_run(reach_ensemble* en) {
+    if (!en) return REACH_EINVAL;
+    FP_BEGIN(en->ctx)
+    flowpipe_run(en->f);
+    return REACH_OK;
+    FP_END(en->ctx)
+}
+
+int32_t reach_ensemble_step(reach_ensemble* en, int64_t b, int64_t k, double* c, double* G) {
+    if (!en) return REACH_EINVAL;
+    FP_BEGIN(en->ctx)
+    Flowpipe* F = en->f;
+    require_ran(F);
+    REACH_REQUIRE(b >= 0 && b < en->batch && k >= 1 && k <= F->N, "reach_ensemble_step: member / step out of range");
+    const double* slot = F->Hflow + (k - 1) * F->q * F->ld;
+    cudaStream_t st = F->ctx->stream;
+    if (c) REACH_CUDA(cudaMemcpyAsync(c, slot + (en->batch * en->p + b) * F->ld, F->n * 8, cudaMemcpyDeviceToHost, st));
+    if (G && en->p > 0)
+        REACH_CUDA(cudaMemcpy2DAsync(G, F->n * 8, slot + b * en->p * F->ld, F->ld * 8, F->n * 8, en->p, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    return REACH_OK;
+    FP_END(en->ctx)
+}
+
+int32_t reach_ensemble_boxes(reach_ensemble* en, int64_t k, double* lo, double* hi) {
+    if (!en || !lo || !hi) return REACH_EINVAL;
+    FP_BEGIN(en->ctx)
+    Flowpipe* F = en->f;
+    require_ran(F);
+    REACH_REQUIRE(k >= 1 && k <= F->N, "reach_ensemble_boxes: step out of range");
+    cudaStream_t st = F->ctx->stream;
+    const size_t cnt = (size_t)F->n * en->batch;
+    if (!en->stage) {
+        REACH_CUDA(cudaMalloc(&en->stage, 2 * cnt * 8));
+        F->owned.push_back(en->stage);
+    }
+    const double* slot = F->Hflow + (k - 1) * F->q * F->ld;
+    zono_box_kernel<<<dim3((unsigned)ceil_div(F->n, 64), (unsigned)en->batch), 64, 0, st>>>(
+        (int)F->n, (int)F->ld, (int)en->p, en->p * F->ld, (int)en->batch, slot, slot + en->batch * en->p * F->ld, F->ld, en->stage,
+        en->stage + cnt);
+    REACH_CUDA(cudaGetLastError());
+    F->ctx->launches++;
+    REACH_CUDA(cudaMemcpyAsync(lo, en->stage, cnt * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaMemcpyAsync(hi, en->stage + cnt, cnt * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    return REACH_OK;
+    FP_END(en->ctx)
+}
+
+int32_t reach_ensemble_timing(reach_ensemble* en, double* run_ms, double* bytes_per_step) {
+    if (!en) return REACH_EINVAL;
+    if (run_ms) *run_ms = en->f->run_ms;
+    if (bytes_per_step) *bytes_per_step = 16.0 * (double)en->f->n * (double)(en->p + 1) * (double)en->batch;
+    return REACH_OK;
+}
+
+void reach_ensemble_free(reach_ensemble* en) {
+    if (!en) return;
+    cudaSetDevice(en->ctx->device);
+    cudaStreamSynchronize(en->ctx->stream);
+    flowpipe_free(en->f);
+    delete en;
 }
 
 void reach_flowpipe_free(reach_flowpipe* fp) {

@@ -146,3 +146,62 @@ def test_c2_shaped_reduced(ctx):
     fp = _device(ctx, D, Om, N, w.max_order, True)
     _compare(fp, R, sels, N)
     fp.close()
+
+
+def test_run_is_idempotent(ctx):
+    A, X0, B, U, delta = _problem(12, 10, 2)
+    N = 30
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, 3, True)
+    fp = _device(ctx, D, Om, N, 3, True)
+    fp.run()
+    fp.run()
+    _compare(fp, R, sels, N)
+    fp.close()
+
+
+@pytest.mark.parametrize("rzg", [True, False])
+@pytest.mark.parametrize("n,p,r", [(3, 10, 2), (5, 40, 3), (16, 100, 1), (16, 100, 5), (16, 100, 7), (33, 500, 4), (270, 3784, 10),
+                                   (7, 3, 2)])
+def test_reduce_order_standalone(ctx, n, p, r, rzg):
+    """`reduce_order(Z, r)` (LazySets, call site GLGM06/post.jl:20): Girard selection, kept generators in
+    ascending-score order, box generators last; unchanged when r*n >= p."""
+    g = np.random.default_rng(n * 1000 + p)
+    G = g.standard_normal((n, p)) * np.exp(g.uniform(-3, 3, p))[None, :]
+    G[:, ::7] = 0.0
+    G[n // 2, 3::7] = 0.0                # some structure: zero columns and zero entries
+    if p > 10:
+        G[:, 5] = 0.0
+        G[0, 5] = 2.5                    # an axis-aligned generator (score exactly 0)
+    c = g.standard_normal(n)
+    Zin = orc.make_zono(c, G, rzg)
+    Zo, sel = orc.reduce_order(Zin, r, rzg, return_selection=True)
+    flags = 0 if rzg else KEEP
+    Gd, ind = ctx.reduce_order(c, Zin.G, r, flags)
+    assert Gd.shape == Zo.G.shape
+    assert_close(Gd, Zo.G, "reduced generators")
+    if sel is not None:
+        assert np.array_equal(ind[:len(sel[1])], sel[1])
+
+
+@pytest.mark.parametrize("n,p,batch,N", [(4, 5, 3, 10), (28, 85, 16, 40), (6, 0, 4, 7)])
+def test_ensemble_homogeneous(ctx, n, p, batch, N):
+    """Batched reach_homog! (GLGM06/reach.jl:15-19): every member must equal its own single flowpipe."""
+    g = np.random.default_rng(n + p + batch)
+    A = g.standard_normal((n, n)) / np.sqrt(n) - np.eye(n)
+    Phi = orc.exp_Adelta(A, 0.05)
+    c0s = g.standard_normal((n, batch))
+    G0s = g.standard_normal((n, p, batch)) * 0.1
+    ens = ctx.ensemble(Phi, c0s, G0s, N).run()
+    for b in range(batch):
+        R = orc.glgm06_reach_homog(orc.Zono(c0s[:, b], G0s[:, :, b]), Phi, N, rzg=False)
+        for k in (1, 2, N // 2, N):
+            c, G = ens.step(b, k)
+            assert_close(c, R[k - 1].c, f"member {b} step {k} centre")
+            assert_close(G, R[k - 1].G.reshape(n, p), f"member {b} step {k} generators")
+    lo, hi = ens.boxes(N)
+    for b in range(batch):
+        R = orc.glgm06_reach_homog(orc.Zono(c0s[:, b], G0s[:, :, b]), Phi, N, rzg=False)
+        rad = np.abs(R[-1].G).sum(axis=1) if p else np.zeros(n)
+        assert_close(lo[:, b], R[-1].c - rad, "lo")
+        assert_close(hi[:, b], R[-1].c + rad, "hi")
+    ens.close()
