@@ -240,6 +240,151 @@ def run_bffpsv18(args, rank, world, dist):
     return out
 
 
+def build_zono_workload():
+    """Discretised GLGM06 problem of config C2 (ISS-shaped, n=270, max_order 10): Omega0 (already reduce_order'ed,
+    GLGM06/post.jl:20), V and Phi.  Host-side preparation only (outside every timed region)."""
+    from oracle import reach_oracle as orc
+    from reachability_jl_b200 import workloads as wl
+    w = wl.iss()
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.phi12_series(np.abs(w.A), w.delta)[2]
+    D = orc.discretize_zonotope(w.A, orc.Box(w.c, w.r), w.delta, w.B, orc.Box(w.cU, w.rU), Phi=Phi, Phi2abs=P2)
+    Om = orc.reduce_order(D.Omega0, w.max_order)
+    N = orc.n_steps_glgm06(w.T, w.delta)
+    return w, D, Om, N
+
+
+def glgm06_algorithmic_bytes_per_step(n, p0, pV, r):
+    """SURVEY.md section 8(d), GLGM06 reduce x2: per reduction 8 n (p_in [score] + p_in [gather/box] + p_out [write])
+    at the steady state p(W) = r n."""
+    pW = r * n
+    return 8.0 * n * ((p0 + pW) * 2 + r * n) + 8.0 * n * ((pW + pV) * 2 + r * n)
+
+
+def run_glgm06(args, rank, world, dist, e2e=True):
+    """C2 on one GPU (a single system does not shard: with N > 1 every rank runs a replica)."""
+    import torch
+    import reachability_jl_b200 as rb
+    w, D, Om, N = build_zono_workload()
+    if args.flow_steps:
+        N = args.flow_steps
+    n, p0, pV, r = w.n, Om.ngens, D.V.ngens, w.max_order
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+    with torch.cuda.stream(stream):
+        ctx = rb.Context(dev, stream=stream.cuda_stream)
+        fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, 0)
+
+        def one_flowpipe():
+            flush.zero_()
+            fp.run()
+
+        for _ in range(args.warmup):
+            one_flowpipe()
+        sampler = ClockSampler(dev)
+        launches0 = ctx.launch_count()
+        _barrier(dist, world)
+        torch.cuda.synchronize()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        tt = dict(gemm_ms=0.0, gemm_flops=0.0, reduce_ms=0.0, gemm_launches=0)
+        for _ in range(args.steps):
+            one_flowpipe()
+            t = fp.timing()
+            for key in tt:
+                tt[key] += t[key]
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        _barrier(dist, world)
+        clocks = sampler.stop()
+        ms = _max_over_ranks(dist, world, ev0.elapsed_time(ev1), dev)
+        launches = ctx.launch_count() - launches0 + args.steps
+        p = fp.ngens()
+        pmax = int(p.max())
+        fp.close()
+        # ---- end to end: host buffers in, all N zonotopes back in host memory (what reach_inhomog! fills) ----
+        e2e_obj = None
+        if e2e and not args.no_e2e:
+            hC = pinned((n, N))
+            hG = pinned((n, pmax, N))
+            hPhi = pinned((n, n)); hPhi[:] = D.Phi
+            hG0 = pinned((n, p0)); hG0[:] = Om.G
+            hGV = pinned((n, pV)); hGV[:] = D.V.G
+
+            def one_e2e():
+                f2 = ctx.glgm06(hPhi, Om.c, hG0, N, r, D.V.c, hGV, 0)
+                f2.run()
+                f2.fetch(hC, hG)
+                f2.close()
+
+            one_e2e()
+            e2e_steps = max(1, min(args.steps, 2))
+            _barrier(dist, world)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                one_e2e()
+            torch.cuda.synchronize()
+            e2e_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
+            e2e_obj = {"value": world * e2e_steps * (N - 1) / e2e_s, "unit": "flowpipe steps/s",
+                       "h2d_bytes_per_step": 8 * (n * n + n * (p0 + pV) + 2 * n),
+                       "d2h_bytes_per_step": int(8 * n * (int(p.sum()) + N)), "steps": e2e_steps,
+                       "api": "reach_glgm06_create + reach_glgm06_run + reach_flowpipe_fetch (pinned host buffers; every "
+                              "zonotope of the flowpipe copied back, as reach_inhomog! materialises them)"}
+        ctx.close()
+    if rank != 0:
+        return None
+    flow_steps = N - 1
+    value = world * args.steps * flow_steps / (ms * 1e-3)
+    hbm, hbm_src = _peaks()
+    alg_bytes = glgm06_algorithmic_bytes_per_step(n, p0, pV, r) * flow_steps * args.steps
+    red_s = tt["reduce_ms"] * 1e-3
+    achieved = alg_bytes / red_s / 1e9 if red_s > 0 else None
+    return {
+        "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w.name}: n={n}, m={w.m}, GLGM06 max_order={r}, delta={w.delta}, T={w.T}, N={N} reach sets per "
+                               f"bench step, p0={p0}, pV={pV}, {pmax} generators per reach set",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (a single system does not shard)",
+                   "l2": "256 MB L2 flush between timed iterations; the flowpipe written per iteration (11.7 GB) exceeds L2"},
+        "e2e": e2e_obj,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
+                     "traffic": None,
+                     "kernel": "apply_step_kernel + rank_lists_kernel (the two Girard reductions of a step: selection, gather, box)",
+                     "launches": int(2 * flow_steps * args.steps), "kernel_ms_total": tt["reduce_ms"],
+                     "kernel_share_of_step": tt["reduce_ms"] / ms,
+                     "peak_source": hbm_src,
+                     "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
+                     "second_kernel": {"kernel": "gemm_dmma_kernel<.,true> (Phi^s * stacked [G0|GV|c0|cV], left multiplication)",
+                                       "bound": "tensor", "achieved": tt["gemm_flops"] / (tt["gemm_ms"] * 1e-3) / 1e12 if tt["gemm_ms"] else None,
+                                       "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "kernel_ms_total": tt["gemm_ms"],
+                                       "launches": int(tt["gemm_launches"])}},
+    }
+
+
+def cpu_sample_glgm06(D, Om, r, n_steps):
+    from oracle import reach_oracle as orc
+    t0 = time.perf_counter()
+    orc.glgm06_reach_inhomog(Om, D.V, D.Phi, n_steps, r)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_glgm06(target_s=12.0):
+    w, D, Om, N = build_zono_workload()
+    per = cpu_sample_glgm06(D, Om, w.max_order, 31) / 30
+    n_cpu = int(max(31, min(N, target_s / max(per, 1e-9))))
+    t = cpu_sample_glgm06(D, Om, w.max_order, n_cpu)
+    return {"value": (n_cpu - 1) / t, "unit": "flowpipe steps/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"first {n_cpu} of {N} reach sets of {w.name} (loop only, Omega0/V/Phi supplied), numpy+BLAS oracle port of "
+                      "reach_inhomog! + reduce_order", "host_cpus": os.cpu_count()}
+
+
 def _as_tensor(ptr, count, dev):
     """Zero-copy torch view of a device buffer owned by the library."""
     import torch
@@ -297,9 +442,39 @@ def cpu_baseline_for(args, target_s=12.0):
             "host_cpus": os.cpu_count()}
 
 
+def run_reference_glgm06(args, rank, world):
+    if rank != 0:
+        return None
+    w, D, Om, N = build_zono_workload()
+    per = cpu_sample_glgm06(D, Om, w.max_order, 31) / 30
+    n_cpu = int(max(31, min(N, 4.0 / max(per, 1e-9))))
+    for _ in range(args.warmup):
+        cpu_sample_glgm06(D, Om, w.max_order, min(n_cpu, 20))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample_glgm06(D, Om, w.max_order, n_cpu)
+    t = time.perf_counter() - t0
+    value = args.steps * (n_cpu - 1) / t
+    cores = cpu_threads()
+    sample = f"each bench step = first {n_cpu} of {N} reach sets of {w.name} (loop only), oracle port, {cores} BLAS threads"
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w.name}: n={w.n}, m={w.m}, GLGM06 max_order={w.max_order}, delta={w.delta}, T={w.T}, N={N}",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "flowpipe steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "flowpipe steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return None
+    if args.workload == "C2":
+        return run_reference_glgm06(args, rank, world)
     w, D, N = build_box_workload(args.workload)
     per = cpu_sample_bffpsv18(D, 6) / 5
     n_cpu = int(max(6, min(N, 4.0 / max(per, 1e-9))))       # ~4 s per bench step
@@ -329,7 +504,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C3", choices=["C1", "C3"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the second headline workload (C2 GLGM06) summary")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
@@ -348,12 +524,22 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
-    out = run_bffpsv18(args, rank, world, dist)
+    if args.workload == "C2":
+        out = run_glgm06(args, rank, world, dist)
+    else:
+        out = run_bffpsv18(args, rank, world, dist)
     if out is not None:
         if args.flow_steps:
             out["config"]["truncated"] = f"PROFILING RUN: flowpipe truncated to {args.flow_steps} reach sets"
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_for(args)
+            out["cpu_baseline"] = cpu_baseline_glgm06() if args.workload == "C2" else cpu_baseline_for(args)
+        if world == 1 and args.workload == "C3" and not args.no_secondary and not args.flow_steps:
+            # the metric names two configurations: the n=270 GLGM06 one rides along as a summary object
+            sec = run_glgm06(args, rank, world, dist)
+            keep = ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "gpu_launches")
+            out["glgm06_c2"] = {k: sec[k] for k in keep}
+            if not args.no_cpu_baseline:
+                out["glgm06_c2"]["cpu_baseline"] = cpu_baseline_glgm06()
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -9,6 +9,7 @@ from oracle import reach_oracle as orc
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 check = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 w = wl.iss()
 t0 = time.time()
 Phi = orc.exp_Adelta(w.A, w.delta)
@@ -18,7 +19,7 @@ Om = orc.reduce_order(D.Omega0, w.max_order)
 print("discretize (oracle, host)", round(time.time() - t0, 2), "s; p0", Om.ngens, "pV", D.V.ngens, flush=True)
 with rb.Context(0) as ctx:
     fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, w.max_order, D.V.c, D.V.G, 0)
-    for it in range(3):
+    for it in range(reps):
         l0 = ctx.launch_count()
         fp.run()
         t = fp.timing()
