@@ -104,17 +104,22 @@ REACH_API int32_t reach_boxplan_timing(reach_boxplan* plan, double* run_ms, doub
 REACH_API void reach_boxplan_destroy(reach_boxplan* plan);
 /* check mode, dense check_blocks (BFFPSV18/check_blocks.jl:105-183) for a half-space property
  * is_contained_in(LinearConstraint(ell, bound)) already mapped to `rows` (partitions.jl:33-46).
+ * The states stay lazy per block (check_blocks.jl:146-156), so the support function is separable over the blocks of
+ * `:blocks`: block_sizes[0..nblocks) groups `rows` into those blocks, in order (NULL: every row is its own block).
+ * eager != 0: stop at the first violation (`:eager_checking`).
  * violation: first violating step (1-based) or 0 (check_blocks.jl:116). */
 REACH_API int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
                              const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
                              const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
-                             const double* ell, double bound, int32_t eager, int64_t* violation);
+                             int64_t nblocks, const int32_t* block_sizes, const double* ell, double bound, int32_t eager,
+                             int64_t* violation);
 /* output_function branch (reach_blocks.jl:152-155,197-199; reach.jl:73-82): stored set is
- * box_approximation(Mout * CPA(Xhat_k)); Mout is q x nrows. centers/radii: q x N. */
+ * box_approximation(Mout * CPA(Xhat_k)); Mout is q x nrows (q <= 8), block_sizes as above. centers/radii: q x N. */
 REACH_API int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
                                   const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
                                   const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
-                                  int64_t q, const double* Mout, int64_t ldm, double* centers, double* radii);
+                                  int64_t nblocks, const int32_t* block_sizes, int64_t q, const double* Mout, int64_t ldm,
+                                  double* centers, double* radii);
 
 /* ---- GLGM06: reach_homog! / reach_inhomog! (GLGM06/reach.jl:5-62) -------------------------------------- */
 /* flags */

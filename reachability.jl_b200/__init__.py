@@ -7,4 +7,6 @@ Only what the path needs: ``csrc/`` (CUDA kernels + the C ABI of include/reach.h
 from ._lib import ReachError, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
 from .backend import Context, BoxPlan, Flowpipe, Ensemble  # noqa: F401
 
+from . import api  # noqa: F401,E402
+
 __version__ = "0.1.0"

@@ -47,8 +47,8 @@ _SIGNATURES = {
     "reach_boxplan_device_results": [vp, C.POINTER(c_double_p), C.POINTER(c_double_p)],
     "reach_boxplan_timing": [vp, c_double_p, c_double_p, c_int64_p, c_double_p],
     "reach_boxplan_destroy": [vp],
-    "reach_bffpsv18_check": _BOX_ARGS + [c_double_p, f64, i32, c_int64_p],
-    "reach_bffpsv18_output_map": _BOX_ARGS + [i64, c_double_p, i64, c_double_p, c_double_p],
+    "reach_bffpsv18_check": _BOX_ARGS + [i64, c_int32_p, c_double_p, f64, i32, c_int64_p],
+    "reach_bffpsv18_output_map": _BOX_ARGS + [i64, c_int32_p, i64, c_double_p, i64, c_double_p, c_double_p],
     "reach_glgm06_create": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
                             i64, i64, i64, i32, C.POINTER(vp)],
     "reach_glgm06_run": [vp],

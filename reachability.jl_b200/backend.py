@@ -163,22 +163,36 @@ class Context:
     def boxplan(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None) -> "BoxPlan":
         return BoxPlan(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
 
-    def bffpsv18_check(self, Phi, c0, r0, N, ell, bound, MU=None, cU=None, rU=None, rpsi=None, rows=None, eager=True):
+    @staticmethod
+    def _blocks(block_sizes, nrows):
+        if block_sizes is None:
+            return 0, None
+        bs = np.ascontiguousarray(block_sizes, dtype=np.int32)
+        assert int(bs.sum()) == nrows
+        return len(bs), bs
+
+    def bffpsv18_check(self, Phi, c0, r0, N, ell, bound, MU=None, cU=None, rU=None, rpsi=None, rows=None, eager=True,
+                       block_sizes=None):
+        """First violating step (1-based) of  ell . x <= bound, or 0.  `block_sizes` groups `rows` into blocks."""
         keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
         ell = fvec(ell)
         assert len(ell) == nrows
+        nb, bs = self._blocks(block_sizes, nrows)
         v = C.c_int64()
-        self._check(self.lib.reach_bffpsv18_check(self._h, *args, dptr(ell), float(bound), int(bool(eager)), C.byref(v)))
+        self._check(self.lib.reach_bffpsv18_check(self._h, *args, nb, iptr(bs), dptr(ell), float(bound), int(bool(eager)),
+                                                  C.byref(v)))
         return int(v.value)
 
-    def bffpsv18_output_map(self, Phi, c0, r0, N, Mout, MU=None, cU=None, rU=None, rpsi=None, rows=None):
+    def bffpsv18_output_map(self, Phi, c0, r0, N, Mout, MU=None, cU=None, rU=None, rpsi=None, rows=None, block_sizes=None):
         keep, args, nrows = self._box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N)
         Mout = fmat(Mout)
         q = Mout.shape[0]
         assert Mout.shape[1] == nrows
+        nb, bs = self._blocks(block_sizes, nrows)
         centers = np.zeros((q, N), order="F")
         radii = np.zeros((q, N), order="F")
-        self._check(self.lib.reach_bffpsv18_output_map(self._h, *args, q, dptr(Mout), q, dptr(centers), dptr(radii)))
+        self._check(self.lib.reach_bffpsv18_output_map(self._h, *args, nb, iptr(bs), q, dptr(Mout), q, dptr(centers),
+                                                       dptr(radii)))
         return centers, radii
 
     # ---- GLGM06 ----------------------------------------------------------------------------------------

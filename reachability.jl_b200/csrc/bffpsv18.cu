@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "../../include/reach.h"
 #include <algorithm>
+#include <climits>
 
 namespace reach {
 
@@ -31,7 +32,18 @@ struct BoxPlan {
     double run_ms = 0, gemm_ms = 0, gemm_flops = 0;
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
-    // optional check-mode / output-map extras are handled by separate entry points
+    // ---- lazy-state variants: output_function (reach_blocks.jl:152-155,191-199) and check mode
+    //      (check_blocks.jl:105-183).  The states stay lazy per block, so the radius is
+    //      sum_b |M[:, b] P[b, :]| r0 + |M| rW   (support function of a CartesianProductArray is separable per block).
+    int64_t qmap = 0, nchunks = 0;
+    double* Mmap = nullptr;            // qmap x nrows, column-major
+    int32_t *blk_len = nullptr;        // nrows: length of the block starting at row l, 0 if l is not a block start
+    double *zpart = nullptr;           // [s][nchunks][qmap] partial sums of the current stack block
+    double *out_c = nullptr, *out_r = nullptr;   // qmap x N
+    bool check = false, eager = true;
+    double bound = 0.0;
+    long long* viol = nullptr;         // device: first violating step (1-based) or LLONG_MAX
+    long long violation = 0;           // host copy after run
 };
 
 namespace {
@@ -119,7 +131,7 @@ __global__ void scan_block_kernel(int nrows, int m, int64_t Rp, int cnt, int64_t
                                   const double* __restrict__ E, int64_t ldE, const double* __restrict__ bsum,
                                   const double* __restrict__ fsum, const double* __restrict__ cU,
                                   const double* __restrict__ rU, double* __restrict__ cW, double* __restrict__ rW,
-                                  double* __restrict__ centers, double* __restrict__ radii) {
+                                  double* __restrict__ centers, double* __restrict__ radii, int add_b) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nrows) return;
     double cw = cW[l], rw = rW[l];
@@ -129,7 +141,7 @@ __global__ void scan_block_kernel(int nrows, int m, int64_t Rp, int cnt, int64_t
         const double a = E[idx + (int64_t)m * ldE];
         const double b = bsum[idx];
         centers[q * nrows + l] = a + cw;
-        radii[q * nrows + l] = b + rw;
+        radii[q * nrows + l] = add_b ? b + rw : rw;      // lazy-state variants keep rW_k alone (|M| rW term)
         if (m > 0 && q + 1 < N) {
             double dc = 0.0, dr = 0.0;
             for (int u = 0; u < m; ++u) {
@@ -143,6 +155,89 @@ __global__ void scan_block_kernel(int nrows, int m, int64_t Rp, int cnt, int64_t
     }
     cW[l] = cw;
     rW[l] = rw;
+}
+
+// zpart[(j * nchunks + chunk) * qmap + i] = sum_{c in chunk} r0[c] * sum_b | sum_{l in b} M[i, l] S[j Rp + l, c] |
+// CTA = one power j x one chunk of MAP_CHUNK columns; threads stride the rows (coalesced), products go through shared
+// memory and the first row of every block sums its block (deterministic, no atomics).
+constexpr int MAP_CHUNK = 32;
+constexpr int MAP_Q = 8;
+__global__ void __launch_bounds__(256) block_abs_map_kernel(int nrows, int n, int64_t Rp, int q, int nchunks,
+                                                            const double* __restrict__ S, int64_t lds,
+                                                            const double* __restrict__ M, const int32_t* __restrict__ blk_len,
+                                                            const double* __restrict__ r0, double* __restrict__ zpart) {
+    extern __shared__ double sm[];              // [q][nrows] products, then [256][MAP_Q] reduction
+    const int chunk = blockIdx.x, j = blockIdx.y, tid = threadIdx.x;
+    double acc[MAP_Q];
+#pragma unroll
+    for (int i = 0; i < MAP_Q; ++i) acc[i] = 0.0;
+    const int c1 = min(n, (chunk + 1) * MAP_CHUNK);
+    for (int c = chunk * MAP_CHUNK; c < c1; ++c) {
+        const double* col = S + (int64_t)c * lds + (int64_t)j * Rp;
+        const double rc = r0[c];
+        for (int l = tid; l < nrows; l += 256) {
+            const double v = col[l];
+#pragma unroll
+            for (int i = 0; i < MAP_Q; ++i)
+                if (i < q) sm[i * nrows + l] = M[i + (int64_t)l * q] * v;
+        }
+        __syncthreads();
+        for (int l = tid; l < nrows; l += 256) {
+            const int len = blk_len[l];
+            if (len > 0) {
+#pragma unroll
+                for (int i = 0; i < MAP_Q; ++i)
+                    if (i < q) {
+                        double t = 0.0;
+                        for (int u = 0; u < len; ++u) t += sm[i * nrows + l + u];
+                        acc[i] = fma(fabs(t), rc, acc[i]);
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    double* red = sm;
+#pragma unroll
+    for (int i = 0; i < MAP_Q; ++i) red[tid * MAP_Q + i] = acc[i];
+    __syncthreads();
+    if (tid < q) {
+        double t = 0.0;
+        for (int u = 0; u < 256; ++u) t += red[u * MAP_Q + tid];
+        zpart[((int64_t)j * nchunks + chunk) * q + tid] = t;
+    }
+}
+
+// Reach sets of the powers [first_col, first_col + cnt): centre = M c_k, radius = Z + |M| rW_k   (reach_blocks.jl:197-199);
+// check mode: rho(l, X_k) = centre + radius > bound  =>  violation (check_property.jl, check_blocks.jl:158-164).
+__global__ void __launch_bounds__(128) map_finish_kernel(int nrows, int q, int nchunks, int cnt, int64_t first_col,
+                                                         const double* __restrict__ M, const double* __restrict__ centers,
+                                                         const double* __restrict__ rwk, const double* __restrict__ zpart,
+                                                         double* __restrict__ out_c, double* __restrict__ out_r, int check,
+                                                         double bound, long long* viol) {
+    __shared__ double sc[128], sr[128];
+    const int j = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
+    if (j >= cnt) return;
+    const int64_t col = first_col + j;
+    double a = 0.0, b = 0.0;
+    for (int l = tid; l < nrows; l += 128) {
+        const double m = M[i + (int64_t)l * q];
+        a = fma(m, centers[col * nrows + l], a);
+        b = fma(fabs(m), rwk[col * nrows + l], b);
+    }
+    sc[tid] = a; sr[tid] = b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o) { sc[tid] += sc[tid + o]; sr[tid] += sr[tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double z = 0.0;
+        if (zpart) for (int ch = 0; ch < nchunks; ++ch) z += zpart[((int64_t)j * nchunks + ch) * q + i];
+        const double c = sc[0], r = z + sr[0];
+        out_c[col * q + i] = c;
+        out_r[col * q + i] = r;
+        if (check && c + r > bound) atomicMin(viol, (long long)(col + 1));
+    }
 }
 
 double* dvec_alloc(Ctx* ctx, int64_t len, const double* host) {
@@ -232,6 +327,8 @@ void boxplan_destroy(BoxPlan* P) {
     for (double* v : {P->c0, P->r0, P->rpsi, P->cU, P->rU, P->bsum, P->fsum, P->cW, P->rW, P->centers, P->radii})
         if (v) cudaFree(v);
     if (P->rows) cudaFree(P->rows);
+    for (void* v : {(void*)P->Mmap, (void*)P->blk_len, (void*)P->zpart, (void*)P->out_c, (void*)P->out_r, (void*)P->viol})
+        if (v) cudaFree(v);
     for (cudaEvent_t e : P->evs) cudaEventDestroy(e);
     delete P;
 }
@@ -246,6 +343,27 @@ void boxplan_run(BoxPlan* P) {
         P->rW);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;
+    if (P->qmap) {
+        // k = 1 uses the boxed Xhat0 (reach_blocks.jl:152-155, check_blocks.jl:118-124): centre M c0[R], radius |M| r0[R]
+        const long long none = LLONG_MAX;
+        REACH_CUDA(cudaMemcpyAsync(P->viol, &none, sizeof(none), cudaMemcpyHostToDevice, st));
+        dim3 gf(1u, (unsigned)P->qmap);
+        map_finish_kernel<<<gf, 128, 0, st>>>((int)nrows, (int)P->qmap, 0, 1, 0, P->Mmap, P->centers, P->radii, nullptr,
+                                              P->out_c, P->out_r, P->check ? 1 : 0, P->bound, P->viol);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        P->violation = 0;
+        if (P->check && P->eager) {
+            long long v;
+            REACH_CUDA(cudaMemcpyAsync(&v, P->viol, sizeof(v), cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+            if (v != LLONG_MAX) {
+                P->violation = v;
+                P->run_ms = 0;
+                return;
+            }
+        }
+    }
     P->gemm_launches = 0;
     P->gemm_flops = 0;
     size_t ev_used = 0;
@@ -317,10 +435,36 @@ void boxplan_run(BoxPlan* P) {
             REACH_CUDA(cudaGetLastError());
             scan_block_kernel<<<(unsigned)ceil_div(nrows, 64), 64, 0, st>>>(
                 (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, P->E.p, P->E.ld, P->bsum, P->fsum, P->cU, P->rU, P->cW,
-                P->rW, P->centers, P->radii);
+                P->rW, P->centers, P->radii, P->qmap ? 0 : 1);
             REACH_CUDA(cudaGetLastError());
             ctx->launches += 2;
+            if (P->qmap) {
+                const size_t smem = sizeof(double) * std::max<size_t>((size_t)P->qmap * nrows, 256 * MAP_Q);
+                dim3 gm((unsigned)P->nchunks, (unsigned)cnt);
+                block_abs_map_kernel<<<gm, 256, smem, st>>>((int)nrows, (int)n, Rp, (int)P->qmap, (int)P->nchunks, P->S[cur].p,
+                                                           P->S[cur].ld, P->Mmap, P->blk_len, P->r0, P->zpart);
+                dim3 gf((unsigned)cnt, (unsigned)P->qmap);
+                map_finish_kernel<<<gf, 128, 0, st>>>((int)nrows, (int)P->qmap, (int)P->nchunks, (int)cnt, b * s + 1, P->Mmap,
+                                                      P->centers, P->radii, P->zpart, P->out_c, P->out_r, P->check ? 1 : 0,
+                                                      P->bound, P->viol);
+                REACH_CUDA(cudaGetLastError());
+                ctx->launches += 2;
+                if (P->check && P->eager) {        // eager_checking: stop at the first stack block with a violation
+                    long long v;
+                    REACH_CUDA(cudaMemcpyAsync(&v, P->viol, sizeof(v), cudaMemcpyDeviceToHost, st));
+                    REACH_CUDA(cudaStreamSynchronize(st));
+                    if (v != LLONG_MAX) break;
+                }
+            }
             cur ^= 1;
+        }
+    }
+    if (P->qmap) {
+        if (P->check) {
+            long long v;
+            REACH_CUDA(cudaMemcpyAsync(&v, P->viol, sizeof(v), cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+            P->violation = (v == LLONG_MAX) ? 0 : v;
         }
     }
     REACH_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -334,6 +478,58 @@ void boxplan_run(BoxPlan* P) {
         REACH_CUDA(cudaEventElapsedTime(&t, P->evs[i], P->evs[i + 1]));
         P->gemm_ms += t;
     }
+}
+
+// Attach an output map (q x nrows, column-major, ldm) with the block structure of `rows` (block_sizes == NULL: 1-D
+// blocks); check != 0 turns it into the half-space check  ell . x <= bound  (q must be 1).
+void boxplan_attach_map(BoxPlan* P, int64_t q, const double* M, int64_t ldm, int64_t nblocks, const int32_t* block_sizes,
+                        bool check, double bound, bool eager) {
+    Ctx* ctx = P->ctx;
+    REACH_REQUIRE(q >= 1 && M && ldm >= q, "bffpsv18: bad output map");
+    if (q > MAP_Q) throw Error(REACH_EUNSUPPORTED, "bffpsv18: output maps with more than 8 rows are not supported in this build");
+    const int64_t nrows = P->nrows;
+    std::vector<int32_t> blen(nrows, 0);
+    if (block_sizes) {
+        int64_t o = 0;
+        for (int64_t b = 0; b < nblocks; ++b) {
+            REACH_REQUIRE(block_sizes[b] >= 1 && o + block_sizes[b] <= nrows, "bffpsv18: block sizes do not match the rows");
+            blen[o] = block_sizes[b];
+            o += block_sizes[b];
+        }
+        REACH_REQUIRE(o == nrows, "bffpsv18: block sizes do not cover the rows");
+    } else {
+        for (int64_t l = 0; l < nrows; ++l) blen[l] = 1;
+    }
+    std::vector<double> Mh((size_t)q * nrows);
+    for (int64_t l = 0; l < nrows; ++l)
+        for (int64_t i = 0; i < q; ++i) Mh[i + l * q] = M[i + l * ldm];
+    P->qmap = q;
+    P->nchunks = ceil_div(P->n, MAP_CHUNK);
+    P->check = check; P->bound = bound; P->eager = eager;
+    cudaStream_t st = ctx->stream;
+    REACH_CUDA(cudaMalloc(&P->Mmap, sizeof(double) * q * nrows));
+    REACH_CUDA(cudaMalloc(&P->blk_len, sizeof(int32_t) * nrows));
+    REACH_CUDA(cudaMalloc(&P->zpart, sizeof(double) * (size_t)P->s * P->nchunks * q));
+    REACH_CUDA(cudaMalloc(&P->out_c, sizeof(double) * q * P->N));
+    REACH_CUDA(cudaMalloc(&P->out_r, sizeof(double) * q * P->N));
+    REACH_CUDA(cudaMalloc(&P->viol, sizeof(long long)));
+    REACH_CUDA(cudaMemsetAsync(P->out_c, 0, sizeof(double) * q * P->N, st));
+    REACH_CUDA(cudaMemsetAsync(P->out_r, 0, sizeof(double) * q * P->N, st));
+    REACH_CUDA(cudaMemcpyAsync(P->Mmap, Mh.data(), sizeof(double) * q * nrows, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(cudaMemcpyAsync(P->blk_len, blen.data(), sizeof(int32_t) * nrows, cudaMemcpyHostToDevice, st));
+    const size_t smem = sizeof(double) * std::max<size_t>((size_t)q * nrows, 256 * MAP_Q);
+    if (smem > 200 * 1024) throw Error(REACH_EUNSUPPORTED, "bffpsv18: output map too large for shared memory (q * nrows > 25600)");
+    REACH_CUDA(cudaFuncSetAttribute(block_abs_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    REACH_CUDA(cudaStreamSynchronize(st));
+}
+
+void boxplan_fetch_map(BoxPlan* P, double* centers, double* radii, int64_t* violation) {
+    Ctx* ctx = P->ctx;
+    const size_t bytes = sizeof(double) * (size_t)P->qmap * (size_t)P->N;
+    if (centers) REACH_CUDA(cudaMemcpyAsync(centers, P->out_c, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (radii) REACH_CUDA(cudaMemcpyAsync(radii, P->out_r, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    REACH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (violation) *violation = P->violation;
 }
 
 void boxplan_fetch(BoxPlan* P, double* centers, double* radii) {

@@ -12,7 +12,9 @@ void boxplan_run(BoxPlan* P);
 void boxplan_fetch(BoxPlan* P, double* centers, double* radii);
 void boxplan_results(BoxPlan* P, double** c, double** r);
 void boxplan_timing(BoxPlan* P, double* run_ms, double* gemm_ms, int64_t* launches, double* flops);
-Ctx* boxplan_ctx(BoxPlan* P);
+void boxplan_attach_map(BoxPlan* P, int64_t q, const double* M, int64_t ldm, int64_t nblocks, const int32_t* block_sizes,
+                        bool check, double bound, bool eager);
+void boxplan_fetch_map(BoxPlan* P, double* centers, double* radii, int64_t* violation);
 Ctx* ctx_of(reach_ctx* h);
 }  // namespace reach
 
@@ -102,6 +104,52 @@ int32_t reach_bffpsv18_boxes(reach_ctx* h, int64_t n, const double* Phi, int64_t
     }
     boxplan_destroy(p);
     if (steps_done) *steps_done = N;
+    return REACH_OK;
+    GUARD_END(ctx)
+}
+
+int32_t reach_bffpsv18_check(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                             const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                             const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                             int64_t nblocks, const int32_t* block_sizes, const double* ell, double bound, int32_t eager,
+                             int64_t* violation) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    GUARD_BEGIN(ctx)
+    REACH_REQUIRE(ell && violation, "reach_bffpsv18_check: ell and violation are required");
+    BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+    try {
+        boxplan_attach_map(p, 1, ell, 1, nblocks, block_sizes, true, bound, eager != 0);
+        boxplan_run(p);
+        boxplan_fetch_map(p, nullptr, nullptr, violation);
+    } catch (...) {
+        boxplan_destroy(p);
+        throw;
+    }
+    boxplan_destroy(p);
+    return REACH_OK;
+    GUARD_END(ctx)
+}
+
+int32_t reach_bffpsv18_output_map(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
+                                  const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
+                                  const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                                  int64_t nblocks, const int32_t* block_sizes, int64_t q, const double* Mout, int64_t ldm,
+                                  double* centers, double* radii) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    GUARD_BEGIN(ctx)
+    REACH_REQUIRE(centers && radii, "reach_bffpsv18_output_map: output buffers required");
+    BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+    try {
+        boxplan_attach_map(p, q, Mout, ldm, nblocks, block_sizes, false, 0.0, false);
+        boxplan_run(p);
+        boxplan_fetch_map(p, centers, radii, nullptr);
+    } catch (...) {
+        boxplan_destroy(p);
+        throw;
+    }
+    boxplan_destroy(p);
     return REACH_OK;
     GUARD_END(ctx)
 }

@@ -1,0 +1,134 @@
+"""GPU: the host-side mirror of the reference interface (`solve`, `BFFPSV18`, `GLGM06`, options, result containers),
+written after /root/reference/test/Reachability/solve_continuous.jl.  Values are checked against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import reach_oracle as orc
+from reachability_jl_b200 import ReachError
+from reachability_jl_b200.api import (BFFPSV18, CLCCS, GLGM06, IVP, LCS, BallInf, Ball2Stub, ConstantInput, Hyperrectangle,
+                                      Interval, LinearConstraint, Options, Singleton, dim, is_contained_in, project, set_of,
+                                      solve, time_end, time_start)
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+A = np.array([[0.0509836, 0.168159, 0.95246, 0.33644],
+              [0.42377, 0.67972, 0.129232, 0.126662],
+              [0.518654, 0.981313, 0.489854, 0.588326],
+              [0.38318, 0.616014, 0.518412, 0.778765]])
+B = np.array([[0.866688, 0.771231], [0.065935, 0.349839], [0.109643, 0.904222], [0.292474, 0.227857]])
+X0 = BallInf(np.ones(4), 0.1)
+
+
+def test_default_options_all_variables():                                   # solve_continuous.jl:15-17
+    s = solve(IVP(LCS(A), X0), T=0.1)
+    rs = s.flowpipes[0].reachsets
+    assert len(rs) == 10 and dim(set_of(rs[0])) == 4 and isinstance(s.options, Options)
+    assert all(isinstance(b, Interval) for b in set_of(rs[0]).array)        # default 1-D partition -> Interval blocks
+    D = orc.discretize_box(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.01)
+    Co, Ro = orc.bffpsv18_reach(D, 10)
+    for k in (0, 4, 9):
+        lo = np.array([b.lo for b in set_of(rs[k]).array])
+        hi = np.array([b.hi for b in set_of(rs[k]).array])
+        assert_close(lo, Co[k] - Ro[k], "lo")
+        assert_close(hi, Co[k] + Ro[k], "hi")
+    assert time_start(rs[0]) == 0.0 and abs(time_end(rs[9]) - 0.1) < 1e-12 and time_start(rs[3]) == time_end(rs[2])
+
+
+def test_vars_and_custom_partition():                                       # :20-29
+    s = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[1, 2], [3, 4]]))
+    rs0 = s.flowpipes[0].reachsets[0]
+    assert dim(set_of(rs0)) == 4 and rs0.dimensions == [1, 2, 3, 4]
+    assert all(type(b) is Hyperrectangle for b in set_of(rs0).array)
+    s = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3]))
+    rs0 = s.flowpipes[0].reachsets[0]
+    assert dim(set_of(rs0)) == 2 and rs0.dimensions == [1, 3]
+
+
+def test_dimension_mismatch_is_an_assertion_error():                        # :32
+    with pytest.raises(AssertionError):
+        solve(IVP(LCS(A), BallInf(np.ones(3), 0.1)), T=0.1)
+
+
+def test_option_validation():
+    with pytest.raises(ValueError):
+        BFFPSV18(δ=-1.0)
+    with pytest.raises(ValueError):
+        BFFPSV18(partition=[[1, 3], [2, 4]])
+    with pytest.raises(ValueError):
+        BFFPSV18(bogus=1)
+    with pytest.raises(ValueError):
+        solve(IVP(LCS(A), X0), Options())                                   # T is mandatory
+    with pytest.raises(ValueError):
+        solve(IVP(LCS(A), X0), Options(T=0.1, mode="check"))                # check mode needs a property
+    with pytest.raises(ValueError):
+        solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(discretization="sideways"))
+
+
+def test_check_mode_known_answers():                                        # :49-75
+    prop = is_contained_in(LinearConstraint([1., 1., 0., 0.], 2.))
+    s = solve(IVP(LCS(A), X0), Options(T=0.1, mode="check", property=prop), op=BFFPSV18(vars=[1, 2], partition=[[1, 2], [3, 4]]))
+    assert s.violation == 1 and not s.satisfied
+    s = solve(IVP(LCS(A), X0), Options(T=0.1, mode="check", property=prop), op=BFFPSV18(vars=[1, 2, 3], partition=[[1, 2], [3, 4]]))
+    assert s.violation == 1
+    prop = is_contained_in(LinearConstraint([1., -1., 0., 0.], 2.))
+    s = solve(IVP(LCS(A), X0), Options(T=0.1, mode="check", property=prop), op=BFFPSV18(vars=[1, 2, 3], partition=[[1, 2], [3, 4]]))
+    assert s.violation == -1 and s.satisfied
+
+
+def test_projection_matrix_output_function():                               # :82-83
+    M = np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0]])
+    s = solve(IVP(LCS(A), X0), Options(T=1.0, projection_matrix=M), op=BFFPSV18(δ=0.1))
+    rs = s.flowpipes[0].reachsets
+    assert len(rs) == 10 and dim(set_of(rs[0])) == 2
+    D = orc.discretize_box(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.1)
+    Co, Ro = orc.bffpsv18_output_map(D, 10, M, np.arange(4), [1, 1, 1, 1])
+    assert_close(np.array([set_of(r).center for r in rs]), Co, "centres")
+    assert_close(np.array([set_of(r).radius for r in rs]), Ro, "radii")
+
+
+def test_interval_block_option_and_project():                               # :116-120, :41-43
+    s = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[i] for i in range(1, 5)], block_options=Interval))
+    assert all(isinstance(b, Interval) for b in set_of(s.flowpipes[0].reachsets[2]).array)
+    ps = project(s, [0, 1])
+    assert dim(set_of(ps.flowpipes[0].reachsets[0])) == 2
+
+
+def test_affine_system_with_inputs():                                       # :157-163
+    U = Interval(0.99, 1.01) * Interval(0.99, 1.01)
+    for inputs in (ConstantInput(U), U):
+        s = solve(IVP(CLCCS(A, B, None, inputs), X0), T=0.1)
+        rs = s.flowpipes[0].reachsets
+        D = orc.discretize_box(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.01, B, orc.Box(np.ones(2), np.full(2, 0.01)))
+        Co, Ro = orc.bffpsv18_reach(D, 10)
+        lo = np.array([b.lo for b in set_of(rs[9]).array])
+        assert_close(lo, Co[9] - Ro[9], "lo")
+    s2 = solve(IVP(CLCCS(np.array([[0.0, 1.0], [0.0, 0.0]]), np.array([[0.0], [-1.0]]), None, Singleton([1.0])),
+                   BallInf(np.zeros(2), 0.1)), T=1.0)
+    assert len(s2.flowpipes[0].reachsets) == 100
+
+
+def test_glgm06_mirror():                                                   # :186-196
+    for op, kw in ((GLGM06(), {}), (GLGM06(max_order=15), {})):
+        s = solve(IVP(LCS(A), X0), Options(T=0.1), op=op)
+        rs = s.flowpipes[0].reachsets
+        assert len(rs) == 10
+        Dz = orc.discretize_zonotope(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.01)
+        R = orc.glgm06_reach(Dz, 10, op["max_order"])
+        for k in (0, 5, 9):
+            assert_close(set_of(rs[k]).center, R[k].c, "centre")
+            assert_close(set_of(rs[k]).generators, R[k].G, "generators")
+    U = Interval(0.99, 1.01) * Interval(0.99, 1.01)
+    s = solve(IVP(CLCCS(A, B, None, U), X0), Options(T=0.1), op=GLGM06())
+    Dz = orc.discretize_zonotope(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.01, B, orc.Box(np.ones(2), np.full(2, 0.01)))
+    R = orc.glgm06_reach(Dz, 10, 10)
+    rs = s.flowpipes[0].reachsets
+    for k in (0, 1, 9):
+        assert_close(set_of(rs[k]).center, R[k].c, "centre")
+        assert_close(set_of(rs[k]).generators, R[k].G, "generators")
+
+
+def test_unsupported_inputs_raise_instead_of_falling_back():
+    with pytest.raises(ReachError) as ei:
+        solve(IVP(LCS(A), Ball2Stub(np.ones(4), 0.1)), Options(T=0.1), op=GLGM06())     # :199-200 needs LazySets on the host
+    assert ei.value.code == 3
