@@ -1,0 +1,81 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, `torch.distributed` plumbing.
+
+* BFFPSV18: the recurrence `P_k[R_g, :] = P_{k-1}[R_g, :] Φ` only needs the rank's own rows and the replicated Φ, so the
+  rows of interest are sharded in contiguous groups of whole partition blocks (a 2-D block is never split), balanced
+  by row count.  There is NO collective inside the time loop; the boxes are all-gathered once at the end.
+* GLGM06 ensembles (config C5): independent members, sharded by contiguous batch ranges, no collective at all.
+* A single GLGM06 system is not sharded (two latency-bound collectives per reduction at n = 270 would only slow it
+  down): `bench.py --gpus N` runs replicas for that workload.
+
+The compute callable is injected so that the host logic is testable on CPU with the `gloo` backend
+(tests/test_sharding_cpu.py); the product path passes `Context.bffpsv18_boxes` / `Context.ensemble`.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_blocks(block_sizes: Sequence[int], rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) range of blocks owned by `rank`: contiguous, whole blocks, balanced by ROW count (greedy prefix split)."""
+    sizes = np.asarray(block_sizes, dtype=np.int64)
+    total = int(sizes.sum())
+    ends = np.cumsum(sizes)
+    # block b goes to the rank whose row interval [total*r/world, total*(r+1)/world) contains the block's midpoint
+    mids = ends - sizes / 2.0
+    owner = np.minimum((mids * world / max(total, 1)).astype(np.int64), world - 1)
+    mine = np.nonzero(owner == rank)[0]
+    if len(mine) == 0:
+        lo = int(np.searchsorted(owner, rank))
+        return lo, lo
+    return int(mine[0]), int(mine[-1]) + 1
+
+
+def shard_rows(partition: Sequence[Sequence[int]], blocks: Sequence[int], rank: int, world: int) -> np.ndarray:
+    """0-based coordinates (in `blocks` order) of the rows this rank computes.  `partition`/`blocks` are 1-based as
+    in the reference (compute_dimensions.jl:1-15)."""
+    sizes = [len(partition[b - 1]) for b in blocks]
+    lo, hi = shard_blocks(sizes, rank, world)
+    return np.asarray([d - 1 for b in blocks[lo:hi] for d in partition[b - 1]], dtype=np.int32)
+
+
+def shard_batch(batch: int, rank: int, world: int) -> slice:
+    return slice((batch * rank) // world, (batch * (rank + 1)) // world)
+
+
+def allgather_boxes(dist, local: "torch.Tensor", counts: List[int]):
+    """All-gather row-sharded results: `local` is (2, rows_local * N) [centres; radii] on the rank's device; `counts`
+    holds every rank's row count.  Shards are padded to the largest one so that a plain equal-size all-gather (one
+    NCCL ring/NVLS collective over NVLink on GPUs, gloo on CPU) does the job.  Returns (per-rank tensors, N)."""
+    import torch
+    mine = counts[dist.get_rank()]
+    t = torch.tensor([local.shape[1] // mine if mine else 0], dtype=torch.int64, device=local.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)         # a rank may own no rows: learn N from the others
+    N = int(t.item())
+    width = max(counts) * N
+    padded = torch.zeros((2, width), dtype=local.dtype, device=local.device)
+    padded[:, :local.shape[1]] = local
+    out = [torch.empty((2, width), dtype=local.dtype, device=local.device) for _ in counts]
+    dist.all_gather(out, padded)
+    return [o[:, :c * N] for o, c in zip(out, counts)], N
+
+
+def bffpsv18_sharded(compute: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]], partition, blocks, dist, device="cpu"):
+    """Run `compute(rows) -> (centers, radii)` ((rows, N) arrays, column k-1 = step k) on this rank's rows and
+    assemble the full (all rows of `blocks`, N) result on every rank."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    counts = [len(shard_rows(partition, blocks, r, world)) for r in range(world)]
+    rows = shard_rows(partition, blocks, rank, world)
+    if len(rows):
+        C, R = compute(rows)
+        N = C.shape[1]
+        local = torch.from_numpy(np.stack([np.asfortranarray(C).ravel(order="F"), np.asfortranarray(R).ravel(order="F")]))
+    else:
+        local = torch.empty((2, 0), dtype=torch.float64)
+    local = local.to(device)
+    parts, N = allgather_boxes(dist, local, counts)
+    Cs = [p[0].cpu().numpy().reshape((c, N), order="F") for p, c in zip(parts, counts) if c]
+    Rs = [p[1].cpu().numpy().reshape((c, N), order="F") for p, c in zip(parts, counts) if c]
+    return np.vstack(Cs), np.vstack(Rs)

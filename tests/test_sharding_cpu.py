@@ -1,0 +1,98 @@
+"""CPU (gloo, world_size 2 and 3): the multi-GPU host logic -- row-block sharding aligned to partition blocks, the
+single end-of-run all-gather and the reassembly order.  The per-rank compute is the oracle
+restricted to the rank's rows, so the assembled result must equal the unsharded oracle run (up to BLAS rounding)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import reach_oracle as orc
+from reachability_jl_b200 import sharding
+
+
+def test_shard_blocks_balanced_and_whole():
+    sizes = [2] * 503
+    seen = []
+    for world in (1, 2, 4, 8, 3):
+        got = [sharding.shard_blocks(sizes, r, world) for r in range(world)]
+        assert got[0][0] == 0 and got[-1][1] == len(sizes)
+        for a, b in zip(got, got[1:]):
+            assert a[1] == b[0]                    # contiguous, no gaps, no overlap
+        rows = [2 * (hi - lo) for lo, hi in got]
+        assert max(rows) - min(rows) <= 2          # balanced by rows up to one block
+        seen.append(rows)
+    # ragged blocks: never split a block, every block owned exactly once
+    sizes = [1, 4, 2, 2, 7, 1, 1, 3]
+    for world in (2, 3, 5, 8, 16):
+        got = [sharding.shard_blocks(sizes, r, world) for r in range(world)]
+        owned = [b for lo, hi in got for b in range(lo, hi)]
+        assert owned == list(range(len(sizes)))
+
+
+def test_shard_rows_follow_partition():
+    partition = [[1, 2], [3, 4], [5], [6, 7, 8]]
+    blocks = [1, 3, 4]
+    r0 = sharding.shard_rows(partition, blocks, 0, 2)
+    r1 = sharding.shard_rows(partition, blocks, 1, 2)
+    assert list(r0) + list(r1) == [0, 1, 4, 5, 6, 7]
+    assert list(sharding.shard_rows(partition, blocks, 0, 1)) == [0, 1, 4, 5, 6, 7]
+
+
+def test_shard_batch_covers_everything():
+    for batch, world in ((4096, 8), (10, 3), (2, 4)):
+        idx = [i for r in range(world) for i in range(batch)[sharding.shard_batch(batch, r, world)]]
+        assert idx == list(range(batch))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.random.default_rng(0)
+        n, m, N = 14, 2, 25
+        A = g.standard_normal((n, n)) / np.sqrt(n) - np.eye(n)
+        D = orc.discretize_box(A, orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1), 0.02,
+                               g.standard_normal((n, m)), orc.Box(np.zeros(m), np.ones(m)))
+        partition = [[1, 2], [3, 4], [5], [6, 7, 8], [9, 10], [11, 12], [13, 14]]
+        blocks = [1, 2, 4, 5, 7]
+
+        def compute(rows):
+            C, R = orc.bffpsv18_reach(D, N, rows)
+            return C.T, R.T
+
+        C, R = sharding.bffpsv18_sharded(compute, partition, blocks, dist)
+        rows_all = [d - 1 for b in blocks for d in partition[b - 1]]
+        Cf, Rf = orc.bffpsv18_reach(D, N, rows_all)
+        # BLAS may block a row subset differently from the full matrix: equality up to rounding, far inside 1e-10
+        ok = (C.shape == Cf.T.shape and np.allclose(C, Cf.T, rtol=1e-13, atol=1e-15) and np.allclose(R, Rf.T, rtol=1e-13, atol=1e-15))
+        if rank == 0:
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_row_sharded_flowpipe_equals_unsharded(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
