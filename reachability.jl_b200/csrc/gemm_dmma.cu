@@ -13,6 +13,7 @@
 // the m8n8k4 fragment loads (lane -> (k = lane%4, row = lane/4)) hit 16 distinct 8-byte bank slots per
 // half-warp: slot = 4*(lane%4) + lane/4 (mod 16).
 #include "common.cuh"
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 namespace reach {
 
@@ -58,6 +59,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tiled TMA load through a tensor map (coordinates: c0 = innermost = k, c1 = row)
+__device__ __forceinline__ void tma_2d_g2s(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -83,16 +92,21 @@ struct GemmParams {
 //                     contiguous -> C[row*ldc + col].  With A = X^T (X n x Q column-major generators) and
 //                     Bt = Phi^s column-major this is  Y = Phi^s * X  with Y column-major again: the left
 //                     multiplication of GLGM06 (linear_map, GLGM06/reach.jl:16,48,54) with no transposes.
-//                     The A tile is moved as 128 bulk copies of 128 B into rows of pitch BK+4 = 20 doubles, so the
-//                     fragment load (row = lane/4, k = lane%4) hits slot 4*(lane/4) + lane%4 (mod 16): conflict-free.
+//                     The 128 x 16 A tile is ONE 2-D tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) per stage
+//                     with the 128-byte swizzle; out-of-range rows / k are zero-filled by the TMA unit.  (128 separate
+//                     128-byte bulk copies per stage starved the DMMA pipe: 12 TFLOP/s, ncu: long-scoreboard on the
+//                     full barrier.)  Bank conflicts are avoided by letting lane t = 2*th + b of a quad feed
+//                     k = 2*(kk + 4*th) + b to the kk-th DMMA of a stage (any 4 distinct k per DMMA are legal as long
+//                     as A and B agree): swizzled A chunk (kk + 4 th) ^ g is distinct over the half-warp, and the B rows
+//                     k >= 8 are shifted by 8 doubles so that slot 8kk + 4b + 8th + g (mod 16) is distinct too.
 template <int WNT, bool AKM>
-__global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmapA) {
     constexpr int BN = 32 * WNT;
     constexpr int PITCH_B = BN + 4;
-    constexpr int PITCH_AK = BK + 4;
-    constexpr int A_STAGE = AKM ? BM * PITCH_AK : BK * PITCH_A;     // doubles
-    constexpr int B_STAGE = BK * PITCH_B;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int A_STAGE = AKM ? BM * BK : BK * PITCH_A;     // doubles (TN: 16 KB, 1024-byte aligned swizzle atoms)
+    constexpr int B_STAGE = BK * PITCH_B + (AKM ? 8 : 0);
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sB = sA + STAGES * A_STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
@@ -125,13 +139,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 __syncwarp();
                 const int k = ks * BK + (lane & 15);
                 if (AKM) {
-#pragma unroll
-                    for (int rr = 0; rr < BM / 32; ++rr) {
-                        const int row = lane + rr * 32;
-                        bulk_g2s(sA + s * A_STAGE + row * PITCH_AK, gA + (int64_t)row * p.lda + ks * BK, BK * 8, &full[s]);
-                    }
+                    if (lane == 0) tma_2d_g2s(sA + s * A_STAGE, &tmapA, ks * BK, tm * BM, &full[s]);
                     if (lane < 16)
-                        bulk_g2s(sB + s * B_STAGE + lane * PITCH_B, gB + (int64_t)k * p.ldbt, BN * 8, &full[s]);
+                        bulk_g2s(sB + s * B_STAGE + lane * PITCH_B + (lane >= 8 ? 8 : 0), gB + (int64_t)k * p.ldbt, BN * 8,
+                                 &full[s]);
                 } else if (lane < 16)
                     bulk_g2s(sA + s * A_STAGE + lane * PITCH_A, gA + (int64_t)k * p.lda, BM * 8, &full[s]);
                 else
@@ -155,17 +166,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                const double* a_s = AKM ? sA + s * A_STAGE + (wm * 64 + g) * PITCH_AK + t
+                const int th = t >> 1, tb = t & 1;
+                const double* a_s = AKM ? sA + s * A_STAGE + (wm * 64 + g) * BK + tb
                                         : sA + s * A_STAGE + t * PITCH_A + wm * 64 + g;
-                const double* b_s = sB + s * B_STAGE + t * PITCH_B + wn * (8 * WNT) + g;
+                const double* b_s = AKM ? sB + s * B_STAGE + (8 * th + tb) * PITCH_B + 8 * th + wn * (8 * WNT) + g
+                                        : sB + s * B_STAGE + t * PITCH_B + wn * (8 * WNT) + g;
 #pragma unroll
                 for (int kk = 0; kk < BK / 4; ++kk) {
                     double a[8], b[WNT];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        a[i] = AKM ? a_s[i * 8 * PITCH_AK + kk * 4] : a_s[kk * 4 * PITCH_A + i * 8];
+                        a[i] = AKM ? a_s[i * 8 * BK + ((((kk + 4 * th) ^ g)) << 1)] : a_s[kk * 4 * PITCH_A + i * 8];
 #pragma unroll
-                    for (int j = 0; j < WNT; ++j) b[j] = b_s[kk * 4 * PITCH_B + j * 8];
+                    for (int j = 0; j < WNT; ++j) b[j] = AKM ? b_s[2 * kk * PITCH_B + j * 8] : b_s[kk * 4 * PITCH_B + j * 8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -224,11 +237,48 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        REACH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (!sym || qres != cudaDriverEntryPointSuccess) throw Error(2, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// Tensor map over the K-contiguous operand: rows x K doubles, row pitch ld; box = 128 rows x 16 k, 128-byte swizzle,
+// out-of-range elements read as zero.
+CUtensorMap make_tmap_rows(const double* base, int64_t rows, int64_t K, int64_t ld) {
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d) for rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
+                 (long long)K, (long long)ld);
+        throw Error(2, buf);
+    }
+    return m;
+}
+
 template <int WNT, bool AKM>
-void launch(Ctx* ctx, const GemmParams& p) {
+void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     constexpr int BN = 32 * WNT;
-    constexpr int A_STAGE = AKM ? BM * (BK + 4) : BK * PITCH_A;
-    const size_t smem = (size_t)STAGES * (A_STAGE + BK * (BN + 4)) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+    constexpr int A_STAGE = AKM ? BM * BK : BK * PITCH_A;
+    constexpr int B_STAGE = BK * (BN + 4) + (AKM ? 8 : 0);
+    const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 2 * STAGES * sizeof(uint64_t) + 1024;
     static bool configured = false;
     if (!configured) {
         REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -236,7 +286,7 @@ void launch(Ctx* ctx, const GemmParams& p) {
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(p);
+    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(p, tmap);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;
 }
@@ -280,10 +330,12 @@ void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t
         if (c < best_cols) { best_cols = c; best = wnt; }
     }
     p.tiles_n = (int)ceil_div(N, 32 * best);
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof(dummy));
     switch (best) {
-        case 4: launch<4, false>(ctx, p); break;
-        case 3: launch<3, false>(ctx, p); break;
-        default: launch<2, false>(ctx, p); break;
+        case 4: launch<4, false>(ctx, p, dummy); break;
+        case 3: launch<3, false>(ctx, p, dummy); break;
+        default: launch<2, false>(ctx, p, dummy); break;
     }
 }
 
@@ -312,10 +364,11 @@ void gemm_left(Ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64
         if (c < best_cols) { best_cols = c; best = wnt; }
     }
     p.tiles_n = (int)ceil_div(n, 32 * best);
+    const CUtensorMap tmap = make_tmap_rows(X, Q, K, ldx);
     switch (best) {
-        case 4: launch<4, true>(ctx, p); break;
-        case 3: launch<3, true>(ctx, p); break;
-        default: launch<2, true>(ctx, p); break;
+        case 4: launch<4, true>(ctx, p, tmap); break;
+        case 3: launch<3, true>(ctx, p, tmap); break;
+        default: launch<2, true>(ctx, p, tmap); break;
     }
 }
 
