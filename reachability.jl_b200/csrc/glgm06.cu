@@ -6,21 +6,22 @@
 //     W   = reduce_order( (cW + P_{k-1} cV, [GW | P_{k-1} GV]), r )                                   (:54-55)
 //     P_k = P_{k-1} Phi                                                                               (:57-58)
 //
-// B200 design
-//  * The mapped generators do not depend on W, so they are produced for a whole BLOCK of s steps by one large DMMA
-//    GEMM: with X = [G0 | GV | c0 | cV] (n x q) and Y_j = Phi^j X, the stack [Y_{bs+1} .. Y_{bs+s}] is Phi^s times the
-//    previous stack (left multiplication; gemm_left keeps everything column-major, one generator = one contiguous
-//    column).  Their Girard scores h = |g|_1 - |g|_inf, the within-segment stable order and the zero-generator flags
-//    are batched per block as well (score_stack / sort_segments): off the sequential critical path.
-//  * Per step only the data-dependent part remains.  W is kept as dense columns plus per-column descriptors
-//    (score h, sorted rank, and an axis tag for box generators so that diag(d) is never stored or read densely).
-//    Because every segment carries its stable sorted order, the sortperm of a concatenation is a MERGE:
-//    rank = own rank + binary search in the other segment (rank_lists, O(p log p), ties resolved by list index as
-//    Julia's stable sortperm does).  apply_step then moves each kept column once (warp per column, 16-byte
-//    vectorised, coalesced) and accumulates |g| of the discarded ones in a fixed order (deterministic, no float
-//    atomics); the last box CTA finalises descriptors, centres and counts for the next step.
-//  * All counts live on the device (zero-generator removal makes them data dependent): the host enqueues the whole
-//    flowpipe without ever synchronising.
+// B200 design ("archive + chain + batched numerics")
+//  * ARCHIVE.  With X = [G0 | GV | c0 | cV] (n x q) every mapped generator the recurrence ever touches is a column of
+//    Y_j = Phi^j X.  All Y_j live in one archive (slot j), produced s slots at a time by ONE large DMMA GEMM
+//    slots[have .. have+s) = Phi^s * slots[have-s .. have)   (left multiplication, gemm_left, columns stay contiguous).
+//    A generator of W is therefore never copied: it is an immutable REFERENCE, either an archive column or a box
+//    generator (step, row) whose value sits in the archive of W box vectors.
+//  * CHAIN.  The only sequential, data-dependent part is the Girard SELECTION of W (which generators are boxed).  It is
+//    pure key logic: every segment carries its stable sorted order, so the sortperm of [W | Phi^k GV] is a merge
+//    (own rank + binary search in the other segment; ties by list index like Julia's stable sortperm).  One persistent
+//    CTA keeps the sorted (score, reference) list of W in shared memory and advances a whole block of steps without any
+//    grid-wide synchronisation; zero-generator removal needs only row-support bit masks, never the values.
+//  * BATCHED NUMERICS.  Everything numerical is then embarrassingly parallel over the steps of the block: box vectors of
+//    the discarded generators (fixed summation order, no float atomics), the R-side selection [Phi^k G0 | W_{k-1}]
+//    against the per-step snapshot of W, the gather of the kept generators into the flowpipe slots (warp per column,
+//    16-byte vectorised, coalesced), centres, and the dense box generators.
+//  * All counts live on the device; the host enqueues the whole flowpipe without synchronising.
 #include "common.cuh"
 #include "../../include/reach.h"
 #include <algorithm>
@@ -32,43 +33,40 @@ namespace {
 
 constexpr int MODE_UNCHANGED = 0;   // r*n >= p: reduce_order returns Z unchanged
 constexpr int MODE_REDUCE = 1;
-constexpr int NBOX_R = 24;          // CTAs accumulating the discarded generators of the R / W reduction
-constexpr int NBOX_W = 12;
-constexpr int NBOX = NBOX_R + NBOX_W;
-constexpr int APPLY_THREADS = 256;
+constexpr int NBW = 4;              // box-sum chunks per step for the W / R reduction
+constexpr int NBR = 16;
+constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
+constexpr int CHAIN_THREADS = 1024;
 
-struct WState {      // ping-pong by step parity
-    int pW;          // generators of W
-    int cur;         // which GW buffer holds them
-    int pad0, pad1;
-};
-
-struct StepPlan {    // written by rank_lists, read by apply_step; kept for every step (selection records)
-    int modeR, pinR, mR, pA;
-    int modeW, pinW, mW, pC;
-};
+struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of step k  (GLGM06/reach.jl:54-55)
+struct PlanR { int mode, pin, m, pA, pW, pad0, pad1, pad2; };   // R reduction of step k  (:48-49)
 
 struct GP {
-    int n, ld, p0, pV, q;
-    int strip;
-    int64_t nkeep, rn;      // n*(r-1), r*n
-    int capW, capR, capListR, capListW;
-    // mapped stack of the current block and its batched metadata
-    const double* Y;
+    int n, ld, p0, pV, q, strip, nwords, record;
+    int64_t nkeep, rn;          // n*(r-1), r*n
+    int capW, capR, capListR, capListW, capDisc, smax;
+    // ---- archive
+    const double* Yall;         // slot j = Phi^j X, q columns each
+    double* Wd;                 // [N+2][ld] box vectors of the W reductions (values of the box-generator references)
+    uint32_t* maskAll;          // [N+1][pV][nwords] row-support masks of the mapped input generators (strip mode)
+    // ---- current batch of steps [k0, k0 + cnt): step k uses slot j = k - 1, block-local index t = k - k0
+    const double* Y;            // = Yall + (k0 - 1) q ld
+    int64_t col0;               // archive column of Y's first column
     double* hS; int* rkS; int* cposS; double* skS; int* cntS;
-    // W: dense columns + descriptors
-    double* GW[2];
-    double* hW[2]; int* tagW[2]; double* valW[2]; int* rkW[2]; double* skW[2];
-    WState* st;
+    // ---- W chain state (sorted list) + per-step snapshots of the batch
+    double* wKeys; int* wRefs; int* wPos; int* wCount;
+    double* snKeys; int* snRefs; int* snPos; int* snCount;
+    PlanW* planW; PlanR* planR;                 // [N+2]
+    int* dlistW;                // [smax][capDisc] references of the generators boxed by the W reduction, sigma order
+    int* tcnt; int* tsrc;       // [smax][n], [smax][n][4]: creation steps of the box generators boxed again, per row
+    int* orderR;                // [smax][capListR] sortperm codes of the R list
+    double* partW; double* partR;               // [smax][NB*][ld]
     double* cW;
-    int* orderR; int* orderW; int64_t order_stride;   // per-step stride (0 when selections are not recorded)
-    double* recH; int64_t rec_stride;                  // per-step scores of both lists (NULL unless recorded)
-    StepPlan* plans;
-    // flowpipe
-    double* Rg; int64_t slot;   // doubles per step slot (ld * capR)
-    double* Rc; double* Rd; int* Rrow; int2* meta;
-    double* partial; unsigned* ticket;
+    // ---- flowpipe
+    double* Rg; int64_t slot; double* Rc; double* Rd; int* Rrow; int2* meta;
+    // ---- selection records
+    int* recOrdW; double* recHW; int* recOrdR; double* recHR;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -82,41 +80,54 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Girard score of one column: lanes stride the rows (double2), fixed order => a pure function of the column's bits.
-__device__ __forceinline__ void column_score(const double* __restrict__ col, int n2, int lane, double& asum, double& amax) {
-    const double2* c2 = reinterpret_cast<const double2*>(col);
-    double s = 0.0, m = 0.0;
-    for (int i = lane; i < n2; i += 32) {
-        const double2 v = c2[i];
-        const double ax = fabs(v.x), ay = fabs(v.y);
-        s += ax;
-        s += ay;
-        m = fmax(m, fmax(ax, ay));
-    }
-    asum = warp_sum(s);
-    amax = warp_max(m);
+// Box-generator reference of (step k, row i) and its decoding.
+__device__ __forceinline__ int tag_ref(int k, int i, int n) { return -1 - (k * n + i); }
+__device__ __forceinline__ void tag_decode(int ref, int n, int& k, int& i) {
+    const int v = -1 - ref;
+    k = v / n;
+    i = v - k * n;
+}
+// Row i <-> (word, bit) of a row-support mask: the score kernel produces the bits with warp ballots over double2 lanes.
+__device__ __forceinline__ void mask_pos(int i, int& word, int& bit) {
+    word = 2 * (i >> 6) + (i & 1);
+    bit = (i & 63) >> 1;
 }
 
-// h for every mapped generator of a block (columns c < p0 + pV of each of the cnt steps); dropped (all-zero, strip
-// mode) columns get +inf.  One warp per column.
+// h = |g|_1 - |g|_inf of every mapped generator of the batch (+inf = all-zero column dropped in strip mode) and, for the
+// input segment, the row-support mask.  One warp per column; a pure function of the column's bits.
 __global__ void __launch_bounds__(256) score_stack_kernel(GP g, int cnt) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int per = g.p0 + g.pV;
     if (warp >= cnt * per) return;
     const int t = warp / per, c = warp % per;
-    const double* col = g.Y + (int64_t)(t * g.q + c) * g.ld;
-    double asum, amax;
-    column_score(col, g.ld / 2, lane, asum, amax);
+    const double2* c2 = reinterpret_cast<const double2*>(g.Y + (int64_t)(t * g.q + c) * g.ld);
+    const int n2 = g.ld / 2;
+    double s = 0.0, m = 0.0;
+    uint32_t* mask = (g.strip && c >= g.p0) ? g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + (c - g.p0)) * g.nwords : nullptr;
+    for (int it = 0; it * 32 < n2; ++it) {
+        const int i = lane + 32 * it;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < n2) v = c2[i];
+        const double ax = fabs(v.x), ay = fabs(v.y);
+        s += ax;
+        s += ay;
+        m = fmax(m, fmax(ax, ay));
+        if (mask) {
+            const unsigned bx = __ballot_sync(0xffffffffu, ax != 0.0), by = __ballot_sync(0xffffffffu, ay != 0.0);
+            if (lane == 0) { mask[2 * it] = bx; mask[2 * it + 1] = by; }
+        }
+    }
+    const double asum = warp_sum(s), amax = warp_max(m);
     if (lane == 0) g.hS[t * g.q + c] = (g.strip && asum == 0.0) ? INFINITY : asum - amax;
 }
 
 // Stable order of every mapped segment (step t, seg 0 = P G0, seg 1 = P GV): rank by counting, O(len^2) but batched
-// over the block and spread over (segment, 256-element chunk) CTAs.
+// over the batch and spread over (segment, 256-element chunk) CTAs.
 __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
     __shared__ double keys[1024];
     const int t = blockIdx.y >> 1, seg = blockIdx.y & 1;
     const int len = seg ? g.pV : g.p0;
-    if (blockIdx.x * 256 >= len && !(blockIdx.x == 0)) return;
+    if (blockIdx.x * 256 >= len && blockIdx.x != 0) return;
     const int base = t * g.q + (seg ? g.p0 : 0);
     const int e = blockIdx.x * 256 + threadIdx.x;
     const double he = e < len ? g.hS[base + e] : INFINITY;
@@ -161,371 +172,449 @@ __device__ __forceinline__ int upper_bound(const double* a, int len, double key)
     return lo;
 }
 
-// sortperm of the two concatenations of step k by merging sorted segments.
-//   R list = [A = P G0 (mapped, step t of the block) | B = W]        (GLGM06/reach.jl:48)
-//   W list = [B = W | C = P GV]                                       (GLGM06/reach.jl:54)
-// order?[sigma] = source code: c < p0+pV -> mapped column c of the step; p0+pV+j -> column j of W.
-__global__ void __launch_bounds__(256) rank_lists_kernel(GP g, int t, int k, int use_smem) {
-    extern __shared__ double sk_s[];
-    const WState st = g.st[k & 1];
-    const int par = k & 1;
-    const int pW = st.pW, pA = g.cntS[t * 2 + 0], pC = g.cntS[t * 2 + 1];
-    const int baseA = t * g.q, baseC = t * g.q + g.p0;
-    const double* skA = g.skS + baseA;
-    const double* skB = g.skW[par];
-    const double* skC = g.skS + baseC;
+// W_1 = V (GLGM06/reach.jl:41-42): the valid columns of the input segment of slot 0, in their stable sorted order.
+__global__ void __launch_bounds__(256) init_w_kernel(GP g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) *g.wCount = g.cntS[1];
+    if (e >= g.pV) return;
+    const double h = g.hS[g.p0 + e];
+    if (!(h < INFINITY)) return;
+    const int rk = g.rkS[g.p0 + e];
+    g.wKeys[rk] = h;
+    g.wRefs[rk] = g.p0 + e;                 // archive column of slot 0
+    g.wPos[rk] = g.cposS[g.p0 + e];
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// CHAIN: the W selections of steps [k0, k0 + cnt), one persistent CTA, state in shared memory (or global scratch when
+// it does not fit).  W list of step k = [W_{k-1} (logical order) | valid columns of P_{k-1} GV]; sigma = stable rank.
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, int use_smem, double* scrKeys,
+                                                                  int* scrInts) {
+    extern __shared__ __align__(16) unsigned char chain_sm[];
+    __shared__ unsigned orm[2 * MAX_IT];
+    __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
+    __shared__ int scan_s[CHAIN_THREADS / 32];
+    __shared__ int s_nd;
+    const int tid = threadIdx.x, cap = g.capW;
+    double* keys[2];
+    int *refs[2], *pos[2], *sig;
     if (use_smem) {
-        double* sA = sk_s;
-        double* sB = sA + pA;
-        double* sC = sB + pW;
-        for (int i = threadIdx.x; i < pA; i += blockDim.x) sA[i] = skA[i];
-        for (int i = threadIdx.x; i < pW; i += blockDim.x) sB[i] = skB[i];
-        for (int i = threadIdx.x; i < pC; i += blockDim.x) sC[i] = skC[i];
+        keys[0] = reinterpret_cast<double*>(chain_sm);
+        keys[1] = keys[0] + cap;
+        refs[0] = reinterpret_cast<int*>(keys[1] + cap);
+    } else {
+        keys[0] = scrKeys;
+        keys[1] = keys[0] + cap;
+        refs[0] = scrInts;
+    }
+    refs[1] = refs[0] + cap;
+    pos[0] = refs[1] + cap;
+    pos[1] = pos[0] + cap;
+    sig = pos[1] + cap;                      // [cap + pV]
+    int pW = *g.wCount;
+    for (int r = tid; r < pW; r += CHAIN_THREADS) {
+        keys[0][r] = g.wKeys[r];
+        refs[0][r] = g.wRefs[r];
+        pos[0][r] = g.wPos[r];
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int t = 0; t < cnt; ++t) {
+        const int k = k0 + t, nxt = cur ^ 1;
+        const int baseC = t * g.q + g.p0;
+        const int pC = g.cntS[t * 2 + 1];
+        const double* skC = g.skS + baseC;
+        const int pin = pW + pC;
+        const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
+        const int m = mode == MODE_REDUCE ? (int)(pin - g.nkeep) : 0;
+        const int nk = pin - m;
+        // generators with score exactly 0 precede everything else; z of them survive the cut
+        const int cntzero = upper_bound(keys[cur], pW, 0.0) + upper_bound(skC, pC, 0.0);
+        const int z = max(0, cntzero - m);
+        if (tid < 2 * MAX_IT) orm[tid] = 0u;
+        if (tid < g.n) tc_s[tid] = 0;
         __syncthreads();
-        skA = sA; skB = sB; skC = sC;
-    }
-    const int pinR = pA + pW, pinW = pW + pC;
-    const int modeR = (g.rn >= (int64_t)pinR) ? MODE_UNCHANGED : MODE_REDUCE;
-    const int modeW = (g.rn >= (int64_t)pinW) ? MODE_UNCHANGED : MODE_REDUCE;
-    int* orderR = g.orderR + (int64_t)k * g.order_stride;
-    int* orderW = g.orderW + (int64_t)k * g.order_stride;
-    double* recH = g.recH ? g.recH + (int64_t)k * g.rec_stride : nullptr;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nmap = g.p0 + g.pV;
-    if (gid == 0) {
-        StepPlan pl;
-        pl.modeR = modeR; pl.pinR = pinR; pl.mR = modeR == MODE_REDUCE ? (int)(pinR - g.nkeep) : 0; pl.pA = pA;
-        pl.modeW = modeW; pl.pinW = pinW; pl.mW = modeW == MODE_REDUCE ? (int)(pinW - g.nkeep) : 0; pl.pC = pC;
-        g.plans[k] = pl;
-    }
-    int e = gid;
-    if (e < g.p0) {                                   // R list, segment A
-        const double h = g.hS[baseA + e];
-        if (recH) recH[e] = h;
-        if (h < INFINITY) orderR[g.rkS[baseA + e] + lower_bound(skB, pW, h)] = e;
-        return;
-    }
-    e -= g.p0;
-    if (e < g.capW) {                                 // R list, segment B
-        if (e < pW) {
-            const double h = g.hW[par][e];
-            if (recH) recH[g.p0 + e] = h;
-            orderR[g.rkW[par][e] + upper_bound(skA, pA, h)] = nmap + e;
-        }
-        return;
-    }
-    e -= g.capW;
-    if (e < g.capW) {                                 // W list, segment B
-        if (e < pW) {
-            const double h = g.hW[par][e];
-            if (recH) recH[g.capListR + e] = h;
-            orderW[g.rkW[par][e] + lower_bound(skC, pC, h)] = nmap + e;
-        }
-        return;
-    }
-    e -= g.capW;
-    if (e < g.pV) {                                   // W list, segment C
-        const double h = g.hS[baseC + e];
-        if (recH) recH[g.capListR + pW + e] = h;
-        if (h < INFINITY) orderW[g.rkS[baseC + e] + upper_bound(skB, pW, h)] = g.p0 + e;
-    }
-}
-
-struct Src {
-    const double* col;   // dense column (nullptr when tagged)
-    int tag;             // axis row of a box generator, -1 dense
-    double val;
-    double h;
-};
-
-__device__ __forceinline__ Src resolve(const GP& g, int code, int t, int par, int cur) {
-    Src s;
-    const int nmap = g.p0 + g.pV;
-    if (code < nmap) {
-        s.col = g.Y + (int64_t)(t * g.q + code) * g.ld;
-        s.tag = -1; s.val = 0.0;
-        s.h = g.hS[t * g.q + code];
-    } else {
-        const int j = code - nmap;
-        s.tag = g.tagW[par][j];
-        s.val = g.valW[par][j];
-        s.h = g.hW[par][j];
-        s.col = s.tag >= 0 ? nullptr : g.GW[cur] + (int64_t)j * g.ld;
-    }
-    return s;
-}
-
-__device__ __forceinline__ void copy_column(const GP& g, const Src& s, double* __restrict__ dst, int lane) {
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    const int n2 = g.ld / 2;
-    if (s.tag < 0) {
-        const double2* c2 = reinterpret_cast<const double2*>(s.col);
-#pragma unroll 4
-        for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
-    } else {
-        for (int i = lane; i < n2; i += 32) {
-            double2 v = make_double2(0.0, 0.0);
-            if (2 * i == s.tag) v.x = s.val;
-            if (2 * i + 1 == s.tag) v.y = s.val;
-            d2[i] = v;
-        }
-    }
-}
-
-__device__ void finalize_step(const GP& g, int t, int k);
-
-// One launch per step: box CTAs (blockIdx.x < NBOX) accumulate the discarded generators, the others copy the kept
-// ones, warp per column.
-__global__ void __launch_bounds__(APPLY_THREADS) apply_step_kernel(GP g, int t, int k) {
-    extern __shared__ double red_s[];       // [APPLY_THREADS/32][ld] cross-warp reduction of the box CTAs
-    __shared__ unsigned last_flag;
-    const StepPlan pl = g.plans[k];
-    const int par = k & 1;
-    const WState st = g.st[par];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n2 = g.ld / 2;
-    const int* orderR = g.orderR + (int64_t)k * g.order_stride;
-    const int* orderW = g.orderW + (int64_t)k * g.order_stride;
-    if (blockIdx.x < NBOX) {
-        const bool isR = blockIdx.x < NBOX_R;
-        const int b = isR ? blockIdx.x : blockIdx.x - NBOX_R;
-        const int nb = isR ? NBOX_R : NBOX_W;
-        const int mode = isR ? pl.modeR : pl.modeW;
-        const int m = isR ? pl.mR : pl.mW;
-        const int* order = isR ? orderR : orderW;
-        if (mode == MODE_REDUCE) {
-            double2 acc[MAX_IT];
-#pragma unroll
-            for (int i = 0; i < MAX_IT; ++i) acc[i] = make_double2(0.0, 0.0);
-            for (int rho = b * (APPLY_THREADS / 32) + warp; rho < m; rho += nb * (APPLY_THREADS / 32)) {
-                const Src s = resolve(g, order[rho], t, par, st.cur);
-                if (s.tag < 0) {
-                    const double2* c2 = reinterpret_cast<const double2*>(s.col);
-#pragma unroll
-                    for (int i = 0; i < MAX_IT; ++i) {
-                        const int idx = lane + 32 * i;
-                        if (idx < n2) {
-                            const double2 v = c2[idx];
-                            acc[i].x += fabs(v.x);
-                            acc[i].y += fabs(v.y);
+        // ---- snapshot of W_{k-1} for the R reduction of this step, stable ranks, boxed list, row-support union ----
+        double* snK = g.snKeys + (int64_t)t * cap;
+        int* snR = g.snRefs + (int64_t)t * cap;
+        int* snP = g.snPos + (int64_t)t * cap;
+        int* dl = g.dlistW + (int64_t)t * g.capDisc;
+        int* recO = g.record ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
+        double* recH = g.record ? g.recHW + (int64_t)k * g.capListW : nullptr;
+        for (int r = tid; r < pW; r += CHAIN_THREADS) {
+            const double key = keys[cur][r];
+            const int ref = refs[cur][r], ps = pos[cur][r];
+            snK[r] = key; snR[r] = ref; snP[r] = ps;
+            const int sigma = r + lower_bound(skC, pC, key);
+            sig[r] = sigma;
+            if (recO) { recO[sigma] = ps; recH[ps] = key; }
+            if (sigma < m) {
+                dl[sigma] = ref;
+                if (g.strip) {
+                    if (ref >= 0) {
+                        const int j = ref / g.q, c = ref - j * g.q - g.p0;
+                        const uint32_t* mk = g.maskAll + ((int64_t)j * g.pV + c) * g.nwords;
+                        for (int w = 0; w < g.nwords; ++w) {
+                            const unsigned b = mk[w];
+                            if (b) atomicOr(&orm[w], b);
                         }
+                    } else {
+                        int kt, it, w, b;
+                        tag_decode(ref, g.n, kt, it);
+                        mask_pos(it, w, b);
+                        atomicOr(&orm[w], 1u << b);
                     }
-                } else {
-                    const int idx = s.tag >> 1;
-#pragma unroll
-                    for (int i = 0; i < MAX_IT; ++i)
-                        if (lane + 32 * i == idx) {
-                            if (s.tag & 1) acc[i].y += fabs(s.val); else acc[i].x += fabs(s.val);
-                        }
+                }
+                if (ref < 0) {      // value = an earlier W box vector entry: remember its creation step for wseq_kernel
+                    int kt, it;
+                    tag_decode(ref, g.n, kt, it);
+                    const int sl = atomicAdd(&tc_s[it], 1);
+                    if (sl < 4) g.tsrc[((int64_t)t * g.n + it) * 4 + sl] = kt;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < MAX_IT; ++i) {
-                const int idx = lane + 32 * i;
-                if (idx < n2) {
-                    red_s[warp * g.ld + 2 * idx] = acc[i].x;
-                    red_s[warp * g.ld + 2 * idx + 1] = acc[i].y;
+        }
+        for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
+            const double h = g.hS[baseC + e];
+            int sigma = -1;
+            if (h < INFINITY) {
+                sigma = g.rkS[baseC + e] + upper_bound(keys[cur], pW, h);
+                if (recO) { const int li = pW + g.cposS[baseC + e]; recO[sigma] = li; recH[li] = h; }
+                if (sigma < m) {
+                    dl[sigma] = (int)(g.col0 + baseC + e);
+                    if (g.strip) {
+                        const uint32_t* mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + e) * g.nwords;
+                        for (int w = 0; w < g.nwords; ++w) {
+                            const unsigned b = mk[w];
+                            if (b) atomicOr(&orm[w], b);
+                        }
+                    }
                 }
+            }
+            sig[cap + e] = sigma;
+        }
+        if (tid == 0) g.snCount[t] = pW;
+        __syncthreads();
+        if (tid < g.n) g.tcnt[(int64_t)t * g.n + tid] = tc_s[tid];
+        // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode) ----
+        int flag = 0, iprime = 0, nd = 0;
+        if (mode == MODE_REDUCE) {
+            if (tid < g.n) {
+                if (g.strip) {
+                    int w, b;
+                    mask_pos(tid, w, b);
+                    flag = (orm[w] >> b) & 1;
+                } else {
+                    flag = 1;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, flag);
+            const int lane = tid & 31, wid = tid >> 5;
+            if (lane == 0) scan_s[wid] = __popc(bal);
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int w = 0; w < CHAIN_THREADS / 32; ++w) { const int c = scan_s[w]; scan_s[w] = acc; acc += c; }
+                s_nd = acc;
             }
             __syncthreads();
-            double* part = g.partial + (int64_t)blockIdx.x * g.ld;
-            for (int i = threadIdx.x; i < g.ld; i += APPLY_THREADS) {
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < APPLY_THREADS / 32; ++w) s += red_s[w * g.ld + i];
-                part[i] = s;
+            nd = s_nd;
+            iprime = scan_s[wid] + __popc(bal & ((1u << lane) - 1u));
+        }
+        // ---- the next W: sorted list (keys, refs) with logical positions ----
+        if (mode == MODE_REDUCE) {
+            for (int r = tid; r < pW; r += CHAIN_THREADS) {
+                const int sigma = sig[r];
+                if (sigma >= m) {
+                    const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
+                    keys[nxt][rk] = keys[cur][r]; refs[nxt][rk] = refs[cur][r]; pos[nxt][rk] = ps;
+                }
             }
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) last_flag = (atomicAdd(g.ticket, 1u) == (unsigned)(NBOX - 1));
-        __syncthreads();
-        if (last_flag) {
-            __threadfence();
-            finalize_step(g, t, k);
-            if (threadIdx.x == 0) *g.ticket = 0u;
-        }
-        return;
-    }
-    // ---- copy jobs ----
-    const int nwarps = (gridDim.x - NBOX) * (APPLY_THREADS / 32);
-    const int w0 = (blockIdx.x - NBOX) * (APPLY_THREADS / 32) + warp;
-    const int nmap = g.p0 + g.pV;
-    double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
-    const int jobsR = g.capListR, jobs = g.capListR + g.capListW;
-    for (int job = w0; job < jobs; job += nwarps) {
-        if (job < jobsR) {
-            if (pl.modeR == MODE_REDUCE) {
-                if (job >= pl.mR && job < pl.pinR) {
-                    const Src s = resolve(g, orderR[job], t, par, st.cur);
-                    copy_column(g, s, slot + (int64_t)(job - pl.mR) * g.ld, lane);
+            for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
+                const int sigma = sig[cap + e];
+                if (sigma >= m) {
+                    const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
+                    keys[nxt][rk] = g.hS[baseC + e]; refs[nxt][rk] = (int)(g.col0 + baseC + e); pos[nxt][rk] = ps;
                 }
-            } else {   // unchanged: [A valid | B] in list order
-                if (job < g.p0) {
-                    if (g.hS[t * g.q + job] < INFINITY) {
-                        const Src s = resolve(g, job, t, par, st.cur);
-                        copy_column(g, s, slot + (int64_t)g.cposS[t * g.q + job] * g.ld, lane);
-                    }
-                } else if (job - g.p0 < st.pW) {
-                    const Src s = resolve(g, nmap + job - g.p0, t, par, st.cur);
-                    copy_column(g, s, slot + (int64_t)(pl.pA + job - g.p0) * g.ld, lane);
-                }
+            }
+            if (flag) {
+                const int rk = z + iprime;
+                keys[nxt][rk] = 0.0; refs[nxt][rk] = tag_ref(k, tid, g.n); pos[nxt][rk] = nk + iprime;
             }
         } else {
-            const int j = job - jobsR;
-            if (pl.modeW == MODE_REDUCE) {
-                if (j >= pl.mW && j < pl.pinW) {
-                    const Src s = resolve(g, orderW[j], t, par, st.cur);
-                    if (s.tag < 0) copy_column(g, s, g.GW[st.cur ^ 1] + (int64_t)(j - pl.mW) * g.ld, lane);
+            for (int r = tid; r < pW; r += CHAIN_THREADS) {
+                const int rk = sig[r];
+                keys[nxt][rk] = keys[cur][r]; refs[nxt][rk] = refs[cur][r]; pos[nxt][rk] = pos[cur][r];
+            }
+            for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
+                const int rk = sig[cap + e];
+                if (rk >= 0) {
+                    keys[nxt][rk] = g.hS[baseC + e]; refs[nxt][rk] = (int)(g.col0 + baseC + e);
+                    pos[nxt][rk] = pW + g.cposS[baseC + e];
                 }
-            } else if (j >= g.capW && j - g.capW < g.pV) {   // append the valid mapped input generators in place
-                const int c = j - g.capW;
-                if (g.hS[t * g.q + g.p0 + c] < INFINITY) {
-                    const Src s = resolve(g, g.p0 + c, t, par, st.cur);
-                    copy_column(g, s, g.GW[st.cur] + (int64_t)(st.pW + g.cposS[t * g.q + g.p0 + c]) * g.ld, lane);
+            }
+        }
+        if (tid == 0) {
+            PlanW pl;
+            pl.mode = mode; pl.pin = pin; pl.m = m; pl.pW = pW; pl.pC = pC; pl.nk = nk; pl.nd = nd; pl.z = z;
+            g.planW[k] = pl;
+        }
+        pW = mode == MODE_REDUCE ? nk + nd : pin;
+        cur = nxt;
+        __syncthreads();
+    }
+    for (int r = tid; r < pW; r += CHAIN_THREADS) {
+        g.wKeys[r] = keys[cur][r];
+        g.wRefs[r] = refs[cur][r];
+        g.wPos[r] = pos[cur][r];
+    }
+    if (tid == 0) *g.wCount = pW;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// batched numerics
+// -----------------------------------------------------------------------------------------------------------------
+struct Acc {
+    double2 v[MAX_IT];
+};
+
+__device__ __forceinline__ void acc_zero(Acc& a) {
+#pragma unroll
+    for (int i = 0; i < MAX_IT; ++i) a.v[i] = make_double2(0.0, 0.0);
+}
+// a += |column ref|  (dense archive column, or the single entry of a box generator when with_tags)
+__device__ __forceinline__ void acc_add(const GP& g, Acc& a, int ref, int lane, bool with_tags) {
+    const int n2 = g.ld / 2;
+    if (ref >= 0) {
+        const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)ref * g.ld);
+#pragma unroll
+        for (int i = 0; i < MAX_IT; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < n2) {
+                const double2 v = c2[idx];
+                a.v[i].x += fabs(v.x);
+                a.v[i].y += fabs(v.y);
+            }
+        }
+    } else if (with_tags) {
+        int kt, it;
+        tag_decode(ref, g.n, kt, it);
+        const double val = fabs(g.Wd[(int64_t)kt * g.ld + it]);
+        const int idx = it >> 1;
+#pragma unroll
+        for (int i = 0; i < MAX_IT; ++i)
+            if (lane + 32 * i == idx) {
+                if (it & 1) a.v[i].y += val; else a.v[i].x += val;
+            }
+    }
+}
+// CTA-wide sum of the warps' accumulators in warp order -> out[0 .. ld)
+__device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc& a, double* red_s, double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n2 = g.ld / 2, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < MAX_IT; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n2) {
+            red_s[warp * g.ld + 2 * idx] = a.v[i].x;
+            red_s[warp * g.ld + 2 * idx + 1] = a.v[i].y;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.ld; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += red_s[w * g.ld + i];
+        out[i] = s;
+    }
+}
+
+// Partial box vectors of the W reductions: chunk b of step t sums |dense discarded generators| in sigma order.
+__global__ void __launch_bounds__(256) wbox_partial_kernel(GP g, int k0) {
+    extern __shared__ double red_s[];
+    const int t = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PlanW pl = g.planW[k0 + t];
+    double* out = g.partW + ((int64_t)t * NBW + b) * g.ld;
+    Acc a;
+    acc_zero(a);
+    if (pl.mode == MODE_REDUCE) {
+        const int chunk = (pl.m + NBW - 1) / NBW;
+        const int lo = b * chunk, hi = min(pl.m, lo + chunk);
+        const int* dl = g.dlistW + (int64_t)t * g.capDisc;
+        for (int s = lo + warp; s < hi; s += 8) acc_add(g, a, dl[s], lane, false);
+    }
+    acc_reduce_store(g, a, red_s, out);
+}
+
+// Sequential over the steps of the batch, parallel over rows: W box vectors (dense partials + discarded box
+// generators, whose values are earlier W box vectors) and the centres  c_k = P c0 + cW ; cW += P cV  (:48,:54).
+__global__ void __launch_bounds__(128) wseq_kernel(GP g, int k0, int cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const int nmap = g.p0 + g.pV;
+    double cw = g.cW[i];
+    for (int t = 0; t < cnt; ++t) {
+        const int k = k0 + t;
+        const PlanW pl = g.planW[k];
+        const double* yc0 = g.Y + (int64_t)(t * g.q + nmap) * g.ld;
+        g.Rc[(int64_t)(k - 1) * g.ld + i] = yc0[i] + cw;
+        cw += yc0[g.ld + i];
+        if (pl.mode == MODE_REDUCE) {
+            double d = 0.0;
+            for (int b = 0; b < NBW; ++b) d += g.partW[((int64_t)t * NBW + b) * g.ld + i];
+            const int tc = g.tcnt[(int64_t)t * g.n + i];
+            if (tc <= 4) {          // creation steps ascending => fixed summation order
+                int ks[4];
+                for (int u = 0; u < tc; ++u) ks[u] = g.tsrc[((int64_t)t * g.n + i) * 4 + u];
+                for (int u = 1; u < tc; ++u)
+                    for (int v = u; v > 0 && ks[v - 1] > ks[v]; --v) { const int x = ks[v]; ks[v] = ks[v - 1]; ks[v - 1] = x; }
+                for (int u = 0; u < tc; ++u) d += fabs(g.Wd[(int64_t)ks[u] * g.ld + i]);
+            } else {                // rare: more than four box generators of one row boxed in the same step
+                const int* dl = g.dlistW + (int64_t)t * g.capDisc;
+                for (int s = 0; s < pl.m; ++s) {
+                    const int ref = dl[s];
+                    if (ref < 0) {
+                        int kt, it;
+                        tag_decode(ref, g.n, kt, it);
+                        if (it == i) d += fabs(g.Wd[(int64_t)kt * g.ld + i]);
+                    }
                 }
+            }
+            g.Wd[(int64_t)k * g.ld + i] = d;
+        }
+    }
+    g.cW[i] = cw;
+}
+
+// sortperm of the R lists [A = P_{k-1} G0 | W_{k-1}] of the batch by merging sorted segments (GLGM06/reach.jl:48-49).
+// orderR[t][sigma] = code: e < p0 -> mapped column e of the step; p0 + rho -> entry of sorted rank rho of the snapshot.
+__global__ void __launch_bounds__(256) rank_r_kernel(GP g, int k0) {
+    const int t = blockIdx.y, k = k0 + t;
+    const int pW = g.snCount[t], pA = g.cntS[t * 2 + 0];
+    const int baseA = t * g.q;
+    const double* skA = g.skS + baseA;
+    const double* snK = g.snKeys + (int64_t)t * g.capW;
+    const int pin = pA + pW;
+    const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
+    int* order = g.orderR + (int64_t)t * g.capListR;
+    int* recO = g.record ? g.recOrdR + (int64_t)k * g.capListR : nullptr;
+    double* recH = g.record ? g.recHR + (int64_t)k * g.capListR : nullptr;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid == 0) {
+        PlanR pl;
+        pl.mode = mode; pl.pin = pin; pl.m = mode == MODE_REDUCE ? (int)(pin - g.nkeep) : 0; pl.pA = pA; pl.pW = pW;
+        pl.pad0 = pl.pad1 = pl.pad2 = 0;
+        g.planR[k] = pl;
+    }
+    if (gid < g.p0) {
+        const double h = g.hS[baseA + gid];
+        if (h < INFINITY) {
+            const int sigma = g.rkS[baseA + gid] + lower_bound(snK, pW, h);
+            order[sigma] = gid;
+            if (recO) { const int li = g.cposS[baseA + gid]; recO[sigma] = li; recH[li] = h; }
+        }
+    } else if (gid - g.p0 < pW) {
+        const int rho = gid - g.p0;
+        const double h = snK[rho];
+        const int sigma = rho + upper_bound(skA, pA, h);
+        order[sigma] = g.p0 + rho;
+        if (recO) { const int li = pA + g.snPos[(int64_t)t * g.capW + rho]; recO[sigma] = li; recH[li] = h; }
+    }
+}
+
+// R gather of the batch: blockIdx.x < NBR accumulate the boxed generators (chunks of sigma), the other CTAs move the
+// kept ones into the flowpipe slot, warp per column.
+__global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
+    extern __shared__ double red_s[];
+    const int t = blockIdx.y, k = k0 + t, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PlanR pl = g.planR[k];
+    const int* order = g.orderR + (int64_t)t * g.capListR;
+    const int* snR = g.snRefs + (int64_t)t * g.capW;
+    const int* snP = g.snPos + (int64_t)t * g.capW;
+    const int n2 = g.ld / 2;
+    if (blockIdx.x < NBR) {
+        Acc a;
+        acc_zero(a);
+        if (pl.mode == MODE_REDUCE) {
+            const int chunk = (pl.m + NBR - 1) / NBR;
+            const int lo = blockIdx.x * chunk, hi = min(pl.m, lo + chunk);
+            for (int s = lo + warp; s < hi; s += 8) {
+                const int code = order[s];
+                const int ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : snR[code - g.p0];
+                acc_add(g, a, ref, lane, true);
+            }
+        }
+        acc_reduce_store(g, a, red_s, g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
+        return;
+    }
+    double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
+    const int nwarps = (gridDim.x - NBR) * 8;
+    const int w0 = (blockIdx.x - NBR) * 8 + warp;
+    const int jobs = pl.mode == MODE_REDUCE ? pl.pin : g.p0 + pl.pW;
+    for (int job = w0; job < jobs; job += nwarps) {
+        int ref, dest;
+        if (pl.mode == MODE_REDUCE) {
+            if (job < pl.m) continue;
+            const int code = order[job];
+            ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : snR[code - g.p0];
+            dest = job - pl.m;
+        } else if (job < g.p0) {          // unchanged: [valid columns of A in order | W in logical order]
+            if (!(g.hS[t * g.q + job] < INFINITY)) continue;
+            ref = (int)(g.col0 + t * g.q + job);
+            dest = g.cposS[t * g.q + job];
+        } else {
+            const int rho = job - g.p0;
+            ref = snR[rho];
+            dest = pl.pA + snP[rho];
+        }
+        double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)dest * g.ld);
+        if (ref >= 0) {
+            const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)ref * g.ld);
+#pragma unroll 4
+            for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
+        } else {
+            int kt, it;
+            tag_decode(ref, g.n, kt, it);
+            const double val = g.Wd[(int64_t)kt * g.ld + it];
+            for (int i = lane; i < n2; i += 32) {
+                double2 v = make_double2(0.0, 0.0);
+                if (2 * i == it) v.x = val;
+                if (2 * i + 1 == it) v.y = val;
+                d2[i] = v;
             }
         }
     }
 }
 
-// Runs in the last box CTA of the step: box vectors, descriptors of the next W, centres, counts.
-__device__ void finalize_step(const GP& g, int t, int k) {
-    __shared__ int scan[APPLY_THREADS];
-    __shared__ int s_z;
-    const StepPlan pl = g.plans[k];
-    const int par = k & 1, nxt = par ^ 1;
-    const WState st = g.st[par];
-    const int tid = threadIdx.x;
-    const int nmap = g.p0 + g.pV;
-    const int* orderW = g.orderW + (int64_t)k * g.order_stride;
-    const int per = (g.n + APPLY_THREADS - 1) / APPLY_THREADS;     // rows per thread (contiguous chunk)
-    // ---------------- R: box vector of the discarded generators ----------------
-    int ndR = 0;
-    if (pl.modeR == MODE_REDUCE) {
-        int cnt = 0;
-        for (int i = tid * per; i < min(g.n, (tid + 1) * per); ++i) {
-            double d = 0.0;
-            for (int b = 0; b < NBOX_R; ++b) d += g.partial[(int64_t)b * g.ld + i];
-            g.Rd[(int64_t)(k - 1) * g.ld + i] = d;
-            cnt += (!g.strip || d != 0.0);
-        }
-        scan[tid] = cnt;
+// Box vector, generator counts and (strip mode) the rows of the dense box generators of every R_k of the batch.
+__global__ void __launch_bounds__(256) finalize_r_kernel(GP g, int k0) {
+    __shared__ int scan[256];
+    const int t = blockIdx.x, k = k0 + t, tid = threadIdx.x;
+    const PlanR pl = g.planR[k];
+    if (pl.mode != MODE_REDUCE) {
+        if (tid == 0) g.meta[k - 1] = make_int2(pl.pin, 0);
+        return;
+    }
+    const int per = (g.n + 255) / 256;
+    int cnt = 0;
+    for (int i = tid * per; i < min(g.n, (tid + 1) * per); ++i) {
+        double d = 0.0;
+        for (int b = 0; b < NBR; ++b) d += g.partR[((int64_t)t * NBR + b) * g.ld + i];
+        g.Rd[(int64_t)(k - 1) * g.ld + i] = d;
+        cnt += (!g.strip || d != 0.0);
+    }
+    scan[tid] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int v = tid >= o ? scan[tid - o] : 0;
         __syncthreads();
-        for (int o = 1; o < APPLY_THREADS; o <<= 1) {
-            const int v = tid >= o ? scan[tid - o] : 0;
-            __syncthreads();
-            scan[tid] += v;
-            __syncthreads();
-        }
-        ndR = scan[APPLY_THREADS - 1];
-        int pos = scan[tid] - cnt;
-        for (int i = tid * per; i < min(g.n, (tid + 1) * per); ++i) {
-            const double d = g.Rd[(int64_t)(k - 1) * g.ld + i];
-            if (!g.strip || d != 0.0) g.Rrow[(int64_t)(k - 1) * g.n + pos++] = i;
-        }
+        scan[tid] += v;
         __syncthreads();
     }
-    if (tid == 0) g.meta[k - 1] = make_int2(pl.modeR == MODE_REDUCE ? pl.pinR - pl.mR : pl.pinR, ndR);
-    // ---------------- W ----------------
-    if (pl.modeW == MODE_REDUCE) {
-        const int nk = pl.pinW - pl.mW;
-        // z = kept generators with score exactly 0 (they precede the new box generators in the stable order)
-        if (tid == 0) s_z = 0;
-        __syncthreads();
-        int zl = 0;
-        for (int pos = tid; pos < nk; pos += APPLY_THREADS) {
-            const int code = orderW[pl.mW + pos];
-            const double h = code < nmap ? g.hS[t * g.q + code] : g.hW[par][code - nmap];
-            zl += (h == 0.0);
-        }
-        if (zl) atomicAdd(&s_z, zl);
-        __syncthreads();
-        const int z = s_z;
-        // box vector, compacted over the non-zero rows in strip mode
-        int cnt = 0;
-        double dloc[8];
-        for (int i = tid * per, u = 0; i < min(g.n, (tid + 1) * per); ++i, ++u) {
-            double d = 0.0;
-            for (int b = 0; b < NBOX_W; ++b) d += g.partial[(int64_t)(NBOX_R + b) * g.ld + i];
-            if (u < 8) dloc[u] = d;
-            cnt += (!g.strip || d != 0.0);
-        }
-        scan[tid] = cnt;
-        __syncthreads();
-        for (int o = 1; o < APPLY_THREADS; o <<= 1) {
-            const int v = tid >= o ? scan[tid - o] : 0;
-            __syncthreads();
-            scan[tid] += v;
-            __syncthreads();
-        }
-        const int nd = scan[APPLY_THREADS - 1];
-        int ip = scan[tid] - cnt;
-        for (int i = tid * per, u = 0; i < min(g.n, (tid + 1) * per); ++i, ++u) {
-            const double d = dloc[u];
-            if (!g.strip || d != 0.0) {
-                const int pos = nk + ip;
-                g.hW[nxt][pos] = 0.0;
-                g.tagW[nxt][pos] = i;
-                g.valW[nxt][pos] = d;
-                g.rkW[nxt][pos] = z + ip;
-                g.skW[nxt][z + ip] = 0.0;
-                ++ip;
-            }
-        }
-        for (int pos = tid; pos < nk; pos += APPLY_THREADS) {
-            const int code = orderW[pl.mW + pos];
-            double h, val = 0.0;
-            int tag = -1;
-            if (code < nmap) {
-                h = g.hS[t * g.q + code];
-            } else {
-                const int j = code - nmap;
-                h = g.hW[par][j]; tag = g.tagW[par][j]; val = g.valW[par][j];
-            }
-            const int rk = pos < z ? pos : pos + nd;
-            g.hW[nxt][pos] = h;
-            g.tagW[nxt][pos] = tag;
-            g.valW[nxt][pos] = val;
-            g.rkW[nxt][pos] = rk;
-            g.skW[nxt][rk] = h;
-        }
-        if (tid == 0) {
-            WState ns; ns.pW = nk + nd; ns.cur = st.cur ^ 1; ns.pad0 = ns.pad1 = 0;
-            g.st[nxt] = ns;
-        }
-    } else {
-        for (int sigma = tid; sigma < pl.pinW; sigma += APPLY_THREADS) {
-            const int code = orderW[sigma];
-            double h, val = 0.0;
-            int tag = -1, pos;
-            if (code < nmap) {
-                h = g.hS[t * g.q + code];
-                pos = st.pW + g.cposS[t * g.q + code];
-            } else {
-                const int j = code - nmap;
-                h = g.hW[par][j]; tag = g.tagW[par][j]; val = g.valW[par][j];
-                pos = j;
-            }
-            g.hW[nxt][pos] = h;
-            g.tagW[nxt][pos] = tag;
-            g.valW[nxt][pos] = val;
-            g.rkW[nxt][pos] = sigma;
-            g.skW[nxt][sigma] = h;
-        }
-        if (tid == 0) {
-            WState ns; ns.pW = pl.pinW; ns.cur = st.cur; ns.pad0 = ns.pad1 = 0;
-            g.st[nxt] = ns;
-        }
+    int p = scan[tid] - cnt;
+    for (int i = tid * per; i < min(g.n, (tid + 1) * per); ++i) {
+        const double d = g.Rd[(int64_t)(k - 1) * g.ld + i];
+        if (!g.strip || d != 0.0) g.Rrow[(int64_t)(k - 1) * g.n + p++] = i;
     }
-    // ---------------- centres: c_k = P c0 + cW ; cW += P cV (GLGM06/reach.jl:48,54) ----------------
-    const double* yc0 = g.Y + (int64_t)(t * g.q + nmap) * g.ld;
-    const double* ycV = yc0 + g.ld;
-    for (int i = tid; i < g.n; i += APPLY_THREADS) {
-        const double cw = g.cW[i];
-        g.Rc[(int64_t)(k - 1) * g.ld + i] = yc0[i] + cw;
-        g.cW[i] = cw + ycV[i];
-    }
+    if (tid == 0) g.meta[k - 1] = make_int2(pl.pin - pl.m, scan[255]);
 }
 
 // Dense box generators of the reach sets of steps [k0, k1): column nk + c of slot k is d[row_c] e_{row_c}.
@@ -550,31 +639,24 @@ __global__ void __launch_bounds__(256) expand_diag_kernel(GP g, int k0, int k1) 
     }
 }
 
-// W_1 = V (GLGM06/reach.jl:41-42): the valid columns of the GV segment of X become the first W.
-__global__ void __launch_bounds__(256) init_w_kernel(GP g, const double* X) {
+// Dense copy of the current W in logical order (box generators synthesised).  out: n x pW, leading dimension ldo.
+__global__ void __launch_bounds__(256) materialize_w_kernel(GP g, double* __restrict__ out, int ldo) {
+    const int pW = *g.wCount;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        WState s; s.pW = g.cntS[1]; s.cur = 0; s.pad0 = s.pad1 = 0;
-        g.st[0] = s;
-    }
-    if (warp >= g.pV) return;
-    const double h = g.hS[g.p0 + warp];
-    if (!(h < INFINITY)) return;
-    const int pos = g.cposS[g.p0 + warp];
-    const double2* c2 = reinterpret_cast<const double2*>(X + (int64_t)(g.p0 + warp) * g.ld);
-    double2* d2 = reinterpret_cast<double2*>(g.GW[0] + (int64_t)pos * g.ld);
-    for (int i = lane; i < g.ld / 2; i += 32) d2[i] = c2[i];
-    if (lane == 0) {
-        const int rk = g.rkS[g.p0 + warp];
-        g.hW[0][pos] = h;
-        g.tagW[0][pos] = -1;
-        g.valW[0][pos] = 0.0;
-        g.rkW[0][pos] = rk;
-        g.skW[0][rk] = h;
+    if (warp >= pW) return;
+    const int ref = g.wRefs[warp];
+    double* dst = out + (int64_t)g.wPos[warp] * ldo;
+    if (ref >= 0) {
+        const double* src = g.Yall + (int64_t)ref * g.ld;
+        for (int i = lane; i < g.n; i += 32) dst[i] = src[i];
+    } else {
+        int kt, it;
+        tag_decode(ref, g.n, kt, it);
+        const double val = g.Wd[(int64_t)kt * g.ld + it];
+        for (int i = lane; i < g.n; i += 32) dst[i] = i == it ? val : 0.0;
     }
 }
 
-// homogeneous flowpipes: number of non-zero columns per step is not tracked (linear_map of a non-singular Phi);
 // box hull of zonotopes: lo/hi[i] = c[i] -/+ sum_j |G[i,j]|
 __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int64_t member_stride, int batch,
                                                        const double* __restrict__ G, const double* __restrict__ c,
@@ -589,18 +671,6 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     const double ci = c[(int64_t)b * c_stride + i];
     lo[(int64_t)b * n + i] = ci - s;
     hi[(int64_t)b * n + i] = ci + s;
-}
-
-// Dense copy of the current W (parity par): tagged box generators are synthesised.  out: n x pW, leading dim ldo.
-__global__ void __launch_bounds__(256) materialize_w_kernel(GP g, int par, double* __restrict__ out, int ldo) {
-    const WState st = g.st[par];
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= st.pW) return;
-    const int tag = g.tagW[par][warp];
-    const double val = g.valW[par][warp];
-    const double* src = g.GW[st.cur] + (int64_t)warp * g.ld;
-    double* dst = out + (int64_t)warp * ldo;
-    for (int i = lane; i < g.n; i += 32) dst[i] = tag < 0 ? src[i] : (i == tag ? val : 0.0);
 }
 
 template <typename T>
@@ -623,16 +693,19 @@ struct Flowpipe {
     int64_t nc = 1;                 // homogeneous: number of centre columns (ensemble: one per member)
     GP g{};
     DMat Phi, PowA, PowB;
-    double* X = nullptr;            // n x q  [G0 | GV | c0 | cV]
-    double* stack[2] = {nullptr, nullptr};
-    double* Hflow = nullptr;        // homogeneous: the flowpipe itself, N slots of q columns
+    double* Hflow = nullptr;        // archive of Phi^j X: the flowpipe itself in the homogeneous case
+    double* scrKeys = nullptr;      // chain scratch when the W list does not fit in shared memory
+    int* scrInts = nullptr;
+    size_t chain_smem = 0;
+    int chain_use_smem = 1;
+    cudaStream_t side = nullptr;    // numerics of batch b overlap the GEMM of batch b+1
     std::vector<void*> owned;
     std::vector<int2> meta_host;
     bool ran = false;
     double run_ms = 0, gemm_ms = 0, gemm_flops = 0, reduce_ms = 0, reduce_bytes = 0;
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
-    double* stage = nullptr;        // staging for strided downloads
+    double* stage = nullptr;        // staging for box queries
 };
 
 void flowpipe_free(Flowpipe* F) {
@@ -640,6 +713,7 @@ void flowpipe_free(Flowpipe* F) {
     dmat_free(F->Phi); dmat_free(F->PowA); dmat_free(F->PowB);
     for (void* p : F->owned) cudaFree(p);
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
+    if (F->side) cudaStreamDestroy(F->side);
     delete F;
 }
 
@@ -669,7 +743,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         F->ctx = ctx; F->n = n; F->p0 = p0; F->pV = pV; F->N = N; F->r = max_order; F->flags = flags;
         F->homog = homog;
         F->record = (flags & REACH_GLGM06_RECORD_SELECTIONS) != 0;
-        F->ld = round_up(n, 4);   // 32-byte aligned columns; the GEMM's K-tail over-read hits finite data times zero pad
+        F->ld = round_up(n, 4);   // 32-byte aligned columns
         const int64_t ld = F->ld;
         F->nc = homog ? nc : 1;
         F->q = homog ? p0 + F->nc : p0 + pV + 2;
@@ -688,80 +762,90 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         GP& g = F->g;
         g.n = (int)n; g.ld = (int)ld; g.p0 = (int)p0; g.pV = (int)pV; g.q = (int)q;
         g.strip = (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) ? 0 : 1;
-        if (homog) {
-            // the flowpipe storage is the stack: slot k-1 = Phi^{k-1} [G0 | c0]  (ensemble: [G_0 .. G_{b-1} | c_0 .. c_{b-1}])
-            const size_t cols = (size_t)N * q + 256;
-            size_t free_b = 0, total_b = 0;
-            REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            if ((double)cols * ld * 8.0 > 0.92 * (double)free_b) {
-                char buf[256];
-                snprintf(buf, sizeof(buf), "glgm06: homogeneous flowpipe needs %.1f GB of HBM (N=%lld sets of %lld columns), "
-                         "%.1f GB free: shard the ensemble across GPUs or shorten the horizon",
-                         (double)cols * ld * 8.0 / 1e9, (long long)N, (long long)q, (double)free_b / 1e9);
-                throw Error(REACH_EUNSUPPORTED, buf);
-            }
-            F->Hflow = (double*)own(dalloc<double>(ctx, cols * ld));
-            up2d(F->Hflow, G0, ldg0, p0);
-            up2d(F->Hflow + p0 * ld, c0, n, nc);
-        } else {
+        g.record = F->record ? 1 : 0;
+        g.nwords = 2 * (int)ceil_div(ld / 2, 32);
+        // ---- archive: slot j = Phi^j X  (homogeneous: X = [G0 | c0], the flowpipe itself; ensemble: [G_0 .. | c_0 ..])
+        const size_t cols = (size_t)N * q + 256;
+        size_t free_b = 0, total_b = 0;
+        REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        double need = (double)cols * ld * 8.0;
+        if (!homog) {
             const int64_t rn = max_order * n;
             g.rn = rn; g.nkeep = n * (max_order - 1);
             g.capW = (int)std::max<int64_t>(rn, pV) + 8;
             g.capR = (int)std::max<int64_t>(rn, p0) + 8;
             g.capListR = (int)p0 + g.capW;
             g.capListW = g.capW + (int)pV;
-            F->X = (double*)own(dalloc<double>(ctx, (size_t)(q + 128) * ld));
-            up2d(F->X, G0, ldg0, p0);
-            up2d(F->X + p0 * ld, GV, ldgv, pV);
-            up2d(F->X + (p0 + pV) * ld, c0, n, 1);
-            up2d(F->X + (p0 + pV + 1) * ld, cV, n, 1);
-            for (int i = 0; i < 2; ++i) {
-                F->stack[i] = (double*)own(dalloc<double>(ctx, (size_t)(s * q + 128) * ld));
-                g.GW[i] = (double*)own(dalloc<double>(ctx, (size_t)(g.capW + (int)pV + 8) * ld));
-                g.hW[i] = (double*)own(dalloc<double>(ctx, g.capListW + 8));
-                g.valW[i] = (double*)own(dalloc<double>(ctx, g.capListW + 8));
-                g.skW[i] = (double*)own(dalloc<double>(ctx, g.capListW + 8));
-                g.tagW[i] = (int*)own(dalloc<int>(ctx, g.capListW + 8));
-                g.rkW[i] = (int*)own(dalloc<int>(ctx, g.capListW + 8));
-            }
-            g.hS = (double*)own(dalloc<double>(ctx, s * q + 8));
-            g.skS = (double*)own(dalloc<double>(ctx, s * q + 8));
-            g.rkS = (int*)own(dalloc<int>(ctx, s * q + 8));
-            g.cposS = (int*)own(dalloc<int>(ctx, s * q + 8));
-            g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
-            g.st = (WState*)own(dalloc<WState>(ctx, 2));
-            g.cW = (double*)own(dalloc<double>(ctx, ld));
-            g.order_stride = F->record ? (int64_t)(g.capListR + g.capListW) : 0;
-            const size_t order_len = (size_t)(g.capListR + g.capListW) * (F->record ? (size_t)(N + 1) : 1);
-            g.orderR = (int*)own(dalloc<int>(ctx, order_len));
-            g.orderW = g.orderR + g.capListR;
-            g.rec_stride = g.order_stride;
-            g.recH = F->record ? (double*)own(dalloc<double>(ctx, order_len)) : nullptr;
-            g.plans = (StepPlan*)own(dalloc<StepPlan>(ctx, N + 2));
+            g.capDisc = (int)std::max<int64_t>(g.capW + pV - g.nkeep, 0) + 8;
+            g.smax = (int)s;
             g.slot = ld * (int64_t)g.capR;
-            size_t free_b = 0, total_b = 0;
-            REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const double need = (double)N * (double)g.slot * 8.0;
-            if (need > 0.92 * (double)free_b) {
-                char buf[256];
-                snprintf(buf, sizeof(buf), "glgm06: flowpipe needs %.1f GB of HBM (N=%lld sets of %d x %d), %.1f GB free",
-                         need / 1e9, (long long)N, (int)n, g.capR, (double)free_b / 1e9);
-                throw Error(REACH_EUNSUPPORTED, buf);
+            need += (double)N * (double)g.slot * 8.0;
+            REACH_REQUIRE((double)N * (double)std::max<int64_t>(q, n) < 2.0e9, "glgm06: N * columns exceeds the 32-bit reference range");
+        }
+        if (need > 0.92 * (double)free_b) {
+            char buf[320];
+            snprintf(buf, sizeof(buf), "glgm06: the flowpipe needs %.1f GB of HBM (N=%lld sets, %lld mapped columns per step%s), "
+                     "%.1f GB free: shard the ensemble across GPUs or shorten the horizon",
+                     need / 1e9, (long long)N, (long long)q, homog ? "" : " + the reduced zonotopes", (double)free_b / 1e9);
+            throw Error(REACH_EUNSUPPORTED, buf);
+        }
+        F->Hflow = (double*)own(dalloc<double>(ctx, cols * ld));
+        g.Yall = F->Hflow;
+        up2d(F->Hflow, G0, ldg0, p0);
+        if (homog) {
+            up2d(F->Hflow + p0 * ld, c0, n, F->nc);
+        } else {
+            up2d(F->Hflow + p0 * ld, GV, ldgv, pV);
+            up2d(F->Hflow + (p0 + pV) * ld, c0, n, 1);
+            up2d(F->Hflow + (p0 + pV + 1) * ld, cV, n, 1);
+            const size_t sq = (size_t)s * q + 8;
+            g.hS = (double*)own(dalloc<double>(ctx, sq));
+            g.skS = (double*)own(dalloc<double>(ctx, sq));
+            g.rkS = (int*)own(dalloc<int>(ctx, sq));
+            g.cposS = (int*)own(dalloc<int>(ctx, sq));
+            g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
+            g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords : 1));
+            g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
+            g.wKeys = (double*)own(dalloc<double>(ctx, g.capW));
+            g.wRefs = (int*)own(dalloc<int>(ctx, g.capW));
+            g.wPos = (int*)own(dalloc<int>(ctx, g.capW));
+            g.wCount = (int*)own(dalloc<int>(ctx, 1));
+            g.snKeys = (double*)own(dalloc<double>(ctx, (size_t)s * g.capW));
+            g.snRefs = (int*)own(dalloc<int>(ctx, (size_t)s * g.capW));
+            g.snPos = (int*)own(dalloc<int>(ctx, (size_t)s * g.capW));
+            g.snCount = (int*)own(dalloc<int>(ctx, s));
+            g.planW = (PlanW*)own(dalloc<PlanW>(ctx, N + 2));
+            g.planR = (PlanR*)own(dalloc<PlanR>(ctx, N + 2));
+            g.dlistW = (int*)own(dalloc<int>(ctx, (size_t)s * g.capDisc));
+            g.tcnt = (int*)own(dalloc<int>(ctx, (size_t)s * n));
+            g.tsrc = (int*)own(dalloc<int>(ctx, (size_t)s * n * 4));
+            g.orderR = (int*)own(dalloc<int>(ctx, (size_t)s * g.capListR));
+            g.partW = (double*)own(dalloc<double>(ctx, (size_t)s * NBW * ld));
+            g.partR = (double*)own(dalloc<double>(ctx, (size_t)s * NBR * ld));
+            g.cW = (double*)own(dalloc<double>(ctx, ld));
+            if (F->record) {
+                g.recOrdW = (int*)own(dalloc<int>(ctx, (size_t)(N + 2) * g.capListW));
+                g.recHW = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * g.capListW));
+                g.recOrdR = (int*)own(dalloc<int>(ctx, (size_t)(N + 2) * g.capListR));
+                g.recHR = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * g.capListR));
             }
             g.Rg = (double*)own(dalloc<double>(ctx, (size_t)N * g.slot, false));
             g.Rc = (double*)own(dalloc<double>(ctx, (size_t)N * ld));
             g.Rd = (double*)own(dalloc<double>(ctx, (size_t)N * ld));
             g.Rrow = (int*)own(dalloc<int>(ctx, (size_t)N * n));
             g.meta = (int2*)own(dalloc<int2>(ctx, N + 1));
-            g.partial = (double*)own(dalloc<double>(ctx, (size_t)NBOX * ld));
-            g.ticket = (unsigned*)own(dalloc<unsigned>(ctx, 1));
-            // R_1 = Omega0 (GLGM06/reach.jl:39-40)
-            if (p0 > 0)
-                REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
-            REACH_CUDA(cudaMemcpyAsync(g.Rc, c0, n * 8, cudaMemcpyHostToDevice, st));
-            if (ld > n) {   // pad rows of slot 0 are read by nobody, but keep them finite
-                REACH_CUDA(cudaMemset2DAsync(g.Rg + n, ld * 8, 0, (ld - n) * 8, p0 > 0 ? p0 : 1, st));
+            // chain working set: keys 2 cap doubles, refs/pos 4 cap ints, sigma (cap + pV) ints
+            F->chain_smem = (size_t)g.capW * (2 * 8 + 4 * 4) + (size_t)(g.capW + pV) * 4 + 64;
+            F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
+            if (!F->chain_use_smem) {
+                F->scrKeys = (double*)own(dalloc<double>(ctx, 2 * (size_t)g.capW));
+                F->scrInts = (int*)own(dalloc<int>(ctx, 5 * (size_t)g.capW + pV + 8));
             }
+            REACH_CUDA(cudaStreamCreateWithFlags(&F->side, cudaStreamNonBlocking));
+            // R_1 = Omega0 (GLGM06/reach.jl:39-40)
+            if (p0 > 0) REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
+            if (ld > n) REACH_CUDA(cudaMemset2DAsync(g.Rg + n, ld * 8, 0, (ld - n) * 8, p0 > 0 ? p0 : 1, st));
+            REACH_CUDA(cudaMemcpyAsync(g.Rc, c0, n * 8, cudaMemcpyHostToDevice, st));
             const int2 m1 = make_int2((int)p0, 0);
             REACH_CUDA(cudaMemcpyAsync(g.meta, &m1, sizeof(int2), cudaMemcpyHostToDevice, st));
         }
@@ -780,6 +864,51 @@ static cudaEvent_t next_event(Flowpipe* F, size_t& used) {
         F->evs.push_back(e);
     }
     return F->evs[used++];
+}
+
+// scores + stable order of the mapped segments of `cnt` steps whose first slot is `slot0`
+static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStream_t st) {
+    Ctx* ctx = F->ctx;
+    g.Y = F->Hflow + slot0 * F->q * F->ld;
+    g.col0 = slot0 * F->q;
+    const int per = g.p0 + g.pV;
+    if (per > 0) {
+        score_stack_kernel<<<(unsigned)ceil_div((int64_t)cnt * per, 8), 256, 0, st>>>(g, cnt);
+        const int maxlen = std::max(g.p0, g.pV);
+        dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(maxlen, 256)), (unsigned)(cnt * 2));
+        sort_segments_kernel<<<grid, 256, 0, st>>>(g);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    } else {
+        REACH_CUDA(cudaMemsetAsync(g.cntS, 0, sizeof(int) * 2 * cnt, st));
+    }
+}
+
+// selection chain + batched numerics of steps [k0, k0 + cnt) (their slots k-1 are in the archive already)
+static void process_steps(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
+    Ctx* ctx = F->ctx;
+    score_and_sort(F, g, k0 - 1, cnt, st);
+    chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, k0, cnt, F->chain_use_smem, F->scrKeys,
+                                                                                F->scrInts);
+    const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
+    wbox_partial_kernel<<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
+    rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
+    apply_r_kernel<<<dim3(NBR + COPY_CTAS, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
+    expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches += 7;
+}
+
+static void set_kernel_attributes(Flowpipe* F) {
+    static bool done = false;
+    if (done) return;
+    REACH_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    done = true;
+    (void)F;
 }
 
 void flowpipe_run(Flowpipe* F) {
@@ -809,121 +938,60 @@ void flowpipe_run(Flowpipe* F) {
         F->gemm_launches++;
         F->gemm_flops += 2.0 * (double)n * n * n;
     };
-    const int64_t npow = N - 1;          // Y_1 .. Y_{N-1}
-    if (F->homog) {
-        // slot j = Phi^j [G0 | c0] (R_{j+1}, GLGM06/reach.jl:15-19).  With the power Phi^w in hand, slots
-        // [have, have + w) = Phi^w * slots [have - w, have): doubling until w = s, then s slots per GEMM.
-        const DMat* pw = &F->Phi;
-        DMat* spare[2] = {&F->PowA, &F->PowB};
-        int sp = 0;
-        int64_t have = 1, w = 1;
-        while (have < N) {
-            const int64_t cnt = std::min(w, N - have);
-            timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
-            have += cnt;
-            if (have < N && w < s) {
-                square(*pw, *spare[sp]);
-                pw = spare[sp];
-                sp ^= 1;
-                w *= 2;
-            }
-        }
-        REACH_CUDA(cudaEventRecord(ctx->ev1, st));
-        REACH_CUDA(cudaEventSynchronize(ctx->ev1));
-        float ms = 0;
-        REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        F->run_ms = ms;
-        F->gemm_ms = 0; F->reduce_ms = 0;
-        for (auto& pr : gemm_ev) {
-            float t = 0;
-            REACH_CUDA(cudaEventElapsedTime(&t, F->evs[pr.first], F->evs[pr.second]));
-            F->gemm_ms += t;
-        }
-        F->meta_host.assign(N, make_int2((int)F->p0, 0));
-        F->ran = true;
-        return;
+    if (!F->homog) {
+        set_kernel_attributes(F);
+        // W_1 = V, cW_1 = cV (GLGM06/reach.jl:41-42)
+        REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (g.p0 + g.pV + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
+        score_and_sort(F, g, 0, 1, st);
+        init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 256)), 256, 0, st>>>(g);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
     }
-    // ---------------- inhomogeneous ----------------
-    const int per = (int)(g.p0 + g.pV);
-    auto score_and_sort = [&](const double* Y, int cnt) {
-        g.Y = Y;
-        if (per > 0) {
-            const int warps = cnt * per;
-            score_stack_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(g, cnt);
-            REACH_CUDA(cudaGetLastError());
-            const int maxlen = (int)std::max(g.p0, g.pV);
-            dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(maxlen, 256)), (unsigned)(cnt * 2));
-            sort_segments_kernel<<<grid, 256, 0, st>>>(g);
-            REACH_CUDA(cudaGetLastError());
-            ctx->launches += 2;
-        } else {
-            REACH_CUDA(cudaMemsetAsync(g.cntS, 0, sizeof(int) * 2 * cnt, st));
+    // slot j = Phi^j X.  With Phi^w in hand, slots [have, have + w) = Phi^w * slots [have - w, have): doubling until
+    // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) are processed as one batch; their
+    // selection chain and numerics run on the side stream and overlap the next GEMM.
+    const DMat* pw = &F->Phi;
+    DMat* spare[2] = {&F->PowA, &F->PowB};
+    int sp = 0;
+    int64_t have = 1, w = 1;
+    cudaEvent_t ev_gemm = nullptr, ev_side = nullptr;
+    if (!F->homog) {
+        ev_gemm = next_event(F, ev_used);
+        ev_side = next_event(F, ev_used);
+        REACH_CUDA(cudaEventRecord(ev_gemm, st));
+        REACH_CUDA(cudaStreamWaitEvent(F->side, ev_gemm, 0));       // side stream starts after the initialisation
+    }
+    while (have < N) {
+        const int64_t cnt = std::min(w, N - have);
+        timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
+        if (!F->homog) {
+            REACH_CUDA(cudaEventRecord(ev_gemm, st));
+            REACH_CUDA(cudaStreamWaitEvent(F->side, ev_gemm, 0));
+            cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
+            red_ev.push_back({ev_used - 2, ev_used - 1});
+            REACH_CUDA(cudaEventRecord(e0, F->side));
+            process_steps(F, g, (int)have + 1, (int)cnt, F->side);
+            REACH_CUDA(cudaEventRecord(e1, F->side));
         }
-    };
-    // W_1 = V (GLGM06/reach.jl:41-42): cW = cV, scores / order of X's own input segment
-    REACH_CUDA(cudaMemcpyAsync(g.cW, F->X + (g.p0 + g.pV + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
-    score_and_sort(F->X, 1);
-    init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 8)), 256, 0, st>>>(g, F->X);
-    REACH_CUDA(cudaGetLastError());
-    ctx->launches++;
-    if (npow > 0) {
-        // first block by doubling: stack0[0] = Phi X, stack0[have..2have) = Phi^have stack0[0..have)
-        timed_gemm(q, F->Phi, F->X, F->stack[0]);
-        const DMat* pw = &F->Phi;
-        DMat* spare[2] = {&F->PowA, &F->PowB};
-        int sp = 0;
-        for (int64_t have = 1; have < s; have *= 2) {
-            timed_gemm(have * q, *pw, F->stack[0], F->stack[0] + have * q * ld);
+        have += cnt;
+        if (have < N && w < s) {
             square(*pw, *spare[sp]);
             pw = spare[sp];
             sp ^= 1;
-        }
-        // pw = Phi^s
-        const size_t smem_keys = (size_t)(g.p0 + g.capW + g.pV) * sizeof(double);
-        const int use_smem = smem_keys <= 200 * 1024 ? 1 : 0;
-        static bool attr_set = false;
-        if (use_smem && !attr_set) {
-            REACH_CUDA(cudaFuncSetAttribute(rank_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
-        const size_t apply_smem = (size_t)(APPLY_THREADS / 32) * ld * sizeof(double);
-        static bool apply_attr = false;
-        if (!apply_attr) {
-            REACH_CUDA(cudaFuncSetAttribute(apply_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-            apply_attr = true;
-        }
-        const int rank_threads = g.p0 + 2 * g.capW + g.pV;
-        const unsigned rank_grid = (unsigned)ceil_div(rank_threads, 256);
-        const unsigned apply_grid = NBOX + 2 * (unsigned)ctx->sm_count;
-        const int64_t nblocks = ceil_div(npow, s);
-        int cur = 0;
-        for (int64_t b = 0; b < nblocks; ++b) {
-            const int cnt = (int)std::min<int64_t>(s, npow - b * s);
-            if (b > 0) {
-                timed_gemm((int64_t)cnt * q, *pw, F->stack[cur ^ 1], F->stack[cur]);
-            }
-            cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
-            red_ev.push_back({ev_used - 2, ev_used - 1});
-            REACH_CUDA(cudaEventRecord(e0, st));
-            score_and_sort(F->stack[cur], cnt);
-            for (int t = 0; t < cnt; ++t) {
-                const int k = (int)(b * s) + t + 2;
-                rank_lists_kernel<<<rank_grid, 256, use_smem ? smem_keys : 0, st>>>(g, t, k, use_smem);
-                apply_step_kernel<<<apply_grid, APPLY_THREADS, apply_smem, st>>>(g, t, k);
-            }
-            REACH_CUDA(cudaGetLastError());
-            const int k0 = (int)(b * s) + 2;
-            dim3 eg(8, (unsigned)cnt);
-            expand_diag_kernel<<<eg, 256, 0, st>>>(g, k0, k0 + cnt);
-            REACH_CUDA(cudaGetLastError());
-            REACH_CUDA(cudaEventRecord(e1, st));
-            ctx->launches += 2 * (uint64_t)cnt + 1;
-            cur ^= 1;
+            w *= 2;
         }
     }
+    if (!F->homog) {
+        REACH_CUDA(cudaEventRecord(ev_side, F->side));
+        REACH_CUDA(cudaStreamWaitEvent(st, ev_side, 0));
+    }
     REACH_CUDA(cudaEventRecord(ctx->ev1, st));
-    F->meta_host.resize(N);
-    REACH_CUDA(cudaMemcpyAsync(F->meta_host.data(), g.meta, sizeof(int2) * N, cudaMemcpyDeviceToHost, st));
+    if (F->homog) {
+        F->meta_host.assign(N, make_int2((int)F->p0, 0));
+    } else {
+        F->meta_host.resize(N);
+        REACH_CUDA(cudaMemcpyAsync(F->meta_host.data(), g.meta, sizeof(int2) * N, cudaMemcpyDeviceToHost, st));
+    }
     REACH_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -957,44 +1025,40 @@ void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const do
         return;
     }
     std::vector<double> zeros((size_t)n * n, 0.0);
-    Flowpipe* F = flowpipe_create(ctx, n, zeros.data(), n, 0, c, nullptr, n, p, c, G, ldg, 2, r, flags & REACH_GLGM06_KEEP_ZERO_GENERATORS);
+    Flowpipe* F = flowpipe_create(ctx, n, zeros.data(), n, 0, c, nullptr, n, p, c, G, ldg, 1, r,
+                                  (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) | REACH_GLGM06_RECORD_SELECTIONS);
     double* dout = nullptr;
     try {
+        set_kernel_attributes(F);
         GP g = F->g;
-        g.Y = F->X;
-        const int per = (int)p;
-        score_stack_kernel<<<(unsigned)ceil_div(per, 8), 256, 0, st>>>(g, 1);
-        dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(per, 256)), 2u);
-        sort_segments_kernel<<<grid, 256, 0, st>>>(g);
-        REACH_CUDA(cudaGetLastError());
-        REACH_CUDA(cudaMemsetAsync(g.st, 0, 2 * sizeof(WState), st));       // W empty, buffer 0
-        const int rank_threads = g.p0 + 2 * g.capW + g.pV;
-        rank_lists_kernel<<<(unsigned)ceil_div(rank_threads, 256), 256, 0, st>>>(g, 0, 2, 0);
-        const size_t apply_smem = (size_t)(APPLY_THREADS / 32) * F->ld * sizeof(double);
-        REACH_CUDA(cudaFuncSetAttribute(apply_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        apply_step_kernel<<<NBOX + 2 * (unsigned)ctx->sm_count, APPLY_THREADS, apply_smem, st>>>(g, 0, 2);
+        // step "k = 1" on slot 0 with an empty W
+        REACH_CUDA(cudaMemsetAsync(g.wCount, 0, sizeof(int), st));
+        score_and_sort(F, g, 0, 1, st);
+        chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, 1, 1, F->chain_use_smem, F->scrKeys,
+                                                                                    F->scrInts);
+        const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
+        wbox_partial_kernel<<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
+        wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, 1, 1);
         REACH_CUDA(cudaGetLastError());
         const int64_t cap = g.capW;
         REACH_CUDA(cudaMalloc(&dout, sizeof(double) * (size_t)cap * n));
-        materialize_w_kernel<<<(unsigned)ceil_div(cap, 8), 256, 0, st>>>(g, 1, dout, (int)n);
+        materialize_w_kernel<<<(unsigned)ceil_div(cap, 8), 256, 0, st>>>(g, dout, (int)n);
         REACH_CUDA(cudaGetLastError());
-        ctx->launches += 5;
-        WState ns;
-        StepPlan pl;
-        REACH_CUDA(cudaMemcpyAsync(&ns, g.st + 1, sizeof(ns), cudaMemcpyDeviceToHost, st));
-        REACH_CUDA(cudaMemcpyAsync(&pl, g.plans + 2, sizeof(pl), cudaMemcpyDeviceToHost, st));
+        ctx->launches += 6;
+        int pW = 0;
+        PlanW pl;
+        REACH_CUDA(cudaMemcpyAsync(&pW, g.wCount, sizeof(int), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(&pl, g.planW + 1, sizeof(pl), cudaMemcpyDeviceToHost, st));
         REACH_CUDA(cudaStreamSynchronize(st));
-        *p_out = ns.pW;
-        if (ns.pW > 0)
-            REACH_CUDA(cudaMemcpy2DAsync(Gout, ldgo * 8, dout, n * 8, n * 8, ns.pW, cudaMemcpyDeviceToHost, st));
+        *p_out = pW;
+        if (pW > 0) REACH_CUDA(cudaMemcpy2DAsync(Gout, ldgo * 8, dout, n * 8, n * 8, pW, cudaMemcpyDeviceToHost, st));
         if (ind) {
-            std::vector<int> order(std::max(pl.pinW, 1));
-            std::vector<int> cpos(p);
-            REACH_CUDA(cudaMemcpyAsync(order.data(), g.orderW + 2 * g.order_stride, sizeof(int) * pl.pinW, cudaMemcpyDeviceToHost, st));
-            REACH_CUDA(cudaMemcpyAsync(cpos.data(), g.cposS, sizeof(int) * p, cudaMemcpyDeviceToHost, st));
+            std::vector<int> order(std::max(pl.pin, 1));
+            REACH_CUDA(cudaMemcpyAsync(order.data(), g.recOrdW + (int64_t)1 * g.capListW, sizeof(int) * pl.pin,
+                                       cudaMemcpyDeviceToHost, st));
             REACH_CUDA(cudaStreamSynchronize(st));
-            for (int sgm = 0; sgm < pl.pinW; ++sgm) ind[sgm] = cpos[order[sgm]];     // code == column (p0 = 0)
-            for (int64_t j = pl.pinW; j < p; ++j) ind[j] = -1;
+            for (int sgm = 0; sgm < pl.pin; ++sgm) ind[sgm] = order[sgm];
+            for (int64_t j = pl.pin; j < p; ++j) ind[j] = -1;
         }
         REACH_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
@@ -1156,12 +1220,18 @@ int32_t reach_flowpipe_selection(reach_flowpipe* fp, int64_t k, int32_t which, i
     REACH_REQUIRE(k >= 2 && k <= F->N && (which == 0 || which == 1), "reach_flowpipe_selection: bad k / which");
     const GP& g = F->g;
     cudaStream_t st = F->ctx->stream;
-    StepPlan pl;
-    REACH_CUDA(cudaMemcpyAsync(&pl, g.plans + k, sizeof(pl), cudaMemcpyDeviceToHost, st));
-    REACH_CUDA(cudaStreamSynchronize(st));
-    const int mode = which ? pl.modeW : pl.modeR;
-    const int pin = which ? pl.pinW : pl.pinR;
-    const int mm = which ? pl.mW : pl.mR;
+    int mode, pin, mm;
+    if (which) {
+        PlanW pl;
+        REACH_CUDA(cudaMemcpyAsync(&pl, g.planW + k, sizeof(pl), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        mode = pl.mode; pin = pl.pin; mm = pl.m;
+    } else {
+        PlanR pl;
+        REACH_CUDA(cudaMemcpyAsync(&pl, g.planR + k, sizeof(pl), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        mode = pl.mode; pin = pl.pin; mm = pl.m;
+    }
     if (mode == MODE_UNCHANGED) {
         if (p_in) *p_in = 0;
         if (m) *m = 0;
@@ -1169,44 +1239,13 @@ int32_t reach_flowpipe_selection(reach_flowpipe* fp, int64_t k, int32_t which, i
     }
     if (p_in) *p_in = pin;
     if (m) *m = mm;
-    if (!ind && !hout) return REACH_OK;
-    const int cap = which ? g.capListW : g.capListR;
-    std::vector<int> order(pin);
-    std::vector<double> hh(cap);
-    const int* dord = (which ? g.orderW : g.orderR) + k * g.order_stride;
-    const double* dh = g.recH + k * g.rec_stride + (which ? g.capListR : 0);
-    REACH_CUDA(cudaMemcpyAsync(order.data(), dord, sizeof(int) * pin, cudaMemcpyDeviceToHost, st));
-    REACH_CUDA(cudaMemcpyAsync(hh.data(), dh, sizeof(double) * cap, cudaMemcpyDeviceToHost, st));
+    // recorded per list element AFTER zero-generator removal, exactly LazySets' index space
+    const int64_t cap = which ? g.capListW : g.capListR;
+    const int* dord = (which ? g.recOrdW : g.recOrdR) + k * cap;
+    const double* dh = (which ? g.recHW : g.recHR) + k * cap;
+    if (ind) REACH_CUDA(cudaMemcpyAsync(ind, dord, sizeof(int) * pin, cudaMemcpyDeviceToHost, st));
+    if (hout) REACH_CUDA(cudaMemcpyAsync(hout, dh, sizeof(double) * pin, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaStreamSynchronize(st));
-    // list element index of a source code, then compaction over the dropped (all-zero) mapped generators
-    const int nmap = g.p0 + g.pV;
-    const int pW = which ? pin - pl.pC : pin - pl.pA;     // generators of W that went in
-    const int seg_len = which ? g.pV : g.p0;              // mapped segment (uncompacted)
-    const int seg_off = which ? pW : 0;                   // its offset in the list
-    std::vector<int> cpos(seg_len);
-    {
-        int c = 0;
-        for (int e = 0; e < seg_len; ++e) {
-            cpos[e] = c;
-            c += (hh[seg_off + e] < INFINITY);
-        }
-    }
-    for (int sgm = 0; sgm < pin; ++sgm) {
-        const int code = order[sgm];
-        int idx;      // compacted list index
-        double hv;
-        if (code < nmap) {
-            const int e = which ? code - g.p0 : code;
-            idx = (which ? pW : 0) + cpos[e];
-            hv = hh[seg_off + e];
-        } else {
-            const int j = code - nmap;
-            idx = which ? j : pl.pA + j;
-            hv = hh[which ? j : g.p0 + j];
-        }
-        if (ind) ind[sgm] = idx;
-        if (hout) hout[idx] = hv;
-    }
     return REACH_OK;
     FP_END(fp->ctx)
 }
