@@ -51,6 +51,7 @@ struct DMat {
 struct Ctx {
     int device = 0;
     int sm_count = 148;
+    int gemm_reserve_sms = 0;       // SMs the persistent GEMM leaves free (GLGM06 keeps one for its selection chain)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     std::string last_error;

@@ -285,7 +285,8 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
         configured = true;
     }
     const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    const int sms = ctx->sm_count - ctx->gemm_reserve_sms > 0 ? ctx->sm_count - ctx->gemm_reserve_sms : 1;
+    const int grid = tiles < sms ? tiles : sms;
     gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(p, tmap);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;

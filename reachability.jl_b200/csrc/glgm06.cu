@@ -43,7 +43,7 @@ struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of ste
 struct PlanR { int mode, pin, m, pA, pW, pad0, pad1, pad2; };   // R reduction of step k  (:48-49)
 
 struct GP {
-    int n, ld, p0, pV, q, strip, nwords, record;
+    int n, ld, p0, pV, q, strip, nwords, nwords4, record;
     int64_t nkeep, rn;          // n*(r-1), r*n
     int capW, capR, capListR, capListW, capDisc, smax;
     // ---- archive
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) score_stack_kernel(GP g, int cnt) {
     const double2* c2 = reinterpret_cast<const double2*>(g.Y + (int64_t)(t * g.q + c) * g.ld);
     const int n2 = g.ld / 2;
     double s = 0.0, m = 0.0;
-    uint32_t* mask = (g.strip && c >= g.p0) ? g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + (c - g.p0)) * g.nwords : nullptr;
+    uint32_t* mask = (g.strip && c >= g.p0) ? g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + (c - g.p0)) * g.nwords4 : nullptr;
     for (int it = 0; it * 32 < n2; ++it) {
         const int i = lane + 32 * it;
         double2 v = make_double2(0.0, 0.0);
@@ -189,53 +189,118 @@ __global__ void __launch_bounds__(256) init_w_kernel(GP g) {
 // CHAIN: the W selections of steps [k0, k0 + cnt), one persistent CTA, state in shared memory (or global scratch when
 // it does not fit).  W list of step k = [W_{k-1} (logical order) | valid columns of P_{k-1} GV]; sigma = stable rank.
 // -----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, int use_smem, double* scrKeys,
-                                                                  int* scrInts) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, int use_smem, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     __shared__ unsigned orm[2 * MAX_IT];
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
     __shared__ int scan_s[CHAIN_THREADS / 32];
-    __shared__ int s_nd;
-    const int tid = threadIdx.x, cap = g.capW;
-    double* keys[2];
-    int *refs[2], *pos[2], *sig;
-    if (use_smem) {
-        keys[0] = reinterpret_cast<double*>(chain_sm);
-        keys[1] = keys[0] + cap;
-        refs[0] = reinterpret_cast<int*>(keys[1] + cap);
-    } else {
-        keys[0] = scrKeys;
-        keys[1] = keys[0] + cap;
-        refs[0] = scrInts;
-    }
-    refs[1] = refs[0] + cap;
-    pos[0] = refs[1] + cap;
-    pos[1] = pos[0] + cap;
-    sig = pos[1] + cap;                      // [cap + pV]
+    __shared__ int s_pC[64];
+    __shared__ int s_nd, s_cz;
+    const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
+    // working set (shared memory, or global scratch when the W list is too long): sorted keys and (ref, pos) payloads of
+    // W, double-buffered; the input segment C_t of two consecutive steps; a histogram for the merge; sigma of C_t.
+    double* base = use_smem ? reinterpret_cast<double*>(chain_sm) : scr;
+    double* kbuf0 = base;
+    double* kbuf1 = kbuf0 + cap;
+    double* cH0 = kbuf1 + cap;
+    double* cSk0 = cH0 + 2 * pV;
+    int2* pbuf0 = reinterpret_cast<int2*>(cSk0 + 2 * pV);
+    int2* pbuf1 = pbuf0 + cap;
+    int* hist = reinterpret_cast<int*>(pbuf1 + cap);          // [cap + 2]
+    int* sigC = hist + cap + 2;                                // [pV]
+    int* cRk0 = sigC + pV;                                     // [2][pV]
+    int* cCp0 = cRk0 + 2 * pV;                                 // [2][pV]
+    if (tid < cnt && tid < 64) s_pC[tid] = g.cntS[tid * 2 + 1];
     int pW = *g.wCount;
     for (int r = tid; r < pW; r += CHAIN_THREADS) {
-        keys[0][r] = g.wKeys[r];
-        refs[0][r] = g.wRefs[r];
-        pos[0][r] = g.wPos[r];
+        kbuf0[r] = g.wKeys[r];
+        pbuf0[r] = make_int2(g.wRefs[r], g.wPos[r]);
+    }
+    for (int e = tid; e < pV; e += CHAIN_THREADS) {
+        const int b0 = g.p0 + e;
+        cH0[e] = g.hS[b0]; cSk0[e] = g.skS[b0]; cRk0[e] = g.rkS[b0]; cCp0[e] = g.cposS[b0];
     }
     __syncthreads();
     int cur = 0;
     for (int t = 0; t < cnt; ++t) {
-        const int k = k0 + t, nxt = cur ^ 1;
+        const int k = k0 + t;
+        const int cb = t & 1;
+        const double* kc = cur ? kbuf1 : kbuf0;
+        double* kn = cur ? kbuf0 : kbuf1;
+        const int2* pc = cur ? pbuf1 : pbuf0;
+        int2* pn = cur ? pbuf0 : pbuf1;
+        const double* cH = cH0 + cb * pV;
+        const double* skC = cSk0 + cb * pV;
+        const int* cRk = cRk0 + cb * pV;
+        const int* cCp = cCp0 + cb * pV;
         const int baseC = t * g.q + g.p0;
-        const int pC = g.cntS[t * 2 + 1];
-        const double* skC = g.skS + baseC;
+        const int pC = s_pC[t];
+        // prefetch the next step's segment into registers (stored to the other buffer at the end of this step)
+        double pfH[2] = {0.0, 0.0}, pfS[2] = {0.0, 0.0};
+        int pfR[2] = {0, 0}, pfC[2] = {0, 0};
+        if (t + 1 < cnt) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CHAIN_THREADS;
+                if (e < pV) {
+                    const int b1 = (t + 1) * g.q + g.p0 + e;
+                    pfH[u] = g.hS[b1]; pfS[u] = g.skS[b1]; pfR[u] = g.rkS[b1]; pfC[u] = g.cposS[b1];
+                }
+            }
+        }
         const int pin = pW + pC;
         const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
         const int m = mode == MODE_REDUCE ? (int)(pin - g.nkeep) : 0;
         const int nk = pin - m;
-        // generators with score exactly 0 precede everything else; z of them survive the cut
-        const int cntzero = upper_bound(keys[cur], pW, 0.0) + upper_bound(skC, pC, 0.0);
-        const int z = max(0, cntzero - m);
+        // ---- S0: clear the merge histogram ----
+        for (int x = tid; x <= pW; x += CHAIN_THREADS) hist[x] = 0;
         if (tid < 2 * MAX_IT) orm[tid] = 0u;
         if (tid < g.n) tc_s[tid] = 0;
+        if (tid == 0) s_cz = upper_bound(kc, pW, 0.0) + upper_bound(skC, pC, 0.0);
         __syncthreads();
-        // ---- snapshot of W_{k-1} for the R reduction of this step, stable ranks, boxed list, row-support union ----
+        // generators with score exactly 0 precede everything else; z of them survive the cut
+        const int z = max(0, s_cz - m);
+        // ---- S1: insertion point of every input generator in the sorted W (the only binary searches of the step) ----
+        for (int e = tid; e < pV; e += CHAIN_THREADS) {
+            const double h = cH[e];
+            int sg = -1;
+            if (h < INFINITY) {
+                const int ip = upper_bound(kc, pW, h);          // W precedes C in the list: ties go to W
+                atomicAdd(&hist[ip], 1);
+                sg = cRk[e] + ip;
+            }
+            sigC[e] = sg;
+        }
+        __syncthreads();
+        // ---- S2: inclusive scan: hist[r] = # input generators sorted before W's rank r  =>  sigma_W(r) = r + hist[r] ----
+        {
+            const int chunk = (pW + CHAIN_THREADS) / CHAIN_THREADS;
+            const int lo = tid * chunk, hi = min(pW + 1, lo + chunk);
+            int sum = 0;
+            for (int x = lo; x < hi; ++x) sum += hist[x];
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) scan_s[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                int v = scan_s[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                scan_s[lane] = v;
+            }
+            __syncthreads();
+            int run = inc - sum + (wid ? scan_s[wid - 1] : 0);
+            for (int x = lo; x < hi; ++x) { run += hist[x]; hist[x] = run; }
+        }
+        __syncthreads();
+        // ---- S3: snapshot of W_{k-1} for the R reduction, boxed list, boxed box generators ----
         double* snK = g.snKeys + (int64_t)t * cap;
         int* snR = g.snRefs + (int64_t)t * cap;
         int* snP = g.snPos + (int64_t)t * cap;
@@ -243,57 +308,69 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
         int* recO = g.record ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
         double* recH = g.record ? g.recHW + (int64_t)k * g.capListW : nullptr;
         for (int r = tid; r < pW; r += CHAIN_THREADS) {
-            const double key = keys[cur][r];
-            const int ref = refs[cur][r], ps = pos[cur][r];
-            snK[r] = key; snR[r] = ref; snP[r] = ps;
-            const int sigma = r + lower_bound(skC, pC, key);
-            sig[r] = sigma;
-            if (recO) { recO[sigma] = ps; recH[ps] = key; }
+            const double key = kc[r];
+            const int2 py = pc[r];
+            snK[r] = key; snR[r] = py.x; snP[r] = py.y;
+            const int sigma = r + hist[r];
+            if (recO) { recO[sigma] = py.y; recH[py.y] = key; }
             if (sigma < m) {
-                dl[sigma] = ref;
-                if (g.strip) {
-                    if (ref >= 0) {
-                        const int j = ref / g.q, c = ref - j * g.q - g.p0;
-                        const uint32_t* mk = g.maskAll + ((int64_t)j * g.pV + c) * g.nwords;
-                        for (int w = 0; w < g.nwords; ++w) {
-                            const unsigned b = mk[w];
-                            if (b) atomicOr(&orm[w], b);
-                        }
-                    } else {
-                        int kt, it, w, b;
-                        tag_decode(ref, g.n, kt, it);
+                dl[sigma] = py.x;
+                if (py.x < 0) {      // boxed box generator: its value is an earlier W box vector entry
+                    int kt, it, w, b;
+                    tag_decode(py.x, g.n, kt, it);
+                    const int sl = atomicAdd(&tc_s[it], 1);
+                    if (sl < 4) g.tsrc[((int64_t)t * g.n + it) * 4 + sl] = kt;
+                    if (g.strip) {
                         mask_pos(it, w, b);
                         atomicOr(&orm[w], 1u << b);
                     }
                 }
-                if (ref < 0) {      // value = an earlier W box vector entry: remember its creation step for wseq_kernel
-                    int kt, it;
-                    tag_decode(ref, g.n, kt, it);
-                    const int sl = atomicAdd(&tc_s[it], 1);
-                    if (sl < 4) g.tsrc[((int64_t)t * g.n + it) * 4 + sl] = kt;
-                }
             }
         }
-        for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
-            const double h = g.hS[baseC + e];
-            int sigma = -1;
-            if (h < INFINITY) {
-                sigma = g.rkS[baseC + e] + upper_bound(keys[cur], pW, h);
-                if (recO) { const int li = pW + g.cposS[baseC + e]; recO[sigma] = li; recH[li] = h; }
-                if (sigma < m) {
-                    dl[sigma] = (int)(g.col0 + baseC + e);
-                    if (g.strip) {
-                        const uint32_t* mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + e) * g.nwords;
-                        for (int w = 0; w < g.nwords; ++w) {
-                            const unsigned b = mk[w];
-                            if (b) atomicOr(&orm[w], b);
+        for (int e = tid; e < pV; e += CHAIN_THREADS) {
+            const int sg = sigC[e];
+            if (sg >= 0) {
+                if (recO) { const int li = pW + cCp[e]; recO[sg] = li; recH[li] = cH[e]; }
+                if (sg < m) dl[sg] = (int)(g.col0 + baseC + e);
+            }
+        }
+        if (tid == 0) g.snCount[t] = pW;
+        if (g.strip && mode == MODE_REDUCE) {
+            // Row-support union of the boxed generators.  The boxed box generators alone usually cover every row
+            // (steady state): only otherwise are the masks of the dense ones fetched (vector loads, all in flight).
+            __syncthreads();
+            int covered = 0;
+            for (int w = 0; w < g.nwords; ++w) covered += __popc(orm[w]);
+            if (covered < g.n) {
+                const int nw4 = g.nwords4 / 4;
+                for (int x = tid; x < pW + pV; x += CHAIN_THREADS) {
+                    const uint32_t* mk = nullptr;
+                    if (x < pW) {
+                        const int ref = pc[x].x;
+                        if (x + hist[x] < m && ref >= 0) {
+                            const int j = ref / g.q, c = ref - j * g.q - g.p0;
+                            mk = g.maskAll + ((int64_t)j * pV + c) * g.nwords4;
+                        }
+                    } else {
+                        const int e = x - pW, sg = sigC[e];
+                        if (sg >= 0 && sg < m) mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)pV + e) * g.nwords4;
+                    }
+                    if (mk) {
+                        uint4 v[2 * MAX_IT / 4];
+#pragma unroll
+                        for (int u = 0; u < 2 * MAX_IT / 4; ++u)
+                            v[u] = u < nw4 ? reinterpret_cast<const uint4*>(mk)[u] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int u = 0; u < 2 * MAX_IT / 4; ++u) {
+                            if (v[u].x) atomicOr(&orm[4 * u + 0], v[u].x);
+                            if (v[u].y) atomicOr(&orm[4 * u + 1], v[u].y);
+                            if (v[u].z) atomicOr(&orm[4 * u + 2], v[u].z);
+                            if (v[u].w) atomicOr(&orm[4 * u + 3], v[u].w);
                         }
                     }
                 }
             }
-            sig[cap + e] = sigma;
         }
-        if (tid == 0) g.snCount[t] = pW;
         __syncthreads();
         if (tid < g.n) g.tcnt[(int64_t)t * g.n + tid] = tc_s[tid];
         // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode) ----
@@ -309,13 +386,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, flag);
-            const int lane = tid & 31, wid = tid >> 5;
             if (lane == 0) scan_s[wid] = __popc(bal);
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0;
-                for (int w = 0; w < CHAIN_THREADS / 32; ++w) { const int c = scan_s[w]; scan_s[w] = acc; acc += c; }
-                s_nd = acc;
+            if (wid == 0) {
+                const int c = scan_s[lane];
+                int v = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                scan_s[lane] = v - c;            // exclusive
+                if (lane == 31) s_nd = v;
             }
             __syncthreads();
             nd = s_nd;
@@ -324,34 +406,31 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
         // ---- the next W: sorted list (keys, refs) with logical positions ----
         if (mode == MODE_REDUCE) {
             for (int r = tid; r < pW; r += CHAIN_THREADS) {
-                const int sigma = sig[r];
+                const int sigma = r + hist[r];
                 if (sigma >= m) {
                     const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
-                    keys[nxt][rk] = keys[cur][r]; refs[nxt][rk] = refs[cur][r]; pos[nxt][rk] = ps;
+                    kn[rk] = kc[r]; pn[rk] = make_int2(pc[r].x, ps);
                 }
             }
-            for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
-                const int sigma = sig[cap + e];
+            for (int e = tid; e < pV; e += CHAIN_THREADS) {
+                const int sigma = sigC[e];
                 if (sigma >= m) {
                     const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
-                    keys[nxt][rk] = g.hS[baseC + e]; refs[nxt][rk] = (int)(g.col0 + baseC + e); pos[nxt][rk] = ps;
+                    kn[rk] = cH[e]; pn[rk] = make_int2((int)(g.col0 + baseC + e), ps);
                 }
             }
             if (flag) {
                 const int rk = z + iprime;
-                keys[nxt][rk] = 0.0; refs[nxt][rk] = tag_ref(k, tid, g.n); pos[nxt][rk] = nk + iprime;
+                kn[rk] = 0.0; pn[rk] = make_int2(tag_ref(k, tid, g.n), nk + iprime);
             }
         } else {
             for (int r = tid; r < pW; r += CHAIN_THREADS) {
-                const int rk = sig[r];
-                keys[nxt][rk] = keys[cur][r]; refs[nxt][rk] = refs[cur][r]; pos[nxt][rk] = pos[cur][r];
+                const int rk = r + hist[r];
+                kn[rk] = kc[r]; pn[rk] = pc[r];
             }
-            for (int e = tid; e < g.pV; e += CHAIN_THREADS) {
-                const int rk = sig[cap + e];
-                if (rk >= 0) {
-                    keys[nxt][rk] = g.hS[baseC + e]; refs[nxt][rk] = (int)(g.col0 + baseC + e);
-                    pos[nxt][rk] = pW + g.cposS[baseC + e];
-                }
+            for (int e = tid; e < pV; e += CHAIN_THREADS) {
+                const int rk = sigC[e];
+                if (rk >= 0) { kn[rk] = cH[e]; pn[rk] = make_int2((int)(g.col0 + baseC + e), pW + cCp[e]); }
             }
         }
         if (tid == 0) {
@@ -360,13 +439,30 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
             g.planW[k] = pl;
         }
         pW = mode == MODE_REDUCE ? nk + nd : pin;
-        cur = nxt;
+        cur ^= 1;
+        if (t + 1 < cnt) {
+            double* nH = cH0 + (cb ^ 1) * pV;
+            double* nS = cSk0 + (cb ^ 1) * pV;
+            int* nR = cRk0 + (cb ^ 1) * pV;
+            int* nC = cCp0 + (cb ^ 1) * pV;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CHAIN_THREADS;
+                if (e < pV) { nH[e] = pfH[u]; nS[e] = pfS[u]; nR[e] = pfR[u]; nC[e] = pfC[u]; }
+            }
+            for (int e = tid + 2 * CHAIN_THREADS; e < pV; e += CHAIN_THREADS) {
+                const int b1 = (t + 1) * g.q + g.p0 + e;
+                nH[e] = g.hS[b1]; nS[e] = g.skS[b1]; nR[e] = g.rkS[b1]; nC[e] = g.cposS[b1];
+            }
+        }
         __syncthreads();
     }
+    const double* kf = cur ? kbuf1 : kbuf0;
+    const int2* pf = cur ? pbuf1 : pbuf0;
     for (int r = tid; r < pW; r += CHAIN_THREADS) {
-        g.wKeys[r] = keys[cur][r];
-        g.wRefs[r] = refs[cur][r];
-        g.wPos[r] = pos[cur][r];
+        g.wKeys[r] = kf[r];
+        g.wRefs[r] = pf[r].x;
+        g.wPos[r] = pf[r].y;
     }
     if (tid == 0) *g.wCount = pW;
 }
@@ -446,30 +542,53 @@ __global__ void __launch_bounds__(256) wbox_partial_kernel(GP g, int k0) {
 
 // Sequential over the steps of the batch, parallel over rows: W box vectors (dense partials + discarded box
 // generators, whose values are earlier W box vectors) and the centres  c_k = P c0 + cW ; cW += P cV  (:48,:54).
+// Software-pipelined: everything of step t+1 that does not depend on the recurrence is loaded during step t.
+struct WseqIn {
+    int mode, tc, m;
+    int ks[4];
+    double base, yc0, ycV;
+};
+__device__ __forceinline__ WseqIn wseq_load(const GP& g, int k0, int t, int i) {
+    WseqIn w;
+    const PlanW pl = g.planW[k0 + t];
+    w.mode = pl.mode; w.m = pl.m;
+    const double* yc0 = g.Y + (int64_t)(t * g.q + g.p0 + g.pV) * g.ld;
+    w.yc0 = yc0[i];
+    w.ycV = yc0[g.ld + i];
+    w.base = 0.0; w.tc = 0;
+    w.ks[0] = w.ks[1] = w.ks[2] = w.ks[3] = 0;
+    if (pl.mode == MODE_REDUCE) {
+        for (int b = 0; b < NBW; ++b) w.base += g.partW[((int64_t)t * NBW + b) * g.ld + i];
+        w.tc = g.tcnt[(int64_t)t * g.n + i];
+        const int4 kk = *reinterpret_cast<const int4*>(g.tsrc + ((int64_t)t * g.n + i) * 4);
+        w.ks[0] = kk.x; w.ks[1] = kk.y; w.ks[2] = kk.z; w.ks[3] = kk.w;
+    }
+    return w;
+}
 __global__ void __launch_bounds__(128) wseq_kernel(GP g, int k0, int cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
-    const int nmap = g.p0 + g.pV;
     double cw = g.cW[i];
+    double dprev = 0.0;
+    int kprev = -1;
+    WseqIn w = wseq_load(g, k0, 0, i);
     for (int t = 0; t < cnt; ++t) {
         const int k = k0 + t;
-        const PlanW pl = g.planW[k];
-        const double* yc0 = g.Y + (int64_t)(t * g.q + nmap) * g.ld;
-        g.Rc[(int64_t)(k - 1) * g.ld + i] = yc0[i] + cw;
-        cw += yc0[g.ld + i];
-        if (pl.mode == MODE_REDUCE) {
-            double d = 0.0;
-            for (int b = 0; b < NBW; ++b) d += g.partW[((int64_t)t * NBW + b) * g.ld + i];
-            const int tc = g.tcnt[(int64_t)t * g.n + i];
-            if (tc <= 4) {          // creation steps ascending => fixed summation order
-                int ks[4];
-                for (int u = 0; u < tc; ++u) ks[u] = g.tsrc[((int64_t)t * g.n + i) * 4 + u];
-                for (int u = 1; u < tc; ++u)
+        WseqIn wn = w;
+        if (t + 1 < cnt) wn = wseq_load(g, k0, t + 1, i);
+        g.Rc[(int64_t)(k - 1) * g.ld + i] = w.yc0 + cw;
+        cw += w.ycV;
+        if (w.mode == MODE_REDUCE) {
+            double d = w.base;
+            if (w.tc <= 4) {          // creation steps ascending => fixed summation order
+                int ks[4] = {w.ks[0], w.ks[1], w.ks[2], w.ks[3]};
+                for (int u = 1; u < w.tc; ++u)
                     for (int v = u; v > 0 && ks[v - 1] > ks[v]; --v) { const int x = ks[v]; ks[v] = ks[v - 1]; ks[v - 1] = x; }
-                for (int u = 0; u < tc; ++u) d += fabs(g.Wd[(int64_t)ks[u] * g.ld + i]);
+                for (int u = 0; u < w.tc; ++u)
+                    d += fabs(ks[u] == kprev ? dprev : g.Wd[(int64_t)ks[u] * g.ld + i]);
             } else {                // rare: more than four box generators of one row boxed in the same step
                 const int* dl = g.dlistW + (int64_t)t * g.capDisc;
-                for (int s = 0; s < pl.m; ++s) {
+                for (int s = 0; s < w.m; ++s) {
                     const int ref = dl[s];
                     if (ref < 0) {
                         int kt, it;
@@ -479,7 +598,10 @@ __global__ void __launch_bounds__(128) wseq_kernel(GP g, int k0, int cnt) {
                 }
             }
             g.Wd[(int64_t)k * g.ld + i] = d;
+            dprev = d;
+            kprev = k;
         }
+        w = wn;
     }
     g.cW[i] = cw;
 }
@@ -694,8 +816,7 @@ struct Flowpipe {
     GP g{};
     DMat Phi, PowA, PowB;
     double* Hflow = nullptr;        // archive of Phi^j X: the flowpipe itself in the homogeneous case
-    double* scrKeys = nullptr;      // chain scratch when the W list does not fit in shared memory
-    int* scrInts = nullptr;
+    double* scr = nullptr;          // chain scratch when the W list does not fit in shared memory
     size_t chain_smem = 0;
     int chain_use_smem = 1;
     cudaStream_t side = nullptr;    // numerics of batch b overlap the GEMM of batch b+1
@@ -764,6 +885,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         g.strip = (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) ? 0 : 1;
         g.record = F->record ? 1 : 0;
         g.nwords = 2 * (int)ceil_div(ld / 2, 32);
+        g.nwords4 = (int)round_up(g.nwords, 4);
         // ---- archive: slot j = Phi^j X  (homogeneous: X = [G0 | c0], the flowpipe itself; ensemble: [G_0 .. | c_0 ..])
         const size_t cols = (size_t)N * q + 256;
         size_t free_b = 0, total_b = 0;
@@ -804,7 +926,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.rkS = (int*)own(dalloc<int>(ctx, sq));
             g.cposS = (int*)own(dalloc<int>(ctx, sq));
             g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
-            g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords : 1));
+            g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords4 + 4 : 4));
             g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
             g.wKeys = (double*)own(dalloc<double>(ctx, g.capW));
             g.wRefs = (int*)own(dalloc<int>(ctx, g.capW));
@@ -835,12 +957,10 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.Rrow = (int*)own(dalloc<int>(ctx, (size_t)N * n));
             g.meta = (int2*)own(dalloc<int2>(ctx, N + 1));
             // chain working set: keys 2 cap doubles, refs/pos 4 cap ints, sigma (cap + pV) ints
-            F->chain_smem = (size_t)g.capW * (2 * 8 + 4 * 4) + (size_t)(g.capW + pV) * 4 + 64;
+            // chain working set: keys 2 cap doubles, (ref, pos) 2 cap int2, histogram cap + 2 ints, 52 bytes per input generator
+            F->chain_smem = (size_t)g.capW * 36 + (size_t)pV * 52 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
-            if (!F->chain_use_smem) {
-                F->scrKeys = (double*)own(dalloc<double>(ctx, 2 * (size_t)g.capW));
-                F->scrInts = (int*)own(dalloc<int>(ctx, 5 * (size_t)g.capW + pV + 8));
-            }
+            if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side, cudaStreamNonBlocking));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
             if (p0 > 0) REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
@@ -888,8 +1008,7 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
 static void process_steps(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
     Ctx* ctx = F->ctx;
     score_and_sort(F, g, k0 - 1, cnt, st);
-    chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, k0, cnt, F->chain_use_smem, F->scrKeys,
-                                                                                F->scrInts);
+    chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, k0, cnt, F->chain_use_smem, F->scr);
     const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
     wbox_partial_kernel<<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
@@ -938,6 +1057,11 @@ void flowpipe_run(Flowpipe* F) {
         F->gemm_launches++;
         F->gemm_flops += 2.0 * (double)n * n * n;
     };
+    struct ReserveGuard {       // one SM stays free for the selection chain while the GEMMs of later batches run
+        Ctx* c; int old;
+        ReserveGuard(Ctx* c_, int v) : c(c_), old(c_->gemm_reserve_sms) { c->gemm_reserve_sms = v; }
+        ~ReserveGuard() { c->gemm_reserve_sms = old; }
+    } reserve(ctx, F->homog ? 0 : 1);
     if (!F->homog) {
         set_kernel_attributes(F);
         // W_1 = V, cW_1 = cV (GLGM06/reach.jl:41-42)
@@ -1034,8 +1158,7 @@ void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const do
         // step "k = 1" on slot 0 with an empty W
         REACH_CUDA(cudaMemsetAsync(g.wCount, 0, sizeof(int), st));
         score_and_sort(F, g, 0, 1, st);
-        chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, 1, 1, F->chain_use_smem, F->scrKeys,
-                                                                                    F->scrInts);
+        chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, 1, 1, F->chain_use_smem, F->scr);
         const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
         wbox_partial_kernel<<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, 1, 1);
