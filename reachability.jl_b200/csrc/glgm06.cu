@@ -42,6 +42,12 @@ constexpr int CHAIN_THREADS = 1024;
 struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of step k  (GLGM06/reach.jl:54-55)
 struct PlanR { int mode, pin, m, pA, pW, pad0, pad1, pad2; };   // R reduction of step k  (:48-49)
 
+struct __align__(16) WEnt {     // one generator of W in the sorted list: score, reference, logical position
+    double key;
+    int ref;
+    int pos;
+};
+
 struct GP {
     int n, ld, p0, pV, q, strip, nwords, nwords4, record;
     int64_t nkeep, rn;          // n*(r-1), r*n
@@ -55,8 +61,8 @@ struct GP {
     int64_t col0;               // archive column of Y's first column
     double* hS; int* rkS; int* cposS; double* skS; int* cntS;
     // ---- W chain state (sorted list) + per-step snapshots of the batch
-    double* wKeys; int* wRefs; int* wPos; int* wCount;
-    double* snKeys; int* snRefs; int* snPos; int* snCount;
+    WEnt* wEnt; int* wCount;
+    WEnt* snEnt; int* snCount;
     PlanW* planW; PlanR* planR;                 // [N+2]
     int* dlistW;                // [smax][capDisc] references of the generators boxed by the W reduction, sigma order
     int* tcnt; int* tsrc;       // [smax][n], [smax][n][4]: creation steps of the box generators boxed again, per row
@@ -155,11 +161,11 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
     if (blockIdx.x == 0 && threadIdx.x == 0) g.cntS[t * 2 + seg] = nvalid;
 }
 
-__device__ __forceinline__ int lower_bound(const double* a, int len, double key) {   // # entries < key
+__device__ __forceinline__ int lower_bound_ent(const WEnt* a, int len, double key) {   // # entries with key < key
     int lo = 0, hi = len;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
+        if (a[mid].key < key) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -179,43 +185,48 @@ __global__ void __launch_bounds__(256) init_w_kernel(GP g) {
     if (e >= g.pV) return;
     const double h = g.hS[g.p0 + e];
     if (!(h < INFINITY)) return;
-    const int rk = g.rkS[g.p0 + e];
-    g.wKeys[rk] = h;
-    g.wRefs[rk] = g.p0 + e;                 // archive column of slot 0
-    g.wPos[rk] = g.cposS[g.p0 + e];
+    WEnt w;
+    w.key = h;
+    w.ref = g.p0 + e;                       // archive column of slot 0
+    w.pos = g.cposS[g.p0 + e];
+    g.wEnt[g.rkS[g.p0 + e]] = w;
 }
 
 // -----------------------------------------------------------------------------------------------------------------
 // CHAIN: the W selections of steps [k0, k0 + cnt), one persistent CTA, state in shared memory (or global scratch when
 // it does not fit).  W list of step k = [W_{k-1} (logical order) | valid columns of P_{k-1} GV]; sigma = stable rank.
 // -----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, int use_smem, double* scr) {
+__device__ __forceinline__ int upper_bound_ent(const WEnt* a, int len, double key) {   // # entries with key <= key
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid].key <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     __shared__ unsigned orm[2 * MAX_IT];
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
     __shared__ int scan_s[CHAIN_THREADS / 32];
     __shared__ int s_pC[64];
-    __shared__ int s_nd, s_cz;
+    __shared__ int s_nd, s_cz, s_czw;
     const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
-    // working set (shared memory, or global scratch when the W list is too long): sorted keys and (ref, pos) payloads of
-    // W, double-buffered; the input segment C_t of two consecutive steps; a histogram for the merge; sigma of C_t.
-    double* base = use_smem ? reinterpret_cast<double*>(chain_sm) : scr;
-    double* kbuf0 = base;
-    double* kbuf1 = kbuf0 + cap;
-    double* cH0 = kbuf1 + cap;
-    double* cSk0 = cH0 + 2 * pV;
-    int2* pbuf0 = reinterpret_cast<int2*>(cSk0 + 2 * pV);
-    int2* pbuf1 = pbuf0 + cap;
-    int* hist = reinterpret_cast<int*>(pbuf1 + cap);          // [cap + 2]
+    // working set (shared memory, or global scratch when the W list is too long): the sorted list of W, double-buffered;
+    // the input segment C_t of two consecutive steps; a histogram for the merge; sigma of C_t.
+    WEnt* ebuf0 = SMEM ? reinterpret_cast<WEnt*>(chain_sm) : reinterpret_cast<WEnt*>(scr);
+    WEnt* ebuf1 = ebuf0 + cap;
+    double* cH0 = reinterpret_cast<double*>(ebuf1 + cap);      // [2][pV]
+    double* cSk0 = cH0 + 2 * pV;                               // [2][pV]
+    int* hist = reinterpret_cast<int*>(cSk0 + 2 * pV);         // [cap + 2]
     int* sigC = hist + cap + 2;                                // [pV]
     int* cRk0 = sigC + pV;                                     // [2][pV]
     int* cCp0 = cRk0 + 2 * pV;                                 // [2][pV]
     if (tid < cnt && tid < 64) s_pC[tid] = g.cntS[tid * 2 + 1];
     int pW = *g.wCount;
-    for (int r = tid; r < pW; r += CHAIN_THREADS) {
-        kbuf0[r] = g.wKeys[r];
-        pbuf0[r] = make_int2(g.wRefs[r], g.wPos[r]);
-    }
+    for (int r = tid; r < pW; r += CHAIN_THREADS) ebuf0[r] = g.wEnt[r];
     for (int e = tid; e < pV; e += CHAIN_THREADS) {
         const int b0 = g.p0 + e;
         cH0[e] = g.hS[b0]; cSk0[e] = g.skS[b0]; cRk0[e] = g.rkS[b0]; cCp0[e] = g.cposS[b0];
@@ -225,15 +236,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
     for (int t = 0; t < cnt; ++t) {
         const int k = k0 + t;
         const int cb = t & 1;
-        const double* kc = cur ? kbuf1 : kbuf0;
-        double* kn = cur ? kbuf0 : kbuf1;
-        const int2* pc = cur ? pbuf1 : pbuf0;
-        int2* pn = cur ? pbuf0 : pbuf1;
+        const WEnt* ec = cur ? ebuf1 : ebuf0;
+        WEnt* en = cur ? ebuf0 : ebuf1;
         const double* cH = cH0 + cb * pV;
         const double* skC = cSk0 + cb * pV;
         const int* cRk = cRk0 + cb * pV;
         const int* cCp = cCp0 + cb * pV;
         const int baseC = t * g.q + g.p0;
+        const int refC0 = (int)(g.col0 + baseC);
         const int pC = s_pC[t];
         // prefetch the next step's segment into registers (stored to the other buffer at the end of this step)
         double pfH[2] = {0.0, 0.0}, pfS[2] = {0.0, 0.0};
@@ -252,24 +262,42 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
         const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
         const int m = mode == MODE_REDUCE ? (int)(pin - g.nkeep) : 0;
         const int nk = pin - m;
-        // ---- S0: clear the merge histogram ----
+        int* dl = g.dlistW + (int64_t)t * g.capDisc;
+        // ---- S0: clear the merge histogram; count the generators with score exactly 0 ----
         for (int x = tid; x <= pW; x += CHAIN_THREADS) hist[x] = 0;
         if (tid < 2 * MAX_IT) orm[tid] = 0u;
         if (tid < g.n) tc_s[tid] = 0;
-        if (tid == 0) s_cz = upper_bound(kc, pW, 0.0) + upper_bound(skC, pC, 0.0);
+        if (tid == 0) {
+            s_czw = upper_bound_ent(ec, pW, 0.0);
+            s_cz = s_czw + upper_bound(skC, pC, 0.0);
+        }
         __syncthreads();
-        // generators with score exactly 0 precede everything else; z of them survive the cut
-        const int z = max(0, s_cz - m);
-        // ---- S1: insertion point of every input generator in the sorted W (the only binary searches of the step) ----
+        const int czw = s_czw;
+        const int z = max(0, s_cz - m);         // zero-score generators that survive the cut: they stay in front
+        // ---- S1: insertion point of every input generator in the sorted W (the only binary searches of the step);
+        //          the box generators of W (score 0, hence sigma = rank) that are boxed again ----
         for (int e = tid; e < pV; e += CHAIN_THREADS) {
             const double h = cH[e];
             int sg = -1;
             if (h < INFINITY) {
-                const int ip = upper_bound(kc, pW, h);          // W precedes C in the list: ties go to W
+                const int ip = upper_bound_ent(ec, pW, h);      // W precedes C in the list: ties go to W
                 atomicAdd(&hist[ip], 1);
                 sg = cRk[e] + ip;
             }
             sigC[e] = sg;
+        }
+        for (int r = CHAIN_THREADS - 1 - tid; r < min(czw, m); r += CHAIN_THREADS) {
+            const int ref = ec[r].ref;
+            if (ref < 0) {          // its value is an earlier W box vector entry: remember the creation step (wseq_kernel)
+                int kt, it, w, b;
+                tag_decode(ref, g.n, kt, it);
+                const int sl = atomicAdd(&tc_s[it], 1);
+                if (sl < 4) g.tsrc[((int64_t)t * g.n + it) * 4 + sl] = kt;
+                if (g.strip) {
+                    mask_pos(it, w, b);
+                    atomicOr(&orm[w], 1u << b);
+                }
+            }
         }
         __syncthreads();
         // ---- S2: inclusive scan: hist[r] = # input generators sorted before W's rank r  =>  sigma_W(r) = r + hist[r] ----
@@ -300,45 +328,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
             for (int x = lo; x < hi; ++x) { run += hist[x]; hist[x] = run; }
         }
         __syncthreads();
-        // ---- S3: snapshot of W_{k-1} for the R reduction, boxed list, boxed box generators ----
-        double* snK = g.snKeys + (int64_t)t * cap;
-        int* snR = g.snRefs + (int64_t)t * cap;
-        int* snP = g.snPos + (int64_t)t * cap;
-        int* dl = g.dlistW + (int64_t)t * g.capDisc;
-        int* recO = g.record ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
-        double* recH = g.record ? g.recHW + (int64_t)k * g.capListW : nullptr;
-        for (int r = tid; r < pW; r += CHAIN_THREADS) {
-            const double key = kc[r];
-            const int2 py = pc[r];
-            snK[r] = key; snR[r] = py.x; snP[r] = py.y;
-            const int sigma = r + hist[r];
-            if (recO) { recO[sigma] = py.y; recH[py.y] = key; }
-            if (sigma < m) {
-                dl[sigma] = py.x;
-                if (py.x < 0) {      // boxed box generator: its value is an earlier W box vector entry
-                    int kt, it, w, b;
-                    tag_decode(py.x, g.n, kt, it);
-                    const int sl = atomicAdd(&tc_s[it], 1);
-                    if (sl < 4) g.tsrc[((int64_t)t * g.n + it) * 4 + sl] = kt;
-                    if (g.strip) {
-                        mask_pos(it, w, b);
-                        atomicOr(&orm[w], 1u << b);
-                    }
-                }
-            }
-        }
-        for (int e = tid; e < pV; e += CHAIN_THREADS) {
-            const int sg = sigC[e];
-            if (sg >= 0) {
-                if (recO) { const int li = pW + cCp[e]; recO[sg] = li; recH[li] = cH[e]; }
-                if (sg < m) dl[sg] = (int)(g.col0 + baseC + e);
-            }
-        }
-        if (tid == 0) g.snCount[t] = pW;
         if (g.strip && mode == MODE_REDUCE) {
             // Row-support union of the boxed generators.  The boxed box generators alone usually cover every row
             // (steady state): only otherwise are the masks of the dense ones fetched (vector loads, all in flight).
-            __syncthreads();
             int covered = 0;
             for (int w = 0; w < g.nwords; ++w) covered += __popc(orm[w]);
             if (covered < g.n) {
@@ -346,7 +338,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
                 for (int x = tid; x < pW + pV; x += CHAIN_THREADS) {
                     const uint32_t* mk = nullptr;
                     if (x < pW) {
-                        const int ref = pc[x].x;
+                        const int ref = ec[x].ref;
                         if (x + hist[x] < m && ref >= 0) {
                             const int j = ref / g.q, c = ref - j * g.q - g.p0;
                             mk = g.maskAll + ((int64_t)j * pV + c) * g.nwords4;
@@ -369,9 +361,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
                         }
                     }
                 }
+                __syncthreads();
             }
         }
-        __syncthreads();
         if (tid < g.n) g.tcnt[(int64_t)t * g.n + tid] = tc_s[tid];
         // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode) ----
         int flag = 0, iprime = 0, nd = 0;
@@ -403,37 +395,53 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
             nd = s_nd;
             iprime = scan_s[wid] + __popc(bal & ((1u << lane) - 1u));
         }
-        // ---- the next W: sorted list (keys, refs) with logical positions ----
-        if (mode == MODE_REDUCE) {
-            for (int r = tid; r < pW; r += CHAIN_THREADS) {
-                const int sigma = r + hist[r];
-                if (sigma >= m) {
-                    const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
-                    kn[rk] = kc[r]; pn[rk] = make_int2(pc[r].x, ps);
+        // ---- S3, one pass: snapshot of W_{k-1} (for the R reduction of this step), boxed list, the next W ----
+        WEnt* sn = g.snEnt + (int64_t)t * cap;
+        int* recO = g.record ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
+        double* recH = g.record ? g.recHW + (int64_t)k * g.capListW : nullptr;
+        for (int r = tid; r < pW; r += CHAIN_THREADS) {
+            WEnt w = ec[r];
+            sn[r] = w;
+            const int sigma = r + hist[r];
+            if (recO) { recO[sigma] = w.pos; recH[w.pos] = w.key; }
+            if (mode == MODE_REDUCE) {
+                if (sigma < m) {
+                    dl[sigma] = w.ref;
+                } else {
+                    const int ps = sigma - m;
+                    w.pos = ps;
+                    en[ps < z ? ps : ps + nd] = w;
                 }
-            }
-            for (int e = tid; e < pV; e += CHAIN_THREADS) {
-                const int sigma = sigC[e];
-                if (sigma >= m) {
-                    const int ps = sigma - m, rk = ps < z ? ps : ps + nd;
-                    kn[rk] = cH[e]; pn[rk] = make_int2((int)(g.col0 + baseC + e), ps);
-                }
-            }
-            if (flag) {
-                const int rk = z + iprime;
-                kn[rk] = 0.0; pn[rk] = make_int2(tag_ref(k, tid, g.n), nk + iprime);
-            }
-        } else {
-            for (int r = tid; r < pW; r += CHAIN_THREADS) {
-                const int rk = r + hist[r];
-                kn[rk] = kc[r]; pn[rk] = pc[r];
-            }
-            for (int e = tid; e < pV; e += CHAIN_THREADS) {
-                const int rk = sigC[e];
-                if (rk >= 0) { kn[rk] = cH[e]; pn[rk] = make_int2((int)(g.col0 + baseC + e), pW + cCp[e]); }
+            } else {
+                en[sigma] = w;
             }
         }
+        for (int e = tid; e < pV; e += CHAIN_THREADS) {
+            const int sigma = sigC[e];
+            if (sigma >= 0) {
+                WEnt w;
+                w.key = cH[e]; w.ref = refC0 + e; w.pos = pW + cCp[e];
+                if (recO) { recO[sigma] = w.pos; recH[w.pos] = w.key; }
+                if (mode == MODE_REDUCE) {
+                    if (sigma < m) {
+                        dl[sigma] = w.ref;
+                    } else {
+                        const int ps = sigma - m;
+                        w.pos = ps;
+                        en[ps < z ? ps : ps + nd] = w;
+                    }
+                } else {
+                    en[sigma] = w;
+                }
+            }
+        }
+        if (flag) {
+            WEnt w;
+            w.key = 0.0; w.ref = tag_ref(k, tid, g.n); w.pos = nk + iprime;
+            en[z + iprime] = w;
+        }
         if (tid == 0) {
+            g.snCount[t] = pW;
             PlanW pl;
             pl.mode = mode; pl.pin = pin; pl.m = m; pl.pW = pW; pl.pC = pC; pl.nk = nk; pl.nd = nd; pl.z = z;
             g.planW[k] = pl;
@@ -457,14 +465,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
         }
         __syncthreads();
     }
-    const double* kf = cur ? kbuf1 : kbuf0;
-    const int2* pf = cur ? pbuf1 : pbuf0;
-    for (int r = tid; r < pW; r += CHAIN_THREADS) {
-        g.wKeys[r] = kf[r];
-        g.wRefs[r] = pf[r].x;
-        g.wPos[r] = pf[r].y;
-    }
+    const WEnt* ef = cur ? ebuf1 : ebuf0;
+    for (int r = tid; r < pW; r += CHAIN_THREADS) g.wEnt[r] = ef[r];
     if (tid == 0) *g.wCount = pW;
+}
+
+static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st) {
+    if (use_smem)
+        chain_kernel<true><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
+    else
+        chain_kernel<false><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -613,7 +623,7 @@ __global__ void __launch_bounds__(256) rank_r_kernel(GP g, int k0) {
     const int pW = g.snCount[t], pA = g.cntS[t * 2 + 0];
     const int baseA = t * g.q;
     const double* skA = g.skS + baseA;
-    const double* snK = g.snKeys + (int64_t)t * g.capW;
+    const WEnt* sn = g.snEnt + (int64_t)t * g.capW;
     const int pin = pA + pW;
     const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
     int* order = g.orderR + (int64_t)t * g.capListR;
@@ -629,16 +639,16 @@ __global__ void __launch_bounds__(256) rank_r_kernel(GP g, int k0) {
     if (gid < g.p0) {
         const double h = g.hS[baseA + gid];
         if (h < INFINITY) {
-            const int sigma = g.rkS[baseA + gid] + lower_bound(snK, pW, h);
+            const int sigma = g.rkS[baseA + gid] + lower_bound_ent(sn, pW, h);
             order[sigma] = gid;
             if (recO) { const int li = g.cposS[baseA + gid]; recO[sigma] = li; recH[li] = h; }
         }
     } else if (gid - g.p0 < pW) {
         const int rho = gid - g.p0;
-        const double h = snK[rho];
+        const double h = sn[rho].key;
         const int sigma = rho + upper_bound(skA, pA, h);
         order[sigma] = g.p0 + rho;
-        if (recO) { const int li = pA + g.snPos[(int64_t)t * g.capW + rho]; recO[sigma] = li; recH[li] = h; }
+        if (recO) { const int li = pA + sn[rho].pos; recO[sigma] = li; recH[li] = h; }
     }
 }
 
@@ -649,8 +659,7 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     const int t = blockIdx.y, k = k0 + t, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PlanR pl = g.planR[k];
     const int* order = g.orderR + (int64_t)t * g.capListR;
-    const int* snR = g.snRefs + (int64_t)t * g.capW;
-    const int* snP = g.snPos + (int64_t)t * g.capW;
+    const WEnt* sn = g.snEnt + (int64_t)t * g.capW;
     const int n2 = g.ld / 2;
     if (blockIdx.x < NBR) {
         Acc a;
@@ -660,7 +669,7 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
             const int lo = blockIdx.x * chunk, hi = min(pl.m, lo + chunk);
             for (int s = lo + warp; s < hi; s += 8) {
                 const int code = order[s];
-                const int ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : snR[code - g.p0];
+                const int ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
                 acc_add(g, a, ref, lane, true);
             }
         }
@@ -676,7 +685,7 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
         if (pl.mode == MODE_REDUCE) {
             if (job < pl.m) continue;
             const int code = order[job];
-            ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : snR[code - g.p0];
+            ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
             dest = job - pl.m;
         } else if (job < g.p0) {          // unchanged: [valid columns of A in order | W in logical order]
             if (!(g.hS[t * g.q + job] < INFINITY)) continue;
@@ -684,8 +693,8 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
             dest = g.cposS[t * g.q + job];
         } else {
             const int rho = job - g.p0;
-            ref = snR[rho];
-            dest = pl.pA + snP[rho];
+            ref = sn[rho].ref;
+            dest = pl.pA + sn[rho].pos;
         }
         double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)dest * g.ld);
         if (ref >= 0) {
@@ -766,8 +775,8 @@ __global__ void __launch_bounds__(256) materialize_w_kernel(GP g, double* __rest
     const int pW = *g.wCount;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= pW) return;
-    const int ref = g.wRefs[warp];
-    double* dst = out + (int64_t)g.wPos[warp] * ldo;
+    const int ref = g.wEnt[warp].ref;
+    double* dst = out + (int64_t)g.wEnt[warp].pos * ldo;
     if (ref >= 0) {
         const double* src = g.Yall + (int64_t)ref * g.ld;
         for (int i = lane; i < g.n; i += 32) dst[i] = src[i];
@@ -928,13 +937,9 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
             g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords4 + 4 : 4));
             g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
-            g.wKeys = (double*)own(dalloc<double>(ctx, g.capW));
-            g.wRefs = (int*)own(dalloc<int>(ctx, g.capW));
-            g.wPos = (int*)own(dalloc<int>(ctx, g.capW));
+            g.wEnt = (WEnt*)own(dalloc<WEnt>(ctx, g.capW));
             g.wCount = (int*)own(dalloc<int>(ctx, 1));
-            g.snKeys = (double*)own(dalloc<double>(ctx, (size_t)s * g.capW));
-            g.snRefs = (int*)own(dalloc<int>(ctx, (size_t)s * g.capW));
-            g.snPos = (int*)own(dalloc<int>(ctx, (size_t)s * g.capW));
+            g.snEnt = (WEnt*)own(dalloc<WEnt>(ctx, (size_t)s * g.capW));
             g.snCount = (int*)own(dalloc<int>(ctx, s));
             g.planW = (PlanW*)own(dalloc<PlanW>(ctx, N + 2));
             g.planR = (PlanR*)own(dalloc<PlanR>(ctx, N + 2));
@@ -957,7 +962,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.Rrow = (int*)own(dalloc<int>(ctx, (size_t)N * n));
             g.meta = (int2*)own(dalloc<int2>(ctx, N + 1));
             // chain working set: keys 2 cap doubles, refs/pos 4 cap ints, sigma (cap + pV) ints
-            // chain working set: keys 2 cap doubles, (ref, pos) 2 cap int2, histogram cap + 2 ints, 52 bytes per input generator
+            // chain working set: two copies of the sorted list (16 B per generator), histogram cap + 2 ints, 52 bytes per input generator
             F->chain_smem = (size_t)g.capW * 36 + (size_t)pV * 52 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
             if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
@@ -1008,7 +1013,7 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
 static void process_steps(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
     Ctx* ctx = F->ctx;
     score_and_sort(F, g, k0 - 1, cnt, st);
-    chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, k0, cnt, F->chain_use_smem, F->scr);
+    launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
     const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
     wbox_partial_kernel<<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
@@ -1023,7 +1028,7 @@ static void process_steps(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) 
 static void set_kernel_attributes(Flowpipe* F) {
     static bool done = false;
     if (done) return;
-    REACH_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     done = true;
@@ -1158,7 +1163,7 @@ void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const do
         // step "k = 1" on slot 0 with an empty W
         REACH_CUDA(cudaMemsetAsync(g.wCount, 0, sizeof(int), st));
         score_and_sort(F, g, 0, 1, st);
-        chain_kernel<<<1, CHAIN_THREADS, F->chain_use_smem ? F->chain_smem : 0, st>>>(g, 1, 1, F->chain_use_smem, F->scr);
+        launch_chain(g, 1, 1, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
         const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
         wbox_partial_kernel<<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, 1, 1);
