@@ -149,6 +149,9 @@ REACH_API int32_t reach_flowpipe_selection(reach_flowpipe* fp, int64_t k, int32_
                                  double* h);
 REACH_API int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, double* gemm_ms, int64_t* gemm_launches,
                               double* gemm_flops, double* reduce_ms, double* reduce_bytes);
+/* CUDA-event time of the last run spent in the selection chain (side stream) and in the batched numerics (second side
+ * stream); the two overlap each other and the GEMMs. */
+REACH_API int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, double* numerics_ms);
 REACH_API void reach_flowpipe_free(reach_flowpipe* fp);
 /* reduce_order(Z, r) of LazySets (Girard), call site GLGM06/post.jl:20.  Gout must hold n x max(p, r*n) doubles;
  * p_out receives the new generator count; ind (p, may be NULL) the sortperm. */

@@ -330,8 +330,10 @@ class Flowpipe:
         nl = C.c_int64()
         self.ctx._check(self.ctx.lib.reach_flowpipe_timing(self._h, C.byref(vals[0]), C.byref(vals[1]), C.byref(nl),
                                                            C.byref(vals[2]), C.byref(vals[3]), C.byref(vals[4])))
+        ch, nu = C.c_double(), C.c_double()
+        self.ctx._check(self.ctx.lib.reach_flowpipe_phase_ms(self._h, C.byref(ch), C.byref(nu)))
         return dict(run_ms=vals[0].value, gemm_ms=vals[1].value, gemm_launches=nl.value, gemm_flops=vals[2].value,
-                    reduce_ms=vals[3].value, reduce_bytes=vals[4].value)
+                    reduce_ms=vals[3].value, reduce_bytes=vals[4].value, chain_ms=ch.value, numerics_ms=nu.value)
 
     def close(self):
         if self._h.value:

@@ -37,7 +37,8 @@ constexpr int NBW = 4;              // box-sum chunks per step for the W / R red
 constexpr int NBR = 16;
 constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
-constexpr int CHAIN_THREADS = 1024;
+constexpr int CHAIN_THREADS = 256;    // small enough to share an SM with the numerics kernels (16 K registers)
+constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
 
 struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of step k  (GLGM06/reach.jl:54-55)
 struct PlanR { int mode, pin, m, pA, pW, pad0, pad1, pad2; };   // R reduction of step k  (:48-49)
@@ -206,11 +207,12 @@ __device__ __forceinline__ int upper_bound_ent(const WEnt* a, int len, double ke
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, int cnt, double* scr) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, int cnt, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     __shared__ unsigned orm[2 * MAX_IT];
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
     __shared__ int scan_s[CHAIN_THREADS / 32];
+    __shared__ int rows_s[CHAIN_ROWS * (CHAIN_THREADS / 32)];
     __shared__ int s_pC[64];
     __shared__ int s_nd, s_cz, s_czw;
     const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
         // ---- S0: clear the merge histogram; count the generators with score exactly 0 ----
         for (int x = tid; x <= pW; x += CHAIN_THREADS) hist[x] = 0;
         if (tid < 2 * MAX_IT) orm[tid] = 0u;
-        if (tid < g.n) tc_s[tid] = 0;
+        for (int i = tid; i < g.n; i += CHAIN_THREADS) tc_s[i] = 0;
         if (tid == 0) {
             s_czw = upper_bound_ent(ec, pW, 0.0);
             s_cz = s_czw + upper_bound(skC, pC, 0.0);
@@ -315,13 +317,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
             if (lane == 31) scan_s[wid] = inc;
             __syncthreads();
             if (wid == 0) {
-                int v = scan_s[lane];
+                int v = lane < CHAIN_THREADS / 32 ? scan_s[lane] : 0;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int u = __shfl_up_sync(0xffffffffu, v, o);
                     if (lane >= o) v += u;
                 }
-                scan_s[lane] = v;
+                if (lane < CHAIN_THREADS / 32) scan_s[lane] = v;
             }
             __syncthreads();
             int run = inc - sum + (wid ? scan_s[wid - 1] : 0);
@@ -364,36 +366,51 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
                 __syncthreads();
             }
         }
-        if (tid < g.n) g.tcnt[(int64_t)t * g.n + tid] = tc_s[tid];
-        // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode) ----
-        int flag = 0, iprime = 0, nd = 0;
-        if (mode == MODE_REDUCE) {
-            if (tid < g.n) {
-                if (g.strip) {
-                    int w, b;
-                    mask_pos(tid, w, b);
-                    flag = (orm[w] >> b) & 1;
-                } else {
-                    flag = 1;
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, flag);
-            if (lane == 0) scan_s[wid] = __popc(bal);
-            __syncthreads();
-            if (wid == 0) {
-                const int c = scan_s[lane];
-                int v = c;
+        for (int i = tid; i < g.n; i += CHAIN_THREADS) g.tcnt[(int64_t)t * g.n + i] = tc_s[i];
+        // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode):
+        //      thread tid owns rows tid, tid + T, ...; iprime = number of flagged rows below, nd = their total ----
+        int flag[CHAIN_ROWS], iprime[CHAIN_ROWS], nd = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v += u;
+        for (int j = 0; j < CHAIN_ROWS; ++j) { flag[j] = 0; iprime[j] = 0; }
+        if (mode == MODE_REDUCE) {
+            unsigned bal[CHAIN_ROWS];
+#pragma unroll
+            for (int j = 0; j < CHAIN_ROWS; ++j) {
+                const int i = tid + j * CHAIN_THREADS;
+                if (i < g.n) {
+                    if (g.strip) {
+                        int w, b;
+                        mask_pos(i, w, b);
+                        flag[j] = (orm[w] >> b) & 1;
+                    } else {
+                        flag[j] = 1;
+                    }
                 }
-                scan_s[lane] = v - c;            // exclusive
-                if (lane == 31) s_nd = v;
+                bal[j] = __ballot_sync(0xffffffffu, flag[j]);
+                if (lane == 0) rows_s[j * (CHAIN_THREADS / 32) + wid] = __popc(bal[j]);
+            }
+            __syncthreads();
+            if (wid == 0) {         // exclusive scan over the CHAIN_ROWS * warps counts, row-major = ascending rows
+                int run = 0;
+                for (int x0 = 0; x0 < CHAIN_ROWS * (CHAIN_THREADS / 32); x0 += 32) {
+                    const int x = x0 + lane;
+                    const int c = x < CHAIN_ROWS * (CHAIN_THREADS / 32) ? rows_s[x] : 0;
+                    int v = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += u;
+                    }
+                    if (x < CHAIN_ROWS * (CHAIN_THREADS / 32)) rows_s[x] = run + v - c;
+                    run += __shfl_sync(0xffffffffu, v, 31);
+                }
+                if (lane == 0) s_nd = run;
             }
             __syncthreads();
             nd = s_nd;
-            iprime = scan_s[wid] + __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+            for (int j = 0; j < CHAIN_ROWS; ++j)
+                iprime[j] = rows_s[j * (CHAIN_THREADS / 32) + wid] + __popc(bal[j] & ((1u << lane) - 1u));
         }
         // ---- S3, one pass: snapshot of W_{k-1} (for the R reduction of this step), boxed list, the next W ----
         WEnt* sn = g.snEnt + (int64_t)t * cap;
@@ -435,11 +452,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(GP g, int k0, i
                 }
             }
         }
-        if (flag) {
-            WEnt w;
-            w.key = 0.0; w.ref = tag_ref(k, tid, g.n); w.pos = nk + iprime;
-            en[z + iprime] = w;
-        }
+#pragma unroll
+        for (int j = 0; j < CHAIN_ROWS; ++j)
+            if (flag[j]) {
+                WEnt w;
+                w.key = 0.0; w.ref = tag_ref(k, tid + j * CHAIN_THREADS, g.n); w.pos = nk + iprime[j];
+                en[z + iprime[j]] = w;
+            }
         if (tid == 0) {
             g.snCount[t] = pW;
             PlanW pl;
@@ -480,21 +499,24 @@ static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, dou
 // -----------------------------------------------------------------------------------------------------------------
 // batched numerics
 // -----------------------------------------------------------------------------------------------------------------
-struct Acc {
-    double2 v[MAX_IT];
+template <int IT>
+struct Acc {        // IT double2 per lane: rows <= 64 * IT.  Small IT keeps the numerics kernels co-resident with the GEMM.
+    double2 v[IT];
 };
 
-__device__ __forceinline__ void acc_zero(Acc& a) {
+template <int IT>
+__device__ __forceinline__ void acc_zero(Acc<IT>& a) {
 #pragma unroll
-    for (int i = 0; i < MAX_IT; ++i) a.v[i] = make_double2(0.0, 0.0);
+    for (int i = 0; i < IT; ++i) a.v[i] = make_double2(0.0, 0.0);
 }
 // a += |column ref|  (dense archive column, or the single entry of a box generator when with_tags)
-__device__ __forceinline__ void acc_add(const GP& g, Acc& a, int ref, int lane, bool with_tags) {
+template <int IT>
+__device__ __forceinline__ void acc_add(const GP& g, Acc<IT>& a, int ref, int lane, bool with_tags) {
     const int n2 = g.ld / 2;
     if (ref >= 0) {
         const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)ref * g.ld);
 #pragma unroll
-        for (int i = 0; i < MAX_IT; ++i) {
+        for (int i = 0; i < IT; ++i) {
             const int idx = lane + 32 * i;
             if (idx < n2) {
                 const double2 v = c2[idx];
@@ -508,17 +530,18 @@ __device__ __forceinline__ void acc_add(const GP& g, Acc& a, int ref, int lane, 
         const double val = fabs(g.Wd[(int64_t)kt * g.ld + it]);
         const int idx = it >> 1;
 #pragma unroll
-        for (int i = 0; i < MAX_IT; ++i)
+        for (int i = 0; i < IT; ++i)
             if (lane + 32 * i == idx) {
                 if (it & 1) a.v[i].y += val; else a.v[i].x += val;
             }
     }
 }
 // CTA-wide sum of the warps' accumulators in warp order -> out[0 .. ld)
-__device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc& a, double* red_s, double* __restrict__ out) {
+template <int IT>
+__device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc<IT>& a, double* red_s, double* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n2 = g.ld / 2, nw = blockDim.x >> 5;
 #pragma unroll
-    for (int i = 0; i < MAX_IT; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = lane + 32 * i;
         if (idx < n2) {
             red_s[warp * g.ld + 2 * idx] = a.v[i].x;
@@ -534,12 +557,13 @@ __device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc& a, doub
 }
 
 // Partial box vectors of the W reductions: chunk b of step t sums |dense discarded generators| in sigma order.
+template <int IT>
 __global__ void __launch_bounds__(256) wbox_partial_kernel(GP g, int k0) {
     extern __shared__ double red_s[];
     const int t = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PlanW pl = g.planW[k0 + t];
     double* out = g.partW + ((int64_t)t * NBW + b) * g.ld;
-    Acc a;
+    Acc<IT> a;
     acc_zero(a);
     if (pl.mode == MODE_REDUCE) {
         const int chunk = (pl.m + NBW - 1) / NBW;
@@ -654,6 +678,7 @@ __global__ void __launch_bounds__(256) rank_r_kernel(GP g, int k0) {
 
 // R gather of the batch: blockIdx.x < NBR accumulate the boxed generators (chunks of sigma), the other CTAs move the
 // kept ones into the flowpipe slot, warp per column.
+template <int IT>
 __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     extern __shared__ double red_s[];
     const int t = blockIdx.y, k = k0 + t, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -662,7 +687,7 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     const WEnt* sn = g.snEnt + (int64_t)t * g.capW;
     const int n2 = g.ld / 2;
     if (blockIdx.x < NBR) {
-        Acc a;
+        Acc<IT> a;
         acc_zero(a);
         if (pl.mode == MODE_REDUCE) {
             const int chunk = (pl.m + NBR - 1) / NBR;
@@ -828,11 +853,13 @@ struct Flowpipe {
     double* scr = nullptr;          // chain scratch when the W list does not fit in shared memory
     size_t chain_smem = 0;
     int chain_use_smem = 1;
-    cudaStream_t side = nullptr;    // numerics of batch b overlap the GEMM of batch b+1
+    cudaStream_t side = nullptr;    // selection chain of batch b (overlaps the GEMM of batch b+1) ...
+    cudaStream_t side2 = nullptr;   // ... and the numerics of batch b (overlap the chain of batch b+1)
+    GP gset[2];                     // batch-local arrays, double-buffered by batch parity
     std::vector<void*> owned;
     std::vector<int2> meta_host;
     bool ran = false;
-    double run_ms = 0, gemm_ms = 0, gemm_flops = 0, reduce_ms = 0, reduce_bytes = 0;
+    double run_ms = 0, gemm_ms = 0, gemm_flops = 0, reduce_ms = 0, reduce_bytes = 0, chain_ms = 0;
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
     double* stage = nullptr;        // staging for box queries
@@ -844,6 +871,7 @@ void flowpipe_free(Flowpipe* F) {
     for (void* p : F->owned) cudaFree(p);
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
     if (F->side) cudaStreamDestroy(F->side);
+    if (F->side2) cudaStreamDestroy(F->side2);
     delete F;
 }
 
@@ -930,25 +958,12 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             up2d(F->Hflow + (p0 + pV) * ld, c0, n, 1);
             up2d(F->Hflow + (p0 + pV + 1) * ld, cV, n, 1);
             const size_t sq = (size_t)s * q + 8;
-            g.hS = (double*)own(dalloc<double>(ctx, sq));
-            g.skS = (double*)own(dalloc<double>(ctx, sq));
-            g.rkS = (int*)own(dalloc<int>(ctx, sq));
-            g.cposS = (int*)own(dalloc<int>(ctx, sq));
-            g.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
             g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords4 + 4 : 4));
             g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
             g.wEnt = (WEnt*)own(dalloc<WEnt>(ctx, g.capW));
             g.wCount = (int*)own(dalloc<int>(ctx, 1));
-            g.snEnt = (WEnt*)own(dalloc<WEnt>(ctx, (size_t)s * g.capW));
-            g.snCount = (int*)own(dalloc<int>(ctx, s));
             g.planW = (PlanW*)own(dalloc<PlanW>(ctx, N + 2));
             g.planR = (PlanR*)own(dalloc<PlanR>(ctx, N + 2));
-            g.dlistW = (int*)own(dalloc<int>(ctx, (size_t)s * g.capDisc));
-            g.tcnt = (int*)own(dalloc<int>(ctx, (size_t)s * n));
-            g.tsrc = (int*)own(dalloc<int>(ctx, (size_t)s * n * 4));
-            g.orderR = (int*)own(dalloc<int>(ctx, (size_t)s * g.capListR));
-            g.partW = (double*)own(dalloc<double>(ctx, (size_t)s * NBW * ld));
-            g.partR = (double*)own(dalloc<double>(ctx, (size_t)s * NBR * ld));
             g.cW = (double*)own(dalloc<double>(ctx, ld));
             if (F->record) {
                 g.recOrdW = (int*)own(dalloc<int>(ctx, (size_t)(N + 2) * g.capListW));
@@ -966,7 +981,26 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             F->chain_smem = (size_t)g.capW * 36 + (size_t)pV * 52 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
             if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
-            REACH_CUDA(cudaStreamCreateWithFlags(&F->side, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {      // batch-local arrays, one set per batch parity
+                GP& h = F->gset[b];
+                h.hS = (double*)own(dalloc<double>(ctx, sq));
+                h.skS = (double*)own(dalloc<double>(ctx, sq));
+                h.rkS = (int*)own(dalloc<int>(ctx, sq));
+                h.cposS = (int*)own(dalloc<int>(ctx, sq));
+                h.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
+                h.snEnt = (WEnt*)own(dalloc<WEnt>(ctx, (size_t)s * g.capW));
+                h.snCount = (int*)own(dalloc<int>(ctx, s));
+                h.dlistW = (int*)own(dalloc<int>(ctx, (size_t)s * g.capDisc));
+                h.tcnt = (int*)own(dalloc<int>(ctx, (size_t)s * n));
+                h.tsrc = (int*)own(dalloc<int>(ctx, (size_t)s * n * 4));
+                h.orderR = (int*)own(dalloc<int>(ctx, (size_t)s * g.capListR));
+                h.partW = (double*)own(dalloc<double>(ctx, (size_t)s * NBW * ld));
+                h.partR = (double*)own(dalloc<double>(ctx, (size_t)s * NBR * ld));
+            }
+            int prio_lo = 0, prio_hi = 0;
+            REACH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            REACH_CUDA(cudaStreamCreateWithPriority(&F->side, cudaStreamNonBlocking, prio_hi));      // the chain is the critical path
+            REACH_CUDA(cudaStreamCreateWithFlags(&F->side2, cudaStreamNonBlocking));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
             if (p0 > 0) REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
             if (ld > n) REACH_CUDA(cudaMemset2DAsync(g.Rg + n, ld * 8, 0, (ld - n) * 8, p0 > 0 ? p0 : 1, st));
@@ -1009,28 +1043,45 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
     }
 }
 
-// selection chain + batched numerics of steps [k0, k0 + cnt) (their slots k-1 are in the archive already)
-static void process_steps(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
-    Ctx* ctx = F->ctx;
+static void bind_set(GP& g, const GP& h) {
+    g.hS = h.hS; g.skS = h.skS; g.rkS = h.rkS; g.cposS = h.cposS; g.cntS = h.cntS;
+    g.snEnt = h.snEnt; g.snCount = h.snCount; g.dlistW = h.dlistW; g.tcnt = h.tcnt; g.tsrc = h.tsrc;
+    g.orderR = h.orderR; g.partW = h.partW; g.partR = h.partR;
+}
+
+// selection chain of steps [k0, k0 + cnt) (their slots k-1 are in the archive already) ...
+static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
     score_and_sort(F, g, k0 - 1, cnt, st);
     launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
+    REACH_CUDA(cudaGetLastError());
+    F->ctx->launches += 1;
+}
+
+// ... and their batched numerics
+static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st) {
     const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
-    wbox_partial_kernel<<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    const int it = F->ld <= 256 ? 4 : (F->ld <= 512 ? 8 : 16);
+    if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
-    apply_r_kernel<<<dim3(NBR + COPY_CTAS, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
+    if (it == 4) apply_r_kernel<4><<<ag, 256, red_smem, st>>>(g, k0);
+    else if (it == 8) apply_r_kernel<8><<<ag, 256, red_smem, st>>>(g, k0);
+    else apply_r_kernel<16><<<ag, 256, red_smem, st>>>(g, k0);
     finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
     expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
     REACH_CUDA(cudaGetLastError());
-    ctx->launches += 7;
+    F->ctx->launches += 6;
 }
 
 static void set_kernel_attributes(Flowpipe* F) {
     static bool done = false;
     if (done) return;
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     done = true;
     (void)F;
 }
@@ -1067,8 +1118,10 @@ void flowpipe_run(Flowpipe* F) {
         ReserveGuard(Ctx* c_, int v) : c(c_), old(c_->gemm_reserve_sms) { c->gemm_reserve_sms = v; }
         ~ReserveGuard() { c->gemm_reserve_sms = old; }
     } reserve(ctx, F->homog ? 0 : 1);
+    std::vector<std::pair<size_t, size_t>> chain_ev;
     if (!F->homog) {
         set_kernel_attributes(F);
+        bind_set(g, F->gset[0]);
         // W_1 = V, cW_1 = cV (GLGM06/reach.jl:41-42)
         REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (g.p0 + g.pV + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
         score_and_sort(F, g, 0, 1, st);
@@ -1077,30 +1130,37 @@ void flowpipe_run(Flowpipe* F) {
         ctx->launches++;
     }
     // slot j = Phi^j X.  With Phi^w in hand, slots [have, have + w) = Phi^w * slots [have - w, have): doubling until
-    // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) are processed as one batch; their
-    // selection chain and numerics run on the side stream and overlap the next GEMM.
+    // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) form one batch.  Three streams:
+    // the GEMM of batch b+1 (main), the selection chain of batch b (side) and the numerics of batch b-1 (side2) overlap;
+    // the batch-local arrays are double-buffered, so the chain of batch b waits for the numerics of batch b-2.
     const DMat* pw = &F->Phi;
     DMat* spare[2] = {&F->PowA, &F->PowB};
     int sp = 0;
     int64_t have = 1, w = 1;
-    cudaEvent_t ev_gemm = nullptr, ev_side = nullptr;
-    if (!F->homog) {
-        ev_gemm = next_event(F, ev_used);
-        ev_side = next_event(F, ev_used);
-        REACH_CUDA(cudaEventRecord(ev_gemm, st));
-        REACH_CUDA(cudaStreamWaitEvent(F->side, ev_gemm, 0));       // side stream starts after the initialisation
-    }
+    std::vector<cudaEvent_t> ev_num;     // numerics of batch b done
+    int bi = 0;
     while (have < N) {
         const int64_t cnt = std::min(w, N - have);
         timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
         if (!F->homog) {
+            cudaEvent_t ev_gemm = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
             REACH_CUDA(cudaStreamWaitEvent(F->side, ev_gemm, 0));
+            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(F->side, ev_num[bi - 2], 0));
+            bind_set(g, F->gset[bi & 1]);
+            cudaEvent_t c0 = next_event(F, ev_used), c1 = next_event(F, ev_used);
+            chain_ev.push_back({ev_used - 2, ev_used - 1});
+            REACH_CUDA(cudaEventRecord(c0, F->side));
+            process_chain(F, g, (int)have + 1, (int)cnt, F->side);
+            REACH_CUDA(cudaEventRecord(c1, F->side));
+            REACH_CUDA(cudaStreamWaitEvent(F->side2, c1, 0));
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             red_ev.push_back({ev_used - 2, ev_used - 1});
-            REACH_CUDA(cudaEventRecord(e0, F->side));
-            process_steps(F, g, (int)have + 1, (int)cnt, F->side);
-            REACH_CUDA(cudaEventRecord(e1, F->side));
+            REACH_CUDA(cudaEventRecord(e0, F->side2));
+            process_numerics(F, g, (int)have + 1, (int)cnt, F->side2);
+            REACH_CUDA(cudaEventRecord(e1, F->side2));
+            ev_num.push_back(e1);
+            ++bi;
         }
         have += cnt;
         if (have < N && w < s) {
@@ -1110,10 +1170,7 @@ void flowpipe_run(Flowpipe* F) {
             w *= 2;
         }
     }
-    if (!F->homog) {
-        REACH_CUDA(cudaEventRecord(ev_side, F->side));
-        REACH_CUDA(cudaStreamWaitEvent(st, ev_side, 0));
-    }
+    if (!F->homog && !ev_num.empty()) REACH_CUDA(cudaStreamWaitEvent(st, ev_num.back(), 0));
     REACH_CUDA(cudaEventRecord(ctx->ev1, st));
     if (F->homog) {
         F->meta_host.assign(N, make_int2((int)F->p0, 0));
@@ -1135,6 +1192,12 @@ void flowpipe_run(Flowpipe* F) {
         float t = 0;
         REACH_CUDA(cudaEventElapsedTime(&t, F->evs[pr.first], F->evs[pr.second]));
         F->reduce_ms += t;
+    }
+    F->chain_ms = 0;
+    for (auto& pr : chain_ev) {
+        float t = 0;
+        REACH_CUDA(cudaEventElapsedTime(&t, F->evs[pr.first], F->evs[pr.second]));
+        F->chain_ms += t;
     }
     F->ran = true;
 }
@@ -1160,12 +1223,13 @@ void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const do
     try {
         set_kernel_attributes(F);
         GP g = F->g;
+        bind_set(g, F->gset[0]);
         // step "k = 1" on slot 0 with an empty W
         REACH_CUDA(cudaMemsetAsync(g.wCount, 0, sizeof(int), st));
         score_and_sort(F, g, 0, 1, st);
         launch_chain(g, 1, 1, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
         const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
-        wbox_partial_kernel<<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
+        wbox_partial_kernel<16><<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, 1, 1);
         REACH_CUDA(cudaGetLastError());
         const int64_t cap = g.capW;
@@ -1484,6 +1548,13 @@ void reach_ensemble_free(reach_ensemble* en) {
     cudaStreamSynchronize(en->ctx->stream);
     flowpipe_free(en->f);
     delete en;
+}
+
+int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, double* numerics_ms) {
+    if (!fp) return REACH_EINVAL;
+    if (chain_ms) *chain_ms = fp->f->chain_ms;
+    if (numerics_ms) *numerics_ms = fp->f->reduce_ms;
+    return REACH_OK;
 }
 
 void reach_flowpipe_free(reach_flowpipe* fp) {
