@@ -26,6 +26,7 @@
 #include "../../include/reach.h"
 #include <algorithm>
 #include <cmath>
+#include <climits>
 
 namespace reach {
 
@@ -35,7 +36,7 @@ constexpr int MODE_UNCHANGED = 0;   // r*n >= p: reduce_order returns Z unchange
 constexpr int MODE_REDUCE = 1;
 constexpr int NBW = 4;              // box-sum chunks per step for the W / R reduction
 constexpr int NBR = 16;
-constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
+constexpr int COPY_CTAS = 16;       // copy CTAs per step of the R gather (a warp resolves and moves 32 columns at a time)
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
 constexpr int CHAIN_THREADS = 256;    // small enough to share an SM with the numerics kernels (16 K registers)
 constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
@@ -160,6 +161,79 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
         if (valid) g.skS[base + less] = he;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) g.cntS[t * 2 + seg] = nvalid;
+}
+
+// Same result as sort_segments_kernel for segments of up to 4096 generators: bitonic sort of (score, index) pairs in
+// shared memory, one CTA per (step, segment).  O(len log^2 len) instead of O(len^2).
+constexpr int BITONIC_MAX = 4096;
+__global__ void __launch_bounds__(512) sort_segments_bitonic_kernel(GP g, int P) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    double* kk = reinterpret_cast<double*>(bsm);            // [P] scores
+    int* ix = reinterpret_cast<int*>(kk + P);               // [P] indices
+    __shared__ int wsum[16];
+    const int t = blockIdx.x >> 1, seg = blockIdx.x & 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = seg ? g.pV : g.p0;
+    const int base = t * g.q + (seg ? g.p0 : 0);
+    for (int i = tid; i < P; i += 512) {
+        kk[i] = i < len ? g.hS[base + i] : INFINITY;
+        ix[i] = i;
+    }
+    __syncthreads();
+    // compact position of every valid generator (exclusive scan of the valid flags in index order)
+    {
+        const int per = (len + 511) / 512;
+        const int lo = tid * per, hi = min(len, lo + per);
+        int c = 0;
+        for (int i = lo; i < hi; ++i) c += kk[i] < INFINITY;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int v = lane < 16 ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (lane < 16) wsum[lane] = v;
+        }
+        __syncthreads();
+        int run = inc - c + (wid ? wsum[wid - 1] : 0);
+        for (int i = lo; i < hi; ++i) {
+            g.cposS[base + i] = run;
+            run += kk[i] < INFINITY;
+        }
+        if (tid == 0) g.cntS[t * 2 + seg] = wsum[15];
+    }
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int x = tid; x < P / 2; x += 512) {
+                const int i = ((x & ~(j - 1)) << 1) | (x & (j - 1));      // index with bit j clear
+                const int l = i | j;
+                const double a = kk[i], b = kk[l];
+                const int ia = ix[i], ib = ix[l];
+                const bool up = (i & k) == 0;
+                const bool gt = a > b || (a == b && ia > ib);
+                if (gt == up) { kk[i] = b; kk[l] = a; ix[i] = ib; ix[l] = ia; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int pos = tid; pos < P; pos += 512) {
+        const int e = ix[pos];
+        if (e < len) {
+            const double h = kk[pos];
+            const bool valid = h < INFINITY;
+            g.rkS[base + e] = valid ? pos : -1;
+            if (valid) g.skS[base + pos] = h;
+        }
+    }
 }
 
 __device__ __forceinline__ int lower_bound_ent(const WEnt* a, int len, double key) {   // # entries with key < key
@@ -569,7 +643,13 @@ __global__ void __launch_bounds__(256) wbox_partial_kernel(GP g, int k0) {
         const int chunk = (pl.m + NBW - 1) / NBW;
         const int lo = b * chunk, hi = min(pl.m, lo + chunk);
         const int* dl = g.dlistW + (int64_t)t * g.capDisc;
-        for (int s = lo + warp; s < hi; s += 8) acc_add(g, a, dl[s], lane, false);
+        const int wchunk = (chunk + 7) / 8;
+        const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
+        for (int s0 = wlo; s0 < whi; s0 += 32) {
+            const int ref = s0 + lane < whi ? dl[s0 + lane] : -1;
+            const int cntj = min(32, whi - s0);
+            for (int j = 0; j < cntj; ++j) acc_add(g, a, __shfl_sync(0xffffffffu, ref, j), lane, false);
+        }
     }
     acc_reduce_store(g, a, red_s, out);
 }
@@ -678,6 +758,29 @@ __global__ void __launch_bounds__(256) rank_r_kernel(GP g, int k0) {
 
 // R gather of the batch: blockIdx.x < NBR accumulate the boxed generators (chunks of sigma), the other CTAs move the
 // kept ones into the flowpipe slot, warp per column.
+constexpr int NO_JOB = INT_MIN;
+
+// (reference, destination column) of copy job `job` of step t, or NO_JOB
+__device__ __forceinline__ void resolve_copy_job(const GP& g, const PlanR& pl, const int* order, const WEnt* sn, int t, int job,
+                                                 int jobs, int& ref, int& dest) {
+    ref = NO_JOB; dest = 0;
+    if (job >= jobs) return;
+    if (pl.mode == MODE_REDUCE) {
+        if (job < pl.m) return;
+        const int code = order[job];
+        ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
+        dest = job - pl.m;
+    } else if (job < g.p0) {          // unchanged: [valid columns of A in order | W in logical order]
+        if (!(g.hS[t * g.q + job] < INFINITY)) return;
+        ref = (int)(g.col0 + t * g.q + job);
+        dest = g.cposS[t * g.q + job];
+    } else {
+        const WEnt w = sn[job - g.p0];
+        ref = w.ref;
+        dest = pl.pA + w.pos;
+    }
+}
+
 template <int IT>
 __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     extern __shared__ double red_s[];
@@ -690,12 +793,20 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
         Acc<IT> a;
         acc_zero(a);
         if (pl.mode == MODE_REDUCE) {
+            // chunk of sigma per CTA, a contiguous sub-chunk per warp; the 32 lanes resolve 32 references at once so that
+            // the column reads are not serialised behind order -> snapshot -> column pointer chases
             const int chunk = (pl.m + NBR - 1) / NBR;
             const int lo = blockIdx.x * chunk, hi = min(pl.m, lo + chunk);
-            for (int s = lo + warp; s < hi; s += 8) {
-                const int code = order[s];
-                const int ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
-                acc_add(g, a, ref, lane, true);
+            const int wchunk = (chunk + 7) / 8;
+            const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
+            for (int s0 = wlo; s0 < whi; s0 += 32) {
+                int ref = NO_JOB;
+                if (s0 + lane < whi) {
+                    const int code = order[s0 + lane];
+                    ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
+                }
+                const int cntj = min(32, whi - s0);
+                for (int j = 0; j < cntj; ++j) acc_add(g, a, __shfl_sync(0xffffffffu, ref, j), lane, true);
             }
         }
         acc_reduce_store(g, a, red_s, g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
@@ -705,36 +816,35 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     const int nwarps = (gridDim.x - NBR) * 8;
     const int w0 = (blockIdx.x - NBR) * 8 + warp;
     const int jobs = pl.mode == MODE_REDUCE ? pl.pin : g.p0 + pl.pW;
-    for (int job = w0; job < jobs; job += nwarps) {
+    for (int j0 = w0 * 32; j0 < jobs; j0 += nwarps * 32) {
         int ref, dest;
-        if (pl.mode == MODE_REDUCE) {
-            if (job < pl.m) continue;
-            const int code = order[job];
-            ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
-            dest = job - pl.m;
-        } else if (job < g.p0) {          // unchanged: [valid columns of A in order | W in logical order]
-            if (!(g.hS[t * g.q + job] < INFINITY)) continue;
-            ref = (int)(g.col0 + t * g.q + job);
-            dest = g.cposS[t * g.q + job];
-        } else {
-            const int rho = job - g.p0;
-            ref = sn[rho].ref;
-            dest = pl.pA + sn[rho].pos;
+        resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);       // 32 jobs resolved in parallel
+        double tval = 0.0;
+        int trow = -1;
+        if (ref != NO_JOB && ref < 0) {
+            int kt;
+            tag_decode(ref, g.n, kt, trow);
+            tval = g.Wd[(int64_t)kt * g.ld + trow];
         }
-        double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)dest * g.ld);
-        if (ref >= 0) {
-            const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)ref * g.ld);
+        const unsigned live = __ballot_sync(0xffffffffu, ref != NO_JOB);
+        for (unsigned rest = live; rest;) {
+            const int j = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const int r = __shfl_sync(0xffffffffu, ref, j), d = __shfl_sync(0xffffffffu, dest, j);
+            double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)d * g.ld);
+            if (r >= 0) {
+                const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)r * g.ld);
 #pragma unroll 4
-            for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
-        } else {
-            int kt, it;
-            tag_decode(ref, g.n, kt, it);
-            const double val = g.Wd[(int64_t)kt * g.ld + it];
-            for (int i = lane; i < n2; i += 32) {
-                double2 v = make_double2(0.0, 0.0);
-                if (2 * i == it) v.x = val;
-                if (2 * i + 1 == it) v.y = val;
-                d2[i] = v;
+                for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
+            } else {
+                const double val = __shfl_sync(0xffffffffu, tval, j);
+                const int it = __shfl_sync(0xffffffffu, trow, j);
+                for (int i = lane; i < n2; i += 32) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (2 * i == it) v.x = val;
+                    if (2 * i + 1 == it) v.y = val;
+                    d2[i] = v;
+                }
             }
         }
     }
@@ -855,6 +965,7 @@ struct Flowpipe {
     int chain_use_smem = 1;
     cudaStream_t side = nullptr;    // selection chain of batch b (overlaps the GEMM of batch b+1) ...
     cudaStream_t side2 = nullptr;   // ... and the numerics of batch b (overlap the chain of batch b+1)
+    cudaStream_t side3 = nullptr;   // scores + segment order of batch b (only need the GEMM of batch b)
     GP gset[2];                     // batch-local arrays, double-buffered by batch parity
     std::vector<void*> owned;
     std::vector<int2> meta_host;
@@ -863,6 +974,8 @@ struct Flowpipe {
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
     double* stage = nullptr;        // staging for box queries
+    bool detail = false;            // REACH_TIMING_DETAIL
+    std::vector<cudaEvent_t> detail_ev;
 };
 
 void flowpipe_free(Flowpipe* F) {
@@ -872,6 +985,7 @@ void flowpipe_free(Flowpipe* F) {
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
     if (F->side) cudaStreamDestroy(F->side);
     if (F->side2) cudaStreamDestroy(F->side2);
+    if (F->side3) cudaStreamDestroy(F->side3);
     delete F;
 }
 
@@ -1001,6 +1115,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             REACH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             REACH_CUDA(cudaStreamCreateWithPriority(&F->side, cudaStreamNonBlocking, prio_hi));      // the chain is the critical path
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side2, cudaStreamNonBlocking));
+            REACH_CUDA(cudaStreamCreateWithFlags(&F->side3, cudaStreamNonBlocking));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
             if (p0 > 0) REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
             if (ld > n) REACH_CUDA(cudaMemset2DAsync(g.Rg + n, ld * 8, 0, (ld - n) * 8, p0 > 0 ? p0 : 1, st));
@@ -1034,8 +1149,14 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
     if (per > 0) {
         score_stack_kernel<<<(unsigned)ceil_div((int64_t)cnt * per, 8), 256, 0, st>>>(g, cnt);
         const int maxlen = std::max(g.p0, g.pV);
-        dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(maxlen, 256)), (unsigned)(cnt * 2));
-        sort_segments_kernel<<<grid, 256, 0, st>>>(g);
+        if (maxlen <= BITONIC_MAX) {
+            int P = 2;
+            while (P < maxlen) P <<= 1;
+            sort_segments_bitonic_kernel<<<(unsigned)(cnt * 2), 512, (size_t)P * 12, st>>>(g, P);
+        } else {
+            dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(maxlen, 256)), (unsigned)(cnt * 2));
+            sort_segments_kernel<<<grid, 256, 0, st>>>(g);
+        }
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 2;
     } else {
@@ -1051,7 +1172,6 @@ static void bind_set(GP& g, const GP& h) {
 
 // selection chain of steps [k0, k0 + cnt) (their slots k-1 are in the archive already) ...
 static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
-    score_and_sort(F, g, k0 - 1, cnt, st);
     launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches += 1;
@@ -1061,17 +1181,31 @@ static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) 
 static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st) {
     const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
     const int it = F->ld <= 256 ? 4 : (F->ld <= 512 ? 8 : 16);
+    auto mark = [&]() {          // REACH_TIMING_DETAIL=1: CUDA events between the kernels (diagnostics only)
+        if (!F->detail) return;
+        cudaEvent_t e;
+        REACH_CUDA(cudaEventCreate(&e));
+        REACH_CUDA(cudaEventRecord(e, st));
+        F->detail_ev.push_back(e);
+    };
+    mark();
     if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
     else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
     else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    mark();
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
+    mark();
     rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
+    mark();
     const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
     if (it == 4) apply_r_kernel<4><<<ag, 256, red_smem, st>>>(g, k0);
     else if (it == 8) apply_r_kernel<8><<<ag, 256, red_smem, st>>>(g, k0);
     else apply_r_kernel<16><<<ag, 256, red_smem, st>>>(g, k0);
+    mark();
     finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
+    mark();
     expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
+    mark();
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches += 6;
 }
@@ -1080,6 +1214,7 @@ static void set_kernel_attributes(Flowpipe* F) {
     static bool done = false;
     if (done) return;
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(sort_segments_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BITONIC_MAX * 12));
     REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     done = true;
@@ -1117,8 +1252,9 @@ void flowpipe_run(Flowpipe* F) {
         Ctx* c; int old;
         ReserveGuard(Ctx* c_, int v) : c(c_), old(c_->gemm_reserve_sms) { c->gemm_reserve_sms = v; }
         ~ReserveGuard() { c->gemm_reserve_sms = old; }
-    } reserve(ctx, F->homog ? 0 : 1);
+    } reserve(ctx, 0);      // measured: letting the GEMM keep every SM (the chain co-resides) beats reserving SMs
     std::vector<std::pair<size_t, size_t>> chain_ev;
+    F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
     if (!F->homog) {
         set_kernel_attributes(F);
         bind_set(g, F->gset[0]);
@@ -1145,9 +1281,14 @@ void flowpipe_run(Flowpipe* F) {
         if (!F->homog) {
             cudaEvent_t ev_gemm = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
-            REACH_CUDA(cudaStreamWaitEvent(F->side, ev_gemm, 0));
-            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(F->side, ev_num[bi - 2], 0));
+            // scores / segment order: after this batch's GEMM and after the numerics that last used this array set
+            REACH_CUDA(cudaStreamWaitEvent(F->side3, ev_gemm, 0));
+            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(F->side3, ev_num[bi - 2], 0));
             bind_set(g, F->gset[bi & 1]);
+            score_and_sort(F, g, have, (int)cnt, F->side3);
+            cudaEvent_t ev_sort = next_event(F, ev_used);
+            REACH_CUDA(cudaEventRecord(ev_sort, F->side3));
+            REACH_CUDA(cudaStreamWaitEvent(F->side, ev_sort, 0));
             cudaEvent_t c0 = next_event(F, ev_used), c1 = next_event(F, ev_used);
             chain_ev.push_back({ev_used - 2, ev_used - 1});
             REACH_CUDA(cudaEventRecord(c0, F->side));
@@ -1192,6 +1333,19 @@ void flowpipe_run(Flowpipe* F) {
         float t = 0;
         REACH_CUDA(cudaEventElapsedTime(&t, F->evs[pr.first], F->evs[pr.second]));
         F->reduce_ms += t;
+    }
+    if (F->detail && !F->detail_ev.empty()) {
+        const char* names[6] = {"wbox_partial", "wseq", "rank_r", "apply_r", "finalize_r", "expand_diag"};
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i + 6 < F->detail_ev.size() + 0 && i + 6 < F->detail_ev.size() + 1; i += 7)
+            for (int j = 0; j < 6; ++j) {
+                float t = 0;
+                cudaEventElapsedTime(&t, F->detail_ev[i + j], F->detail_ev[i + j + 1]);
+                acc[j] += t;
+            }
+        for (int j = 0; j < 6; ++j) fprintf(stderr, "[reach detail] %-13s %8.3f ms in situ\n", names[j], acc[j]);
+        for (cudaEvent_t e : F->detail_ev) cudaEventDestroy(e);
+        F->detail_ev.clear();
     }
     F->chain_ms = 0;
     for (auto& pr : chain_ev) {
