@@ -290,7 +290,7 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        tt = dict(gemm_ms=0.0, gemm_flops=0.0, reduce_ms=0.0, gemm_launches=0)
+        tt = dict(gemm_ms=0.0, gemm_flops=0.0, reduce_ms=0.0, gemm_launches=0, chain_ms=0.0)
         for _ in range(args.steps):
             one_flowpipe()
             t = fp.timing()
@@ -342,7 +342,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
     hbm, hbm_src = _peaks()
     alg_bytes = glgm06_algorithmic_bytes_per_step(n, p0, pV, r) * flow_steps * args.steps
     red_s = tt["reduce_ms"] * 1e-3
-    achieved = alg_bytes / red_s / 1e9 if red_s > 0 else None
+    gemm_tf = tt["gemm_flops"] / (tt["gemm_ms"] * 1e-3) / 1e12 if tt["gemm_ms"] else None
+    nbatches = int(tt["gemm_launches"])
     return {
         "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -354,17 +355,24 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         "e2e": e2e_obj,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
-                     "traffic": None,
-                     "kernel": "apply_step_kernel + rank_lists_kernel (the two Girard reductions of a step: selection, gather, box)",
-                     "launches": int(2 * flow_steps * args.steps), "kernel_ms_total": tt["reduce_ms"],
-                     "kernel_share_of_step": tt["reduce_ms"] / ms,
-                     "peak_source": hbm_src,
-                     "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
-                     "second_kernel": {"kernel": "gemm_dmma_kernel<.,true> (Phi^s * stacked [G0|GV|c0|cV], left multiplication)",
-                                       "bound": "tensor", "achieved": tt["gemm_flops"] / (tt["gemm_ms"] * 1e-3) / 1e12 if tt["gemm_ms"] else None,
-                                       "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "kernel_ms_total": tt["gemm_ms"],
-                                       "launches": int(tt["gemm_launches"])}},
+        # dominant kernel by work: the left-multiplication DMMA GEMM that maps the generators of a whole batch of steps.
+        # Its CUDA-event time is taken IN SITU, i.e. while the selection chain and the batched numerics of the
+        # neighbouring batches share the SMs with it (three overlapping streams), so it understates the kernel alone
+        # (30.4 TFLOP/s in isolation, profiles/r01/gemm_left_check_b200.log).
+        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None, "traffic": None,
+                     "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA)",
+                     "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
+                     "algorithmic_flops_per_flowpipe_step": 2.0 * n * n * (p0 + pV + 2),
+                     "peak_source": "FP64 DMMA register-resident loop measured on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl)",
+                     "second_kernel": {"kernel": "batched numerics of the two Girard reductions (wbox_partial, wseq, rank_r, apply_r, "
+                                                 "finalize_r, expand_diag), second side stream, in situ",
+                                       "bound": "hbm", "achieved": alg_bytes / red_s / 1e9 if red_s > 0 else None, "peak": hbm,
+                                       "unit": "GB/s", "frac": alg_bytes / red_s / 1e9 / hbm if red_s > 0 else None,
+                                       "peak_source": hbm_src, "kernel_ms_total": tt["reduce_ms"],
+                                       "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r)},
+                     "selection_chain": {"kernel": "chain_kernel (one persistent CTA, key logic only)", "kernel_ms_total": tt["chain_ms"],
+                                         "us_per_flowpipe_step": 1e3 * tt["chain_ms"] / (flow_steps * args.steps)}},
     }
 
 

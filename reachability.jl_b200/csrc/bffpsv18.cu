@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(128) map_finish_kernel(int nrows, int q, int n
 }
 
 double* dvec_alloc(Ctx* ctx, int64_t len, const double* host) {
-    double* p = nullptr;
-    REACH_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)(len > 0 ? len : 1)));
+    double* p = (double*)ctx_malloc(ctx, sizeof(double) * (size_t)(len > 0 ? len : 1));
     if (host && len > 0)
         REACH_CUDA(cudaMemcpyAsync(p, host, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
     else
@@ -292,7 +291,7 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
             P->rU = dvec_alloc(ctx, m, rU);
             P->rpsi = dvec_alloc(ctx, n, rpsi);
         }
-        REACH_CUDA(cudaMalloc(&P->rows, sizeof(int32_t) * nrows));
+        P->rows = (int32_t*)ctx_malloc(ctx, sizeof(int32_t) * nrows);
         REACH_CUDA(cudaMemcpyAsync(P->rows, rows, sizeof(int32_t) * nrows, cudaMemcpyHostToDevice, ctx->stream));
         P->centers = dvec_alloc(ctx, nrows * N, nullptr);
         P->radii = dvec_alloc(ctx, nrows * N, nullptr);
@@ -325,10 +324,10 @@ void boxplan_destroy(BoxPlan* P) {
     for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->MU})
         dmat_free(*d);
     for (double* v : {P->c0, P->r0, P->rpsi, P->cU, P->rU, P->bsum, P->fsum, P->cW, P->rW, P->centers, P->radii})
-        if (v) cudaFree(v);
-    if (P->rows) cudaFree(P->rows);
+        if (v) ctx_free(P->ctx, v);
+    if (P->rows) ctx_free(P->ctx, P->rows);
     for (void* v : {(void*)P->Mmap, (void*)P->blk_len, (void*)P->zpart, (void*)P->out_c, (void*)P->out_r, (void*)P->viol})
-        if (v) cudaFree(v);
+        if (v) ctx_free(P->ctx, v);
     for (cudaEvent_t e : P->evs) cudaEventDestroy(e);
     delete P;
 }
@@ -507,12 +506,12 @@ void boxplan_attach_map(BoxPlan* P, int64_t q, const double* M, int64_t ldm, int
     P->nchunks = ceil_div(P->n, MAP_CHUNK);
     P->check = check; P->bound = bound; P->eager = eager;
     cudaStream_t st = ctx->stream;
-    REACH_CUDA(cudaMalloc(&P->Mmap, sizeof(double) * q * nrows));
-    REACH_CUDA(cudaMalloc(&P->blk_len, sizeof(int32_t) * nrows));
-    REACH_CUDA(cudaMalloc(&P->zpart, sizeof(double) * (size_t)P->s * P->nchunks * q));
-    REACH_CUDA(cudaMalloc(&P->out_c, sizeof(double) * q * P->N));
-    REACH_CUDA(cudaMalloc(&P->out_r, sizeof(double) * q * P->N));
-    REACH_CUDA(cudaMalloc(&P->viol, sizeof(long long)));
+    P->Mmap = (decltype(P->Mmap))ctx_malloc(ctx, sizeof(double) * q * nrows);
+    P->blk_len = (decltype(P->blk_len))ctx_malloc(ctx, sizeof(int32_t) * nrows);
+    P->zpart = (decltype(P->zpart))ctx_malloc(ctx, sizeof(double) * (size_t)P->s * P->nchunks * q);
+    P->out_c = (decltype(P->out_c))ctx_malloc(ctx, sizeof(double) * q * P->N);
+    P->out_r = (decltype(P->out_r))ctx_malloc(ctx, sizeof(double) * q * P->N);
+    P->viol = (decltype(P->viol))ctx_malloc(ctx, sizeof(long long));
     REACH_CUDA(cudaMemsetAsync(P->out_c, 0, sizeof(double) * q * P->N, st));
     REACH_CUDA(cudaMemsetAsync(P->out_r, 0, sizeof(double) * q * P->N, st));
     REACH_CUDA(cudaMemcpyAsync(P->Mmap, Mh.data(), sizeof(double) * q * nrows, cudaMemcpyHostToDevice, st));

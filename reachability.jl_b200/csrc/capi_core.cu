@@ -70,6 +70,7 @@ void reach_ctx_destroy(reach_ctx* ctx) {
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
     for (void* p : ctx->c.scratch) cudaFree(p);
+    ctx_release_pool(&ctx->c);
     if (ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
     if (ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
     if (ctx->c.stream && ctx->c.owns_stream) cudaStreamDestroy(ctx->c.stream);

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <map>
+#include <unordered_map>
 #include <cuda_runtime.h>
 
 namespace reach {
@@ -39,7 +41,9 @@ inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 
 // Device matrix, column-major (Julia layout), zero-padded so that every tile the GEMM touches exists:
 //   rows_alloc = round_up(rows, 8) + 128 slack, cols_alloc = round_up(cols, 128)  (see DESIGN.md "HBM layout").
+struct Ctx;
 struct DMat {
+    Ctx* ctx = nullptr;
     double* p = nullptr;
     int64_t rows = 0, cols = 0;     // logical
     int64_t ld = 0;                 // leading dimension (doubles), multiple of 16
@@ -60,7 +64,17 @@ struct Ctx {
     double t_discretize_ms = 0, t_loop_ms = 0, t_h2d_ms = 0, t_d2h_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> scratch;     // freed at destroy
+    // size-keyed cache of device blocks: repeated calls with the same shapes (one-shot C-ABI entry points) skip
+    // cudaMalloc / cudaFree.  Blocks are only recycled after the owning stream has been synchronised.
+    std::multimap<size_t, void*> pool;
+    std::unordered_map<void*, size_t> block_size;
+    size_t pooled_bytes = 0;
+    size_t pool_limit = (size_t)48 << 30;
 };
+
+void* ctx_malloc(Ctx* ctx, size_t bytes);       // never returns nullptr (throws)
+void ctx_free(Ctx* ctx, void* p);               // back to the cache (or cudaFree beyond the limit)
+void ctx_release_pool(Ctx* ctx);
 
 DMat dmat_alloc(Ctx* ctx, int64_t rows, int64_t cols, int64_t extra_rows = 0);
 void dmat_free(DMat& m);

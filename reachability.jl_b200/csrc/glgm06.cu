@@ -941,9 +941,8 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
 
 template <typename T>
 T* dalloc(Ctx* ctx, size_t count, bool zero = true) {
-    T* p = nullptr;
     if (count == 0) count = 1;
-    REACH_CUDA(cudaMalloc(&p, sizeof(T) * count));
+    T* p = (T*)ctx_malloc(ctx, sizeof(T) * count);
     if (zero) REACH_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * count, ctx->stream));
     return p;
 }
@@ -981,7 +980,7 @@ struct Flowpipe {
 void flowpipe_free(Flowpipe* F) {
     if (!F) return;
     dmat_free(F->Phi); dmat_free(F->PowA); dmat_free(F->PowB);
-    for (void* p : F->owned) cudaFree(p);
+    for (void* p : F->owned) ctx_free(F->ctx, p);
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
     if (F->side) cudaStreamDestroy(F->side);
     if (F->side2) cudaStreamDestroy(F->side2);
@@ -1041,6 +1040,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         const size_t cols = (size_t)N * q + 256;
         size_t free_b = 0, total_b = 0;
         REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->pooled_bytes;       // cached blocks are released on demand (ctx_malloc)
         double need = (double)cols * ld * 8.0;
         if (!homog) {
             const int64_t rn = max_order * n;
