@@ -36,7 +36,8 @@ constexpr int MODE_UNCHANGED = 0;   // r*n >= p: reduce_order returns Z unchange
 constexpr int MODE_REDUCE = 1;
 constexpr int NBW = 4;              // box-sum chunks per step for the W / R reduction
 constexpr int NBR = 16;
-constexpr int COPY_CTAS = 16;       // copy CTAs per step of the R gather (a warp resolves and moves 32 columns at a time)
+constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
+constexpr int COPY_JB = 8;          // columns a warp resolves (one per lane) and then moves back to back
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
 constexpr int CHAIN_THREADS = 256;    // small enough to share an SM with the numerics kernels (16 K registers)
 constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
@@ -816,9 +817,9 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
     const int nwarps = (gridDim.x - NBR) * 8;
     const int w0 = (blockIdx.x - NBR) * 8 + warp;
     const int jobs = pl.mode == MODE_REDUCE ? pl.pin : g.p0 + pl.pW;
-    for (int j0 = w0 * 32; j0 < jobs; j0 += nwarps * 32) {
-        int ref, dest;
-        resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);       // 32 jobs resolved in parallel
+    for (int j0 = w0 * COPY_JB; j0 < jobs; j0 += nwarps * COPY_JB) {
+        int ref = NO_JOB, dest = 0;
+        if (lane < COPY_JB) resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);   // resolved in parallel
         double tval = 0.0;
         int trow = -1;
         if (ref != NO_JOB && ref < 0) {
