@@ -165,3 +165,46 @@ def test_boxplan_is_repeatable_and_counts_launches(ctx):
     t = plan.timing()
     assert t["run_ms"] > 0 and t["gemm_launches"] > 0
     plan.close()
+
+
+def test_config_c4_mna5_full_dimension(ctx):
+    """BASELINE.json configs[3]: n = 10913 (MNA5-shaped), 1-D blocks, delta = 1e-3.  Full state dimension on the GPU
+    (Phi = 953 MB, 2.6 TFLOP per step); the oracle follows a handful of rows (its cost is O(rows n^2) per step) with
+    the same Phi, which the device discretisation produces (device expm is pinned against the oracle at smaller n in
+    tests/test_discretize_gpu.py).  Also checks the row sharding of SURVEY.md section 8e at this size: two disjoint
+    row shards reproduce the rows of the unsharded run bit for bit."""
+    from reachability_jl_b200 import workloads as wl
+    from reachability_jl_b200 import sharding
+    w = wl.mna5()
+    n = w.n
+    out = ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU)
+    D = orc.DiscreteBoxProblem(out["Phi"], out["c0"], out["r0"], out["MU"], out["cU"], out["rU"], out["rpsi"], out["rE"], None)
+    # the device discretisation at this size: a few columns of Phi against the action of the sparse exponential
+    # (scipy expm_multiply, Al-Mohy & Higham), and Omega0's box contains X0
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import expm_multiply
+    cols = [0, 5, n // 2, n - 1]
+    I4 = np.zeros((n, len(cols)))
+    I4[cols, range(len(cols))] = 1.0
+    E = expm_multiply(sp.csc_matrix(w.A) * w.delta, I4)
+    assert np.max(np.abs(out["Phi"][:, cols] - E)) < 1e-11
+    assert np.all(out["c0"] - out["r0"] <= w.c - w.r + 1e-15) and np.all(out["c0"] + out["r0"] >= w.c + w.r - 1e-15)
+    N = 12
+    rows = np.array([0, 1, 9, 10, 1212, 5000, 5001, 10912], dtype=np.int32)
+    Co, Ro = orc.bffpsv18_reach(D, N, rows)
+    C, R = ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+    assert_close(C.T, Co, "C4 centres (row subset)")
+    assert_close(R.T, Ro, "C4 radii (row subset)")
+    # all rows, sharded over 2 "ranks" (contiguous whole blocks), vs the same rows taken from the subset run
+    part = [[i] for i in range(1, n + 1)]
+    blocks = list(range(1, n + 1))
+    r0_ = sharding.shard_rows(part, blocks, 0, 2)
+    r1_ = sharding.shard_rows(part, blocks, 1, 2)
+    assert len(r0_) + len(r1_) == n and r0_[-1] + 1 == r1_[0]
+    Cs0, Rs0 = ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, 4, D.MU, D.cU, D.rU, D.rpsi, r0_)
+    Cs1, Rs1 = ctx.bffpsv18_boxes(D.Phi, D.c0, D.r0, 4, D.MU, D.cU, D.rU, D.rpsi, r1_)
+    full_c = np.vstack([Cs0, Cs1])
+    full_r = np.vstack([Rs0, Rs1])
+    assert_close(full_c[rows, :], Co[:4].T, "sharded centres")
+    assert_close(full_r[rows, :], Ro[:4].T, "sharded radii")
+    assert np.all(full_r >= 0)
