@@ -228,7 +228,11 @@ def run_bffpsv18(args, rank, world, dist):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None, "traffic": None,
+                     "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (M=16128, N=1008, K=1006) from the
+                     # `ncu --set full` capture profiles/r01/ncu_gemm_dmma_c3_raw_summary.txt: 138.8 MB + 93.2 MB
+                     # (algorithmic: 130 MB stack read + 8 MB Phi^s + 130 MB stack write, part of which stays in L2)
+                     "traffic": 232.0e6 if (w.n == 1006 and world == 1) else None,
                      "kernel": "gemm_dmma_kernel (stacked power GEMM S·[Phi^s | dB | c0])",
                      "launches": int(gemm_launches), "kernel_ms_total": gemm_ms,
                      "kernel_share_of_step": gemm_ms / ms,
@@ -360,7 +364,10 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         # neighbouring batches share the SMs with it (three overlapping streams), so it understates the kernel alone
         # (30.4 TFLOP/s in isolation, profiles/r01/gemm_left_check_b200.log).
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None, "traffic": None,
+                     "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None,
+                     # one 32-step launch (270 x 43488 x 270): dram read 96.0 MB + write 52.8 MB
+                     # (profiles/r01/ncu_glgm06_c2_raw_summary.txt); algorithmic 94.6 MB read + 94.6 MB write
+                     "traffic": 148.8e6,
                      "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA)",
                      "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
                      "algorithmic_flops_per_flowpipe_step": 2.0 * n * n * (p0 + pV + 2),
