@@ -320,8 +320,7 @@ def run_glgm06(args, rank, world, dist, e2e=True):
 
             def one_e2e():
                 f2 = ctx.glgm06(hPhi, Om.c, hG0, N, r, D.V.c, hGV, 0)
-                f2.run()
-                f2.fetch(hC, hG)
+                f2.run_fetch(hC, hG)
                 f2.close()
 
             one_e2e()
@@ -336,8 +335,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
             e2e_obj = {"value": world * e2e_steps * (N - 1) / e2e_s, "unit": "flowpipe steps/s",
                        "h2d_bytes_per_step": 8 * (n * n + n * (p0 + pV) + 2 * n),
                        "d2h_bytes_per_step": int(8 * n * (int(p.sum()) + N)), "steps": e2e_steps,
-                       "api": "reach_glgm06_create + reach_glgm06_run + reach_flowpipe_fetch (pinned host buffers; every "
-                              "zonotope of the flowpipe copied back, as reach_inhomog! materialises them)"}
+                       "api": "reach_glgm06_create + reach_glgm06_run_fetch (pinned host buffers; every zonotope of the "
+                              "flowpipe copied back, batch by batch while later batches compute, as reach_inhomog! materialises them)"}
         ctx.close()
     if rank != 0:
         return None

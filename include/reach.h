@@ -131,6 +131,10 @@ REACH_API int32_t reach_glgm06_create(reach_ctx* ctx, int64_t n, const double* P
                             const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV,
                             int64_t ldgv, int64_t N, int64_t max_order, int32_t flags, reach_flowpipe** out);
 REACH_API int32_t reach_glgm06_run(reach_flowpipe* fp); /* whole recurrence on the device; results stay there */
+/* run + fetch in one call, streamed: every batch of reach sets is copied to the host (layout of reach_flowpipe_fetch;
+ * pinned buffers overlap best) while the later batches are still being computed.  This is the shape of
+ * `reach_inhomog!(R, ...)` filling its caller-allocated vector (GLGM06/reach.jl:30-36). */
+REACH_API int32_t reach_glgm06_run_fetch(reach_flowpipe* fp, double* centers, double* G, int64_t pmax);
 /* Number of generators of every reach set R_1..R_N. */
 REACH_API int32_t reach_flowpipe_ngens(reach_flowpipe* fp, int32_t* p /* N */);
 /* Reach set k (1-based): centre (n) and generators (n x p_k, leading dimension ldg >= n). */

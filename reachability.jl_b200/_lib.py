@@ -52,6 +52,7 @@ _SIGNATURES = {
     "reach_glgm06_create": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
                             i64, i64, i64, i32, C.POINTER(vp)],
     "reach_glgm06_run": [vp],
+    "reach_glgm06_run_fetch": [vp, c_double_p, c_double_p, i64],
     "reach_flowpipe_ngens": [vp, c_int32_p],
     "reach_flowpipe_step": [vp, i64, c_double_p, c_double_p, i64],
     "reach_flowpipe_fetch": [vp, c_double_p, c_double_p, i64],

@@ -283,6 +283,13 @@ class Flowpipe:
         self.ctx._check(self.ctx.lib.reach_glgm06_run(self._h))
         return self
 
+    def run_fetch(self, centers, G):
+        """Run and stream every reach set into caller-owned Fortran arrays centers (n, N), G (n, pmax, N)."""
+        assert centers.flags.f_contiguous and G.flags.f_contiguous
+        assert centers.shape == (self.n, self.N) and G.shape[0] == self.n and G.shape[2] == self.N
+        self.ctx._check(self.ctx.lib.reach_glgm06_run_fetch(self._h, dptr(centers), dptr(G), G.shape[1]))
+        return self
+
     def ngens(self) -> np.ndarray:
         p = np.zeros(self.N, dtype=np.int32)
         self.ctx._check(self.ctx.lib.reach_flowpipe_ngens(self._h, iptr(p)))

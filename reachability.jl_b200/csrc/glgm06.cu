@@ -906,6 +906,18 @@ __global__ void __launch_bounds__(256) expand_diag_kernel(GP g, int k0, int k1) 
     }
 }
 
+// Reach sets of steps [k0, k0 + cnt) packed for the host: slab t = n x pmax doubles (leading dimension n), columns
+// beyond the set's generator count zeroed.  One warp per column.
+__global__ void __launch_bounds__(256) pack_slots_kernel(GP g, int k0, int cnt, int pmax, double* __restrict__ out) {
+    const int t = blockIdx.y, k = k0 + t, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= cnt || warp >= pmax) return;
+    const int2 mt = g.meta[k - 1];
+    const int p = mt.x + mt.y;
+    const double* src = g.Rg + (int64_t)(k - 1) * g.slot + (int64_t)warp * g.ld;
+    double* dst = out + ((int64_t)t * pmax + warp) * g.n;
+    for (int i = lane; i < g.n; i += 32) dst[i] = warp < p ? src[i] : 0.0;
+}
+
 // Dense copy of the current W in logical order (box generators synthesised).  out: n x pW, leading dimension ldo.
 __global__ void __launch_bounds__(256) materialize_w_kernel(GP g, double* __restrict__ out, int ldo) {
     const int pW = *g.wCount;
@@ -974,6 +986,10 @@ struct Flowpipe {
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
     double* stage = nullptr;        // staging for box queries
+    // streaming fetch (reach_glgm06_run_fetch): host destination, copy stream, device staging of one batch
+    double* sink_c = nullptr; double* sink_G = nullptr; int64_t sink_pmax = 0;
+    cudaStream_t cpy = nullptr;
+    double* pack = nullptr;
     bool detail = false;            // REACH_TIMING_DETAIL
     std::vector<cudaEvent_t> detail_ev;
 };
@@ -986,6 +1002,7 @@ void flowpipe_free(Flowpipe* F) {
     if (F->side) cudaStreamDestroy(F->side);
     if (F->side2) cudaStreamDestroy(F->side2);
     if (F->side3) cudaStreamDestroy(F->side3);
+    if (F->cpy) cudaStreamDestroy(F->cpy);
     delete F;
 }
 
@@ -1265,6 +1282,14 @@ void flowpipe_run(Flowpipe* F) {
         init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 256)), 256, 0, st>>>(g);
         REACH_CUDA(cudaGetLastError());
         ctx->launches++;
+        if (F->sink_G) {            // R_1 = Omega0
+            cudaEvent_t ev_init = next_event(F, ev_used);
+            REACH_CUDA(cudaEventRecord(ev_init, st));
+            REACH_CUDA(cudaStreamWaitEvent(F->cpy, ev_init, 0));
+            pack_slots_kernel<<<dim3((unsigned)ceil_div(F->sink_pmax, 8), 1u), 256, 0, F->cpy>>>(g, 1, 1, (int)F->sink_pmax, F->pack);
+            REACH_CUDA(cudaGetLastError());
+            REACH_CUDA(cudaMemcpyAsync(F->sink_G, F->pack, (size_t)n * F->sink_pmax * 8, cudaMemcpyDeviceToHost, F->cpy));
+        }
     }
     // slot j = Phi^j X.  With Phi^w in hand, slots [have, have + w) = Phi^w * slots [have - w, have): doubling until
     // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) form one batch.  Three streams:
@@ -1302,6 +1327,15 @@ void flowpipe_run(Flowpipe* F) {
             process_numerics(F, g, (int)have + 1, (int)cnt, F->side2);
             REACH_CUDA(cudaEventRecord(e1, F->side2));
             ev_num.push_back(e1);
+            if (F->sink_G) {        // stream this batch's reach sets to the host while the later batches are computed
+                REACH_CUDA(cudaStreamWaitEvent(F->cpy, e1, 0));
+                dim3 pg((unsigned)ceil_div(F->sink_pmax, 8), (unsigned)cnt);
+                pack_slots_kernel<<<pg, 256, 0, F->cpy>>>(g, (int)have + 1, (int)cnt, (int)F->sink_pmax, F->pack);
+                REACH_CUDA(cudaGetLastError());
+                ctx->launches++;
+                REACH_CUDA(cudaMemcpyAsync(F->sink_G + have * n * F->sink_pmax, F->pack, (size_t)cnt * n * F->sink_pmax * 8,
+                                           cudaMemcpyDeviceToHost, F->cpy));
+            }
             ++bi;
         }
         have += cnt;
@@ -1313,6 +1347,13 @@ void flowpipe_run(Flowpipe* F) {
         }
     }
     if (!F->homog && !ev_num.empty()) REACH_CUDA(cudaStreamWaitEvent(st, ev_num.back(), 0));
+    if (!F->homog && (F->sink_G || F->sink_c)) {
+        cudaEvent_t ev_cpy = next_event(F, ev_used);
+        if (F->sink_c)
+            REACH_CUDA(cudaMemcpy2DAsync(F->sink_c, n * 8, g.Rc, ld * 8, n * 8, N, cudaMemcpyDeviceToHost, F->cpy));
+        REACH_CUDA(cudaEventRecord(ev_cpy, F->cpy));
+        REACH_CUDA(cudaStreamWaitEvent(st, ev_cpy, 0));
+    }
     REACH_CUDA(cudaEventRecord(ctx->ev1, st));
     if (F->homog) {
         F->meta_host.assign(N, make_int2((int)F->p0, 0));
@@ -1478,6 +1519,34 @@ int32_t reach_glgm06_run(reach_flowpipe* fp) {
     if (!fp) return REACH_EINVAL;
     FP_BEGIN(fp->ctx)
     flowpipe_run(fp->f);
+    return REACH_OK;
+    FP_END(fp->ctx)
+}
+
+int32_t reach_glgm06_run_fetch(reach_flowpipe* fp, double* centers, double* G, int64_t pmax) {
+    if (!fp) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    Flowpipe* F = fp->f;
+    if (F->homog || !G) {           // nothing to overlap: run, then fetch
+        flowpipe_run(F);
+        return reach_flowpipe_fetch(fp, centers, G, pmax);
+    }
+    REACH_REQUIRE(pmax >= 1, "reach_glgm06_run_fetch: pmax must be positive");
+    if (!F->cpy) REACH_CUDA(cudaStreamCreateWithFlags(&F->cpy, cudaStreamNonBlocking));
+    F->pack = (double*)ctx_malloc(F->ctx, (size_t)F->s * F->n * pmax * 8);
+    F->sink_c = centers; F->sink_G = G; F->sink_pmax = pmax;
+    try {
+        flowpipe_run(F);
+    } catch (...) {
+        F->sink_c = F->sink_G = nullptr;
+        ctx_free(F->ctx, F->pack); F->pack = nullptr;
+        throw;
+    }
+    F->sink_c = F->sink_G = nullptr;
+    ctx_free(F->ctx, F->pack); F->pack = nullptr;
+    for (int64_t k = 0; k < F->N; ++k)
+        REACH_REQUIRE(F->meta_host[k].x + F->meta_host[k].y <= pmax,
+                      "reach_glgm06_run_fetch: pmax smaller than a reach set's generator count (that set is truncated)");
     return REACH_OK;
     FP_END(fp->ctx)
 }

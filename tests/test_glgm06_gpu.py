@@ -137,6 +137,22 @@ def test_bulk_fetch_matches_stepwise(ctx):
     fp.close()
 
 
+def test_streamed_run_fetch_matches_fetch(ctx):
+    A, X0, B, U, delta = _problem(13, 20, 3)
+    N = 70
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, 4, True)
+    fp = _device(ctx, D, Om, N, 4, True, record=False)
+    C, G, p = fp.fetch()
+    C2 = np.full_like(C, np.nan)
+    G2 = np.full_like(G, np.nan)
+    fp.run_fetch(C2, G2)
+    assert np.array_equal(C, C2)
+    for k in range(N):
+        assert np.array_equal(G[:, :p[k], k], G2[:, :p[k], k])
+        assert np.all(G2[:, p[k]:, k] == 0.0)
+    fp.close()
+
+
 def test_c2_shaped_reduced(ctx):
     """BASELINE.json config C2 (ISS-shaped modal system, GLGM06, max_order 10) at n=54, N=60."""
     from reachability_jl_b200 import workloads as wl
