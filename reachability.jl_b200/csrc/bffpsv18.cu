@@ -32,6 +32,11 @@ struct BoxPlan {
     double run_ms = 0, gemm_ms = 0, gemm_flops = 0;
     int64_t gemm_launches = 0;
     std::vector<cudaEvent_t> evs;
+    // the streaming passes of block b (abs-row-sums, scan) overlap the GEMM of block b+1 on a side stream
+    cudaStream_t side = nullptr;
+    DMat E1;
+    double *bsum1 = nullptr, *fsum1 = nullptr;
+    std::vector<cudaEvent_t> sync_evs;
     // ---- lazy-state variants: output_function (reach_blocks.jl:152-155,191-199) and check mode
     //      (check_blocks.jl:105-183).  The states stay lazy per block, so the radius is
     //      sum_b |M[:, b] P[b, :]| r0 + |M| rW   (support function of a CartesianProductArray is separable per block).
@@ -310,6 +315,12 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
             P->E = dmat_alloc(ctx, s * P->Rp, m + 1);
             P->bsum = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
             P->fsum = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
+            if ((N - 1) > s) {      // more than one block: double-buffer what the side stream consumes
+                P->E1 = dmat_alloc(ctx, s * P->Rp, m + 1);
+                P->bsum1 = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
+                P->fsum1 = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
+                REACH_CUDA(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+            }
         }
         REACH_CUDA(cudaStreamSynchronize(ctx->stream));   // host pointers are not retained past this call
     } catch (...) {
@@ -321,8 +332,12 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
 
 void boxplan_destroy(BoxPlan* P) {
     if (!P) return;
-    for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->MU})
+    for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->E1, &P->MU})
         dmat_free(*d);
+    for (double* v : {P->bsum1, P->fsum1})
+        if (v) ctx_free(P->ctx, v);
+    if (P->side) cudaStreamDestroy(P->side);
+    for (cudaEvent_t e : P->sync_evs) cudaEventDestroy(e);
     for (double* v : {P->c0, P->r0, P->rpsi, P->cU, P->rU, P->bsum, P->fsum, P->cW, P->rW, P->centers, P->radii})
         if (v) ctx_free(P->ctx, v);
     if (P->rows) ctx_free(P->ctx, P->rows);
@@ -407,36 +422,77 @@ void boxplan_run(BoxPlan* P) {
         const int64_t npow = N - 1;
         const int64_t nblocks = ceil_div(npow, s);
         int cur = 0;
+        // Overlap (plain box mode, more than one block): abs-row-sums of block b run beside GEMM b (both only read
+        // S[cur]); the scan of block b runs beside GEMM b+1.  E / bsum / fsum are double-buffered by block parity.
+        const bool overlap = !P->qmap && P->side != nullptr && nblocks > 1;
+        size_t sync_used = 0;
+        auto sync_event = [&]() {
+            if (sync_used == P->sync_evs.size()) {
+                cudaEvent_t e;
+                REACH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                P->sync_evs.push_back(e);
+            }
+            return P->sync_evs[sync_used++];
+        };
+        std::vector<cudaEvent_t> evG, evAbs, evScan;
+        if (overlap) {
+            cudaEvent_t ready = sync_event();
+            REACH_CUDA(cudaEventRecord(ready, st));
+            REACH_CUDA(cudaStreamWaitEvent(P->side, ready, 0));
+        }
         for (int64_t b = 0; b < nblocks; ++b) {
             const int64_t cnt = std::min<int64_t>(s, npow - b * s);
             const bool last = (b == nblocks - 1);
+            const int par = overlap ? (int)(b & 1) : 0;
+            DMat& Eb = par ? P->E1 : P->E;
+            double* bsum = par ? P->bsum1 : P->bsum;
+            double* fsum = par ? P->fsum1 : P->fsum;
+            cudaStream_t ss = overlap ? P->side : st;
+            if (overlap) {
+                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(st, evAbs[b - 1], 0));      // GEMM b overwrites the stack abs(b-1) read
+                if (b > 1) REACH_CUDA(cudaStreamWaitEvent(st, evScan[b - 2], 0));     // ... and the E buffer scan(b-2) read
+            }
             cudaEvent_t e0 = next_event(), e1 = next_event();
             REACH_CUDA(cudaEventRecord(e0, st));
             if (!last) {
                 GemmEpilogue ep;
-                ep.C2 = P->E.p; ep.ldc2 = P->E.ld; ep.nsplit = n;
+                ep.C2 = Eb.p; ep.ldc2 = Eb.ld; ep.nsplit = n;
                 gemm_nt(ctx, s * Rp, n + m + 1, n, P->S[cur].p, P->S[cur].ld, P->BtAug.p, P->BtAug.ld, P->S[cur ^ 1].p,
                         P->S[cur ^ 1].ld, ep);
                 P->gemm_flops += 2.0 * (double)(s * nrows) * n * (double)(n + m + 1);
             } else {
-                gemm_nt(ctx, cnt * Rp, m + 1, n, P->S[cur].p, P->S[cur].ld, P->BtSmall.p, P->BtSmall.ld, P->E.p, P->E.ld);
+                gemm_nt(ctx, cnt * Rp, m + 1, n, P->S[cur].p, P->S[cur].ld, P->BtSmall.p, P->BtSmall.ld, Eb.p, Eb.ld);
                 P->gemm_flops += 2.0 * (double)(cnt * nrows) * n * (double)(m + 1);
             }
             REACH_CUDA(cudaEventRecord(e1, st));
             P->gemm_launches++;
+            if (overlap) {
+                evG.push_back(sync_event());
+                REACH_CUDA(cudaEventRecord(evG[b], st));
+                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(ss, evG[b - 1], 0));        // S[cur] of this block is complete
+            }
             const unsigned grid = (unsigned)ceil_div(cnt * Rp, 64);
             if (m > 0)
-                abs_rowsums_kernel<true><<<grid, 256, 0, st>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, P->rpsi,
-                                                               P->bsum, P->fsum);
+                abs_rowsums_kernel<true><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, P->rpsi,
+                                                               bsum, fsum);
             else
-                abs_rowsums_kernel<false><<<grid, 256, 0, st>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, nullptr,
-                                                                P->bsum, nullptr);
+                abs_rowsums_kernel<false><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, nullptr,
+                                                                bsum, nullptr);
             REACH_CUDA(cudaGetLastError());
-            scan_block_kernel<<<(unsigned)ceil_div(nrows, 64), 64, 0, st>>>(
-                (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, P->E.p, P->E.ld, P->bsum, P->fsum, P->cU, P->rU, P->cW,
+            if (overlap) {
+                evAbs.push_back(sync_event());
+                REACH_CUDA(cudaEventRecord(evAbs[b], ss));
+                REACH_CUDA(cudaStreamWaitEvent(ss, evG[b], 0));                       // E of this block is complete
+            }
+            scan_block_kernel<<<(unsigned)ceil_div(nrows, 64), 64, 0, ss>>>(
+                (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, Eb.p, Eb.ld, bsum, fsum, P->cU, P->rU, P->cW,
                 P->rW, P->centers, P->radii, P->qmap ? 0 : 1);
             REACH_CUDA(cudaGetLastError());
             ctx->launches += 2;
+            if (overlap) {
+                evScan.push_back(sync_event());
+                REACH_CUDA(cudaEventRecord(evScan[b], ss));
+            }
             if (P->qmap) {
                 const size_t smem = sizeof(double) * std::max<size_t>((size_t)P->qmap * nrows, 256 * MAP_Q);
                 dim3 gm((unsigned)P->nchunks, (unsigned)cnt);
@@ -457,6 +513,7 @@ void boxplan_run(BoxPlan* P) {
             }
             cur ^= 1;
         }
+        if (overlap && !evScan.empty()) REACH_CUDA(cudaStreamWaitEvent(st, evScan.back(), 0));
     }
     if (P->qmap) {
         if (P->check) {
