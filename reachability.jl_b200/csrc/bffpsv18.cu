@@ -245,6 +245,67 @@ __global__ void __launch_bounds__(128) map_finish_kernel(int nrows, int q, int n
     }
 }
 
+// Same recurrences as scan_block_kernel for the latency-bound regime (few rows, long blocks: config C1): one WARP per
+// row, every lane owns a contiguous chunk of the block's powers; chunk sums, a warp exclusive scan (shuffles) and a
+// second pass that emits the boxes.  Summation order: chunk-local then across chunks (differs from the sequential
+// order by rounding only; deterministic).
+__global__ void __launch_bounds__(128) scan_block_warp_kernel(int nrows, int m, int64_t Rp, int cnt, int64_t first_power, int64_t N,
+                                                              const double* __restrict__ E, int64_t ldE,
+                                                              const double* __restrict__ bsum, const double* __restrict__ fsum,
+                                                              const double* __restrict__ cU, const double* __restrict__ rU,
+                                                              double* __restrict__ cW, double* __restrict__ rW,
+                                                              double* __restrict__ centers, double* __restrict__ radii, int add_b) {
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= nrows) return;
+    const int chunk = (cnt + 31) / 32;
+    const int j0 = lane * chunk, j1 = min(cnt, j0 + chunk);
+    double sc = 0.0, sr = 0.0;
+    if (m > 0)
+        for (int j = j0; j < j1; ++j) {
+            const int64_t q = first_power + j;
+            if (q + 1 < N) {
+                const int64_t idx = (int64_t)j * Rp + l;
+                double dc = 0.0, dr = 0.0;
+                for (int u = 0; u < m; ++u) {
+                    const double e = E[idx + (int64_t)u * ldE];
+                    dc += e * cU[u];
+                    dr += fabs(e) * rU[u];
+                }
+                sc += dc;
+                sr += dr + fsum[idx];
+            }
+        }
+    double pc = sc, pr = sr;       // inclusive scan over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double vc = __shfl_up_sync(0xffffffffu, pc, o), vr = __shfl_up_sync(0xffffffffu, pr, o);
+        if (lane >= o) { pc += vc; pr += vr; }
+    }
+    const double totc = __shfl_sync(0xffffffffu, pc, 31), totr = __shfl_sync(0xffffffffu, pr, 31);
+    double cw = cW[l] + (pc - sc), rw = rW[l] + (pr - sr);
+    for (int j = j0; j < j1; ++j) {
+        const int64_t q = first_power + j;
+        const int64_t idx = (int64_t)j * Rp + l;
+        centers[q * nrows + l] = E[idx + (int64_t)m * ldE] + cw;
+        radii[q * nrows + l] = add_b ? bsum[idx] + rw : rw;
+        if (m > 0 && q + 1 < N) {
+            double dc = 0.0, dr = 0.0;
+            for (int u = 0; u < m; ++u) {
+                const double e = E[idx + (int64_t)u * ldE];
+                dc += e * cU[u];
+                dr += fabs(e) * rU[u];
+            }
+            cw += dc;
+            rw += dr + fsum[idx];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        cW[l] += totc;
+        rW[l] += totr;
+    }
+}
+
 double* dvec_alloc(Ctx* ctx, int64_t len, const double* host) {
     double* p = (double*)ctx_malloc(ctx, sizeof(double) * (size_t)(len > 0 ? len : 1));
     if (host && len > 0)
@@ -484,9 +545,14 @@ void boxplan_run(BoxPlan* P) {
                 REACH_CUDA(cudaEventRecord(evAbs[b], ss));
                 REACH_CUDA(cudaStreamWaitEvent(ss, evG[b], 0));                       // E of this block is complete
             }
-            scan_block_kernel<<<(unsigned)ceil_div(nrows, 64), 64, 0, ss>>>(
-                (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, Eb.p, Eb.ld, bsum, fsum, P->cU, P->rU, P->cW,
-                P->rW, P->centers, P->radii, P->qmap ? 0 : 1);
+            if (cnt >= 64 && nrows <= 512)
+                scan_block_warp_kernel<<<(unsigned)ceil_div(nrows * 32, 128), 128, 0, ss>>>(
+                    (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, Eb.p, Eb.ld, bsum, fsum, P->cU, P->rU, P->cW,
+                    P->rW, P->centers, P->radii, P->qmap ? 0 : 1);
+            else
+                scan_block_kernel<<<(unsigned)ceil_div(nrows, 64), 64, 0, ss>>>(
+                    (int)nrows, (int)m, Rp, (int)cnt, b * s + 1, N, Eb.p, Eb.ld, bsum, fsum, P->cU, P->rU, P->cW,
+                    P->rW, P->centers, P->radii, P->qmap ? 0 : 1);
             REACH_CUDA(cudaGetLastError());
             ctx->launches += 2;
             if (overlap) {
