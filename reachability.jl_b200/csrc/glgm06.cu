@@ -952,6 +952,71 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     hi[(int64_t)b * n + i] = ci + s;
 }
 
+// Homogeneous recurrence for small state dimension (n <= 32; config C5: n = 28): Y_k = Phi Y_{k-1} column by column.
+// The whole flowpipe is ONE launch: a thread owns one column (a generator or a centre of one ensemble member), keeps it
+// in registers and marches it through all the steps, so every slot is written once and read never (HBM traffic =
+// the flowpipe itself).  Phi travels as a kernel parameter: the fully unrolled FMA chain takes its coefficients from
+// the constant bank, no loads.  Exactly the reference's recurrence R_k = linear_map(Phi, R_{k-1})  (GLGM06/reach.jl:15-19).
+template <int NN>
+struct PhiParam {
+    double v[NN * NN];          // v[i * NN + k] = Phi[i, k], zero padded
+};
+
+template <int NN>
+__global__ void __launch_bounds__(64, 5) homog_small_kernel(const PhiParam<NN> phi, int n, int ld, int64_t q, int64_t nsteps,
+                                                          double* __restrict__ Y) {
+    // the 32 columns of a warp are contiguous in memory (32 * ld doubles): results are transposed through shared memory
+    // so that every store instruction writes 256 contiguous bytes instead of 32 sectors 8 bytes at a time
+    __shared__ double tr[2][32 * (NN + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t col0 = ((int64_t)blockIdx.x * blockDim.x + warp * 32);
+    const int64_t col = col0 + lane;
+    if (col0 >= q) return;
+    const int ncol = (int)min((int64_t)32, q - col0);          // columns of this warp that exist
+    const int chunk = ncol * ld;                                 // doubles this warp owns per slot
+    double x[NN];
+    {
+        const double* src = Y + col0 * ld;
+        for (int idx = lane; idx < chunk; idx += 32) tr[warp][(idx / ld) * (NN + 1) + idx % ld] = src[idx];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NN; ++i) x[i] = (i < n && lane < ncol) ? tr[warp][lane * (NN + 1) + i] : 0.0;
+        __syncwarp();
+    }
+    for (int64_t step = 1; step <= nsteps; ++step) {
+        double y[NN];
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < NN; ++k) acc = fma(phi.v[i * NN + k], x[k], acc);
+            y[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+            tr[warp][lane * (NN + 1) + i] = y[i];
+            x[i] = y[i];
+        }
+        __syncwarp();
+        double* dst = Y + (step * q + col0) * ld;
+        for (int idx = lane; idx < chunk; idx += 32) {
+            const int c = idx / ld, i = idx - c * ld;
+            dst[idx] = i < n ? tr[warp][c * (NN + 1) + i] : 0.0;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NN>
+static void launch_homog_small(Ctx* ctx, const double* phi_host, int n, int ld, int64_t q, int64_t nsteps, double* Y) {
+    PhiParam<NN> P;
+    for (int i = 0; i < NN; ++i)
+        for (int k = 0; k < NN; ++k) P.v[i * NN + k] = (i < n && k < n) ? phi_host[i + (size_t)k * n] : 0.0;
+    homog_small_kernel<NN><<<(unsigned)ceil_div(q, 64), 64, 0, ctx->stream>>>(P, n, ld, q, nsteps, Y);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
 template <typename T>
 T* dalloc(Ctx* ctx, size_t count, bool zero = true) {
     if (count == 0) count = 1;
@@ -990,6 +1055,7 @@ struct Flowpipe {
     double* sink_c = nullptr; double* sink_G = nullptr; int64_t sink_pmax = 0;
     cudaStream_t cpy = nullptr;
     double* pack = nullptr;
+    std::vector<double> phi_host;   // n <= 32: Phi as a kernel parameter of homog_small_kernel
     bool detail = false;            // REACH_TIMING_DETAIL
     std::vector<cudaEvent_t> detail_ev;
 };
@@ -1042,6 +1108,10 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         cudaStream_t st = ctx->stream;
         F->Phi = dmat_alloc(ctx, n, n);
         dmat_upload(ctx, F->Phi, Phi, ldphi);
+        if (homog && n <= 32) {
+            F->phi_host.resize((size_t)n * n);
+            for (int64_t k = 0; k < n; ++k) std::memcpy(&F->phi_host[k * n], Phi + k * ldphi, sizeof(double) * n);
+        }
         if (s > 1) { F->PowA = dmat_alloc(ctx, n, n); F->PowB = dmat_alloc(ctx, n, n); }
         auto own = [&](void* p) { F->owned.push_back(p); return p; };
         auto up2d = [&](double* dst, const double* src, int64_t lds, int64_t cols) {
@@ -1273,6 +1343,22 @@ void flowpipe_run(Flowpipe* F) {
     } reserve(ctx, 0);      // measured: letting the GEMM keep every SM (the chain co-resides) beats reserving SMs
     std::vector<std::pair<size_t, size_t>> chain_ev;
     F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
+    if (F->homog && !F->phi_host.empty() && N > 1) {
+        const int nn = (int)n;
+        if (nn <= 8) launch_homog_small<8>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        else if (nn <= 16) launch_homog_small<16>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        else if (nn <= 24) launch_homog_small<24>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        else if (nn <= 28) launch_homog_small<28>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        else launch_homog_small<32>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        REACH_CUDA(cudaEventRecord(ctx->ev1, st));
+        REACH_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms0 = 0;
+        REACH_CUDA(cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1));
+        F->run_ms = ms0; F->gemm_ms = 0; F->reduce_ms = 0; F->chain_ms = 0;
+        F->meta_host.assign(N, make_int2((int)F->p0, 0));
+        F->ran = true;
+        return;
+    }
     if (!F->homog) {
         set_kernel_attributes(F);
         bind_set(g, F->gset[0]);
