@@ -1,0 +1,80 @@
+"""CPU: the host-side mirror's option handling and bookkeeping (no device needed) -- option tables and validation
+(BFFPSV18.jl:25-129, GLGM06/init.jl:4-29), `compute_blocks` / `compute_dimensions` (BFFPSV18.jl:413-434,
+compute_dimensions.jl:1-15), set helpers, time stamps, and the absence of any CPU fallback."""
+import numpy as np
+import pytest
+
+from oracle import reach_oracle as orc
+from reachability_jl_b200 import ReachError
+from reachability_jl_b200 import api
+from reachability_jl_b200.api import (BFFPSV18, GLGM06, IVP, LCS, BallInf, Ball2Stub, CartesianProductArray, Hyperrectangle,
+                                      Interval, Options, Singleton, dim, ispartition)
+
+
+def test_option_tables_and_aliases():
+    op = BFFPSV18(delta=0.05, vars=[1, 3], partition=[[1, 2], [3, 4]])
+    assert op["δ"] == 0.05 and op["discretization"] == "forward" and op["algorithm"] == "explicit"
+    assert BFFPSV18(sampling_time=0.2)["δ"] == 0.2
+    assert GLGM06()["max_order"] == 10 and GLGM06()["δ"] == 1e-2
+    assert Options(time_horizon=3.0)["T"] == 3.0
+    for bad in (dict(δ=0.0), dict(algorithm="implicit"), dict(vars=[]), dict(vars=[0, 1]), dict(partition=[[2], [1]]), dict(nope=1)):
+        with pytest.raises(ValueError):
+            BFFPSV18(**bad)
+    with pytest.raises(ValueError):
+        GLGM06(order=3)
+
+
+def test_ispartition_and_blocks_match_the_oracle():
+    assert ispartition([[1, 2], [3], [4, 5, 6]]) and not ispartition([[1, 3], [2]]) and not ispartition([[2, 3]])
+    part = [[1, 2], [3, 4], [5], [6, 7, 8]]
+    for vars_ in ([1], [3], [1, 3], [5, 8], [2, 4, 6], list(range(1, 9))):
+        assert api.compute_blocks(vars_, part) == orc.compute_blocks(vars_, part)
+        b = api.compute_blocks(vars_, part)
+        assert api.compute_dimensions(part, b) == orc.compute_dimensions(part, b)
+
+
+def test_sets_and_products():
+    X = Interval(0.99, 1.01) * Interval(-1.0, 1.0) * BallInf([0.0, 2.0], 0.5)
+    assert isinstance(X, CartesianProductArray) and dim(X) == 4
+    c, r = api._as_box(X, "set")
+    assert np.allclose(c, [1.0, 0.0, 0.0, 2.0]) and np.allclose(r, [0.01, 1.0, 0.5, 0.5])
+    assert np.array_equal(Singleton([1.0, 2.0]).radius, [0.0, 0.0])
+    with pytest.raises(ValueError):
+        Hyperrectangle([0.0], [-1.0])
+    with pytest.raises(ReachError) as ei:
+        api._as_box(Ball2Stub([0.0, 0.0], 1.0), "initial set")
+    assert ei.value.code == 3 and "no CPU fallback" in str(ei.value)
+
+
+def test_time_stamps_accumulate_like_the_reference():
+    t0, t1 = api._times(5, 0.1)                       # t0 = t1; t1 += δ  (reach_blocks.jl:200-201)
+    acc, ref0, ref1 = 0.1, [0.0], [0.1]
+    for _ in range(4):
+        ref0.append(acc)
+        acc += 0.1
+        ref1.append(acc)
+    assert list(t0) == ref0 and list(t1) == ref1
+
+
+def test_solve_argument_errors_come_before_any_device_work():
+    A = np.eye(3)
+    with pytest.raises(ValueError):
+        api.solve(IVP(LCS(A), BallInf(np.ones(3), 0.1)), Options())                 # no time horizon
+    with pytest.raises(ValueError):
+        api.solve(IVP(LCS(A), BallInf(np.ones(3), 0.1)), Options(T=-1.0))
+    with pytest.raises(ValueError):
+        api.solve(IVP(LCS(A), BallInf(np.ones(3), 0.1)), Options(T=1.0, mode="check"))
+    with pytest.raises(AssertionError):
+        api.solve(IVP(LCS(A), BallInf(np.ones(2), 0.1)), Options(T=1.0))            # solve.jl:64
+
+
+def test_block_option_rules():
+    part = [[1], [2, 3]]
+    assert api._block_set_types(BFFPSV18(), part) == [Interval, Hyperrectangle]       # BFFPSV18.jl:436-443
+    assert api._block_set_types(BFFPSV18(block_options=Hyperrectangle), part) == [Hyperrectangle, Hyperrectangle]
+    with pytest.raises(ValueError):
+        api._block_set_types(BFFPSV18(block_options=Interval), part)                  # Interval needs a 1-D block
+    with pytest.raises(ReachError):
+        api._block_set_types(BFFPSV18(block_options=Ball2Stub), part)                 # not on the device path
+    with pytest.raises(ValueError):
+        api._block_set_types(BFFPSV18(block_options=-1.0), part)                      # DomainError in the reference

@@ -221,3 +221,20 @@ def test_ensemble_homogeneous(ctx, n, p, batch, N):
         assert_close(lo[:, b], R[-1].c - rad, "lo")
         assert_close(hi[:, b], R[-1].c + rad, "hi")
     ens.close()
+
+
+def test_long_w_list_uses_global_scratch(ctx):
+    """r*n large enough that the selection chain's working set exceeds shared memory (global-scratch instantiation)."""
+    A, X0, B, U, delta = _problem(21, 96, 40)
+    N, r = 12, 75                                   # capW = 7208 entries > 200 KB of chain state
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, r, True)
+    fp = _device(ctx, D, Om, N, r, True)
+    _compare(fp, R, sels, N)
+    fp.close()
+    # and a reduction that actually triggers with a long list: many input generators, moderate order
+    A, X0, B, U, delta = _problem(22, 64, 64)
+    N, r = 40, 3
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, r, False)
+    fp = _device(ctx, D, Om, N, r, False)
+    _compare(fp, R, sels, N)
+    fp.close()
