@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
     __shared__ int scan_s[CHAIN_THREADS / 32];
     __shared__ int rows_s[CHAIN_ROWS * (CHAIN_THREADS / 32)];
-    __shared__ int s_pC[64];
+    __shared__ int s_pC[128];
     __shared__ int s_nd, s_cz, s_czw;
     const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
     // working set (shared memory, or global scratch when the W list is too long): the sorted list of W, double-buffered;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
     int* sigC = hist + cap + 2;                                // [pV]
     int* cRk0 = sigC + pV;                                     // [2][pV]
     int* cCp0 = cRk0 + 2 * pV;                                 // [2][pV]
-    if (tid < cnt && tid < 64) s_pC[tid] = g.cntS[tid * 2 + 1];
+    if (tid < cnt && tid < 128) s_pC[tid] = g.cntS[tid * 2 + 1];
     int pW = *g.wCount;
     for (int r = tid; r < pW; r += CHAIN_THREADS) ebuf0[r] = g.wEnt[r];
     for (int e = tid; e < pV; e += CHAIN_THREADS) {
@@ -1073,10 +1073,11 @@ void flowpipe_free(Flowpipe* F) {
 }
 
 static int64_t pick_block(int64_t n, int64_t q, int64_t N) {
-    // enough stacked columns for ~4 waves of 128-row tiles on 148 SMs
+    // enough stacked columns for ~8 waves of 128-row tiles on 148 SMs (power of two: the doubling schedule needs it);
+    // measured at C2: s = 16 / 32 / 64 / 128 -> 27.7 / 22.8 / 21.5 / 21.3 ms per 2000-step flowpipe
     const int64_t tiles_n = ceil_div(n, 96);
     int64_t s = 1;
-    while (s < 64 && s < N - 1 && ceil_div(s * q, 128) * tiles_n < 148 * 4) s *= 2;
+    while (s < 64 && s < N - 1 && ceil_div(s * q, 128) * tiles_n < 148 * 8) s *= 2;
     return s;
 }
 
@@ -1104,6 +1105,11 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         F->q = homog ? p0 + F->nc : p0 + pV + 2;
         const int64_t q = F->q;
         F->s = N > 2 ? pick_block(n, q, N) : 1;
+        if (getenv("REACH_GLGM06_BLOCK") && N > 2) {      // tuning knob, rounded down to a power of two
+            int64_t want = std::max(1, std::min(128, atoi(getenv("REACH_GLGM06_BLOCK")))), pw2 = 1;
+            while (pw2 * 2 <= want) pw2 *= 2;
+            F->s = pw2;
+        }
         const int64_t s = F->s;
         cudaStream_t st = ctx->stream;
         F->Phi = dmat_alloc(ctx, n, n);
