@@ -952,69 +952,76 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     hi[(int64_t)b * n + i] = ci + s;
 }
 
-// Homogeneous recurrence for small state dimension (n <= 32; config C5: n = 28): Y_k = Phi Y_{k-1} column by column.
-// The whole flowpipe is ONE launch: a thread owns one column (a generator or a centre of one ensemble member), keeps it
-// in registers and marches it through all the steps, so every slot is written once and read never (HBM traffic =
-// the flowpipe itself).  Phi travels as a kernel parameter: the fully unrolled FMA chain takes its coefficients from
-// the constant bank, no loads.  Exactly the reference's recurrence R_k = linear_map(Phi, R_{k-1})  (GLGM06/reach.jl:15-19).
-template <int NN>
-struct PhiParam {
-    double v[NN * NN];          // v[i * NN + k] = Phi[i, k], zero padded
-};
+// Homogeneous recurrence for small state dimension (n <= 32; config C5: n = 28): Y_k = Phi Y_{k-1}, exactly the reference's
+// R_k = linear_map(Phi, R_{k-1}) (GLGM06/reach.jl:15-19).  The whole flowpipe is ONE launch: every slot is written once
+// and read never (HBM traffic = the flowpipe itself).  A thread-per-column FMA version reached 150 k steps/s on 512
+// members of C5 (the FP64 vector pipe tops out near 11 TFLOP/s on B200); this tensor-core version reaches 270 k:
+// a warp owns 32 consecutive columns.  Phi sits in registers as m8n8k4 A fragments for the whole flowpipe; every
+// step reads the B fragments of the current columns from a padded shared-memory tile (pitch 36: conflict-free), runs
+// MT x 4 x KT DMMAs, writes the accumulators back into the tile and streams the tile out with 256-byte stores.
+__device__ __forceinline__ void dmma884_acc(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
-template <int NN>
-__global__ void __launch_bounds__(64, 5) homog_small_kernel(const PhiParam<NN> phi, int n, int ld, int64_t q, int64_t nsteps,
-                                                          double* __restrict__ Y) {
-    // the 32 columns of a warp are contiguous in memory (32 * ld doubles): results are transposed through shared memory
-    // so that every store instruction writes 256 contiguous bytes instead of 32 sectors 8 bytes at a time
-    __shared__ double tr[2][32 * (NN + 1)];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t col0 = ((int64_t)blockIdx.x * blockDim.x + warp * 32);
-    const int64_t col = col0 + lane;
+template <int MT, int KT>
+__global__ void __launch_bounds__(128) homog_small_dmma_kernel(const double* __restrict__ Phi, int ldphi, int n, int ld, int64_t q,
+                                                               int64_t nsteps, double* __restrict__ Y) {
+    constexpr int P = 36;
+    __shared__ double tile[4][32 * P];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t col0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;
     if (col0 >= q) return;
-    const int ncol = (int)min((int64_t)32, q - col0);          // columns of this warp that exist
-    const int chunk = ncol * ld;                                 // doubles this warp owns per slot
-    double x[NN];
+    const int ncol = (int)min((int64_t)32, q - col0);
+    const int chunk = ncol * ld;
+    double* tr = tile[warp];
+    double a[MT][KT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            const int row = 8 * mt + g, k = 4 * kt + t;
+            a[mt][kt] = (row < n && k < n) ? Phi[row + (int64_t)k * ldphi] : 0.0;
+        }
+    for (int idx = lane; idx < 32 * P; idx += 32) tr[idx] = 0.0;
+    __syncwarp();
     {
         const double* src = Y + col0 * ld;
-        for (int idx = lane; idx < chunk; idx += 32) tr[warp][(idx / ld) * (NN + 1) + idx % ld] = src[idx];
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < NN; ++i) x[i] = (i < n && lane < ncol) ? tr[warp][lane * (NN + 1) + i] : 0.0;
-        __syncwarp();
+        for (int idx = lane; idx < chunk; idx += 32) {
+            const int c = idx / ld, i = idx - c * ld;
+            if (i < n) tr[c * P + i] = src[idx];
+        }
     }
+    __syncwarp();
     for (int64_t step = 1; step <= nsteps; ++step) {
-        double y[NN];
+        double d[MT][4][2];
 #pragma unroll
-        for (int i = 0; i < NN; ++i) {
-            double acc = 0.0;
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int k = 0; k < NN; ++k) acc = fma(phi.v[i * NN + k], x[k], acc);
-            y[i] = acc;
-        }
+            for (int nt = 0; nt < 4; ++nt) d[mt][nt][0] = d[mt][nt][1] = 0.0;
 #pragma unroll
-        for (int i = 0; i < NN; ++i) {
-            tr[warp][lane * (NN + 1) + i] = y[i];
-            x[i] = y[i];
-        }
+        for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const double b = tr[(8 * nt + g) * P + 4 * kt + t];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma884_acc(d[mt][nt][0], d[mt][nt][1], a[mt][kt], b);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                tr[(8 * nt + 2 * t) * P + 8 * mt + g] = d[mt][nt][0];
+                tr[(8 * nt + 2 * t + 1) * P + 8 * mt + g] = d[mt][nt][1];
+            }
         __syncwarp();
         double* dst = Y + (step * q + col0) * ld;
         for (int idx = lane; idx < chunk; idx += 32) {
             const int c = idx / ld, i = idx - c * ld;
-            dst[idx] = i < n ? tr[warp][c * (NN + 1) + i] : 0.0;
+            dst[idx] = i < n ? tr[c * P + i] : 0.0;
         }
         __syncwarp();
     }
-}
-
-template <int NN>
-static void launch_homog_small(Ctx* ctx, const double* phi_host, int n, int ld, int64_t q, int64_t nsteps, double* Y) {
-    PhiParam<NN> P;
-    for (int i = 0; i < NN; ++i)
-        for (int k = 0; k < NN; ++k) P.v[i * NN + k] = (i < n && k < n) ? phi_host[i + (size_t)k * n] : 0.0;
-    homog_small_kernel<NN><<<(unsigned)ceil_div(q, 64), 64, 0, ctx->stream>>>(P, n, ld, q, nsteps, Y);
-    REACH_CUDA(cudaGetLastError());
-    ctx->launches++;
 }
 
 template <typename T>
@@ -1351,11 +1358,17 @@ void flowpipe_run(Flowpipe* F) {
     F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
     if (F->homog && !F->phi_host.empty() && N > 1) {
         const int nn = (int)n;
-        if (nn <= 8) launch_homog_small<8>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
-        else if (nn <= 16) launch_homog_small<16>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
-        else if (nn <= 24) launch_homog_small<24>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
-        else if (nn <= 28) launch_homog_small<28>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
-        else launch_homog_small<32>(ctx, F->phi_host.data(), nn, (int)ld, q, N - 1, F->Hflow);
+        const unsigned grid = (unsigned)ceil_div(q, 128);
+#define REACH_HOMOG_DMMA(MT, KT)                                                                                               \
+    homog_small_dmma_kernel<MT, KT><<<grid, 128, 0, st>>>(F->Phi.p, (int)F->Phi.ld, nn, (int)ld, q, N - 1, F->Hflow)
+        if (nn <= 8) REACH_HOMOG_DMMA(1, 2);
+        else if (nn <= 16) REACH_HOMOG_DMMA(2, 4);
+        else if (nn <= 24) REACH_HOMOG_DMMA(3, 6);
+        else if (nn <= 28) REACH_HOMOG_DMMA(4, 7);
+        else REACH_HOMOG_DMMA(4, 8);
+#undef REACH_HOMOG_DMMA
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
         REACH_CUDA(cudaEventRecord(ctx->ev1, st));
         REACH_CUDA(cudaEventSynchronize(ctx->ev1));
         float ms0 = 0;
