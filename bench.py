@@ -399,6 +399,88 @@ def cpu_baseline_glgm06(target_s=12.0):
                       "reach_inhomog! + reduce_order", "host_cpus": os.cpu_count()}
 
 
+def run_ensemble(args, rank, world, dist):
+    """C5: batched homogeneous GLGM06 ensemble of a heli28-shaped system (n = 28).  512 members per GPU (the 4096
+    splits of BASELINE.json's config on 8 GPUs), members sharded by rank, no collective: weak scaling."""
+    import torch
+    import reachability_jl_b200 as rb
+    from oracle import reach_oracle as orc
+    from reachability_jl_b200 import workloads as wl, sharding
+    w = wl.heli28()
+    n = w.n
+    per_gpu = 512
+    total = per_gpu * world
+    N = args.flow_steps or orc.n_steps_glgm06(w.T, w.delta)
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.Phi2(np.abs(w.A), w.delta)
+    cs, rs = wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])           # 4096 sub-boxes of X0
+    sl = sharding.shard_batch(total, rank, world)
+    cs, rs = cs[:, sl], rs[:, sl]
+    D0 = orc.discretize_zonotope(w.A, orc.Box(cs[:, 0], rs[:, 0]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2)
+    p = D0.Omega0.ngens
+    c0s = np.zeros((n, per_gpu), order="F")
+    G0s = np.zeros((n, p, per_gpu), order="F")
+    for b in range(per_gpu):
+        Db = orc.discretize_zonotope(w.A, orc.Box(cs[:, b], rs[:, b]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2)
+        c0s[:, b], G0s[:, :, b] = Db.Omega0.c, Db.Omega0.G
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+    with torch.cuda.stream(stream):
+        ctx = rb.Context(dev, stream=stream.cuda_stream)
+        ens = ctx.ensemble(Phi, c0s, G0s, N)
+
+        def one():
+            flush.zero_()
+            ens.run()
+
+        for _ in range(args.warmup):
+            one()
+        sampler = ClockSampler(dev)
+        launches0 = ctx.launch_count()
+        _barrier(dist, world)
+        torch.cuda.synchronize()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        kern_ms = 0.0
+        for _ in range(args.steps):
+            one()
+            kern_ms += ens.timing()["run_ms"]
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        _barrier(dist, world)
+        clocks = sampler.stop()
+        ms = _max_over_ranks(dist, world, ev0.elapsed_time(ev1), dev)
+        launches = ctx.launch_count() - launches0 + args.steps
+        lo, hi = ens.boxes(N)
+        assert np.all(np.isfinite(lo)) and np.all(hi >= lo)
+        ens.close()
+        ctx.close()
+    if rank != 0:
+        return None
+    hbm, hbm_src = _peaks()
+    steps = N - 1
+    bytes_per_step = 16.0 * n * (p + 1) * per_gpu                         # SURVEY 8(d): read + write of one ensemble step
+    achieved = bytes_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e9
+    return {
+        "metric": METRIC, "value": args.steps * steps * total / (ms * 1e-3), "unit": "ensemble member flowpipe steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5-heli28 ensemble: n={n}, {p} generators, {per_gpu} members per GPU ({total} in total), "
+                               f"homogeneous GLGM06, delta={w.delta}, N={N} reach sets per bench step",
+                   "parallelism": f"members sharded x{world}, Phi replicated, no collective",
+                   "l2": "256 MB L2 flush between timed iterations; the ensemble flowpipe (19.7 GB per GPU) exceeds L2"},
+        "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "kernel": "homog_small_dmma_kernel<4,7> (whole flowpipe in one launch; real traffic = the writes, half of the "
+                               "algorithmic read+write figure)", "launches": args.steps, "kernel_ms_total": kern_ms,
+                     "kernel_share_of_step": kern_ms / ms, "peak_source": hbm_src,
+                     "algorithmic_bytes_per_ensemble_step": bytes_per_step},
+    }
+
+
 def _as_tensor(ptr, count, dev):
     """Zero-copy torch view of a device buffer owned by the library."""
     import torch
@@ -518,7 +600,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the second headline workload (C2 GLGM06) summary")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -540,6 +622,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     if args.workload == "C2":
         out = run_glgm06(args, rank, world, dist)
+    elif args.workload == "C5":
+        out = run_ensemble(args, rank, world, dist)
+        args.no_cpu_baseline = True
     else:
         out = run_bffpsv18(args, rank, world, dist)
     if out is not None:
