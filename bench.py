@@ -207,6 +207,21 @@ def run_bffpsv18(args, rank, world, dist):
         e2e_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
         h2d = 8 * (n * n + n * m + 3 * n + 2 * m) + 4 * R
         d2h = 16 * R * N
+        # solve()-shaped call: device discretisation (A, X0, B, U from the host) + the flowpipe, host results out
+        solve_s = None
+        if e2e_steps:
+            hA = pinned((n, n)); hA[:] = w.A
+
+            def one_solve():
+                Dd = ctx.discretize_box(hA, w.delta, w.c, w.r, w.B, w.cU, w.rU)
+                ctx.bffpsv18_boxes_into(Dd["Phi"], Dd["c0"], Dd["r0"], N, Dd["MU"], Dd["cU"], Dd["rU"], Dd["rpsi"], rows, hc, hr)
+
+            one_solve()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one_solve()
+            torch.cuda.synchronize()
+            solve_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
         plan.close()
         ctx.close()
     if rank != 0:
@@ -224,7 +239,10 @@ def run_bffpsv18(args, rank, world, dist):
                    "rows_per_gpu": R, "parallelism": f"row-block sharding x{world}, Phi replicated" if world > 1 else "single GPU",
                    "l2": "256 MB L2 flush between timed iterations; power stacks 2 x 132 MB exceed L2"},
         "e2e": {"value": e2e_steps * flow_steps / e2e_s if e2e_steps else None, "unit": "flowpipe steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "reach_bffpsv18_boxes (host buffers, pinned)"},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "reach_bffpsv18_boxes (host buffers, pinned)",
+                "with_discretize": {"value": flow_steps / solve_s if solve_s else None, "unit": "flowpipe steps/s",
+                                    "api": "reach_discretize_box + reach_bffpsv18_boxes: N / t_solve of SURVEY 8(d), expm and "
+                                           "Phi2(|A|) on the device included"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",

@@ -238,3 +238,50 @@ def test_long_w_list_uses_global_scratch(ctx):
     fp = _device(ctx, D, Om, N, r, False)
     _compare(fp, R, sels, N)
     fp.close()
+
+
+def test_config_c2_full_size_properties(ctx):
+    """BASELINE.json configs[1] at full size (n = 270, max_order 10, N = 2000, 2700 generators per reach set, 11.7 GB):
+    (a) the first 120 reach sets -- growth phase, first reductions, steady state -- equal the oracle's entry by entry;
+    (b) size-independent properties over all 2000 steps: generator counts, closed-form centres at sampled steps
+        (c_k = Phi^{k-1} c0 + sum_{j<k-1} Phi^j cV, reduce_order never moves the centre), the box part of every
+        sampled reach set is axis-aligned and non-negative, and a second run reproduces the first bit for bit."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.iss()
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.phi12_series(np.abs(w.A), w.delta)[2]
+    D = orc.discretize_zonotope(w.A, orc.Box(w.c, w.r), w.delta, w.B, orc.Box(w.cU, w.rU), Phi=Phi, Phi2abs=P2)
+    Om = orc.reduce_order(D.Omega0, w.max_order)
+    N = orc.n_steps_glgm06(w.T, w.delta)
+    n, r = w.n, w.max_order
+    assert N == 2000 and Om.ngens == 1084 and D.V.ngens == 273
+    fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, 0).run()
+    p = fp.ngens()
+    Ro = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, 120, r)
+    for k in list(range(1, 16)) + [40, 77, 120]:
+        c, G = fp.step(k, int(p[k - 1]))
+        assert G.shape == Ro[k - 1].G.shape
+        assert_close(c, Ro[k - 1].c, f"centre {k}")
+        assert_close(G, Ro[k - 1].G, f"generators {k}")
+    assert list(p[:7]) == [1084, 1357, 1630, 1903, 2176, 2449, 2700] and np.all(p[6:] == r * n)
+    acc = np.zeros(n)           # sum_{j < k-1} Phi^j cV
+    Pj = np.eye(n)
+    samples = {2, 3, 500, 1000, 2000}
+    keep = {}
+    for k in range(1, N + 1):
+        if k in samples:
+            keep[k] = Pj @ Om.c + acc if k > 1 else Om.c.copy()      # Pj = Phi^{k-1}
+        acc = acc + Pj @ D.V.c
+        Pj = Pj @ D.Phi
+    for k in sorted(samples):
+        c, G = fp.step(k, int(p[k - 1]))
+        assert_close(c, keep[k], f"closed-form centre {k}")
+        if k >= 7:              # reduced sets end with the n box generators
+            box = G[:, -n:]
+            assert np.count_nonzero(box - np.diag(np.diag(box))) == 0 and np.all(np.diag(box) > 0)
+        assert np.all(np.isfinite(G))
+    c_a, G_a = fp.step(1999)
+    fp.run()
+    c_b, G_b = fp.step(1999)
+    assert np.array_equal(c_a, c_b) and np.array_equal(G_a, G_b)      # deterministic: no float atomics, fixed orders
+    fp.close()
