@@ -131,6 +131,22 @@ REACH_API int32_t reach_glgm06_create(reach_ctx* ctx, int64_t n, const double* P
                             const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV,
                             int64_t ldgv, int64_t N, int64_t max_order, int32_t flags, reach_flowpipe** out);
 REACH_API int32_t reach_glgm06_run(reach_flowpipe* fp); /* whole recurrence on the device; results stay there */
+/* Column-sharded single system over `nranks` GPUs (one process and context per GPU): rank g keeps and maps only the
+ * generators [p0 g/nranks, p0 (g+1)/nranks) of Omega0 and the same slice of V; the order-reduction SELECTION runs replicated
+ * on the all-reduced scores, so every rank takes identical decisions (reduce_order, GLGM06/reach.jl:49,55).  The caller
+ * drives the batches in order: for every batch b in [0, nbatches) and phase in 0..3 call reach_glgm06_shard_phase, then
+ * sum-all-reduce (NCCL over NVLink) the buffers reach_glgm06_shard_buffer reports: after phase 0 `which` = 0 (scores,
+ * float64) and 1 (row-support masks, int32); after phase 1 `which` = 2 (W box partials); after phase 2 `which` = 3 (R box
+ * partials).  Afterwards reach_flowpipe_step returns this rank's columns of R_k (the others are zero): the slabs of the
+ * ranks have disjoint support and their sum is the reach set; centres are replicated. */
+REACH_API int32_t reach_glgm06_create_sharded(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
+                                    const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV,
+                                    int64_t ldgv, int64_t N, int64_t max_order, int32_t flags, int32_t rank, int32_t nranks,
+                                    reach_flowpipe** out);
+REACH_API int32_t reach_glgm06_shard_nbatches(reach_flowpipe* fp, int64_t* nbatches);
+REACH_API int32_t reach_glgm06_shard_phase(reach_flowpipe* fp, int64_t batch, int32_t phase);
+REACH_API int32_t reach_glgm06_shard_buffer(reach_flowpipe* fp, int64_t batch, int32_t which, void** dev_ptr, int64_t* count,
+                                  int32_t* dtype /* 0 = float64, 1 = int32 */);
 /* run + fetch in one call, streamed: every batch of reach sets is copied to the host (layout of reach_flowpipe_fetch;
  * pinned buffers overlap best) while the later batches are still being computed.  This is the shape of
  * `reach_inhomog!(R, ...)` filling its caller-allocated vector (GLGM06/reach.jl:30-36). */

@@ -51,6 +51,11 @@ _SIGNATURES = {
     "reach_bffpsv18_output_map": _BOX_ARGS + [i64, c_int32_p, i64, c_double_p, i64, c_double_p, c_double_p],
     "reach_glgm06_create": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
                             i64, i64, i64, i32, C.POINTER(vp)],
+    "reach_glgm06_create_sharded": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
+                                    i64, i64, i64, i32, i32, i32, C.POINTER(vp)],
+    "reach_glgm06_shard_nbatches": [vp, c_int64_p],
+    "reach_glgm06_shard_phase": [vp, i64, i32],
+    "reach_glgm06_shard_buffer": [vp, i64, i32, C.POINTER(vp), c_int64_p, c_int32_p],
     "reach_glgm06_run": [vp],
     "reach_glgm06_run_fetch": [vp, c_double_p, c_double_p, i64],
     "reach_flowpipe_ngens": [vp, c_int32_p],

@@ -199,6 +199,9 @@ class Context:
     def glgm06(self, Phi, c0, G0, N, max_order=10, cV=None, GV=None, flags=0) -> "Flowpipe":
         return Flowpipe(self, Phi, c0, G0, N, max_order, cV, GV, flags)
 
+    def glgm06_sharded(self, Phi, c0, G0, N, max_order, cV, GV, rank, nranks, flags=0) -> "ShardedFlowpipe":
+        return ShardedFlowpipe(self, Phi, c0, G0, N, max_order, cV, GV, flags, rank, nranks)
+
     def reduce_order(self, c, G, r, flags=0):
         G = fmat(G)
         n, p = G.shape
@@ -352,6 +355,45 @@ class Flowpipe:
             self.close()
         except Exception:
             pass
+
+
+class ShardedFlowpipe(Flowpipe):
+    """Column-sharded `reach_flowpipe` of one rank (reach_glgm06_create_sharded): driven phase by phase, see
+    `sharding.run_sharded`."""
+
+    def __init__(self, ctx: Context, Phi, c0, G0, N, max_order, cV, GV, flags, rank, nranks):
+        self.ctx = ctx
+        Phi = fmat(Phi)
+        n = Phi.shape[0]
+        c0 = fvec(c0)
+        G0 = fmat(G0).reshape(n, -1, order="F")
+        cV = fvec(cV)
+        GV = fmat(GV).reshape(n, -1, order="F")
+        self.n, self.N, self.rank, self.nranks = n, int(N), int(rank), int(nranks)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.reach_glgm06_create_sharded(ctx._h, n, dptr(Phi), n, G0.shape[1], dptr(c0), dptr(G0), n, GV.shape[1],
+                                                       dptr(cV), dptr(GV) if GV.shape[1] else None, n, int(N), int(max_order),
+                                                       int(flags), int(rank), int(nranks), C.byref(self._h)))
+
+    def nbatches(self) -> int:
+        v = C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_glgm06_shard_nbatches(self._h, C.byref(v)))
+        return int(v.value)
+
+    def phase(self, batch: int, phase: int):
+        self.ctx._check(self.ctx.lib.reach_glgm06_shard_phase(self._h, int(batch), int(phase)))
+
+    def buffer(self, batch: int, which: int):
+        """(device pointer, element count, numpy dtype string) of the buffer to sum-all-reduce, or None when empty."""
+        ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int32()
+        self.ctx._check(self.ctx.lib.reach_glgm06_shard_buffer(self._h, int(batch), int(which), C.byref(ptr), C.byref(cnt),
+                                                               C.byref(dt)))
+        if cnt.value == 0:
+            return None
+        return ptr.value, int(cnt.value), ("<f8" if dt.value == 0 else "<i4")
+
+    def run(self):
+        raise ReachError(1, "a column-sharded flowpipe is driven by sharding.run_sharded (collectives between the phases)")
 
 
 class Ensemble:

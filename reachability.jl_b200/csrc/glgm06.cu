@@ -55,6 +55,9 @@ struct GP {
     int n, ld, p0, pV, q, strip, nwords, nwords4, record;
     int64_t nkeep, rn;          // n*(r-1), r*n
     int capW, capR, capListR, capListW, capDisc, smax;
+    // column sharding (multi-GPU): this rank owns the generators [a0, a1) of G0 and [c0r, c1r) of GV;
+    // its archive stores only those (la + lc columns) plus the two centre columns, qloc per slot.  Single GPU: all.
+    int a0, a1, c0r, c1r, la, lc, qloc, rank, nranks;
     // ---- archive
     const double* Yall;         // slot j = Phi^j X, q columns each
     double* Wd;                 // [N+2][ld] box vectors of the W reductions (values of the box-generator references)
@@ -102,14 +105,32 @@ __device__ __forceinline__ void mask_pos(int i, int& word, int& bit) {
     bit = (i & 63) >> 1;
 }
 
+// Archive column of a (global) reference, or nullptr when another rank owns it.
+__device__ __forceinline__ const double* col_ptr(const GP& g, int ref) {
+    const int j = ref / g.q, c = ref - j * g.q;
+    int l;
+    if (c < g.p0) {
+        if (c < g.a0 || c >= g.a1) return nullptr;
+        l = c - g.a0;
+    } else if (c < g.p0 + g.pV) {
+        const int cc = c - g.p0;
+        if (cc < g.c0r || cc >= g.c1r) return nullptr;
+        l = g.la + cc - g.c0r;
+    } else {
+        l = g.la + g.lc + (c - g.p0 - g.pV);      // centres are replicated
+    }
+    return g.Yall + ((int64_t)j * g.qloc + l) * g.ld;
+}
+
 // h = |g|_1 - |g|_inf of every mapped generator of the batch (+inf = all-zero column dropped in strip mode) and, for the
 // input segment, the row-support mask.  One warp per column; a pure function of the column's bits.
 __global__ void __launch_bounds__(256) score_stack_kernel(GP g, int cnt) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int per = g.p0 + g.pV;
+    const int per = g.la + g.lc;                 // the generators this rank owns
     if (warp >= cnt * per) return;
-    const int t = warp / per, c = warp % per;
-    const double2* c2 = reinterpret_cast<const double2*>(g.Y + (int64_t)(t * g.q + c) * g.ld);
+    const int t = warp / per, lcol = warp % per;
+    const int c = lcol < g.la ? g.a0 + lcol : g.p0 + g.c0r + (lcol - g.la);     // global column
+    const double2* c2 = reinterpret_cast<const double2*>(g.Y + (int64_t)(t * g.qloc + lcol) * g.ld);
     const int n2 = g.ld / 2;
     double s = 0.0, m = 0.0;
     uint32_t* mask = (g.strip && c >= g.p0) ? g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + (c - g.p0)) * g.nwords4 : nullptr;
@@ -589,7 +610,8 @@ template <int IT>
 __device__ __forceinline__ void acc_add(const GP& g, Acc<IT>& a, int ref, int lane, bool with_tags) {
     const int n2 = g.ld / 2;
     if (ref >= 0) {
-        const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)ref * g.ld);
+        const double2* c2 = reinterpret_cast<const double2*>(col_ptr(g, ref));
+        if (c2 == nullptr) return;                // another rank sums this generator (partials are all-reduced)
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
             const int idx = lane + 32 * i;
@@ -599,7 +621,7 @@ __device__ __forceinline__ void acc_add(const GP& g, Acc<IT>& a, int ref, int la
                 a.v[i].y += fabs(v.y);
             }
         }
-    } else if (with_tags) {
+    } else if (with_tags && g.rank == 0) {        // box generators are replicated: rank 0 accounts for them
         int kt, it;
         tag_decode(ref, g.n, kt, it);
         const double val = fabs(g.Wd[(int64_t)kt * g.ld + it]);
@@ -667,7 +689,7 @@ __device__ __forceinline__ WseqIn wseq_load(const GP& g, int k0, int t, int i) {
     WseqIn w;
     const PlanW pl = g.planW[k0 + t];
     w.mode = pl.mode; w.m = pl.m;
-    const double* yc0 = g.Y + (int64_t)(t * g.q + g.p0 + g.pV) * g.ld;
+    const double* yc0 = g.Y + (int64_t)(t * g.qloc + g.la + g.lc) * g.ld;
     w.yc0 = yc0[i];
     w.ycV = yc0[g.ld + i];
     w.base = 0.0; w.tc = 0;
@@ -834,11 +856,15 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
             const int r = __shfl_sync(0xffffffffu, ref, j), d = __shfl_sync(0xffffffffu, dest, j);
             double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)d * g.ld);
             if (r >= 0) {
-                const double2* c2 = reinterpret_cast<const double2*>(g.Yall + (int64_t)r * g.ld);
+                const double2* c2 = reinterpret_cast<const double2*>(col_ptr(g, r));
+                if (c2) {
 #pragma unroll 4
-                for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
+                    for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
+                } else {        // owned by another rank: the slabs of the ranks have disjoint support
+                    for (int i = lane; i < n2; i += 32) d2[i] = make_double2(0.0, 0.0);
+                }
             } else {
-                const double val = __shfl_sync(0xffffffffu, tval, j);
+                const double val = g.rank == 0 ? __shfl_sync(0xffffffffu, tval, j) : 0.0;
                 const int it = __shfl_sync(0xffffffffu, trow, j);
                 for (int i = lane; i < n2; i += 32) {
                     double2 v = make_double2(0.0, 0.0);
@@ -895,7 +921,7 @@ __global__ void __launch_bounds__(256) expand_diag_kernel(GP g, int k0, int k1) 
     double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
     for (int c = blockIdx.x * 8 + warp; c < nd; c += gridDim.x * 8) {
         const int row = g.Rrow[(int64_t)(k - 1) * g.n + c];
-        const double d = g.Rd[(int64_t)(k - 1) * g.ld + row];
+        const double d = g.rank == 0 ? g.Rd[(int64_t)(k - 1) * g.ld + row] : 0.0;
         double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)(nk + c) * g.ld);
         for (int i = lane; i < n2; i += 32) {
             double2 v = make_double2(0.0, 0.0);
@@ -926,8 +952,8 @@ __global__ void __launch_bounds__(256) materialize_w_kernel(GP g, double* __rest
     const int ref = g.wEnt[warp].ref;
     double* dst = out + (int64_t)g.wEnt[warp].pos * ldo;
     if (ref >= 0) {
-        const double* src = g.Yall + (int64_t)ref * g.ld;
-        for (int i = lane; i < g.n; i += 32) dst[i] = src[i];
+        const double* src = col_ptr(g, ref);
+        for (int i = lane; i < g.n; i += 32) dst[i] = src ? src[i] : 0.0;
     } else {
         int kt, it;
         tag_decode(ref, g.n, kt, it);
@@ -1041,6 +1067,14 @@ struct Flowpipe {
     int flags = 0;
     bool homog = false, record = false;
     int64_t nc = 1;                 // homogeneous: number of centre columns (ensemble: one per member)
+    int64_t qloc = 0;               // archive columns per slot on this rank (= q unless column-sharded)
+    int rank = 0, nranks = 1;
+    // column-sharded phase machine (reach_glgm06_shard_*): batches are processed in order, collectives in between
+    struct Batch { int64_t have, cnt, w; bool square_after; };
+    std::vector<Batch> sched;
+    int64_t next_batch = 0;
+    const DMat* pw = nullptr;
+    int sp = 0;
     GP g{};
     DMat Phi, PowA, PowB;
     double* Hflow = nullptr;        // archive of Phi^j X: the flowpipe itself in the homogeneous case
@@ -1090,8 +1124,9 @@ static int64_t pick_block(int64_t n, int64_t q, int64_t N) {
 
 Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
                           const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV, int64_t ldgv,
-                          int64_t N, int64_t max_order, int32_t flags, int64_t nc = 1) {
+                          int64_t N, int64_t max_order, int32_t flags, int64_t nc = 1, int rank = 0, int nranks = 1) {
     REACH_REQUIRE(n > 0 && Phi && ldphi >= n, "glgm06: bad Phi");
+    REACH_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "glgm06: bad rank / nranks");
     REACH_REQUIRE(p0 >= 0 && c0 && (p0 == 0 || (G0 && ldg0 >= n)), "glgm06: bad Omega0");
     REACH_REQUIRE(N >= 1, "glgm06: N must be >= 1");
     const bool homog = (cV == nullptr);
@@ -1133,12 +1168,24 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         };
         GP& g = F->g;
         g.n = (int)n; g.ld = (int)ld; g.p0 = (int)p0; g.pV = (int)pV; g.q = (int)q;
+        F->rank = rank; F->nranks = nranks;
+        g.rank = rank; g.nranks = nranks;
+        if (homog) {
+            REACH_REQUIRE(nranks == 1, "glgm06: homogeneous flowpipes are sharded by members, not by columns");
+            g.a0 = 0; g.a1 = (int)p0; g.c0r = 0; g.c1r = 0; g.la = (int)p0; g.lc = 0; g.qloc = (int)q;
+        } else {
+            g.a0 = (int)(p0 * rank / nranks); g.a1 = (int)(p0 * (rank + 1) / nranks);
+            g.c0r = (int)(pV * rank / nranks); g.c1r = (int)(pV * (rank + 1) / nranks);
+            g.la = g.a1 - g.a0; g.lc = g.c1r - g.c0r; g.qloc = g.la + g.lc + 2;
+        }
+        F->qloc = g.qloc;
+        const int64_t qloc = F->qloc;
         g.strip = (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) ? 0 : 1;
         g.record = F->record ? 1 : 0;
         g.nwords = 2 * (int)ceil_div(ld / 2, 32);
         g.nwords4 = (int)round_up(g.nwords, 4);
         // ---- archive: slot j = Phi^j X  (homogeneous: X = [G0 | c0], the flowpipe itself; ensemble: [G_0 .. | c_0 ..])
-        const size_t cols = (size_t)N * q + 256;
+        const size_t cols = (size_t)N * qloc + 256;
         size_t free_b = 0, total_b = 0;
         REACH_CUDA(cudaMemGetInfo(&free_b, &total_b));
         free_b += ctx->pooled_bytes;       // cached blocks are released on demand (ctx_malloc)
@@ -1165,13 +1212,13 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         }
         F->Hflow = (double*)own(dalloc<double>(ctx, cols * ld));
         g.Yall = F->Hflow;
-        up2d(F->Hflow, G0, ldg0, p0);
+        if (g.la > 0) up2d(F->Hflow, G0 + (int64_t)g.a0 * ldg0, ldg0, g.la);
         if (homog) {
             up2d(F->Hflow + p0 * ld, c0, n, F->nc);
         } else {
-            up2d(F->Hflow + p0 * ld, GV, ldgv, pV);
-            up2d(F->Hflow + (p0 + pV) * ld, c0, n, 1);
-            up2d(F->Hflow + (p0 + pV + 1) * ld, cV, n, 1);
+            if (g.lc > 0) up2d(F->Hflow + (int64_t)g.la * ld, GV + (int64_t)g.c0r * ldgv, ldgv, g.lc);
+            up2d(F->Hflow + (int64_t)(g.la + g.lc) * ld, c0, n, 1);
+            up2d(F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, cV, n, 1);
             const size_t sq = (size_t)s * q + 8;
             g.maskAll = (uint32_t*)own(dalloc<uint32_t>(ctx, g.strip ? (size_t)(N + 1) * std::max<int64_t>(pV, 1) * g.nwords4 + 4 : 4));
             g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
@@ -1218,8 +1265,10 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side2, cudaStreamNonBlocking));
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side3, cudaStreamNonBlocking));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
-            if (p0 > 0) REACH_CUDA(cudaMemcpy2DAsync(g.Rg, ld * 8, G0, ldg0 * 8, n * 8, p0, cudaMemcpyHostToDevice, st));
-            if (ld > n) REACH_CUDA(cudaMemset2DAsync(g.Rg + n, ld * 8, 0, (ld - n) * 8, p0 > 0 ? p0 : 1, st));
+            if (p0 > 0) REACH_CUDA(cudaMemsetAsync(g.Rg, 0, (size_t)p0 * ld * 8, st));
+            if (g.la > 0)
+                REACH_CUDA(cudaMemcpy2DAsync(g.Rg + (int64_t)g.a0 * ld, ld * 8, G0 + (int64_t)g.a0 * ldg0, ldg0 * 8, n * 8, g.la,
+                                             cudaMemcpyHostToDevice, st));
             REACH_CUDA(cudaMemcpyAsync(g.Rc, c0, n * 8, cudaMemcpyHostToDevice, st));
             const int2 m1 = make_int2((int)p0, 0);
             REACH_CUDA(cudaMemcpyAsync(g.meta, &m1, sizeof(int2), cudaMemcpyHostToDevice, st));
@@ -1241,15 +1290,29 @@ static cudaEvent_t next_event(Flowpipe* F, size_t& used) {
     return F->evs[used++];
 }
 
-// scores + stable order of the mapped segments of `cnt` steps whose first slot is `slot0`
-static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStream_t st) {
+// scores (+ row-support masks) of the mapped generators this rank owns, for `cnt` steps whose first slot is `slot0`
+static void score_only(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStream_t st) {
     Ctx* ctx = F->ctx;
-    g.Y = F->Hflow + slot0 * F->q * F->ld;
+    g.Y = F->Hflow + slot0 * F->qloc * F->ld;
     g.col0 = slot0 * F->q;
-    const int per = g.p0 + g.pV;
+    if (F->nranks > 1) {        // entries of the other ranks must be 0 for the sum all-reduce
+        REACH_CUDA(cudaMemsetAsync(g.hS, 0, sizeof(double) * (size_t)cnt * F->q, st));
+        if (g.strip && F->pV > 0)
+            REACH_CUDA(cudaMemsetAsync(g.maskAll + (size_t)slot0 * F->pV * g.nwords4, 0, sizeof(uint32_t) * (size_t)cnt * F->pV * g.nwords4, st));
+    }
+    const int per = g.la + g.lc;
     if (per > 0) {
         score_stack_kernel<<<(unsigned)ceil_div((int64_t)cnt * per, 8), 256, 0, st>>>(g, cnt);
-        const int maxlen = std::max(g.p0, g.pV);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+}
+
+// stable order of the (global) segments from the (all-reduced) scores
+static void sort_only(Flowpipe* F, GP& g, int cnt, cudaStream_t st) {
+    Ctx* ctx = F->ctx;
+    const int maxlen = std::max(g.p0, g.pV);
+    if (maxlen > 0) {
         if (maxlen <= BITONIC_MAX) {
             int P = 2;
             while (P < maxlen) P <<= 1;
@@ -1259,10 +1322,15 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
             sort_segments_kernel<<<grid, 256, 0, st>>>(g);
         }
         REACH_CUDA(cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches++;
     } else {
         REACH_CUDA(cudaMemsetAsync(g.cntS, 0, sizeof(int) * 2 * cnt, st));
     }
+}
+
+static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStream_t st) {
+    score_only(F, g, slot0, cnt, st);
+    sort_only(F, g, cnt, st);
 }
 
 static void bind_set(GP& g, const GP& h) {
@@ -1325,7 +1393,8 @@ static void set_kernel_attributes(Flowpipe* F) {
 void flowpipe_run(Flowpipe* F) {
     Ctx* ctx = F->ctx;
     cudaStream_t st = ctx->stream;
-    const int64_t n = F->n, ld = F->ld, q = F->q, N = F->N, s = F->s;
+    const int64_t n = F->n, ld = F->ld, q = F->qloc, N = F->N, s = F->s;
+    REACH_REQUIRE(F->nranks == 1, "glgm06: a column-sharded flowpipe is driven through reach_glgm06_shard_phase");
     GP g = F->g;
     size_t ev_used = 0;
     F->gemm_launches = 0; F->gemm_flops = 0;
@@ -1382,7 +1451,7 @@ void flowpipe_run(Flowpipe* F) {
         set_kernel_attributes(F);
         bind_set(g, F->gset[0]);
         // W_1 = V, cW_1 = cV (GLGM06/reach.jl:41-42)
-        REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (g.p0 + g.pV + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
         score_and_sort(F, g, 0, 1, st);
         init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 256)), 256, 0, st>>>(g);
         REACH_CUDA(cudaGetLastError());
@@ -1503,6 +1572,130 @@ void flowpipe_run(Flowpipe* F) {
     F->ran = true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Column-sharded flowpipe (multi-GPU): every rank maps, scores and gathers only the generators it
+// owns; the selection chain is key logic and runs replicated.  One batch = four phases with a sum all-reduce of a small
+// buffer between them (issued by the caller with torch.distributed / NCCL over NVLink):
+//   phase 0  GEMM of the batch on the own columns + their scores          -> all-reduce scores (and row-support masks)
+//   phase 1  segment order, selection chain, own part of the W box sums   -> all-reduce W box partials
+//   phase 2  W box recurrence + centres, R ranks, own part of the R gather -> all-reduce R box partials
+//   phase 3  R box vectors, counts, dense box generators (rank 0)
+// Batch 0 is the initialisation (W_1 = V); batches must be processed in order.
+// ---------------------------------------------------------------------------------------------------------------
+static void shard_build_schedule(Flowpipe* F) {
+    F->sched.clear();
+    int64_t have = 1, w = 1;
+    while (have < F->N) {
+        const int64_t cnt = std::min(w, F->N - have);
+        Flowpipe::Batch b{have, cnt, w, false};
+        have += cnt;
+        if (have < F->N && w < F->s) { b.square_after = true; w *= 2; }
+        F->sched.push_back(b);
+    }
+}
+
+int64_t flowpipe_shard_nbatches(Flowpipe* F) {
+    if (F->sched.empty() && F->N > 1) shard_build_schedule(F);
+    return 1 + (int64_t)F->sched.size();
+}
+
+void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
+    REACH_REQUIRE(!F->homog, "glgm06: homogeneous flowpipes are not column-sharded");
+    const int64_t nb = flowpipe_shard_nbatches(F);
+    REACH_REQUIRE(b >= 0 && b < nb && phase >= 0 && phase < 4, "glgm06: bad batch / phase");
+    Ctx* ctx = F->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = F->n, ld = F->ld, N = F->N;
+    set_kernel_attributes(F);
+    GP g = F->g;
+    bind_set(g, F->gset[0]);
+    if (b == 0) {
+        g.Y = F->Hflow;
+        g.col0 = 0;
+        if (phase == 0) {
+            F->next_batch = 0; F->pw = &F->Phi; F->sp = 0; F->ran = false;
+            REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
+            score_only(F, g, 0, 1, st);
+        } else if (phase == 1) {
+            sort_only(F, g, 1, st);
+            init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 256)), 256, 0, st>>>(g);
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches++;
+        } else if (phase == 3) {
+            F->next_batch = 1;
+            if (N == 1) { F->meta_host.assign(1, make_int2((int)F->p0, 0)); F->ran = true; }
+        }
+        REACH_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    REACH_REQUIRE(b == F->next_batch, "glgm06: sharded batches must be processed in order");
+    const Flowpipe::Batch& B = F->sched[b - 1];
+    const int k0 = (int)B.have + 1, cnt = (int)B.cnt;
+    g.Y = F->Hflow + B.have * F->qloc * ld;
+    g.col0 = B.have * F->q;
+    const size_t red_smem = (size_t)8 * ld * sizeof(double);
+    const int it = ld <= 256 ? 4 : (ld <= 512 ? 8 : 16);
+    if (phase == 0) {
+        gemm_left(ctx, n, B.cnt * F->qloc, n, F->pw->p, F->pw->ld, F->Hflow + (B.have - B.w) * F->qloc * ld, ld,
+                  F->Hflow + B.have * F->qloc * ld, ld);
+        score_only(F, g, B.have, cnt, st);
+    } else if (phase == 1) {
+        sort_only(F, g, cnt, st);
+        launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
+        if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+        else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+        else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    } else if (phase == 2) {
+        wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
+        rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
+        const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
+        if (it == 4) apply_r_kernel<4><<<ag, 256, red_smem, st>>>(g, k0);
+        else if (it == 8) apply_r_kernel<8><<<ag, 256, red_smem, st>>>(g, k0);
+        else apply_r_kernel<16><<<ag, 256, red_smem, st>>>(g, k0);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 3;
+    } else {
+        finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
+        expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+        if (B.square_after) {
+            DMat* spare[2] = {&F->PowA, &F->PowB};
+            gemm_left(ctx, n, n, n, F->pw->p, F->pw->ld, F->pw->p, F->pw->ld, spare[F->sp]->p, spare[F->sp]->ld);
+            F->pw = spare[F->sp];
+            F->sp ^= 1;
+        }
+        F->next_batch = b + 1;
+        if (b == nb - 1) {
+            F->meta_host.resize(N);
+            REACH_CUDA(cudaMemcpyAsync(F->meta_host.data(), g.meta, sizeof(int2) * N, cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+            F->ran = true;
+        }
+    }
+    REACH_CUDA(cudaStreamSynchronize(st));
+}
+
+// Device buffer the caller all-reduces (sum) after phase `which`-dependent: 0 scores, 1 row-support masks, 2 W box
+// partials, 3 R box partials.  dtype 0 = float64, 1 = int32.
+void flowpipe_shard_buffer(Flowpipe* F, int64_t b, int which, void** ptr, int64_t* count, int* dtype) {
+    const int64_t nb = flowpipe_shard_nbatches(F);
+    REACH_REQUIRE(b >= 0 && b < nb && which >= 0 && which < 4, "glgm06: bad batch / buffer");
+    const GP& h = F->gset[0];
+    const int64_t cnt = b == 0 ? 1 : F->sched[b - 1].cnt, slot0 = b == 0 ? 0 : F->sched[b - 1].have;
+    *dtype = 0;
+    if (which == 0) { *ptr = h.hS; *count = cnt * F->q; }
+    else if (which == 1) {
+        *dtype = 1;
+        *ptr = F->g.maskAll + (size_t)slot0 * std::max<int64_t>(F->pV, 1) * F->g.nwords4;
+        *count = F->g.strip ? cnt * F->pV * F->g.nwords4 : 0;
+    }
+    else if (which == 2) { *ptr = h.partW; *count = b == 0 ? 0 : cnt * NBW * F->ld; }
+    else { *ptr = h.partR; *count = b == 0 ? 0 : cnt * NBR * F->ld; }
+}
+
 // reduce_order(Z, r) of LazySets (Girard 2005; call site GLGM06/post.jl:20) as ONE step of the same
 // machinery: W list = [ (empty W) | the columns of G ], so scores, stable order, boxing and zero-generator removal
 // are exactly the kernels the time loop uses.
@@ -1618,6 +1811,48 @@ int32_t reach_glgm06_create(reach_ctx* h, int64_t n, const double* Phi, int64_t 
     *out = new reach_flowpipe{f, ctx};
     return REACH_OK;
     FP_END(ctx)
+}
+
+int32_t reach_glgm06_create_sharded(reach_ctx* h, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,
+                                    const double* G0, int64_t ldg0, int64_t pV, const double* cV, const double* GV,
+                                    int64_t ldgv, int64_t N, int64_t max_order, int32_t flags, int32_t rank, int32_t nranks,
+                                    reach_flowpipe** out) {
+    if (!h || !out) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    *out = nullptr;
+    FP_BEGIN(ctx)
+    REACH_REQUIRE(cV != nullptr, "reach_glgm06_create_sharded: the homogeneous recurrence is sharded by members (reach_ensemble_*)");
+    Flowpipe* f = flowpipe_create(ctx, n, Phi, ldphi, p0, c0, G0, ldg0, pV, cV, GV, ldgv, N, max_order, flags, 1, rank, nranks);
+    *out = new reach_flowpipe{f, ctx};
+    return REACH_OK;
+    FP_END(ctx)
+}
+
+int32_t reach_glgm06_shard_nbatches(reach_flowpipe* fp, int64_t* nbatches) {
+    if (!fp || !nbatches) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    *nbatches = flowpipe_shard_nbatches(fp->f);
+    return REACH_OK;
+    FP_END(fp->ctx)
+}
+
+int32_t reach_glgm06_shard_phase(reach_flowpipe* fp, int64_t batch, int32_t phase) {
+    if (!fp) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    flowpipe_shard_phase(fp->f, batch, phase);
+    return REACH_OK;
+    FP_END(fp->ctx)
+}
+
+int32_t reach_glgm06_shard_buffer(reach_flowpipe* fp, int64_t batch, int32_t which, void** dev_ptr, int64_t* count,
+                                  int32_t* dtype) {
+    if (!fp || !dev_ptr || !count || !dtype) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    int dt = 0;
+    flowpipe_shard_buffer(fp->f, batch, which, dev_ptr, count, &dt);
+    *dtype = dt;
+    return REACH_OK;
+    FP_END(fp->ctx)
 }
 
 int32_t reach_glgm06_run(reach_flowpipe* fp) {

@@ -4,8 +4,11 @@
   rows of interest are sharded in contiguous groups of whole partition blocks (a 2-D block is never split), balanced
   by row count.  There is NO collective inside the time loop; the boxes are all-gathered once at the end.
 * GLGM06 ensembles (config C5): independent members, sharded by contiguous batch ranges, no collective at all.
-* A single GLGM06 system is not sharded (two latency-bound collectives per reduction at n = 270 would only slow it
-  down): `bench.py --gpus N` runs replicas for that workload.
+* A single GLGM06 system shards its generator COLUMNS (`run_sharded`): every rank maps, scores and gathers only the
+  generators it owns; the Girard selection is key logic and runs replicated on the all-reduced scores, so all ranks take
+  identical decisions.  Because the steps are processed in batches, the exchange is three small sum all-reduces per
+  BATCH of steps (scores + row-support masks, W box partials, R box partials), not per reduction.  At n = 270 this does
+  not beat one GPU (SURVEY.md section 8e says so); it exists for large n * p.
 
 The compute callable is injected so that the host logic is testable on CPU with the `gloo` backend
 (tests/test_sharding_cpu.py); the product path passes `Context.bffpsv18_boxes` / `Context.ensemble`.
@@ -79,3 +82,52 @@ def bffpsv18_sharded(compute: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarra
     Cs = [p[0].cpu().numpy().reshape((c, N), order="F") for p, c in zip(parts, counts) if c]
     Rs = [p[1].cpu().numpy().reshape((c, N), order="F") for p, c in zip(parts, counts) if c]
     return np.vstack(Cs), np.vstack(Rs)
+
+
+# which buffers are sum-all-reduced after which phase of a batch (include/reach.h, reach_glgm06_shard_phase)
+SHARD_COLLECTIVES = {0: (0, 1), 1: (2,), 2: (3,), 3: ()}
+
+
+def _device_tensor(ptr, count, typestr, device):
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+def run_sharded(engine, dist, as_tensor=None, sync=None):
+    """Drive a column-sharded GLGM06 flowpipe: `engine` exposes nbatches(), phase(batch, phase) and
+    buffer(batch, which) (backend.ShardedFlowpipe, or a mock on CPU); `as_tensor` turns what buffer() returns into a
+    torch tensor aliasing the engine's memory (default: a zero-copy view of the device buffer)."""
+    import torch
+    if as_tensor is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def as_tensor(buf):
+            return _device_tensor(buf[0], buf[1], buf[2], dev)
+    if sync is None:
+        def sync():
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+    for b in range(engine.nbatches()):
+        for phase in range(4):
+            engine.phase(b, phase)
+            for which in SHARD_COLLECTIVES[phase]:
+                buf = engine.buffer(b, which)
+                if buf is not None:
+                    dist.all_reduce(as_tensor(buf), op=dist.ReduceOp.SUM)
+            sync()
+    return engine
+
+
+def gather_sharded_step(engine, k, p, dist, device):
+    """Reach set k of a column-sharded flowpipe on every rank: the ranks' slabs have disjoint support, so the sum is the
+    generator matrix; centres are replicated."""
+    import torch
+    c, G = engine.step(k, p)
+    t = torch.from_numpy(np.ascontiguousarray(G)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return c, t.cpu().numpy()

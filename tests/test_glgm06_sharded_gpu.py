@@ -1,0 +1,94 @@
+"""GPU (one device): the column-sharded GLGM06 phase machine (reach_glgm06_create_sharded / _shard_phase / _shard_buffer).
+Two (or three) ranks are emulated on ONE GPU as separate sharded flowpipes whose all-reduce buffers are summed in
+place between the phases -- exactly what `sharding.run_sharded` does with NCCL on a multi-GPU box
+(tools/glgm06_sharded_check.py is the real multi-process run; profiles/r01/glgm06_sharded_2gpu_check.log).
+Results must equal the oracle: every rank takes the same selections from the all-reduced scores, the ranks' slabs have
+disjoint support and sum to the reach set."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reach_oracle as orc
+from reachability_jl_b200 import sharding
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+class _EmulatedRanks:
+    """Drives several sharded engines of one process like sharding.run_sharded drives one per process."""
+
+    def __init__(self, engines):
+        self.engines = engines
+        self.dev = torch.device("cuda", 0)
+
+    def run(self):
+        for b in range(self.engines[0].nbatches()):
+            for phase in range(4):
+                for e in self.engines:
+                    e.phase(b, phase)
+                for which in sharding.SHARD_COLLECTIVES[phase]:
+                    bufs = [e.buffer(b, which) for e in self.engines]
+                    if bufs[0] is None:
+                        assert all(x is None for x in bufs)
+                        continue
+                    ts = [sharding._device_tensor(p, c, d, self.dev) for (p, c, d) in bufs]
+                    total = torch.stack(ts).sum(dim=0)
+                    for t in ts:
+                        t.copy_(total)
+                torch.cuda.synchronize()
+
+    def step(self, k):
+        p = self.engines[0].ngens()
+        parts = [e.step(k, int(p[k - 1])) for e in self.engines]
+        for (c, _) in parts[1:]:
+            assert np.array_equal(c, parts[0][0])            # centres are replicated
+        G = sum(g for (_, g) in parts)
+        support = sum((np.abs(g).sum(axis=0) > 0).astype(int) for (_, g) in parts)
+        assert support.max() <= 1                            # disjoint column support
+        return parts[0][0], G
+
+
+def _problem(seed, n, m):
+    g = np.random.default_rng(seed)
+    A = g.standard_normal((n, n)) / np.sqrt(n) - 1.2 * np.eye(n)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m))
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3)
+    return A, X0, B, U
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("n,m,N,r,rzg", [(6, 1, 40, 2, True), (13, 3, 33, 4, True), (20, 20, 20, 5, False), (33, 2, 70, 6, True),
+                                         (9, 2, 60, 1, True)])
+def test_column_sharded_flowpipe_equals_oracle(ctx, nranks, n, m, N, r, rzg):
+    A, X0, B, U = _problem(700 + n, n, m)
+    D = orc.discretize_zonotope(A, X0, 0.01, B, U, rzg=rzg)
+    Om = orc.reduce_order(D.Omega0, r, rzg)
+    R = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, r, rzg)
+    engines = [ctx.glgm06_sharded(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, rk, nranks, flags=0 if rzg else 1) for rk in range(nranks)]
+    emu = _EmulatedRanks(engines)
+    emu.run()
+    emu.run()                                # the phase machine restarts cleanly (idempotent)
+    p = engines[0].ngens()
+    for e in engines[1:]:
+        assert np.array_equal(e.ngens(), p)  # replicated selection: identical generator counts on every rank
+    for k in range(1, N + 1):
+        assert p[k - 1] == R[k - 1].ngens
+        c, G = emu.step(k)
+        assert_close(c, R[k - 1].c, f"centre {k}")
+        assert_close(G, R[k - 1].G, f"generators {k}")
+    for e in engines:
+        e.close()
+
+
+def test_sharded_engine_refuses_plain_run(ctx):
+    import reachability_jl_b200 as rb
+    A, X0, B, U = _problem(1, 5, 1)
+    D = orc.discretize_zonotope(A, X0, 0.01, B, U)
+    e = ctx.glgm06_sharded(D.Phi, D.Omega0.c, D.Omega0.G, 5, 3, D.V.c, D.V.G, 0, 2)
+    with pytest.raises(rb.ReachError):
+        e.run()
+    with pytest.raises(rb.ReachError):
+        e.phase(2, 0)                        # batches must be processed in order
+    e.close()

@@ -96,3 +96,58 @@ def test_gloo_row_sharded_flowpipe_equals_unsharded(world):
         p.join(120)
         assert p.exitcode == 0
     assert q.get() is True
+
+
+class _MockEngine:
+    """Stands in for backend.ShardedFlowpipe: records the call sequence; every buffer starts as rank + 1."""
+
+    def __init__(self, rank, nb=3):
+        self.rank, self.nb, self.log, self.bufs = rank, nb, [], {}
+
+    def nbatches(self):
+        return self.nb
+
+    def phase(self, b, ph):
+        self.log.append(("phase", b, ph))
+        for which in sharding.SHARD_COLLECTIVES[ph]:
+            if not (b == 0 and which in (2, 3)):             # the initialisation batch has no box partials
+                self.bufs[(b, which)] = torch.full((4,), float(self.rank + 1), dtype=torch.float64)
+
+    def buffer(self, b, which):
+        self.log.append(("buffer", b, which))
+        return self.bufs.get((b, which))
+
+
+def _sharded_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _MockEngine(rank)
+        sharding.run_sharded(eng, dist, as_tensor=lambda t: t, sync=lambda: None)
+        want = float(sum(range(1, world + 1)))
+        ok = all(bool(torch.all(t == want)) for t in eng.bufs.values())
+        # order: phases 0..3 of batch 0, then batch 1, ...; the collectives of a phase directly after it
+        phases = [e for e in eng.log if e[0] == "phase"]
+        ok = ok and phases == [("phase", b, ph) for b in range(3) for ph in range(4)]
+        i0 = eng.log.index(("phase", 1, 0))
+        ok = ok and eng.log[i0 + 1:i0 + 3] == [("buffer", 1, 0), ("buffer", 1, 1)] and eng.log[i0 + 3] == ("phase", 1, 1)
+        if rank == 0:
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_run_sharded_places_the_collectives():
+    """`run_sharded`: four phases per batch in order, sum all-reduce of the reported buffers right after their phase."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
