@@ -326,6 +326,11 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         launches = ctx.launch_count() - launches0 + args.steps
         p = fp.ngens()
         pmax = int(p.max())
+        # diagnostics pass outside the timed region: the same flowpipe with every kernel alone on one stream
+        fp.set_serial(True)
+        fp.run()
+        alone = fp.timing()
+        fp.set_serial(False)
         fp.close()
         # ---- end to end: host buffers in, all N zonotopes back in host memory (what reach_inhomog! fills) ----
         e2e_obj = None
@@ -387,6 +392,12 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                      "traffic": 148.8e6,
                      "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA)",
                      "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
+                     "alone": {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",
+                               "gemm_tflops": alone["gemm_flops"] / (alone["gemm_ms"] * 1e-3) / 1e12,
+                               "gemm_frac": alone["gemm_flops"] / (alone["gemm_ms"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                               "gemm_ms": alone["gemm_ms"], "numerics_ms": alone["numerics_ms"], "chain_ms": alone["chain_ms"],
+                               "numerics_gbs": glgm06_algorithmic_bytes_per_step(n, p0, pV, r) * flow_steps / (alone["numerics_ms"] * 1e-3) / 1e9,
+                               "run_ms": alone["run_ms"]},
                      "algorithmic_flops_per_flowpipe_step": 2.0 * n * n * (p0 + pV + 2),
                      "peak_source": "FP64 DMMA register-resident loop measured on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl)",
                      "second_kernel": {"kernel": "batched numerics of the two Girard reductions (wbox_partial, wseq, rank_r, apply_r, "

@@ -172,6 +172,9 @@ REACH_API int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, doub
 /* CUDA-event time of the last run spent in the selection chain (side stream) and in the batched numerics (second side
  * stream); the two overlap each other and the GEMMs. */
 REACH_API int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, double* numerics_ms);
+/* Diagnostics: serial != 0 makes the next runs issue everything on one stream (no overlap), so that the per-kernel
+ * CUDA-event times of reach_flowpipe_timing / _phase_ms are those of each kernel running alone. */
+REACH_API int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial);
 REACH_API void reach_flowpipe_free(reach_flowpipe* fp);
 /* reduce_order(Z, r) of LazySets (Girard), call site GLGM06/post.jl:20.  Gout must hold n x max(p, r*n) doubles;
  * p_out receives the new generator count; ind (p, may be NULL) the sortperm. */

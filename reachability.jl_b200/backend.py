@@ -293,6 +293,11 @@ class Flowpipe:
         self.ctx._check(self.ctx.lib.reach_glgm06_run_fetch(self._h, dptr(centers), dptr(G), G.shape[1]))
         return self
 
+    def set_serial(self, serial: bool):
+        """Diagnostics: run without stream overlap so that per-kernel times are those of each kernel alone."""
+        self.ctx._check(self.ctx.lib.reach_flowpipe_set_serial(self._h, int(bool(serial))))
+        return self
+
     def ngens(self) -> np.ndarray:
         p = np.zeros(self.N, dtype=np.int32)
         self.ctx._check(self.ctx.lib.reach_flowpipe_ngens(self._h, iptr(p)))

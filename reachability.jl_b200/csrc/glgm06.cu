@@ -1097,6 +1097,7 @@ struct Flowpipe {
     cudaStream_t cpy = nullptr;
     double* pack = nullptr;
     std::vector<double> phi_host;   // n <= 32: Phi as a kernel parameter of homog_small_kernel
+    bool serial = false;            // diagnostics: no stream overlap, every kernel timed alone (reach_flowpipe_set_serial)
     bool detail = false;            // REACH_TIMING_DETAIL
     std::vector<cudaEvent_t> detail_ev;
 };
@@ -1475,6 +1476,7 @@ void flowpipe_run(Flowpipe* F) {
     int64_t have = 1, w = 1;
     std::vector<cudaEvent_t> ev_num;     // numerics of batch b done
     int bi = 0;
+    cudaStream_t sChain = F->serial ? st : F->side, sNum = F->serial ? st : F->side2, sSort = F->serial ? st : F->side3;
     while (have < N) {
         const int64_t cnt = std::min(w, N - have);
         timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
@@ -1482,24 +1484,24 @@ void flowpipe_run(Flowpipe* F) {
             cudaEvent_t ev_gemm = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
             // scores / segment order: after this batch's GEMM and after the numerics that last used this array set
-            REACH_CUDA(cudaStreamWaitEvent(F->side3, ev_gemm, 0));
-            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(F->side3, ev_num[bi - 2], 0));
+            REACH_CUDA(cudaStreamWaitEvent(sSort, ev_gemm, 0));
+            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - 2], 0));
             bind_set(g, F->gset[bi & 1]);
-            score_and_sort(F, g, have, (int)cnt, F->side3);
+            score_and_sort(F, g, have, (int)cnt, sSort);
             cudaEvent_t ev_sort = next_event(F, ev_used);
-            REACH_CUDA(cudaEventRecord(ev_sort, F->side3));
-            REACH_CUDA(cudaStreamWaitEvent(F->side, ev_sort, 0));
+            REACH_CUDA(cudaEventRecord(ev_sort, sSort));
+            REACH_CUDA(cudaStreamWaitEvent(sChain, ev_sort, 0));
             cudaEvent_t c0 = next_event(F, ev_used), c1 = next_event(F, ev_used);
             chain_ev.push_back({ev_used - 2, ev_used - 1});
-            REACH_CUDA(cudaEventRecord(c0, F->side));
-            process_chain(F, g, (int)have + 1, (int)cnt, F->side);
-            REACH_CUDA(cudaEventRecord(c1, F->side));
-            REACH_CUDA(cudaStreamWaitEvent(F->side2, c1, 0));
+            REACH_CUDA(cudaEventRecord(c0, sChain));
+            process_chain(F, g, (int)have + 1, (int)cnt, sChain);
+            REACH_CUDA(cudaEventRecord(c1, sChain));
+            REACH_CUDA(cudaStreamWaitEvent(sNum, c1, 0));
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             red_ev.push_back({ev_used - 2, ev_used - 1});
-            REACH_CUDA(cudaEventRecord(e0, F->side2));
-            process_numerics(F, g, (int)have + 1, (int)cnt, F->side2);
-            REACH_CUDA(cudaEventRecord(e1, F->side2));
+            REACH_CUDA(cudaEventRecord(e0, sNum));
+            process_numerics(F, g, (int)have + 1, (int)cnt, sNum);
+            REACH_CUDA(cudaEventRecord(e1, sNum));
             ev_num.push_back(e1);
             if (F->sink_G) {        // stream this batch's reach sets to the host while the later batches are computed
                 REACH_CUDA(cudaStreamWaitEvent(F->cpy, e1, 0));
@@ -2112,6 +2114,12 @@ void reach_ensemble_free(reach_ensemble* en) {
     cudaStreamSynchronize(en->ctx->stream);
     flowpipe_free(en->f);
     delete en;
+}
+
+int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial) {
+    if (!fp) return REACH_EINVAL;
+    fp->f->serial = serial != 0;
+    return REACH_OK;
 }
 
 int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, double* numerics_ms) {
