@@ -37,6 +37,8 @@ extern "C" {
 
 #define REACH_FORWARD 0  /* discretize(...; algorithm="forward")  discretize.jl:654-655 */
 #define REACH_BACKWARD 1 /* discretize(...; algorithm="backward") discretize.jl:656-657 */
+#define REACH_FIRSTORDER 2 /* discretize_firstorder, p = Inf      discretize.jl:403-473 */
+#define REACH_NOBLOATING 3 /* discretize_nobloating               discretize.jl:527-552 */
 
 typedef struct reach_ctx reach_ctx;
 typedef struct reach_boxplan reach_boxplan;   /* BFFPSV18 problem resident on the device */
@@ -68,7 +70,9 @@ REACH_API int32_t reach_phi12(reach_ctx* ctx, int64_t n, const double* A, int64_
  * entering through B (n x m; m = 0: homogeneous; B == NULL with m == n: identity), followed by the box
  * decomposition of the lazy Ω0 that BFFPSV18 performs (BFFPSV18/reach.jl:64-65).
  * Outputs (each may be NULL): Phi n x n; Phi2abs = Φ₂(|A|, δ) n x n; c0, r0 (n) box of Ω0; rE (n) radius of Einit;
- * rpsi (n) radius of Eψ0; MU = δ·B (n x m, ld n). */
+ * rpsi (n) radius of Eψ0; MU = δ·B (n x m, ld n).
+ * algorithm REACH_FIRSTORDER: the first-order model with infinity-norm balls (rE = α, rpsi = β uniform; Phi2abs is not
+ * computed); REACH_NOBLOATING: Ω0 = X0, MU = Φ₁(A, δ)·B, rpsi = 0. */
 REACH_API int32_t reach_discretize_box(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm,
                              const double* c, const double* r, int64_t m, const double* B, int64_t ldb,
                              const double* cU, const double* rU, double* Phi, int64_t ldphi, double* Phi2abs,

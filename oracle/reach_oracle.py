@@ -306,6 +306,8 @@ def discretize_box(A, X0: Box, delta: float, B=None, U: Optional[Box] = None,
     n = A.shape[0]
     if Phi is None:
         Phi = exp_Adelta(A, delta)                            # :649
+    if algorithm in ("firstorder", "nobloating"):
+        return _discretize_box_other(A, X0, delta, B, U, algorithm, Phi)
     Phi2abs, rE, rpsi = _bloating(A, Phi, X0, delta, algorithm, B, U, Phi2abs)
     absPhi = np.abs(Phi)
     cY = Phi @ X0.c
@@ -322,6 +324,43 @@ def discretize_box(A, X0: Box, delta: float, B=None, U: Optional[Box] = None,
     c0 = (hi + lo) / 2
     r0 = (hi - lo) / 2
     return DiscreteBoxProblem(Phi, c0, r0, MU, cU, rU, rpsi, rE, Phi2abs)
+
+
+def _discretize_box_other(A, X0: Box, delta, B, U, algorithm, Phi) -> DiscreteBoxProblem:
+    """The two other approximation models `discretize` dispatches to (discretize.jl:105-115), in the same array form.
+
+    * ``"nobloating"`` (discretize.jl:527-552): ``Ω0 = X0``, ``V = Φ₁(A, δ) U`` -- no bloating terms.
+    * ``"firstorder"`` with ``p = Inf`` (discretize.jl:403-473, Le Guernic & Girard 2010): ``κ = e^{δ‖A‖} − 1 − δ‖A‖``,
+      ``α = κ (‖X0‖ + ‖U‖/‖A‖)``, ``β = κ ‖U‖/‖A‖``, ``Ω0 = CH(X0, ΦX0 ⊕ δU ⊕ □α)``, ``V = δU ⊕ □β`` with infinity-norm
+      balls, i.e. uniform box radii (``norm(X, Inf)`` of a box = max_i |c_i| + r_i; of the lazy ``B*U`` its box bound)."""
+    n = A.shape[0]
+    Bm = None if U is None else (np.eye(n) if B is None else np.asarray(B, dtype=np.float64))
+    if algorithm == "nobloating":
+        if U is None:
+            return DiscreteBoxProblem(Phi, X0.c.copy(), X0.r.copy(), None, None, None, None, np.zeros(n), None)
+        MU = Phi1(A, delta) @ Bm                                 # Φ₁(A, δ) * (B U)
+        return DiscreteBoxProblem(Phi, X0.c.copy(), X0.r.copy(), MU, U.c, U.r, np.zeros(n), np.zeros(n), None)
+    Anorm = np.abs(A).sum(axis=1).max()                       # opnorm(A, Inf)
+    kappa = math.exp(delta * Anorm) - 1.0 - delta * Anorm
+    RX0 = np.max(np.abs(X0.c) + X0.r)
+    cY = Phi @ X0.c
+    rY = np.abs(Phi) @ X0.r
+    MU = cU = rU = rpsi = None
+    if U is None:
+        alpha = kappa * RX0
+    else:
+        RU = np.max(np.abs(Bm @ U.c) + np.abs(Bm) @ U.r)
+        alpha = kappa * (RX0 + RU / Anorm)
+        beta = kappa * RU / Anorm
+        MU, cU, rU = delta * Bm, U.c, U.r
+        rpsi = np.full(n, beta)
+        cY = cY + MU @ cU
+        rY = rY + np.abs(MU) @ rU
+    rE = np.full(n, alpha)
+    rY = rY + rE
+    hi = np.maximum(X0.c + X0.r, cY + rY)
+    lo = np.minimum(X0.c - X0.r, cY - rY)
+    return DiscreteBoxProblem(Phi, (hi + lo) / 2, (hi - lo) / 2, MU, cU, rU, rpsi, rE, None)
 
 
 def discretize_zonotope(A, X0: Box, delta: float, B=None, U: Optional[Box] = None,

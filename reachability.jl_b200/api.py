@@ -469,7 +469,7 @@ def _post_bffpsv18(op, problem, opts, ctx):
     blocks = compute_blocks(vars_, partition)
     dims = compute_dimensions(partition, blocks)
     types = _block_set_types(op, partition)
-    if op["discretization"] not in ("forward", "backward"):
+    if op["discretization"] not in ("forward", "backward", "firstorder", "nobloating"):
         raise ValueError(f"the algorithm {op['discretization']} is unknown")          # discretize.jl:121
     if op["exp_method"] not in ("base", "sm100a"):
         raise ReachError(3, f"exp_method {op['exp_method']!r} is unsupported on the sm_100a path")

@@ -98,7 +98,7 @@ class Context:
         """Returns dict(Phi, c0, r0, rE, rpsi, MU[, Phi2abs])."""
         A = fmat(A)
         n = A.shape[0]
-        alg = {"forward": 0, "backward": 1}.get(algorithm)
+        alg = {"forward": 0, "backward": 1, "firstorder": 2, "nobloating": 3}.get(algorithm)
         if alg is None:
             raise ValueError(f"the algorithm {algorithm} is unknown")
         c, r = fvec(c), fvec(r)

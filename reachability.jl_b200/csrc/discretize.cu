@@ -228,6 +228,105 @@ using namespace reach;
     catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
     catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
 
+// discretize_firstorder (p = Inf, discretize.jl:403-473) and discretize_nobloating (:527-552) for box sets, in the same
+// array form as the interpolation models.
+static int32_t discretize_box_other(Ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm,
+                                    const double* c, const double* r, int64_t m, const double* B, int64_t ldb, const double* cU,
+                                    const double* rU, double* Phi, int64_t ldphi, double* c0, double* r0, double* rE,
+                                    double* rpsi, double* MU) {
+    cudaStream_t st = ctx->stream;
+    DMat dA = dmat_alloc(ctx, n, n), dPhi = dmat_alloc(ctx, n, n), dB, dMU, dP1;
+    const int64_t NV = 13;      // 0 c, 1 r, 2 Φc, 3 |Φ|r, 4 ones -> α, 5 |A|1 -> β, 6 |c|+r, 7 |Bc_U|+|B|r_U, 8 δBc_U, 9 |δB|r_U, 10 c0, 11 r0, 12 zeros
+    double* vec = (double*)ctx_malloc(ctx, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1)));
+    REACH_CUDA(cudaMemsetAsync(vec, 0, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1)), st));
+    auto V = [&](int i) { return vec + (int64_t)i * n; };
+    double* dcU = vec + NV * n;
+    double* drU = dcU + std::max<int64_t>(m, 1);
+    dmat_upload(ctx, dA, A, lda);
+    REACH_CUDA(cudaMemcpyAsync(V(0), c, n * 8, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(cudaMemcpyAsync(V(1), r, n * 8, cudaMemcpyHostToDevice, st));
+    expm_family(ctx, n, dA.p, dA.ld, delta, false, &dPhi, nullptr, nullptr);
+    const unsigned gv = (unsigned)ceil_div(n, 256);
+    std::vector<double> hn(n), hx(n), hu(n);
+    if (m > 0) {
+        REACH_CUDA(cudaMemcpyAsync(dcU, cU, m * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(drU, rU, m * 8, cudaMemcpyHostToDevice, st));
+        dB = dmat_alloc(ctx, n, m);
+        if (B) {
+            dmat_upload(ctx, dB, B, ldb);
+        } else {
+            dim3 g2((unsigned)ceil_div(n, 256), (unsigned)n);
+            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, dA.p, dA.ld, 0.0, nullptr, 0, 1.0, dB.p, dB.ld);
+        }
+        dMU = dmat_alloc(ctx, n, m);
+    }
+    if (algorithm == REACH_NOBLOATING) {
+        REACH_CUDA(cudaMemcpyAsync(V(10), c, n * 8, cudaMemcpyHostToDevice, st));       // Ω0 = X0
+        REACH_CUDA(cudaMemcpyAsync(V(11), r, n * 8, cudaMemcpyHostToDevice, st));
+        if (m > 0) {
+            dP1 = dmat_alloc(ctx, n, n);
+            expm_family(ctx, n, dA.p, dA.ld, delta, false, nullptr, &dP1, nullptr);
+            gemm_left(ctx, n, m, n, dP1.p, dP1.ld, dB.p, dB.ld, dMU.p, dMU.ld);           // Φ₁(A, δ) * B
+        }
+        // rE = rpsi = 0 (vec is zero-filled): V(4) doubles as the zero vector
+    } else {
+        // ‖A‖_inf, ‖X0‖_inf, ‖B U‖_inf: row sums on the device, the three maxima on the host (scalars of the model)
+        REACH_CUDA(cudaMemsetAsync(V(4), 0, n * 8, st));
+        {
+            std::vector<double> ones(n, 1.0);
+            REACH_CUDA(cudaMemcpyAsync(V(4), ones.data(), n * 8, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+        }
+        box_matvec(ctx, n, n, dA.p, dA.ld, nullptr, V(4), nullptr, V(5));                 // |A| 1
+        sih_kernel<<<gv, 256, 0, st>>>((int)n, V(0), V(1), V(6));                         // |c| + r
+        if (m > 0) {
+            box_matvec(ctx, n, m, dB.p, dB.ld, dcU, drU, V(8), V(9));                     // box of B U
+            sih_kernel<<<gv, 256, 0, st>>>((int)n, V(8), V(9), V(7));
+        }
+        REACH_CUDA(cudaMemcpyAsync(hn.data(), V(5), n * 8, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(hx.data(), V(6), n * 8, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(hu.data(), V(7), n * 8, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        const double Anorm = *std::max_element(hn.begin(), hn.end());
+        const double RX0 = *std::max_element(hx.begin(), hx.end());
+        const double RU = m > 0 ? *std::max_element(hu.begin(), hu.end()) : 0.0;
+        const double kappa = std::exp(delta * Anorm) - 1.0 - delta * Anorm;
+        const double alpha = m > 0 ? kappa * (RX0 + RU / Anorm) : kappa * RX0;
+        const double beta = m > 0 ? kappa * RU / Anorm : 0.0;
+        std::vector<double> av(n, alpha), bv(n, beta);
+        REACH_CUDA(cudaMemcpyAsync(V(4), av.data(), n * 8, cudaMemcpyHostToDevice, st));   // rE = α
+        REACH_CUDA(cudaMemcpyAsync(V(5), bv.data(), n * 8, cudaMemcpyHostToDevice, st));   // rpsi = β
+        REACH_CUDA(cudaStreamSynchronize(st));
+        box_matvec(ctx, n, n, dPhi.p, dPhi.ld, V(0), V(1), V(2), V(3));                   // box of ΦX0
+        if (m > 0) {
+            dim3 gm((unsigned)ceil_div(n, 256), (unsigned)m);
+            scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, dB.p, dB.ld, delta, 0, dMU.p, dMU.ld);   // δ B
+            box_matvec(ctx, n, m, dMU.p, dMU.ld, dcU, drU, V(8), V(9));
+        }
+        // Ω0 = CH(X0, ΦX0 ⊕ δU ⊕ □α): the kernel adds rE, and for inputs ur + rpsi; β must not enter Ω0 => pass zeros
+        omega0_box_kernel<<<gv, 256, 0, st>>>((int)n, V(0), V(1), V(2), V(3), V(4), m > 0 ? V(8) : nullptr, V(9), V(12), V(10), V(11));
+    }
+    REACH_CUDA(cudaGetLastError());
+    if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_box: ldphi"); dmat_download(ctx, dPhi, Phi, ldphi); }
+    auto down = [&](double* dst, const double* src) {
+        if (dst) REACH_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, st));
+    };
+    down(c0, V(10)); down(r0, V(11));
+    if (algorithm == REACH_NOBLOATING) {
+        std::vector<double> z(n, 0.0);
+        if (rE) std::memcpy(rE, z.data(), n * 8);
+        if (rpsi && m > 0) std::memcpy(rpsi, z.data(), n * 8);
+    } else {
+        down(rE, V(4));
+        if (m > 0) down(rpsi, V(5));
+    }
+    if (m > 0 && MU) dmat_download(ctx, dMU, MU, n);
+    REACH_CUDA(cudaStreamSynchronize(st));
+    dmat_free(dA); dmat_free(dPhi); dmat_free(dB); dmat_free(dMU); dmat_free(dP1);
+    ctx_free(ctx, vec);
+    return REACH_OK;
+}
+
 extern "C" {
 
 int32_t reach_expm(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, double* Phi, int64_t ldphi) {
@@ -270,8 +369,10 @@ int32_t reach_discretize_box(reach_ctx* h, int64_t n, const double* A, int64_t l
     Ctx* ctx = ctx_of(h);
     D_BEGIN(ctx)
     REACH_REQUIRE(n > 0 && A && lda >= n && c && r, "reach_discretize_box: bad A / X0");
-    if (algorithm != REACH_FORWARD && algorithm != REACH_BACKWARD)
-        throw Error(REACH_EINVAL, "the algorithm is unknown");      // ArgumentError at discretize.jl:659
+    if (algorithm < REACH_FORWARD || algorithm > REACH_NOBLOATING)
+        throw Error(REACH_EINVAL, "the algorithm is unknown");      // ArgumentError at discretize.jl:121,659
+    if (algorithm == REACH_FIRSTORDER || algorithm == REACH_NOBLOATING)
+        return discretize_box_other(ctx, n, A, lda, delta, algorithm, c, r, m, B, ldb, cU, rU, Phi, ldphi, c0, r0, rE, rpsi, MU);
     REACH_REQUIRE(m >= 0 && (m == 0 || (cU && rU)), "reach_discretize_box: inputs need cU, rU");
     REACH_REQUIRE(!B || ldb >= n, "reach_discretize_box: bad ldb");
     REACH_REQUIRE(B || m == 0 || m == n, "reach_discretize_box: B == NULL means identity and needs m == n");

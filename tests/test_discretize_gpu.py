@@ -88,3 +88,30 @@ def test_discretize_box_random_then_flowpipe(ctx, n, m, alg):
 def test_unknown_algorithm_raises(ctx):
     with pytest.raises(ValueError):
         ctx.discretize_box(np.eye(2), 0.1, np.zeros(2), np.ones(2), algorithm="sideways")
+
+
+@pytest.mark.parametrize("n,m", [(3, 0), (4, 2), (33, 5), (20, 20), (130, 1)])
+@pytest.mark.parametrize("alg", ["firstorder", "nobloating"])
+def test_other_discretisation_models_then_flowpipe(ctx, n, m, alg):
+    """`discretize_firstorder` (p = Inf, discretize.jl:403-473) and `discretize_nobloating` (:527-552) in array form."""
+    g = np.random.default_rng(n * 11 + m)
+    A = _A(n + 2, n, 2.0)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m)) if m and m != n else None
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3) if m else None
+    D = orc.discretize_box(A, X0, 0.02, B, U, algorithm=alg)
+    out = ctx.discretize_box(A, 0.02, X0.c, X0.r, B, None if U is None else U.c, None if U is None else U.r, algorithm=alg)
+    assert_close(out["Phi"], D.Phi, "Phi")
+    assert_close(out["c0"], D.c0, "c0")
+    assert_close(out["r0"], D.r0, "r0")
+    assert_close(out["rE"], D.rE, "rE")
+    if m:
+        assert_close(out["rpsi"], D.rpsi, "rpsi")
+        assert_close(out["MU"], D.MU, "MU")
+    N = 30
+    C, R = ctx.bffpsv18_boxes(out["Phi"], out["c0"], out["r0"], N, out["MU"], out["cU"], out["rU"], out["rpsi"])
+    Co, Ro = orc.bffpsv18_reach(D, N)
+    assert_close(C.T, Co, "centres")
+    assert_close(R.T, Ro, "radii")
+    if alg == "nobloating":
+        assert np.array_equal(out["c0"], X0.c) and np.array_equal(out["r0"], X0.r)

@@ -323,3 +323,34 @@ def test_step_counts():
     assert orc.n_steps_glgm06(20.0, 0.01) == 2000          # round, GLGM06/post.jl:12
     assert orc.compute_dimensions([[1, 2], [3, 4], [5]], [1, 3]) == [1, 2, 5]
     assert orc.compute_blocks([1, 3], [[1], [2], [3], [4]]) == [1, 3]
+
+
+def test_firstorder_and_nobloating_models():
+    """`discretize_firstorder` (discretize.jl:403-473) must contain sampled trajectories on every [k delta, (k+1) delta];
+    `discretize_nobloating` (:527-552) is exact at the grid points for constant inputs (Phi1 = int_0^delta e^{As} ds)."""
+    g = np.random.default_rng(17)
+    n, m, delta, N = 5, 2, 0.05, 12
+    A = g.standard_normal((n, n)) - 1.5 * np.eye(n)
+    B = g.standard_normal((n, m))
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.2)
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3)
+    Dn = orc.discretize_box(A, X0, delta, B, U, algorithm="nobloating")
+    Cn, Rn = orc.bffpsv18_reach(Dn, N)
+    Df = orc.discretize_box(A, X0, delta, B, U, algorithm="firstorder")
+    Cf, Rf = orc.bffpsv18_reach(Df, N)
+    import scipy.linalg as sla
+    for trial in range(20):
+        x0 = X0.c + X0.r * g.uniform(-1, 1, n)
+        u = U.c + U.r * g.uniform(-1, 1, m)
+        # exact solution with constant input: x(t) = e^{At} x0 + int_0^t e^{As} ds B u
+        M = np.zeros((n + m, n + m)); M[:n, :n] = A; M[:n, n:] = B
+        for k in range(N):
+            for frac in (0.0, 0.3, 0.77, 1.0):
+                t = (k + frac) * delta
+                E = sla.expm(M * t)
+                x = E[:n, :n] @ x0 + E[:n, n:] @ u
+                assert np.all(np.abs(x - Cf[k]) <= Rf[k] * (1 + 1e-9) + 1e-12), ("firstorder", k, frac)
+            tg = k * delta                     # nobloating: the k-th set is the exact image at t = k delta
+            E = sla.expm(M * tg)
+            x = E[:n, :n] @ x0 + E[:n, n:] @ u
+            assert np.all(np.abs(x - Cn[k]) <= Rn[k] * (1 + 1e-9) + 1e-12), ("nobloating", k)
