@@ -284,7 +284,8 @@ def glgm06_algorithmic_bytes_per_step(n, p0, pV, r):
 
 
 def run_glgm06(args, rank, world, dist, e2e=True):
-    """C2 on one GPU (a single system does not shard: with N > 1 every rank runs a replica)."""
+    """C2 on one GPU; with N > 1 every rank runs a replica (column sharding of one system exists, sharding.run_sharded,
+    but is latency-bound at n = 270: SURVEY.md section 8e)."""
     import torch
     import reachability_jl_b200 as rb
     w, D, Om, N = build_zono_workload()
@@ -376,7 +377,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w.name}: n={n}, m={w.m}, GLGM06 max_order={r}, delta={w.delta}, T={w.T}, N={N} reach sets per "
                                f"bench step, p0={p0}, pV={pV}, {pmax} generators per reach set",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (a single system does not shard)",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (the column-sharded variant, sharding.run_sharded, "
+                                                                     "exists but does not beat one GPU at n=270, DESIGN.md section 5)",
                    "l2": "256 MB L2 flush between timed iterations; the flowpipe written per iteration (11.7 GB) exceeds L2"},
         "e2e": e2e_obj,
         "gpu_launches": int(launches),
