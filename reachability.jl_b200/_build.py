@@ -8,7 +8,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libreach_sm100a.so"
-NVCC_FLAGS = [
+EXTRA = os.environ.get("REACH_NVCC_EXTRA", "").split()     # e.g. -DREACH_CHAIN_PROFILE (diagnostics builds)
+NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]

@@ -14,7 +14,8 @@
 //    generator (step, row) whose value sits in the archive of W box vectors.
 //  * CHAIN.  The only sequential, data-dependent part is the Girard SELECTION of W (which generators are boxed).  It is
 //    pure key logic: every segment carries its stable sorted order, so the sortperm of [W | Phi^k GV] is a merge
-//    (own rank + binary search in the other segment; ties by list index like Julia's stable sortperm).  One persistent
+//    (merge path: a binary search per thread along its diagonal, then a short sequential merge; ties by list index like
+//    Julia's stable sortperm).  One persistent
 //    CTA keeps the sorted (score, reference) list of W in shared memory and advances a whole block of steps without any
 //    grid-wide synchronisation; zero-generator removal needs only row-support bit masks, never the values.
 //  * BATCHED NUMERICS.  Everything numerical is then embarrassingly parallel over the steps of the block: box vectors of
@@ -66,6 +67,7 @@ struct GP {
     const double* Y;            // = Yall + (k0 - 1) q ld
     int64_t col0;               // archive column of Y's first column
     double* hS; int* rkS; int* cposS; double* skS; int* cntS;
+    int* ordS; int* cpsS; int* cntZ;   // by sorted rank: element index, its compact position; # zero scores per segment
     // ---- W chain state (sorted list) + per-step snapshots of the batch
     WEnt* wEnt; int* wCount;
     WEnt* snEnt; int* snCount;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
     const int base = t * g.q + (seg ? g.p0 : 0);
     const int e = blockIdx.x * 256 + threadIdx.x;
     const double he = e < len ? g.hS[base + e] : INFINITY;
-    int less = 0, cpos = 0, nvalid = 0;
+    int less = 0, cpos = 0, nvalid = 0, nzero = 0;
     for (int j0 = 0; j0 < len; j0 += 1024) {
         const int tile = min(1024, len - j0);
         __syncthreads();
@@ -174,15 +176,16 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
             less += (hj < he) || (hj == he && valid && gj < e);
             cpos += valid && gj < e;
             nvalid += valid;
+            nzero += (hj == 0.0);
         }
     }
     if (e < len) {
         const bool valid = he < INFINITY;
         g.rkS[base + e] = valid ? less : -1;
         g.cposS[base + e] = cpos;
-        if (valid) g.skS[base + less] = he;
+        if (valid) { g.skS[base + less] = he; g.ordS[base + less] = e; g.cpsS[base + less] = cpos; }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) g.cntS[t * 2 + seg] = nvalid;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g.cntS[t * 2 + seg] = nvalid; g.cntZ[t * 2 + seg] = nzero; }
 }
 
 // Same result as sort_segments_kernel for segments of up to 4096 generators: bitonic sort of (score, index) pairs in
@@ -247,15 +250,26 @@ __global__ void __launch_bounds__(512) sort_segments_bitonic_kernel(GP g, int P)
         }
     }
     __syncthreads();
+    if (tid == 0) wsum[0] = 0;
+    __syncthreads();
+    int nz = 0;
     for (int pos = tid; pos < P; pos += 512) {
         const int e = ix[pos];
         if (e < len) {
             const double h = kk[pos];
             const bool valid = h < INFINITY;
             g.rkS[base + e] = valid ? pos : -1;
-            if (valid) g.skS[base + pos] = h;
+            if (valid) {
+                g.skS[base + pos] = h;
+                g.ordS[base + pos] = e;
+                g.cpsS[base + pos] = g.cposS[base + e];      // written by this CTA before the sort
+                nz += (h == 0.0);
+            }
         }
     }
+    if (nz) atomicAdd(&wsum[0], nz);
+    __syncthreads();
+    if (tid == 0) g.cntZ[t * 2 + seg] = wsum[0];
 }
 
 __device__ __forceinline__ int lower_bound_ent(const WEnt* a, int len, double key) {   // # entries with key < key
@@ -263,6 +277,14 @@ __device__ __forceinline__ int lower_bound_ent(const WEnt* a, int len, double ke
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (a[mid].key < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int lower_bound(const double* a, int len, double key) {   // # entries < key
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -302,57 +324,71 @@ __device__ __forceinline__ int upper_bound_ent(const WEnt* a, int len, double ke
     return lo;
 }
 
-template <bool SMEM>
+#ifdef REACH_CHAIN_PROFILE
+__device__ unsigned long long g_chain_prof[8];
+#define CHAIN_TICK(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_chain_prof[i], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#else
+#define CHAIN_TICK(i) do { } while (0)
+#endif
+
+template <bool SMEM, bool RECORD>
 __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, int cnt, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     __shared__ unsigned orm[2 * MAX_IT];
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
-    __shared__ int scan_s[CHAIN_THREADS / 32];
     __shared__ int rows_s[CHAIN_ROWS * (CHAIN_THREADS / 32)];
-    __shared__ int s_pC[128];
-    __shared__ int s_nd, s_cz, s_czw;
+    __shared__ int s_pC[128], s_zC[128];
+    __shared__ int s_nd;
     const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
     // working set (shared memory, or global scratch when the W list is too long): the sorted list of W, double-buffered;
-    // the input segment C_t of two consecutive steps; a histogram for the merge; sigma of C_t.
+    // the input segment C_t of two consecutive steps in sorted order (score, element, compact position).
     WEnt* ebuf0 = SMEM ? reinterpret_cast<WEnt*>(chain_sm) : reinterpret_cast<WEnt*>(scr);
     WEnt* ebuf1 = ebuf0 + cap;
-    double* cH0 = reinterpret_cast<double*>(ebuf1 + cap);      // [2][pV]
-    double* cSk0 = cH0 + 2 * pV;                               // [2][pV]
-    int* hist = reinterpret_cast<int*>(cSk0 + 2 * pV);         // [cap + 2]
-    int* sigC = hist + cap + 2;                                // [pV]
-    int* cRk0 = sigC + pV;                                     // [2][pV]
-    int* cCp0 = cRk0 + 2 * pV;                                 // [2][pV]
-    if (tid < cnt && tid < 128) s_pC[tid] = g.cntS[tid * 2 + 1];
+    const int pV1 = pV + 2;                                    // room for the +inf sentinel (kept even)
+    double* cSk0 = reinterpret_cast<double*>(ebuf1 + cap);     // [2][pV1]
+    int* cOrd0 = reinterpret_cast<int*>(cSk0 + 2 * pV1);       // [2][pV1]
+    int* cCp0 = cOrd0 + 2 * pV1;                               // [2][pV1]
+    int* dls = cCp0 + 2 * pV1;                                  // [capDisc] boxed list of the step, staged for a coalesced store
+    if (tid < cnt && tid < 128) { s_pC[tid] = g.cntS[tid * 2 + 1]; s_zC[tid] = g.cntZ[tid * 2 + 1]; }
     int pW = *g.wCount;
     for (int r = tid; r < pW; r += CHAIN_THREADS) ebuf0[r] = g.wEnt[r];
     for (int e = tid; e < pV; e += CHAIN_THREADS) {
         const int b0 = g.p0 + e;
-        cH0[e] = g.hS[b0]; cSk0[e] = g.skS[b0]; cRk0[e] = g.rkS[b0]; cCp0[e] = g.cposS[b0];
+        cSk0[e] = g.skS[b0]; cOrd0[e] = g.ordS[b0]; cCp0[e] = g.cpsS[b0];
     }
     __syncthreads();
+    // number of zero-score generators at the head of the sorted W (carried from step to step)
+    int czw = 0;
+    for (int lo = 0, hi = pW; ; ) {            // every thread runs the same search once per launch
+        if (lo >= hi) { czw = lo; break; }
+        const int mid = (lo + hi) >> 1;
+        if (ebuf0[mid].key <= 0.0) lo = mid + 1; else hi = mid;
+    }
     int cur = 0;
+#ifdef REACH_CHAIN_PROFILE
+    long long tick_ = clock64();
+#endif
     for (int t = 0; t < cnt; ++t) {
         const int k = k0 + t;
         const int cb = t & 1;
         const WEnt* ec = cur ? ebuf1 : ebuf0;
         WEnt* en = cur ? ebuf0 : ebuf1;
-        const double* cH = cH0 + cb * pV;
-        const double* skC = cSk0 + cb * pV;
-        const int* cRk = cRk0 + cb * pV;
-        const int* cCp = cCp0 + cb * pV;
+        const double* skC = cSk0 + cb * pV1;
+        const int* cOrd = cOrd0 + cb * pV1;
+        const int* cCp = cCp0 + cb * pV1;
         const int baseC = t * g.q + g.p0;
         const int refC0 = (int)(g.col0 + baseC);
         const int pC = s_pC[t];
         // prefetch the next step's segment into registers (stored to the other buffer at the end of this step)
-        double pfH[2] = {0.0, 0.0}, pfS[2] = {0.0, 0.0};
-        int pfR[2] = {0, 0}, pfC[2] = {0, 0};
+        double pfS[2] = {0.0, 0.0};
+        int pfO[2] = {0, 0}, pfC[2] = {0, 0};
         if (t + 1 < cnt) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CHAIN_THREADS;
                 if (e < pV) {
                     const int b1 = (t + 1) * g.q + g.p0 + e;
-                    pfH[u] = g.hS[b1]; pfS[u] = g.skS[b1]; pfR[u] = g.rkS[b1]; pfC[u] = g.cposS[b1];
+                    pfS[u] = g.skS[b1]; pfO[u] = g.ordS[b1]; pfC[u] = g.cpsS[b1];
                 }
             }
         }
@@ -360,31 +396,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
         const int mode = (g.rn >= (int64_t)pin) ? MODE_UNCHANGED : MODE_REDUCE;
         const int m = mode == MODE_REDUCE ? (int)(pin - g.nkeep) : 0;
         const int nk = pin - m;
+        const int z = max(0, czw + s_zC[t] - m);       // zero-score generators that survive the cut: they stay in front
         int* dl = g.dlistW + (int64_t)t * g.capDisc;
-        // ---- S0: clear the merge histogram; count the generators with score exactly 0 ----
-        for (int x = tid; x <= pW; x += CHAIN_THREADS) hist[x] = 0;
+        CHAIN_TICK(0);
+        // ---- A: the box generators of W (score 0, hence sigma = rank) that are boxed again ----
         if (tid < 2 * MAX_IT) orm[tid] = 0u;
         for (int i = tid; i < g.n; i += CHAIN_THREADS) tc_s[i] = 0;
-        if (tid == 0) {
-            s_czw = upper_bound_ent(ec, pW, 0.0);
-            s_cz = s_czw + upper_bound(skC, pC, 0.0);
+        if (tid == 0) {             // sentinels for the merge of this step
+            const_cast<WEnt*>(ec)[pW] = WEnt{INFINITY, 0, 0};
+            const_cast<double*>(skC)[pC] = INFINITY;
         }
         __syncthreads();
-        const int czw = s_czw;
-        const int z = max(0, s_cz - m);         // zero-score generators that survive the cut: they stay in front
-        // ---- S1: insertion point of every input generator in the sorted W (the only binary searches of the step);
-        //          the box generators of W (score 0, hence sigma = rank) that are boxed again ----
-        for (int e = tid; e < pV; e += CHAIN_THREADS) {
-            const double h = cH[e];
-            int sg = -1;
-            if (h < INFINITY) {
-                const int ip = upper_bound_ent(ec, pW, h);      // W precedes C in the list: ties go to W
-                atomicAdd(&hist[ip], 1);
-                sg = cRk[e] + ip;
-            }
-            sigC[e] = sg;
-        }
-        for (int r = CHAIN_THREADS - 1 - tid; r < min(czw, m); r += CHAIN_THREADS) {
+        for (int r = tid; r < min(czw, m); r += CHAIN_THREADS) {
             const int ref = ec[r].ref;
             if (ref < 0) {          // its value is an earlier W box vector entry: remember the creation step (wseq_kernel)
                 int kt, it, w, b;
@@ -398,52 +421,34 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
             }
         }
         __syncthreads();
-        // ---- S2: inclusive scan: hist[r] = # input generators sorted before W's rank r  =>  sigma_W(r) = r + hist[r] ----
-        {
-            const int chunk = (pW + CHAIN_THREADS) / CHAIN_THREADS;
-            const int lo = tid * chunk, hi = min(pW + 1, lo + chunk);
-            int sum = 0;
-            for (int x = lo; x < hi; ++x) sum += hist[x];
-            int inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane == 31) scan_s[wid] = inc;
-            __syncthreads();
-            if (wid == 0) {
-                int v = lane < CHAIN_THREADS / 32 ? scan_s[lane] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v += u;
-                }
-                if (lane < CHAIN_THREADS / 32) scan_s[lane] = v;
-            }
-            __syncthreads();
-            int run = inc - sum + (wid ? scan_s[wid - 1] : 0);
-            for (int x = lo; x < hi; ++x) { run += hist[x]; hist[x] = run; }
-        }
-        __syncthreads();
+        CHAIN_TICK(1);
         if (g.strip && mode == MODE_REDUCE) {
             // Row-support union of the boxed generators.  The boxed box generators alone usually cover every row
-            // (steady state): only otherwise are the masks of the dense ones fetched (vector loads, all in flight).
-            int covered = 0;
-            for (int w = 0; w < g.nwords; ++w) covered += __popc(orm[w]);
+            // (steady state); only otherwise are the dense ones located (binary search) and their masks fetched.
+            if (wid == 0) {
+                int c = lane < g.nwords ? __popc(orm[lane]) : 0;
+                if (g.nwords > 32) c += (lane + 32 < g.nwords) ? __popc(orm[lane + 32]) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == 0) s_nd = c;
+            }
+            __syncthreads();
+            const int covered = s_nd;
+            __syncthreads();
             if (covered < g.n) {
                 const int nw4 = g.nwords4 / 4;
-                for (int x = tid; x < pW + pV; x += CHAIN_THREADS) {
+                for (int x = tid; x < pW + pC; x += CHAIN_THREADS) {
                     const uint32_t* mk = nullptr;
                     if (x < pW) {
-                        const int ref = ec[x].ref;
-                        if (x + hist[x] < m && ref >= 0) {
-                            const int j = ref / g.q, c = ref - j * g.q - g.p0;
+                        const WEnt w = ec[x];
+                        if (w.ref >= 0 && x + lower_bound(skC, pC, w.key) < m) {
+                            const int j = w.ref / g.q, c = w.ref - j * g.q - g.p0;
                             mk = g.maskAll + ((int64_t)j * pV + c) * g.nwords4;
                         }
                     } else {
-                        const int e = x - pW, sg = sigC[e];
-                        if (sg >= 0 && sg < m) mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)pV + e) * g.nwords4;
+                        const int jc = x - pW;
+                        if (jc + upper_bound_ent(ec, pW, skC[jc]) < m)
+                            mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)pV + cOrd[jc]) * g.nwords4;
                     }
                     if (mk) {
                         uint4 v[2 * MAX_IT / 4];
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
             }
         }
         for (int i = tid; i < g.n; i += CHAIN_THREADS) g.tcnt[(int64_t)t * g.n + i] = tc_s[i];
-        // ---- rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode):
+        CHAIN_TICK(2);
+        // ---- B: rows of the new box generators (all rows, or the non-zero rows of the box vector in strip mode):
         //      thread tid owns rows tid, tid + T, ...; iprime = number of flagged rows below, nd = their total ----
         int flag[CHAIN_ROWS], iprime[CHAIN_ROWS], nd = 0;
 #pragma unroll
@@ -508,36 +514,46 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
             for (int j = 0; j < CHAIN_ROWS; ++j)
                 iprime[j] = rows_s[j * (CHAIN_THREADS / 32) + wid] + __popc(bal[j] & ((1u << lane) - 1u));
         }
-        // ---- S3, one pass: snapshot of W_{k-1} (for the R reduction of this step), boxed list, the next W ----
+        CHAIN_TICK(3);
+        // ---- C: MERGE PATH.  The stable sortperm of [W | C_t] is the merge of two sorted lists (ties: W first, it
+        //      precedes C in the list).  Thread tid produces the sigma range [tid L, (tid+1) L): a binary search along its
+        //      diagonal finds how many entries of W / C precede it, then L sequential merge steps emit, per entry: the
+        //      snapshot of W_{k-1} (for the R reduction), the boxed list, and the next W. ----
         WEnt* sn = g.snEnt + (int64_t)t * cap;
-        int* recO = g.record ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
-        double* recH = g.record ? g.recHW + (int64_t)k * g.capListW : nullptr;
-        for (int r = tid; r < pW; r += CHAIN_THREADS) {
-            WEnt w = ec[r];
-            sn[r] = w;
-            const int sigma = r + hist[r];
-            if (recO) { recO[sigma] = w.pos; recH[w.pos] = w.key; }
-            if (mode == MODE_REDUCE) {
-                if (sigma < m) {
-                    dl[sigma] = w.ref;
-                } else {
-                    const int ps = sigma - m;
-                    w.pos = ps;
-                    en[ps < z ? ps : ps + nd] = w;
-                }
-            } else {
-                en[sigma] = w;
+        int* recO = RECORD ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
+        double* recH = RECORD ? g.recHW + (int64_t)k * g.capListW : nullptr;
+#pragma unroll 4
+        for (int r = tid; r < pW; r += CHAIN_THREADS) sn[r] = ec[r];       // coalesced; the merge below touches only smem
+        {
+            const int L = ((pin + CHAIN_THREADS - 1) / CHAIN_THREADS) | 1;     // odd: the 16-byte stores of a quarter-warp hit distinct banks
+            const int d0 = min(pin, tid * L), d1 = min(pin, d0 + L);
+            // i = # entries of W among the first d0 merged: largest i with (i == 0 || W[i-1] <= C[d0-i])  (W wins ties)
+            int lo = max(0, d0 - pC), hi = min(d0, pW);
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;               // candidate i = mid: needs W[mid-1] <= C[d0-mid]
+                const int jc = d0 - mid;
+                const bool ok = jc >= pC || ec[mid - 1].key <= skC[jc];
+                if (ok) lo = mid; else hi = mid - 1;
             }
-        }
-        for (int e = tid; e < pV; e += CHAIN_THREADS) {
-            const int sigma = sigC[e];
-            if (sigma >= 0) {
+            int i = lo, j = d0 - lo;
+            CHAIN_TICK(6);
+            // sentinels (+inf) close both lists, so the loop body needs no bounds checks
+            const WEnt* wp = ec + i;
+            WEnt wi = *wp;
+            double cj = skC[j];
+            for (int sigma = d0; sigma < d1; ++sigma) {
                 WEnt w;
-                w.key = cH[e]; w.ref = refC0 + e; w.pos = pW + cCp[e];
-                if (recO) { recO[sigma] = w.pos; recH[w.pos] = w.key; }
+                if (wi.key <= cj) {          // W precedes C in the list: ties go to W
+                    w = wi;
+                    wi = *++wp;
+                } else {
+                    w.key = cj; w.ref = refC0 + cOrd[j]; w.pos = pW + cCp[j];
+                    cj = skC[++j];
+                }
+                if (RECORD) { recO[sigma] = w.pos; recH[w.pos] = w.key; }
                 if (mode == MODE_REDUCE) {
                     if (sigma < m) {
-                        dl[sigma] = w.ref;
+                        dls[sigma] = w.ref;
                     } else {
                         const int ps = sigma - m;
                         w.pos = ps;
@@ -547,6 +563,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
                     en[sigma] = w;
                 }
             }
+            CHAIN_TICK(7);
+            __syncthreads();
+            for (int x = tid; x < m; x += CHAIN_THREADS) dl[x] = dls[x];
         }
 #pragma unroll
         for (int j = 0; j < CHAIN_ROWS; ++j)
@@ -561,24 +580,26 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
             pl.mode = mode; pl.pin = pin; pl.m = m; pl.pW = pW; pl.pC = pC; pl.nk = nk; pl.nd = nd; pl.z = z;
             g.planW[k] = pl;
         }
+        CHAIN_TICK(4);
+        czw = mode == MODE_REDUCE ? z + nd : czw + s_zC[t];
         pW = mode == MODE_REDUCE ? nk + nd : pin;
         cur ^= 1;
         if (t + 1 < cnt) {
-            double* nH = cH0 + (cb ^ 1) * pV;
-            double* nS = cSk0 + (cb ^ 1) * pV;
-            int* nR = cRk0 + (cb ^ 1) * pV;
-            int* nC = cCp0 + (cb ^ 1) * pV;
+            double* nS = cSk0 + (cb ^ 1) * pV1;
+            int* nO = cOrd0 + (cb ^ 1) * pV1;
+            int* nC = cCp0 + (cb ^ 1) * pV1;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CHAIN_THREADS;
-                if (e < pV) { nH[e] = pfH[u]; nS[e] = pfS[u]; nR[e] = pfR[u]; nC[e] = pfC[u]; }
+                if (e < pV) { nS[e] = pfS[u]; nO[e] = pfO[u]; nC[e] = pfC[u]; }
             }
             for (int e = tid + 2 * CHAIN_THREADS; e < pV; e += CHAIN_THREADS) {
                 const int b1 = (t + 1) * g.q + g.p0 + e;
-                nH[e] = g.hS[b1]; nS[e] = g.skS[b1]; nR[e] = g.rkS[b1]; nC[e] = g.cposS[b1];
+                nS[e] = g.skS[b1]; nO[e] = g.ordS[b1]; nC[e] = g.cpsS[b1];
             }
         }
         __syncthreads();
+        CHAIN_TICK(5);
     }
     const WEnt* ef = cur ? ebuf1 : ebuf0;
     for (int r = tid; r < pW; r += CHAIN_THREADS) g.wEnt[r] = ef[r];
@@ -586,10 +607,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
 }
 
 static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st) {
-    if (use_smem)
-        chain_kernel<true><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
-    else
-        chain_kernel<false><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
+    if (use_smem) {
+        if (g.record) chain_kernel<true, true><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
+        else chain_kernel<true, false><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
+    } else {
+        if (g.record) chain_kernel<false, true><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
+        else chain_kernel<false, false><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -1241,7 +1265,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.meta = (int2*)own(dalloc<int2>(ctx, N + 1));
             // chain working set: keys 2 cap doubles, refs/pos 4 cap ints, sigma (cap + pV) ints
             // chain working set: two copies of the sorted list (16 B per generator), histogram cap + 2 ints, 52 bytes per input generator
-            F->chain_smem = (size_t)g.capW * 36 + (size_t)pV * 52 + 64;
+            F->chain_smem = (size_t)g.capW * 32 + (size_t)(pV + 2) * 32 + (size_t)g.capDisc * 4 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
             if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
             for (int b = 0; b < 2; ++b) {      // batch-local arrays, one set per batch parity
@@ -1251,6 +1275,9 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
                 h.rkS = (int*)own(dalloc<int>(ctx, sq));
                 h.cposS = (int*)own(dalloc<int>(ctx, sq));
                 h.cntS = (int*)own(dalloc<int>(ctx, 2 * s + 8));
+                h.ordS = (int*)own(dalloc<int>(ctx, sq));
+                h.cpsS = (int*)own(dalloc<int>(ctx, sq));
+                h.cntZ = (int*)own(dalloc<int>(ctx, 2 * s + 8));
                 h.snEnt = (WEnt*)own(dalloc<WEnt>(ctx, (size_t)s * g.capW));
                 h.snCount = (int*)own(dalloc<int>(ctx, s));
                 h.dlistW = (int*)own(dalloc<int>(ctx, (size_t)s * g.capDisc));
@@ -1336,6 +1363,7 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
 
 static void bind_set(GP& g, const GP& h) {
     g.hS = h.hS; g.skS = h.skS; g.rkS = h.rkS; g.cposS = h.cposS; g.cntS = h.cntS;
+    g.ordS = h.ordS; g.cpsS = h.cpsS; g.cntZ = h.cntZ;
     g.snEnt = h.snEnt; g.snCount = h.snCount; g.dlistW = h.dlistW; g.tcnt = h.tcnt; g.tsrc = h.tsrc;
     g.orderR = h.orderR; g.partW = h.partW; g.partR = h.partR;
 }
@@ -1383,7 +1411,8 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
 static void set_kernel_attributes(Flowpipe* F) {
     static bool done = false;
     if (done) return;
-    REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(sort_segments_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BITONIC_MAX * 12));
     REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
@@ -1565,6 +1594,16 @@ void flowpipe_run(Flowpipe* F) {
         for (cudaEvent_t e : F->detail_ev) cudaEventDestroy(e);
         F->detail_ev.clear();
     }
+#ifdef REACH_CHAIN_PROFILE
+    {
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_chain_prof, sizeof(h));
+        const char* nm[8] = {"prefetch+setup", "A tags", "strip union", "B rows scan", "C diag+plan", "stage next", "C search", "C merge loop"};
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "[chain prof] %-16s %10.1f cycles/step\n", nm[i], (double)h[i] / (double)(F->N - 1));
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_chain_prof, z, sizeof(z));
+    }
+#endif
     F->chain_ms = 0;
     for (auto& pr : chain_ev) {
         float t = 0;
