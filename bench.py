@@ -131,10 +131,25 @@ def box_algorithmic_flops_per_step(n, R, m):
     return 2.0 * R * n * n + 4.0 * R * n + 2.0 * R * n * m + 4.0 * R * m + 2.0 * R * n
 
 
+class _Disc:
+    """Attribute view of the dict `Context.discretize_box` returns (same field names as the oracle's result)."""
+
+    def __init__(self, d):
+        self.__dict__.update(d)
+
+
 def run_bffpsv18(args, rank, world, dist):
     import torch
     import reachability_jl_b200 as rb
-    w, D, N = build_box_workload(args.workload)
+    big = args.workload == "C4"
+    if big:
+        # n = 10913: the host discretisation (a dense 10913^3 expm + Phi2 series in numpy) would take many minutes, so the
+        # inputs of the loop are prepared by the library's own device discretisation (outside every timed region)
+        from reachability_jl_b200 import workloads as wl
+        w, D, N = wl.mna5(), None, None
+        N = int(w.extra["N"])
+    else:
+        w, D, N = build_box_workload(args.workload)
     if args.flow_steps:
         N = args.flow_steps
     n, m = w.n, w.m
@@ -146,8 +161,16 @@ def run_bffpsv18(args, rank, world, dist):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")    # > 126 MB L2
     with torch.cuda.stream(stream):
         ctx = rb.Context(dev, stream=stream.cuda_stream)
+        disc_s = None
+        if big:
+            t0 = time.perf_counter()
+            D = _Disc(ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU))
+            disc_s = time.perf_counter() - t0
         # ---- device-resident arm: inputs uploaded once, K complete flowpipes timed ------------------------
         plan = ctx.boxplan(D.Phi, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+        # C4: a full flowpipe is minutes of DMMA work, so the warm-up passes run a truncated flowpipe of the same problem
+        warm_N = min(N, 48) if big else N
+        warm_plan = ctx.boxplan(D.Phi, D.c0, D.r0, warm_N, D.MU, D.cU, D.rU, D.rpsi, rows) if warm_N != N else plan
         gathered = mine = None
         if world > 1:
             sizes = [len(shard_rows(n, w.partition, r, world)) for r in range(world)]
@@ -165,7 +188,13 @@ def run_bffpsv18(args, rank, world, dist):
                 dist.all_gather(gathered, mine)   # "gather only at the end" (NCCL over NVLink)
 
         for _ in range(args.warmup):
-            one_flowpipe()
+            if warm_plan is plan:
+                one_flowpipe()
+            else:
+                flush.zero_()
+                warm_plan.run()
+        if world > 1 and warm_plan is not plan:      # NCCL warm-up of the end-of-run gather
+            dist.all_gather(gathered, mine)
         sampler = ClockSampler(dev)
         launches0 = ctx.launch_count()
         _barrier(dist, world)
@@ -195,8 +224,8 @@ def run_bffpsv18(args, rank, world, dist):
         vecs = {k: pinned((len(v),)) for k, v in dict(c0=D.c0, r0=D.r0, cU=D.cU, rU=D.rU, rpsi=D.rpsi).items()}
         for k, v in dict(c0=D.c0, r0=D.r0, cU=D.cU, rU=D.rU, rpsi=D.rpsi).items():
             vecs[k][:] = v
-        e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
-        for _ in range(1 if e2e_steps else 0):
+        e2e_steps = 0 if args.no_e2e else (1 if big else max(1, min(args.steps, 3)))
+        for _ in range(1 if (e2e_steps and not big) else 0):
             ctx.bffpsv18_boxes_into(hPhi, vecs["c0"], vecs["r0"], N, hMU, vecs["cU"], vecs["rU"], vecs["rpsi"], rows, hc, hr)
         _barrier(dist, world)
         torch.cuda.synchronize()
@@ -209,7 +238,7 @@ def run_bffpsv18(args, rank, world, dist):
         d2h = 16 * R * N
         # solve()-shaped call: device discretisation (A, X0, B, U from the host) + the flowpipe, host results out
         solve_s = None
-        if e2e_steps:
+        if e2e_steps and not big:
             hA = pinned((n, n)); hA[:] = w.A
 
             def one_solve():
@@ -222,8 +251,12 @@ def run_bffpsv18(args, rank, world, dist):
             one_solve()
             torch.cuda.synchronize()
             solve_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
+        if warm_plan is not plan:
+            warm_plan.close()
         plan.close()
         ctx.close()
+    if big and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        args._c4_cpu = cpu_baseline_c4(w, D, N)
     if rank != 0:
         return None
     flow_steps = N - 1
@@ -237,12 +270,16 @@ def run_bffpsv18(args, rank, world, dist):
         "config": {"workload": f"{w.name}: n={n}, m={m}, BFFPSV18 {len(w.partition)} blocks of dim "
                                f"{len(w.partition[0])}, delta={w.delta}, T={w.T}, N={N} reach sets per bench step",
                    "rows_per_gpu": R, "parallelism": f"row-block sharding x{world}, Phi replicated" if world > 1 else "single GPU",
-                   "l2": "256 MB L2 flush between timed iterations; power stacks 2 x 132 MB exceed L2"},
+                   "l2": "256 MB L2 flush between timed iterations; " + ("Phi (953 MB) and the power stacks exceed L2" if big else
+                                                                         "power stacks 2 x 132 MB exceed L2"),
+                   **({"warmup_note": f"warm-up passes run the first {warm_N} reach sets of the same problem (a full flowpipe is "
+                                      f"{2.0 * R * n * n * (N - 1) / 1e12:.0f} TFLOP on this rank)",
+                       "device_discretize_s": disc_s} if big else {})},
         "e2e": {"value": e2e_steps * flow_steps / e2e_s if e2e_steps else None, "unit": "flowpipe steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "reach_bffpsv18_boxes (host buffers, pinned)",
                 "with_discretize": {"value": flow_steps / solve_s if solve_s else None, "unit": "flowpipe steps/s",
                                     "api": "reach_discretize_box + reach_bffpsv18_boxes: N / t_solve of SURVEY 8(d), expm and "
-                                           "Phi2(|A|) on the device included"}},
+                                           "Phi2(|A|) on the device included"} if not big else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
@@ -356,11 +393,33 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                 one_e2e()
             torch.cuda.synchronize()
             e2e_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
+            # solve() + project(sol, plot_vars): the flowpipe stays in HBM, every reach set is projected on the device
+            # (reach_flowpipe_project) and only the 2 x N boxes cross PCIe
+            P2 = np.zeros((2, n)); P2[0, 0] = 1.0; P2[1, n // 2] = 1.0
+
+            def one_proj():
+                f2 = ctx.glgm06(hPhi, Om.c, hG0, N, r, D.V.c, hGV, 0)
+                f2.run()
+                out = f2.project(P2)
+                f2.close()
+                return out
+
+            one_proj()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                one_proj()
+            torch.cuda.synchronize()
+            proj_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
             e2e_obj = {"value": world * e2e_steps * (N - 1) / e2e_s, "unit": "flowpipe steps/s",
                        "h2d_bytes_per_step": 8 * (n * n + n * (p0 + pV) + 2 * n),
                        "d2h_bytes_per_step": int(8 * n * (int(p.sum()) + N)), "steps": e2e_steps,
                        "api": "reach_glgm06_create + reach_glgm06_run_fetch (pinned host buffers; every zonotope of the "
-                              "flowpipe copied back, batch by batch while later batches compute, as reach_inhomog! materialises them)"}
+                              "flowpipe copied back, batch by batch while later batches compute, as reach_inhomog! materialises them)",
+                       "projected": {"value": world * e2e_steps * (N - 1) / proj_s, "unit": "flowpipe steps/s",
+                                     "d2h_bytes_per_step": 2 * 2 * 8 * N,
+                                     "api": "reach_glgm06_create + reach_glgm06_run + reach_flowpipe_project (solve + project(sol, vars): "
+                                            "2-D boxes of every reach set computed on the device, only they are copied back)"}}
         ctx.close()
     if rank != 0:
         return None
@@ -557,7 +616,17 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def cpu_baseline_c4(w, D, N, n_cpu=4):
+    """C4: one reach set is a 2 n^3 = 2.6 TFLOP dgemm on the host, so the sample is the first few reach sets."""
+    t = cpu_sample_bffpsv18(D, n_cpu)
+    return {"value": (n_cpu - 1) / t, "unit": "flowpipe steps/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"first {n_cpu} of {N} reach sets of {w.name} (loop only, Phi from the device discretisation), numpy+BLAS "
+                      "oracle port of reach_blocks!", "host_cpus": os.cpu_count()}
+
+
 def cpu_baseline_for(args, target_s=12.0):
+    if args.workload == "C4":
+        return getattr(args, "_c4_cpu", None)
     w, D, N = build_box_workload(args.workload)
     t_probe = cpu_sample_bffpsv18(D, 6)                 # 5 steps
     per = t_probe / 5
@@ -602,6 +671,9 @@ def run_reference(args, rank, world):
         return None
     if args.workload == "C2":
         return run_reference_glgm06(args, rank, world)
+    if args.workload in ("C4", "C5"):
+        return {"impl": "reference", "unavailable": f"{args.workload}: the CPU arm of this workload is the cpu_baseline object of the "
+                "default arm (C4's inputs come from the device discretisation; a host expm of n=10913 alone takes minutes)"}
     w, D, N = build_box_workload(args.workload)
     per = cpu_sample_bffpsv18(D, 6) / 5
     n_cpu = int(max(6, min(N, 4.0 / max(per, 1e-9))))       # ~4 s per bench step
@@ -631,7 +703,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the second headline workload (C2 GLGM06) summary")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -165,6 +165,15 @@ REACH_API int32_t reach_flowpipe_step(reach_flowpipe* fp, int64_t k, double* c, 
 REACH_API int32_t reach_flowpipe_fetch(reach_flowpipe* fp, double* centers, double* G, int64_t pmax);
 /* Box hull of reach set k: lo/hi (n). */
 REACH_API int32_t reach_flowpipe_box(reach_flowpipe* fp, int64_t k, double* lo, double* hi);
+/* project(Rsets, options) for a zonotope flowpipe (project_reach.jl:18-99; `project(rs, M)` of ReachSet.jl): every reach
+ * set is mapped through the q x n projection matrix M (1 <= q <= 4, column-major, ld ldm) ON THE DEVICE, so that only the
+ * projected sets cross PCIe (C2: 86 MB instead of 11.7 GB).  centers, radii (q x N): the Hyperrectangle overapproximation
+ * of M * R_k, `set_type_proj = Hyperrectangle` (default_options.jl:69): centre M c_k, radius sum_j |M g_j|.
+ * Gp (may be NULL): the projected zonotopes themselves, N slabs of q x pmax (ld q), slab k-1 = M * G_k in its first p_k
+ * columns (what `ε_proj < Inf` / HPolygon consumers need).  For a column-sharded flowpipe the radii (and Gp columns) are this
+ * rank's partial results. */
+REACH_API int32_t reach_flowpipe_project(reach_flowpipe* fp, int64_t q, const double* M, int64_t ldm, double* centers,
+                                 double* radii, double* Gp, int64_t pmax);
 /* Order-reduction record of step k >= 2 (which = 0: reduce_order of R_k, GLGM06/reach.jl:49; which = 1: of W, :55):
  * p_in columns went in, m were boxed; ind[0..p_in) = sortperm(h) 0-based; h[0..p_in) the scores. Outputs may be NULL.
  * m == 0 and p_in == 0 mean "no reduction happened" (r*n >= p).  Needs REACH_GLGM06_RECORD_SELECTIONS.

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "reach_flowpipe_step": [vp, i64, c_double_p, c_double_p, i64],
     "reach_flowpipe_fetch": [vp, c_double_p, c_double_p, i64],
     "reach_flowpipe_box": [vp, i64, c_double_p, c_double_p],
+    "reach_flowpipe_project": [vp, i64, c_double_p, i64, c_double_p, c_double_p, c_double_p, i64],
     "reach_flowpipe_selection": [vp, i64, i32, c_int32_p, c_int32_p, c_int32_p, c_double_p],
     "reach_flowpipe_timing": [vp, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p],
     "reach_flowpipe_phase_ms": [vp, c_double_p, c_double_p],

@@ -591,17 +591,65 @@ def _post_glgm06(op, problem, opts, ctx):
     def make(i):
         ck, Gk = fp.step(i + 1, int(p[i]))
         return ReachSet(Zonotope(ck, Gk), float(t0[i]), float(t1[i]))       # post.jl:27
-    return ReachSolution([Flowpipe(_LazyReachSets(N, make))], opts, dict(flowpipe=fp, ngens=p, Phi=Phi, Omega0=(c0, G0red), V=V))
+    return ReachSolution([Flowpipe(_LazyReachSets(N, make))], opts, dict(flowpipe=fp, ngens=p, Phi=Phi, Omega0=(c0, G0red), V=V, times=(t0, t1)))
+
+
+def _projection_rows(vars_, n, M, T):
+    """The projection matrix `project_reach` assembles (project_reach.jl:53-86): rows over the state variables; with
+    `vars_[0] == 0` (time) only the y row.  M: optional 1 x n `:projection_matrix`, T: optional `:transformation_matrix`."""
+    xaxis, yaxis = vars_
+    got_time = xaxis == 0
+    if xaxis < 0:
+        raise ValueError(f"value {xaxis} for x variable not allowed")          # DomainError, project_reach.jl:27-28
+    if yaxis <= 0:
+        raise ValueError(f"value {yaxis} for y variable not allowed")          # :29-30
+    if M is None:
+        P = np.zeros((1 if got_time else 2, n))
+        if got_time:
+            P[0, yaxis - 1] = 1.0
+        else:
+            P[0, xaxis - 1] = 1.0
+            P[1, yaxis - 1] = 1.0
+    else:
+        M = np.asarray(M, dtype=np.float64).reshape(-1, n)
+        assert M.shape[0] == 1, "currently we only support one-dimensional projection matrices"      # :64-65
+        if got_time:
+            P = M[:1].copy()
+        else:
+            P = np.zeros((2, n))
+            P[1] = M[0]
+            P[0, xaxis - 1] = 1.0
+    if T is not None:
+        P = P @ np.asarray(T, dtype=np.float64)                                   # :78-86 (state part of [S 0; 0 1])
+    return P, got_time
 
 
 def project(sol: ReachSolution, vars_: Optional[Sequence[int]] = None):
-    """`project(sol)` for box flowpipes (project_reach.jl:18-99): 2-D boxes over `plot_vars` (0 = time)."""
+    """`project(sol)` (project_reach.jl:18-99) with the default `set_type_proj = Hyperrectangle`: 2-D boxes over
+    `plot_vars` (0 = time).  Zonotope flowpipes (GLGM06) are projected ON THE DEVICE (`reach_flowpipe_project`), only the
+    2 x N boxes come back; decomposed box flowpipes (BFFPSV18) are already per-coordinate boxes on the host."""
     vars_ = list(vars_ if vars_ is not None else sol.options.get("plot_vars", [0, 1]))
-    assert len(vars_) == 2
-    C, R, dims = sol.arrays["centers"], sol.arrays["radii"], sol.arrays.get("dimensions")
-    if dims is None:
-        raise ReachError(3, "project: only decomposed box flowpipes are supported on this path")
+    assert len(vars_) == 2, "we only support projection to two dimensions"
     rs = sol.flowpipes[0].reachsets
+    fp = sol.arrays.get("flowpipe")
+    if fp is not None:
+        n = fp.n
+        P, got_time = _projection_rows(vars_, n, sol.options.get("projection_matrix"), sol.options.get("transformation_matrix"))
+        Cp, Rp = fp.project(P)
+        N = Cp.shape[1]
+        t0, t1 = sol.arrays["times"]
+        out = []
+        for i in range(N):
+            if got_time:
+                c = np.array([(t0[i] + t1[i]) / 2, Cp[0, i]])
+                r = np.array([(t1[i] - t0[i]) / 2, Rp[0, i]])
+            else:
+                c, r = Cp[:, i].copy(), Rp[:, i].copy()
+            out.append(ReachSet(Hyperrectangle(c, r), float(t0[i]), float(t1[i])))
+        return ReachSolution([Flowpipe(out)], sol.options, dict(centers=Cp, radii=Rp, projection=P))
+    C, R, dims = sol.arrays.get("centers"), sol.arrays.get("radii"), sol.arrays.get("dimensions")
+    if dims is None:
+        raise ReachError(3, "project: only decomposed box flowpipes and zonotope flowpipes are supported on this path")
     out = []
     for i in range(len(rs)):
         lo, hi = [], []

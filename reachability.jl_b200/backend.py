@@ -329,6 +329,23 @@ class Flowpipe:
         self.ctx._check(self.ctx.lib.reach_flowpipe_box(self._h, int(k), dptr(lo), dptr(hi)))
         return lo, hi
 
+    def project(self, M, generators: bool = False, Gp=None):
+        """`project(rs, M)` of every reach set on the device (project_reach.jl:18-99): M is q x n with q <= 4.
+        Returns (centers (q, N), radii (q, N)[, Gp (q, pmax, N)]): box of M * R_k and optionally M * G_k itself."""
+        M = fmat(np.asarray(M, dtype=np.float64).reshape(-1, self.n))
+        q = M.shape[0]
+        centers = np.zeros((q, self.N), order="F")
+        radii = np.zeros((q, self.N), order="F")
+        pmax = 0
+        if generators and Gp is None:
+            pmax = int(self.ngens().max())
+            Gp = np.zeros((q, max(pmax, 1), self.N), order="F")
+        if Gp is not None:
+            assert Gp.flags.f_contiguous and Gp.shape[0] == q and Gp.shape[2] == self.N
+            pmax = Gp.shape[1]
+        self.ctx._check(self.ctx.lib.reach_flowpipe_project(self._h, q, dptr(M), q, dptr(centers), dptr(radii), dptr(Gp), pmax))
+        return (centers, radii, Gp) if Gp is not None else (centers, radii)
+
     def selection(self, k: int, which: int = 0, pmax: int = 1 << 16):
         pin, m = C.c_int32(), C.c_int32()
         self.ctx._check(self.ctx.lib.reach_flowpipe_selection(self._h, int(k), int(which), C.byref(pin), C.byref(m),

@@ -58,6 +58,8 @@ struct Ctx {
     int gemm_reserve_sms = 0;       // SMs the persistent GEMM leaves free (GLGM06 keeps one for its selection chain)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
+    int* gemm_sched = nullptr;      // dynamic tile-scheduler words of the persistent GEMM (gemm_dmma.cu)
+    uint32_t gemm_sched_next = 0;
     std::string last_error;
     // launch accounting (bench.py "gpu_launches") and per-phase timings
     uint64_t launches = 0;

@@ -13,6 +13,7 @@
 // the m8n8k4 fragment loads (lane -> (k = lane%4, row = lane/4)) hit 16 distinct 8-byte bank slots per
 // half-warp: slot = 4*(lane%4) + lane/4 (mod 16).
 #include "common.cuh"
+#include "tma.cuh"
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 namespace reach {
@@ -26,39 +27,6 @@ constexpr int PITCH_A = BM + 4;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// 1-D bulk async copy global -> shared through the TMA engine, completion counted on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // 2-D tiled TMA load through a tensor map (coordinates: c0 = innermost = k, c1 = row)
 __device__ __forceinline__ void tma_2d_g2s(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -84,6 +52,7 @@ struct GemmParams {
     double* C2;      // columns >= nsplit are stored to C2[(col - nsplit) * ldc2 + row] (fused side products)
     int64_t ldc2;
     int nsplit;
+    int* sched;      // sched[0] = dynamic tile counter, sched[1] = CTAs that finished fetching (both zero between launches)
 };
 
 // WNT = n8 tiles per warp along N; CTA tile is 128 x (32*WNT).
@@ -111,6 +80,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
     double* sB = sA + STAGES * A_STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
     uint64_t* empty = full + STAGES;
+    int* tile_ring = reinterpret_cast<int*>(empty + STAGES);   // tile id travelling with the first k-step of every tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,15 +89,35 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], CONSUMER_WARPS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
     const int num_tiles = p.tiles_m * p.tiles_n;
     if (warp == CONSUMER_WARPS) {
         // ===== producer warp: lanes 0..15 move A rows, lanes 16..31 move Bt rows of each k-step =====
+        // Tiles are handed out DYNAMICALLY (first one = blockIdx.x, the rest from an atomic counter): the other kernels of
+        // the path share SMs with this one (GLGM06's selection chain owns most of one SM), and with a static round-robin
+        // the slowest SM would set the duration of the whole launch.
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tile = blockIdx.x;
+        while (true) {
+            if (tile >= num_tiles) {                       // sentinel: tells the consumers to leave
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                if (lane == 0) {
+                    tile_ring[s] = -1;
+                    mbar_arrive(&full[s]);
+                    // the last CTA to stop fetching re-arms the scheduler words for the next launch
+                    __threadfence();
+                    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+                        p.sched[0] = 0;
+                        __threadfence();
+                        p.sched[1] = 0;
+                    }
+                }
+                break;
+            }
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
             const double* gA = AKM ? p.A + (int64_t)tm * BM * p.lda : p.A + (int64_t)tm * BM;
             const double* gB = p.Bt + (int64_t)tn * BN;
@@ -135,7 +125,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(BK * (BM + BN) * sizeof(double)));
+                if (lane == 0) {
+                    if (ks == 0) tile_ring[s] = tile;
+                    mbar_expect_tx(&full[s], (uint32_t)(BK * (BM + BN) * sizeof(double)));
+                }
                 __syncwarp();
                 const int k = ks * BK + (lane & 15);
                 if (AKM) {
@@ -148,13 +141,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                 else
                     bulk_g2s(sB + s * B_STAGE + (lane - 16) * PITCH_B, gB + (int64_t)k * p.ldbt, BN * 8, &full[s]);
             }
+            if (lane == 0) tile = (int)gridDim.x + atomicAdd(p.sched, 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
         }
     } else {
         // ===== consumer warps: 2 (M) x 4 (N); warp tile 64 x 8*WNT =====
         const int wm = warp >> 2, wn = warp & 3;
         const int g = lane >> 2, t = lane & 3;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        while (true) {
+            mbar_wait(&full[it % STAGES], (it / STAGES) & 1);
+            const int tile = tile_ring[it % STAGES];
+            if (tile < 0) break;
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
             double acc[8][WNT][2];
 #pragma unroll
@@ -278,7 +276,8 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     constexpr int BN = 32 * WNT;
     constexpr int A_STAGE = AKM ? BM * BK : BK * PITCH_A;
     constexpr int B_STAGE = BK * (BN + 4) + (AKM ? 8 : 0);
-    const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 2 * STAGES * sizeof(uint64_t) + 1024;
+    const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 2 * STAGES * sizeof(uint64_t) +
+                        STAGES * sizeof(int) + 1024;
     static bool configured = false;
     if (!configured) {
         REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -287,7 +286,16 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = ctx->sm_count - ctx->gemm_reserve_sms > 0 ? ctx->sm_count - ctx->gemm_reserve_sms : 1;
     const int grid = tiles < sms ? tiles : sms;
-    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(p, tmap);
+    // scheduler words: a small ring so that two launches in flight never share a pair (each launch leaves its pair zeroed)
+    constexpr int SCHED_RING = 64;
+    if (!ctx->gemm_sched) {
+        REACH_CUDA(cudaMalloc(&ctx->gemm_sched, 2 * SCHED_RING * sizeof(int)));
+        ctx->scratch.push_back(ctx->gemm_sched);
+        REACH_CUDA(cudaMemset(ctx->gemm_sched, 0, 2 * SCHED_RING * sizeof(int)));
+    }
+    GemmParams q = p;
+    q.sched = ctx->gemm_sched + 2 * (ctx->gemm_sched_next++ % SCHED_RING);
+    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(q, tmap);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;
 }

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <climits>
+#include "tma.cuh"
 
 namespace reach {
 
@@ -35,10 +36,12 @@ namespace {
 
 constexpr int MODE_UNCHANGED = 0;   // r*n >= p: reduce_order returns Z unchanged
 constexpr int MODE_REDUCE = 1;
-constexpr int NBW = 4;              // box-sum chunks per step for the W / R reduction
+constexpr int NBW = 4;              // box-sum chunks per step for the W reduction (wseq adds them up per row: keep it small)
 constexpr int NBR = 16;
 constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
 constexpr int COPY_JB = 8;          // columns a warp resolves (one per lane) and then moves back to back
+constexpr int NUM_WARPS = 4;        // warps per CTA of the TMA-staged numerics kernels (wbox_partial, apply_r)
+constexpr int STAGE_BYTES = 16384;  // staging per warp: JB = min(8, STAGE_BYTES / column bytes) columns in flight
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
 constexpr int CHAIN_THREADS = 256;    // small enough to share an SM with the numerics kernels (16 K registers)
 constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
@@ -606,7 +609,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, i
     if (tid == 0) *g.wCount = pW;
 }
 
-static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st) {
+static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st,
+                         bool exclusive = false) {
+    // exclusive: ask for so much shared memory that neither a GEMM CTA nor a numerics CTA fits next to the chain -- it
+    // then owns the SM the GEMM leaves free (Ctx::gemm_reserve_sms) and runs at its stand-alone speed
+    if (use_smem && exclusive) smem = std::max<size_t>(smem, 200 * 1024);
     if (use_smem) {
         if (g.record) chain_kernel<true, true><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
         else chain_kernel<true, false><<<1, CHAIN_THREADS, smem, st>>>(g, k0, cnt, scr);
@@ -677,28 +684,111 @@ __device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc<IT>& a, 
     }
 }
 
+// ---- TMA-staged column access ------------------------------------------------------------------------------------
+// The numerics kernels run next to the persistent DMMA GEMM of a later batch, which leaves room for ONE small CTA per
+// SM.  With register-staged loads (one 2 KB column per warp in flight) that CTA could not cover the HBM latency
+// (measured: a 64-step batch took 1.8 ms in situ against 0.24 ms alone).  Here every warp owns a shared-memory stage of
+// JB columns; one lane per column issues a bulk copy (TMA engine, SASS UBLKCP) and the warp waits on an mbarrier, so a
+// 4-warp CTA keeps ~70 KB in flight with no registers held.
+struct WarpStage {
+    double* buf;        // JB columns of ld doubles
+    uint64_t* bar;
+    uint32_t phase;
+};
+__device__ __forceinline__ WarpStage warp_stage_init(const GP& g, unsigned char* smem, int jb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpStage ws;
+    ws.buf = reinterpret_cast<double*>(smem) + (size_t)warp * jb * g.ld;
+    ws.bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * g.ld) + warp;
+    ws.phase = 0;
+    if (lane == 0) mbar_init(ws.bar, 1);
+    mbar_fence_init();
+    __syncthreads();
+    return ws;
+}
+// scratch of acc_reduce_store behind the stages and barriers
+__device__ __forceinline__ double* stage_red(const GP& g, unsigned char* smem, int jb) {
+    return reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * g.ld + NUM_WARPS;
+}
+// Lane j < jb holds column pointer `src` (or nullptr): start the bulk loads of the warp's group.  Returns the ballot.
+__device__ __forceinline__ unsigned stage_load(const GP& g, WarpStage& ws, const double* src, int lane) {
+    const unsigned dense = __ballot_sync(0xffffffffu, src != nullptr);
+    if (dense) {
+        if (lane == 0) mbar_expect_tx(ws.bar, (uint32_t)(__popc(dense) * g.ld * 8));
+        __syncwarp();
+        if (src) bulk_g2s(ws.buf + (size_t)lane * g.ld, src, (uint32_t)(g.ld * 8), ws.bar);
+    }
+    return dense;
+}
+__device__ __forceinline__ void stage_wait(WarpStage& ws) {
+    mbar_wait(ws.bar, ws.phase);
+    ws.phase ^= 1;
+}
+// a += |staged column j| for every j of `dense`, in lane order
+template <int IT>
+__device__ __forceinline__ void acc_add_staged(const GP& g, Acc<IT>& a, const WarpStage& ws, unsigned dense, int lane) {
+    const int n2 = g.ld / 2;
+    for (unsigned rest = dense; rest;) {
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const double2* c2 = reinterpret_cast<const double2*>(ws.buf + (size_t)j * g.ld);
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < n2) {
+                const double2 v = c2[idx];
+                a.v[i].x += fabs(v.x);
+                a.v[i].y += fabs(v.y);
+            }
+        }
+    }
+    __syncwarp();           // every lane is done reading before the next bulk load lands in the stage
+}
+// a += |box generator (tval at row trow)| of the lanes in `tags`, in lane order
+template <int IT>
+__device__ __forceinline__ void acc_add_tags(Acc<IT>& a, unsigned tags, double tval, int trow, int lane) {
+    for (unsigned rest = tags; rest;) {
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const double val = fabs(__shfl_sync(0xffffffffu, tval, j));
+        const int it = __shfl_sync(0xffffffffu, trow, j);
+        const int idx = it >> 1;
+#pragma unroll
+        for (int i = 0; i < IT; ++i)
+            if (lane + 32 * i == idx) {
+                if (it & 1) a.v[i].y += val; else a.v[i].x += val;
+            }
+    }
+}
+
 // Partial box vectors of the W reductions: chunk b of step t sums |dense discarded generators| in sigma order.
 template <int IT>
-__global__ void __launch_bounds__(256) wbox_partial_kernel(GP g, int k0) {
-    extern __shared__ double red_s[];
+__global__ void __launch_bounds__(NUM_WARPS * 32) wbox_partial_kernel(GP g, int k0, int jb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int t = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PlanW pl = g.planW[k0 + t];
     double* out = g.partW + ((int64_t)t * NBW + b) * g.ld;
+    WarpStage ws = warp_stage_init(g, smem_raw, jb);
     Acc<IT> a;
     acc_zero(a);
     if (pl.mode == MODE_REDUCE) {
         const int chunk = (pl.m + NBW - 1) / NBW;
         const int lo = b * chunk, hi = min(pl.m, lo + chunk);
         const int* dl = g.dlistW + (int64_t)t * g.capDisc;
-        const int wchunk = (chunk + 7) / 8;
+        const int wchunk = (chunk + NUM_WARPS - 1) / NUM_WARPS;
         const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
-        for (int s0 = wlo; s0 < whi; s0 += 32) {
-            const int ref = s0 + lane < whi ? dl[s0 + lane] : -1;
-            const int cntj = min(32, whi - s0);
-            for (int j = 0; j < cntj; ++j) acc_add(g, a, __shfl_sync(0xffffffffu, ref, j), lane, false);
+        for (int s0 = wlo; s0 < whi; s0 += jb) {
+            const int ref = (lane < jb && s0 + lane < whi) ? dl[s0 + lane] : -1;     // box generators are wseq's business
+            const double* src = ref >= 0 ? col_ptr(g, ref) : nullptr;   // nullptr: another rank sums it (partials are all-reduced)
+            const unsigned dense = stage_load(g, ws, src, lane);
+            if (dense) {
+                stage_wait(ws);
+                acc_add_staged(g, a, ws, dense, lane);
+            }
         }
     }
-    acc_reduce_store(g, a, red_s, out);
+    __syncthreads();
+    acc_reduce_store(g, a, stage_red(g, smem_raw, jb), out);
 }
 
 // Sequential over the steps of the batch, parallel over rows: W box vectors (dense partials + discarded box
@@ -829,43 +919,61 @@ __device__ __forceinline__ void resolve_copy_job(const GP& g, const PlanR& pl, c
 }
 
 template <int IT>
-__global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
-    extern __shared__ double red_s[];
+__global__ void __launch_bounds__(NUM_WARPS * 32) apply_r_kernel(GP g, int k0, int jb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int t = blockIdx.y, k = k0 + t, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PlanR pl = g.planR[k];
     const int* order = g.orderR + (int64_t)t * g.capListR;
     const WEnt* sn = g.snEnt + (int64_t)t * g.capW;
     const int n2 = g.ld / 2;
+    WarpStage ws = warp_stage_init(g, smem_raw, jb);
     if (blockIdx.x < NBR) {
         Acc<IT> a;
         acc_zero(a);
         if (pl.mode == MODE_REDUCE) {
-            // chunk of sigma per CTA, a contiguous sub-chunk per warp; the 32 lanes resolve 32 references at once so that
-            // the column reads are not serialised behind order -> snapshot -> column pointer chases
+            // chunk of sigma per CTA, a contiguous sub-chunk per warp; jb lanes resolve jb references at once (order ->
+            // snapshot -> column pointer) and the columns arrive together through the TMA engine
             const int chunk = (pl.m + NBR - 1) / NBR;
             const int lo = blockIdx.x * chunk, hi = min(pl.m, lo + chunk);
-            const int wchunk = (chunk + 7) / 8;
+            const int wchunk = (chunk + NUM_WARPS - 1) / NUM_WARPS;
             const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
-            for (int s0 = wlo; s0 < whi; s0 += 32) {
+            for (int s0 = wlo; s0 < whi; s0 += jb) {
                 int ref = NO_JOB;
-                if (s0 + lane < whi) {
+                if (lane < jb && s0 + lane < whi) {
                     const int code = order[s0 + lane];
                     ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
                 }
-                const int cntj = min(32, whi - s0);
-                for (int j = 0; j < cntj; ++j) acc_add(g, a, __shfl_sync(0xffffffffu, ref, j), lane, true);
+                const double* src = (ref != NO_JOB && ref >= 0) ? col_ptr(g, ref) : nullptr;
+                const unsigned dense = stage_load(g, ws, src, lane);
+                double tval = 0.0;
+                int trow = -1;
+                const bool is_tag = ref != NO_JOB && ref < 0 && g.rank == 0;   // box generators are replicated: rank 0 accounts for them
+                if (is_tag) {
+                    int kt;
+                    tag_decode(ref, g.n, kt, trow);
+                    tval = g.Wd[(int64_t)kt * g.ld + trow];
+                }
+                const unsigned tags = __ballot_sync(0xffffffffu, is_tag);
+                if (dense) {
+                    stage_wait(ws);
+                    acc_add_staged(g, a, ws, dense, lane);
+                }
+                acc_add_tags(a, tags, tval, trow, lane);
             }
         }
-        acc_reduce_store(g, a, red_s, g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
+        __syncthreads();
+        acc_reduce_store(g, a, stage_red(g, smem_raw, jb), g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
         return;
     }
     double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
-    const int nwarps = (gridDim.x - NBR) * 8;
-    const int w0 = (blockIdx.x - NBR) * 8 + warp;
+    const int nwarps = (gridDim.x - NBR) * NUM_WARPS;
+    const int w0 = (blockIdx.x - NBR) * NUM_WARPS + warp;
     const int jobs = pl.mode == MODE_REDUCE ? pl.pin : g.p0 + pl.pW;
-    for (int j0 = w0 * COPY_JB; j0 < jobs; j0 += nwarps * COPY_JB) {
+    for (int j0 = w0 * jb; j0 < jobs; j0 += nwarps * jb) {
         int ref = NO_JOB, dest = 0;
-        if (lane < COPY_JB) resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);   // resolved in parallel
+        if (lane < jb) resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);   // resolved in parallel
+        const double* src = (ref != NO_JOB && ref >= 0) ? col_ptr(g, ref) : nullptr;
+        const unsigned dense = stage_load(g, ws, src, lane);        // archive column -> stage (global -> shared bulk copy)
         double tval = 0.0;
         int trow = -1;
         if (ref != NO_JOB && ref < 0) {
@@ -873,32 +981,34 @@ __global__ void __launch_bounds__(256) apply_r_kernel(GP g, int k0) {
             tag_decode(ref, g.n, kt, trow);
             tval = g.Wd[(int64_t)kt * g.ld + trow];
         }
-        const unsigned live = __ballot_sync(0xffffffffu, ref != NO_JOB);
-        for (unsigned rest = live; rest;) {
+        // box generators (one non-zero) and columns another rank owns (zeros here: the slabs of the ranks have disjoint
+        // support) are written with plain stores while the bulk loads are in flight
+        const unsigned other = __ballot_sync(0xffffffffu, ref != NO_JOB && src == nullptr);
+        for (unsigned rest = other; rest;) {
             const int j = __ffs(rest) - 1;
             rest &= rest - 1;
             const int r = __shfl_sync(0xffffffffu, ref, j), d = __shfl_sync(0xffffffffu, dest, j);
+            const double val = (r < 0 && g.rank == 0) ? __shfl_sync(0xffffffffu, tval, j) : 0.0;
+            const int it = r < 0 ? __shfl_sync(0xffffffffu, trow, j) : -1;
             double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)d * g.ld);
-            if (r >= 0) {
-                const double2* c2 = reinterpret_cast<const double2*>(col_ptr(g, r));
-                if (c2) {
-#pragma unroll 4
-                    for (int i = lane; i < n2; i += 32) d2[i] = c2[i];
-                } else {        // owned by another rank: the slabs of the ranks have disjoint support
-                    for (int i = lane; i < n2; i += 32) d2[i] = make_double2(0.0, 0.0);
-                }
-            } else {
-                const double val = g.rank == 0 ? __shfl_sync(0xffffffffu, tval, j) : 0.0;
-                const int it = __shfl_sync(0xffffffffu, trow, j);
-                for (int i = lane; i < n2; i += 32) {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (2 * i == it) v.x = val;
-                    if (2 * i + 1 == it) v.y = val;
-                    d2[i] = v;
-                }
+            for (int i = lane; i < n2; i += 32) {
+                double2 v = make_double2(0.0, 0.0);
+                if (2 * i == it) v.x = val;
+                if (2 * i + 1 == it) v.y = val;
+                d2[i] = v;
             }
         }
+        if (dense) {
+            stage_wait(ws);
+            if (src) {                                              // stage -> flowpipe slot (shared -> global bulk copy)
+                bulk_s2g(slot + (int64_t)dest * g.ld, ws.buf + (size_t)lane * g.ld, (uint32_t)(g.ld * 8));
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            __syncwarp();
+        }
     }
+    bulk_wait0();
 }
 
 // Box vector, generator counts and (strip mode) the rows of the dense box generators of every R_k of the batch.
@@ -1000,6 +1110,86 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     const double ci = c[(int64_t)b * c_stride + i];
     lo[(int64_t)b * n + i] = ci - s;
     hi[(int64_t)b * n + i] = ci + s;
+}
+
+// ---- projection of a zonotope flowpipe: M * R_k (project_reach.jl:18-99, linear map of every reach set) -----------
+// One warp per generator column: lanes stride the column with 16-byte loads and carry the q <= 4 dot products with the
+// rows of M (Mt: q rows of n doubles); out[((k-1)*pmax + col)*q + row].  Columns beyond the set's count are zeroed.
+struct ProjIn {
+    const double* G;        // generators of step 1
+    int64_t slot;           // doubles between consecutive steps
+    const double* c;        // centre of step 1
+    int64_t cstride;
+    const int2* meta;       // per-step generator counts (x + y), or nullptr: p_const
+    int p_const;
+    int n, ld, q, pmax, N;
+};
+
+__device__ __forceinline__ void proj_column(const double* __restrict__ col, const double* __restrict__ Mt, int n, int q,
+                                            int lane, double acc[4]) {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+    const int n2 = n >> 1;
+    for (int i = lane; i < n2; i += 32) {
+        const double2 v = reinterpret_cast<const double2*>(col)[i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r < q) {
+                const double2 m = reinterpret_cast<const double2*>(Mt + (int64_t)r * (n + (n & 1)))[i];
+                acc[r] = fma(m.y, v.y, fma(m.x, v.x, acc[r]));
+            }
+    }
+    if ((n & 1) && lane == 0) {
+        const double v = col[n - 1];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r < q) acc[r] = fma(Mt[(int64_t)r * (n + 1) + n - 1], v, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (r < q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+}
+
+__global__ void __launch_bounds__(256) project_gens_kernel(ProjIn in, const double* __restrict__ Mt, double* __restrict__ out) {
+    const int k = blockIdx.y, col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= in.N || col >= in.pmax) return;
+    const int p = in.meta ? in.meta[k].x + in.meta[k].y : in.p_const;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (col < p) proj_column(in.G + (int64_t)k * in.slot + (int64_t)col * in.ld, Mt, in.n, in.q, lane, acc);
+    if (lane < in.q) {
+        const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        out[((int64_t)k * in.pmax + col) * in.q + lane] = v;
+    }
+}
+
+// Centre M c_k and the box radius sum_j |M g_j| of every projected reach set (set_type_proj = Hyperrectangle,
+// default_options.jl:69), fixed summation order: thread t adds columns t, t+256, ... and a shared-memory tree follows.
+__global__ void __launch_bounds__(256) project_box_kernel(ProjIn in, const double* __restrict__ Mt, const double* __restrict__ Gp,
+                                                          double* __restrict__ centers, double* __restrict__ radii) {
+    __shared__ double red[256];
+    const int k = blockIdx.x;
+    const int p = in.meta ? in.meta[k].x + in.meta[k].y : in.p_const;
+    for (int r = 0; r < in.q; ++r) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < p; j += 256) s += fabs(Gp[((int64_t)k * in.pmax + j) * in.q + r]);
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) radii[(int64_t)k * in.q + r] = red[0];
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        double acc[4];
+        proj_column(in.c + (int64_t)k * in.cstride, Mt, in.n, in.q, threadIdx.x, acc);
+        if ((int)threadIdx.x < in.q) {
+            const int l = threadIdx.x;
+            centers[(int64_t)k * in.q + l] = l == 0 ? acc[0] : l == 1 ? acc[1] : l == 2 ? acc[2] : acc[3];
+        }
+    }
 }
 
 // Homogeneous recurrence for small state dimension (n <= 32; config C5: n = 28): Y_k = Phi Y_{k-1}, exactly the reference's
@@ -1105,9 +1295,11 @@ struct Flowpipe {
     double* scr = nullptr;          // chain scratch when the W list does not fit in shared memory
     size_t chain_smem = 0;
     int chain_use_smem = 1;
+    bool chain_exclusive = false;   // the chain owns one SM (the GEMM grid leaves it free)
     cudaStream_t side = nullptr;    // selection chain of batch b (overlaps the GEMM of batch b+1) ...
     cudaStream_t side2 = nullptr;   // ... and the numerics of batch b (overlap the chain of batch b+1)
     cudaStream_t side3 = nullptr;   // scores + segment order of batch b (only need the GEMM of batch b)
+    cudaStream_t side4 = nullptr;   // R sortperm of batch b (only needs the chain of batch b)
     GP gset[2];                     // batch-local arrays, double-buffered by batch parity
     std::vector<void*> owned;
     std::vector<int2> meta_host;
@@ -1134,6 +1326,7 @@ void flowpipe_free(Flowpipe* F) {
     if (F->side) cudaStreamDestroy(F->side);
     if (F->side2) cudaStreamDestroy(F->side2);
     if (F->side3) cudaStreamDestroy(F->side3);
+    if (F->side4) cudaStreamDestroy(F->side4);
     if (F->cpy) cudaStreamDestroy(F->cpy);
     delete F;
 }
@@ -1292,6 +1485,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             REACH_CUDA(cudaStreamCreateWithPriority(&F->side, cudaStreamNonBlocking, prio_hi));      // the chain is the critical path
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side2, cudaStreamNonBlocking));
             REACH_CUDA(cudaStreamCreateWithFlags(&F->side3, cudaStreamNonBlocking));
+            REACH_CUDA(cudaStreamCreateWithFlags(&F->side4, cudaStreamNonBlocking));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
             if (p0 > 0) REACH_CUDA(cudaMemsetAsync(g.Rg, 0, (size_t)p0 * ld * 8, st));
             if (g.la > 0)
@@ -1368,16 +1562,26 @@ static void bind_set(GP& g, const GP& h) {
     g.orderR = h.orderR; g.partW = h.partW; g.partR = h.partR;
 }
 
+// columns per warp stage and dynamic shared memory of the TMA-staged numerics kernels: stages | mbarriers | reduction scratch
+static int numerics_jb(int64_t ld) { return (int)std::max<int64_t>(1, std::min<int64_t>(COPY_JB, STAGE_BYTES / (ld * 8))); }
+static size_t numerics_smem(int64_t ld, int jb) {
+    return (size_t)NUM_WARPS * jb * ld * 8 + NUM_WARPS * sizeof(uint64_t) + (size_t)NUM_WARPS * ld * 8;
+}
+
 // selection chain of steps [k0, k0 + cnt) (their slots k-1 are in the archive already) ...
 static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
-    launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
+    launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st, F->chain_exclusive);
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches += 1;
 }
 
 // ... and their batched numerics
-static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st) {
-    const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
+// `rank_st` (optional): rank_r only needs the chain's snapshot, so it may run on its own stream next to wbox / wseq;
+// `rank_done` is then recorded there and awaited before apply_r.
+static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st, cudaStream_t rank_st = nullptr,
+                             cudaEvent_t rank_done = nullptr) {
+    const int jb = numerics_jb(F->ld);
+    const size_t red_smem = numerics_smem(F->ld, jb);
     const int it = F->ld <= 256 ? 4 : (F->ld <= 512 ? 8 : 16);
     auto mark = [&]() {          // REACH_TIMING_DETAIL=1: CUDA events between the kernels (diagnostics only)
         if (!F->detail) return;
@@ -1387,18 +1591,24 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
         F->detail_ev.push_back(e);
     };
     mark();
-    if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
-    else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
-    else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+    if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+    else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+    else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     mark();
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     mark();
-    rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
+    if (rank_st && rank_st != st) {
+        rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, rank_st>>>(g, k0);
+        REACH_CUDA(cudaEventRecord(rank_done, rank_st));
+        REACH_CUDA(cudaStreamWaitEvent(st, rank_done, 0));
+    } else {
+        rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
+    }
     mark();
     const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
-    if (it == 4) apply_r_kernel<4><<<ag, 256, red_smem, st>>>(g, k0);
-    else if (it == 8) apply_r_kernel<8><<<ag, 256, red_smem, st>>>(g, k0);
-    else apply_r_kernel<16><<<ag, 256, red_smem, st>>>(g, k0);
+    if (it == 4) apply_r_kernel<4><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+    else if (it == 8) apply_r_kernel<8><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+    else apply_r_kernel<16><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     mark();
     finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
     mark();
@@ -1414,8 +1624,13 @@ static void set_kernel_attributes(Flowpipe* F) {
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(sort_segments_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BITONIC_MAX * 12));
-    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    const int num_smem = 112 * 1024;        // 4 warps x 16 KB stages + scratch for n <= 1024
+    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
+    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
+    REACH_CUDA(cudaFuncSetAttribute(wbox_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
+    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
+    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
+    REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
     done = true;
     (void)F;
 }
@@ -1452,7 +1667,24 @@ void flowpipe_run(Flowpipe* F) {
         Ctx* c; int old;
         ReserveGuard(Ctx* c_, int v) : c(c_), old(c_->gemm_reserve_sms) { c->gemm_reserve_sms = v; }
         ~ReserveGuard() { c->gemm_reserve_sms = old; }
-    } reserve(ctx, 0);      // measured: letting the GEMM keep every SM (the chain co-resides) beats reserving SMs
+    } reserve(ctx, 0);
+    if (!F->homog && !F->serial) {
+        // SM partition of the pipelined run.  The persistent GEMM is issue-bound, so kernels that share its SMs crawl (a
+        // 64-step batch of numerics took 1.8 ms next to it against 0.24 ms alone) and the chain lost half its speed.  The
+        // GEMM therefore leaves K SMs free: one is owned by the selection chain (which asks for so much shared memory that
+        // nothing fits beside it), the others run the HBM-bound numerics at full occupancy.  K balances the two: t_gemm at
+        // the DMMA peak against t_numerics at ~4 TB/s, scaled by 0.5 because the numerics CTAs that land next to GEMM CTAs
+        // still contribute.  (C2: K = 33 gave 106 k steps/s against 89 k with K = 0; the dynamic tile scheduler of the GEMM
+        // makes any grid size free of wave quantisation.)  REACH_GEMM_RESERVE / REACH_CHAIN_EXCLUSIVE override (diagnostics).
+        const char* e = getenv("REACH_CHAIN_EXCLUSIVE");
+        F->chain_exclusive = F->chain_use_smem && (!e || atoi(e) != 0);
+        const double t_gemm = 2.0 * (double)n * n * F->q / 37.0e12;
+        const double t_num = 8.0 * (double)ld * (2.0 * F->r * n + F->p0 + F->pV) * 1.25 / 4.0e12;
+        int K = (int)(0.5 * ctx->sm_count * t_num / (t_gemm + t_num) + 0.5) + (F->chain_exclusive ? 1 : 0);
+        K = std::max(F->chain_exclusive ? 2 : 0, std::min(K, ctx->sm_count / 2));
+        const char* r = getenv("REACH_GEMM_RESERVE");
+        ctx->gemm_reserve_sms = r ? atoi(r) : K;
+    }
     std::vector<std::pair<size_t, size_t>> chain_ev;
     F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
     if (F->homog && !F->phi_host.empty() && N > 1) {
@@ -1529,7 +1761,12 @@ void flowpipe_run(Flowpipe* F) {
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             red_ev.push_back({ev_used - 2, ev_used - 1});
             REACH_CUDA(cudaEventRecord(e0, sNum));
-            process_numerics(F, g, (int)have + 1, (int)cnt, sNum);
+            if (F->serial || F->detail) {
+                process_numerics(F, g, (int)have + 1, (int)cnt, sNum);
+            } else {
+                REACH_CUDA(cudaStreamWaitEvent(F->side4, c1, 0));
+                process_numerics(F, g, (int)have + 1, (int)cnt, sNum, F->side4, next_event(F, ev_used));
+            }
             REACH_CUDA(cudaEventRecord(e1, sNum));
             ev_num.push_back(e1);
             if (F->sink_G) {        // stream this batch's reach sets to the host while the later batches are computed
@@ -1604,6 +1841,14 @@ void flowpipe_run(Flowpipe* F) {
         cudaMemcpyToSymbol(g_chain_prof, z, sizeof(z));
     }
 #endif
+    if (getenv("REACH_TIMELINE")) {     // diagnostics: start/end of every batch's GEMM, chain and numerics relative to the run start
+        auto rel = [&](size_t e) { float t = 0; cudaEventElapsedTime(&t, ctx->ev0, F->evs[e]); return t; };
+        for (size_t b = 0; b < chain_ev.size(); ++b)
+            fprintf(stderr, "[reach timeline] batch %3zu chain %8.3f - %8.3f   numerics %8.3f - %8.3f\n", b,
+                    rel(chain_ev[b].first), rel(chain_ev[b].second), rel(red_ev[b].first), rel(red_ev[b].second));
+        for (size_t b = 0; b < gemm_ev.size(); ++b)
+            fprintf(stderr, "[reach timeline] gemm %3zu %8.3f - %8.3f\n", b, rel(gemm_ev[b].first), rel(gemm_ev[b].second));
+    }
     F->chain_ms = 0;
     for (auto& pr : chain_ev) {
         float t = 0;
@@ -1674,7 +1919,8 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
     const int k0 = (int)B.have + 1, cnt = (int)B.cnt;
     g.Y = F->Hflow + B.have * F->qloc * ld;
     g.col0 = B.have * F->q;
-    const size_t red_smem = (size_t)8 * ld * sizeof(double);
+    const int jb = numerics_jb(ld);
+    const size_t red_smem = numerics_smem(ld, jb);
     const int it = ld <= 256 ? 4 : (ld <= 512 ? 8 : 16);
     if (phase == 0) {
         gemm_left(ctx, n, B.cnt * F->qloc, n, F->pw->p, F->pw->ld, F->Hflow + (B.have - B.w) * F->qloc * ld, ld,
@@ -1683,18 +1929,18 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
     } else if (phase == 1) {
         sort_only(F, g, cnt, st);
         launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
-        if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
-        else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
-        else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), 256, red_smem, st>>>(g, k0);
+        if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+        else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+        else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 2;
     } else if (phase == 2) {
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
         rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
         const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
-        if (it == 4) apply_r_kernel<4><<<ag, 256, red_smem, st>>>(g, k0);
-        else if (it == 8) apply_r_kernel<8><<<ag, 256, red_smem, st>>>(g, k0);
-        else apply_r_kernel<16><<<ag, 256, red_smem, st>>>(g, k0);
+        if (it == 4) apply_r_kernel<4><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+        else if (it == 8) apply_r_kernel<8><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+        else apply_r_kernel<16><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 3;
     } else {
@@ -1763,8 +2009,9 @@ void reduce_order_once(Ctx* ctx, int64_t n, int64_t p, const double* c, const do
         REACH_CUDA(cudaMemsetAsync(g.wCount, 0, sizeof(int), st));
         score_and_sort(F, g, 0, 1, st);
         launch_chain(g, 1, 1, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
-        const size_t red_smem = (size_t)8 * F->ld * sizeof(double);
-        wbox_partial_kernel<16><<<dim3(NBW, 1), 256, red_smem, st>>>(g, 1);
+        const int jb = numerics_jb(F->ld);
+        const size_t red_smem = numerics_smem(F->ld, jb);
+        wbox_partial_kernel<16><<<dim3(NBW, 1), NUM_WARPS * 32, red_smem, st>>>(g, 1, jb);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, 1, 1);
         REACH_CUDA(cudaGetLastError());
         const int64_t cap = g.capW;
@@ -2002,6 +2249,55 @@ int32_t reach_flowpipe_box(reach_flowpipe* fp, int64_t k, double* lo, double* hi
     REACH_CUDA(cudaMemcpyAsync(lo, F->stage, F->n * 8, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaMemcpyAsync(hi, F->stage + F->n, F->n * 8, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaStreamSynchronize(st));
+    return REACH_OK;
+    FP_END(fp->ctx)
+}
+
+int32_t reach_flowpipe_project(reach_flowpipe* fp, int64_t q, const double* M, int64_t ldm, double* centers, double* radii,
+                               double* Gp, int64_t pmax) {
+    if (!fp || !M) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    Flowpipe* F = fp->f;
+    require_ran(F);
+    REACH_REQUIRE(q >= 1 && q <= 4 && ldm >= q, "reach_flowpipe_project: 1 <= q <= 4 rows and ldm >= q are required");
+    int64_t need = 0;
+    for (const int2& m : F->meta_host) need = std::max<int64_t>(need, m.x + m.y);
+    if (Gp) REACH_REQUIRE(pmax >= need, "reach_flowpipe_project: pmax smaller than a reach set's generator count");
+    else pmax = std::max<int64_t>(need, 1);
+    cudaStream_t st = F->ctx->stream;
+    const int64_t n = F->n, N = F->N, npad = n + (n & 1);
+    // M (q x n, column-major, ld ldm) -> q contiguous rows of npad doubles
+    std::vector<double> mt((size_t)q * npad, 0.0);
+    for (int64_t r = 0; r < q; ++r)
+        for (int64_t i = 0; i < n; ++i) mt[(size_t)r * npad + i] = M[i * ldm + r];
+    double* dM = (double*)ctx_malloc(F->ctx, mt.size() * 8);
+    double* dG = (double*)ctx_malloc(F->ctx, (size_t)q * pmax * N * 8);
+    double* dcr = (double*)ctx_malloc(F->ctx, (size_t)2 * q * N * 8);
+    try {
+        REACH_CUDA(cudaMemcpyAsync(dM, mt.data(), mt.size() * 8, cudaMemcpyHostToDevice, st));
+        ProjIn in;
+        if (F->homog) {
+            in.G = F->Hflow; in.slot = F->q * F->ld; in.c = F->Hflow + F->p0 * F->ld; in.cstride = F->q * F->ld;
+            in.meta = nullptr; in.p_const = (int)F->p0;
+        } else {
+            in.G = F->g.Rg; in.slot = F->g.slot; in.c = F->g.Rc; in.cstride = F->ld; in.meta = F->g.meta; in.p_const = 0;
+        }
+        in.n = (int)n; in.ld = (int)F->ld; in.q = (int)q; in.pmax = (int)pmax; in.N = (int)N;
+        project_gens_kernel<<<dim3((unsigned)ceil_div(pmax, 8), (unsigned)N), 256, 0, st>>>(in, dM, dG);
+        REACH_CUDA(cudaGetLastError());
+        project_box_kernel<<<(unsigned)N, 256, 0, st>>>(in, dM, dG, dcr, dcr + q * N);
+        REACH_CUDA(cudaGetLastError());
+        F->ctx->launches += 2;
+        if (centers) REACH_CUDA(cudaMemcpyAsync(centers, dcr, (size_t)q * N * 8, cudaMemcpyDeviceToHost, st));
+        if (radii) REACH_CUDA(cudaMemcpyAsync(radii, dcr + q * N, (size_t)q * N * 8, cudaMemcpyDeviceToHost, st));
+        if (Gp) REACH_CUDA(cudaMemcpyAsync(Gp, dG, (size_t)q * pmax * N * 8, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        ctx_free(F->ctx, dM); ctx_free(F->ctx, dG); ctx_free(F->ctx, dcr);
+        throw;
+    }
+    ctx_free(F->ctx, dM); ctx_free(F->ctx, dG); ctx_free(F->ctx, dcr);
     return REACH_OK;
     FP_END(fp->ctx)
 }

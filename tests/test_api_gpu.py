@@ -128,6 +128,23 @@ def test_glgm06_mirror():                                                   # :1
         assert_close(set_of(rs[k]).generators, R[k].G, "generators")
 
 
+def test_glgm06_project_on_the_device():                                   # project_reach.jl:18-99 on a zonotope flowpipe
+    U = Interval(0.99, 1.01) * Interval(0.99, 1.01)
+    s = solve(IVP(CLCCS(A, B, None, U), X0), Options(T=0.1), op=GLGM06())
+    Dz = orc.discretize_zonotope(A, orc.Box(np.ones(4), np.full(4, 0.1)), 0.01, B, orc.Box(np.ones(2), np.full(2, 0.01)))
+    R = orc.glgm06_reach(Dz, 10, 10)
+    p13 = project(s, [1, 3]).flowpipes[0].reachsets             # two state variables
+    pt2 = project(s, [0, 2]).flowpipes[0].reachsets             # time x state variable
+    for k in (0, 4, 9):
+        rad = np.abs(R[k].G).sum(axis=1)
+        assert_close(set_of(p13[k]).center, R[k].c[[0, 2]], "centre (1,3)")
+        assert_close(set_of(p13[k]).radius, rad[[0, 2]], "radius (1,3)")
+        assert_close(set_of(pt2[k]).center, np.array([0.01 * k + 0.005, R[k].c[1]]), "centre (t,2)")
+        assert_close(set_of(pt2[k]).radius, np.array([0.005, rad[1]]), "radius (t,2)")
+    with pytest.raises(ValueError):
+        project(s, [1, 0])                                         # DomainError: y variable must be positive (:29-30)
+
+
 def test_unsupported_inputs_raise_instead_of_falling_back():
     with pytest.raises(ReachError) as ei:
         solve(IVP(LCS(A), Ball2Stub(np.ones(4), 0.1)), Options(T=0.1), op=GLGM06())     # :199-200 needs LazySets on the host

@@ -285,3 +285,41 @@ def test_config_c2_full_size_properties(ctx):
     c_b, G_b = fp.step(1999)
     assert np.array_equal(c_a, c_b) and np.array_equal(G_a, G_b)      # deterministic: no float atomics, fixed orders
     fp.close()
+
+
+# ---- projection of the zonotope flowpipe on the device (project_reach.jl:18-99) ------------------------------------
+@pytest.mark.parametrize("n,m,N,r,q", [(9, 2, 14, 3, 2), (16, 1, 10, 2, 1), (31, 3, 12, 2, 4), (6, 0, 9, 5, 3)])
+def test_projection_matches_host_linear_map(ctx, n, m, N, r, q):
+    """`project(rs, M)` = linear_map(M, Z) per reach set, Hyperrectangle overapproximation of the result
+    (set_type_proj default): device kernels vs numpy on the oracle's zonotopes."""
+    A, X0, B, U, delta = _problem(300 + n, n, m)
+    D, Om, R, _ = _oracle(A, X0, B, U, delta, N, r, True)
+    fp = _device(ctx, D, Om, N, r, True, record=False)
+    M = np.random.default_rng(n).standard_normal((q, n))
+    if q >= 2:
+        M[1] = 0.0
+        M[1, n - 1] = 1.0           # a plain coordinate selection, as project_reach builds it
+    C, Rad, Gp = fp.project(M, generators=True)
+    p = fp.ngens()
+    for k in range(1, N + 1):
+        Z = R[k - 1]
+        assert_close(C[:, k - 1], M @ Z.c, f"step {k} projected centre")
+        MG = M @ Z.G
+        assert_close(Gp[:, :p[k - 1], k - 1], MG, f"step {k} projected generators")
+        assert np.all(Gp[:, p[k - 1]:, k - 1] == 0.0)
+        assert_close(Rad[:, k - 1], np.abs(MG).sum(axis=1), f"step {k} projected box radius")
+    C2, Rad2 = fp.project(M)                   # boxes only: identical bits (fixed summation order)
+    assert np.array_equal(C2, C) and np.array_equal(Rad2, Rad)
+    fp.close()
+
+
+def test_projection_rejects_bad_arguments(ctx):
+    A, X0, B, U, delta = _problem(7, 5, 1)
+    D, Om, R, _ = _oracle(A, X0, B, U, delta, 4, 3, True)
+    fp = _device(ctx, D, Om, 4, 3, True, record=False)
+    from reachability_jl_b200 import ReachError
+    with pytest.raises(ReachError):
+        fp.project(np.ones((5, 5)))            # q > 4
+    with pytest.raises(ReachError):
+        fp.project(np.ones((2, 5)), Gp=np.zeros((2, 1, 4), order="F"))     # pmax too small
+    fp.close()
