@@ -125,6 +125,34 @@ REACH_API int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t n, const dou
                                   int64_t nblocks, const int32_t* block_sizes, int64_t q, const double* Mout, int64_t ldm,
                                   double* centers, double* radii);
 
+/* ---- sparse A, lazy matrix exponential: `:lazy_expm` / `exp_method = "lazy"` --------------------------------- */
+/* The state matrix as Julia's SparseMatrixCSC fields (colptr n+1, rowval nnz, nzval nnz; 1-based Int64), kept on the device
+ * as CSR of Aᵀ (the same arrays) and CSR of A.  Φ = e^{Aδ} is never formed on this path: every use of Φ is the ACTION
+ * of e^{δA} / e^{δAᵀ} on a block of vectors, a scaled Taylor series of sparse x dense-block products carried to full
+ * double precision -- the device counterpart of `SparseMatrixExp` + `get_rows` / `get_columns` / `expmv`
+ * (discretize.jl:153-154, 302-306; BFFPSV18/reach_blocks.jl:37-38). */
+typedef struct reach_sparse reach_sparse;
+REACH_API int32_t reach_sparse_create(reach_ctx* ctx, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                              const double* nzval, reach_sparse** out);
+REACH_API void reach_sparse_free(reach_sparse* sp);
+/* Y = e^{δA} X (transpose_op = 0: what get_columns needs) or e^{δAᵀ} X (1: get_rows); X, Y n x R column-major. */
+REACH_API int32_t reach_expmv(reach_sparse* sp, double delta, int32_t transpose_op, int64_t R, const double* X, int64_t ldx,
+                      double* Y, int64_t ldy);
+/* reach_discretize_box for a sparse A with REACH_FORWARD / REACH_BACKWARD (others: REACH_EUNSUPPORTED): same outputs except
+ * the matrices -- c0, r0 (box of Ω0), rE, rpsi (n), MU = δB (n x m, ld n); each may be NULL. */
+REACH_API int32_t reach_discretize_box_sparse(reach_sparse* sp, double delta, int32_t algorithm, const double* c, const double* r,
+                                      int64_t m, const double* B, int64_t ldb, const double* cU, const double* rU,
+                                      double* c0, double* r0, double* rE, double* rpsi, double* MU);
+/* reach_blocks!(ϕ::SparseMatrixExp, ...) for Interval / Hyperrectangle blocks (BFFPSV18/reach_blocks.jl:227-397): the rows
+ * of interest of e^{kδA} are advanced on the device, W_kᵀ = e^{δAᵀ} W_{k-1}ᵀ (the reference recomputes them with a Krylov
+ * expmv from ϕpowerk.M = kδA at every step, :306).  Arguments and outputs as reach_bffpsv18_boxes, without Phi. */
+REACH_API int32_t reach_bffpsv18_boxes_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m,
+                                    const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                                    int64_t nrows, const int32_t* rows, int64_t N, double* centers, double* radii,
+                                    int64_t* steps_done);
+/* CUDA-event time of the last call on `sp`, its sparse x block products and their algorithmic HBM/L2 bytes. */
+REACH_API int32_t reach_sparse_timing(reach_sparse* sp, double* run_ms, int64_t* products, double* bytes);
+
 /* ---- GLGM06: reach_homog! / reach_inhomog! (GLGM06/reach.jl:5-62) -------------------------------------- */
 /* flags */
 #define REACH_GLGM06_KEEP_ZERO_GENERATORS 1 /* Zonotope(c, G; remove_zero_generators=false) semantics */

@@ -467,6 +467,45 @@ def bffpsv18_reach(P: DiscreteBoxProblem, N: int, rows: Optional[Sequence[int]] 
     return C, R
 
 
+def bffpsv18_reach_lazy(A, P: DiscreteBoxProblem, delta: float, N: int, rows: Optional[Sequence[int]] = None):
+    """``reach_blocks!(ϕ::SparseMatrixExp, ...)`` (BFFPSV18/reach_blocks.jl:227-310), restated LITERALLY: the lazy
+    exponent matrix accumulates, ``ϕpowerk.M .= ϕpowerk.M + ϕ.M`` (:306), and the rows of ``exp(ϕpowerk.M)`` are taken
+    from scratch at every step (``row(ϕpowerk, bi) = get_rows(ϕpowerk, bi)``, :37-38 -- LazySets evaluates them with
+    Expokit's Krylov ``expmv``; here with a dense ``expm`` of kδA, i.e. to full precision).  Same box arithmetic as
+    `bffpsv18_reach`; used to pin the device path's recurrence W_k = W_{k-1} e^{δA} against the from-scratch rows.
+    O(N n^3): small cases only."""
+    A = np.asarray(A.toarray() if hasattr(A, "toarray") else A, dtype=np.float64)
+    n = A.shape[0]
+    rows = np.arange(n) if rows is None else np.asarray(rows, dtype=np.int64)
+    C = np.zeros((N, len(rows)))
+    R = np.zeros((N, len(rows)))
+    C[0] = P.c0[rows]
+    R[0] = P.r0[rows]
+    if N == 1:
+        return C, R
+    inhomog = P.MU is not None
+    if inhomog:
+        cW = (P.MU @ P.cU)[rows]                               # :256-262
+        rW = (np.abs(P.MU) @ P.rU + P.rpsi)[rows]
+    M1 = A * delta                                             # ϕ.M
+    Mk = M1.copy()                                             # ϕpowerk = SparseMatrixExp(copy(ϕ.M))  :257
+    for k in range(2, N + 1):
+        Pk = expm_julia(Mk)[rows, :]                           # row(ϕpowerk, bi)  :269
+        c = Pk @ P.c0
+        r = np.abs(Pk) @ P.r0
+        if inhomog:
+            c = c + cW
+            r = r + rW
+        C[k - 1] = c
+        R[k - 1] = r
+        if inhomog:                                            # :284-287 (inside the block loop, before the store)
+            PM = Pk @ P.MU
+            cW = cW + PM @ P.cU
+            rW = rW + np.abs(PM) @ P.rU + np.abs(Pk) @ P.rpsi
+        Mk = Mk + M1                                           # :306
+    return C, R
+
+
 def _block_slices(nrows: int, block_sizes: Optional[Sequence[int]]):
     """Slices of ``rows`` belonging to each block of ``:blocks`` (consecutive groups; None: one single block)."""
     if block_sizes is None:

@@ -49,6 +49,14 @@ _SIGNATURES = {
     "reach_boxplan_destroy": [vp],
     "reach_bffpsv18_check": _BOX_ARGS + [i64, c_int32_p, c_double_p, f64, i32, c_int64_p],
     "reach_bffpsv18_output_map": _BOX_ARGS + [i64, c_int32_p, i64, c_double_p, i64, c_double_p, c_double_p],
+    "reach_sparse_create": [vp, i64, i64, c_int64_p, c_int64_p, c_double_p, C.POINTER(vp)],
+    "reach_sparse_free": [vp],
+    "reach_expmv": [vp, f64, i32, i64, c_double_p, i64, c_double_p, i64],
+    "reach_discretize_box_sparse": [vp, f64, i32, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p,
+                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p],
+    "reach_bffpsv18_boxes_lazy": [vp, f64, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p, c_double_p,
+                                  i64, c_int32_p, i64, c_double_p, c_double_p, c_int64_p],
+    "reach_sparse_timing": [vp, c_double_p, c_int64_p, c_double_p],
     "reach_glgm06_create": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
                             i64, i64, i64, i32, C.POINTER(vp)],
     "reach_glgm06_create_sharded": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
@@ -80,7 +88,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {
     "reach_ctx_destroy": None, "reach_boxplan_destroy": None, "reach_flowpipe_free": None,
-    "reach_ensemble_free": None, "reach_last_error": C.c_char_p,
+    "reach_ensemble_free": None, "reach_last_error": C.c_char_p, "reach_sparse_free": None,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -196,7 +196,7 @@ IVP = InitialValueProblem
 
 
 def statedim(S) -> int:
-    return np.asarray(S.A).shape[0]
+    return (S.A if hasattr(S.A, "toarray") else np.asarray(S.A)).shape[0]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -380,13 +380,15 @@ def _context(device=0) -> Context:
     return _ctx_cache[device]
 
 
-def _normalize(problem):
+def _normalize(problem, keep_sparse=False):
     """`normalize(system)` (Utils/normalization.jl:69-102,143-166) restricted to what the device path accepts:
     returns (A, B or None, U box (cU, rU) or None)."""
     S = problem.s
-    A = np.asarray(S.A, dtype=np.float64)
+    A = S.A
     if hasattr(A, "toarray"):
-        A = A.toarray()
+        A = A if keep_sparse else A.toarray()              # Matrix(A*δ), discretize.jl:152
+    else:
+        A = np.asarray(A, dtype=np.float64)
     if A.ndim != 2 or A.shape[0] != A.shape[1]:
         raise ValueError("the state matrix must be square")
     if isinstance(S, LinearContinuousSystem):
@@ -458,7 +460,7 @@ def _block_set_types(op, partition):
 
 def _post_bffpsv18(op, problem, opts, ctx):
     n = opts["n"]
-    A, B, U = _normalize(problem)
+    A, B, U = _normalize(problem, keep_sparse=op["exp_method"] == "lazy")
     if op["assume_homogeneous"]:
         B, U = None, None
     delta, T = float(op["δ"]), float(opts["T"])
@@ -471,13 +473,28 @@ def _post_bffpsv18(op, problem, opts, ctx):
     types = _block_set_types(op, partition)
     if op["discretization"] not in ("forward", "backward", "firstorder", "nobloating"):
         raise ValueError(f"the algorithm {op['discretization']} is unknown")          # discretize.jl:121
-    if op["exp_method"] not in ("base", "sm100a"):
-        raise ReachError(3, f"exp_method {op['exp_method']!r} is unsupported on the sm_100a path")
+    if op["exp_method"] not in ("base", "sm100a", "lazy"):
+        if op["exp_method"] == "pade":
+            raise ReachError(3, "exp_method 'pade' is unsupported on the sm_100a path")
+        raise ValueError(f"the exponentiation method {op['exp_method']} is unknown")    # ArgumentError, discretize.jl:158
     c, r = _as_box(problem.x0, "initial set")
     N = int(math.ceil(T / delta))                                          # reach.jl:54
+    rows = np.asarray(dims, dtype=np.int32) - 1
+    if op["exp_method"] == "lazy":
+        # ϕ = SparseMatrixExp(A*δ) (discretize.jl:153-154) -> reach_blocks!(ϕ::SparseMatrixExp, ...) (reach_blocks.jl:227-397):
+        # the matrix exponential is only ever applied to blocks of vectors on the device
+        if opts["mode"] == "check" or (opts["projection_matrix"] is not None and not opts["project_reachset"]):
+            raise ReachError(3, "check mode / output functions with a lazy matrix exponential are unsupported on the sm_100a path")
+        Sp = ctx.sparse(A)
+        try:
+            D = Sp.discretize_box(delta, c, r, B if U is not None else None, None if U is None else U[0],
+                                  None if U is None else U[1], algorithm=op["discretization"])
+            C, R = Sp.bffpsv18_boxes(delta, D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
+        finally:
+            Sp.close()
+        return _box_solution(C, R, N, delta, partition, blocks, dims, types, opts, D)
     D = ctx.discretize_box(A, delta, c, r, B if U is not None else None, None if U is None else U[0],
                            None if U is None else U[1], algorithm=op["discretization"])
-    rows = np.asarray(dims, dtype=np.int32) - 1
     if opts["mode"] == "check":
         prop = opts["property"]
         ell = np.asarray(prop.constraint.a, dtype=np.float64)
@@ -508,6 +525,12 @@ def _post_bffpsv18(op, problem, opts, ctx):
             return ReachSet(Hyperrectangle(C[:, i], R[:, i]), float(t0[i]), float(t1[i]))     # reach.jl:82
         return ReachSolution([Flowpipe(_LazyReachSets(N, make))], opts, dict(centers=C, radii=R))
     C, R = ctx.bffpsv18_boxes(D["Phi"], D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
+    return _box_solution(C, R, N, delta, partition, blocks, dims, types, opts, D)
+
+
+def _box_solution(C, R, N, delta, partition, blocks, dims, types, opts, D):
+    """The `SparseReachSet{CartesianProductArray}` flowpipe of reach.jl:79 over the (centers, radii) arrays."""
+    t0, t1 = _times(N, delta)
     offs = np.concatenate([[0], np.cumsum([len(partition[b - 1]) for b in blocks])])
 
     def make(i):

@@ -214,8 +214,110 @@ class Context:
                                                 C.byref(pout), iptr(ind)))
         return np.asfortranarray(Gout[:, :pout.value]), ind
 
+    def sparse(self, A) -> "SparseSystem":
+        """Upload a sparse state matrix (scipy.sparse matrix, or dense array: its nonzeros) for the lazy-expm path."""
+        return SparseSystem(self, A)
+
     def ensemble(self, Phi, c0s, G0s, N) -> "Ensemble":
         return Ensemble(self, Phi, c0s, G0s, N)
+
+
+def _csc_fields(A):
+    """(n, colptr, rowval, nzval) of A in Julia's SparseMatrixCSC convention (1-based Int64 indices)."""
+    if hasattr(A, "tocsc"):
+        M = A.tocsc()
+        M.sort_indices()
+        n = M.shape[0]
+        assert M.shape[0] == M.shape[1], "the state matrix must be square"
+        return (n, np.ascontiguousarray(M.indptr, dtype=np.int64) + 1, np.ascontiguousarray(M.indices, dtype=np.int64) + 1,
+                np.ascontiguousarray(M.data, dtype=np.float64))
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    assert A.ndim == 2 and A.shape[1] == n, "the state matrix must be square"
+    rows, cols = np.nonzero(A.T)[1], np.nonzero(A.T)[0]          # column-major order of the nonzeros
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(colptr, cols + 1, 1)
+    colptr = np.cumsum(colptr) + 1
+    return n, colptr, np.ascontiguousarray(rows, dtype=np.int64) + 1, np.ascontiguousarray(A[rows, cols], dtype=np.float64)
+
+
+class SparseSystem:
+    """`reach_sparse`: a sparse state matrix on the device; Φ = e^{Aδ} is only ever applied, never formed
+    (`SparseMatrixExp`, discretize.jl:153-154; BFFPSV18 `:lazy_expm`, reach_blocks.jl:227-397)."""
+
+    def __init__(self, ctx: Context, A):
+        self.ctx = ctx
+        self.n, colptr, rowval, nzval = _csc_fields(A)
+        self.nnz = len(nzval)
+        self._h = C.c_void_p()
+        i64p = C.POINTER(C.c_int64)
+        ctx._check(ctx.lib.reach_sparse_create(ctx._h, self.n, self.nnz, colptr.ctypes.data_as(i64p),
+                                               rowval.ctypes.data_as(i64p), dptr(nzval), C.byref(self._h)))
+
+    def expmv(self, delta: float, X, transpose: bool = False) -> np.ndarray:
+        """e^{δA} X (or e^{δAᵀ} X) for a block of vectors X (n x R)."""
+        X = fmat(np.asarray(X, dtype=np.float64).reshape(self.n, -1))
+        Y = np.zeros_like(X, order="F")
+        self.ctx._check(self.ctx.lib.reach_expmv(self._h, float(delta), int(bool(transpose)), X.shape[1], dptr(X), self.n,
+                                                 dptr(Y), self.n))
+        return Y
+
+    def discretize_box(self, delta, c, r, B=None, cU=None, rU=None, algorithm="forward"):
+        """Returns dict(c0, r0, rE, rpsi, MU, cU, rU) -- `Context.discretize_box` without the dense matrices."""
+        n = self.n
+        alg = {"forward": 0, "backward": 1, "firstorder": 2, "nobloating": 3}.get(algorithm)
+        if alg is None:
+            raise ValueError(f"the algorithm {algorithm} is unknown")
+        c, r = fvec(c), fvec(r)
+        m, Bm = 0, None
+        if cU is not None:
+            cU, rU = fvec(cU), fvec(rU)
+            m = len(cU)
+            Bm = None if B is None else fmat(np.asarray(B, dtype=np.float64).reshape(n, -1))
+            assert Bm is None or Bm.shape == (n, m)
+        c0, r0, rE = np.zeros(n), np.zeros(n), np.zeros(n)
+        rpsi = np.zeros(n) if m else None
+        MU = np.zeros((n, m), order="F") if m else None
+        self.ctx._check(self.ctx.lib.reach_discretize_box_sparse(self._h, float(delta), alg, dptr(c), dptr(r), m, dptr(Bm), n,
+                                                                 dptr(cU), dptr(rU), dptr(c0), dptr(r0), dptr(rE), dptr(rpsi),
+                                                                 dptr(MU)))
+        return dict(c0=c0, r0=r0, rE=rE, rpsi=rpsi, MU=MU, cU=cU if m else None, rU=rU if m else None)
+
+    def bffpsv18_boxes(self, delta, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None):
+        """Lazy-expm `reach_blocks!`: (centers, radii), each (nrows, N) Fortran arrays."""
+        n = self.n
+        c0, r0 = fvec(c0), fvec(r0)
+        m = 0
+        if MU is not None:
+            MU = fmat(MU).reshape(n, -1, order="F")
+            m = MU.shape[1]
+            cU, rU, rpsi = fvec(cU), fvec(rU), fvec(rpsi)
+        else:
+            cU = rU = rpsi = None
+        rows = np.arange(n, dtype=np.int32) if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        centers = np.zeros((len(rows), int(N)), order="F")
+        radii = np.zeros((len(rows), int(N)), order="F")
+        done = C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_bffpsv18_boxes_lazy(self._h, float(delta), dptr(c0), dptr(r0), m, dptr(MU), n,
+                                                               dptr(cU), dptr(rU), dptr(rpsi), len(rows), iptr(rows), int(N),
+                                                               dptr(centers), dptr(radii), C.byref(done)))
+        return centers, radii
+
+    def timing(self):
+        ms, prod, b = C.c_double(), C.c_int64(), C.c_double()
+        self.ctx._check(self.ctx.lib.reach_sparse_timing(self._h, C.byref(ms), C.byref(prod), C.byref(b)))
+        return dict(run_ms=ms.value, products=prod.value, bytes=b.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.ctx.lib.reach_sparse_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BoxPlan:

@@ -111,6 +111,14 @@ void launch2d(Ctx* ctx, int n, dim3& grid) { grid = dim3((unsigned)ceil_div(n, 2
 
 }  // namespace
 
+// box decomposition of Ω0 on device vectors (shared with the sparse path, sparse.cu)
+void omega0_box(Ctx* ctx, int64_t n, const double* c, const double* r, const double* pc, const double* pr, const double* rE,
+                const double* uc, const double* ur, const double* rpsi, double* c0, double* r0) {
+    omega0_box_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>((int)n, c, r, pc, pr, rE, uc, ur, rpsi, c0, r0);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
 // Horner chain + doubling.  dA: n x n on the device (ld lda).  Outputs are DMats allocated by the caller (any may
 // be NULL): P0 = e^{Aδ}, P1 = Φ₁(A, δ), P2 = Φ₂(A, δ).  take_abs: use |A| entrywise (Φ₂(abs.(A), δ), discretize.jl:652).
 void expm_family(Ctx* ctx, int64_t n, const double* dA, int64_t lda, double delta, bool take_abs, DMat* P0, DMat* P1,

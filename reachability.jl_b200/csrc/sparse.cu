@@ -1,0 +1,807 @@
+// Sparse-A ("lazy matrix exponential") variants of the path: Φ = e^{Aδ} is never formed.
+//
+//   BFFPSV18 with `:lazy_expm`  -- reach_blocks!(ϕ::SparseMatrixExp, ...)       BFFPSV18/reach_blocks.jl:227-397
+//       rows of e^{kδA} come from `get_rows(ϕpowerk, bi)` (:37-38), ϕpowerk.M .= ϕpowerk.M + ϕ.M (:306)
+//   discretize with `exp_method = "lazy"` -- ϕ = SparseMatrixExp(A*δ), Φ₂ through get_columns of the 3n x 3n
+//       sparse exponential                                                      discretize.jl:153-154, 302-306
+//
+// The reference evaluates every row with a Krylov `expmv` (Expokit, tolerance 1e-7) from scratch at every step.  B200
+// design: the block of rows of interest W_k = e^{kδA}[rows, :] is kept TRANSPOSED on the device (n x R, the R values of
+// one state contiguous) and advanced by  W_kᵀ = e^{δAᵀ} W_{k-1}ᵀ  -- the same recurrence as the dense path
+// (reach_blocks.jl:217-218) -- with a scaled truncated Taylor series of sparse-matrix x dense-block products carried to
+// full double precision (‖δA‖/s <= 1, m terms until the remainder is below 2^-64).  Julia's SparseMatrixCSC of A *is* the
+// CSR of Aᵀ, so the arrays cross the ABI untouched.  Every product is one HBM/L2-bound kernel: nnz·12 B of matrix +
+// 16·n·R B of block traffic; the per-step box epilogue is a column reduction of the same block.
+#include "common.cuh"
+#include "../../include/reach.h"
+#include <cmath>
+#include <algorithm>
+
+namespace reach {
+
+void omega0_box(Ctx* ctx, int64_t n, const double* c, const double* r, const double* pc, const double* pr, const double* rE,
+                const double* uc, const double* ur, const double* rpsi, double* c0, double* r0);   // discretize.cu
+
+namespace {
+
+struct Csr {
+    int n = 0;
+    int64_t nnz = 0;
+    int* ptr = nullptr;
+    int* idx = nullptr;
+    double* val = nullptr;
+};
+
+// Tn = alpha * op(S) * T ;  Yout = Yin + Tn          op = |.| entrywise when ABS
+// Blocks are n x ld2 double2 ("row-block" layout: the R values of state i are contiguous).  Thread = (row i, double2 l2);
+// the nonzeros of a row are read by all its threads (broadcast), the gathered block rows are coalesced.
+template <bool ABS>
+__global__ void __launch_bounds__(256) spmm_taylor_kernel(Csr S, int ld2, const double2* __restrict__ T, double2* __restrict__ Tn,
+                                                          const double2* __restrict__ Yin, double2* __restrict__ Yout, double alpha) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(t / ld2), l2 = (int)(t - (int64_t)i * ld2);
+    if (i >= S.n) return;
+    double2 acc = make_double2(0.0, 0.0);
+    const int p1 = S.ptr[i + 1];
+    // four nonzeros at a time: their (index, value) loads and then their four gathers are independent, so a row costs
+    // three dependent memory round trips instead of two per nonzero; the sums keep CSR order
+    for (int p = S.ptr[i]; p < p1; p += 4) {
+        int jj[4];
+        double vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = p + u < p1;
+            jj[u] = ok ? S.idx[p + u] : i;
+            vv[u] = ok ? S.val[p + u] : 0.0;
+        }
+        double2 xx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xx[u] = T[(int64_t)jj[u] * ld2 + l2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (p + u < p1) {
+                const double v = ABS ? fabs(vv[u]) : vv[u];
+                acc.x = fma(v, xx[u].x, acc.x);
+                acc.y = fma(v, xx[u].y, acc.y);
+            }
+    }
+    acc.x *= alpha;
+    acc.y *= alpha;
+    const int64_t o = (int64_t)i * ld2 + l2;
+    if (Tn) Tn[o] = acc;
+    if (Yout) {
+        double2 y = Yin ? Yin[o] : make_double2(0.0, 0.0);
+        y.x += acc.x;
+        y.y += acc.y;
+        Yout[o] = y;
+    }
+}
+
+// X[i*ld + l] = (i == sel[l]) for l < cnt   (identity columns / unit rows of interest)
+__global__ void unit_block_kernel(int n, int ld, int cnt, const int* __restrict__ sel, double* __restrict__ X) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * ld) return;
+    const int i = (int)(t / ld), l = (int)(t - (int64_t)i * ld);
+    X[t] = (l < cnt && sel[l] == i) ? 1.0 : 0.0;
+}
+
+// Row-wise box products of a row-block Z (n x cnt, ld):  sgn[i] (+)= sum_l Z[i,l] c[l],  mag[i] (+)= sum_l |Z[i,l]| w[l].
+// One warp per row, lanes stride l, xor-shuffle tree (fixed order).
+__global__ void __launch_bounds__(256) row_box_kernel(int n, int ld, int cnt, const double* __restrict__ Z,
+                                                      const double* __restrict__ c, const double* __restrict__ w,
+                                                      double* __restrict__ sgn, double* __restrict__ mag, int accumulate) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    double a = 0.0, b = 0.0;
+    for (int l = lane; l < cnt; l += 32) {
+        const double z = Z[(int64_t)i * ld + l];
+        if (c) a = fma(z, c[l], a);
+        if (w) b = fma(fabs(z), w[l], b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        if (sgn) sgn[i] = (accumulate ? sgn[i] : 0.0) + a;
+        if (mag) mag[i] = (accumulate ? mag[i] : 0.0) + b;
+    }
+}
+
+__global__ void bump_kernel(int* ctr, int by) { *ctr += by; }
+__global__ void gather_kernel(int cnt, const int* __restrict__ sel, const double* __restrict__ v, double* __restrict__ out) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < cnt) out[l] = v[sel[l]];
+}
+__global__ void sih_vec_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = fabs(a[i]) + b[i];
+}
+__global__ void scale_vec_kernel(int n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = alpha * x[i];
+}
+
+// One step of the lazy reach_blocks! recurrence for the R rows of interest (block Wt = P_{k-1}[rows,:]ᵀ, n x ld):
+//   c_k = P c0 + cW,  r_k = |P| r0 + rW                              reach_blocks.jl:266-283 (box of the lazy sum)
+//   cW += (P MU) cU,  rW += |P MU| rU + |P| rψ                       :284-287
+// Two kernels.  `lazy_partial_kernel`: CTA (bx, by, bz) = 32 rows of interest x state slice by x quantity group bz
+// (bz = 0: P c0, |P| r0, |P| rψ; bz >= 1: the products with 8 columns of MU), 8 sub-slices per CTA, ascending j inside a
+// sub-slice; partial sums go to part[quantity][slice][l].  `lazy_finish_kernel` adds the slices in order and applies the
+// recurrences.  Every sum has a fixed order.
+constexpr int STEP_SUB = 8;
+constexpr int STEP_MCHUNK = 8;
+__global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(int n, int ld, int R, int nsl, const double* __restrict__ Wt,
+                                                                     const double* __restrict__ c0, const double* __restrict__ r0,
+                                                                     const double* __restrict__ rpsi, int m,
+                                                                     const double* __restrict__ MU /* n x m, ld n */,
+                                                                     double* __restrict__ part, int ldp) {
+    __shared__ double red[STEP_SUB][32];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int l = blockIdx.x * 32 + lx, sl = blockIdx.y, grp = blockIdx.z;
+    const bool live = l < R;
+    const int chunk = (n + nsl - 1) / nsl;
+    const int j0 = sl * chunk, j1 = min(n, j0 + chunk);
+    auto combine_store = [&](double v, int quantity) {       // sub-slices in order -> part[quantity][sl][l]
+        red[ly][lx] = v;
+        __syncthreads();
+        if (ly == 0 && live) {
+            double s = 0.0;
+            for (int q = 0; q < STEP_SUB; ++q) s += red[q][lx];
+            part[((int64_t)quantity * nsl + sl) * ldp + l] = s;
+        }
+        __syncthreads();
+    };
+    if (grp == 0) {
+        double sc = 0.0, sr = 0.0, sp = 0.0;
+        if (live)
+            for (int j = j0 + ly; j < j1; j += STEP_SUB) {
+                const double w = Wt[(int64_t)j * ld + l];
+                sc = fma(w, c0[j], sc);
+                sr = fma(fabs(w), r0[j], sr);
+                if (rpsi) sp = fma(fabs(w), rpsi[j], sp);
+            }
+        combine_store(sc, 0);
+        combine_store(sr, 1);
+        combine_store(sp, 2);
+    } else {
+        const int i0 = (grp - 1) * STEP_MCHUNK;
+        double pm[STEP_MCHUNK];
+#pragma unroll
+        for (int u = 0; u < STEP_MCHUNK; ++u) pm[u] = 0.0;
+        if (live)
+            for (int j = j0 + ly; j < j1; j += STEP_SUB) {
+                const double w = Wt[(int64_t)j * ld + l];
+#pragma unroll
+                for (int u = 0; u < STEP_MCHUNK; ++u)
+                    if (i0 + u < m) pm[u] = fma(w, MU[(int64_t)(i0 + u) * n + j], pm[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < STEP_MCHUNK; ++u)
+            if (i0 + u < m) combine_store(pm[u], 3 + i0 + u);
+    }
+}
+
+__global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(int R, int nsl, int m, const double* __restrict__ part, int ldp,
+                                                                    const double* __restrict__ cU, const double* __restrict__ rU,
+                                                                    double* __restrict__ cW, double* __restrict__ rW,
+                                                                    double* __restrict__ centers, double* __restrict__ radii,
+                                                                    const int* __restrict__ kctr, int koff) {
+    __shared__ double redc[STEP_SUB][32], redr[STEP_SUB][32];
+    // output column = device-side step counter + offset: the same captured graph serves every pair of steps
+    const int64_t col = (int64_t)(*kctr + koff) * R;
+    centers += col;
+    radii += col;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int l = blockIdx.x * 32 + lx;
+    const bool live = l < R;
+    auto slices = [&](int quantity) {
+        double s = 0.0;
+        for (int q = 0; q < nsl; ++q) s += part[((int64_t)quantity * nsl + q) * ldp + l];
+        return s;
+    };
+    double dc = 0.0, dr = 0.0;
+    if (live)
+        for (int i = ly; i < m; i += STEP_SUB) {         // inputs strided over the sub-warps, combined in order below
+            const double v = slices(3 + i);
+            dc = fma(v, cU[i], dc);
+            dr = fma(fabs(v), rU[i], dr);
+        }
+    redc[ly][lx] = dc;
+    redr[ly][lx] = dr;
+    __syncthreads();
+    if (ly == 0 && live) {
+        dc = 0.0; dr = 0.0;
+        for (int q = 0; q < STEP_SUB; ++q) { dc += redc[q][lx]; dr += redr[q][lx]; }
+        const double sc = slices(0), sr = slices(1), sp = slices(2);
+        const double cw = m > 0 ? cW[l] : 0.0, rw = m > 0 ? rW[l] : 0.0;
+        centers[l] = sc + cw;
+        radii[l] = sr + rw;
+        if (m > 0) {
+            cW[l] = cw + dc;
+            rW[l] = rw + dr + sp;
+        }
+    }
+}
+
+// step 1 and the initial input boxes: centers/radii column 0 = X̂0[rows]; Ŵ_1 = box(MU U ⊕ Eψ)[rows]  (:241-262)
+__global__ void lazy_init_kernel(int n, int R, const int* __restrict__ rows, const double* __restrict__ c0,
+                                 const double* __restrict__ r0, const double* __restrict__ rpsi, int m,
+                                 const double* __restrict__ MU, const double* __restrict__ cU, const double* __restrict__ rU,
+                                 double* __restrict__ cW, double* __restrict__ rW, double* __restrict__ centers,
+                                 double* __restrict__ radii) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= R) return;
+    const int row = rows[l];
+    centers[l] = c0[row];
+    radii[l] = r0[row];
+    if (m > 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double v = MU[(int64_t)i * n + row];
+            a = fma(v, cU[i], a);
+            b = fma(fabs(v), rU[i], b);
+        }
+        cW[l] = a;
+        rW[l] = b + rpsi[row];
+    }
+}
+
+template <typename T>
+T* dnew(Ctx* ctx, size_t count) { return (T*)ctx_malloc(ctx, std::max<size_t>(count, 1) * sizeof(T)); }
+
+}  // namespace
+
+struct SparseSys {
+    Ctx* ctx = nullptr;
+    int64_t n = 0, nnz = 0;
+    Csr At, Ar;                 // CSR of Aᵀ (= the caller's CSC of A) and CSR of A
+    double norm_row = 0, norm_col = 0;      // max abs row sum / column sum of A
+    std::vector<void*> owned;
+    double last_ms = 0;
+    int64_t last_products = 0;
+    double last_bytes = 0;
+};
+
+void sparse_free(SparseSys* S) {
+    if (!S) return;
+    for (void* p : S->owned) ctx_free(S->ctx, p);
+    delete S;
+}
+
+SparseSys* sparse_create(Ctx* ctx, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    REACH_REQUIRE(n > 0 && n < (int64_t)1 << 30 && nnz >= 0 && nnz < (int64_t)1 << 31 && colptr && (nnz == 0 || (rowval && nzval)),
+                  "reach_sparse_create: bad arguments");
+    REACH_REQUIRE(colptr[0] == 1 && colptr[n] == nnz + 1, "reach_sparse_create: colptr must be 1-based with colptr[n+1] = nnz + 1");
+    // host: 0-based int32 copies of the CSC (= CSR of Aᵀ) and the transposed structure (CSR of A), plus the norms
+    std::vector<int> tp(n + 1), ti(nnz), rp(n + 1, 0), ri(nnz);
+    std::vector<double> rv(nnz), rows_abs(n, 0.0);
+    double norm_col = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        REACH_REQUIRE(colptr[j + 1] >= colptr[j], "reach_sparse_create: colptr must be non-decreasing");
+        tp[j] = (int)(colptr[j] - 1);
+        double s = 0.0;
+        for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) {
+            const int64_t i = rowval[p] - 1;
+            REACH_REQUIRE(i >= 0 && i < n, "reach_sparse_create: row index out of range");
+            REACH_REQUIRE(std::isfinite(nzval[p]), "reach_sparse_create: non-finite entry");
+            ti[p] = (int)i;
+            rp[i + 1]++;
+            s += std::fabs(nzval[p]);
+            rows_abs[i] += std::fabs(nzval[p]);
+        }
+        norm_col = std::max(norm_col, s);
+    }
+    tp[n] = (int)nnz;
+    for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
+    std::vector<int> fill(rp.begin(), rp.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = tp[j]; p < tp[j + 1]; ++p) {
+            const int q = fill[ti[p]]++;
+            ri[q] = (int)j;
+            rv[q] = nzval[p];
+        }
+    SparseSys* S = new SparseSys();
+    S->ctx = ctx; S->n = n; S->nnz = nnz;
+    S->norm_col = norm_col;
+    S->norm_row = n ? *std::max_element(rows_abs.begin(), rows_abs.end()) : 0.0;
+    try {
+        cudaStream_t st = ctx->stream;
+        auto up = [&](Csr& C, const std::vector<int>& p, const std::vector<int>& ix, const double* v) {
+            C.n = (int)n; C.nnz = nnz;
+            C.ptr = dnew<int>(ctx, n + 1); S->owned.push_back(C.ptr);
+            C.idx = dnew<int>(ctx, nnz); S->owned.push_back(C.idx);
+            C.val = dnew<double>(ctx, nnz); S->owned.push_back(C.val);
+            REACH_CUDA(cudaMemcpyAsync(C.ptr, p.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st));
+            if (nnz) {
+                REACH_CUDA(cudaMemcpyAsync(C.idx, ix.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+                REACH_CUDA(cudaMemcpyAsync(C.val, v, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+            }
+        };
+        up(S->At, tp, ti, nzval);
+        up(S->Ar, rp, ri, rv.data());
+        REACH_CUDA(cudaStreamSynchronize(st));      // the host vectors die here
+    } catch (...) {
+        sparse_free(S);
+        throw;
+    }
+    return S;
+}
+
+namespace {
+
+int64_t block_ld(int64_t R) { return round_up(std::max<int64_t>(R, 1), 4); }
+
+template <bool ABS>
+void spmm(SparseSys* S, const Csr& M, int64_t ld, const double* T, double* Tn, const double* Yin, double* Yout, double alpha) {
+    const int ld2 = (int)(ld / 2);
+    const int64_t threads = S->n * ld2;
+    spmm_taylor_kernel<ABS><<<(unsigned)ceil_div(threads, 256), 256, 0, S->ctx->stream>>>(
+        M, ld2, (const double2*)T, (double2*)Tn, (const double2*)Yin, (double2*)Yout, alpha);
+    REACH_CUDA(cudaGetLastError());
+    S->ctx->launches++;
+    S->last_products++;
+    S->last_bytes += 12.0 * (double)S->nnz + 8.0 * (double)S->n * ld * ((Tn ? 1 : 0) + (Yout ? 2 : 0) + 1);
+}
+
+// scaling s and number of Taylor terms m for theta_total = ‖δ M‖: the pair with the fewest products s*m among
+// theta = theta_total / s <= 2 (larger theta lets the alternating series cancel digits), remainder < 2^-64
+int taylor_terms(double theta) {
+    double term = 1.0;
+    int m = 0;
+    while (m < 80) {
+        ++m;
+        term *= theta / m;
+        if (theta < m + 1 && term / (1.0 - theta / (m + 1)) < 5.4e-20) break;
+    }
+    return m;
+}
+void taylor_plan(double theta_total, int& s, int& m) {
+    const int s0 = (int)std::max(1.0, std::ceil(theta_total / 2.0));
+    s = s0;
+    m = taylor_terms(theta_total / s0);
+    for (int c = s0 + 1; c <= 4 * s0 + 4; ++c) {
+        const int mc = taylor_terms(theta_total / c);
+        if ((int64_t)c * mc < (int64_t)s * m) { s = c; m = mc; }
+    }
+}
+
+// W <- e^{δ op(M)} W for a row-block W (n x ld); T0, T1, W2: workspaces of the same size.  Returns the buffer that holds
+// the result (W or W2: the accumulation ping-pongs so that no product reads a block it is writing).
+double* expm_action(SparseSys* S, const Csr& M, double delta, int64_t ld, double* W, double* W2, double* T0, double* T1) {
+    int s, m;
+    taylor_plan(std::fabs(delta) * std::max(S->norm_row, S->norm_col), s, m);
+    for (int rep = 0; rep < s; ++rep) {
+        spmm<false>(S, M, ld, W, T0, W, W2, delta / s);                                   // term 1: W2 = W + (δ/s) M W
+        double* t = T0;
+        double* tn = T1;
+        for (int j = 2; j <= m; ++j) {
+            spmm<false>(S, M, ld, t, tn, W2, W2, delta / (s * (double)j));                // term j, accumulated in place
+            std::swap(t, tn);
+        }
+        std::swap(W, W2);
+    }
+    return W;
+}
+
+// y = Φ₂(|A|, δ) v = Σ_{i>=0} δ^{i+2}/(i+2)! |A|^i v   (discretize.jl:296-301 for the nonnegative matrix |A|; all terms are
+// nonnegative when v is, so the plain series is stable).  v, y, t0, t1: n x 4 row-blocks (ld 4, column 0 used).
+void phi2abs_action(SparseSys* S, double delta, const double* v, double* y, double* t0, double* t1) {
+    const int64_t n = S->n;
+    cudaStream_t st = S->ctx->stream;
+    const unsigned g = (unsigned)ceil_div(4 * n, 256);
+    scale_vec_kernel<<<g, 256, 0, st>>>((int)(4 * n), delta * delta / 2.0, v, t0);        // term 0
+    REACH_CUDA(cudaMemcpyAsync(y, t0, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
+    const double theta = std::fabs(delta) * std::max(S->norm_row, S->norm_col);
+    double bound = 1.0;     // (i+2)!-normalised size of term i relative to term 0
+    double* t = t0;
+    double* tn = t1;
+    for (int i = 1; i < 400; ++i) {
+        spmm<true>(S, S->Ar, 4, t, tn, y, y, delta / (i + 2.0));
+        std::swap(t, tn);
+        bound *= theta / (i + 2.0);
+        if (bound < 5.4e-20 && theta / (i + 3.0) < 0.5) break;
+    }
+    S->ctx->launches++;
+}
+
+}  // namespace
+
+// Y = e^{δA} X (transpose = 0) or e^{δAᵀ} X (1) for host column-major blocks X, Y (n x R).
+void sparse_expmv(SparseSys* S, double delta, int transpose_op, int64_t R, const double* X, int64_t ldx, double* Y, int64_t ldy) {
+    Ctx* ctx = S->ctx;
+    const int64_t n = S->n, ld = block_ld(R);
+    REACH_REQUIRE(R >= 1 && X && Y && ldx >= n && ldy >= n, "reach_expmv: bad arguments");
+    cudaStream_t st = ctx->stream;
+    std::vector<double> hb((size_t)n * ld, 0.0);
+    for (int64_t l = 0; l < R; ++l)
+        for (int64_t i = 0; i < n; ++i) hb[(size_t)i * ld + l] = X[l * ldx + i];
+    double* buf[4];
+    for (auto& b : buf) b = dnew<double>(ctx, (size_t)n * ld);
+    try {
+        REACH_CUDA(cudaMemcpyAsync(buf[0], hb.data(), sizeof(double) * n * ld, cudaMemcpyHostToDevice, st));
+        S->last_products = 0; S->last_bytes = 0;
+        REACH_CUDA(cudaEventRecord(ctx->ev0, st));
+        double* res = expm_action(S, transpose_op ? S->At : S->Ar, delta, ld, buf[0], buf[1], buf[2], buf[3]);
+        REACH_CUDA(cudaEventRecord(ctx->ev1, st));
+        REACH_CUDA(cudaMemcpyAsync(hb.data(), res, sizeof(double) * n * ld, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        S->last_ms = ms;
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        for (auto& b : buf) ctx_free(ctx, b);
+        throw;
+    }
+    for (auto& b : buf) ctx_free(ctx, b);
+    for (int64_t l = 0; l < R; ++l)
+        for (int64_t i = 0; i < n; ++i) Y[l * ldy + i] = hb[(size_t)i * ld + l];
+}
+
+// discretize_interpolation (forward / backward) + box decomposition of Ω0 with A sparse and Φ never formed.
+void sparse_discretize_box(SparseSys* S, double delta, int32_t algorithm, const double* c, const double* r, int64_t m,
+                           const double* B, int64_t ldb, const double* cU, const double* rU, double* c0, double* r0,
+                           double* rE, double* rpsi, double* MU) {
+    Ctx* ctx = S->ctx;
+    const int64_t n = S->n;
+    if (algorithm != REACH_FORWARD && algorithm != REACH_BACKWARD) {
+        if (algorithm == REACH_FIRSTORDER || algorithm == REACH_NOBLOATING)
+            throw Error(REACH_EUNSUPPORTED, "reach_discretize_box_sparse: only the forward / backward interpolation models run on the sparse path");
+        throw Error(REACH_EINVAL, "the algorithm is unknown");
+    }
+    REACH_REQUIRE(c && r && m >= 0 && (m == 0 || (cU && rU)), "reach_discretize_box_sparse: bad X0 / U");
+    REACH_REQUIRE(!B || ldb >= n, "reach_discretize_box_sparse: bad ldb");
+    REACH_REQUIRE(B || m == 0 || m == n, "reach_discretize_box_sparse: B == NULL means identity and needs m == n");
+    cudaStream_t st = ctx->stream;
+    const bool backward = algorithm == REACH_BACKWARD;
+    // columns of Φ (and A²) that matter for |Φ| r, |A²| r: those with r_j != 0 (the others contribute exact zeros)
+    std::vector<int> J;
+    for (int64_t j = 0; j < n; ++j) {
+        REACH_REQUIRE(r[j] >= 0.0 && std::isfinite(r[j]) && std::isfinite(c[j]), "reach_discretize_box_sparse: bad X0");
+        if (r[j] != 0.0) J.push_back((int)j);
+    }
+    const int64_t CH = std::min<int64_t>(256, std::max<int64_t>(4, (int64_t)J.size()));
+    const int64_t ldJ = block_ld(CH), ldm = block_ld(std::max<int64_t>(m, 1));
+    std::vector<void*> tmp;
+    auto alloc = [&](size_t count) { double* p = dnew<double>(ctx, count); tmp.push_back(p); return p; };
+    auto free_all = [&]() { for (void* p : tmp) ctx_free(ctx, p); tmp.clear(); };
+    try {
+        // n-vectors live in n x 4 row-blocks (column 0 used): the same SpMM kernel serves as SpMV
+        const size_t nv = (size_t)n * 4;
+        double* vc = alloc(nv); double* va = alloc(nv); double* vb = alloc(nv); double* vt0 = alloc(nv); double* vt1 = alloc(nv);
+        double* vw = alloc(nv); double* vw2 = alloc(nv);
+        double* pc = alloc(n); double* pr = alloc(n); double* a1 = alloc(n); double* b1 = alloc(n); double* s1 = alloc(nv);
+        double* dE = alloc(nv); double* dr = alloc(n); double* dc = alloc(n);
+        double* uc = alloc(n); double* ur = alloc(n); double* a2 = alloc(n); double* b2 = alloc(n); double* s2 = alloc(nv);
+        double* dpsi = alloc(nv); double* dc0 = alloc(n); double* dr0 = alloc(n);
+        double* ZJ[4];
+        for (auto& z : ZJ) z = alloc((size_t)n * ldJ);
+        int* dsel = (int*)alloc((size_t)(CH + 1) / 2 + 1);
+        double* dwt = alloc(CH);
+        std::vector<double> hv(nv, 0.0);
+        for (int64_t i = 0; i < n; ++i) hv[(size_t)i * 4] = c[i];
+        REACH_CUDA(cudaMemcpyAsync(vc, hv.data(), sizeof(double) * nv, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(dc, c, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(dr, r, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        const unsigned gw = (unsigned)ceil_div(n * 32, 256), gv = (unsigned)ceil_div(n, 256);
+        auto col0 = [&](const double* blk, double* out) {       // column 0 of an n x 4 block -> dense vector
+            REACH_CUDA(cudaMemcpy2DAsync(out, 8, blk, 32, 8, n, cudaMemcpyDeviceToDevice, st));
+        };
+        // Φ c   (centre of ΦX0, discretize.jl:679,685)
+        REACH_CUDA(cudaMemcpyAsync(vw, vc, sizeof(double) * nv, cudaMemcpyDeviceToDevice, st));
+        double* phic = expm_action(S, S->Ar, delta, 4, vw, vw2, vt0, vt1);
+        col0(phic, pc);
+        // centre part of (A²)X0 (forward, :655) or (A²Φ)X0 (backward, :657)
+        spmm<false>(S, S->Ar, 4, backward ? phic : vc, va, nullptr, nullptr, 1.0);
+        spmm<false>(S, S->Ar, 4, va, vb, nullptr, nullptr, 1.0);
+        col0(vb, a1);
+        // radius parts: |Φ| r and |A²| r (|A²Φ| r), column chunk by column chunk of the identity
+        REACH_CUDA(cudaMemsetAsync(pr, 0, sizeof(double) * n, st));
+        REACH_CUDA(cudaMemsetAsync(b1, 0, sizeof(double) * n, st));
+        for (size_t j0 = 0; j0 < J.size(); j0 += (size_t)CH) {
+            const int cnt = (int)std::min<size_t>((size_t)CH, J.size() - j0);
+            REACH_CUDA(cudaMemcpyAsync(dsel, J.data() + j0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
+            gather_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(cnt, dsel, dr, dwt);
+            unit_block_kernel<<<(unsigned)ceil_div(n * ldJ, 256), 256, 0, st>>>((int)n, (int)ldJ, cnt, dsel, ZJ[0]);
+            double* E = ZJ[0];
+            double* PhiJ = nullptr;
+            if (backward) {         // Φ E_J first, then A², sharing the block with |Φ| r
+                PhiJ = expm_action(S, S->Ar, delta, ldJ, ZJ[0], ZJ[1], ZJ[2], ZJ[3]);
+                row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldJ, cnt, PhiJ, nullptr, dwt, nullptr, pr, 1);
+                double* other = PhiJ == ZJ[0] ? ZJ[1] : ZJ[0];
+                spmm<false>(S, S->Ar, ldJ, PhiJ, ZJ[2], nullptr, nullptr, 1.0);
+                spmm<false>(S, S->Ar, ldJ, ZJ[2], other, nullptr, nullptr, 1.0);
+                row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldJ, cnt, other, nullptr, dwt, nullptr, b1, 1);
+            } else {
+                spmm<false>(S, S->Ar, ldJ, E, ZJ[2], nullptr, nullptr, 1.0);
+                spmm<false>(S, S->Ar, ldJ, ZJ[2], ZJ[3], nullptr, nullptr, 1.0);
+                row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldJ, cnt, ZJ[3], nullptr, dwt, nullptr, b1, 1);
+                PhiJ = expm_action(S, S->Ar, delta, ldJ, ZJ[0], ZJ[1], ZJ[2], ZJ[3]);
+                row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldJ, cnt, PhiJ, nullptr, dwt, nullptr, pr, 1);
+            }
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches += 4;
+            REACH_CUDA(cudaStreamSynchronize(st));       // J chunk upload buffer is reused
+        }
+        // Einit radius = Φ₂(|A|, δ) sih((A²)X0)
+        REACH_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * nv, st));
+        sih_vec_kernel<<<gv, 256, 0, st>>>((int)n, a1, b1, a2);                   // a2 used as scratch
+        REACH_CUDA(cudaMemcpy2DAsync(s1, 32, a2, 8, 8, n, cudaMemcpyDeviceToDevice, st));
+        phi2abs_action(S, delta, s1, dE, vt0, vt1);
+        double* rEv = alloc(n);
+        col0(dE, rEv);
+        double* rpsiv = alloc(n);
+        if (m > 0) {
+            // B in row-block layout (identity when B == NULL), A B, box of (A B) U and of δ B U
+            std::vector<double> hB((size_t)n * ldm, 0.0);
+            for (int64_t i = 0; i < n; ++i)
+                for (int64_t l = 0; l < m; ++l) hB[(size_t)i * ldm + l] = B ? B[l * ldb + i] : (i == l ? 1.0 : 0.0);
+            double* dB = alloc((size_t)n * ldm);
+            double* dAB = alloc((size_t)n * ldm);
+            double* dcu = alloc(m); double* dru = alloc(m);
+            REACH_CUDA(cudaMemcpyAsync(dB, hB.data(), sizeof(double) * n * ldm, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpyAsync(dcu, cU, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpyAsync(dru, rU, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+            spmm<false>(S, S->Ar, ldm, dB, dAB, nullptr, nullptr, 1.0);            // A * U0 = (A B) U     :671
+            row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldm, (int)m, dAB, dcu, dru, a2, b2, 0);
+            REACH_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * nv, st));
+            sih_vec_kernel<<<gv, 256, 0, st>>>((int)n, a2, b2, uc);               // uc as scratch
+            REACH_CUDA(cudaMemcpy2DAsync(s2, 32, uc, 8, 8, n, cudaMemcpyDeviceToDevice, st));
+            phi2abs_action(S, delta, s2, dpsi, vt0, vt1);                          // Eψ0 radius
+            col0(dpsi, rpsiv);
+            row_box_kernel<<<gw, 256, 0, st>>>((int)n, (int)ldm, (int)m, dB, dcu, dru, a2, b2, 0);   // box of B U
+            scale_vec_kernel<<<gv, 256, 0, st>>>((int)n, delta, a2, uc);          // δ U0
+            scale_vec_kernel<<<gv, 256, 0, st>>>((int)n, std::fabs(delta), b2, ur);
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches += 5;
+            REACH_CUDA(cudaStreamSynchronize(st));       // hB dies here
+        }
+        omega0_box(ctx, n, dc, dr, pc, pr, rEv, m > 0 ? uc : nullptr, ur, rpsiv, dc0, dr0);
+        auto down = [&](double* dst, const double* src) {
+            if (dst) REACH_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, st));
+        };
+        down(c0, dc0); down(r0, dr0); down(rE, rEv);
+        if (m > 0) down(rpsi, rpsiv);
+        REACH_CUDA(cudaStreamSynchronize(st));
+        if (m > 0 && MU)
+            for (int64_t l = 0; l < m; ++l)
+                for (int64_t i = 0; i < n; ++i) MU[l * n + i] = delta * (B ? B[l * ldb + i] : (i == l ? 1.0 : 0.0));
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        free_all();
+        throw;
+    }
+    free_all();
+}
+
+// reach_blocks! for a SparseMatrixExp (lazy rows), box blocks: see the header of this file.
+void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
+                           int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
+                           const int32_t* rows, int64_t N, double* centers, double* radii) {
+    Ctx* ctx = S->ctx;
+    const int64_t n = S->n;
+    REACH_REQUIRE(c0 && r0 && N >= 1 && centers && radii, "reach_bffpsv18_boxes_lazy: bad arguments");
+    if (m == 0 || !MU) { m = 0; MU = nullptr; }
+    REACH_REQUIRE(m == 0 || (cU && rU && rpsi && ldmu >= n), "reach_bffpsv18_boxes_lazy: inputs need MU, cU, rU, rpsi");
+    std::vector<int> hrows;
+    if (rows) {
+        REACH_REQUIRE(nrows >= 1, "reach_bffpsv18_boxes_lazy: nrows must be positive");
+        for (int64_t l = 0; l < nrows; ++l) {
+            REACH_REQUIRE(rows[l] >= 0 && rows[l] < n, "reach_bffpsv18_boxes_lazy: row index out of range");
+            hrows.push_back(rows[l]);
+        }
+    } else {
+        nrows = n;
+        for (int64_t l = 0; l < n; ++l) hrows.push_back((int)l);
+    }
+    const int64_t R = nrows, ld = block_ld(R);
+    cudaStream_t st = ctx->stream;
+    std::vector<void*> tmp;
+    auto alloc = [&](size_t count) { double* p = dnew<double>(ctx, count); tmp.push_back(p); return p; };
+    auto free_all = [&]() { for (void* p : tmp) ctx_free(ctx, p); tmp.clear(); };
+    try {
+        double* W[4];
+        for (auto& w : W) w = alloc((size_t)n * ld);
+        double* dC = alloc((size_t)R * N); double* dR = alloc((size_t)R * N);
+        double* dc0 = alloc(n); double* dr0 = alloc(n); double* dpsi = alloc(n);
+        double* dMU = alloc((size_t)n * std::max<int64_t>(m, 1)); double* dcu = alloc(std::max<int64_t>(m, 1));
+        double* dru = alloc(std::max<int64_t>(m, 1));
+        double* cW = alloc(R); double* rW = alloc(R);
+        // epilogue geometry: ~2000 CTAs over (row chunks, state slices, quantity groups)
+        const unsigned gx = (unsigned)ceil_div(R, 32);
+        const int gz = 1 + (int)ceil_div(m, STEP_MCHUNK);
+        const int nsl = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(148, ceil_div(n, 64)), 2048 / ((int64_t)gx * gz)));
+        const int64_t ldp = round_up(R, 32);
+        double* part = alloc((size_t)(3 + m) * nsl * ldp);
+        int* drows = (int*)alloc((size_t)(R + 1) / 2 + 1);
+        REACH_CUDA(cudaMemcpyAsync(dc0, c0, n * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(dr0, r0, n * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(drows, hrows.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+        if (m > 0) {
+            REACH_CUDA(cudaMemcpyAsync(dpsi, rpsi, n * 8, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpy2DAsync(dMU, n * 8, MU, ldmu * 8, n * 8, m, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpyAsync(dcu, cU, m * 8, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpyAsync(dru, rU, m * 8, cudaMemcpyHostToDevice, st));
+        }
+        S->last_products = 0; S->last_bytes = 0;
+        REACH_CUDA(cudaEventRecord(ctx->ev0, st));
+        lazy_init_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>((int)n, (int)R, drows, dc0, dr0, dpsi, (int)m, dMU, dcu, dru,
+                                                                     cW, rW, dC, dR);
+        unit_block_kernel<<<(unsigned)ceil_div(n * ld, 256), 256, 0, st>>>((int)n, (int)ld, (int)R, drows, W[0]);
+        ctx->launches += 2;
+        double* cur = W[0];
+        int* kctr = (int*)alloc(1);
+        const int one = 1;
+        REACH_CUDA(cudaMemcpyAsync(kctr, &one, sizeof(int), cudaMemcpyHostToDevice, st));     // next output column (0-based)
+        auto one_step = [&](int koff) {
+            // rows of e^{(k-1)δA}: one more factor e^{δAᵀ} on the transposed block     (:306, :37-38)
+            double* a = cur;
+            double* b = nullptr;
+            double* t0 = nullptr;
+            double* t1 = nullptr;
+            for (auto& w : W) {
+                if (w == a) continue;
+                if (!b) b = w; else if (!t0) t0 = w; else t1 = w;
+            }
+            cur = expm_action(S, S->At, delta, ld, a, b, t0, t1);
+            lazy_partial_kernel<<<dim3(gx, (unsigned)nsl, (unsigned)gz), 32 * STEP_SUB, 0, st>>>(
+                (int)n, (int)ld, (int)R, nsl, cur, dc0, dr0, m > 0 ? dpsi : nullptr, (int)m, dMU, part, (int)ldp);
+            lazy_finish_kernel<<<gx, 32 * STEP_SUB, 0, st>>>((int)R, nsl, (int)m, part, (int)ldp, dcu, dru, cW, rW, dC, dR,
+                                                             kctr, koff);
+            REACH_CUDA(cudaGetLastError());
+            ctx->launches += 2;
+        };
+        // The step is launch-bound (two dozen ~3 us kernels): two consecutive steps -- after which the buffer rotation
+        // repeats -- are captured once into a CUDA graph and replayed; the output column comes from a device counter.
+        int64_t steps = N - 1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        if (steps >= 6 && !getenv("REACH_LAZY_NO_GRAPH")) {
+            double* cur0 = cur;
+            const uint64_t l0 = ctx->launches;
+            const int64_t p0 = S->last_products;
+            const double b0 = S->last_bytes;
+            REACH_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            cudaError_t cap = cudaSuccess;
+            try {
+                one_step(0);
+                one_step(1);
+                bump_kernel<<<1, 1, 0, st>>>(kctr, 2);
+            } catch (...) {
+                cap = cudaErrorUnknown;
+            }
+            const cudaError_t endc = cudaStreamEndCapture(st, &graph);
+            if (cap != cudaSuccess || endc != cudaSuccess || cur != cur0) {
+                if (graph) cudaGraphDestroy(graph);
+                throw Error(2, "reach_bffpsv18_boxes_lazy: CUDA graph capture of the step failed");
+            }
+            const cudaError_t inst = cudaGraphInstantiate(&gexec, graph, nullptr, nullptr, 0);
+            if (inst != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                throw Error(2, std::string("reach_bffpsv18_boxes_lazy: cudaGraphInstantiate: ") + cudaGetErrorString(inst));
+            }
+            const int64_t pairs = steps / 2;
+            const uint64_t per_l = ctx->launches - l0 + 1;
+            const int64_t per_p = S->last_products - p0;
+            const double per_b = S->last_bytes - b0;
+            ctx->launches = l0; S->last_products = p0; S->last_bytes = b0;
+            for (int64_t q = 0; q < pairs; ++q) {
+                const cudaError_t le = cudaGraphLaunch(gexec, st);
+                if (le != cudaSuccess) {
+                    cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph);
+                    throw Error(2, std::string("reach_bffpsv18_boxes_lazy: cudaGraphLaunch: ") + cudaGetErrorString(le));
+                }
+            }
+            ctx->launches += per_l * pairs; S->last_products += per_p * pairs; S->last_bytes += per_b * pairs;
+            steps -= 2 * pairs;
+        }
+        for (int64_t q = 0; q < steps; ++q) {
+            one_step(0);
+            bump_kernel<<<1, 1, 0, st>>>(kctr, 1);
+            ctx->launches++;
+        }
+        REACH_CUDA(cudaGetLastError());
+        REACH_CUDA(cudaEventRecord(ctx->ev1, st));
+        REACH_CUDA(cudaMemcpyAsync(centers, dC, sizeof(double) * R * N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(radii, dR, sizeof(double) * R * N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
+        float ms = 0;
+        REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        S->last_ms = ms;
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        free_all();
+        throw;
+    }
+    free_all();
+}
+
+}  // namespace reach
+
+// =========================================================================================================
+// C ABI (include/reach.h)
+// =========================================================================================================
+namespace reach { Ctx* ctx_of(reach_ctx* h); }
+using namespace reach;
+
+struct reach_sparse {
+    SparseSys* s;
+    Ctx* ctx;
+};
+
+#define SP_BEGIN(ctx)                                      \
+    if (!(ctx)) return REACH_EINVAL;                       \
+    try {                                                  \
+        REACH_CUDA(cudaSetDevice((ctx)->device));
+#define SP_END(ctx)                                                                               \
+    }                                                                                             \
+    catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+
+extern "C" {
+
+int32_t reach_sparse_create(reach_ctx* h, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                            const double* nzval, reach_sparse** out) {
+    if (!h || !out) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    *out = nullptr;
+    SP_BEGIN(ctx)
+    SparseSys* s = sparse_create(ctx, n, nnz, colptr, rowval, nzval);
+    *out = new reach_sparse{s, ctx};
+    return REACH_OK;
+    SP_END(ctx)
+}
+
+void reach_sparse_free(reach_sparse* sp) {
+    if (!sp) return;
+    cudaSetDevice(sp->ctx->device);
+    cudaStreamSynchronize(sp->ctx->stream);
+    sparse_free(sp->s);
+    delete sp;
+}
+
+int32_t reach_expmv(reach_sparse* sp, double delta, int32_t transpose_op, int64_t R, const double* X, int64_t ldx, double* Y,
+                    int64_t ldy) {
+    if (!sp) return REACH_EINVAL;
+    SP_BEGIN(sp->ctx)
+    sparse_expmv(sp->s, delta, transpose_op, R, X, ldx, Y, ldy);
+    return REACH_OK;
+    SP_END(sp->ctx)
+}
+
+int32_t reach_discretize_box_sparse(reach_sparse* sp, double delta, int32_t algorithm, const double* c, const double* r,
+                                    int64_t m, const double* B, int64_t ldb, const double* cU, const double* rU, double* c0,
+                                    double* r0, double* rE, double* rpsi, double* MU) {
+    if (!sp) return REACH_EINVAL;
+    SP_BEGIN(sp->ctx)
+    sparse_discretize_box(sp->s, delta, algorithm, c, r, m, B, ldb, cU, rU, c0, r0, rE, rpsi, MU);
+    return REACH_OK;
+    SP_END(sp->ctx)
+}
+
+int32_t reach_bffpsv18_boxes_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m,
+                                  const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                                  int64_t nrows, const int32_t* rows, int64_t N, double* centers, double* radii,
+                                  int64_t* steps_done) {
+    if (!sp) return REACH_EINVAL;
+    SP_BEGIN(sp->ctx)
+    sparse_bffpsv18_boxes(sp->s, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii);
+    if (steps_done) *steps_done = N;
+    return REACH_OK;
+    SP_END(sp->ctx)
+}
+
+int32_t reach_sparse_timing(reach_sparse* sp, double* run_ms, int64_t* products, double* bytes) {
+    if (!sp) return REACH_EINVAL;
+    if (run_ms) *run_ms = sp->s->last_ms;
+    if (products) *products = sp->s->last_products;
+    if (bytes) *bytes = sp->s->last_bytes;
+    return REACH_OK;
+}
+
+}  // extern "C"

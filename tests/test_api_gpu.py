@@ -149,3 +149,22 @@ def test_unsupported_inputs_raise_instead_of_falling_back():
     with pytest.raises(ReachError) as ei:
         solve(IVP(LCS(A), Ball2Stub(np.ones(4), 0.1)), Options(T=0.1), op=GLGM06())     # :199-200 needs LazySets on the host
     assert ei.value.code == 3
+
+
+def test_lazy_exp_method_runs_the_sparse_path():                            # BFFPSV18(:exp_method => "lazy"), discretize.jl:153-154
+    import scipy.sparse as sp
+    g = np.random.default_rng(3)
+    n = 12
+    Ad = np.diag(-g.uniform(0.5, 2.0, n)) + np.diag(g.standard_normal(n - 1) * 0.3, 1) + np.diag(g.standard_normal(n - 1) * 0.3, -1)
+    Bd = g.standard_normal((n, 1))
+    prob = lambda Amat: IVP(CLCCS(Amat, Bd, None, Interval(0.9, 1.1)), BallInf(np.ones(n), 0.05))
+    op = lambda method: BFFPSV18(δ=0.02, vars=[1, 4, 12], exp_method=method)
+    dense = solve(prob(Ad), Options(T=0.4), op=op("base"))
+    lazy = solve(prob(sp.csc_matrix(Ad)), Options(T=0.4), op=op("lazy"))
+    lazy_dense_input = solve(prob(Ad), Options(T=0.4), op=op("lazy"))
+    assert_close(lazy.arrays["centers"], dense.arrays["centers"], "centres")
+    assert_close(lazy.arrays["radii"], dense.arrays["radii"], "radii")
+    assert np.array_equal(lazy_dense_input.arrays["radii"], lazy.arrays["radii"])
+    assert len(lazy.flowpipes[0].reachsets) == 20 and dim(set_of(lazy.flowpipes[0].reachsets[3])) == 3
+    with pytest.raises(ValueError):
+        solve(prob(Ad), Options(T=0.4), op=op("krylov"))                  # ArgumentError: unknown method (discretize.jl:158)

@@ -1,0 +1,135 @@
+"""GPU parity: the sparse-A / lazy-expm variants (`reach_sparse_*`, `reach_expmv`, `reach_discretize_box_sparse`,
+`reach_bffpsv18_boxes_lazy`) against the oracle.
+
+Reference behaviour: BFFPSV18 with `:lazy_expm` (BFFPSV18/reach_blocks.jl:227-397, rows of exp(kδA) through
+`get_rows`) and `discretize` with a lazy exponential (discretize.jl:153-154, 302-306).  The oracle evaluates the same
+quantities with dense matrix exponentials (`bffpsv18_reach`, `bffpsv18_reach_lazy` literal restatement, `discretize_box`);
+tolerance 1e-10 relative + 1e-12 absolute as everywhere (tests/util.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import reach_oracle as orc
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _sparse_system(seed, n, density=0.05, stiff=3.0):
+    g = np.random.default_rng(seed)
+    M = sp.random(n, n, density=density, random_state=np.random.RandomState(seed), format="csc")
+    M.data = g.standard_normal(len(M.data))
+    A = M.toarray()
+    np.fill_diagonal(A, 0.0)
+    A -= np.diag(g.uniform(0.5, stiff, n) + np.abs(A).sum(axis=1))      # diagonally dominant, stable
+    return A
+
+
+@pytest.mark.parametrize("n,R,delta,transpose", [(7, 1, 0.1, False), (40, 5, 0.05, True), (123, 33, 0.02, False),
+                                                 (64, 64, 0.7, True)])
+def test_expmv_matches_dense_expm(ctx, n, R, delta, transpose):
+    A = _sparse_system(n, n)
+    X = np.random.default_rng(n + 1).standard_normal((n, R))
+    S = ctx.sparse(sp.csc_matrix(A))
+    Y = S.expmv(delta, X, transpose=transpose)
+    Phi = orc.exp_Adelta(A, delta)
+    assert_close(Y, (Phi.T if transpose else Phi) @ X, "expmv")
+    S.close()
+
+
+def test_sparse_create_accepts_dense_and_rejects_bad_csc(ctx):
+    from reachability_jl_b200 import ReachError
+    import ctypes as C
+    A = _sparse_system(3, 12)
+    S1, S2 = ctx.sparse(A), ctx.sparse(sp.csc_matrix(A))
+    x = np.arange(12.0)
+    assert np.array_equal(S1.expmv(0.1, x), S2.expmv(0.1, x))
+    S1.close(); S2.close()
+    colptr = np.array([1, 2, 4], dtype=np.int64)         # colptr[n] != nnz + 1
+    rowval = np.array([1, 2], dtype=np.int64)
+    val = np.ones(2)
+    h = C.c_void_p()
+    i64p = C.POINTER(C.c_int64)
+    rc = ctx.lib.reach_sparse_create(ctx._h, 2, 2, colptr.ctypes.data_as(i64p), rowval.ctypes.data_as(i64p),
+                                     val.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h))
+    assert rc == 1 and not h.value
+
+
+@pytest.mark.parametrize("n,m,algorithm,sparse_r", [(30, 0, "forward", False), (45, 2, "forward", True),
+                                                    (45, 2, "backward", False), (18, 18, "forward", False)])
+def test_sparse_discretize_matches_dense_oracle(ctx, n, m, algorithm, sparse_r):
+    g = np.random.default_rng(100 + n + m)
+    A = _sparse_system(n, n)
+    c = g.standard_normal(n)
+    r = np.abs(g.standard_normal(n)) * 0.1
+    if sparse_r:
+        r[n // 3:] = 0.0                                  # only some columns of Φ matter for |Φ| r
+    B = U = None
+    if m:
+        B = None if m == n else g.standard_normal((n, m))
+        U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.2)
+    D = orc.discretize_box(A, orc.Box(c, r), 0.02, B, U, algorithm=algorithm)
+    S = ctx.sparse(sp.csc_matrix(A))
+    d = S.discretize_box(0.02, c, r, B, None if U is None else U.c, None if U is None else U.r, algorithm=algorithm)
+    assert_close(d["c0"], D.c0, "c0")
+    assert_close(d["r0"], D.r0, "r0")
+    assert_close(d["rE"], D.rE, "rE")
+    if m:
+        assert_close(d["rpsi"], D.rpsi, "rpsi")
+        assert_close(d["MU"], D.MU, "MU")
+    S.close()
+
+
+def test_sparse_discretize_rejects_other_models(ctx):
+    from reachability_jl_b200 import ReachError
+    S = ctx.sparse(_sparse_system(1, 6))
+    with pytest.raises(ReachError) as ei:
+        S.discretize_box(0.01, np.zeros(6), np.ones(6), algorithm="firstorder")
+    assert ei.value.code == 3
+    with pytest.raises(ValueError):
+        S.discretize_box(0.01, np.zeros(6), np.ones(6), algorithm="sideways")
+    S.close()
+
+
+@pytest.mark.parametrize("n,m,N,rows", [(24, 0, 12, None), (37, 2, 25, [0, 5, 36]), (80, 3, 40, list(range(10, 50))),
+                                        (16, 1, 1, [3])])
+def test_lazy_boxes_match_dense_recurrence_and_literal_rows(ctx, n, m, N, rows):
+    g = np.random.default_rng(7 * n + m)
+    A = _sparse_system(2 * n + 1, n)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m)) if m else None
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.2) if m else None
+    delta = 0.02
+    D = orc.discretize_box(A, X0, delta, B, U)
+    Co, Ro = orc.bffpsv18_reach(D, N, rows)
+    S = ctx.sparse(sp.csc_matrix(A))
+    Cd, Rd = S.bffpsv18_boxes(delta, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi,
+                              None if rows is None else np.asarray(rows, dtype=np.int32))
+    assert_close(Cd.T, Co, "lazy centres vs dense recurrence")
+    assert_close(Rd.T, Ro, "lazy radii vs dense recurrence")
+    if N <= 25:       # the reference's own formulation: rows of exp(kδA) from scratch at every step
+        Cl, Rl = orc.bffpsv18_reach_lazy(A, D, delta, N, rows)
+        assert_close(Cd.T, Cl, "lazy centres vs from-scratch rows")
+        assert_close(Rd.T, Rl, "lazy radii vs from-scratch rows")
+    S.close()
+
+
+def test_lazy_path_end_to_end_matches_dense_device_path(ctx):
+    """Sparse discretisation + lazy rows against the dense device path (expm / Φ₂ GEMM chain + stacked DMMA power
+    GEMM) on a C4-shaped system at reduced size: two independent device implementations of the same flowpipe."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.mna5(n=600, N=60, seed=5)
+    rows = np.array([0, 1, 2, 9, 77, 333, 599], dtype=np.int32)
+    N = 60
+    Dd = ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU)
+    C1, R1 = ctx.bffpsv18_boxes(Dd["Phi"], Dd["c0"], Dd["r0"], N, Dd["MU"], Dd["cU"], Dd["rU"], Dd["rpsi"], rows)
+    S = ctx.sparse(sp.csc_matrix(w.A))
+    Ds = S.discretize_box(w.delta, w.c, w.r, w.B, w.cU, w.rU)
+    for key in ("c0", "r0", "rE", "rpsi", "MU"):
+        assert_close(Ds[key], Dd[key], key)
+    C2, R2 = S.bffpsv18_boxes(w.delta, Ds["c0"], Ds["r0"], N, Ds["MU"], Ds["cU"], Ds["rU"], Ds["rpsi"], rows)
+    assert_close(C2, C1, "centres")
+    assert_close(R2, R1, "radii")
+    t = S.timing()
+    assert t["products"] > 0 and t["run_ms"] > 0
+    S.close()

@@ -354,3 +354,21 @@ def test_firstorder_and_nobloating_models():
             E = sla.expm(M * tg)
             x = E[:n, :n] @ x0 + E[:n, n:] @ u
             assert np.all(np.abs(x - Cn[k]) <= Rn[k] * (1 + 1e-9) + 1e-12), ("nobloating", k)
+
+
+def test_lazy_expm_literal_restatement_agrees_with_the_recurrence():
+    """reach_blocks! for a SparseMatrixExp (reach_blocks.jl:227-310) takes the rows of exp(kδA) from scratch at every
+    step; the dense variant (:135-224) multiplies by Φ.  Same sets up to rounding: the oracle's two restatements agree
+    far inside the parity tolerance."""
+    g = np.random.default_rng(11)
+    n = 14
+    A = g.standard_normal((n, n)) / 3 - 1.5 * np.eye(n)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, 2))
+    U = orc.Box(g.standard_normal(2), np.array([0.1, 0.3]))
+    D = orc.discretize_box(A, X0, 0.03, B, U)
+    rows = [0, 3, 13]
+    C1, R1 = orc.bffpsv18_reach(D, 30, rows)
+    C2, R2 = orc.bffpsv18_reach_lazy(A, D, 0.03, 30, rows)
+    assert_close(C2, C1, "centres")
+    assert_close(R2, R1, "radii")
