@@ -8,6 +8,8 @@
 #   check_blocks  (dense, half-space) ReachSets/ContinuousPost/BFFPSV18/check_blocks.jl:105-183
 #   reach_homog! / reach_inhomog!     ReachSets/ContinuousPost/GLGM06/reach.jl:5-62, called at GLGM06/post.jl:32,36
 #   reduce_order (call site)          ReachSets/ContinuousPost/GLGM06/post.jl:20
+#   project_reach (zonotopes)         ReachSets/project_reach.jl:18-99
+#   SparseMatrixExp / lazy rows       ReachSets/discretize.jl:153-154, 302-306; BFFPSV18/reach_blocks.jl:227-397
 #
 # No Julia toolchain exists in the build container or on the GPU box, so this file is NOT exercised by the test suite;
 # the Python ctypes binding (reachability.jl_b200/_lib.py) drives the identical entry points and is what the parity
@@ -162,6 +164,53 @@ function reduce_order(Z::Zonotope, r::Int)
         (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int32, Ptr{Float64}, Int64, Ref{Int64}, Ptr{Int32}),
         ctx.handle, n, p, Vector{Float64}(Z.center), G, n, r, 0, Gout, n, pout, C_NULL))
     return Zonotope(Z.center, Gout[:, 1:pout[]])
+end
+
+# ---- project_reach.jl:18-99 -- zonotope flowpipe projected on the device; `h` is a live reach_flowpipe handle
+#      (keep it instead of fetching every zonotope when only `project(sol)` is wanted)
+function project_flowpipe(ctx::Context, h::Ptr{Cvoid}, M::Matrix{Float64}, N::Int)
+    q = size(M, 1)
+    C = Matrix{Float64}(undef, q, N); R = Matrix{Float64}(undef, q, N)
+    check(ctx, ccall((:reach_flowpipe_project, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64), h, q, M, q, C, R, C_NULL, 0))
+    return [Hyperrectangle(C[:, k], R[:, k]) for k in 1:N]
+end
+
+# ---- exp_method = "lazy": SparseMatrixExp(A*δ) never leaves the device (discretize.jl:153-154, reach_blocks.jl:227-397)
+mutable struct SparseSystem
+    handle::Ptr{Cvoid}
+    n::Int
+    function SparseSystem(A::SparseMatrixCSC{Float64,Int64})
+        ctx = context(); h = Ref{Ptr{Cvoid}}(C_NULL); n = size(A, 1)
+        check(ctx, ccall((:reach_sparse_create, LIB), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+            ctx.handle, n, nnz(A), A.colptr, A.rowval, A.nzval, h))
+        s = new(h[], n)
+        finalizer(x -> ccall((:reach_sparse_free, LIB), Cvoid, (Ptr{Cvoid},), x.handle), s)
+        return s
+    end
+end
+
+# rows of exp(δA): get_rows(SparseMatrixExp(A*δ), rows) = (e^{δAᵀ} E_rows)ᵀ
+function get_rows(S::SparseSystem, δ::Float64, rows::Vector{Int})
+    E = zeros(S.n, length(rows)); for (l, i) in enumerate(rows); E[i, l] = 1.0; end
+    Y = similar(E)
+    check(context(), ccall((:reach_expmv, LIB), Int32,
+        (Ptr{Cvoid}, Float64, Int32, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64), S.handle, δ, 1, length(rows), E, S.n, Y, S.n))
+    return permutedims(Y)
+end
+
+# reach_blocks!(ϕ::SparseMatrixExp, ...) for box blocks: same marshalling as the dense method above, without Φ
+function reach_blocks_lazy!(S::SparseSystem, δ::Float64, Xhat0, inputs, N::Int, dimensions::Vector{Int})
+    c0, r0 = boxof(Xhat0); rows = Int32.(dimensions .- 1); nr = length(rows)
+    C = Matrix{Float64}(undef, nr, N); R = Matrix{Float64}(undef, nr, N); done = Ref{Int64}(0)
+    m, MU, cU, rU, rψ = inputs === nothing ? (0, C_NULL, C_NULL, C_NULL, C_NULL) :
+        (size(inputs.MU, 2), inputs.MU, inputs.cU, inputs.rU, inputs.rψ)
+    check(context(), ccall((:reach_bffpsv18_boxes_lazy, LIB), Int32,
+        (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Int64, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        S.handle, δ, c0, r0, m, MU, S.n, cU, rU, rψ, nr, rows, N, C, R, done))
+    return C, R          # regrouped into SparseReachSet{CartesianProductArray} exactly as in reach_blocks! above
 end
 
 end # module
