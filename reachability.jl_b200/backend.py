@@ -160,6 +160,28 @@ class Context:
         self._check(self.lib.reach_bffpsv18_boxes(self._h, *args, dptr(centers), dptr(radii), C.byref(done)))
         return int(done.value)
 
+    def bffpsv18_boxes_csc(self, Phi_sparse, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None):
+        """Sparse twin of `bffpsv18_boxes` (reach_blocks.jl:47-132): Φ as a scipy.sparse matrix, sent as CSC fields."""
+        n, colptr, rowval, nzval = _csc_fields(Phi_sparse)
+        c0, r0 = fvec(c0), fvec(r0)
+        m = 0
+        if MU is not None:
+            MU = fmat(MU).reshape(n, -1, order="F")
+            m = MU.shape[1]
+            cU, rU, rpsi = fvec(cU), fvec(rU), fvec(rpsi)
+        else:
+            cU = rU = rpsi = None
+        rows = np.arange(n, dtype=np.int32) if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        centers = np.zeros((len(rows), int(N)), order="F")
+        radii = np.zeros((len(rows), int(N)), order="F")
+        done = C.c_int64()
+        i64p = C.POINTER(C.c_int64)
+        self._check(self.lib.reach_bffpsv18_boxes_csc(self._h, n, len(nzval), colptr.ctypes.data_as(i64p),
+                                                      rowval.ctypes.data_as(i64p), dptr(nzval), dptr(c0), dptr(r0), m, dptr(MU),
+                                                      n, dptr(cU), dptr(rU), dptr(rpsi), len(rows), iptr(rows), int(N),
+                                                      dptr(centers), dptr(radii), C.byref(done)))
+        return centers, radii
+
     def boxplan(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None) -> "BoxPlan":
         return BoxPlan(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
 

@@ -330,10 +330,48 @@ int64_t choose_block(int64_t n, int64_t Rp, int64_t N, int64_t m) {
 
 void boxplan_destroy(BoxPlan* P);
 
+// Φ given as Julia's SparseMatrixCSC fields (1-based Int64): scattered into the zero-filled dense device matrix.  The sparse
+// reach_blocks! (reach_blocks.jl:47-132) computes the same sets as the dense one -- it only skips blocks that are zero --
+// and Φ^k fills in quickly, so the device keeps the dense DMMA recurrence and only the upload is sparse.
+__global__ void csc_scatter_kernel(int n, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                   const double* __restrict__ nzval, double* __restrict__ D, int64_t ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) D[(int64_t)j * ld + (rowval[p] - 1)] = nzval[p];
+}
+
+void upload_phi_csc(Ctx* ctx, DMat& Phi, int64_t n, const PhiCsc& csc) {
+    REACH_REQUIRE(csc.nnz >= 0 && csc.colptr && (csc.nnz == 0 || (csc.rowval && csc.nzval)), "bffpsv18: bad CSC Phi");
+    REACH_REQUIRE(csc.colptr[0] == 1 && csc.colptr[n] == csc.nnz + 1, "bffpsv18: CSC colptr must be 1-based with colptr[n+1] = nnz + 1");
+    for (int64_t j = 0; j < n; ++j) REACH_REQUIRE(csc.colptr[j + 1] >= csc.colptr[j], "bffpsv18: CSC colptr must be non-decreasing");
+    for (int64_t p = 0; p < csc.nnz; ++p)
+        REACH_REQUIRE(csc.rowval[p] >= 1 && csc.rowval[p] <= n, "bffpsv18: CSC row index out of range");
+    cudaStream_t st = ctx->stream;
+    int64_t* dcp = (int64_t*)ctx_malloc(ctx, sizeof(int64_t) * (n + 1));
+    int64_t* drv = (int64_t*)ctx_malloc(ctx, sizeof(int64_t) * std::max<int64_t>(csc.nnz, 1));
+    double* dnz = (double*)ctx_malloc(ctx, sizeof(double) * std::max<int64_t>(csc.nnz, 1));
+    try {
+        REACH_CUDA(cudaMemcpyAsync(dcp, csc.colptr, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+        if (csc.nnz) {
+            REACH_CUDA(cudaMemcpyAsync(drv, csc.rowval, sizeof(int64_t) * csc.nnz, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaMemcpyAsync(dnz, csc.nzval, sizeof(double) * csc.nnz, cudaMemcpyHostToDevice, st));
+        }
+        csc_scatter_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>((int)n, dcp, drv, dnz, Phi.p, Phi.ld);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        REACH_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        ctx_free(ctx, dcp); ctx_free(ctx, drv); ctx_free(ctx, dnz);
+        throw;
+    }
+    ctx_free(ctx, dcp); ctx_free(ctx, drv); ctx_free(ctx, dnz);
+}
+
 BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0, const double* r0,
                         int64_t m, const double* MU, int64_t ldmu, const double* cU, const double* rU,
-                        const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N) {
-    REACH_REQUIRE(n > 0 && Phi && c0 && r0 && ldphi >= n, "bffpsv18: bad Phi/c0/r0");
+                        const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N, const PhiCsc* csc) {
+    REACH_REQUIRE(n > 0 && c0 && r0 && ((Phi && ldphi >= n) || csc), "bffpsv18: bad Phi/c0/r0");
     REACH_REQUIRE(N >= 1, "bffpsv18: N must be >= 1");
     REACH_REQUIRE(nrows > 0 && nrows <= n && rows, "bffpsv18: bad rows");
     if (!MU) m = 0;
@@ -347,7 +385,8 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
         P->s = N > 2 ? choose_block(n, P->Rp, N, m) : 1;
         const int64_t s = P->s;
         P->Phi = dmat_alloc(ctx, n, n);
-        dmat_upload(ctx, P->Phi, Phi, ldphi);
+        if (Phi) dmat_upload(ctx, P->Phi, Phi, ldphi);
+        else upload_phi_csc(ctx, P->Phi, n, *csc);
         P->c0 = dvec_alloc(ctx, n, c0);
         P->r0 = dvec_alloc(ctx, n, r0);
         if (m > 0) {

@@ -6,7 +6,7 @@ namespace reach {
 struct BoxPlan;
 BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0, const double* r0,
                         int64_t m, const double* MU, int64_t ldmu, const double* cU, const double* rU,
-                        const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N);
+                        const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N, const PhiCsc* csc = nullptr);
 void boxplan_destroy(BoxPlan* P);
 void boxplan_run(BoxPlan* P);
 void boxplan_fetch(BoxPlan* P, double* centers, double* radii);
@@ -95,6 +95,29 @@ int32_t reach_bffpsv18_boxes(reach_ctx* h, int64_t n, const double* Phi, int64_t
     GUARD_BEGIN(ctx)
     REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes: output buffers required");
     BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+    try {
+        boxplan_run(p);
+        boxplan_fetch(p, centers, radii);
+    } catch (...) {
+        boxplan_destroy(p);
+        throw;
+    }
+    boxplan_destroy(p);
+    if (steps_done) *steps_done = N;
+    return REACH_OK;
+    GUARD_END(ctx)
+}
+
+int32_t reach_bffpsv18_boxes_csc(reach_ctx* h, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                                 const double* nzval, const double* c0, const double* r0, int64_t m, const double* MU,
+                                 int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
+                                 const int32_t* rows, int64_t N, double* centers, double* radii, int64_t* steps_done) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    GUARD_BEGIN(ctx)
+    REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes_csc: output buffers required");
+    const PhiCsc csc{nnz, colptr, rowval, nzval};
+    BoxPlan* p = boxplan_create(ctx, n, nullptr, 0, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, &csc);
     try {
         boxplan_run(p);
         boxplan_fetch(p, centers, radii);

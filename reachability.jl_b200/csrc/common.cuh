@@ -84,6 +84,14 @@ void dmat_upload(Ctx* ctx, DMat& dst, const double* host, int64_t ld_host);     
 void dmat_download(Ctx* ctx, const DMat& src, double* host, int64_t ld_host);
 void dmat_zero(Ctx* ctx, DMat& m);
 
+// A host matrix given as Julia's SparseMatrixCSC fields (1-based Int64 indices)
+struct PhiCsc {
+    int64_t nnz;
+    const int64_t* colptr;
+    const int64_t* rowval;
+    const double* nzval;
+};
+
 // ---- primitives (each is one kernel launch on ctx->stream) -------------------------------------------
 // C[M x N] = A[M x K] * B[K x N], A and C column-major, B given TRANSPOSED (Bt[k*ldbt + j] = B[k, j]).
 // All operands zero-padded as DMat guarantees.  Fused options: see gemm_dmma.cu.

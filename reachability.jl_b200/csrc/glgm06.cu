@@ -1129,6 +1129,7 @@ __device__ __forceinline__ void proj_column(const double* __restrict__ col, cons
                                             int lane, double acc[4]) {
     acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
     const int n2 = n >> 1;
+#pragma unroll 4
     for (int i = lane; i < n2; i += 32) {
         const double2 v = reinterpret_cast<const double2*>(col)[i];
 #pragma unroll

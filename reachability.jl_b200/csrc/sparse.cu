@@ -183,12 +183,15 @@ __global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(int n, int 
     }
 }
 
+// Sub-warp ly owns the quantities q = ly, ly + 8, ... of a pass (64 quantities per pass): it adds their state slices in
+// slice order; sub-warp 0 then applies the input recurrences in input order.
+constexpr int FIN_Q = 64;
 __global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(int R, int nsl, int m, const double* __restrict__ part, int ldp,
                                                                     const double* __restrict__ cU, const double* __restrict__ rU,
                                                                     double* __restrict__ cW, double* __restrict__ rW,
                                                                     double* __restrict__ centers, double* __restrict__ radii,
                                                                     const int* __restrict__ kctr, int koff) {
-    __shared__ double redc[STEP_SUB][32], redr[STEP_SUB][32];
+    __shared__ double qs[FIN_Q][32];
     // output column = device-side step counter + offset: the same captured graph serves every pair of steps
     const int64_t col = (int64_t)(*kctr + koff) * R;
     centers += col;
@@ -196,25 +199,33 @@ __global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(int R, int n
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int l = blockIdx.x * 32 + lx;
     const bool live = l < R;
-    auto slices = [&](int quantity) {
-        double s = 0.0;
-        for (int q = 0; q < nsl; ++q) s += part[((int64_t)quantity * nsl + q) * ldp + l];
-        return s;
-    };
-    double dc = 0.0, dr = 0.0;
-    if (live)
-        for (int i = ly; i < m; i += STEP_SUB) {         // inputs strided over the sub-warps, combined in order below
-            const double v = slices(3 + i);
-            dc = fma(v, cU[i], dc);
-            dr = fma(fabs(v), rU[i], dr);
+    const int nq = 3 + m;
+    double sc = 0.0, sr = 0.0, sp = 0.0, dc = 0.0, dr = 0.0;
+    for (int q0 = 0; q0 < nq; q0 += FIN_Q) {
+        for (int q = q0 + ly; q < min(nq, q0 + FIN_Q); q += STEP_SUB) {
+            double s = 0.0;
+            if (live) {
+                const double* pq = part + (int64_t)q * nsl * ldp + l;
+#pragma unroll 8
+                for (int sl = 0; sl < nsl; ++sl) s += pq[(int64_t)sl * ldp];
+            }
+            qs[q - q0][lx] = s;
         }
-    redc[ly][lx] = dc;
-    redr[ly][lx] = dr;
-    __syncthreads();
+        __syncthreads();
+        if (ly == 0 && live)
+            for (int q = q0; q < min(nq, q0 + FIN_Q); ++q) {
+                const double v = qs[q - q0][lx];
+                if (q == 0) sc = v;
+                else if (q == 1) sr = v;
+                else if (q == 2) sp = v;
+                else {
+                    dc = fma(v, cU[q - 3], dc);
+                    dr = fma(fabs(v), rU[q - 3], dr);
+                }
+            }
+        __syncthreads();
+    }
     if (ly == 0 && live) {
-        dc = 0.0; dr = 0.0;
-        for (int q = 0; q < STEP_SUB; ++q) { dc += redc[q][lx]; dr += redr[q][lx]; }
-        const double sc = slices(0), sr = slices(1), sp = slices(2);
         const double cw = m > 0 ? cW[l] : 0.0, rw = m > 0 ? rW[l] : 0.0;
         centers[l] = sc + cw;
         radii[l] = sr + rw;
@@ -613,7 +624,8 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
         // epilogue geometry: ~2000 CTAs over (row chunks, state slices, quantity groups)
         const unsigned gx = (unsigned)ceil_div(R, 32);
         const int gz = 1 + (int)ceil_div(m, STEP_MCHUNK);
-        const int nsl = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(148, ceil_div(n, 64)), 2048 / ((int64_t)gx * gz)));
+        const int nsl = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, ceil_div(n, 64)),
+                                                                    std::max<int64_t>(8, 2048 / ((int64_t)gx * gz))));
         const int64_t ldp = round_up(R, 32);
         double* part = alloc((size_t)(3 + m) * nsl * ldp);
         int* drows = (int*)alloc((size_t)(R + 1) / 2 + 1);

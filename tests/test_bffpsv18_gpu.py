@@ -208,3 +208,26 @@ def test_config_c4_mna5_full_dimension(ctx):
     assert_close(full_c[rows, :], Co[:4].T, "sharded centres")
     assert_close(full_r[rows, :], Ro[:4].T, "sharded radii")
     assert np.all(full_r >= 0)
+
+
+def test_sparse_csc_phi_is_bit_identical_to_dense(ctx):
+    """reach_blocks!(ϕ::SparseMatrixCSC, ...) (reach_blocks.jl:47-132): same sets as the dense method; the device scatters the
+    CSC fields into its dense layout, so the results equal those of Matrix(Φ) bit for bit."""
+    import scipy.sparse as sp
+    g = np.random.default_rng(5)
+    n, N = 41, 30
+    Phi = np.zeros((n, n))
+    for i in range(0, n - 1, 2):                      # block-diagonal Φ stays sparse under powers
+        Phi[i:i + 2, i:i + 2] = g.standard_normal((2, 2)) * 0.6
+    Phi[-1, -1] = 0.5
+    c0, r0 = g.standard_normal(n), np.abs(g.standard_normal(n))
+    MU = g.standard_normal((n, 2)) * 0.1
+    cU, rU, rpsi = g.standard_normal(2), np.abs(g.standard_normal(2)), np.abs(g.standard_normal(n)) * 0.01
+    rows = np.array([0, 1, 7, 40], dtype=np.int32)
+    Cd, Rd = ctx.bffpsv18_boxes(Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
+    Cs, Rs = ctx.bffpsv18_boxes_csc(sp.csc_matrix(Phi), c0, r0, N, MU, cU, rU, rpsi, rows)
+    assert np.array_equal(Cs, Cd) and np.array_equal(Rs, Rd)
+    P = orc.DiscreteBoxProblem(Phi, c0, r0, MU, cU, rU, rpsi, None, None)
+    Co, Ro = orc.bffpsv18_reach(P, N, rows)
+    assert_close(Cs.T, Co, "centres")
+    assert_close(Rs.T, Ro, "radii")
