@@ -26,6 +26,9 @@ class Context:
         if rc != 0:
             raise ReachError(rc, (self.lib.reach_last_error(None) or b"").decode())
         self.device = device
+        # borrowed cudaStream_t handle; None: the context owns its stream (a NULL handle -- torch's legacy default stream --
+        # is NOT borrowed: reach_ctx_create_on_stream(dev, NULL) creates a private non-blocking stream)
+        self.stream = int(stream) if stream else None
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

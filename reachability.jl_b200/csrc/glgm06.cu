@@ -1912,7 +1912,6 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
             F->next_batch = 1;
             if (N == 1) { F->meta_host.assign(1, make_int2((int)F->p0, 0)); F->ran = true; }
         }
-        REACH_CUDA(cudaStreamSynchronize(st));
         return;
     }
     REACH_REQUIRE(b == F->next_batch, "glgm06: sharded batches must be processed in order");
@@ -1963,7 +1962,8 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
             F->ran = true;
         }
     }
-    REACH_CUDA(cudaStreamSynchronize(st));
+    // No host synchronisation: the phases and the caller's all-reduces are ordered on the context's stream (the caller
+    // issues the collectives on that stream, or synchronises it itself -- sharding.run_sharded does either).
 }
 
 // Device buffer the caller all-reduces (sum) after phase `which`-dependent: 0 scores, 1 row-support masks, 2 W box

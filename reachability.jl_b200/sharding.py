@@ -98,16 +98,26 @@ def _device_tensor(ptr, count, typestr, device):
     return torch.as_tensor(a, device=device)
 
 
-def run_sharded(engine, dist, as_tensor=None, sync=None):
+def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None):
     """Drive a column-sharded GLGM06 flowpipe: `engine` exposes nbatches(), phase(batch, phase) and
     buffer(batch, which) (backend.ShardedFlowpipe, or a mock on CPU); `as_tensor` turns what buffer() returns into a
-    torch tensor aliasing the engine's memory (default: a zero-copy view of the device buffer)."""
+    torch tensor aliasing the engine's memory (default: a zero-copy view of the device buffer).
+
+    `stream_ordered`: the engine's context issues its kernels on torch's CURRENT CUDA stream (``Context(dev,
+    stream=torch.cuda.current_stream().cuda_stream)``).  The NCCL all-reduces are then ordered against the phases on the
+    device (torch makes the collective wait for the current stream and the current stream wait for the collective), and
+    the host enqueues the whole flowpipe without a single synchronisation.  Default: detected from the engine's context;
+    otherwise the stream is synchronised around every collective."""
     import torch
     if as_tensor is None:
         dev = torch.device("cuda", torch.cuda.current_device())
 
         def as_tensor(buf):
             return _device_tensor(buf[0], buf[1], buf[2], dev)
+    if stream_ordered is None:
+        ctx = getattr(engine, "ctx", None)
+        stream_ordered = bool(torch.cuda.is_available() and ctx is not None and getattr(ctx, "stream", None) is not None
+                              and ctx.stream == torch.cuda.current_stream().cuda_stream)
     if sync is None:
         def sync():
             if torch.cuda.is_available():
@@ -118,8 +128,12 @@ def run_sharded(engine, dist, as_tensor=None, sync=None):
             for which in SHARD_COLLECTIVES[phase]:
                 buf = engine.buffer(b, which)
                 if buf is not None:
+                    if not stream_ordered:
+                        sync()                      # the phase's kernels must be done before NCCL reads the buffer
                     dist.all_reduce(as_tensor(buf), op=dist.ReduceOp.SUM)
-            sync()
+                    if not stream_ordered:
+                        sync()
+    sync()
     return engine
 
 

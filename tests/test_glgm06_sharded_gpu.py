@@ -27,6 +27,7 @@ class _EmulatedRanks:
             for phase in range(4):
                 for e in self.engines:
                     e.phase(b, phase)
+                self.engines[0].ctx.sync()       # the phases are asynchronous; the emulated collective runs on torch's stream
                 for which in sharding.SHARD_COLLECTIVES[phase]:
                     bufs = [e.buffer(b, which) for e in self.engines]
                     if bufs[0] is None:

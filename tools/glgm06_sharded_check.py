@@ -24,7 +24,9 @@ if full:
     w = wl.iss()
     cases.append(("C2-iss n=270", w.A, orc.Box(w.c, w.r), w.B, orc.Box(w.cU, w.rU), w.delta, 2000, 10, True, 150))
 ok = True
-with rb.Context(dev) as ctx:
+torch_stream = torch.cuda.Stream(device=dev)          # the library borrows it, NCCL orders its collectives against it
+torch.cuda.set_stream(torch_stream)
+with rb.Context(dev, stream=torch_stream.cuda_stream) as ctx:
     for (name, A, X0, B, U, delta, N, r, rzg, ncheck) in cases:
         D = orc.discretize_zonotope(A, X0, delta, B, U, rzg=rzg)
         Om = orc.reduce_order(D.Omega0, r, rzg)
