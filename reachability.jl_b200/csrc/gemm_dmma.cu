@@ -278,10 +278,11 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     constexpr int B_STAGE = BK * (BN + 4) + (AKM ? 8 : 0);
     const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 2 * STAGES * sizeof(uint64_t) +
                         STAGES * sizeof(int) + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};      // function attributes are per device
+    const int dev = ctx->device & 63;
+    if (!configured[dev]) {
         REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = ctx->sm_count - ctx->gemm_reserve_sms > 0 ? ctx->sm_count - ctx->gemm_reserve_sms : 1;

@@ -1620,7 +1620,8 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
 }
 
 static void set_kernel_attributes(Flowpipe* F) {
-    static bool done = false;
+    static bool done_on[64] = {false};         // function attributes are per device
+    bool& done = done_on[F->ctx->device & 63];
     if (done) return;
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1633,7 +1634,6 @@ static void set_kernel_attributes(Flowpipe* F) {
     REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
     REACH_CUDA(cudaFuncSetAttribute(apply_r_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, num_smem));
     done = true;
-    (void)F;
 }
 
 void flowpipe_run(Flowpipe* F) {

@@ -16,7 +16,6 @@
 #include "../../include/reach.h"
 #include <cmath>
 #include <algorithm>
-
 namespace reach {
 
 void omega0_box(Ctx* ctx, int64_t n, const double* c, const double* r, const double* pc, const double* pr, const double* rE,
@@ -36,23 +35,21 @@ struct Csr {
 // Blocks are n x ld2 double2 ("row-block" layout: the R values of state i are contiguous).  Thread = (row i, double2 l2);
 // the nonzeros of a row are read by all its threads (broadcast), the gathered block rows are coalesced.
 template <bool ABS>
-__global__ void __launch_bounds__(256) spmm_taylor_kernel(Csr S, int ld2, const double2* __restrict__ T, double2* __restrict__ Tn,
-                                                          const double2* __restrict__ Yin, double2* __restrict__ Yout, double alpha) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void spmm_item(const Csr& S, int ld2, const double2* T, double2* Tn, const double2* Yin, double2* Yout,
+                                          double alpha, int64_t t) {
     const int i = (int)(t / ld2), l2 = (int)(t - (int64_t)i * ld2);
-    if (i >= S.n) return;
     double2 acc = make_double2(0.0, 0.0);
-    const int p1 = S.ptr[i + 1];
+    const int p1 = __ldg(S.ptr + i + 1);
     // four nonzeros at a time: their (index, value) loads and then their four gathers are independent, so a row costs
     // three dependent memory round trips instead of two per nonzero; the sums keep CSR order
-    for (int p = S.ptr[i]; p < p1; p += 4) {
+    for (int p = __ldg(S.ptr + i); p < p1; p += 4) {
         int jj[4];
         double vv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const bool ok = p + u < p1;
-            jj[u] = ok ? S.idx[p + u] : i;
-            vv[u] = ok ? S.val[p + u] : 0.0;
+            jj[u] = ok ? __ldg(S.idx + p + u) : i;
+            vv[u] = ok ? __ldg(S.val + p + u) : 0.0;
         }
         double2 xx[4];
 #pragma unroll
@@ -75,6 +72,13 @@ __global__ void __launch_bounds__(256) spmm_taylor_kernel(Csr S, int ld2, const 
         y.y += acc.y;
         Yout[o] = y;
     }
+}
+
+template <bool ABS>
+__global__ void __launch_bounds__(256) spmm_taylor_kernel(Csr S, int ld2, const double2* T, double2* Tn, const double2* Yin,
+                                                          double2* Yout, double alpha) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)S.n * ld2) spmm_item<ABS>(S, ld2, T, Tn, Yin, Yout, alpha, t);
 }
 
 // X[i*ld + l] = (i == sel[l]) for l < cnt   (identity columns / unit rows of interest)
@@ -132,24 +136,29 @@ __global__ void scale_vec_kernel(int n, double alpha, const double* __restrict__
 // recurrences.  Every sum has a fixed order.
 constexpr int STEP_SUB = 8;
 constexpr int STEP_MCHUNK = 8;
-__global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(int n, int ld, int R, int nsl, const double* __restrict__ Wt,
-                                                                     const double* __restrict__ c0, const double* __restrict__ r0,
-                                                                     const double* __restrict__ rpsi, int m,
-                                                                     const double* __restrict__ MU /* n x m, ld n */,
-                                                                     double* __restrict__ part, int ldp) {
-    __shared__ double red[STEP_SUB][32];
+constexpr int FIN_Q = 64;
+
+struct StepGeom {       // epilogue geometry and operands (device pointers)
+    int n, ld, R, nsl, m, ldp, gx, gz;
+    const double* c0; const double* r0; const double* rpsi;      // rpsi may be nullptr (homogeneous)
+    const double* MU; const double* cU; const double* rU;        // MU: n x m, ld n
+    double* cW; double* rW; double* part;
+};
+
+// virtual CTA (bx, sl, grp): 32 rows of interest x state slice sl x quantity group grp.  `red`: STEP_SUB x 32 doubles.
+__device__ __forceinline__ void lazy_partial_block(const StepGeom& g, const double* Wt, int bx, int sl, int grp, double (*red)[32]) {
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int l = blockIdx.x * 32 + lx, sl = blockIdx.y, grp = blockIdx.z;
-    const bool live = l < R;
-    const int chunk = (n + nsl - 1) / nsl;
-    const int j0 = sl * chunk, j1 = min(n, j0 + chunk);
+    const int l = bx * 32 + lx;
+    const bool live = l < g.R;
+    const int chunk = (g.n + g.nsl - 1) / g.nsl;
+    const int j0 = sl * chunk, j1 = min(g.n, j0 + chunk);
     auto combine_store = [&](double v, int quantity) {       // sub-slices in order -> part[quantity][sl][l]
         red[ly][lx] = v;
         __syncthreads();
         if (ly == 0 && live) {
             double s = 0.0;
             for (int q = 0; q < STEP_SUB; ++q) s += red[q][lx];
-            part[((int64_t)quantity * nsl + sl) * ldp + l] = s;
+            g.part[((int64_t)quantity * g.nsl + sl) * g.ldp + l] = s;
         }
         __syncthreads();
     };
@@ -157,10 +166,10 @@ __global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(int n, int 
         double sc = 0.0, sr = 0.0, sp = 0.0;
         if (live)
             for (int j = j0 + ly; j < j1; j += STEP_SUB) {
-                const double w = Wt[(int64_t)j * ld + l];
-                sc = fma(w, c0[j], sc);
-                sr = fma(fabs(w), r0[j], sr);
-                if (rpsi) sp = fma(fabs(w), rpsi[j], sp);
+                const double w = Wt[(int64_t)j * g.ld + l];
+                sc = fma(w, g.c0[j], sc);
+                sr = fma(fabs(w), g.r0[j], sr);
+                if (g.rpsi) sp = fma(fabs(w), g.rpsi[j], sp);
             }
         combine_store(sc, 0);
         combine_store(sr, 1);
@@ -172,42 +181,32 @@ __global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(int n, int 
         for (int u = 0; u < STEP_MCHUNK; ++u) pm[u] = 0.0;
         if (live)
             for (int j = j0 + ly; j < j1; j += STEP_SUB) {
-                const double w = Wt[(int64_t)j * ld + l];
+                const double w = Wt[(int64_t)j * g.ld + l];
 #pragma unroll
                 for (int u = 0; u < STEP_MCHUNK; ++u)
-                    if (i0 + u < m) pm[u] = fma(w, MU[(int64_t)(i0 + u) * n + j], pm[u]);
+                    if (i0 + u < g.m) pm[u] = fma(w, g.MU[(int64_t)(i0 + u) * g.n + j], pm[u]);
             }
 #pragma unroll
         for (int u = 0; u < STEP_MCHUNK; ++u)
-            if (i0 + u < m) combine_store(pm[u], 3 + i0 + u);
+            if (i0 + u < g.m) combine_store(pm[u], 3 + i0 + u);
     }
 }
 
-// Sub-warp ly owns the quantities q = ly, ly + 8, ... of a pass (64 quantities per pass): it adds their state slices in
-// slice order; sub-warp 0 then applies the input recurrences in input order.
-constexpr int FIN_Q = 64;
-__global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(int R, int nsl, int m, const double* __restrict__ part, int ldp,
-                                                                    const double* __restrict__ cU, const double* __restrict__ rU,
-                                                                    double* __restrict__ cW, double* __restrict__ rW,
-                                                                    double* __restrict__ centers, double* __restrict__ radii,
-                                                                    const int* __restrict__ kctr, int koff) {
-    __shared__ double qs[FIN_Q][32];
-    // output column = device-side step counter + offset: the same captured graph serves every pair of steps
-    const int64_t col = (int64_t)(*kctr + koff) * R;
-    centers += col;
-    radii += col;
+// virtual CTA bx of the finish: sub-warp ly owns the quantities q = ly, ly + 8, ... of a pass (64 quantities per pass) and
+// adds their state slices in slice order; sub-warp 0 then applies the input recurrences in input order.  `qs`: FIN_Q x 32.
+__device__ __forceinline__ void lazy_finish_block(const StepGeom& g, int bx, double* centers, double* radii, double (*qs)[32]) {
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int l = blockIdx.x * 32 + lx;
-    const bool live = l < R;
-    const int nq = 3 + m;
+    const int l = bx * 32 + lx;
+    const bool live = l < g.R;
+    const int nq = 3 + g.m;
     double sc = 0.0, sr = 0.0, sp = 0.0, dc = 0.0, dr = 0.0;
     for (int q0 = 0; q0 < nq; q0 += FIN_Q) {
         for (int q = q0 + ly; q < min(nq, q0 + FIN_Q); q += STEP_SUB) {
             double s = 0.0;
             if (live) {
-                const double* pq = part + (int64_t)q * nsl * ldp + l;
+                const double* pq = g.part + (int64_t)q * g.nsl * g.ldp + l;
 #pragma unroll 8
-                for (int sl = 0; sl < nsl; ++sl) s += pq[(int64_t)sl * ldp];
+                for (int sl = 0; sl < g.nsl; ++sl) s += pq[(int64_t)sl * g.ldp];
             }
             qs[q - q0][lx] = s;
         }
@@ -219,21 +218,34 @@ __global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(int R, int n
                 else if (q == 1) sr = v;
                 else if (q == 2) sp = v;
                 else {
-                    dc = fma(v, cU[q - 3], dc);
-                    dr = fma(fabs(v), rU[q - 3], dr);
+                    dc = fma(v, g.cU[q - 3], dc);
+                    dr = fma(fabs(v), g.rU[q - 3], dr);
                 }
             }
         __syncthreads();
     }
     if (ly == 0 && live) {
-        const double cw = m > 0 ? cW[l] : 0.0, rw = m > 0 ? rW[l] : 0.0;
+        const double cw = g.m > 0 ? g.cW[l] : 0.0, rw = g.m > 0 ? g.rW[l] : 0.0;
         centers[l] = sc + cw;
         radii[l] = sr + rw;
-        if (m > 0) {
-            cW[l] = cw + dc;
-            rW[l] = rw + dr + sp;
+        if (g.m > 0) {
+            g.cW[l] = cw + dc;
+            g.rW[l] = rw + dr + sp;
         }
     }
+}
+
+__global__ void __launch_bounds__(32 * STEP_SUB) lazy_partial_kernel(StepGeom g, const double* Wt) {
+    __shared__ double red[STEP_SUB][32];
+    lazy_partial_block(g, Wt, blockIdx.x, blockIdx.y, blockIdx.z, red);
+}
+
+// output column = device-side step counter + offset: the same captured graph serves every pair of steps
+__global__ void __launch_bounds__(32 * STEP_SUB) lazy_finish_kernel(StepGeom g, double* centers, double* radii, const int* kctr,
+                                                                    int koff) {
+    __shared__ double qs[FIN_Q][32];
+    const int64_t col = (int64_t)(*kctr + koff) * g.R;
+    lazy_finish_block(g, blockIdx.x, centers + col, radii + col, qs);
 }
 
 // step 1 and the initial input boxes: centers/radii column 0 = X̂0[rows]; Ŵ_1 = box(MU U ⊕ Eψ)[rows]  (:241-262)
@@ -644,6 +656,14 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
                                                                      cW, rW, dC, dR);
         unit_block_kernel<<<(unsigned)ceil_div(n * ld, 256), 256, 0, st>>>((int)n, (int)ld, (int)R, drows, W[0]);
         ctx->launches += 2;
+        StepGeom geom;
+        geom.n = (int)n; geom.ld = (int)ld; geom.R = (int)R; geom.nsl = nsl; geom.m = (int)m; geom.ldp = (int)ldp;
+        geom.gx = (int)gx; geom.gz = gz;
+        geom.c0 = dc0; geom.r0 = dr0; geom.rpsi = m > 0 ? dpsi : nullptr; geom.MU = dMU; geom.cU = dcu; geom.rU = dru;
+        geom.cW = cW; geom.rW = rW; geom.part = part;
+        int64_t steps = N - 1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
         double* cur = W[0];
         int* kctr = (int*)alloc(1);
         const int one = 1;
@@ -659,18 +679,15 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
                 if (!b) b = w; else if (!t0) t0 = w; else t1 = w;
             }
             cur = expm_action(S, S->At, delta, ld, a, b, t0, t1);
-            lazy_partial_kernel<<<dim3(gx, (unsigned)nsl, (unsigned)gz), 32 * STEP_SUB, 0, st>>>(
-                (int)n, (int)ld, (int)R, nsl, cur, dc0, dr0, m > 0 ? dpsi : nullptr, (int)m, dMU, part, (int)ldp);
-            lazy_finish_kernel<<<gx, 32 * STEP_SUB, 0, st>>>((int)R, nsl, (int)m, part, (int)ldp, dcu, dru, cW, rW, dC, dR,
-                                                             kctr, koff);
+            lazy_partial_kernel<<<dim3(gx, (unsigned)nsl, (unsigned)gz), 32 * STEP_SUB, 0, st>>>(geom, cur);
+            lazy_finish_kernel<<<gx, 32 * STEP_SUB, 0, st>>>(geom, dC, dR, kctr, koff);
             REACH_CUDA(cudaGetLastError());
             ctx->launches += 2;
         };
-        // The step is launch-bound (two dozen ~3 us kernels): two consecutive steps -- after which the buffer rotation
-        // repeats -- are captured once into a CUDA graph and replayed; the output column comes from a device counter.
-        int64_t steps = N - 1;
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t gexec = nullptr;
+        // The step is a chain of two dozen short kernels: two consecutive steps -- after which the buffer rotation repeats
+        // -- are captured once into a CUDA graph and replayed; the output column comes from a device counter.  (A single
+        // persistent cooperative kernel with grid barriers between the Taylor terms was measured SLOWER, 5.8 k against
+        // 7.0 k steps/s on C4 with 31 rows: a barrier over ~600 CTAs costs more than a kernel boundary inside a graph.)
         if (steps >= 6 && !getenv("REACH_LAZY_NO_GRAPH")) {
             double* cur0 = cur;
             const uint64_t l0 = ctx->launches;

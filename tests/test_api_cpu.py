@@ -78,3 +78,38 @@ def test_block_option_rules():
         api._block_set_types(BFFPSV18(block_options=Ball2Stub), part)                 # not on the device path
     with pytest.raises(ValueError):
         api._block_set_types(BFFPSV18(block_options=-1.0), part)                      # DomainError in the reference
+
+
+def test_projection_matrix_assembly_follows_project_reach():
+    """`project_reach` (project_reach.jl:53-86): rows over the state variables; time (0) drops out of the matrix."""
+    P, got_time = api._projection_rows([1, 3], 4, None, None)
+    assert not got_time and np.array_equal(P, np.array([[1.0, 0, 0, 0], [0, 0, 1.0, 0]]))
+    P, got_time = api._projection_rows([0, 2], 4, None, None)
+    assert got_time and np.array_equal(P, np.array([[0, 1.0, 0, 0]]))
+    M = np.array([[1.0, -1.0, 0.5, 0.0]])
+    P, got_time = api._projection_rows([0, 2], 4, M, None)          # 1 x n projection matrix against time (:69-71)
+    assert got_time and np.array_equal(P, M)
+    P, _ = api._projection_rows([2, 3], 4, M, None)                 # against a state variable (:72-76)
+    assert np.array_equal(P, np.array([[0, 1.0, 0, 0], M[0]]))
+    T = np.diag([2.0, 3.0, 4.0, 5.0])
+    P, _ = api._projection_rows([1, 2], 4, None, T)                 # :78-86
+    assert np.array_equal(P, np.array([[2.0, 0, 0, 0], [0, 3.0, 0, 0]]))
+    with pytest.raises(ValueError):
+        api._projection_rows([-1, 2], 4, None, None)                # DomainError (:27-28)
+    with pytest.raises(ValueError):
+        api._projection_rows([1, 0], 4, None, None)                 # DomainError (:29-30)
+    with pytest.raises(AssertionError):
+        api._projection_rows([1, 2], 4, np.ones((2, 4)), None)      # only one-dimensional projection matrices (:64-65)
+
+
+def test_csc_fields_follow_julia_sparse_matrix_csc():
+    """What crosses the ABI for a sparse A is exactly `A.colptr`, `A.rowval`, `A.nzval` of Julia's SparseMatrixCSC."""
+    import scipy.sparse as sp
+    from reachability_jl_b200.backend import _csc_fields
+    A = np.array([[1.0, 0, 2.0], [0, 0, 3.0], [4.0, 5.0, 0]])
+    for form in (A, sp.csc_matrix(A), sp.csr_matrix(A), sp.coo_matrix(A)):
+        n, colptr, rowval, nzval = _csc_fields(form)
+        assert n == 3 and colptr.dtype == np.int64 and rowval.dtype == np.int64
+        assert colptr.tolist() == [1, 3, 4, 6] and rowval.tolist() == [1, 3, 3, 1, 2] and nzval.tolist() == [1.0, 4.0, 5.0, 2.0, 3.0]
+    n, colptr, rowval, nzval = _csc_fields(np.zeros((2, 2)))
+    assert colptr.tolist() == [1, 1, 1] and len(rowval) == 0 and len(nzval) == 0

@@ -133,3 +133,26 @@ def test_lazy_path_end_to_end_matches_dense_device_path(ctx):
     t = S.timing()
     assert t["products"] > 0 and t["run_ms"] > 0
     S.close()
+
+
+def test_graph_replay_and_eager_steps_produce_identical_bits(ctx, monkeypatch):
+    """Two steps of the lazy recurrence are captured into a CUDA graph and replayed (output column from a device counter);
+    REACH_LAZY_NO_GRAPH issues the same kernels eagerly (what the ncu launch lists profile)."""
+    g = np.random.default_rng(77)
+    n, m, N = 150, 3, 34
+    A = _sparse_system(9, n, density=0.03, stiff=8.0)         # ‖δA‖ > 2: more than one scaling repetition
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m))
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.2)
+    delta = 0.2
+    D = orc.discretize_box(A, X0, delta, B, U)
+    rows = np.arange(0, n, 3, dtype=np.int32)
+    S = ctx.sparse(sp.csc_matrix(A))
+    C1, R1 = S.bffpsv18_boxes(delta, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+    monkeypatch.setenv("REACH_LAZY_NO_GRAPH", "1")
+    C2, R2 = S.bffpsv18_boxes(delta, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+    assert np.array_equal(C1, C2) and np.array_equal(R1, R2)
+    Co, Ro = orc.bffpsv18_reach(D, N, rows)
+    assert_close(C1.T, Co, "centres")
+    assert_close(R1.T, Ro, "radii")
+    S.close()
