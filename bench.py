@@ -255,6 +255,9 @@ def run_bffpsv18(args, rank, world, dist):
             warm_plan.close()
         plan.close()
         ctx.close()
+    lazy_obj = None
+    if big and rank == 0 and world == 1:
+        lazy_obj = run_c4_lazy(w, dev, N)
     if big and rank == 0 and world == 1 and not args.no_cpu_baseline:
         args._c4_cpu = cpu_baseline_c4(w, D, N)
     if rank != 0:
@@ -296,7 +299,34 @@ def run_bffpsv18(args, rank, world, dist):
                                     "(tcgen05 has no f64 kind, so its bf16 peak does not apply)",
                      "executed_flops": gemm_flops},
     }
+    if lazy_obj is not None:
+        out["lazy_expm_rows"] = lazy_obj
     return out
+
+
+def run_c4_lazy(w, dev, N, nrows=31):
+    """C4 with `exp_method = "lazy"`: sparse A on the device, sparse discretisation, `nrows` rows of interest
+    advanced by the action of e^{δAᵀ}.  Rides along on the C4 line; timed with CUDA events inside the library."""
+    import scipy.sparse as sp
+    import reachability_jl_b200 as rb
+    n = w.n
+    rows = np.unique(np.concatenate([np.arange(10), np.linspace(0, n - 1, nrows - 10).astype(int)]))[:nrows].astype(np.int32)
+    with rb.Context(dev) as ctx:
+        S = ctx.sparse(sp.csc_matrix(w.A))
+        S.discretize_box(w.delta, w.c, w.r, w.B, w.cU, w.rU)
+        t0 = time.perf_counter()
+        Ds = S.discretize_box(w.delta, w.c, w.r, w.B, w.cU, w.rU)
+        disc_s = time.perf_counter() - t0
+        best = None
+        for _ in range(3):
+            S.bffpsv18_boxes(w.delta, Ds["c0"], Ds["r0"], N, Ds["MU"], Ds["cU"], Ds["rU"], Ds["rpsi"], rows)
+            t = S.timing()
+            best = t if best is None or t["run_ms"] < best["run_ms"] else best
+        S.close()
+    return {"value": (N - 1) / (best["run_ms"] * 1e-3), "unit": "flowpipe steps/s", "rows_of_interest": int(len(rows)),
+            "sparse_discretize_s": disc_s, "products_per_step": best["products"] / (N - 1),
+            "algorithmic_gbs": best["bytes"] / (best["run_ms"] * 1e-3) / 1e9,
+            "api": "reach_sparse_create + reach_discretize_box_sparse + reach_bffpsv18_boxes_lazy (best of 3, CUDA events)"}
 
 
 def build_zono_workload():
@@ -405,9 +435,11 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                 return out
 
             one_proj()
+            one_proj()
+            proj_steps = 5                      # a solve + project call is ~25 ms: a few more of them than of the 1.3 s full fetch
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
+            for _ in range(proj_steps):
                 one_proj()
             torch.cuda.synchronize()
             proj_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
@@ -416,7 +448,7 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                        "d2h_bytes_per_step": int(8 * n * (int(p.sum()) + N)), "steps": e2e_steps,
                        "api": "reach_glgm06_create + reach_glgm06_run_fetch (pinned host buffers; every zonotope of the "
                               "flowpipe copied back, batch by batch while later batches compute, as reach_inhomog! materialises them)",
-                       "projected": {"value": world * e2e_steps * (N - 1) / proj_s, "unit": "flowpipe steps/s",
+                       "projected": {"value": world * proj_steps * (N - 1) / proj_s, "unit": "flowpipe steps/s", "steps": proj_steps,
                                      "d2h_bytes_per_step": 2 * 2 * 8 * N,
                                      "api": "reach_glgm06_create + reach_glgm06_run + reach_flowpipe_project (solve + project(sol, vars): "
                                             "2-D boxes of every reach set computed on the device, only they are copied back)"}}
@@ -448,9 +480,9 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         # (30.4 TFLOP/s in isolation, profiles/r01/gemm_left_check_b200.log).
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None,
-                     # one 32-step launch (270 x 43488 x 270): dram read 96.0 MB + write 52.8 MB
-                     # (profiles/r01/ncu_glgm06_c2_raw_summary.txt); algorithmic 94.6 MB read + 94.6 MB write
-                     "traffic": 148.8e6,
+                     # one 64-step launch (270 x 86976 x 270) on 113 SMs: dram read 192.1 MB + write 150.1 MB
+                     # (profiles/r01/ncu_session4_kernels_summary.txt); algorithmic 189.2 MB read + 189.2 MB write
+                     "traffic": 342.2e6,
                      "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA)",
                      "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
                      "alone": {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",

@@ -280,6 +280,16 @@ def test_config_c2_full_size_properties(ctx):
             box = G[:, -n:]
             assert np.count_nonzero(box - np.diag(np.diag(box))) == 0 and np.all(np.diag(box) > 0)
         assert np.all(np.isfinite(G))
+    # (c) device-side projection of all 2000 reach sets (project_reach.jl:18-99) against the fetched zonotopes and the box hull
+    M = np.zeros((2, n)); M[0, 3] = 1.0; M[1] = np.random.default_rng(1).standard_normal(n)
+    Cp, Rp = fp.project(M)
+    for k in sorted(samples):
+        c, G = fp.step(k, int(p[k - 1]))
+        assert_close(Cp[:, k - 1], M @ c, f"projected centre {k}")
+        assert_close(Rp[:, k - 1], np.abs(M @ G).sum(axis=1), f"projected radius {k}")
+        lo, hi = fp.box(k)
+        assert_close(Cp[0, k - 1] - Rp[0, k - 1], lo[3], f"coordinate projection = box hull {k}")
+    assert np.all(np.isfinite(Cp)) and np.all(Rp > 0)
     c_a, G_a = fp.step(1999)
     fp.run()
     c_b, G_b = fp.step(1999)
