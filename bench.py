@@ -105,8 +105,8 @@ _KEEP = []
 # ---------------------------------------------------------------------------------------------------------
 
 def build_box_workload(name):
-    """Discretised BFFPSV18 problem of config C1/C3/C4 (inputs of the hot loop).  Discretisation runs on the host
-    here only to PREPARE the synthetic inputs (outside every timed region)."""
+    """Discretised BFFPSV18 problem of config C1/C3 on the HOST, for the CPU legs only (`cpu_baseline`, `--impl reference`):
+    the GPU arm prepares its inputs with the library's own device discretisation."""
     from oracle import reach_oracle as orc          # bench.py may use the oracle to prepare inputs / CPU arm only
     from reachability_jl_b200 import workloads as wl
     w = {"C1": wl.building, "C3": wl.fom}[name]()
@@ -141,15 +141,14 @@ class _Disc:
 def run_bffpsv18(args, rank, world, dist):
     import torch
     import reachability_jl_b200 as rb
+    import math
+    from reachability_jl_b200 import workloads as wl
     big = args.workload == "C4"
-    if big:
-        # n = 10913: the host discretisation (a dense 10913^3 expm + Phi2 series in numpy) would take many minutes, so the
-        # inputs of the loop are prepared by the library's own device discretisation (outside every timed region)
-        from reachability_jl_b200 import workloads as wl
-        w, D, N = wl.mna5(), None, None
-        N = int(w.extra["N"])
-    else:
-        w, D, N = build_box_workload(args.workload)
+    # The inputs of the loop (Phi, box of Omega0, discretised input) come from the library's own device discretisation,
+    # outside every timed region: nothing under oracle/ is on this arm's path (the CPU legs below use it).
+    w = {"C1": wl.building, "C3": wl.fom, "C4": wl.mna5}[args.workload]()
+    D = None
+    N = int(w.extra["N"]) if big else int(math.ceil(w.T / w.delta))          # reach.jl:54
     if args.flow_steps:
         N = args.flow_steps
     n, m = w.n, w.m
@@ -161,11 +160,9 @@ def run_bffpsv18(args, rank, world, dist):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")    # > 126 MB L2
     with torch.cuda.stream(stream):
         ctx = rb.Context(dev, stream=stream.cuda_stream)
-        disc_s = None
-        if big:
-            t0 = time.perf_counter()
-            D = _Disc(ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU))
-            disc_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        D = _Disc(ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU))
+        disc_s = time.perf_counter() - t0
         # ---- device-resident arm: inputs uploaded once, K complete flowpipes timed ------------------------
         plan = ctx.boxplan(D.Phi, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
         # C4: a full flowpipe is minutes of DMMA work, so the warm-up passes run a truncated flowpipe of the same problem
@@ -275,9 +272,9 @@ def run_bffpsv18(args, rank, world, dist):
                    "rows_per_gpu": R, "parallelism": f"row-block sharding x{world}, Phi replicated" if world > 1 else "single GPU",
                    "l2": "256 MB L2 flush between timed iterations; " + ("Phi (953 MB) and the power stacks exceed L2" if big else
                                                                          "power stacks 2 x 132 MB exceed L2"),
+                   "device_discretize_s": disc_s,
                    **({"warmup_note": f"warm-up passes run the first {warm_N} reach sets of the same problem (a full flowpipe is "
-                                      f"{2.0 * R * n * n * (N - 1) / 1e12:.0f} TFLOP on this rank)",
-                       "device_discretize_s": disc_s} if big else {})},
+                                      f"{2.0 * R * n * n * (N - 1) / 1e12:.0f} TFLOP on this rank)"} if big else {})},
         "e2e": {"value": e2e_steps * flow_steps / e2e_s if e2e_steps else None, "unit": "flowpipe steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "reach_bffpsv18_boxes (host buffers, pinned)",
                 "with_discretize": {"value": flow_steps / solve_s if solve_s else None, "unit": "flowpipe steps/s",
@@ -330,8 +327,8 @@ def run_c4_lazy(w, dev, N, nrows=31):
 
 
 def build_zono_workload():
-    """Discretised GLGM06 problem of config C2 (ISS-shaped, n=270, max_order 10): Omega0 (already reduce_order'ed,
-    GLGM06/post.jl:20), V and Phi.  Host-side preparation only (outside every timed region)."""
+    """Discretised GLGM06 problem of config C2 (ISS-shaped, n=270, max_order 10) on the HOST, for the CPU legs only: Omega0
+    (already reduce_order'ed, GLGM06/post.jl:20), V and Phi."""
     from oracle import reach_oracle as orc
     from reachability_jl_b200 import workloads as wl
     w = wl.iss()
@@ -355,16 +352,23 @@ def run_glgm06(args, rank, world, dist, e2e=True):
     but is latency-bound at n = 270: SURVEY.md section 8e)."""
     import torch
     import reachability_jl_b200 as rb
-    w, D, Om, N = build_zono_workload()
-    if args.flow_steps:
-        N = args.flow_steps
-    n, p0, pV, r = w.n, Om.ngens, D.V.ngens, w.max_order
+    from reachability_jl_b200 import api, workloads as wl
+    w = wl.iss()
+    N = args.flow_steps or int(round(w.T / w.delta))                         # GLGM06/post.jl:12
+    n, r = w.n, w.max_order
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
     with torch.cuda.stream(stream):
         ctx = rb.Context(dev, stream=stream.cuda_stream)
+        # discretised problem from the product path itself (device expm / Phi2 + the host-side zonotope bookkeeping of
+        # api.discretize_zonotope, device reduce_order of Omega0: GLGM06/post.jl:15-20), outside every timed region
+        Phi, (c0z, G0z), Vz = api.discretize_zonotope(ctx, w.A, w.delta, w.c, w.r, w.B, (w.cU, w.rU))
+        G0red, _ = ctx.reduce_order(c0z, G0z, r)
+        D = _Disc(dict(Phi=Phi, V=_Disc(dict(c=Vz[0], G=Vz[1], ngens=Vz[1].shape[1]))))
+        Om = _Disc(dict(c=c0z, G=G0red, ngens=G0red.shape[1]))
+        p0, pV = Om.ngens, D.V.ngens
         fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, 0)
 
         def one_flowpipe():
@@ -526,31 +530,30 @@ def run_ensemble(args, rank, world, dist):
     splits of BASELINE.json's config on 8 GPUs), members sharded by rank, no collective: weak scaling."""
     import torch
     import reachability_jl_b200 as rb
-    from oracle import reach_oracle as orc
-    from reachability_jl_b200 import workloads as wl, sharding
+    from reachability_jl_b200 import api, workloads as wl, sharding
     w = wl.heli28()
     n = w.n
     per_gpu = 512
     total = per_gpu * world
-    N = args.flow_steps or orc.n_steps_glgm06(w.T, w.delta)
-    Phi = orc.exp_Adelta(w.A, w.delta)
-    P2 = orc.Phi2(np.abs(w.A), w.delta)
+    N = args.flow_steps or int(round(w.T / w.delta))                      # GLGM06/post.jl:12
     cs, rs = wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])           # 4096 sub-boxes of X0
     sl = sharding.shard_batch(total, rank, world)
     cs, rs = cs[:, sl], rs[:, sl]
-    D0 = orc.discretize_zonotope(w.A, orc.Box(cs[:, 0], rs[:, 0]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2)
-    p = D0.Omega0.ngens
-    c0s = np.zeros((n, per_gpu), order="F")
-    G0s = np.zeros((n, p, per_gpu), order="F")
-    for b in range(per_gpu):
-        Db = orc.discretize_zonotope(w.A, orc.Box(cs[:, b], rs[:, b]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2)
-        c0s[:, b], G0s[:, :, b] = Db.Omega0.c, Db.Omega0.G
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
     with torch.cuda.stream(stream):
         ctx = rb.Context(dev, stream=stream.cuda_stream)
+        # every member's Omega0 from the product path (device discretisation + host-side zonotope bookkeeping), untimed
+        c0s = G0s = Phi = None
+        for b in range(per_gpu):
+            Phi, (c0b, G0b), _ = api.discretize_zonotope(ctx, w.A, w.delta, cs[:, b], rs[:, b], remove_zero_generators=False)
+            if c0s is None:
+                p = G0b.shape[1]
+                c0s = np.zeros((n, per_gpu), order="F")
+                G0s = np.zeros((n, p, per_gpu), order="F")
+            c0s[:, b], G0s[:, :, b] = c0b, G0b
         ens = ctx.ensemble(Phi, c0s, G0s, N)
 
         def one():
