@@ -8,10 +8,10 @@
 // The reference evaluates every row with a Krylov `expmv` (Expokit, tolerance 1e-7) from scratch at every step.  B200
 // design: the block of rows of interest W_k = e^{kδA}[rows, :] is kept TRANSPOSED on the device (n x R, the R values of
 // one state contiguous) and advanced by  W_kᵀ = e^{δAᵀ} W_{k-1}ᵀ  -- the same recurrence as the dense path
-// (reach_blocks.jl:217-218) -- with a scaled truncated Taylor series of sparse-matrix x dense-block products carried to
-// full double precision (‖δA‖/s <= 1, m terms until the remainder is below 2^-64).  Julia's SparseMatrixCSC of A *is* the
+// (reach_blocks.jl:217-218) -- with a scaled truncated Taylor series (Horner form) of sparse-matrix x dense-block products
+// carried to full double precision (‖δA‖/s <= 2, m terms until the remainder is below 2^-64).  Julia's SparseMatrixCSC of A *is* the
 // CSR of Aᵀ, so the arrays cross the ABI untouched.  Every product is one HBM/L2-bound kernel: nnz·12 B of matrix +
-// 16·n·R B of block traffic; the per-step box epilogue is a column reduction of the same block.
+// 24·n·R B of block traffic; the per-step box epilogue is a column reduction of the same block.
 #include "common.cuh"
 #include "../../include/reach.h"
 #include <cmath>
@@ -365,7 +365,7 @@ void spmm(SparseSys* S, const Csr& M, int64_t ld, const double* T, double* Tn, c
     REACH_CUDA(cudaGetLastError());
     S->ctx->launches++;
     S->last_products++;
-    S->last_bytes += 12.0 * (double)S->nnz + 8.0 * (double)S->n * ld * ((Tn ? 1 : 0) + (Yout ? 2 : 0) + 1);
+    S->last_bytes += 12.0 * (double)S->nnz + 8.0 * (double)S->n * ld * (1 + (Tn ? 1 : 0) + (Yin ? 1 : 0) + (Yout ? 1 : 0));
 }
 
 // scaling s and number of Taylor terms m for theta_total = ‖δ M‖: the pair with the fewest products s*m among
@@ -390,18 +390,20 @@ void taylor_plan(double theta_total, int& s, int& m) {
     }
 }
 
-// W <- e^{δ op(M)} W for a row-block W (n x ld); T0, T1, W2: workspaces of the same size.  Returns the buffer that holds
-// the result (W or W2: the accumulation ping-pongs so that no product reads a block it is writing).
+// W <- e^{δ op(M)} W for a row-block W (n x ld); W2, T0, T1: workspaces of the same size.  Returns the buffer that holds
+// the result (W or W2).  The truncated series is evaluated in HORNER form,
+//     t_m = v,   t_{j-1} = v + (δ / (s j)) M t_j   (j = m .. 1),   e^{δM/s} v ≈ t_0,
+// one fused product per term that gathers t_j, reads v and writes t_{j-1}: three block passes per term instead of the four
+// of a running sum (term in, term out, accumulator in and out), which is what counts once the block no longer fits in L2.
 double* expm_action(SparseSys* S, const Csr& M, double delta, int64_t ld, double* W, double* W2, double* T0, double* T1) {
     int s, m;
     taylor_plan(std::fabs(delta) * std::max(S->norm_row, S->norm_col), s, m);
     for (int rep = 0; rep < s; ++rep) {
-        spmm<false>(S, M, ld, W, T0, W, W2, delta / s);                                   // term 1: W2 = W + (δ/s) M W
-        double* t = T0;
-        double* tn = T1;
-        for (int j = 2; j <= m; ++j) {
-            spmm<false>(S, M, ld, t, tn, W2, W2, delta / (s * (double)j));                // term j, accumulated in place
-            std::swap(t, tn);
+        const double* t = W;                                    // t_m = v
+        for (int j = m; j >= 1; --j) {
+            double* out = j == 1 ? W2 : (t == T0 ? T1 : T0);    // the last term lands in the other W buffer
+            spmm<false>(S, M, ld, t, nullptr, W, out, delta / (s * (double)j));
+            t = out;
         }
         std::swap(W, W2);
     }
@@ -601,27 +603,16 @@ void sparse_discretize_box(SparseSys* S, double delta, int32_t algorithm, const 
 }
 
 // reach_blocks! for a SparseMatrixExp (lazy rows), box blocks: see the header of this file.
-void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
-                           int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
-                           const int32_t* rows, int64_t N, double* centers, double* radii) {
+// One panel of rows of interest (hrows[0 .. R)): the whole time loop for these rows; results go to the host arrays
+// centers / radii (leading dimension ldo = all rows of the call) at row offset `row0`.
+static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
+                             int64_t ldmu, const double* cU, const double* rU, const double* rpsi, const int* hrows_ptr,
+                             int64_t R, int64_t N, double* centers, double* radii, int64_t ldo, int64_t row0) {
     Ctx* ctx = S->ctx;
     const int64_t n = S->n;
-    REACH_REQUIRE(c0 && r0 && N >= 1 && centers && radii, "reach_bffpsv18_boxes_lazy: bad arguments");
-    if (m == 0 || !MU) { m = 0; MU = nullptr; }
-    REACH_REQUIRE(m == 0 || (cU && rU && rpsi && ldmu >= n), "reach_bffpsv18_boxes_lazy: inputs need MU, cU, rU, rpsi");
-    std::vector<int> hrows;
-    if (rows) {
-        REACH_REQUIRE(nrows >= 1, "reach_bffpsv18_boxes_lazy: nrows must be positive");
-        for (int64_t l = 0; l < nrows; ++l) {
-            REACH_REQUIRE(rows[l] >= 0 && rows[l] < n, "reach_bffpsv18_boxes_lazy: row index out of range");
-            hrows.push_back(rows[l]);
-        }
-    } else {
-        nrows = n;
-        for (int64_t l = 0; l < n; ++l) hrows.push_back((int)l);
-    }
-    const int64_t R = nrows, ld = block_ld(R);
+    const int64_t ld = block_ld(R);
     cudaStream_t st = ctx->stream;
+    struct { const int* p; const int* data() const { return p; } } hrows{hrows_ptr};
     std::vector<void*> tmp;
     auto alloc = [&](size_t count) { double* p = dnew<double>(ctx, count); tmp.push_back(p); return p; };
     auto free_all = [&]() { for (void* p : tmp) ctx_free(ctx, p); tmp.clear(); };
@@ -650,7 +641,6 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
             REACH_CUDA(cudaMemcpyAsync(dcu, cU, m * 8, cudaMemcpyHostToDevice, st));
             REACH_CUDA(cudaMemcpyAsync(dru, rU, m * 8, cudaMemcpyHostToDevice, st));
         }
-        S->last_products = 0; S->last_bytes = 0;
         REACH_CUDA(cudaEventRecord(ctx->ev0, st));
         lazy_init_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>((int)n, (int)R, drows, dc0, dr0, dpsi, (int)m, dMU, dcu, dru,
                                                                      cW, rW, dC, dR);
@@ -734,20 +724,53 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
         }
         REACH_CUDA(cudaGetLastError());
         REACH_CUDA(cudaEventRecord(ctx->ev1, st));
-        REACH_CUDA(cudaMemcpyAsync(centers, dC, sizeof(double) * R * N, cudaMemcpyDeviceToHost, st));
-        REACH_CUDA(cudaMemcpyAsync(radii, dR, sizeof(double) * R * N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpy2DAsync(centers + row0, ldo * 8, dC, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpy2DAsync(radii + row0, ldo * 8, dR, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
         REACH_CUDA(cudaStreamSynchronize(st));
         if (gexec) cudaGraphExecDestroy(gexec);
         if (graph) cudaGraphDestroy(graph);
         float ms = 0;
         REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        S->last_ms = ms;
+        S->last_ms += ms;
     } catch (...) {
         cudaStreamSynchronize(st);
         free_all();
         throw;
     }
     free_all();
+}
+
+// reach_blocks! for a SparseMatrixExp (lazy rows), box blocks: see the header of this file.  The rows of interest are
+// independent of each other, so they are processed in PANELS whose working set (three n x panel blocks of the Horner
+// recurrence) stays in the 126 MB L2: every gathered block row is then re-read from L2 instead of HBM by the ~nnz/n
+// matrix rows that reference it (all 10913 rows of C4 at once: 39 steps/s, HBM-bound; in panels: see profiles/).
+void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
+                           int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
+                           const int32_t* rows, int64_t N, double* centers, double* radii) {
+    const int64_t n = S->n;
+    REACH_REQUIRE(c0 && r0 && N >= 1 && centers && radii, "reach_bffpsv18_boxes_lazy: bad arguments");
+    if (m == 0 || !MU) { m = 0; MU = nullptr; }
+    REACH_REQUIRE(m == 0 || (cU && rU && rpsi && ldmu >= n), "reach_bffpsv18_boxes_lazy: inputs need MU, cU, rU, rpsi");
+    std::vector<int> hrows;
+    if (rows) {
+        REACH_REQUIRE(nrows >= 1, "reach_bffpsv18_boxes_lazy: nrows must be positive");
+        for (int64_t l = 0; l < nrows; ++l) {
+            REACH_REQUIRE(rows[l] >= 0 && rows[l] < n, "reach_bffpsv18_boxes_lazy: row index out of range");
+            hrows.push_back(rows[l]);
+        }
+    } else {
+        nrows = n;
+        for (int64_t l = 0; l < n; ++l) hrows.push_back((int)l);
+    }
+    // panel width: three blocks of n x panel doubles within ~64 MB (half of L2: measured best on C4), a multiple of 32
+    int64_t panel = std::max<int64_t>(32, (((int64_t)64 << 20) / (3 * 8 * n)) / 32 * 32);
+    if (const char* e = getenv("REACH_LAZY_PANEL")) panel = std::max<int64_t>(4, atoll(e));
+    const int64_t npan = ceil_div(nrows, panel);
+    const int64_t width = round_up(ceil_div(nrows, npan), 4);        // equal panels
+    S->last_ms = 0; S->last_products = 0; S->last_bytes = 0;
+    for (int64_t r0p = 0; r0p < nrows; r0p += width)
+        lazy_boxes_panel(S, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, hrows.data() + r0p, std::min(width, nrows - r0p), N, centers,
+                         radii, nrows, r0p);
 }
 
 }  // namespace reach

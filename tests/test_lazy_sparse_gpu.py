@@ -152,6 +152,10 @@ def test_graph_replay_and_eager_steps_produce_identical_bits(ctx, monkeypatch):
     monkeypatch.setenv("REACH_LAZY_NO_GRAPH", "1")
     C2, R2 = S.bffpsv18_boxes(delta, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
     assert np.array_equal(C1, C2) and np.array_equal(R1, R2)
+    # rows of interest are processed in L2-sized panels; every row is independent, so the panel width cannot change a bit
+    monkeypatch.setenv("REACH_LAZY_PANEL", "12")
+    C3, R3 = S.bffpsv18_boxes(delta, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi, rows)
+    assert np.array_equal(C1, C3) and np.array_equal(R1, R3)
     Co, Ro = orc.bffpsv18_reach(D, N, rows)
     assert_close(C1.T, Co, "centres")
     assert_close(R1.T, Ro, "radii")

@@ -13,9 +13,9 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 check_dense = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 w = wl.mna5()
 n = w.n
-rows = np.unique(np.concatenate([np.arange(10), np.linspace(0, n - 1, max(R - 10, 1)).astype(int)]))[:R].astype(np.int32)
+rows = None if R >= n else np.unique(np.concatenate([np.arange(10), np.linspace(0, n - 1, max(R - 10, 1)).astype(int)]))[:R].astype(np.int32)
 As = sp.csc_matrix(w.A)
-print(f"{w.name}: n={n}, nnz={As.nnz}, rows of interest {len(rows)}, N={N}", flush=True)
+print(f"{w.name}: n={n}, nnz={As.nnz}, rows of interest {n if rows is None else len(rows)}, N={N}", flush=True)
 with rb.Context(0) as ctx:
     S = ctx.sparse(As)
     for it in range(2):
