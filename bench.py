@@ -409,12 +409,52 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         launches = ctx.launch_count() - launches0 + args.steps
         p = fp.ngens()
         pmax = int(p.max())
+        map_info = fp.map_info()
         # diagnostics pass outside the timed region: the same flowpipe with every kernel alone on one stream
         fp.set_serial(True)
         fp.run()
         alone = fp.timing()
         fp.set_serial(False)
         fp.close()
+        # Phi of this workload is structurally sparse (decoupled modes), so the library maps the generators with an ELL
+        # sparse product.  The dense DMMA GEMM path (what a dense Phi gets) is timed too, same flowpipe, same results:
+        dense = None
+        if map_info["sparse_levels"] > 0:
+            os.environ["REACH_GLGM06_DENSE"] = "1"
+            try:
+                fd = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, 0)
+            finally:
+                del os.environ["REACH_GLGM06_DENSE"]
+            for _ in range(2):
+                flush.zero_()
+                fd.run()
+            dtt = dict(gemm_ms=0.0, gemm_flops=0.0, reduce_ms=0.0, chain_ms=0.0)
+            evd0, evd1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            evd0.record(stream)
+            for _ in range(args.steps):
+                flush.zero_()
+                fd.run()
+                t = fd.timing()
+                for key in dtt:
+                    dtt[key] += t[key]
+            evd1.record(stream)
+            torch.cuda.synchronize()
+            dms = evd0.elapsed_time(evd1)
+            fd.set_serial(True)
+            fd.run()
+            dalone = fd.timing()
+            fd.close()
+            dense = {"value": world * args.steps * (N - 1) / (dms * 1e-3), "unit": "flowpipe steps/s", "ms_per_step": dms / args.steps,
+                     "note": "REACH_GLGM06_DENSE=1: linear_map(Phi^w, .) as the left-multiplication DMMA GEMM (the path of a dense Phi)",
+                     "roofline": {"bound": "tensor", "achieved": dtt["gemm_flops"] / (dtt["gemm_ms"] * 1e-3) / 1e12,
+                                  "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": dtt["gemm_flops"] / (dtt["gemm_ms"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                                  "traffic": 342.2e6, "kernel": "gemm_dmma_kernel<3,true> in situ (64-step launches on the SMs the "
+                                  "partition leaves to it)", "kernel_ms_total": dtt["gemm_ms"], "kernel_share_of_step": dtt["gemm_ms"] / dms,
+                                  "alone": {"gemm_tflops": dalone["gemm_flops"] / (dalone["gemm_ms"] * 1e-3) / 1e12,
+                                            "gemm_ms": dalone["gemm_ms"], "numerics_ms": dalone["numerics_ms"],
+                                            "chain_ms": dalone["chain_ms"], "run_ms": dalone["run_ms"]}}}
         # ---- end to end: host buffers in, all N zonotopes back in host memory (what reach_inhomog! fills) ----
         e2e_obj = None
         if e2e and not args.no_e2e:
@@ -477,6 +517,44 @@ def run_glgm06(args, rank, world, dist, e2e=True):
     red_s = tt["reduce_ms"] * 1e-3
     gemm_tf = tt["gemm_flops"] / (tt["gemm_ms"] * 1e-3) / 1e12 if tt["gemm_ms"] else None
     nbatches = int(tt["gemm_launches"])
+    numerics = {"kernel": "batched numerics of the two Girard reductions (wbox_partial, wseq, rank_r, apply_r, finalize_r, "
+                          "expand_diag; TMA-staged gather), side stream, in situ",
+                "bound": "hbm", "achieved": alg_bytes / red_s / 1e9 if red_s > 0 else None, "peak": hbm, "unit": "GB/s",
+                "frac": alg_bytes / red_s / 1e9 / hbm if red_s > 0 else None, "peak_source": hbm_src,
+                "kernel_ms_total": tt["reduce_ms"],
+                "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
+                # dram bytes of the dominant numerics kernel, one 64-step launch of apply_r_kernel<8> (ncu --set full,
+                # profiles/r01/ncu_session4_kernels_summary.txt): 163.9 MB read + 288.8 MB written
+                "traffic": 452.7e6,
+                "note": "achieved counts SURVEY 8(d)'s ALGORITHMIC bytes (40.9 MB per step: score pass + gather pass + write of both "
+                        "reductions); the archive/reference design moves about a third of that (W is never rewritten, scores travel "
+                        "with the references, box generators are tags), so frac can exceed 1"}
+    chain = {"kernel": "chain_kernel (one persistent CTA on its own SM, key logic only)", "kernel_ms_total": tt["chain_ms"],
+             "us_per_flowpipe_step": 1e3 * tt["chain_ms"] / (flow_steps * args.steps)}
+    alone_obj = {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",
+                 "map_ms": alone["gemm_ms"], "numerics_ms": alone["numerics_ms"], "chain_ms": alone["chain_ms"],
+                 "numerics_gbs": glgm06_algorithmic_bytes_per_step(n, p0, pV, r) * flow_steps / (alone["numerics_ms"] * 1e-3) / 1e9,
+                 "run_ms": alone["run_ms"]}
+    map_bytes = 16.0 * n * (p0 + pV + 2) * flow_steps * args.steps          # read X, write Y: 8 n q each way per step
+    if map_info["sparse_levels"] > 0:
+        # structurally sparse Phi: no GEMM on the path; the HBM-bound numerics are the dominant kernels by bytes, the selection
+        # chain is the critical path by latency
+        map_obj = {"kind": "ell_sparse", "nnz_per_row": map_info["nnz_per_row"], "launches": nbatches,
+                   "kernel": "ell_left_kernel (Phi^w in ELL form, thread per state row, 16 generators per CTA)",
+                   "kernel_ms_total": tt["gemm_ms"], "algorithmic_gbs": map_bytes / (tt["gemm_ms"] * 1e-3) / 1e9 if tt["gemm_ms"] else None,
+                   "note": "Phi of this workload (decoupled modes) and its powers have 2 non-zeros per row; detected at creation, "
+                           "results equal the dense GEMM's (tests/test_glgm06_gpu.py::test_sparse_phi_map_equals_dense_gemm); "
+                           "`dense_gemm_path` times the DMMA path on the same flowpipe"}
+        roof = dict(numerics, alone=alone_obj, selection_chain=chain)
+    else:
+        map_obj = {"kind": "dense_dmma_gemm", "launches": nbatches}
+        roof = {"bound": "tensor", "achieved": gemm_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None, "traffic": 342.2e6,
+                "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA), in situ",
+                "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
+                "alone": alone_obj, "algorithmic_flops_per_flowpipe_step": 2.0 * n * n * (p0 + pV + 2),
+                "peak_source": "FP64 DMMA register-resident loop measured on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl)",
+                "second_kernel": numerics, "selection_chain": chain}
     return {
         "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -489,33 +567,9 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         "e2e": e2e_obj,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        # dominant kernel by work: the left-multiplication DMMA GEMM that maps the generators of a whole batch of steps.
-        # Its CUDA-event time is taken IN SITU, i.e. while the selection chain and the batched numerics of the
-        # neighbouring batches share the SMs with it (three overlapping streams), so it understates the kernel alone
-        # (30.4 TFLOP/s in isolation, profiles/r01/gemm_left_check_b200.log).
-        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": gemm_tf / FP64_DMMA_PEAK_TFLOPS if gemm_tf else None,
-                     # one 64-step launch (270 x 86976 x 270) on 113 SMs: dram read 192.1 MB + write 150.1 MB
-                     # (profiles/r01/ncu_session4_kernels_summary.txt); algorithmic 189.2 MB read + 189.2 MB write
-                     "traffic": 342.2e6,
-                     "kernel": "gemm_dmma_kernel<3,true> (Phi^s * archive slots [G0|GV|c0|cV], left multiplication, tensor-map TMA)",
-                     "launches": nbatches, "kernel_ms_total": tt["gemm_ms"], "kernel_share_of_step": tt["gemm_ms"] / ms,
-                     "alone": {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",
-                               "gemm_tflops": alone["gemm_flops"] / (alone["gemm_ms"] * 1e-3) / 1e12,
-                               "gemm_frac": alone["gemm_flops"] / (alone["gemm_ms"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
-                               "gemm_ms": alone["gemm_ms"], "numerics_ms": alone["numerics_ms"], "chain_ms": alone["chain_ms"],
-                               "numerics_gbs": glgm06_algorithmic_bytes_per_step(n, p0, pV, r) * flow_steps / (alone["numerics_ms"] * 1e-3) / 1e9,
-                               "run_ms": alone["run_ms"]},
-                     "algorithmic_flops_per_flowpipe_step": 2.0 * n * n * (p0 + pV + 2),
-                     "peak_source": "FP64 DMMA register-resident loop measured on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl)",
-                     "second_kernel": {"kernel": "batched numerics of the two Girard reductions (wbox_partial, wseq, rank_r, apply_r, "
-                                                 "finalize_r, expand_diag), second side stream, in situ",
-                                       "bound": "hbm", "achieved": alg_bytes / red_s / 1e9 if red_s > 0 else None, "peak": hbm,
-                                       "unit": "GB/s", "frac": alg_bytes / red_s / 1e9 / hbm if red_s > 0 else None,
-                                       "peak_source": hbm_src, "kernel_ms_total": tt["reduce_ms"],
-                                       "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r)},
-                     "selection_chain": {"kernel": "chain_kernel (one persistent CTA, key logic only)", "kernel_ms_total": tt["chain_ms"],
-                                         "us_per_flowpipe_step": 1e3 * tt["chain_ms"] / (flow_steps * args.steps)}},
+        "roofline": roof,
+        "generator_map": map_obj,
+        **({"dense_gemm_path": dense} if dense is not None else {}),
     }
 
 
@@ -784,8 +838,8 @@ def main():
         if world == 1 and args.workload == "C3" and not args.no_secondary and not args.flow_steps:
             # the metric names two configurations: the n=270 GLGM06 one rides along as a summary object
             sec = run_glgm06(args, rank, world, dist)
-            keep = ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "gpu_launches")
-            out["glgm06_c2"] = {k: sec[k] for k in keep}
+            keep = ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "gpu_launches", "generator_map", "dense_gemm_path")
+            out["glgm06_c2"] = {k: sec[k] for k in keep if k in sec}
             if not args.no_cpu_baseline:
                 out["glgm06_c2"]["cpu_baseline"] = cpu_baseline_glgm06()
         print(json.dumps(out), flush=True)

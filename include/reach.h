@@ -221,6 +221,11 @@ REACH_API int32_t reach_flowpipe_timing(reach_flowpipe* fp, double* run_ms, doub
 /* CUDA-event time of the last run spent in the selection chain (side stream) and in the batched numerics (second side
  * stream); the two overlap each other and the GEMMs. */
 REACH_API int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, double* numerics_ms);
+/* How linear_map(Phi^w, .) runs for this flowpipe: sparse_levels > 0 means Phi and the powers the run uses are structurally
+ * sparse (at most nnz_per_row <= 8 non-zeros per row, e.g. decoupled modes) and the generator map is an ELL sparse product
+ * (HBM-bound) instead of the dense DMMA GEMM; the results are those of the dense product (the skipped terms are exact
+ * zeros).  Detected at creation; the environment variable REACH_GLGM06_DENSE=1 forces the GEMM. */
+REACH_API int32_t reach_flowpipe_map_info(reach_flowpipe* fp, int32_t* sparse_levels, int32_t* nnz_per_row);
 /* Diagnostics: serial != 0 makes the next runs issue everything on one stream (no overlap), so that the per-kernel
  * CUDA-event times of reach_flowpipe_timing / _phase_ms are those of each kernel running alone. */
 REACH_API int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial);

@@ -420,6 +420,12 @@ class Flowpipe:
         self.ctx._check(self.ctx.lib.reach_glgm06_run_fetch(self._h, dptr(centers), dptr(G), G.shape[1]))
         return self
 
+    def map_info(self):
+        """dict(sparse_levels, nnz_per_row): whether the generator map runs as an ELL sparse product (structurally sparse Φ)."""
+        a, b = C.c_int32(), C.c_int32()
+        self.ctx._check(self.ctx.lib.reach_flowpipe_map_info(self._h, C.byref(a), C.byref(b)))
+        return dict(sparse_levels=int(a.value), nnz_per_row=int(b.value))
+
     def set_serial(self, serial: bool):
         """Diagnostics: run without stream overlap so that per-kernel times are those of each kernel alone."""
         self.ctx._check(self.ctx.lib.reach_flowpipe_set_serial(self._h, int(bool(serial))))

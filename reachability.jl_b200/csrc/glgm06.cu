@@ -43,7 +43,12 @@ constexpr int COPY_JB = 8;          // columns a warp resolves (one per lane) an
 constexpr int NUM_WARPS = 4;        // warps per CTA of the TMA-staged numerics kernels (wbox_partial, apply_r)
 constexpr int STAGE_BYTES = 16384;  // staging per warp: JB = min(8, STAGE_BYTES / column bytes) columns in flight
 constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
-constexpr int CHAIN_THREADS = 256;    // small enough to share an SM with the numerics kernels (16 K registers)
+#ifndef REACH_CHAIN_THREADS
+#define REACH_CHAIN_THREADS 512
+#endif
+// threads of the single selection-chain CTA (it owns an SM in the pipelined run): C2 chain time 10.8 ms with 256 threads,
+// 9.7 ms with 512, 11.2 ms with 1024 (-DREACH_CHAIN_THREADS=... to rebuild)
+constexpr int CHAIN_THREADS = REACH_CHAIN_THREADS;
 constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
 
 struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of step k  (GLGM06/reach.jl:54-55)
@@ -335,7 +340,7 @@ __device__ unsigned long long g_chain_prof[8];
 #endif
 
 template <bool SMEM, bool RECORD>
-__global__ void __launch_bounds__(CHAIN_THREADS, 3) chain_kernel(GP g, int k0, int cnt, double* scr) {
+__global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) chain_kernel(GP g, int k0, int cnt, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     __shared__ unsigned orm[2 * MAX_IT];
     __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
@@ -1112,6 +1117,66 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     hi[(int64_t)b * n + i] = ci + s;
 }
 
+// ---- structurally sparse Phi: the generator map as a sparse product -------------------------------------------------------
+// Decoupled / block-diagonal systems (the ISS-shaped C2: 135 independent 2 x 2 modes) have a Phi = e^{A delta} with a handful of
+// non-zeros per row, and so have all its powers.  linear_map(Phi^w, Z) (GLGM06/reach.jl:16,48,54) is then an ELL sparse x
+// generator-block product: HBM-bound (read X once, write Y once) instead of 2 n^2 flop per generator.  The products that
+// are skipped are exact zeros, and the non-zero terms of a row are added in ascending k like the DMMA k-loop does, so the
+// result equals the dense GEMM's.  Detection is automatic at flowpipe creation (REACH_GLGM06_DENSE=1 forces the GEMM).
+constexpr int ELL_MAX = 8;
+
+// One warp per row i of P (n x n, column-major, ld): non-zeros compacted in ascending k into idx/val[i*ELL_MAX + .]; count[i].
+__global__ void __launch_bounds__(256) ell_build_kernel(int n, const double* __restrict__ P, int64_t ld, int* __restrict__ idx,
+                                                        double* __restrict__ val, int* __restrict__ count) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    int base = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        const double v = k < n ? P[(int64_t)k * ld + i] : 0.0;
+        const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
+        const int pos = base + __popc(mask & ((1u << lane) - 1u));
+        if (v != 0.0 && pos < ELL_MAX) {
+            idx[i * ELL_MAX + pos] = k;
+            val[i * ELL_MAX + pos] = v;
+        }
+        base += __popc(mask);
+    }
+    for (int w = base + lane; w < ELL_MAX; w += 32) {      // pad: multiplies x[0] by zero
+        idx[i * ELL_MAX + w] = 0;
+        val[i * ELL_MAX + w] = 0.0;
+    }
+    if (lane == 0) count[i] = base;
+}
+
+// Y[:, g] = P X[:, g] for Q generator columns (ld doubles each).  Thread = row i (its ELL row lives in registers), CTA =
+// ELL_GPB generators: the gathered entries of a 2 KB column come from L1, the stores are coalesced.
+constexpr int ELL_GPB = 16;
+template <int W>
+__global__ void __launch_bounds__(1024) ell_left_kernel(int n, int ld, int64_t Q, const int* __restrict__ idx,
+                                                        const double* __restrict__ val, const double* __restrict__ X,
+                                                        double* __restrict__ Y) {
+    const int i = threadIdx.x;
+    int ji[W];
+    double vi[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        ji[w] = i < n ? idx[i * ELL_MAX + w] : 0;
+        vi[w] = i < n ? val[i * ELL_MAX + w] : 0.0;
+    }
+    const int64_t g0 = (int64_t)blockIdx.x * ELL_GPB;
+#pragma unroll 4
+    for (int u = 0; u < ELL_GPB; ++u) {
+        const int64_t g = g0 + u;
+        if (g >= Q || i >= n) continue;
+        const double* x = X + g * ld;
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc = fma(vi[w], x[ji[w]], acc);
+        Y[g * ld + i] = acc;
+    }
+}
+
 // ---- projection of a zonotope flowpipe: M * R_k (project_reach.jl:18-99, linear map of every reach set) -----------
 // One warp per generator column: lanes stride the column with 16-byte loads and carry the q <= 4 dot products with the
 // rows of M (Mt: q rows of n doubles); out[((k-1)*pmax + col)*q + row].  Columns beyond the set's count are zeroed.
@@ -1289,9 +1354,13 @@ struct Flowpipe {
     std::vector<Batch> sched;
     int64_t next_batch = 0;
     const DMat* pw = nullptr;
-    int sp = 0;
+    int sp = 0, shard_lvl = 0;
     GP g{};
     DMat Phi, PowA, PowB;
+    // ELL form of Phi^(2^l) for the first `ell_levels` doubling levels (structurally sparse Phi); width = non-zeros per row
+    int ell_levels = 0, ell_width = 0;
+    int* ell_idx = nullptr; double* ell_val = nullptr;       // [level][n][ELL_MAX]
+    bool force_dense = false;
     double* Hflow = nullptr;        // archive of Phi^j X: the flowpipe itself in the homogeneous case
     double* scr = nullptr;          // chain scratch when the W list does not fit in shared memory
     size_t chain_smem = 0;
@@ -1496,12 +1565,65 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             const int2 m1 = make_int2((int)p0, 0);
             REACH_CUDA(cudaMemcpyAsync(g.meta, &m1, sizeof(int2), cudaMemcpyHostToDevice, st));
         }
+        // structurally sparse Phi?  ELL forms of Phi^(2^l) for the doubling levels the run uses (see ell_left_kernel)
+        F->force_dense = getenv("REACH_GLGM06_DENSE") != nullptr;
+        if (F->phi_host.empty() && n >= 16 && !F->force_dense) {
+            int nlev = 1;
+            for (int64_t w = 1; w < s; w *= 2) ++nlev;
+            int* idx = (int*)own(dalloc<int>(ctx, (size_t)nlev * n * ELL_MAX));
+            double* val = (double*)own(dalloc<double>(ctx, (size_t)nlev * n * ELL_MAX));
+            int* cnt = (int*)own(dalloc<int>(ctx, n));
+            std::vector<int> hc(n);
+            const DMat* P = &F->Phi;
+            DMat* spare[2] = {&F->PowA, &F->PowB};
+            int sp = 0, width = 0;
+            for (int lvl = 0; lvl < nlev; ++lvl) {
+                ell_build_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>((int)n, P->p, P->ld, idx + (size_t)lvl * n * ELL_MAX,
+                                                                                 val + (size_t)lvl * n * ELL_MAX, cnt);
+                REACH_CUDA(cudaGetLastError());
+                ctx->launches++;
+                REACH_CUDA(cudaMemcpyAsync(hc.data(), cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+                REACH_CUDA(cudaStreamSynchronize(st));
+                const int mx = *std::max_element(hc.begin(), hc.end());
+                if (mx > ELL_MAX || (int64_t)mx * 8 > n) break;
+                width = std::max(width, mx);
+                F->ell_levels = lvl + 1;
+                if (lvl + 1 < nlev) {
+                    gemm_left(ctx, n, n, n, P->p, P->ld, P->p, P->ld, spare[sp]->p, spare[sp]->ld);
+                    P = spare[sp];
+                    sp ^= 1;
+                }
+            }
+            if (F->ell_levels < nlev) F->ell_levels = 0;      // mixed sparse / dense levels: not worth the bookkeeping
+            F->ell_width = width;
+            F->ell_idx = idx;
+            F->ell_val = val;
+        }
         REACH_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
         flowpipe_free(F);
         throw;
     }
     return F;
+}
+
+// slots Y = Phi^(2^lvl) X for Q generator columns: the ELL product when Phi is structurally sparse, else the DMMA GEMM
+static bool map_slots(Flowpipe* F, int lvl, const DMat& P, int64_t Q, const double* Xp, double* Yp) {
+    Ctx* ctx = F->ctx;
+    const int64_t n = F->n, ld = F->ld;
+    if (lvl < F->ell_levels) {
+        const int* idx = F->ell_idx + (size_t)lvl * n * ELL_MAX;
+        const double* val = F->ell_val + (size_t)lvl * n * ELL_MAX;
+        const unsigned grid = (unsigned)ceil_div(Q, ELL_GPB), block = (unsigned)round_up(n, 32);
+        if (F->ell_width <= 2) ell_left_kernel<2><<<grid, block, 0, ctx->stream>>>((int)n, (int)ld, Q, idx, val, Xp, Yp);
+        else if (F->ell_width <= 4) ell_left_kernel<4><<<grid, block, 0, ctx->stream>>>((int)n, (int)ld, Q, idx, val, Xp, Yp);
+        else ell_left_kernel<8><<<grid, block, 0, ctx->stream>>>((int)n, (int)ld, Q, idx, val, Xp, Yp);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return true;
+    }
+    gemm_left(ctx, n, Q, n, P.p, P.ld, Xp, ld, Yp, ld);
+    return false;
 }
 
 static cudaEvent_t next_event(Flowpipe* F, size_t& used) {
@@ -1646,14 +1768,15 @@ void flowpipe_run(Flowpipe* F) {
     F->gemm_launches = 0; F->gemm_flops = 0;
     REACH_CUDA(cudaEventRecord(ctx->ev0, st));
     std::vector<std::pair<size_t, size_t>> gemm_ev, red_ev;
+    int lvl = 0;        // doubling level of the current power Phi^(2^lvl)
     auto timed_gemm = [&](int64_t Q, const DMat& P, const double* Xp, double* Yp) {
         cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
         gemm_ev.push_back({ev_used - 2, ev_used - 1});
         REACH_CUDA(cudaEventRecord(e0, st));
-        gemm_left(ctx, n, Q, n, P.p, P.ld, Xp, ld, Yp, ld);
+        const bool sparse = map_slots(F, lvl, P, Q, Xp, Yp);
         REACH_CUDA(cudaEventRecord(e1, st));
         F->gemm_launches++;
-        F->gemm_flops += 2.0 * (double)n * (double)n * (double)Q;
+        if (!sparse) F->gemm_flops += 2.0 * (double)n * (double)n * (double)Q;
     };
     auto square = [&](const DMat& P, DMat& out) {
         cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
@@ -1783,10 +1906,11 @@ void flowpipe_run(Flowpipe* F) {
         }
         have += cnt;
         if (have < N && w < s) {
-            square(*pw, *spare[sp]);
+            if (F->ell_levels == 0) square(*pw, *spare[sp]);      // the ELL forms of all levels were built at creation
             pw = spare[sp];
             sp ^= 1;
             w *= 2;
+            ++lvl;
         }
     }
     if (!F->homog && !ev_num.empty()) REACH_CUDA(cudaStreamWaitEvent(st, ev_num.back(), 0));
@@ -1900,7 +2024,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         g.Y = F->Hflow;
         g.col0 = 0;
         if (phase == 0) {
-            F->next_batch = 0; F->pw = &F->Phi; F->sp = 0; F->ran = false;
+            F->next_batch = 0; F->pw = &F->Phi; F->sp = 0; F->shard_lvl = 0; F->ran = false;
             REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
             score_only(F, g, 0, 1, st);
         } else if (phase == 1) {
@@ -1923,8 +2047,8 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
     const size_t red_smem = numerics_smem(ld, jb);
     const int it = ld <= 256 ? 4 : (ld <= 512 ? 8 : 16);
     if (phase == 0) {
-        gemm_left(ctx, n, B.cnt * F->qloc, n, F->pw->p, F->pw->ld, F->Hflow + (B.have - B.w) * F->qloc * ld, ld,
-                  F->Hflow + B.have * F->qloc * ld, ld);
+        map_slots(F, F->shard_lvl, *F->pw, B.cnt * F->qloc, F->Hflow + (B.have - B.w) * F->qloc * ld,
+                  F->Hflow + B.have * F->qloc * ld);
         score_only(F, g, B.have, cnt, st);
     } else if (phase == 1) {
         sort_only(F, g, cnt, st);
@@ -1950,9 +2074,11 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         ctx->launches += 2;
         if (B.square_after) {
             DMat* spare[2] = {&F->PowA, &F->PowB};
-            gemm_left(ctx, n, n, n, F->pw->p, F->pw->ld, F->pw->p, F->pw->ld, spare[F->sp]->p, spare[F->sp]->ld);
+            if (F->ell_levels == 0)
+                gemm_left(ctx, n, n, n, F->pw->p, F->pw->ld, F->pw->p, F->pw->ld, spare[F->sp]->p, spare[F->sp]->ld);
             F->pw = spare[F->sp];
             F->sp ^= 1;
+            F->shard_lvl++;
         }
         F->next_batch = b + 1;
         if (b == nb - 1) {
@@ -2450,6 +2576,13 @@ void reach_ensemble_free(reach_ensemble* en) {
     cudaStreamSynchronize(en->ctx->stream);
     flowpipe_free(en->f);
     delete en;
+}
+
+int32_t reach_flowpipe_map_info(reach_flowpipe* fp, int32_t* sparse_levels, int32_t* nnz_per_row) {
+    if (!fp) return REACH_EINVAL;
+    if (sparse_levels) *sparse_levels = fp->f->ell_levels;
+    if (nnz_per_row) *nnz_per_row = fp->f->ell_levels ? fp->f->ell_width : 0;
+    return REACH_OK;
 }
 
 int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial) {

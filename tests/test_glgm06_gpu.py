@@ -333,3 +333,45 @@ def test_projection_rejects_bad_arguments(ctx):
     with pytest.raises(ReachError):
         fp.project(np.ones((2, 5)), Gp=np.zeros((2, 1, 4), order="F"))     # pmax too small
     fp.close()
+
+
+# ---- structurally sparse Phi: the generator map as an ELL sparse product ----------------------------------------------
+@pytest.mark.parametrize("n,m,N,r", [(40, 2, 45, 3), (33, 1, 70, 2)])
+def test_sparse_phi_map_equals_dense_gemm(ctx, n, m, N, r, monkeypatch):
+    """Decoupled 2 x 2 modes: Phi and its powers have two non-zeros per row, so linear_map(Phi^w, .) runs as a sparse
+    product.  Same results as the DMMA GEMM (forced with REACH_GLGM06_DENSE) -- the skipped terms are exact zeros -- and both
+    agree with the oracle, order-reduction selections included."""
+    g = np.random.default_rng(n)
+    A, X0, B, U, delta = _problem(500 + n, n, m, dense=False)
+    Phi = np.zeros((n, n))                       # exact block-diagonal exponential (scipy's Pade would fill in 1e-20 noise)
+    for i in range(n // 2):
+        blk = A[2 * i:2 * i + 2, 2 * i:2 * i + 2]
+        Phi[2 * i:2 * i + 2, 2 * i:2 * i + 2] = orc.exp_Adelta(blk, delta)
+    if n % 2:
+        Phi[-1, -1] = np.exp(A[-1, -1] * delta)
+    D = orc.discretize_zonotope(A, X0, delta, B, U, rzg=True, Phi=Phi)
+    Om = orc.reduce_order(D.Omega0, r, True)
+    R, sels = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, r, True, return_selections=True)
+    fp = _device(ctx, D, Om, N, r, True)
+    info = fp.map_info()
+    assert info["sparse_levels"] >= 1 and info["nnz_per_row"] == 2
+    _compare(fp, R, sels, N)
+    monkeypatch.setenv("REACH_GLGM06_DENSE", "1")
+    fd = _device(ctx, D, Om, N, r, True)
+    assert fd.map_info()["sparse_levels"] == 0
+    p = fp.ngens()
+    assert np.array_equal(p, fd.ngens())
+    for k in (1, 2, N // 2, N):
+        cs, Gs = fp.step(k, int(p[k - 1]))
+        cd, Gd = fd.step(k, int(p[k - 1]))
+        assert_close(cs, cd, f"step {k} centre: sparse map vs dense GEMM")
+        assert_close(Gs, Gd, f"step {k} generators: sparse map vs dense GEMM")
+    fp.close(); fd.close()
+
+
+def test_dense_phi_keeps_the_gemm(ctx):
+    A, X0, B, U, delta = _problem(3, 24, 2)
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, 6, 3, True)
+    fp = _device(ctx, D, Om, 6, 3, True)
+    assert fp.map_info() == dict(sparse_levels=0, nnz_per_row=0)
+    fp.close()

@@ -19,6 +19,7 @@ Om = orc.reduce_order(D.Omega0, w.max_order)
 print("discretize (oracle, host)", round(time.time() - t0, 2), "s; p0", Om.ngens, "pV", D.V.ngens, flush=True)
 with rb.Context(0) as ctx:
     fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, w.max_order, D.V.c, D.V.G, 0)
+    print("generator map:", fp.map_info(), "(REACH_GLGM06_DENSE=1 forces the DMMA GEMM)", flush=True)
     for it in range(reps):
         l0 = ctx.launch_count()
         fp.run()
