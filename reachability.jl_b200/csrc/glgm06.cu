@@ -1165,15 +1165,25 @@ __global__ void __launch_bounds__(1024) ell_left_kernel(int n, int ld, int64_t Q
         vi[w] = i < n ? val[i * ELL_MAX + w] : 0.0;
     }
     const int64_t g0 = (int64_t)blockIdx.x * ELL_GPB;
-#pragma unroll 4
-    for (int u = 0; u < ELL_GPB; ++u) {
-        const int64_t g = g0 + u;
-        if (g >= Q || i >= n) continue;
-        const double* x = X + g * ld;
-        double acc = 0.0;
+    constexpr int U = W <= 2 ? 8 : (W <= 4 ? 4 : 2);       // generators in flight per thread: U * W independent loads
+#pragma unroll 1
+    for (int u0 = 0; u0 < ELL_GPB; u0 += U) {
+        double xv[U][W];
 #pragma unroll
-        for (int w = 0; w < W; ++w) acc = fma(vi[w], x[ji[w]], acc);
-        Y[g * ld + i] = acc;
+        for (int u = 0; u < U; ++u) {                      // unconditional loads (clamped column) so that they all issue at once
+            const int64_t g = min(g0 + u0 + u, Q - 1);
+            const double* x = X + g * ld;
+#pragma unroll
+            for (int w = 0; w < W; ++w) xv[u][w] = x[ji[w]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) acc = fma(vi[w], xv[u][w], acc);
+            const int64_t g = g0 + u0 + u;
+            if (g < Q && i < n) Y[g * ld + i] = acc;
+        }
     }
 }
 
