@@ -1187,6 +1187,76 @@ __global__ void __launch_bounds__(1024) ell_left_kernel(int n, int ld, int64_t Q
     }
 }
 
+// The same product FUSED with the Girard scores of the mapped generators (score_stack_kernel): the CTA keeps its 16 mapped
+// columns in shared memory and its warps then run score_stack_kernel's column loop on them -- same lane striding, same
+// warp tree, hence the same bits -- so the scores (and, in strip mode, the row-support masks of the input segment) never
+// re-read the slots from HBM.  Single-rank flowpipes only (all columns of a slot are local: [G0 | GV | c0 | cV]).
+template <int W>
+__global__ void __launch_bounds__(1024) ell_left_score_kernel(GP g, int cnt, const int* __restrict__ idx,
+                                                              const double* __restrict__ val, const double* __restrict__ X,
+                                                              double* __restrict__ Yout) {
+    extern __shared__ __align__(16) double ycol[];          // ELL_GPB columns of ld doubles
+    const int n = g.n, ld = g.ld;
+    const int i = threadIdx.x;
+    const int64_t Q = (int64_t)cnt * g.q;
+    int ji[W];
+    double vi[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        ji[w] = i < n ? idx[i * ELL_MAX + w] : 0;
+        vi[w] = i < n ? val[i * ELL_MAX + w] : 0.0;
+    }
+    const int64_t g0 = (int64_t)blockIdx.x * ELL_GPB;
+    constexpr int U = W <= 2 ? 8 : (W <= 4 ? 4 : 2);
+#pragma unroll 1
+    for (int u0 = 0; u0 < ELL_GPB; u0 += U) {
+        double xv[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t gq = min(g0 + u0 + u, Q - 1);
+            const double* x = X + gq * ld;
+#pragma unroll
+            for (int w = 0; w < W; ++w) xv[u][w] = x[ji[w]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) acc = fma(vi[w], xv[u][w], acc);
+            const int64_t gq = g0 + u0 + u;
+            if (gq < Q && i < n) Yout[gq * ld + i] = acc;
+            if (i < ld) ycol[(u0 + u) * ld + i] = i < n ? acc : 0.0;       // pad rows are zero, as in the archive
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n2 = ld / 2;
+    for (int u = warp; u < ELL_GPB; u += nwarps) {
+        const int64_t gq = g0 + u;
+        if (gq >= Q) break;
+        const int t = (int)(gq / g.q), c = (int)(gq - (int64_t)t * g.q);
+        if (c >= g.p0 + g.pV) continue;                     // the two centre columns of a slot carry no score
+        const double2* c2 = reinterpret_cast<const double2*>(ycol + u * ld);
+        double s = 0.0, m = 0.0;
+        uint32_t* mask = (g.strip && c >= g.p0) ? g.maskAll + ((g.col0 / g.q + t) * (int64_t)g.pV + (c - g.p0)) * g.nwords4 : nullptr;
+        for (int it = 0; it * 32 < n2; ++it) {
+            const int k = lane + 32 * it;
+            double2 v = make_double2(0.0, 0.0);
+            if (k < n2) v = c2[k];
+            const double ax = fabs(v.x), ay = fabs(v.y);
+            s += ax;
+            s += ay;
+            m = fmax(m, fmax(ax, ay));
+            if (mask) {
+                const unsigned bx = __ballot_sync(0xffffffffu, ax != 0.0), by = __ballot_sync(0xffffffffu, ay != 0.0);
+                if (lane == 0) { mask[2 * it] = bx; mask[2 * it + 1] = by; }
+            }
+        }
+        const double asum = warp_sum(s), amax = warp_max(m);
+        if (lane == 0) g.hS[t * g.q + c] = (g.strip && asum == 0.0) ? INFINITY : asum - amax;
+    }
+}
+
 // ---- projection of a zonotope flowpipe: M * R_k (project_reach.jl:18-99, linear map of every reach set) -----------
 // One warp per generator column: lanes stride the column with 16-byte loads and carry the q <= 4 dot products with the
 // rows of M (Mt: q rows of n doubles); out[((k-1)*pmax + col)*q + row].  Columns beyond the set's count are zeroed.
@@ -1617,6 +1687,32 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
     return F;
 }
 
+// ELL product of a whole batch fused with its scores (g bound to the batch's array set, g.Y / g.col0 set): true when launched
+static bool map_slots_scored(Flowpipe* F, int lvl, GP& g, int64_t slot0, int cnt, const double* Xp, double* Yp) {
+    Ctx* ctx = F->ctx;
+    const int64_t n = F->n, ld = F->ld;
+    const size_t smem = (size_t)ELL_GPB * ld * sizeof(double);
+    if (lvl >= F->ell_levels || F->nranks != 1 || smem > 96 * 1024) return false;
+    g.Y = F->Hflow + slot0 * F->qloc * ld;
+    g.col0 = slot0 * F->q;
+    static bool attr[64] = {false};
+    if (!attr[ctx->device & 63]) {
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr[ctx->device & 63] = true;
+    }
+    const int* idx = F->ell_idx + (size_t)lvl * n * ELL_MAX;
+    const double* val = F->ell_val + (size_t)lvl * n * ELL_MAX;
+    const unsigned grid = (unsigned)ceil_div((int64_t)cnt * F->q, ELL_GPB), block = (unsigned)round_up(ld, 32);
+    if (F->ell_width <= 2) ell_left_score_kernel<2><<<grid, block, smem, ctx->stream>>>(g, cnt, idx, val, Xp, Yp);
+    else if (F->ell_width <= 4) ell_left_score_kernel<4><<<grid, block, smem, ctx->stream>>>(g, cnt, idx, val, Xp, Yp);
+    else ell_left_score_kernel<8><<<grid, block, smem, ctx->stream>>>(g, cnt, idx, val, Xp, Yp);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return true;
+}
+
 // slots Y = Phi^(2^lvl) X for Q generator columns: the ELL product when Phi is structurally sparse, else the DMMA GEMM
 static bool map_slots(Flowpipe* F, int lvl, const DMat& P, int64_t Q, const double* Xp, double* Yp) {
     Ctx* ctx = F->ctx;
@@ -1874,7 +1970,21 @@ void flowpipe_run(Flowpipe* F) {
     cudaStream_t sChain = F->serial ? st : F->side, sNum = F->serial ? st : F->side2, sSort = F->serial ? st : F->side3;
     while (have < N) {
         const int64_t cnt = std::min(w, N - have);
-        timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
+        bool scored = false;
+        if (!F->homog && lvl < F->ell_levels && !F->serial) {
+            // sparse Phi: the map also produces the scores, so it writes into this batch's array set and has to wait for the
+            // numerics that last used it (two batches back)
+            bind_set(g, F->gset[bi & 1]);
+            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(st, ev_num[bi - 2], 0));
+            cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
+            gemm_ev.push_back({ev_used - 2, ev_used - 1});
+            REACH_CUDA(cudaEventRecord(e0, st));
+            scored = map_slots_scored(F, lvl, g, have, (int)cnt, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
+            REACH_CUDA(cudaEventRecord(e1, st));
+            if (scored) F->gemm_launches++;
+            else { gemm_ev.pop_back(); }
+        }
+        if (!scored) timed_gemm(cnt * q, *pw, F->Hflow + (have - w) * q * ld, F->Hflow + have * q * ld);
         if (!F->homog) {
             cudaEvent_t ev_gemm = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
@@ -1882,7 +1992,13 @@ void flowpipe_run(Flowpipe* F) {
             REACH_CUDA(cudaStreamWaitEvent(sSort, ev_gemm, 0));
             if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - 2], 0));
             bind_set(g, F->gset[bi & 1]);
-            score_and_sort(F, g, have, (int)cnt, sSort);
+            if (scored) {
+                g.Y = F->Hflow + have * F->qloc * ld;
+                g.col0 = have * F->q;
+                sort_only(F, g, (int)cnt, sSort);
+            } else {
+                score_and_sort(F, g, have, (int)cnt, sSort);
+            }
             cudaEvent_t ev_sort = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_sort, sSort));
             REACH_CUDA(cudaStreamWaitEvent(sChain, ev_sort, 0));

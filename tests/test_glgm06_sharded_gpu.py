@@ -93,3 +93,34 @@ def test_sharded_engine_refuses_plain_run(ctx):
     with pytest.raises(rb.ReachError):
         e.phase(2, 0)                        # batches must be processed in order
     e.close()
+
+
+def test_column_sharded_flowpipe_with_structurally_sparse_phi(ctx):
+    """Decoupled 2 x 2 modes: every rank maps its generators with the ELL sparse product instead of the GEMM."""
+    g = np.random.default_rng(21)
+    n, m, N, r, nranks = 36, 2, 50, 3, 2
+    A = np.zeros((n, n))
+    Phi = np.zeros((n, n))
+    for i in range(n // 2):
+        w = g.uniform(1.0, 30.0)
+        blk = np.array([[-0.1, w], [-w, -0.1]])
+        A[2 * i:2 * i + 2, 2 * i:2 * i + 2] = blk
+        Phi[2 * i:2 * i + 2, 2 * i:2 * i + 2] = orc.exp_Adelta(blk, 0.01)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m))
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.3)
+    D = orc.discretize_zonotope(A, X0, 0.01, B, U, Phi=Phi)
+    Om = orc.reduce_order(D.Omega0, r)
+    R = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, r)
+    engines = [ctx.glgm06_sharded(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, rk, nranks) for rk in range(nranks)]
+    assert all(e.map_info()["nnz_per_row"] == 2 for e in engines)
+    emu = _EmulatedRanks(engines)
+    emu.run()
+    p = engines[0].ngens()
+    for k in range(1, N + 1):
+        assert p[k - 1] == R[k - 1].ngens
+        c, G = emu.step(k)
+        assert_close(c, R[k - 1].c, f"centre {k}")
+        assert_close(G, R[k - 1].G, f"generators {k}")
+    for e in engines:
+        e.close()
