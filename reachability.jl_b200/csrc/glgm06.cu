@@ -413,8 +413,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
         if (tid == 0) {             // sentinels for the merge of this step
             const_cast<WEnt*>(ec)[pW] = WEnt{INFINITY, 0, 0};
             const_cast<double*>(skC)[pC] = INFINITY;
+            if (SMEM) bulk_wait_read0();    // the previous step's snapshot has left the buffer this step's merge overwrites
         }
         __syncthreads();
+        if (SMEM && tid == 0 && pW > 0) {
+            // snapshot of W for the batched numerics: ONE bulk copy shared -> global (TMA engine) instead of 43 KB of store
+            // instructions on the critical path; the list is read-only for the rest of the step
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_s2g(g.snEnt + (int64_t)t * cap, ec, (uint32_t)pW * (uint32_t)sizeof(WEnt));
+            bulk_commit();
+        }
         for (int r = tid; r < min(czw, m); r += CHAIN_THREADS) {
             const int ref = ec[r].ref;
             if (ref < 0) {          // its value is an earlier W box vector entry: remember the creation step (wseq_kernel)
@@ -530,8 +538,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
         WEnt* sn = g.snEnt + (int64_t)t * cap;
         int* recO = RECORD ? g.recOrdW + (int64_t)k * g.capListW : nullptr;
         double* recH = RECORD ? g.recHW + (int64_t)k * g.capListW : nullptr;
+        if (!SMEM) {
 #pragma unroll 4
-        for (int r = tid; r < pW; r += CHAIN_THREADS) sn[r] = ec[r];       // coalesced; the merge below touches only smem
+            for (int r = tid; r < pW; r += CHAIN_THREADS) sn[r] = ec[r];   // coalesced; the merge below touches only the list
+        }
         {
             const int L = ((pin + CHAIN_THREADS - 1) / CHAIN_THREADS) | 1;     // odd: the 16-byte stores of a quarter-warp hit distinct banks
             const int d0 = min(pin, tid * L), d1 = min(pin, d0 + L);
@@ -611,6 +621,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
     }
     const WEnt* ef = cur ? ebuf1 : ebuf0;
     for (int r = tid; r < pW; r += CHAIN_THREADS) g.wEnt[r] = ef[r];
+    if (SMEM && tid == 0) bulk_wait0();       // the snapshots are in global memory before the kernel ends
     if (tid == 0) *g.wCount = pW;
 }
 
