@@ -23,6 +23,14 @@ import threading
 import time
 from pathlib import Path
 
+if "reference" in sys.argv or os.environ.get("WORLD_SIZE", "1") == "1":
+    # The CPU legs use every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the
+    # reference arm into a single-thread baseline.  Must happen before numpy / BLAS load.  (The GPU arm under torchrun keeps
+    # torchrun's setting: its host side does no BLAS work inside any timed region.)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        if "reference" in sys.argv or _v not in os.environ:
+            os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
