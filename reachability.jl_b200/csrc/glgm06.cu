@@ -415,11 +415,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
             const_cast<double*>(skC)[pC] = INFINITY;
             if (SMEM) bulk_wait_read0();    // the previous step's snapshot has left the buffer this step's merge overwrites
         }
+        // every thread orders its generic-proxy writes of the list (previous step's merge) before the async-proxy read below
+        if (SMEM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (SMEM && tid == 0 && pW > 0) {
             // snapshot of W for the batched numerics: ONE bulk copy shared -> global (TMA engine) instead of 43 KB of store
             // instructions on the critical path; the list is read-only for the rest of the step
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bulk_s2g(g.snEnt + (int64_t)t * cap, ec, (uint32_t)pW * (uint32_t)sizeof(WEnt));
             bulk_commit();
         }
