@@ -263,6 +263,15 @@ class BFFPSV18(_Post):
         p = self["partition"]
         if p is not None and not ispartition(p):
             raise ValueError("option partition is not a partition")
+        if self["sih_method"] not in ("concrete", "lazy"):
+            # symmetric_interval_hull vs the lazy SymmetricIntervalHull (discretize.jl:636-643): the same box either way
+            raise ValueError(f"the method {self['sih_method']} is unknown")
+        v = self["lazy_inputs_interval"]
+        if not (v is None or callable(v) or (isinstance(v, int) and not isinstance(v, bool) and v >= -1)):
+            # BFFPSV18.jl:51-56.  Any admissible value yields the same sets on this path: for Interval / Hyperrectangle blocks
+            # the box of a lazily accumulated Minkowski sum is the sum of the boxes (axis-direction support functions add up),
+            # so keeping the inputs lazy for k steps (reach.jl:114-147) cannot change the result.
+            raise ValueError("option lazy_inputs_interval must be an integer >= -1 or a predicate over indices")
 
 
 class GLGM06(_Post):

@@ -113,3 +113,12 @@ def test_csc_fields_follow_julia_sparse_matrix_csc():
         assert colptr.tolist() == [1, 3, 4, 6] and rowval.tolist() == [1, 3, 3, 1, 2] and nzval.tolist() == [1.0, 4.0, 5.0, 2.0, 3.0]
     n, colptr, rowval, nzval = _csc_fields(np.zeros((2, 2)))
     assert colptr.tolist() == [1, 1, 1] and len(rowval) == 0 and len(nzval) == 0
+
+
+def test_discretization_and_input_options_are_validated():      # BFFPSV18.jl:43-56, discretize.jl:636-643
+    for ok in (dict(sih_method="lazy"), dict(sih_method="concrete"), dict(lazy_inputs_interval=-1), dict(lazy_inputs_interval=0),
+               dict(lazy_inputs_interval=5), dict(lazy_inputs_interval=lambda k: False), dict(exp_method="lazy", assume_sparse=True)):
+        BFFPSV18(**ok)
+    for bad in (dict(sih_method="eager"), dict(lazy_inputs_interval=-2), dict(lazy_inputs_interval="never")):
+        with pytest.raises(ValueError):
+            BFFPSV18(**bad)

@@ -168,3 +168,30 @@ def test_lazy_exp_method_runs_the_sparse_path():                            # BF
     assert len(lazy.flowpipes[0].reachsets) == 20 and dim(set_of(lazy.flowpipes[0].reachsets[3])) == 3
     with pytest.raises(ValueError):
         solve(prob(Ad), Options(T=0.4), op=op("krylov"))                  # ArgumentError: unknown method (discretize.jl:158)
+
+
+def test_reference_option_variants_of_solve_continuous():                   # solve_continuous.jl:90-121
+    """The option variants the reference's own test file runs through `solve`: lazy / concrete sih, a lazy matrix exponential
+    on a sparse A with and without :assume_sparse, lazy input handling, Interval blocks with a lazy exponential.  For box
+    blocks they all describe the same flowpipe; every variant must run and agree with the default one."""
+    import scipy.sparse as sp
+    base = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[1, 2], [3, 4]]))
+    variants = [
+        (A, dict(sih_method="lazy")),                                         # :91-93
+        (A, dict(sih_method="concrete")),                                     # :95-97
+        (sp.csc_matrix(A), dict(exp_method="lazy", assume_sparse=False)),      # :99-102
+        (sp.csc_matrix(A), dict(exp_method="lazy", assume_sparse=True)),       # :104-107
+        (A, dict(lazy_inputs_interval=lambda k: False)),                      # :109-112
+    ]
+    for Amat, kw in variants:
+        s = solve(IVP(LCS(Amat), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[1, 2], [3, 4]], **kw))
+        assert len(s.flowpipes[0].reachsets) == 10 and dim(set_of(s.flowpipes[0].reachsets[0])) == 4
+        assert_close(s.arrays["centers"], base.arrays["centers"], f"centres {kw}")
+        assert_close(s.arrays["radii"], base.arrays["radii"], f"radii {kw}")
+    s = solve(IVP(LCS(sp.csc_matrix(A)), X0), Options(T=0.1),
+              op=BFFPSV18(vars=[1, 3], partition=[[i] for i in range(1, 5)], exp_method="lazy", block_options=Interval))   # :116-121
+    rs = s.flowpipes[0].reachsets
+    assert len(rs) == 10 and dim(set_of(rs[0])) == 2
+    dense = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[i] for i in range(1, 5)], block_options=Interval))
+    assert_close(s.arrays["centers"], dense.arrays["centers"], "Interval blocks, lazy exponential: centres")
+    assert_close(s.arrays["radii"], dense.arrays["radii"], "Interval blocks, lazy exponential: radii")
