@@ -274,7 +274,7 @@ def run_bffpsv18(args, rank, world, dist):
     out = {
         "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w.name}: n={n}, m={m}, BFFPSV18 {len(w.partition)} blocks of dim "
                                f"{len(w.partition[0])}, delta={w.delta}, T={w.T}, N={N} reach sets per bench step",
                    "rows_per_gpu": R, "parallelism": f"row-block sharding x{world}, Phi replicated" if world > 1 else "single GPU",
@@ -797,7 +797,7 @@ def run_reference(args, rank, world):
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w.name}: n={w.n}, m={w.m}, BFFPSV18, delta={w.delta}, T={w.T}, N={N}", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "flowpipe steps/s", "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
