@@ -158,6 +158,18 @@ REACH_API int32_t reach_bffpsv18_boxes_lazy(reach_sparse* sp, double delta, cons
                                     const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
                                     int64_t nrows, const int32_t* rows, int64_t N, double* centers, double* radii,
                                     int64_t* steps_done);
+/* The output_function branch and check mode with a lazy exponential (reach_blocks.jl:227-397 with output_function;
+ * check_blocks.jl for a SparseMatrixExp): arguments as reach_bffpsv18_output_map / reach_bffpsv18_check.  The per-block
+ * functionals Σ_{l in b_i} M[a,l] e^{kδA}[rows[l], :] are advanced as extra columns of the same recurrence. */
+REACH_API int32_t reach_bffpsv18_output_map_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m,
+                                         const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                                         int64_t nrows, const int32_t* rows, int64_t N, int64_t nblocks,
+                                         const int32_t* block_sizes, int64_t q, const double* Mout, int64_t ldm, double* centers,
+                                         double* radii);
+REACH_API int32_t reach_bffpsv18_check_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m,
+                                    const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                                    int64_t nrows, const int32_t* rows, int64_t N, int64_t nblocks, const int32_t* block_sizes,
+                                    const double* ell, double bound, int32_t eager, int64_t* violation);
 /* CUDA-event time of the last call on `sp`, its sparse x block products and their algorithmic HBM/L2 bytes. */
 REACH_API int32_t reach_sparse_timing(reach_sparse* sp, double* run_ms, int64_t* products, double* bytes);
 

@@ -58,6 +58,10 @@ _SIGNATURES = {
                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p],
     "reach_bffpsv18_boxes_lazy": [vp, f64, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p, c_double_p,
                                   i64, c_int32_p, i64, c_double_p, c_double_p, c_int64_p],
+    "reach_bffpsv18_output_map_lazy": [vp, f64, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p, c_double_p,
+                                       i64, c_int32_p, i64, i64, c_int32_p, i64, c_double_p, i64, c_double_p, c_double_p],
+    "reach_bffpsv18_check_lazy": [vp, f64, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p, c_double_p,
+                                  i64, c_int32_p, i64, i64, c_int32_p, c_double_p, f64, i32, c_int64_p],
     "reach_sparse_timing": [vp, c_double_p, c_int64_p, c_double_p],
     "reach_glgm06_create": [vp, i64, c_double_p, i64, i64, c_double_p, c_double_p, i64, i64, c_double_p, c_double_p,
                             i64, i64, i64, i32, C.POINTER(vp)],

@@ -441,6 +441,28 @@ def solve(problem: InitialValueProblem, options: Optional[Options] = None, op=No
     raise ReachError(3, f"post operator {type(op).__name__} is not on the sm_100a path")
 
 
+def _property_on_rows(prop, n, dims, rows):
+    """`inout_map_property` (partitions.jl:33-46) for `is_contained_in(LinearConstraint(a, b))`: the normal vector restricted
+    to the coordinates of the computed blocks."""
+    ell = np.asarray(prop.constraint.a, dtype=np.float64)
+    if len(ell) != n:
+        raise AssertionError("the property has the wrong dimension")
+    outside = np.setdiff1d(np.nonzero(ell)[0] + 1, dims)
+    if len(outside):
+        raise ValueError(f"the property involves variables {outside.tolist()} outside the computed blocks")
+    return ell[rows], float(prop.constraint.b)
+
+
+def _output_matrix_on_rows(M, n, rows):
+    """`:projection_matrix` as output function (reach.jl:73-82): its columns on the coordinates of the computed blocks."""
+    M = np.asarray(M, dtype=np.float64)
+    if M.ndim != 2 or M.shape[1] != n:
+        raise AssertionError("the projection matrix has the wrong number of columns")
+    if np.any(np.delete(M, rows, axis=1) != 0):
+        raise ValueError("the projection matrix involves variables outside the computed blocks")
+    return np.ascontiguousarray(M[:, rows])
+
+
 def _block_set_types(op, partition):
     """`:block_options_init` / `:block_options_iter` (BFFPSV18.jl:104-129, 436-443): only the two box types run on
     the device."""
@@ -492,12 +514,26 @@ def _post_bffpsv18(op, problem, opts, ctx):
     if op["exp_method"] == "lazy":
         # ϕ = SparseMatrixExp(A*δ) (discretize.jl:153-154) -> reach_blocks!(ϕ::SparseMatrixExp, ...) (reach_blocks.jl:227-397):
         # the matrix exponential is only ever applied to blocks of vectors on the device
-        if opts["mode"] == "check" or (opts["projection_matrix"] is not None and not opts["project_reachset"]):
-            raise ReachError(3, "check mode / output functions with a lazy matrix exponential are unsupported on the sm_100a path")
         Sp = ctx.sparse(A)
         try:
             D = Sp.discretize_box(delta, c, r, B if U is not None else None, None if U is None else U[0],
                                   None if U is None else U[1], algorithm=op["discretization"])
+            sizes = np.asarray([len(partition[b - 1]) for b in blocks], dtype=np.int32)
+            if opts["mode"] == "check":
+                ell, bound = _property_on_rows(opts["property"], n, dims, rows)
+                v = Sp.bffpsv18_check(delta, D["c0"], D["r0"], N, ell, bound, D["MU"], D["cU"], D["rU"], D["rpsi"], rows,
+                                      eager=op["eager_checking"], block_sizes=sizes)
+                return CheckSolution(v == 0, -1 if v == 0 else v, opts)
+            M = opts["projection_matrix"]
+            if M is not None and not opts["project_reachset"]:
+                full = _output_matrix_on_rows(M, n, rows)
+                C, R = Sp.bffpsv18_output_map(delta, D["c0"], D["r0"], N, full, D["MU"], D["cU"], D["rU"], D["rpsi"], rows,
+                                              block_sizes=sizes)
+                t0, t1 = _times(N, delta)
+
+                def make(i):
+                    return ReachSet(Hyperrectangle(C[:, i], R[:, i]), float(t0[i]), float(t1[i]))     # reach.jl:82
+                return ReachSolution([Flowpipe(_LazyReachSets(N, make))], opts, dict(centers=C, radii=R))
             C, R = Sp.bffpsv18_boxes(delta, D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
         finally:
             Sp.close()
@@ -505,28 +541,16 @@ def _post_bffpsv18(op, problem, opts, ctx):
     D = ctx.discretize_box(A, delta, c, r, B if U is not None else None, None if U is None else U[0],
                            None if U is None else U[1], algorithm=op["discretization"])
     if opts["mode"] == "check":
-        prop = opts["property"]
-        ell = np.asarray(prop.constraint.a, dtype=np.float64)
-        if len(ell) != n:
-            raise AssertionError("the property has the wrong dimension")
-        outside = np.setdiff1d(np.nonzero(ell)[0] + 1, dims)
-        if len(outside):
-            raise ValueError(f"the property involves variables {outside.tolist()} outside the computed blocks")   # partitions.jl:33-46
+        ell, bound = _property_on_rows(opts["property"], n, dims, rows)
         sizes = np.asarray([len(partition[b - 1]) for b in blocks], dtype=np.int32)
-        v = ctx.bffpsv18_check(D["Phi"], D["c0"], D["r0"], N, ell[rows], prop.constraint.b, D["MU"], D["cU"], D["rU"],
+        v = ctx.bffpsv18_check(D["Phi"], D["c0"], D["r0"], N, ell, bound, D["MU"], D["cU"], D["rU"],
                                D["rpsi"], rows, eager=op["eager_checking"], block_sizes=sizes)
         return CheckSolution(v == 0, -1 if v == 0 else v, opts)           # BFFPSV18.jl:396-403
     t0, t1 = _times(N, delta)
     M = opts["projection_matrix"]
     if M is not None and not opts["project_reachset"]:
-        M = np.asarray(M, dtype=np.float64)
         sizes = np.asarray([len(partition[b - 1]) for b in blocks], dtype=np.int32)
-        full = np.zeros((M.shape[0], len(dims)))
-        if M.shape[1] != n:
-            raise AssertionError("the projection matrix has the wrong number of columns")
-        if np.any(np.delete(M, rows, axis=1) != 0):
-            raise ValueError("the projection matrix involves variables outside the computed blocks")
-        full[:] = M[:, rows]
+        full = _output_matrix_on_rows(M, n, rows)
         C, R = ctx.bffpsv18_output_map(D["Phi"], D["c0"], D["r0"], N, full, D["MU"], D["cU"], D["rU"], D["rpsi"], rows,
                                        block_sizes=sizes)
 

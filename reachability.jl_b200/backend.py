@@ -328,6 +328,43 @@ class SparseSystem:
                                                                dptr(centers), dptr(radii), C.byref(done)))
         return centers, radii
 
+    def _lazy_args(self, c0, r0, MU, cU, rU, rpsi, rows, block_sizes):
+        n = self.n
+        c0, r0 = fvec(c0), fvec(r0)
+        m = 0
+        if MU is not None:
+            MU = fmat(MU).reshape(n, -1, order="F")
+            m = MU.shape[1]
+            cU, rU, rpsi = fvec(cU), fvec(rU), fvec(rpsi)
+        else:
+            cU = rU = rpsi = None
+        rows = np.arange(n, dtype=np.int32) if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        nb, bs = Context._blocks(block_sizes, len(rows))
+        keep = (c0, r0, MU, cU, rU, rpsi, rows, bs)
+        return keep, (dptr(c0), dptr(r0), m, dptr(MU), n, dptr(cU), dptr(rU), dptr(rpsi), len(rows), iptr(rows)), nb, bs
+
+    def bffpsv18_output_map(self, delta, c0, r0, N, Mout, MU=None, cU=None, rU=None, rpsi=None, rows=None, block_sizes=None):
+        """`output_function` branch with a lazy exponential: (centers, radii), each (q, N)."""
+        keep, args, nb, bs = self._lazy_args(c0, r0, MU, cU, rU, rpsi, rows, block_sizes)
+        Mout = fmat(np.asarray(Mout, dtype=np.float64).reshape(-1, args[8]))
+        q = Mout.shape[0]
+        centers = np.zeros((q, int(N)), order="F")
+        radii = np.zeros((q, int(N)), order="F")
+        self.ctx._check(self.ctx.lib.reach_bffpsv18_output_map_lazy(self._h, float(delta), *args, int(N), nb, iptr(bs), q, dptr(Mout), q,
+                                                                    dptr(centers), dptr(radii)))
+        return centers, radii
+
+    def bffpsv18_check(self, delta, c0, r0, N, ell, bound, MU=None, cU=None, rU=None, rpsi=None, rows=None, eager=True,
+                       block_sizes=None) -> int:
+        """Check mode with a lazy exponential: first violating step (1-based) or 0."""
+        keep, args, nb, bs = self._lazy_args(c0, r0, MU, cU, rU, rpsi, rows, block_sizes)
+        ell = fvec(ell)
+        assert len(ell) == args[8]
+        v = C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_bffpsv18_check_lazy(self._h, float(delta), *args, int(N), nb, iptr(bs), dptr(ell),
+                                                               float(bound), int(bool(eager)), C.byref(v)))
+        return int(v.value)
+
     def timing(self):
         ms, prod, b = C.c_double(), C.c_int64(), C.c_double()
         self.ctx._check(self.ctx.lib.reach_sparse_timing(self._h, C.byref(ms), C.byref(prod), C.byref(b)))

@@ -143,6 +143,8 @@ struct StepGeom {       // epilogue geometry and operands (device pointers)
     const double* c0; const double* r0; const double* rpsi;      // rpsi may be nullptr (homogeneous)
     const double* MU; const double* cU; const double* rU;        // MU: n x m, ld n
     double* cW; double* rW; double* part;
+    const double* cbase;            // start of the centres array (column offsets of cWs / rWs follow the output column)
+    double* cWs; double* rWs;       // optional (R x N): the input boxes Ŵ_k every step USES (check mode / output maps need them)
 };
 
 // virtual CTA (bx, sl, grp): 32 rows of interest x state slice sl x quantity group grp.  `red`: STEP_SUB x 32 doubles.
@@ -228,6 +230,10 @@ __device__ __forceinline__ void lazy_finish_block(const StepGeom& g, int bx, dou
         const double cw = g.m > 0 ? g.cW[l] : 0.0, rw = g.m > 0 ? g.rW[l] : 0.0;
         centers[l] = sc + cw;
         radii[l] = sr + rw;
+        if (g.cWs) {
+            g.cWs[(centers - g.cbase) + l] = cw;
+            g.rWs[(centers - g.cbase) + l] = rw;
+        }
         if (g.m > 0) {
             g.cW[l] = cw + dc;
             g.rW[l] = rw + dr + sp;
@@ -605,9 +611,13 @@ void sparse_discretize_box(SparseSys* S, double delta, int32_t algorithm, const 
 // reach_blocks! for a SparseMatrixExp (lazy rows), box blocks: see the header of this file.
 // One panel of rows of interest (hrows[0 .. R)): the whole time loop for these rows; results go to the host arrays
 // centers / radii (leading dimension ldo = all rows of the call) at row offset `row0`.
+// V0 (optional, host n x R column-major): functional mode -- the block starts from the columns of V0 instead of unit vectors
+// (homogeneous only; column 0 of the outputs is V0ᵀc0, |V0|ᵀr0).  cWs_out / rWs_out (optional): the input boxes per step.
 static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
                              int64_t ldmu, const double* cU, const double* rU, const double* rpsi, const int* hrows_ptr,
-                             int64_t R, int64_t N, double* centers, double* radii, int64_t ldo, int64_t row0) {
+                             int64_t R, int64_t N, double* centers, double* radii, int64_t ldo, int64_t row0,
+                             const double* V0 = nullptr, double* cWs_out = nullptr, double* rWs_out = nullptr) {
+    REACH_REQUIRE(!V0 || m == 0, "lazy functionals are homogeneous");
     Ctx* ctx = S->ctx;
     const int64_t n = S->n;
     const int64_t ld = block_ld(R);
@@ -624,6 +634,8 @@ static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const
         double* dMU = alloc((size_t)n * std::max<int64_t>(m, 1)); double* dcu = alloc(std::max<int64_t>(m, 1));
         double* dru = alloc(std::max<int64_t>(m, 1));
         double* cW = alloc(R); double* rW = alloc(R);
+        double* dcWs = cWs_out ? alloc((size_t)R * N) : nullptr;
+        double* drWs = cWs_out ? alloc((size_t)R * N) : nullptr;
         // epilogue geometry: ~2000 CTAs over (row chunks, state slices, quantity groups)
         const unsigned gx = (unsigned)ceil_div(R, 32);
         const int gz = 1 + (int)ceil_div(m, STEP_MCHUNK);
@@ -634,23 +646,42 @@ static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const
         int* drows = (int*)alloc((size_t)(R + 1) / 2 + 1);
         REACH_CUDA(cudaMemcpyAsync(dc0, c0, n * 8, cudaMemcpyHostToDevice, st));
         REACH_CUDA(cudaMemcpyAsync(dr0, r0, n * 8, cudaMemcpyHostToDevice, st));
-        REACH_CUDA(cudaMemcpyAsync(drows, hrows.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+        if (!V0) REACH_CUDA(cudaMemcpyAsync(drows, hrows.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
         if (m > 0) {
             REACH_CUDA(cudaMemcpyAsync(dpsi, rpsi, n * 8, cudaMemcpyHostToDevice, st));
             REACH_CUDA(cudaMemcpy2DAsync(dMU, n * 8, MU, ldmu * 8, n * 8, m, cudaMemcpyHostToDevice, st));
             REACH_CUDA(cudaMemcpyAsync(dcu, cU, m * 8, cudaMemcpyHostToDevice, st));
             REACH_CUDA(cudaMemcpyAsync(dru, rU, m * 8, cudaMemcpyHostToDevice, st));
         }
-        REACH_CUDA(cudaEventRecord(ctx->ev0, st));
-        lazy_init_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>((int)n, (int)R, drows, dc0, dr0, dpsi, (int)m, dMU, dcu, dru,
-                                                                     cW, rW, dC, dR);
-        unit_block_kernel<<<(unsigned)ceil_div(n * ld, 256), 256, 0, st>>>((int)n, (int)ld, (int)R, drows, W[0]);
-        ctx->launches += 2;
         StepGeom geom;
         geom.n = (int)n; geom.ld = (int)ld; geom.R = (int)R; geom.nsl = nsl; geom.m = (int)m; geom.ldp = (int)ldp;
         geom.gx = (int)gx; geom.gz = gz;
         geom.c0 = dc0; geom.r0 = dr0; geom.rpsi = m > 0 ? dpsi : nullptr; geom.MU = dMU; geom.cU = dcu; geom.rU = dru;
         geom.cW = cW; geom.rW = rW; geom.part = part;
+        geom.cbase = dC; geom.cWs = dcWs; geom.rWs = drWs;
+        if (dcWs) {
+            REACH_CUDA(cudaMemsetAsync(dcWs, 0, sizeof(double) * R * N, st));
+            REACH_CUDA(cudaMemsetAsync(drWs, 0, sizeof(double) * R * N, st));
+        }
+        REACH_CUDA(cudaEventRecord(ctx->ev0, st));
+        int* kzero = (int*)alloc(1);
+        REACH_CUDA(cudaMemsetAsync(kzero, 0, sizeof(int), st));
+        if (V0) {
+            std::vector<double> hb((size_t)n * ld, 0.0);
+            for (int64_t l = 0; l < R; ++l)
+                for (int64_t i = 0; i < n; ++i) hb[(size_t)i * ld + l] = V0[l * n + i];
+            REACH_CUDA(cudaMemcpyAsync(W[0], hb.data(), sizeof(double) * n * ld, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(cudaStreamSynchronize(st));
+            // column 0: the functionals of the initial block itself
+            lazy_partial_kernel<<<dim3(gx, (unsigned)nsl, (unsigned)gz), 32 * STEP_SUB, 0, st>>>(geom, W[0]);
+            lazy_finish_kernel<<<gx, 32 * STEP_SUB, 0, st>>>(geom, dC, dR, kzero, 0);
+        } else {
+            lazy_init_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>((int)n, (int)R, drows, dc0, dr0, dpsi, (int)m, dMU, dcu,
+                                                                         dru, cW, rW, dC, dR);
+            unit_block_kernel<<<(unsigned)ceil_div(n * ld, 256), 256, 0, st>>>((int)n, (int)ld, (int)R, drows, W[0]);
+        }
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches += 2;
         int64_t steps = N - 1;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t gexec = nullptr;
@@ -726,6 +757,10 @@ static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const
         REACH_CUDA(cudaEventRecord(ctx->ev1, st));
         REACH_CUDA(cudaMemcpy2DAsync(centers + row0, ldo * 8, dC, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
         REACH_CUDA(cudaMemcpy2DAsync(radii + row0, ldo * 8, dR, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
+        if (cWs_out) {
+            REACH_CUDA(cudaMemcpy2DAsync(cWs_out + row0, ldo * 8, dcWs, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaMemcpy2DAsync(rWs_out + row0, ldo * 8, drWs, R * 8, R * 8, N, cudaMemcpyDeviceToHost, st));
+        }
         REACH_CUDA(cudaStreamSynchronize(st));
         if (gexec) cudaGraphExecDestroy(gexec);
         if (graph) cudaGraphDestroy(graph);
@@ -746,7 +781,8 @@ static void lazy_boxes_panel(SparseSys* S, double delta, const double* c0, const
 // matrix rows that reference it (all 10913 rows of C4 at once: 39 steps/s, HBM-bound; in panels: see profiles/).
 void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
                            int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
-                           const int32_t* rows, int64_t N, double* centers, double* radii) {
+                           const int32_t* rows, int64_t N, double* centers, double* radii, double* cWs = nullptr,
+                           double* rWs = nullptr) {
     const int64_t n = S->n;
     REACH_REQUIRE(c0 && r0 && N >= 1 && centers && radii, "reach_bffpsv18_boxes_lazy: bad arguments");
     if (m == 0 || !MU) { m = 0; MU = nullptr; }
@@ -770,7 +806,125 @@ void sparse_bffpsv18_boxes(SparseSys* S, double delta, const double* c0, const d
     S->last_ms = 0; S->last_products = 0; S->last_bytes = 0;
     for (int64_t r0p = 0; r0p < nrows; r0p += width)
         lazy_boxes_panel(S, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, hrows.data() + r0p, std::min(width, nrows - r0p), N, centers,
-                         radii, nrows, r0p);
+                         radii, nrows, r0p, nullptr, cWs, rWs);
+}
+
+namespace {
+// out[a, k] for k >= 1 (0-based column): centre = Σ_i sc[(a,i), k] + Σ_l M[a,l] cW[l,k], radius = Σ_i sr[(a,i), k] + Σ_l |M[a,l]| rW[l,k];
+// column 0: M c0[rows], |M| r0[rows] (the boxed X̂0, reach_blocks.jl:152-155 / check_blocks.jl:122-129).  Thread per (a, k).
+__global__ void lazy_map_combine_kernel(int q, int nb, int R, int N, const double* __restrict__ sc, const double* __restrict__ sr,
+                                        const double* __restrict__ cWs, const double* __restrict__ rWs, const double* __restrict__ M,
+                                        const double* __restrict__ c0r, const double* __restrict__ r0r, double* __restrict__ outc,
+                                        double* __restrict__ outr) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= q * N) return;
+    const int a = t % q, k = t / q;
+    double c = 0.0, r = 0.0;
+    if (k == 0) {
+        for (int l = 0; l < R; ++l) {
+            c = fma(M[(int64_t)l * q + a], c0r[l], c);
+            r = fma(fabs(M[(int64_t)l * q + a]), r0r[l], r);
+        }
+    } else {
+        const int F = q * nb;
+        for (int i = 0; i < nb; ++i) {
+            c += sc[(int64_t)k * F + a * nb + i];
+            r += sr[(int64_t)k * F + a * nb + i];
+        }
+        if (cWs)
+            for (int l = 0; l < R; ++l) {
+                c = fma(M[(int64_t)l * q + a], cWs[(int64_t)k * R + l], c);
+                r = fma(fabs(M[(int64_t)l * q + a]), rWs[(int64_t)k * R + l], r);
+            }
+    }
+    outc[(int64_t)k * q + a] = c;
+    outr[(int64_t)k * q + a] = r;
+}
+}  // namespace
+
+// output_function / check-mode states with a lazy exponential: the blocks stay lazy (reach_blocks.jl:266-283 with
+// output_function, check_blocks.jl), so per block i and output row a the functional v = Σ_{l in b_i} M[a,l] e^{kδA}[rows[l], :]
+// enters as v c0 + |v| r0.  The functionals are just more columns for the same linear recurrence (block of q x nb
+// combinations of unit vectors instead of unit vectors); the input boxes Ŵ_k come out of the ordinary row run.
+void sparse_output_map(SparseSys* S, double delta, const double* c0, const double* r0, int64_t m, const double* MU, int64_t ldmu,
+                       const double* cU, const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,
+                       int64_t nblocks, const int32_t* block_sizes, int64_t q, const double* Mout, int64_t ldm, double* centers,
+                       double* radii) {
+    Ctx* ctx = S->ctx;
+    const int64_t n = S->n, R = nrows;
+    REACH_REQUIRE(rows && R >= 1 && q >= 1 && Mout && ldm >= q && centers && radii && N >= 1, "lazy output map: bad arguments");
+    if (m == 0 || !MU) { m = 0; MU = nullptr; }
+    std::vector<int64_t> boff(1, 0);
+    if (block_sizes) {
+        for (int64_t b = 0; b < nblocks; ++b) { REACH_REQUIRE(block_sizes[b] >= 1, "lazy output map: empty block"); boff.push_back(boff.back() + block_sizes[b]); }
+        REACH_REQUIRE(boff.back() == R, "lazy output map: block sizes must add up to nrows");
+    } else {
+        for (int64_t l = 1; l <= R; ++l) boff.push_back(l);      // every row is its own block
+    }
+    const int64_t nb = (int64_t)boff.size() - 1, F = q * nb;
+    for (int64_t l = 0; l < R; ++l) REACH_REQUIRE(rows[l] >= 0 && rows[l] < n, "lazy output map: row index out of range");
+    double total_ms = 0;
+    int64_t total_products = 0;
+    double total_bytes = 0;
+    // (1) input boxes Ŵ_k per row (only with inputs)
+    std::vector<double> tc, tr, cWs, rWs;
+    if (m > 0) {
+        tc.resize((size_t)R * N); tr.resize((size_t)R * N); cWs.resize((size_t)R * N); rWs.resize((size_t)R * N);
+        sparse_bffpsv18_boxes(S, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, R, rows, N, tc.data(), tr.data(), cWs.data(), rWs.data());
+        total_ms += S->last_ms; total_products += S->last_products; total_bytes += S->last_bytes;
+    }
+    // (2) the functionals: column (a, i) starts as Σ_{l in b_i} M[a,l] e_{rows[l]}
+    std::vector<double> sc((size_t)F * N), sr((size_t)F * N);
+    {
+        int64_t panel = std::max<int64_t>(32, (((int64_t)64 << 20) / (3 * 8 * n)) / 32 * 32);
+        const int64_t npan = ceil_div(F, panel), width = round_up(ceil_div(F, npan), 4);
+        for (int64_t f0 = 0; f0 < F; f0 += width) {
+            const int64_t fc = std::min(width, F - f0);
+            std::vector<double> V0((size_t)n * fc, 0.0);
+            for (int64_t f = 0; f < fc; ++f) {
+                const int64_t a = (f0 + f) / nb, i = (f0 + f) % nb;
+                for (int64_t l = boff[i]; l < boff[i + 1]; ++l) V0[(size_t)f * n + rows[l]] += Mout[l * ldm + a];
+            }
+            S->last_ms = 0; S->last_products = 0; S->last_bytes = 0;
+            lazy_boxes_panel(S, delta, c0, r0, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, fc, N, sc.data(), sr.data(), F, f0,
+                             V0.data());
+            total_ms += S->last_ms; total_products += S->last_products; total_bytes += S->last_bytes;
+        }
+    }
+    // (3) combine on the device
+    cudaStream_t st = ctx->stream;
+    std::vector<void*> tmp;
+    auto up = [&](const double* h, size_t count) {
+        double* d = dnew<double>(ctx, count);
+        tmp.push_back(d);
+        REACH_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+        return d;
+    };
+    try {
+        std::vector<double> hM((size_t)q * R), c0r(R), r0r(R);
+        for (int64_t l = 0; l < R; ++l) {
+            c0r[l] = c0[rows[l]]; r0r[l] = r0[rows[l]];
+            for (int64_t a = 0; a < q; ++a) hM[(size_t)l * q + a] = Mout[l * ldm + a];
+        }
+        double* dsc = up(sc.data(), sc.size()); double* dsr = up(sr.data(), sr.size());
+        double* dcw = m > 0 ? up(cWs.data(), cWs.size()) : nullptr; double* drw = m > 0 ? up(rWs.data(), rWs.size()) : nullptr;
+        double* dM = up(hM.data(), hM.size()); double* dc0r = up(c0r.data(), R); double* dr0r = up(r0r.data(), R);
+        double* dout = dnew<double>(ctx, (size_t)2 * q * N);
+        tmp.push_back(dout);
+        lazy_map_combine_kernel<<<(unsigned)ceil_div(q * N, 128), 128, 0, st>>>((int)q, (int)nb, (int)R, (int)N, dsc, dsr, dcw, drw, dM,
+                                                                               dc0r, dr0r, dout, dout + q * N);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        REACH_CUDA(cudaMemcpyAsync(centers, dout, sizeof(double) * q * N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaMemcpyAsync(radii, dout + q * N, sizeof(double) * q * N, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        for (void* p : tmp) ctx_free(ctx, p);
+        throw;
+    }
+    for (void* p : tmp) ctx_free(ctx, p);
+    S->last_ms = total_ms; S->last_products = total_products; S->last_bytes = total_bytes;
 }
 
 }  // namespace reach
@@ -844,6 +998,36 @@ int32_t reach_bffpsv18_boxes_lazy(reach_sparse* sp, double delta, const double* 
     SP_BEGIN(sp->ctx)
     sparse_bffpsv18_boxes(sp->s, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii);
     if (steps_done) *steps_done = N;
+    return REACH_OK;
+    SP_END(sp->ctx)
+}
+
+int32_t reach_bffpsv18_output_map_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m,
+                                       const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                                       int64_t nrows, const int32_t* rows, int64_t N, int64_t nblocks, const int32_t* block_sizes,
+                                       int64_t q, const double* Mout, int64_t ldm, double* centers, double* radii) {
+    if (!sp) return REACH_EINVAL;
+    SP_BEGIN(sp->ctx)
+    sparse_output_map(sp->s, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, nblocks, block_sizes, q, Mout, ldm, centers,
+                      radii);
+    return REACH_OK;
+    SP_END(sp->ctx)
+}
+
+int32_t reach_bffpsv18_check_lazy(reach_sparse* sp, double delta, const double* c0, const double* r0, int64_t m, const double* MU,
+                                  int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
+                                  const int32_t* rows, int64_t N, int64_t nblocks, const int32_t* block_sizes, const double* ell,
+                                  double bound, int32_t eager, int64_t* violation) {
+    if (!sp) return REACH_EINVAL;
+    SP_BEGIN(sp->ctx)
+    REACH_REQUIRE(ell && violation && N >= 1, "reach_bffpsv18_check_lazy: ell and violation are required");
+    std::vector<double> c(N), r(N);
+    sparse_output_map(sp->s, delta, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, nblocks, block_sizes, 1, ell, 1, c.data(),
+                      r.data());
+    *violation = 0;
+    for (int64_t k = 0; k < N; ++k)
+        if (c[k] + r[k] > bound) { *violation = k + 1; break; }     // first violating step (check_blocks.jl:116); eager or not, the same index
+    (void)eager;
     return REACH_OK;
     SP_END(sp->ctx)
 }

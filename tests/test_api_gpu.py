@@ -195,3 +195,22 @@ def test_reference_option_variants_of_solve_continuous():                   # so
     dense = solve(IVP(LCS(A), X0), Options(T=0.1), op=BFFPSV18(vars=[1, 3], partition=[[i] for i in range(1, 5)], block_options=Interval))
     assert_close(s.arrays["centers"], dense.arrays["centers"], "Interval blocks, lazy exponential: centres")
     assert_close(s.arrays["radii"], dense.arrays["radii"], "Interval blocks, lazy exponential: radii")
+
+
+def test_check_mode_and_output_function_with_a_lazy_exponential():
+    """The check-mode known answers of solve_continuous.jl:49-75 and an output function, through exp_method = "lazy"."""
+    import scipy.sparse as sp
+    As = sp.csc_matrix(A)
+    for prop_a, expect_violation in ((np.array([1.0, 1.0, 0.0, 0.0]), True), (np.array([1.0, -1.0, 0.0, 0.0]), False)):
+        prop = is_contained_in(LinearConstraint(prop_a, 2.0))
+        for method in ("base", "lazy"):
+            s = solve(IVP(LCS(As if method == "lazy" else A), X0), Options(T=0.1, mode="check", property=prop),
+                      op=BFFPSV18(vars=[1, 2, 3], partition=[[1, 2], [3, 4]], exp_method=method))
+            assert s.satisfied == (not expect_violation), (method, prop_a)
+            assert (s.violation == 1) if expect_violation else (s.violation == -1)
+    M = np.array([[1.0, 0.5, 0.0, 0.0], [0.0, 0.0, 1.0, -1.0]])
+    kw = dict(vars=[1, 2, 3, 4], partition=[[1, 2], [3, 4]])
+    sd = solve(IVP(LCS(A), X0), Options(T=0.1, projection_matrix=M), op=BFFPSV18(**kw))
+    sl = solve(IVP(LCS(As), X0), Options(T=0.1, projection_matrix=M), op=BFFPSV18(exp_method="lazy", **kw))
+    assert_close(sl.arrays["centers"], sd.arrays["centers"], "output function centres")
+    assert_close(sl.arrays["radii"], sd.arrays["radii"], "output function radii")

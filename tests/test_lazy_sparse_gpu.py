@@ -160,3 +160,32 @@ def test_graph_replay_and_eager_steps_produce_identical_bits(ctx, monkeypatch):
     assert_close(C1.T, Co, "centres")
     assert_close(R1.T, Ro, "radii")
     S.close()
+
+
+@pytest.mark.parametrize("n,m,N,q", [(30, 0, 15, 1), (42, 2, 22, 2), (25, 3, 18, 3)])
+def test_lazy_output_map_and_check_match_the_dense_oracle(ctx, n, m, N, q):
+    """output_function branch and check mode with a lazy exponential: blocks stay lazy, so the absolute value is taken per
+    block of the product M[:, b_i] P[b_i, :] (oracle `bffpsv18_output_map` / `bffpsv18_check`)."""
+    g = np.random.default_rng(31 * n + m)
+    A = _sparse_system(3 * n + 2, n)
+    X0 = orc.Box(g.standard_normal(n), np.abs(g.standard_normal(n)) * 0.1)
+    B = g.standard_normal((n, m)) if m else None
+    U = orc.Box(g.standard_normal(m), np.abs(g.standard_normal(m)) * 0.2) if m else None
+    delta = 0.02
+    D = orc.discretize_box(A, X0, delta, B, U)
+    rows = np.array([0, 1, 4, 5, 6, 11, 12, n - 1], dtype=np.int32)
+    sizes = [2, 3, 2, 1]                                  # blocks of the partition the rows belong to
+    M = g.standard_normal((q, len(rows)))
+    Co, Ro = orc.bffpsv18_output_map(D, N, M, rows, sizes)
+    S = ctx.sparse(sp.csc_matrix(A))
+    Cd, Rd = S.bffpsv18_output_map(delta, D.c0, D.r0, N, M, D.MU, D.cU, D.rU, D.rpsi, rows, block_sizes=sizes)
+    assert_close(Cd.T, Co, "output map centres")
+    assert_close(Rd.T, Ro, "output map radii")
+    # check mode on the first output row: thresholds around the largest support value
+    ell = M[0]
+    rho = Co[:, 0] + Ro[:, 0]
+    for bound in (rho.max() + 1.0, np.sort(rho)[len(rho) // 2] * (1 - 1e-6) - 1e-9, rho.min() - 1.0):
+        want = orc.bffpsv18_check(D, N, ell, bound, rows, eager=True, block_sizes=sizes)
+        got = S.bffpsv18_check(delta, D.c0, D.r0, N, ell, bound, D.MU, D.cU, D.rU, D.rpsi, rows, block_sizes=sizes)
+        assert got == want, (bound, got, want)
+    S.close()
