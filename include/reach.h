@@ -126,7 +126,8 @@ REACH_API int32_t reach_bffpsv18_check(reach_ctx* ctx, int64_t n, const double* 
                              int64_t nblocks, const int32_t* block_sizes, const double* ell, double bound, int32_t eager,
                              int64_t* violation);
 /* output_function branch (reach_blocks.jl:152-155,197-199; reach.jl:73-82): stored set is
- * box_approximation(Mout * CPA(Xhat_k)); Mout is q x nrows (q <= 8), block_sizes as above. centers/radii: q x N. */
+ * box_approximation(Mout * CPA(Xhat_k)); Mout is q x nrows (any q; the kernels carry 8 output rows at a time), block_sizes as
+ * above. centers/radii: q x N. */
 REACH_API int32_t reach_bffpsv18_output_map(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
                                   const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,
                                   const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows, int64_t N,

@@ -1,5 +1,6 @@
 // C ABI: BFFPSV18 entry points (include/reach.h).
 #include "common.cuh"
+#include <algorithm>
 #include "../../include/reach.h"
 
 namespace reach {
@@ -162,17 +163,41 @@ int32_t reach_bffpsv18_output_map(reach_ctx* h, int64_t n, const double* Phi, in
     if (!h) return REACH_EINVAL;
     Ctx* ctx = ctx_of(h);
     GUARD_BEGIN(ctx)
-    REACH_REQUIRE(centers && radii, "reach_bffpsv18_output_map: output buffers required");
-    BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
-    try {
-        boxplan_attach_map(p, q, Mout, ldm, nblocks, block_sizes, false, 0.0, false);
-        boxplan_run(p);
-        boxplan_fetch_map(p, centers, radii, nullptr);
-    } catch (...) {
+    REACH_REQUIRE(centers && radii && q >= 1 && Mout && ldm >= q, "reach_bffpsv18_output_map: bad output map / buffers");
+    // the map kernels carry up to 8 output rows; wider maps run in groups of 8 rows (the recurrence is repeated per group)
+    constexpr int64_t QMAX = 8;
+    std::vector<double> Mg, cg, rg;
+    for (int64_t q0 = 0; q0 < q; q0 += QMAX) {
+        const int64_t qc = std::min(QMAX, q - q0);
+        const bool whole = (q <= QMAX);
+        const double* Mp = Mout;
+        int64_t ldp = ldm;
+        if (!whole) {
+            Mg.assign((size_t)qc * nrows, 0.0);
+            for (int64_t l = 0; l < nrows; ++l)
+                for (int64_t a = 0; a < qc; ++a) Mg[(size_t)l * qc + a] = Mout[l * ldm + q0 + a];
+            cg.assign((size_t)qc * N, 0.0);
+            rg.assign((size_t)qc * N, 0.0);
+            Mp = Mg.data();
+            ldp = qc;
+        }
+        BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
+        try {
+            boxplan_attach_map(p, qc, Mp, ldp, nblocks, block_sizes, false, 0.0, false);
+            boxplan_run(p);
+            boxplan_fetch_map(p, whole ? centers : cg.data(), whole ? radii : rg.data(), nullptr);
+        } catch (...) {
+            boxplan_destroy(p);
+            throw;
+        }
         boxplan_destroy(p);
-        throw;
+        if (!whole)
+            for (int64_t k = 0; k < N; ++k)
+                for (int64_t a = 0; a < qc; ++a) {
+                    centers[k * q + q0 + a] = cg[(size_t)k * qc + a];
+                    radii[k * q + q0 + a] = rg[(size_t)k * qc + a];
+                }
     }
-    boxplan_destroy(p);
     return REACH_OK;
     GUARD_END(ctx)
 }

@@ -59,7 +59,8 @@ def test_check_first_violation_matches_oracle(ctx, n, m, N, sizes):
 
 @pytest.mark.parametrize("n,m,N,q,sizes,rows", [(4, 0, 10, 2, [2, 2], None), (6, 2, 40, 1, [1] * 6, None), (9, 1, 70, 3, [2, 3, 4], None),
                                                 (20, 3, 130, 8, [20], None), (33, 2, 90, 2, [2] * 16 + [1], None),
-                                                (40, 3, 50, 2, [2, 2, 2], [4, 5, 10, 11, 38, 39]), (130, 1, 200, 2, None, None)])
+                                                (40, 3, 50, 2, [2, 2, 2], [4, 5, 10, 11, 38, 39]), (130, 1, 200, 2, None, None),
+                                                (14, 2, 25, 11, [2] * 7, None), (10, 0, 12, 17, [5, 5], None)])    # q > 8: groups of 8 rows
 def test_output_map_matches_oracle(ctx, n, m, N, q, sizes, rows):
     D = _problem(600 + n, n, m)
     g = np.random.default_rng(n + q)
