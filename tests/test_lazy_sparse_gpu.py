@@ -189,3 +189,28 @@ def test_lazy_output_map_and_check_match_the_dense_oracle(ctx, n, m, N, q):
         got = S.bffpsv18_check(delta, D.c0, D.r0, N, ell, bound, D.MU, D.cU, D.rU, D.rpsi, rows, block_sizes=sizes)
         assert got == want, (bound, got, want)
     S.close()
+
+
+@pytest.mark.parametrize("name", ["lcs4", "clccs4", "doc5"])
+def test_lazy_path_reproduces_the_golden_fixtures(ctx, name):
+    """The committed golden vectors (tests/golden/*.npz: the reference's own test systems, frozen oracle outputs) through the
+    sparse discretisation and the lazy recurrence -- no oracle call at run time."""
+    from pathlib import Path
+    Gd = np.load(Path(__file__).resolve().parent / "golden" / f"{name}.npz")
+    A, c, r, delta, T = Gd["A"], Gd["c"], Gd["r"], float(Gd["delta"]), float(Gd["T"])
+    B = Gd["B"] if "B" in Gd else None
+    cU = Gd["cU"] if "cU" in Gd else None
+    rU = Gd["rU"] if "rU" in Gd else None
+    S = ctx.sparse(sp.csc_matrix(A))
+    for alg in ("forward", "backward"):
+        D = S.discretize_box(delta, c, r, B, cU, rU, algorithm=alg)
+        assert_close(D["c0"], Gd[f"{alg}_c0"], f"{alg} c0")
+        assert_close(D["r0"], Gd[f"{alg}_r0"], f"{alg} r0")
+        assert_close(D["rE"], Gd[f"{alg}_rE"], f"{alg} rE")
+        if B is not None:
+            assert_close(D["rpsi"], Gd[f"{alg}_rpsi"], f"{alg} rpsi")
+        N = Gd[f"{alg}_centers"].shape[0]
+        C, R = S.bffpsv18_boxes(delta, D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"])
+        assert_close(C.T, Gd[f"{alg}_centers"], f"{alg} centres")
+        assert_close(R.T, Gd[f"{alg}_radii"], f"{alg} radii")
+    S.close()
