@@ -1659,7 +1659,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         }
         // structurally sparse Phi?  ELL forms of Phi^(2^l) for the doubling levels the run uses (see ell_left_kernel)
         F->force_dense = getenv("REACH_GLGM06_DENSE") != nullptr;
-        if (F->phi_host.empty() && n >= 16 && !F->force_dense) {
+        if (F->phi_host.empty() && n >= 16 && n <= 1024 && !F->force_dense) {      // one thread per state row in the ELL kernels
             int nlev = 1;
             for (int64_t w = 1; w < s; w *= 2) ++nlev;
             int* idx = (int*)own(dalloc<int>(ctx, (size_t)nlev * n * ELL_MAX));
