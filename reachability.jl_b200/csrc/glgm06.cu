@@ -20,8 +20,12 @@
 //    grid-wide synchronisation; zero-generator removal needs only row-support bit masks, never the values.
 //  * BATCHED NUMERICS.  Everything numerical is then embarrassingly parallel over the steps of the block: box vectors of
 //    the discarded generators (fixed summation order, no float atomics), the R-side selection [Phi^k G0 | W_{k-1}]
-//    against the per-step snapshot of W, the gather of the kept generators into the flowpipe slots (warp per column,
-//    16-byte vectorised, coalesced), centres, and the dense box generators.
+//    against the per-step snapshot of W, the gather of the kept generators into the flowpipe slots (columns staged through
+//    shared memory with bulk copies, TMA engine), centres, and the dense box generators.
+//  * PIPELINE.  Five streams: map of batch b+1 (main) | scores + segment order | selection chain of batch b (owns one SM) |
+//    R sortperm | numerics of batch b-1; the persistent GEMM leaves K SMs to the chain and the HBM-bound numerics.
+//  * SPARSE PHI.  When Phi (and the powers the run uses) has at most 8 non-zeros per row, the map is an ELL sparse product
+//    fused with the Girard scores instead of the GEMM (decoupled modes: the ISS-shaped C2).
 //  * All counts live on the device; the host enqueues the whole flowpipe without synchronising.
 #include "common.cuh"
 #include "../../include/reach.h"
@@ -1970,9 +1974,10 @@ void flowpipe_run(Flowpipe* F) {
         }
     }
     // slot j = Phi^j X.  With Phi^w in hand, slots [have, have + w) = Phi^w * slots [have - w, have): doubling until
-    // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) form one batch.  Three streams:
-    // the GEMM of batch b+1 (main), the selection chain of batch b (side) and the numerics of batch b-1 (side2) overlap;
-    // the batch-local arrays are double-buffered, so the chain of batch b waits for the numerics of batch b-2.
+    // w = s, then s slots per GEMM.  The steps k = have+1 .. have+cnt (slot k-1) form one batch.  The map of batch b+1
+    // (main stream), the scores / segment order of batch b+1 (side3), the selection chain of batch b (side), its R sortperm
+    // (side4) and the numerics of batch b-1 (side2) overlap; the batch-local arrays are double-buffered, so the chain of
+    // batch b waits for the numerics of batch b-2.
     const DMat* pw = &F->Phi;
     DMat* spare[2] = {&F->PowA, &F->PowB};
     int sp = 0;
