@@ -151,3 +151,27 @@ def test_gloo_run_sharded_places_the_collectives():
         p.join(120)
         assert p.exitcode == 0
     assert q.get() is True
+
+
+class _SingleRankDist:
+    """world_size-1 stand-in for torch.distributed (no process group needed): the all-reduce is the identity."""
+
+    class ReduceOp:
+        SUM = "sum"
+
+    @staticmethod
+    def all_reduce(t, op=None):
+        return t
+
+
+def test_run_sharded_synchronises_around_collectives_unless_stream_ordered():
+    """Without a shared CUDA stream the phases are asynchronous, so the driver must synchronise before NCCL reads a buffer and
+    after it wrote it; with `stream_ordered` (library and torch on the same stream) no synchronisation is issued between the
+    phases at all."""
+    for stream_ordered, per_collective in ((False, 2), (True, 0)):
+        eng, syncs = _MockEngine(0), []
+        sharding.run_sharded(eng, _SingleRankDist, as_tensor=lambda t: t, sync=lambda: syncs.append(len(eng.log)),
+                             stream_ordered=stream_ordered)
+        ncoll = sum(1 for v in eng.bufs.values() if v is not None)
+        assert len(syncs) == per_collective * ncoll + 1            # + the final one
+        assert syncs[-1] == len(eng.log)
