@@ -1466,7 +1466,11 @@ struct Flowpipe {
     cudaStream_t side2 = nullptr;   // ... and the numerics of batch b (overlap the chain of batch b+1)
     cudaStream_t side3 = nullptr;   // scores + segment order of batch b (only need the GEMM of batch b)
     cudaStream_t side4 = nullptr;   // R sortperm of batch b (only needs the chain of batch b)
-    GP gset[2];                     // batch-local arrays, double-buffered by batch parity
+    // batch-local arrays, NSET-fold buffered: with two sets the loop numerics(b-1) -> map(b+1) -> sort -> chain(b+1) ->
+    // numerics(b+1) spans two batches and left a gap between consecutive chains (0.31 ms per batch at C2); with three sets it
+    // spans three and the chain (0.25 ms per batch) runs back to back
+    static constexpr int NSET = 3;
+    GP gset[NSET];
     std::vector<void*> owned;
     std::vector<int2> meta_host;
     bool ran = false;
@@ -1627,7 +1631,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             F->chain_smem = (size_t)g.capW * 32 + (size_t)(pV + 2) * 32 + (size_t)g.capDisc * 4 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
             if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
-            for (int b = 0; b < 2; ++b) {      // batch-local arrays, one set per batch parity
+            for (int b = 0; b < Flowpipe::NSET; ++b) {      // batch-local arrays, one set per batch in flight
                 GP& h = F->gset[b];
                 h.hS = (double*)own(dalloc<double>(ctx, sq));
                 h.skS = (double*)own(dalloc<double>(ctx, sq));
@@ -1991,8 +1995,8 @@ void flowpipe_run(Flowpipe* F) {
         if (!F->homog && lvl < F->ell_levels && !F->serial) {
             // sparse Phi: the map also produces the scores, so it writes into this batch's array set and has to wait for the
             // numerics that last used it (two batches back)
-            bind_set(g, F->gset[bi & 1]);
-            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(st, ev_num[bi - 2], 0));
+            bind_set(g, F->gset[bi % Flowpipe::NSET]);
+            if (bi >= Flowpipe::NSET) REACH_CUDA(cudaStreamWaitEvent(st, ev_num[bi - Flowpipe::NSET], 0));
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             gemm_ev.push_back({ev_used - 2, ev_used - 1});
             REACH_CUDA(cudaEventRecord(e0, st));
@@ -2007,8 +2011,8 @@ void flowpipe_run(Flowpipe* F) {
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
             // scores / segment order: after this batch's GEMM and after the numerics that last used this array set
             REACH_CUDA(cudaStreamWaitEvent(sSort, ev_gemm, 0));
-            if (bi >= 2) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - 2], 0));
-            bind_set(g, F->gset[bi & 1]);
+            if (bi >= Flowpipe::NSET) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - Flowpipe::NSET], 0));
+            bind_set(g, F->gset[bi % Flowpipe::NSET]);
             if (scored) {
                 g.Y = F->Hflow + have * F->qloc * ld;
                 g.col0 = have * F->q;
