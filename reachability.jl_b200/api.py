@@ -435,10 +435,14 @@ def solve(problem: InitialValueProblem, options: Optional[Options] = None, op=No
     assert dim(problem.x0) == n, "the system's state dimension and the initial set dimension must match"   # solve.jl:64
     opts["n"] = n
     if isinstance(op, BFFPSV18):
-        return _post_bffpsv18(op, problem, opts, _context(device))
-    if isinstance(op, GLGM06):
-        return _post_glgm06(op, problem, opts, _context(device))
-    raise ReachError(3, f"post operator {type(op).__name__} is not on the sm_100a path")
+        sol = _post_bffpsv18(op, problem, opts, _context(device))
+    elif isinstance(op, GLGM06):
+        sol = _post_glgm06(op, problem, opts, _context(device))
+    else:
+        raise ReachError(3, f"post operator {type(op).__name__} is not on the sm_100a path")
+    if opts["project_reachset"] and isinstance(sol, ReachSolution):
+        return project(sol)                     # `:project_reachset` (BFFPSV18.jl:376-381, GLGM06/post.jl:46-49): over `:plot_vars`
+    return sol
 
 
 def _property_on_rows(prop, n, dims, rows):

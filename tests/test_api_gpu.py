@@ -214,3 +214,15 @@ def test_check_mode_and_output_function_with_a_lazy_exponential():
     sl = solve(IVP(LCS(As), X0), Options(T=0.1, projection_matrix=M), op=BFFPSV18(exp_method="lazy", **kw))
     assert_close(sl.arrays["centers"], sd.arrays["centers"], "output function centres")
     assert_close(sl.arrays["radii"], sd.arrays["radii"], "output function radii")
+
+
+def test_project_reachset_option_projects_inside_solve():                   # BFFPSV18.jl:376-381, GLGM06/post.jl:46-49
+    for op in (GLGM06(), BFFPSV18(vars=[1, 3], partition=[[1, 2], [3, 4]])):
+        s = solve(IVP(LCS(A), X0), Options(T=0.1, project_reachset=True, plot_vars=[1, 3]), op=op)
+        plain = solve(IVP(LCS(A), X0), Options(T=0.1, plot_vars=[1, 3]), op=op)
+        want = project(plain).flowpipes[0].reachsets
+        got = s.flowpipes[0].reachsets
+        assert len(got) == 10 and dim(set_of(got[0])) == 2
+        for k in (0, 9):
+            assert_close(set_of(got[k]).center, set_of(want[k]).center, "centre")
+            assert_close(set_of(got[k]).radius, set_of(want[k]).radius, "radius")
