@@ -375,3 +375,46 @@ def test_dense_phi_keeps_the_gemm(ctx):
     fp = _device(ctx, D, Om, 6, 3, True)
     assert fp.map_info() == dict(sparse_levels=0, nnz_per_row=0)
     fp.close()
+
+
+def test_config_c5_ensemble_full_length_properties(ctx):
+    """BASELINE.json configs[4] at one GPU's share of the 4096 splits (256 of the 512 members here, to bound the test's 10 GB):
+    heli28-shaped n = 28, N = 2000 reach sets per member.  (a) sampled members equal their own oracle flowpipe at sampled
+    steps up to the last one; (b) closed form R_k = Phi^{k-1} (c0, G0) for every member at the last step through the box
+    hull; (c) the boxes of the sub-boxes stay inside the box of the parent set's flowpipe (monotonicity of the split)."""
+    from reachability_jl_b200 import workloads as wl
+    w = wl.heli28()
+    n, N = w.n, orc.n_steps_glgm06(w.T, w.delta)
+    assert N == 2000
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.Phi2(np.abs(w.A), w.delta)
+    cs, rs = wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])
+    assert cs.shape[1] == 4096
+    batch = 256
+    members = np.linspace(0, 4095, batch).astype(int)
+    zs = [orc.discretize_zonotope(w.A, orc.Box(cs[:, b], rs[:, b]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2).Omega0 for b in members]
+    p = zs[0].ngens
+    assert p == 85 and all(z.ngens == p for z in zs)
+    c0s = np.stack([z.c for z in zs], axis=1)
+    G0s = np.stack([z.G for z in zs], axis=2)
+    ens = ctx.ensemble(Phi, c0s, G0s, N).run()
+    for b in (0, 97, batch - 1):
+        R = orc.glgm06_reach_homog(zs[b], Phi, N, rzg=False)
+        for k in (1, 2, 500, N):
+            c, G = ens.step(b, k)
+            assert_close(c, R[k - 1].c, f"member {b} step {k} centre")
+            assert_close(G, R[k - 1].G, f"member {b} step {k} generators")
+    PN = np.linalg.matrix_power(Phi, N - 1)
+    lo, hi = ens.boxes(N)
+    cN = PN @ c0s
+    radN = np.stack([np.abs(PN @ G0s[:, :, b]).sum(axis=1) for b in range(batch)], axis=1)
+    scale = np.abs(cN) + radN
+    assert np.max(np.abs(lo - (cN - radN)) / (1e-9 * scale + 1e-12)) <= 1.0       # matrix_power takes another product order
+    assert np.max(np.abs(hi - (cN + radN)) / (1e-9 * scale + 1e-12)) <= 1.0
+    parent = orc.discretize_zonotope(w.A, orc.Box(w.c, w.r), w.delta, rzg=False, Phi=Phi, Phi2abs=P2).Omega0
+    Rp = orc.glgm06_reach_homog(parent, Phi, 40, rzg=False)
+    lo40, hi40 = ens.boxes(40)
+    rad = np.abs(Rp[39].G).sum(axis=1)
+    tol = 1e-9 * (np.abs(Rp[39].c) + rad) + 1e-12
+    assert np.all(lo40 >= (Rp[39].c - rad - tol)[:, None]) and np.all(hi40 <= (Rp[39].c + rad + tol)[:, None])
+    ens.close()
