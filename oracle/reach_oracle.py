@@ -651,21 +651,28 @@ def glgm06_reach_homog(Omega0: Zono, Phi: np.ndarray, N: int, rzg: bool = True):
     return R
 
 
+def glgm06_iter_inhomog(Omega0: Zono, V: Zono, Phi: np.ndarray, N: int, max_order: int, rzg: bool = True):
+    """``reach_inhomog!`` -- GLGM06/reach.jl:30-62, one reach set at a time: yields ``(k, R_k, (selR, selW))`` for
+    k = 1..N (selections None at k = 1), so that full-length parity tests need not hold the whole flowpipe."""
+    yield 1, Omega0, None
+    W = V                                                     # :41-42
+    Pk = Phi.copy()                                           # :43
+    for k in range(2, N + 1):
+        Rk = minkowski_sum(linear_map(Pk, Omega0, rzg), W, rzg)          # :48
+        Rk, selR = reduce_order(Rk, max_order, rzg, return_selection=True)   # :49
+        W = minkowski_sum(W, linear_map(Pk, V, rzg), rzg)               # :54
+        W, selW = reduce_order(W, max_order, rzg, return_selection=True)   # :55
+        yield k, Rk, (selR, selW)
+        Pk = Pk @ Phi                                         # :57-58
+
+
 def glgm06_reach_inhomog(Omega0: Zono, V: Zono, Phi: np.ndarray, N: int, max_order: int, rzg: bool = True,
                          return_selections: bool = False):
     """``reach_inhomog!`` -- GLGM06/reach.jl:30-62."""
-    R = [Omega0]
-    sels = [None]
-    W = V                                                     # :41-42
-    Pk = Phi.copy()                                           # :43
-    for _ in range(2, N + 1):
-        Rk = minkowski_sum(linear_map(Pk, Omega0, rzg), W, rzg)          # :48
-        Rk, selR = reduce_order(Rk, max_order, rzg, return_selection=True)   # :49
+    R, sels = [], []
+    for _, Rk, sel in glgm06_iter_inhomog(Omega0, V, Phi, N, max_order, rzg):
         R.append(Rk)
-        W = minkowski_sum(W, linear_map(Pk, V, rzg), rzg)               # :54
-        W, selW = reduce_order(W, max_order, rzg, return_selection=True)   # :55
-        sels.append((selR, selW))
-        Pk = Pk @ Phi                                         # :57-58
+        sels.append(sel)
     return (R, sels) if return_selections else R
 
 
