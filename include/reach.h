@@ -12,8 +12,9 @@
  *     dimension, valid only for the duration of the call; the library copies what it needs to the device
  *     before returning and never retains host pointers.
  *   - indices crossing the ABI are 0-based int32; sizes are int64 (Julia Int).
- *   - one reach_ctx is bound to one CUDA device and one stream; multi-GPU runs use one process (rank) and
- *     one context per GPU and shard rows / steps / problems across ranks (DESIGN.md "Multi-GPU").
+ *   - reach_ctx_create binds a context to one CUDA device and one stream; multi-GPU runs either use one process (rank)
+ *     and one context per GPU and shard rows / steps / problems across ranks, or ONE process with a multi-device
+ *     context (reach_ctx_create_multi) whose BFFPSV18 calls shard the rows inside the library (DESIGN.md "Multi-GPU").
  */
 #ifndef REACH_SM100A_H
 #define REACH_SM100A_H
@@ -40,6 +41,10 @@ extern "C" {
 #define REACH_FIRSTORDER 2 /* discretize_firstorder, p = Inf      discretize.jl:403-473 */
 #define REACH_NOBLOATING 3 /* discretize_nobloating               discretize.jl:527-552 */
 
+/* zonotope flags (discretisation and GLGM06) */
+#define REACH_GLGM06_KEEP_ZERO_GENERATORS 1 /* Zonotope(c, G; remove_zero_generators=false) semantics */
+#define REACH_GLGM06_RECORD_SELECTIONS 2    /* keep sortperm + scores of every reduce_order call (reach_flowpipe_selection) */
+
 typedef struct reach_ctx reach_ctx;
 typedef struct reach_boxplan reach_boxplan;   /* BFFPSV18 problem resident on the device */
 typedef struct reach_flowpipe reach_flowpipe; /* GLGM06 problem + zonotope flowpipe resident on the device */
@@ -52,6 +57,14 @@ REACH_API int32_t reach_ctx_create(int32_t device, reach_ctx** out);
 /* Same, but all work is issued on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream
  * or CUDA.jl's task stream); the stream is borrowed, not owned.  stream == NULL behaves like reach_ctx_create. */
 REACH_API int32_t reach_ctx_create_on_stream(int32_t device, void* stream, reach_ctx** out);
+/* One handle over SEVERAL devices of one process: devices[0] is the primary device -- every entry point
+ * works on it exactly as with reach_ctx_create -- and reach_bffpsv18_boxes / reach_bffpsv18_boxes_csc additionally shard
+ * their rows of interest in contiguous ranges over all ndev devices (Phi and the sets replicated, one host thread per
+ * device, no collective: P_k[R_g, :] = P_{k-1}[R_g, :] Phi needs only the shard's own rows; the results are gathered by the
+ * strided download into the caller's arrays).  This is how a single Julia task (`solve`, src/solve.jl:59-81) gets all GPUs of
+ * a box through one `ccall`.  A device may be listed more than once (the shards then share it). */
+REACH_API int32_t reach_ctx_create_multi(const int32_t* devices, int32_t ndev, reach_ctx** out);
+REACH_API int32_t reach_ctx_device_count(reach_ctx* ctx, int32_t* ndev);
 REACH_API void reach_ctx_destroy(reach_ctx* ctx);
 /* Message of the last failure on this context (ctx == NULL: last failure of reach_ctx_create). */
 REACH_API const char* reach_last_error(const reach_ctx* ctx);
@@ -77,6 +90,21 @@ REACH_API int32_t reach_discretize_box(reach_ctx* ctx, int64_t n, const double* 
                              const double* c, const double* r, int64_t m, const double* B, int64_t ldb,
                              const double* cU, const double* rU, double* Phi, int64_t ldphi, double* Phi2abs,
                              int64_t ldphi2, double* c0, double* r0, double* rE, double* rpsi, double* MU);
+
+/* discretize(...; set_operations = "zonotope") for a box X0 = (c, r) and a constant box input U = (cU, rU) through B
+ * (discretize.jl:705-743 with `_convert_or_overapproximate`, :882-890) -- what GLGM06 calls (GLGM06/post.jl:15-18):
+ *   homogeneous (m == 0):  Z2 = linear_map(Φ, Z1 ⊕ Einit),  Ω0 = overapproximate(ConvexHull(Z1, Z2), Zonotope)      :706-709
+ *   inhomogeneous:         Z2 = ΦZ1 ⊕ δU0 ⊕ Eψ0 ⊕ Einit,  Ω0 as above,  V = δU0 ⊕ Eψ0                               :715-727
+ * computed on the device, zero-generator removal of the `Zonotope` constructor included (flags:
+ * REACH_GLGM06_KEEP_ZERO_GENERATORS keeps them).  algorithm: REACH_FORWARD / REACH_BACKWARD; REACH_FIRSTORDER and
+ * REACH_NOBLOATING return REACH_EINVAL like the reference's ArgumentError (discretize.jl:105-115).
+ * Outputs: Phi n x n (may be NULL); Ω0 = (c0, G0) with G0 n x p0, the caller provides room for 4n + m + 1 columns;
+ * V = (cV, GV) with GV n x pV, room for n + m columns (ignored when m == 0; *pV = 0). */
+REACH_API int32_t reach_discretize_zonotope(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta,
+                                    int32_t algorithm, const double* c, const double* r, int64_t m, const double* B,
+                                    int64_t ldb, const double* cU, const double* rU, int32_t flags, double* Phi, int64_t ldphi,
+                                    double* c0, double* G0, int64_t ldg0, int64_t* p0, double* cV, double* GV, int64_t ldgv,
+                                    int64_t* pV);
 
 /* ---- BFFPSV18: dense reach_blocks! (BFFPSV18/reach_blocks.jl:135-224) ---------------------------------- */
 /* One-shot host-buffer call = the method the shim adds for
@@ -175,9 +203,7 @@ REACH_API int32_t reach_bffpsv18_check_lazy(reach_sparse* sp, double delta, cons
 REACH_API int32_t reach_sparse_timing(reach_sparse* sp, double* run_ms, int64_t* products, double* bytes);
 
 /* ---- GLGM06: reach_homog! / reach_inhomog! (GLGM06/reach.jl:5-62) -------------------------------------- */
-/* flags */
-#define REACH_GLGM06_KEEP_ZERO_GENERATORS 1 /* Zonotope(c, G; remove_zero_generators=false) semantics */
-#define REACH_GLGM06_RECORD_SELECTIONS 2    /* keep sortperm + scores of every reduce_order call (reach_flowpipe_selection) */
+/* flags: REACH_GLGM06_KEEP_ZERO_GENERATORS, REACH_GLGM06_RECORD_SELECTIONS (defined above) */
 /* Upload Ω0red = (c0, G0 n x p0) (already reduce_order'ed, GLGM06/post.jl:20 -- or call reach_reduce_order) and
  * the discretised input V = (cV, GV n x pV); pV == 0 and cV == NULL selects reach_homog!. */
 REACH_API int32_t reach_glgm06_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, int64_t p0, const double* c0,

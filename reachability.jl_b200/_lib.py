@@ -31,6 +31,8 @@ _SIGNATURES = {
     "reach_version": [],
     "reach_ctx_create": [i32, C.POINTER(vp)],
     "reach_ctx_create_on_stream": [i32, vp, C.POINTER(vp)],
+    "reach_ctx_create_multi": [c_int32_p, i32, C.POINTER(vp)],
+    "reach_ctx_device_count": [vp, c_int32_p],
     "reach_ctx_destroy": [vp],
     "reach_last_error": [vp],
     "reach_sync": [vp],
@@ -40,6 +42,9 @@ _SIGNATURES = {
     "reach_discretize_box": [vp, i64, c_double_p, i64, f64, i32, c_double_p, c_double_p, i64, c_double_p, i64,
                              c_double_p, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p, c_double_p,
                              c_double_p, c_double_p, c_double_p],
+    "reach_discretize_zonotope": [vp, i64, c_double_p, i64, f64, i32, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p,
+                                  c_double_p, i32, c_double_p, i64, c_double_p, c_double_p, i64, c_int64_p, c_double_p, c_double_p,
+                                  i64, c_int64_p],
     "reach_bffpsv18_boxes": _BOX_ARGS + [c_double_p, c_double_p, c_int64_p],
     "reach_bffpsv18_boxes_csc": [vp, i64, i64, c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p, i64, c_double_p, i64,
                                  c_double_p, c_double_p, c_double_p, i64, c_int32_p, i64, c_double_p, c_double_p, c_int64_p],

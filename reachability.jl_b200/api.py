@@ -437,6 +437,10 @@ def solve(problem: InitialValueProblem, options: Optional[Options] = None, op=No
     if isinstance(op, BFFPSV18):
         sol = _post_bffpsv18(op, problem, opts, _context(device))
     elif isinstance(op, GLGM06):
+        if op["discretization"] in ("firstorder", "nobloating"):
+            # discretize(...; set_operations="zonotope") throws ArgumentError for these models (discretize.jl:105-115); running
+            # them anyway would drop the bloating terms silently and return an unsound flowpipe
+            raise ValueError(f"the algorithm {op['discretization']} with set operations=zonotope is not implemented")
         sol = _post_glgm06(op, problem, opts, _context(device))
     else:
         raise ReachError(3, f"post operator {type(op).__name__} is not on the sm_100a path")
@@ -583,53 +587,19 @@ def _box_solution(C, R, N, delta, partition, blocks, dims, types, opts, D):
 
 
 def discretize_zonotope(ctx: Context, A, delta, c, r, B=None, U=None, algorithm="forward", remove_zero_generators=True):
-    """`discretize(...; set_operations="zonotope")` (discretize.jl:705-743) for a box X0: the matrix work (Φ, Φ₂(|A|),
-    Einit, Eψ0) runs on the device; what remains is LazySets bookkeeping on the returned arrays -- column scaling,
-    concatenation, and the convex-hull formula of `overapproximate(CH(Z1, Z2), Zonotope)`.
-    Returns (Phi, (c0, G0), (cV, GV) or None)."""
-    n = len(c)
-    D = ctx.discretize_box(A, delta, c, r, B if U is not None else None, None if U is None else U[0],
-                           None if U is None else U[1], algorithm=algorithm)
-    Phi = D["Phi"]
-
-    def strip(G):
-        G = G.reshape(n, -1)
-        return G[:, np.any(G != 0.0, axis=0)] if remove_zero_generators and G.shape[1] else G
-
-    def diag(v):
-        return strip(np.diag(v))
-
-    def matvec(M, v):       # device GEMM with one column
-        return ctx.dgemm_left(M, np.asarray(v, dtype=np.float64).reshape(-1, 1))[0].ravel()
-
-    Z1c, Z1G = c, diag(r)                                                    # convert(Zonotope, X0)    :707 / :717
-    Einit = diag(D["rE"])                                                    # :706 / :715
-    PhiX0c = matvec(Phi, c)
-    PhiX0G = strip(Phi * r[None, :])                                         # Φ diag(r): column scaling
-    if U is None:
-        Z2c, Z2G = PhiX0c, strip(np.hstack([PhiX0G, strip(Phi * D["rE"][None, :])]))   # linear_map(Φ, Z1 ⊕ Einit)  :708
-        V = None
-    else:
-        cU, rU = U
-        Bm = np.eye(n) if B is None else B
-        U0c = cU.copy() if B is None else matvec(Bm, cU)                     # convert(Zonotope, B*U)   :719
-        dU0c = delta * U0c                                                   # :720-721
-        dU0G = strip(delta * (Bm * rU[None, :]))
-        Epsi = diag(D["rpsi"])                                               # :716
-        Z2c = PhiX0c + dU0c
-        Z2G = strip(np.hstack([PhiX0G, dU0G, Epsi, Einit]))                   # :722
-        V = (dU0c, strip(np.hstack([dU0G, Epsi])))                            # :726
-    # overapproximate(CH(Z1, Z2), Zonotope): operand with more generators first   (SURVEY.md B.5)
-    (c1, G1_), (c2, G2_) = (Z1c, Z1G), (Z2c, Z2G)
-    if G2_.shape[1] > G1_.shape[1]:
-        (c1, G1_), (c2, G2_) = (c2, G2_), (c1, G1_)
-    q = G2_.shape[1]
-    c0 = (c1 + c2) / 2
-    if G1_.shape[1] == q:
-        G0 = np.hstack([G1_ + G2_, (c1 - c2)[:, None], G1_ - G2_]) / 2
-    else:
-        G0 = np.hstack([(G1_[:, :q] + G2_) / 2, ((c1 - c2) / 2)[:, None], (G1_[:, :q] - G2_) / 2, G1_[:, q:]])
-    return Phi, (c0, strip(G0)), V
+    """`discretize(...; set_operations="zonotope")` (discretize.jl:705-743) for a box X0: Φ, Φ₂(|A|), Einit, Eψ0 AND the
+    concrete zonotope arithmetic (convert, linear_map, minkowski_sum, overapproximate(CH(Z1, Z2), Zonotope), the
+    constructor's zero-generator removal) run on the device behind `reach_discretize_zonotope`.
+    Returns (Phi, (c0, G0), (cV, GV) or None).  `firstorder` / `nobloating` raise like the reference's ArgumentError
+    (discretize.jl:105-115)."""
+    if algorithm in ("firstorder", "nobloating"):
+        raise ValueError(f"the algorithm {algorithm} with set operations=zonotope is not implemented")
+    if algorithm not in ("forward", "backward"):
+        raise ValueError(f"the algorithm {algorithm} is unknown")                      # discretize.jl:121
+    D = ctx.discretize_zonotope(A, delta, c, r, B if U is not None else None, None if U is None else U[0],
+                                None if U is None else U[1], algorithm=algorithm, remove_zero_generators=remove_zero_generators)
+    V = None if U is None else (D["cV"], D["GV"])
+    return D["Phi"], (D["c0"], D["G0"]), V
 
 
 def _post_glgm06(op, problem, opts, ctx):
@@ -641,6 +611,8 @@ def _post_glgm06(op, problem, opts, ctx):
     if N < 1:
         raise ValueError("the time horizon is shorter than half a time step")
     c, r = _as_box(problem.x0, "initial set")
+    if op["discretization"] in ("firstorder", "nobloating"):                 # ArgumentError, discretize.jl:105-115
+        raise ValueError(f"the algorithm {op['discretization']} with set operations=zonotope is not implemented")
     Phi, (c0, G0), V = discretize_zonotope(ctx, A, delta, c, r, B, U, op["discretization"])
     G0red, _ = ctx.reduce_order(c0, G0, max_order)                           # post.jl:20
     fp = ctx.glgm06(Phi, c0, G0red, N, max_order, None if V is None else V[0], None if V is None else V[1], 0)

@@ -18,11 +18,21 @@ RECORD_SELECTIONS = 2        # REACH_GLGM06_RECORD_SELECTIONS
 class Context:
     """`reach_ctx`: one CUDA device + stream.  Raises ReachError when no B200 is visible."""
 
-    def __init__(self, device: int = 0, stream: Optional[int] = None):
-        """`stream`: a cudaStream_t handle to borrow (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+    def __init__(self, device=0, stream: Optional[int] = None):
+        """`device`: a CUDA device index, or a sequence of them for a multi-device context (reach_ctx_create_multi: the BFFPSV18
+        box calls then shard their rows over all listed devices inside the library).
+        `stream`: a cudaStream_t handle to borrow (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         self.lib = _lib.load()
         self._h = C.c_void_p()
-        rc = self.lib.reach_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(self._h))
+        if isinstance(device, (list, tuple, np.ndarray)):
+            assert stream is None, "a multi-device context owns its streams"
+            devs = np.ascontiguousarray(device, dtype=np.int32)
+            rc = self.lib.reach_ctx_create_multi(iptr(devs), len(devs), C.byref(self._h))
+            self.devices = [int(d) for d in devs]
+            device = self.devices[0] if len(devs) else 0
+        else:
+            rc = self.lib.reach_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(self._h))
+            self.devices = [int(device)]
         if rc != 0:
             raise ReachError(rc, (self.lib.reach_last_error(None) or b"").decode())
         self.device = device
@@ -53,6 +63,11 @@ class Context:
 
     def sync(self):
         self._check(self.lib.reach_sync(self._h))
+
+    def device_count(self) -> int:
+        v = C.c_int32()
+        self._check(self.lib.reach_ctx_device_count(self._h, C.byref(v)))
+        return int(v.value)
 
     def launch_count(self) -> int:
         v = C.c_uint64()
@@ -124,6 +139,37 @@ class Context:
         if want_phi2abs:
             out["Phi2abs"] = P2
         return out
+
+    def discretize_zonotope(self, A, delta, c, r, B=None, cU=None, rU=None, algorithm="forward", remove_zero_generators=True):
+        """`discretize(...; set_operations="zonotope")` on the device (reach_discretize_zonotope).
+        Returns dict(Phi, c0, G0, cV, GV) -- cV / GV are None for a homogeneous system."""
+        A = fmat(A)
+        n = A.shape[0]
+        alg = {"forward": 0, "backward": 1, "firstorder": 2, "nobloating": 3}.get(algorithm)
+        if alg is None:
+            raise ValueError(f"the algorithm {algorithm} is unknown")
+        if alg >= 2:        # ArgumentError, discretize.jl:105-115
+            raise ValueError(f"the algorithm {algorithm} with set operations=zonotope is not implemented")
+        c, r = fvec(c), fvec(r)
+        m, Bm = 0, None
+        if cU is not None:
+            cU, rU = fvec(cU), fvec(rU)
+            m = len(cU)
+            Bm = None if B is None else fmat(np.asarray(B, dtype=np.float64).reshape(n, -1))
+            assert Bm is None or Bm.shape == (n, m)
+            assert Bm is not None or m == n, "B = None means the identity and needs an n-dimensional input set"
+        Phi = np.zeros((n, n), order="F")
+        c0 = np.zeros(n)
+        G0 = np.zeros((n, 4 * n + m + 1), order="F")
+        cV = np.zeros(n) if m else None
+        GV = np.zeros((n, n + m), order="F") if m else None
+        p0, pV = C.c_int64(), C.c_int64()
+        flags = 0 if remove_zero_generators else KEEP_ZERO_GENERATORS
+        self._check(self.lib.reach_discretize_zonotope(
+            self._h, n, dptr(A), n, float(delta), alg, dptr(c), dptr(r), m, dptr(Bm), n, dptr(cU), dptr(rU), flags,
+            dptr(Phi), n, dptr(c0), dptr(G0), n, C.byref(p0), dptr(cV), dptr(GV), n, C.byref(pV)))
+        return dict(Phi=Phi, c0=c0, G0=np.asfortranarray(G0[:, :p0.value]), cV=cV,
+                    GV=np.asfortranarray(GV[:, :pV.value]) if m else None)
 
     # ---- BFFPSV18 --------------------------------------------------------------------------------------
     @staticmethod

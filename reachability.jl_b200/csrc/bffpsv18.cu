@@ -383,6 +383,11 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
         P->ctx = ctx; P->n = n; P->m = m; P->nrows = nrows; P->N = N;
         P->Rp = round_up(nrows, 8);
         P->s = N > 2 ? choose_block(n, P->Rp, N, m) : 1;
+        if (const char* e = getenv("REACH_BFFPSV18_BLOCK")) {       // diagnostics: powers per stacked GEMM, rounded down to a power of two
+            int64_t want = std::max(1, std::min(1024, atoi(e))), pw2 = 1;
+            while (pw2 * 2 <= want) pw2 *= 2;
+            if (N > 2) P->s = pw2;
+        }
         const int64_t s = P->s;
         P->Phi = dmat_alloc(ctx, n, n);
         if (Phi) dmat_upload(ctx, P->Phi, Phi, ldphi);
@@ -432,6 +437,9 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
 
 void boxplan_destroy(BoxPlan* P) {
     if (!P) return;
+    // the blocks go back to the context's pool at once: neither stream of this plan may still be using them
+    if (P->side) cudaStreamSynchronize(P->side);
+    if (P->ctx) cudaStreamSynchronize(P->ctx->stream);
     for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->E1, &P->MU})
         dmat_free(*d);
     for (double* v : {P->bsum1, P->fsum1})
@@ -691,6 +699,19 @@ void boxplan_fetch_map(BoxPlan* P, double* centers, double* radii, int64_t* viol
     if (radii) REACH_CUDA(cudaMemcpyAsync(radii, P->out_r, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     REACH_CUDA(cudaStreamSynchronize(ctx->stream));
     if (violation) *violation = P->violation;
+}
+
+// Rows of this plan into rows [0, nrows) of an ld_out x N column-major host array (ld_out >= nrows): the shards of a
+// multi-device call land side by side in the caller's result arrays.
+void boxplan_fetch_strided(BoxPlan* P, double* centers, double* radii, int64_t ld_out) {
+    Ctx* ctx = P->ctx;
+    REACH_REQUIRE(ld_out >= P->nrows, "bffpsv18: output leading dimension smaller than the shard");
+    const size_t w = sizeof(double) * (size_t)P->nrows;
+    if (centers)
+        REACH_CUDA(cudaMemcpy2DAsync(centers, ld_out * sizeof(double), P->centers, w, w, P->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (radii)
+        REACH_CUDA(cudaMemcpy2DAsync(radii, ld_out * sizeof(double), P->radii, w, w, P->N, cudaMemcpyDeviceToHost, ctx->stream));
+    REACH_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 void boxplan_fetch(BoxPlan* P, double* centers, double* radii) {

@@ -1,6 +1,7 @@
 // C ABI: BFFPSV18 entry points (include/reach.h).
 #include "common.cuh"
 #include <algorithm>
+#include <thread>
 #include "../../include/reach.h"
 
 namespace reach {
@@ -11,6 +12,8 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
 void boxplan_destroy(BoxPlan* P);
 void boxplan_run(BoxPlan* P);
 void boxplan_fetch(BoxPlan* P, double* centers, double* radii);
+void boxplan_fetch_strided(BoxPlan* P, double* centers, double* radii, int64_t ld_out);
+std::vector<Ctx*> ctxs_of(reach_ctx* h);
 void boxplan_results(BoxPlan* P, double** c, double** r);
 void boxplan_timing(BoxPlan* P, double* run_ms, double* gemm_ms, int64_t* launches, double* flops);
 void boxplan_attach_map(BoxPlan* P, int64_t q, const double* M, int64_t ldm, int64_t nblocks, const int32_t* block_sizes,
@@ -32,7 +35,50 @@ struct reach_boxplan {
         REACH_CUDA(cudaSetDevice((ctx)->device));
 #define GUARD_END(ctx) \
     } catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; } \
-    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; } \
+    catch (...) { (ctx)->last_error = "unknown exception"; return REACH_ECUDA; }
+
+namespace {
+
+// BFFPSV18 on a multi-device context (reach_ctx_create_multi): the rows of interest are sharded in
+// contiguous ranges over the devices, Phi and the sets are replicated, and every device runs the complete recurrence on
+// its rows -- P_k[R_g, :] = P_{k-1}[R_g, :] Phi needs nothing from the other shards, so there is NO collective: one host
+// thread per device drives upload, time loop and the strided download into the caller's arrays ("gather only at the end").
+// For the box set types every coordinate is independent, so a shard boundary may fall inside a partition block.
+void boxes_multi(const std::vector<Ctx*>& cs, int64_t n, const double* Phi, int64_t ldphi, const PhiCsc* csc, const double* c0,
+                 const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU, const double* rU, const double* rpsi,
+                 int64_t nrows, const int32_t* rows, int64_t N, double* centers, double* radii) {
+    const int64_t G = std::min<int64_t>((int64_t)cs.size(), nrows);
+    struct Part { int code = 0; std::string msg; };
+    std::vector<Part> parts((size_t)G);
+    std::vector<std::thread> th;
+    for (int64_t g = 0; g < G; ++g) {
+        th.emplace_back([&, g]() {
+            Ctx* ctx = cs[(size_t)g];
+            const int64_t lo = nrows * g / G, hi = nrows * (g + 1) / G;
+            BoxPlan* p = nullptr;
+            try {
+                REACH_CUDA(cudaSetDevice(ctx->device));
+                p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, hi - lo, rows + lo, N, csc);
+                boxplan_run(p);
+                boxplan_fetch_strided(p, centers + lo, radii + lo, nrows);
+            } catch (const reach::Error& e) {
+                parts[(size_t)g].code = e.code; parts[(size_t)g].msg = e.what();
+            } catch (const std::exception& e) {
+                parts[(size_t)g].code = REACH_ECUDA; parts[(size_t)g].msg = e.what();
+            } catch (...) {
+                parts[(size_t)g].code = REACH_ECUDA; parts[(size_t)g].msg = "unknown exception";
+            }
+            if (p) boxplan_destroy(p);
+        });
+    }
+    for (std::thread& t : th) t.join();
+    for (int64_t g = 0; g < G; ++g)
+        if (parts[(size_t)g].code)
+            throw reach::Error(parts[(size_t)g].code, "device " + std::to_string(cs[(size_t)g]->device) + ": " + parts[(size_t)g].msg);
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -95,6 +141,12 @@ int32_t reach_bffpsv18_boxes(reach_ctx* h, int64_t n, const double* Phi, int64_t
     Ctx* ctx = ctx_of(h);
     GUARD_BEGIN(ctx)
     REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes: output buffers required");
+    const std::vector<Ctx*> cs = ctxs_of(h);
+    if (cs.size() > 1 && nrows > 1 && rows) {
+        boxes_multi(cs, n, Phi, ldphi, nullptr, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii);
+        if (steps_done) *steps_done = N;
+        return REACH_OK;
+    }
     BoxPlan* p = boxplan_create(ctx, n, Phi, ldphi, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N);
     try {
         boxplan_run(p);
@@ -118,6 +170,12 @@ int32_t reach_bffpsv18_boxes_csc(reach_ctx* h, int64_t n, int64_t nnz, const int
     GUARD_BEGIN(ctx)
     REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes_csc: output buffers required");
     const PhiCsc csc{nnz, colptr, rowval, nzval};
+    const std::vector<Ctx*> cs = ctxs_of(h);
+    if (cs.size() > 1 && nrows > 1 && rows) {
+        boxes_multi(cs, n, nullptr, 0, &csc, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii);
+        if (steps_done) *steps_done = N;
+        return REACH_OK;
+    }
     BoxPlan* p = boxplan_create(ctx, n, nullptr, 0, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, &csc);
     try {
         boxplan_run(p);

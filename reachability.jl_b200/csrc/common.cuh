@@ -67,7 +67,9 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> scratch;     // freed at destroy
     // size-keyed cache of device blocks: repeated calls with the same shapes (one-shot C-ABI entry points) skip
-    // cudaMalloc / cudaFree.  Blocks are only recycled after the owning stream has been synchronised.
+    // cudaMalloc / cudaFree.  ctx_free parks a block at once and ctx_malloc hands it out without synchronising, so the OWNER
+    // must have drained every stream that touched the block before it calls ctx_free: boxplan_destroy / flowpipe_free
+    // synchronise their side streams first, DevScratch / DMatGuard synchronise the context's stream in their destructors.
     std::multimap<size_t, void*> pool;
     std::unordered_map<void*, size_t> block_size;
     size_t pooled_bytes = 0;
@@ -78,11 +80,42 @@ void* ctx_malloc(Ctx* ctx, size_t bytes);       // never returns nullptr (throws
 void ctx_free(Ctx* ctx, void* p);               // back to the cache (or cudaFree beyond the limit)
 void ctx_release_pool(Ctx* ctx);
 
+// RAII scratch of pooled device blocks for one C-ABI call: the destructor drains the context's stream first, so a block never
+// goes back to the pool while a kernel or copy of this call may still touch it (also when an exception unwinds the call).
+struct DevScratch {
+    Ctx* ctx;
+    std::vector<void*> blocks;
+    explicit DevScratch(Ctx* c) : ctx(c) {}
+    DevScratch(const DevScratch&) = delete;
+    DevScratch& operator=(const DevScratch&) = delete;
+    ~DevScratch() {
+        cudaStreamSynchronize(ctx->stream);
+        for (void* p : blocks) ctx_free(ctx, p);
+    }
+    template <typename T>
+    T* get(size_t count) {
+        T* p = (T*)ctx_malloc(ctx, sizeof(T) * (count ? count : 1));
+        blocks.push_back(p);
+        return p;
+    }
+};
+
 DMat dmat_alloc(Ctx* ctx, int64_t rows, int64_t cols, int64_t extra_rows = 0);
 void dmat_free(DMat& m);
 void dmat_upload(Ctx* ctx, DMat& dst, const double* host, int64_t ld_host);      // host col-major -> device
 void dmat_download(Ctx* ctx, const DMat& src, double* host, int64_t ld_host);
 void dmat_zero(Ctx* ctx, DMat& m);
+// owns a DMat for the duration of a C-ABI call; like DevScratch it drains the stream before the block is recycled
+struct DMatGuard {
+    DMat m;
+    explicit DMatGuard(DMat d) : m(d) {}
+    DMatGuard(const DMatGuard&) = delete;
+    DMatGuard& operator=(const DMatGuard&) = delete;
+    ~DMatGuard() {
+        if (m.ctx && m.p) cudaStreamSynchronize(m.ctx->stream);
+        dmat_free(m);
+    }
+};
 
 // A host matrix given as Julia's SparseMatrixCSC fields (1-based Int64 indices)
 struct PhiCsc {

@@ -107,6 +107,85 @@ __global__ void omega0_box_kernel(int n, const double* __restrict__ c, const dou
     r0[i] = (hi - lo) / 2;
 }
 
+
+// ---- set_operations = "zonotope" (discretize.jl:705-743): concrete zonotope arithmetic on the device ------------------------
+// Candidate generators of Z2, one warp per column, with a "has a non-zero entry" flag per column (the `Zonotope`
+// constructor's zero-generator removal):
+//   inhomogeneous (:718-722)  [ Φ diag(r) | δ (B diag(rU)) | diag(rψ) | diag(rE) ]      3n + m columns
+//   homogeneous   (:708)      [ Φ diag(r) | Φ diag(rE) ]                                2n columns   (Φ also maps Einit)
+__global__ void __launch_bounds__(256) zono_cand_kernel(int n, int m, int homog, const double* __restrict__ Phi, int64_t ldphi,
+                                                        const double* __restrict__ r, const double* __restrict__ rE,
+                                                        const double* __restrict__ B, int64_t ldb, const double* __restrict__ rU,
+                                                        double delta, const double* __restrict__ rpsi, double* __restrict__ C,
+                                                        int64_t ldc, int* __restrict__ flags) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int ncand = homog ? 2 * n : 3 * n + m;
+    if (j >= ncand) return;
+    int any = 0;
+    for (int i = lane; i < n; i += 32) {
+        double v;
+        if (j < n) v = Phi[(int64_t)j * ldphi + i] * r[j];                               // linear_map(ϕ, Z1)
+        else if (homog) v = Phi[(int64_t)(j - n) * ldphi + i] * rE[j - n];               // ϕ * Einit
+        else if (j < n + m) v = delta * (B[(int64_t)(j - n) * ldb + i] * rU[j - n]);     // linear_map(δI, convert(Zonotope, B*U))
+        else if (j < 2 * n + m) v = (i == j - n - m) ? rpsi[i] : 0.0;                    // Eψ0
+        else v = (i == j - 2 * n - m) ? rE[i] : 0.0;                                     // Einit
+        C[(int64_t)j * ldc + i] = v;
+        any |= (v != 0.0);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[j] = any;
+}
+
+// overapproximate(ConvexHull(ZA, ZB), Zonotope) with ngens(ZA) = qA >= qB = ngens(ZB), one warp per column:
+//   [ (GA[:, 1:qB] + GB)/2 | (cA - cB)/2 | (GA[:, 1:qB] - GB)/2 | GA[:, qB+1:end] ],   centre (cA + cB)/2.
+// An operand is either Z1 = convert(Zonotope, X0) (type 0: column j = r[j] e_j) or Z2 (type 1: candidate column j of C).
+struct ZonoOperand {
+    int type, q;
+    const int* idx;         // the generators that exist (zero-generator removal already applied)
+    const double* c;        // centre
+};
+__device__ __forceinline__ double zono_entry(const ZonoOperand& z, int col, int i, const double* __restrict__ r,
+                                             const double* __restrict__ C, int64_t ldc) {
+    const int j = z.idx[col];
+    return z.type == 0 ? (i == j ? r[j] : 0.0) : C[(int64_t)j * ldc + i];
+}
+__global__ void __launch_bounds__(256) zono_ch_kernel(int n, ZonoOperand za, ZonoOperand zb, const double* __restrict__ r,
+                                                      const double* __restrict__ C, int64_t ldc, double* __restrict__ out,
+                                                      int64_t ldo, int* __restrict__ flags, double* __restrict__ c0) {
+    const int oc = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int qB = zb.q, total = za.q + zb.q + 1;
+    if (oc >= total) return;
+    int any = 0;
+    for (int i = lane; i < n; i += 32) {
+        double v;
+        if (oc < qB) v = (zono_entry(za, oc, i, r, C, ldc) + zono_entry(zb, oc, i, r, C, ldc)) / 2;
+        else if (oc == qB) {
+            v = (za.c[i] - zb.c[i]) / 2;
+            c0[i] = (za.c[i] + zb.c[i]) / 2;
+        } else if (oc <= 2 * qB) v = (zono_entry(za, oc - qB - 1, i, r, C, ldc) - zono_entry(zb, oc - qB - 1, i, r, C, ldc)) / 2;
+        else v = zono_entry(za, oc - qB - 1, i, r, C, ldc);
+        out[(int64_t)oc * ldo + i] = v;
+        any |= (v != 0.0);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[oc] = any;
+}
+
+// dst[:, k] = src[:, idx[k]]
+__global__ void __launch_bounds__(256) gather_cols_kernel(int n, int count, const int* __restrict__ idx, const double* __restrict__ src,
+                                                          int64_t lds, double* __restrict__ dst, int64_t ldd) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= count) return;
+    const int j = idx[k];
+    for (int i = lane; i < n; i += 32) dst[(int64_t)k * ldd + i] = src[(int64_t)j * lds + i];
+}
+
+// y = a + alpha * b
+__global__ void axpy_vec_kernel(int n, const double* __restrict__ a, double alpha, const double* __restrict__ b, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (a ? a[i] : 0.0) + alpha * b[i];
+}
+
 void launch2d(Ctx* ctx, int n, dim3& grid) { grid = dim3((unsigned)ceil_div(n, 256), (unsigned)n); (void)ctx; }
 
 }  // namespace
@@ -234,7 +313,8 @@ using namespace reach;
 #define D_END(ctx)                                                                                \
     }                                                                                             \
     catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
-    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; } \
+    catch (...) { (ctx)->last_error = "unknown exception"; return REACH_ECUDA; }
 
 // discretize_firstorder (p = Inf, discretize.jl:403-473) and discretize_nobloating (:527-552) for box sets, in the same
 // array form as the interpolation models.
@@ -335,6 +415,86 @@ static int32_t discretize_box_other(Ctx* ctx, int64_t n, const double* A, int64_
     return REACH_OK;
 }
 
+
+// Device results of discretize_interpolation (forward / backward) for a box X0 and a constant box input through B, kept on
+// the device: the box entry point downloads them, the zonotope entry point keeps building on them.
+struct BoxDev {
+    Ctx* ctx = nullptr;
+    int64_t n = 0, m = 0;
+    DMat dA, dPhi, dP2, dM, dM2, dB, dMU;
+    double* vec = nullptr;
+    // n-vectors: 0 c, 1 r, 2 Φc, 3 |Φ|r, 4-6 inner sih of (A²)X0, 7 rE, 8 (δB)cU, 9 |δB|rU, 10-12 inner sih of (AB)U, 13 rψ,
+    //            14 c0, 15 r0, 16 B cU, 17 Φc + δ(B cU) ; then the m-vectors cU, rU
+    static constexpr int NV = 18;
+    double* V(int i) const { return vec + (int64_t)i * n; }
+    double* dcU() const { return vec + (int64_t)NV * n; }
+    double* drU() const { return dcU() + std::max<int64_t>(m, 1); }
+    ~BoxDev() {
+        if (ctx) cudaStreamSynchronize(ctx->stream);      // nothing may still be using the blocks that go back to the pool
+        dmat_free(dA); dmat_free(dPhi); dmat_free(dP2); dmat_free(dM); dmat_free(dM2); dmat_free(dB); dmat_free(dMU);
+        if (vec) ctx_free(ctx, vec);
+    }
+};
+
+static void interp_box_device(Ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm, const double* c,
+                              const double* r, int64_t m, const double* B, int64_t ldb, const double* cU, const double* rU,
+                              BoxDev& d) {
+    REACH_REQUIRE(m >= 0 && (m == 0 || (cU && rU)), "reach_discretize: inputs need cU, rU");
+    REACH_REQUIRE(!B || ldb >= n, "reach_discretize: bad ldb");
+    REACH_REQUIRE(B || m == 0 || m == n, "reach_discretize: B == NULL means identity and needs m == n");
+    cudaStream_t st = ctx->stream;
+    d.ctx = ctx; d.n = n; d.m = m;
+    d.dA = dmat_alloc(ctx, n, n); d.dPhi = dmat_alloc(ctx, n, n); d.dP2 = dmat_alloc(ctx, n, n); d.dM = dmat_alloc(ctx, n, n);
+    const size_t vbytes = sizeof(double) * (size_t)(BoxDev::NV * n + 2 * std::max<int64_t>(m, 1));
+    d.vec = (double*)ctx_malloc(ctx, vbytes);
+    REACH_CUDA(cudaMemsetAsync(d.vec, 0, vbytes, st));
+    dmat_upload(ctx, d.dA, A, lda);
+    REACH_CUDA(cudaMemcpyAsync(d.V(0), c, n * 8, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(cudaMemcpyAsync(d.V(1), r, n * 8, cudaMemcpyHostToDevice, st));
+    expm_family(ctx, n, d.dA.p, d.dA.ld, delta, false, &d.dPhi, nullptr, nullptr);          // ϕ = exp_Aδ(A, δ)        :649
+    expm_family(ctx, n, d.dA.p, d.dA.ld, delta, true, nullptr, nullptr, &d.dP2);            // Phi2Aabs = Φ₂(|A|, δ)   :652
+    gemm_left(ctx, n, n, n, d.dA.p, d.dA.ld, d.dA.p, d.dA.ld, d.dM.p, d.dM.ld);              // A * A                   :655
+    const DMat* Msel = &d.dM;
+    if (algorithm == REACH_BACKWARD) {                                                       // A * A * ϕ               :657
+        d.dM2 = dmat_alloc(ctx, n, n);
+        gemm_left(ctx, n, n, n, d.dM.p, d.dM.ld, d.dPhi.p, d.dPhi.ld, d.dM2.p, d.dM2.ld);
+        Msel = &d.dM2;
+    }
+    const unsigned gv = (unsigned)ceil_div(n, 256);
+    box_matvec(ctx, n, n, Msel->p, Msel->ld, d.V(0), d.V(1), d.V(4), d.V(5));                // box of (A²)X0
+    sih_kernel<<<gv, 256, 0, st>>>((int)n, d.V(4), d.V(5), d.V(6));                          // inner sih
+    box_matvec(ctx, n, n, d.dP2.p, d.dP2.ld, nullptr, d.V(6), nullptr, d.V(7));              // Einit radius = Φ₂|A| s1
+    box_matvec(ctx, n, n, d.dPhi.p, d.dPhi.ld, d.V(0), d.V(1), d.V(2), d.V(3));              // box of ΦX0
+    ctx->launches += 1;
+    if (m > 0) {
+        REACH_CUDA(cudaMemcpyAsync(d.dcU(), cU, m * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(cudaMemcpyAsync(d.drU(), rU, m * 8, cudaMemcpyHostToDevice, st));
+        d.dB = dmat_alloc(ctx, n, m);
+        if (B) {
+            dmat_upload(ctx, d.dB, B, ldb);
+        } else {
+            dim3 g2((unsigned)ceil_div(n, 256), (unsigned)n);
+            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, d.dA.p, d.dA.ld, 0.0, nullptr, 0, 1.0, d.dB.p, d.dB.ld);
+            ctx->launches++;
+        }
+        d.dMU = dmat_alloc(ctx, n, m);
+        gemm_left(ctx, n, m, n, d.dA.p, d.dA.ld, d.dB.p, d.dB.ld, d.dMU.p, d.dMU.ld);        // A * U0 = (A B) U        :671
+        box_matvec(ctx, n, m, d.dMU.p, d.dMU.ld, d.dcU(), d.drU(), d.V(10), d.V(11));
+        sih_kernel<<<gv, 256, 0, st>>>((int)n, d.V(10), d.V(11), d.V(12));
+        box_matvec(ctx, n, n, d.dP2.p, d.dP2.ld, nullptr, d.V(12), nullptr, d.V(13));        // Eψ0 radius
+        // δ U0: MU = δ B, box of MU * U
+        dim3 gm((unsigned)ceil_div(n, 256), (unsigned)m);
+        scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, d.dB.p, d.dB.ld, delta, 0, d.dMU.p, d.dMU.ld);
+        box_matvec(ctx, n, m, d.dMU.p, d.dMU.ld, d.dcU(), d.drU(), d.V(8), d.V(9));
+        box_matvec(ctx, n, m, d.dB.p, d.dB.ld, d.dcU(), nullptr, d.V(16), nullptr);          // B cU (centre of convert(Zonotope, B*U))
+        ctx->launches += 2;
+    }
+    omega0_box_kernel<<<gv, 256, 0, st>>>((int)n, d.V(0), d.V(1), d.V(2), d.V(3), d.V(7), m > 0 ? d.V(8) : nullptr, d.V(9), d.V(13),
+                                          d.V(14), d.V(15));
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
 extern "C" {
 
 int32_t reach_expm(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, double* Phi, int64_t ldphi) {
@@ -381,76 +541,115 @@ int32_t reach_discretize_box(reach_ctx* h, int64_t n, const double* A, int64_t l
         throw Error(REACH_EINVAL, "the algorithm is unknown");      // ArgumentError at discretize.jl:121,659
     if (algorithm == REACH_FIRSTORDER || algorithm == REACH_NOBLOATING)
         return discretize_box_other(ctx, n, A, lda, delta, algorithm, c, r, m, B, ldb, cU, rU, Phi, ldphi, c0, r0, rE, rpsi, MU);
-    REACH_REQUIRE(m >= 0 && (m == 0 || (cU && rU)), "reach_discretize_box: inputs need cU, rU");
-    REACH_REQUIRE(!B || ldb >= n, "reach_discretize_box: bad ldb");
-    REACH_REQUIRE(B || m == 0 || m == n, "reach_discretize_box: B == NULL means identity and needs m == n");
     cudaStream_t st = ctx->stream;
-    DMat dA = dmat_alloc(ctx, n, n), dPhi = dmat_alloc(ctx, n, n), dP2 = dmat_alloc(ctx, n, n), dM = dmat_alloc(ctx, n, n);
-    DMat dM2, dB, dAB;
-    double* vec = nullptr;     // n-vectors: c r pc pr a1 b1 s1 rE uc ur a2 b2 s2 rpsi c0 r0 ; m-vectors: cU rU
-    const int64_t NV = 16;
-    REACH_CUDA(cudaMalloc(&vec, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1))));
-    REACH_CUDA(cudaMemsetAsync(vec, 0, sizeof(double) * (NV * n + 2 * std::max<int64_t>(m, 1)), st));
-    auto V = [&](int i) { return vec + (int64_t)i * n; };
-    double* dcU = vec + NV * n;
-    double* drU = dcU + std::max<int64_t>(m, 1);
-    dmat_upload(ctx, dA, A, lda);
-    REACH_CUDA(cudaMemcpyAsync(V(0), c, n * 8, cudaMemcpyHostToDevice, st));
-    REACH_CUDA(cudaMemcpyAsync(V(1), r, n * 8, cudaMemcpyHostToDevice, st));
-    expm_family(ctx, n, dA.p, dA.ld, delta, false, &dPhi, nullptr, nullptr);          // ϕ = exp_Aδ(A, δ)        :649
-    expm_family(ctx, n, dA.p, dA.ld, delta, true, nullptr, nullptr, &dP2);            // Phi2Aabs = Φ₂(|A|, δ)   :652
-    gemm_left(ctx, n, n, n, dA.p, dA.ld, dA.p, dA.ld, dM.p, dM.ld);                    // A * A                   :655
-    const DMat* Msel = &dM;
-    if (algorithm == REACH_BACKWARD) {                                                 // A * A * ϕ               :657
-        dM2 = dmat_alloc(ctx, n, n);
-        gemm_left(ctx, n, n, n, dM.p, dM.ld, dPhi.p, dPhi.ld, dM2.p, dM2.ld);
-        Msel = &dM2;
-    }
-    const unsigned gv = (unsigned)ceil_div(n, 256);
-    box_matvec(ctx, n, n, Msel->p, Msel->ld, V(0), V(1), V(4), V(5));                  // box of (A²)X0
-    sih_kernel<<<gv, 256, 0, st>>>((int)n, V(4), V(5), V(6));                          // inner sih
-    box_matvec(ctx, n, n, dP2.p, dP2.ld, nullptr, V(6), nullptr, V(7));                // Einit radius = Φ₂|A| s1
-    box_matvec(ctx, n, n, dPhi.p, dPhi.ld, V(0), V(1), V(2), V(3));                    // box of ΦX0
-    ctx->launches += 1;
-    if (m > 0) {
-        REACH_CUDA(cudaMemcpyAsync(dcU, cU, m * 8, cudaMemcpyHostToDevice, st));
-        REACH_CUDA(cudaMemcpyAsync(drU, rU, m * 8, cudaMemcpyHostToDevice, st));
-        dB = dmat_alloc(ctx, n, m);
-        if (B) {
-            dmat_upload(ctx, dB, B, ldb);
-        } else {
-            dim3 g2((unsigned)ceil_div(n, 256), (unsigned)n);
-            axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, dA.p, dA.ld, 0.0, nullptr, 0, 1.0, dB.p, dB.ld);
-            ctx->launches++;
-        }
-        dAB = dmat_alloc(ctx, n, m);
-        gemm_left(ctx, n, m, n, dA.p, dA.ld, dB.p, dB.ld, dAB.p, dAB.ld);              // A * U0 = (A B) U        :671
-        box_matvec(ctx, n, m, dAB.p, dAB.ld, dcU, drU, V(10), V(11));
-        sih_kernel<<<gv, 256, 0, st>>>((int)n, V(10), V(11), V(12));
-        box_matvec(ctx, n, n, dP2.p, dP2.ld, nullptr, V(12), nullptr, V(13));          // Eψ0 radius
-        // δ U0: MU = δ B, box of MU * U
-        dim3 gm((unsigned)ceil_div(n, 256), (unsigned)m);
-        scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, dB.p, dB.ld, delta, 0, dAB.p, dAB.ld);   // reuse dAB as MU
-        box_matvec(ctx, n, m, dAB.p, dAB.ld, dcU, drU, V(8), V(9));
-        ctx->launches += 2;
-    }
-    omega0_box_kernel<<<gv, 256, 0, st>>>((int)n, V(0), V(1), V(2), V(3), V(7), m > 0 ? V(8) : nullptr, V(9), V(13),
-                                          V(14), V(15));
-    REACH_CUDA(cudaGetLastError());
-    ctx->launches++;
-    if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_box: ldphi"); dmat_download(ctx, dPhi, Phi, ldphi); }
-    if (Phi2abs) { REACH_REQUIRE(ldphi2 >= n, "reach_discretize_box: ldphi2"); dmat_download(ctx, dP2, Phi2abs, ldphi2); }
+    BoxDev d;
+    interp_box_device(ctx, n, A, lda, delta, algorithm, c, r, m, B, ldb, cU, rU, d);
+    if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_box: ldphi"); dmat_download(ctx, d.dPhi, Phi, ldphi); }
+    if (Phi2abs) { REACH_REQUIRE(ldphi2 >= n, "reach_discretize_box: ldphi2"); dmat_download(ctx, d.dP2, Phi2abs, ldphi2); }
     auto down = [&](double* dst, int i) {
-        if (dst) REACH_CUDA(cudaMemcpyAsync(dst, V(i), n * 8, cudaMemcpyDeviceToHost, st));
+        if (dst) REACH_CUDA(cudaMemcpyAsync(dst, d.V(i), n * 8, cudaMemcpyDeviceToHost, st));
     };
     down(c0, 14); down(r0, 15); down(rE, 7);
     if (m > 0) {
         down(rpsi, 13);
-        if (MU) dmat_download(ctx, dAB, MU, n);
+        if (MU) dmat_download(ctx, d.dMU, MU, n);
     }
     REACH_CUDA(cudaStreamSynchronize(st));
-    dmat_free(dA); dmat_free(dPhi); dmat_free(dP2); dmat_free(dM); dmat_free(dM2); dmat_free(dB); dmat_free(dAB);
-    cudaFree(vec);
+    return REACH_OK;
+    D_END(ctx)
+}
+
+
+// discretize(...; set_operations = "zonotope") for a box X0 and a constant box input through B (discretize.jl:705-743,
+// 882-890): Φ, Φ₂(|A|), Einit, Eψ0 as in reach_discretize_box, then -- on the device -- the concrete zonotope arithmetic
+// (convert, linear_map, minkowski_sum, overapproximate(ConvexHull(Z1, Z2), Zonotope)) with the `Zonotope` constructor's
+// zero-generator removal.  Only which generators EXIST is decided on the host, from the per-column flags the kernels emit.
+int32_t reach_discretize_zonotope(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, int32_t algorithm,
+                                  const double* c, const double* r, int64_t m, const double* B, int64_t ldb, const double* cU,
+                                  const double* rU, int32_t flags, double* Phi, int64_t ldphi, double* c0, double* G0, int64_t ldg0,
+                                  int64_t* p0, double* cV, double* GV, int64_t ldgv, int64_t* pV) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    D_BEGIN(ctx)
+    REACH_REQUIRE(n > 0 && A && lda >= n && c && r, "reach_discretize_zonotope: bad A / X0");
+    REACH_REQUIRE(c0 && G0 && ldg0 >= n && p0, "reach_discretize_zonotope: c0, G0 (n x (4n + m + 1)) and p0 are required");
+    if (algorithm == REACH_FIRSTORDER || algorithm == REACH_NOBLOATING)      // ArgumentError, discretize.jl:105-115
+        throw Error(REACH_EINVAL, std::string("the algorithm ") + (algorithm == REACH_FIRSTORDER ? "firstorder" : "nobloating") +
+                                      " with set operations=zonotope is not implemented");
+    if (algorithm != REACH_FORWARD && algorithm != REACH_BACKWARD)
+        throw Error(REACH_EINVAL, "the algorithm is unknown");               // discretize.jl:121
+    if (m > 0) REACH_REQUIRE(cV && GV && ldgv >= n && pV, "reach_discretize_zonotope: inputs need cV, GV (n x (n + m)) and pV");
+    const bool rzg = (flags & REACH_GLGM06_KEEP_ZERO_GENERATORS) == 0;
+    cudaStream_t st = ctx->stream;
+    BoxDev d;
+    interp_box_device(ctx, n, A, lda, delta, algorithm, c, r, m, B, ldb, cU, rU, d);
+    const int homog = m == 0 ? 1 : 0;
+    const int64_t ncand = homog ? 2 * n : 3 * n + m, ld = round_up(n, 2), nout_max = n + ncand + 1;
+    DevScratch scr(ctx);        // freed after the stream has drained (also on the error path)
+    double* C = scr.get<double>((size_t)ncand * ld);
+    double* Out = scr.get<double>((size_t)nout_max * ld);
+    double* Fin = scr.get<double>((size_t)nout_max * ld);
+    int* dflags = scr.get<int>(nout_max);
+    int* didx = scr.get<int>(3 * nout_max);
+    zono_cand_kernel<<<(unsigned)ceil_div(ncand * 32, 256), 256, 0, st>>>((int)n, (int)m, homog, d.dPhi.p, d.dPhi.ld, d.V(1), d.V(7),
+                                                                         d.dB.p, d.dB.ld, d.drU(), delta, d.V(13), C, ld, dflags);
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    std::vector<int> f2(ncand);
+    REACH_CUDA(cudaMemcpyAsync(f2.data(), dflags, sizeof(int) * ncand, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> idx1, idx2, idxV;
+    for (int64_t j = 0; j < n; ++j) if (!rzg || r[j] != 0.0) idx1.push_back((int)j);            // convert(Zonotope, X0)   :707 / :717
+    for (int64_t j = 0; j < ncand; ++j) if (!rzg || f2[j]) idx2.push_back((int)j);
+    if (!homog) for (int64_t j = n; j < 2 * n + m; ++j) if (!rzg || f2[j]) idxV.push_back((int)j);   // minkowski_sum(δU0, Eψ0)  :726
+    // centre of Z2: Φ c (+ δ (B cU))
+    const double* c2 = d.V(2);
+    if (!homog) {
+        axpy_vec_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((int)n, d.V(2), delta, d.V(16), d.V(17));
+        ctx->launches++;
+        c2 = d.V(17);
+    }
+    const bool swap = idx2.size() > idx1.size();        // the operand with more generators goes first
+    int* dA_idx = didx;
+    int* dB_idx = didx + nout_max;
+    const std::vector<int>& ia = swap ? idx2 : idx1;
+    const std::vector<int>& ib = swap ? idx1 : idx2;
+    if (!ia.empty()) REACH_CUDA(cudaMemcpyAsync(dA_idx, ia.data(), sizeof(int) * ia.size(), cudaMemcpyHostToDevice, st));
+    if (!ib.empty()) REACH_CUDA(cudaMemcpyAsync(dB_idx, ib.data(), sizeof(int) * ib.size(), cudaMemcpyHostToDevice, st));
+    ZonoOperand za{swap ? 1 : 0, (int)ia.size(), dA_idx, swap ? c2 : d.V(0)};
+    ZonoOperand zb{swap ? 0 : 1, (int)ib.size(), dB_idx, swap ? d.V(0) : c2};
+    const int64_t nout = (int64_t)ia.size() + (int64_t)ib.size() + 1;
+    zono_ch_kernel<<<(unsigned)ceil_div(nout * 32, 256), 256, 0, st>>>((int)n, za, zb, d.V(1), C, ld, Out, ld, dflags, d.V(14));
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches++;
+    std::vector<int> fo(nout), idxO;
+    REACH_CUDA(cudaMemcpyAsync(fo.data(), dflags, sizeof(int) * nout, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    for (int64_t j = 0; j < nout; ++j) if (!rzg || fo[j]) idxO.push_back((int)j);
+    int* dO_idx = didx + 2 * nout_max;
+    auto gather_down = [&](const std::vector<int>& idx, const double* src, double* host, int64_t ldh) {
+        if (idx.empty()) return;
+        REACH_CUDA(cudaMemcpyAsync(dO_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
+        gather_cols_kernel<<<(unsigned)ceil_div((int64_t)idx.size() * 32, 256), 256, 0, st>>>((int)n, (int)idx.size(), dO_idx, src, ld, Fin, ld);
+        REACH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        REACH_CUDA(cudaMemcpy2DAsync(host, ldh * 8, Fin, ld * 8, n * 8, idx.size(), cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));        // dO_idx / Fin are reused by the next gather
+    };
+    gather_down(idxO, Out, G0, ldg0);
+    *p0 = (int64_t)idxO.size();
+    REACH_CUDA(cudaMemcpyAsync(c0, d.V(14), n * 8, cudaMemcpyDeviceToHost, st));
+    if (!homog) {
+        gather_down(idxV, C, GV, ldgv);
+        *pV = (int64_t)idxV.size();
+        axpy_vec_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((int)n, nullptr, delta, d.V(16), d.V(17));     // δ (B cU)
+        ctx->launches++;
+        REACH_CUDA(cudaMemcpyAsync(cV, d.V(17), n * 8, cudaMemcpyDeviceToHost, st));
+    } else if (pV) {
+        *pV = 0;
+    }
+    if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_zonotope: ldphi"); dmat_download(ctx, d.dPhi, Phi, ldphi); }
+    REACH_CUDA(cudaStreamSynchronize(st));
     return REACH_OK;
     D_END(ctx)
 }

@@ -14,6 +14,7 @@
 // half-warp: slot = 4*(lane%4) + lane/4 (mod 16).
 #include "common.cuh"
 #include "tma.cuh"
+#include <mutex>
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 namespace reach {
@@ -239,8 +240,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+std::mutex g_config_mutex;      // guards the per-device "function attributes set" flags and the driver entry point below
+
 EncodeTiledFn encode_tiled() {
     static EncodeTiledFn fn = nullptr;
+    std::lock_guard<std::mutex> lock(g_config_mutex);
     if (!fn) {
         void* sym = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -280,9 +284,12 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
                         STAGES * sizeof(int) + 1024;
     static bool configured[64] = {false};      // function attributes are per device
     const int dev = ctx->device & 63;
-    if (!configured[dev]) {
-        REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = true;
+    {
+        std::lock_guard<std::mutex> lock(g_config_mutex);     // contexts of several devices may run on their own host threads
+        if (!configured[dev]) {
+            REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = true;
+        }
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = ctx->sm_count - ctx->gemm_reserve_sms > 0 ? ctx->sm_count - ctx->gemm_reserve_sms : 1;

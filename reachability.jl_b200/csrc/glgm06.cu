@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cmath>
 #include <climits>
+#include <mutex>
 #include "tma.cuh"
 
 namespace reach {
@@ -1490,6 +1491,11 @@ struct Flowpipe {
 
 void flowpipe_free(Flowpipe* F) {
     if (!F) return;
+    // the blocks go back to the context's pool at once: no stream of this flowpipe may still be using them (a run that
+    // threw half-way leaves its side streams busy)
+    for (cudaStream_t s : {F->side, F->side2, F->side3, F->side4, F->cpy})
+        if (s) cudaStreamSynchronize(s);
+    if (F->ctx) cudaStreamSynchronize(F->ctx->stream);
     dmat_free(F->Phi); dmat_free(F->PowA); dmat_free(F->PowB);
     for (void* p : F->owned) ctx_free(F->ctx, p);
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
@@ -1716,6 +1722,8 @@ static bool map_slots_scored(Flowpipe* F, int lvl, GP& g, int64_t slot0, int cnt
     g.Y = F->Hflow + slot0 * F->qloc * ld;
     g.col0 = slot0 * F->q;
     static bool attr[64] = {false};
+    static std::mutex attr_mutex;
+    std::lock_guard<std::mutex> attr_lock(attr_mutex);
     if (!attr[ctx->device & 63]) {
         REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1869,6 +1877,8 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
 
 static void set_kernel_attributes(Flowpipe* F) {
     static bool done_on[64] = {false};         // function attributes are per device
+    static std::mutex done_mutex;
+    std::lock_guard<std::mutex> done_lock(done_mutex);
     bool& done = done_on[F->ctx->device & 63];
     if (done) return;
     REACH_CUDA(cudaFuncSetAttribute(chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2338,7 +2348,8 @@ struct reach_flowpipe {
 #define FP_END(ctx)                                                                               \
     }                                                                                             \
     catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
-    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; } \
+    catch (...) { (ctx)->last_error = "unknown exception"; return REACH_ECUDA; }
 
 namespace {
 

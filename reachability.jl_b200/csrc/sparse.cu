@@ -947,7 +947,8 @@ struct reach_sparse {
 #define SP_END(ctx)                                                                               \
     }                                                                                             \
     catch (const reach::Error& e) { (ctx)->last_error = e.what(); return e.code; }                \
-    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; }
+    catch (const std::exception& e) { (ctx)->last_error = e.what(); return REACH_ECUDA; } \
+    catch (...) { (ctx)->last_error = "unknown exception"; return REACH_ECUDA; }
 
 extern "C" {
 

@@ -122,3 +122,12 @@ def test_discretization_and_input_options_are_validated():      # BFFPSV18.jl:43
     for bad in (dict(sih_method="eager"), dict(lazy_inputs_interval=-2), dict(lazy_inputs_interval="never")):
         with pytest.raises(ValueError):
             BFFPSV18(**bad)
+
+
+def test_glgm06_rejects_discretisations_without_zonotope_operations():
+    """discretize.jl:105-115: `firstorder` / `nobloating` with set_operations="zonotope" throw ArgumentError in the reference;
+    the mirror raises before any device work instead of silently dropping the bloating terms (unsound flowpipe)."""
+    prob = IVP(LCS(-np.eye(3)), BallInf(np.ones(3), 0.1))
+    for alg in ("firstorder", "nobloating"):
+        with pytest.raises(ValueError, match="with set operations=zonotope is not implemented"):
+            api.solve(prob, Options(T=0.1), op=GLGM06(discretization=alg))

@@ -372,3 +372,29 @@ def test_lazy_expm_literal_restatement_agrees_with_the_recurrence():
     C2, R2 = orc.bffpsv18_reach_lazy(A, D, 0.03, 30, rows)
     assert_close(C2, C1, "centres")
     assert_close(R2, R1, "radii")
+
+
+def test_hull_zonotope_hand_derived_example():
+    """`overapproximate(ConvexHull(Z1, Z2), Zonotope)` (call sites discretize.jl:709,724) on numbers small enough to do by
+    hand (Girard-style enclosure): Z1 = ((0,0), [e1 e2]) has more generators than Z2 = ((2,0), [(1,1)]), so it goes
+    first and q = 1:  c = (1,0);  G = [ (e1+(1,1))/2 | ((0,0)-(2,0))/2 | (e1-(1,1))/2 | e2 ].
+    The COLUMN ORDER is the recalled LazySets convention -- an assumption no reference-held value can confirm here."""
+    Z = orc.ch_zonotope(orc.Zono(np.zeros(2), np.eye(2)), orc.Zono(np.array([2.0, 0.0]), np.array([[1.0], [1.0]])))
+    assert np.array_equal(Z.c, [1.0, 0.0])
+    assert np.array_equal(Z.G, np.array([[1.0, -1.0, 0.0, 0.0], [0.5, 0.0, -0.5, 1.0]]))
+    # whatever the column order: the enclosure contains both operands' vertices
+    for v in ([1, 1], [1, -1], [-1, 1], [-1, -1], [3, 1], [1, -1]):
+        d = np.array([0.3, -0.8])
+        assert d @ Z.c + np.abs(d @ Z.G).sum() >= d @ np.array(v, dtype=float) - 1e-15
+
+
+def test_reduce_order_hand_derived_example():
+    """`reduce_order(Z, r)` (call sites GLGM06/post.jl:20, reach.jl:49,55) by hand, n = 2, p = 5, r = 2:
+    scores h = |g|_1 - |g|_inf = [0, 0, 2, 0.5, 1]; stable sortperm = [1, 2, 4, 5, 3] (the two axis-aligned generators tie at
+    exactly 0 and keep their order); m = p - floor(n (r - 1)) = 3 generators are boxed: d = |g1| + |g2| + |g4| = (1.5, 3.5);
+    result [g5 g3 | diag(d)] -- kept generators in ascending-score order, box generators last."""
+    G = np.array([[1.0, 0.0, 2.0, 0.5, 1.0], [0.0, 3.0, 2.0, 0.5, 4.0]])
+    Z, (h, ind, m) = orc.reduce_order(orc.Zono(np.zeros(2), G), 2, return_selection=True)
+    assert np.array_equal(h, [0.0, 0.0, 2.0, 0.5, 1.0]) and list(ind) == [0, 1, 3, 4, 2] and m == 3
+    assert np.array_equal(Z.G, np.array([[1.0, 2.0, 1.5, 0.0], [4.0, 2.0, 0.0, 3.5]]))
+    assert orc.reduce_order(orc.Zono(np.zeros(2), G[:, :4]), 2).G.shape == (2, 4)        # r n >= p: unchanged
