@@ -23,7 +23,7 @@ namespace reach {
 struct BoxPlan {
     Ctx* ctx = nullptr;
     int64_t n = 0, m = 0, nrows = 0, N = 0, Rp = 0, s = 1;
-    DMat Phi, PowA, PowB, PowT, BtAug, BtSmall, S[2], E, MU;
+    DMat Phi, PowA, PowB, PowT, AccA, AccB, BtAug, BtSmall, S[2], E, MU;
     double *c0 = nullptr, *r0 = nullptr, *rpsi = nullptr, *cU = nullptr, *rU = nullptr;
     double *bsum = nullptr, *fsum = nullptr, *cW = nullptr, *rW = nullptr;
     int32_t* rows = nullptr;
@@ -37,6 +37,9 @@ struct BoxPlan {
     DMat E1;
     double *bsum1 = nullptr, *fsum1 = nullptr;
     std::vector<cudaEvent_t> sync_evs;
+    // fused abs-sum epilogue of the stacked GEMM: partial |P_k| r0, |P_k| rψ per column group, double-buffered by block parity
+    double* part[2] = {nullptr, nullptr};
+    int64_t ngroups = 0, ldpart = 0;
     // ---- lazy-state variants: output_function (reach_blocks.jl:152-155,191-199) and check mode
     //      (check_blocks.jl:105-183).  The states stay lazy per block, so the radius is
     //      sum_b |M[:, b] P[b, :]| r0 + |M| rW   (support function of a CartesianProductArray is separable per block).
@@ -128,6 +131,22 @@ __global__ void __launch_bounds__(256) abs_rowsums_kernel(int64_t mrows, int n, 
             if (WITH_F) fsum[r] = f;
         }
     }
+}
+
+// bsum[i] = sum_q part[(2 q) ldpart + i], fsum[i] = sum_q part[(2 q + 1) ldpart + i]: the column-group partials that the stacked
+// GEMM's epilogue produced (gemm_dmma.cu), added in ascending column order => deterministic.
+__global__ void __launch_bounds__(256) combine_partials_kernel(int64_t mrows, int ngroups, const double* __restrict__ part,
+                                                               int64_t ldpart, int with_f, double* __restrict__ bsum,
+                                                               double* __restrict__ fsum) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mrows) return;
+    double b = 0.0, f = 0.0;
+    for (int q = 0; q < ngroups; ++q) {
+        b += part[(int64_t)(2 * q) * ldpart + i];
+        if (with_f) f += part[(int64_t)(2 * q + 1) * ldpart + i];
+    }
+    bsum[i] = b;
+    if (with_f) fsum[i] = f;
 }
 
 // Sequential scan over the cnt powers of one stack block, one thread per row of interest.
@@ -315,15 +334,26 @@ double* dvec_alloc(Ctx* ctx, int64_t len, const double* host) {
     return p;
 }
 
-int64_t choose_block(int64_t n, int64_t Rp, int64_t N, int64_t m) {
-    // enough stacked rows for ~6 waves of 128x128 tiles on 148 SMs, capped by N-1, 1024 and ~24 GB of stacks
-    const int64_t want_tiles = 148 * 6;
-    const int64_t tiles_n = ceil_div(n + m + 1, 128);
-    int64_t s = 1;
-    while (s < 1024 && s < N - 1 && ceil_div(s * Rp, 128) * tiles_n < want_tiles) s *= 2;
+int64_t choose_block(int64_t n, int64_t Rp, int64_t N, int64_t m, int sms) {
+    // enough stacked rows for ~6 waves of 128-row tiles on the SMs, capped by N-1, 1024 and ~24 GB of stacks ...
+    const int64_t want_tiles = (int64_t)sms * 6;
+    const int64_t tiles_n = gemm_nt_col_groups(n + m + 1) / 4;
+    int64_t s0 = 1;
+    while (s0 < 1024 && s0 < N - 1 && ceil_div(s0 * Rp, 128) * tiles_n < want_tiles) s0 *= 2;
     const double bytes_per_block = 2.0 * (double)Rp * (double)round_up(n, 128) * 8.0;
-    while (s > 1 && bytes_per_block * (double)s > 24e9) s /= 2;
-    return s;
+    while (s0 > 1 && bytes_per_block * (double)s0 > 24e9) s0 /= 2;
+    if (s0 <= 2) return s0;
+    // ... then ANY depth in [s0, 2 s0] (not only powers of two): the persistent GEMM hands out equal tiles, so the launch
+    // takes ceil(tiles / SMs) waves -- pick the depth whose last wave is fullest and whose row padding is smallest
+    // (C3: s = 16 -> 1008 tiles = 6.8 waves, 97.3 % of the tile slots used; s = 49 -> 3088 tiles = 20.9 waves, 99.3 %)
+    int64_t best = s0;
+    double best_eff = 0.0;
+    for (int64_t s = s0; s <= 2 * s0 && s <= N - 1 && s <= 1024 && bytes_per_block * (double)s <= 24e9; ++s) {
+        const int64_t tiles = ceil_div(s * Rp, 128) * tiles_n;
+        const double eff = (double)(s * Rp) / 128.0 * (double)tiles_n / (double)(ceil_div(tiles, sms) * sms);
+        if (eff > best_eff + 1e-3) { best_eff = eff; best = s; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -382,12 +412,9 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
     try {
         P->ctx = ctx; P->n = n; P->m = m; P->nrows = nrows; P->N = N;
         P->Rp = round_up(nrows, 8);
-        P->s = N > 2 ? choose_block(n, P->Rp, N, m) : 1;
-        if (const char* e = getenv("REACH_BFFPSV18_BLOCK")) {       // diagnostics: powers per stacked GEMM, rounded down to a power of two
-            int64_t want = std::max(1, std::min(1024, atoi(e))), pw2 = 1;
-            while (pw2 * 2 <= want) pw2 *= 2;
-            if (N > 2) P->s = pw2;
-        }
+        P->s = N > 2 ? choose_block(n, P->Rp, N, m, ctx->sm_count) : 1;
+        if (const char* e = getenv("REACH_BFFPSV18_BLOCK"))         // diagnostics: powers per stacked GEMM (any depth >= 1)
+            if (N > 2) P->s = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(1024, N - 1), atoi(e)));
         const int64_t s = P->s;
         P->Phi = dmat_alloc(ctx, n, n);
         if (Phi) dmat_upload(ctx, P->Phi, Phi, ldphi);
@@ -411,6 +438,10 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
             if (s > 1) {
                 P->PowA = dmat_alloc(ctx, n, n);
                 P->PowB = dmat_alloc(ctx, n, n);
+                if (s & (s - 1)) {      // Phi^s of a depth that is not a power of two: product of the squares at its set bits
+                    P->AccA = dmat_alloc(ctx, n, n);
+                    P->AccB = dmat_alloc(ctx, n, n);
+                }
             }
             P->PowT = dmat_alloc(ctx, n, n);
             P->BtAug = dmat_alloc(ctx, n + m + 1, n);
@@ -425,6 +456,9 @@ BoxPlan* boxplan_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, c
                 P->bsum1 = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
                 P->fsum1 = dvec_alloc(ctx, s * P->Rp + 128, nullptr);
                 REACH_CUDA(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+                P->ngroups = gemm_nt_col_groups(n + m + 1);
+                P->ldpart = round_up(s * P->Rp, 16);
+                for (int b = 0; b < 2; ++b) P->part[b] = dvec_alloc(ctx, 2 * P->ngroups * P->ldpart, nullptr);
             }
         }
         REACH_CUDA(cudaStreamSynchronize(ctx->stream));   // host pointers are not retained past this call
@@ -440,9 +474,9 @@ void boxplan_destroy(BoxPlan* P) {
     // the blocks go back to the context's pool at once: neither stream of this plan may still be using them
     if (P->side) cudaStreamSynchronize(P->side);
     if (P->ctx) cudaStreamSynchronize(P->ctx->stream);
-    for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->E1, &P->MU})
+    for (DMat* d : {&P->Phi, &P->PowA, &P->PowB, &P->PowT, &P->AccA, &P->AccB, &P->BtAug, &P->BtSmall, &P->S[0], &P->S[1], &P->E, &P->E1, &P->MU})
         dmat_free(*d);
-    for (double* v : {P->bsum1, P->fsum1})
+    for (double* v : {P->bsum1, P->fsum1, P->part[0], P->part[1]})
         if (v) ctx_free(P->ctx, v);
     if (P->side) cudaStreamDestroy(P->side);
     for (cudaEvent_t e : P->sync_evs) cudaEventDestroy(e);
@@ -506,22 +540,55 @@ void boxplan_run(BoxPlan* P) {
         // side operand [δB | c0], transposed
         if (m > 0) transpose(ctx, n, m, P->MU.p, P->MU.ld, P->BtSmall.p, P->BtSmall.ld);
         transpose(ctx, n, 1, P->c0, n, P->BtSmall.p + m, P->BtSmall.ld);
-        // doubling: stack blocks [have, 2*have) = stack blocks [0, have) · Φ^have ;  Φ^{2 have} = Φ^have · Φ^have
+        // doubling: with the stack blocks [0, have) and Φ^have in hand, blocks [have, have + cnt) = blocks [0, cnt) · Φ^have with
+        // cnt = min(have, s - have); Φ^{2 have} = Φ^have · Φ^have.  Φ^s is the product of the squares at the set bits of s
+        // (for a power of two: the last square itself).
         const DMat* pow = &P->Phi;
         DMat* spare[2] = {&P->PowA, &P->PowB};
-        int sp = 0;
-        for (int64_t have = 1; have < s; have *= 2) {
-            transpose(ctx, n, n, pow->p, pow->ld, P->PowT.p, P->PowT.ld);
+        DMat* accb[2] = {&P->AccA, &P->AccB};
+        const DMat* acc = nullptr;
+        int sp = 0, ap = 0;
+        int64_t have = 1;
+        for (int level = 0; s > 1; ++level) {
+            const bool bit = ((s >> level) & 1) != 0, more = (s >> (level + 1)) != 0, grow = have < s;
+            if (grow || more || (bit && acc)) transpose(ctx, n, n, pow->p, pow->ld, P->PowT.p, P->PowT.ld);
             cudaEvent_t e0 = next_event(), e1 = next_event();
             REACH_CUDA(cudaEventRecord(e0, st));
-            gemm_nt(ctx, have * Rp, n, n, P->S[0].p, P->S[0].ld, P->PowT.p, P->PowT.ld, P->S[0].p + have * Rp, P->S[0].ld);
-            gemm_nt(ctx, n, n, n, pow->p, pow->ld, P->PowT.p, P->PowT.ld, spare[sp]->p, spare[sp]->ld);
+            if (grow) {
+                const int64_t cnt = std::min(have, s - have);
+                gemm_nt(ctx, cnt * Rp, n, n, P->S[0].p, P->S[0].ld, P->PowT.p, P->PowT.ld, P->S[0].p + have * Rp, P->S[0].ld);
+                P->gemm_launches++;
+                P->gemm_flops += 2.0 * (double)(cnt * nrows) * n * n;
+                have += cnt;
+            }
+            if (bit) {
+                if (!acc) {                 // lowest set bit: Φ^s starts as this square
+                    if (more) {
+                        REACH_CUDA(cudaMemcpyAsync(accb[ap]->p, pow->p, pow->bytes(), cudaMemcpyDeviceToDevice, st));
+                        acc = accb[ap];
+                        ap ^= 1;
+                    } else {
+                        acc = pow;          // s is a power of two: the last square is Φ^s
+                    }
+                } else {
+                    gemm_nt(ctx, n, n, n, acc->p, acc->ld, P->PowT.p, P->PowT.ld, accb[ap]->p, accb[ap]->ld);
+                    P->gemm_launches++;
+                    P->gemm_flops += 2.0 * (double)n * n * n;
+                    acc = accb[ap];
+                    ap ^= 1;
+                }
+            }
+            if (more) {
+                gemm_nt(ctx, n, n, n, pow->p, pow->ld, P->PowT.p, P->PowT.ld, spare[sp]->p, spare[sp]->ld);
+                P->gemm_launches++;
+                P->gemm_flops += 2.0 * (double)n * n * n;
+            }
             REACH_CUDA(cudaEventRecord(e1, st));
-            P->gemm_launches += 2;
-            P->gemm_flops += 2.0 * (double)(have * nrows) * n * n + 2.0 * (double)n * n * n;
+            if (!more) break;
             pow = spare[sp];
             sp ^= 1;
         }
+        if (s > 1) pow = acc;
         // B_aug^T = [Φ^s | δB | c0]^T
         transpose(ctx, n, n, pow->p, pow->ld, P->BtAug.p, P->BtAug.ld);
         if (m > 0) transpose(ctx, n, m, P->MU.p, P->MU.ld, P->BtAug.p + n, P->BtAug.ld);
@@ -530,9 +597,13 @@ void boxplan_run(BoxPlan* P) {
         const int64_t npow = N - 1;
         const int64_t nblocks = ceil_div(npow, s);
         int cur = 0;
-        // Overlap (plain box mode, more than one block): abs-row-sums of block b run beside GEMM b (both only read
-        // S[cur]); the scan of block b runs beside GEMM b+1.  E / bsum / fsum are double-buffered by block parity.
+        // Overlap (plain box mode, more than one block).  The weighted abs-row-sums |P_k| r0, |P_k| rψ of block b + 1 come out
+        // of the EPILOGUE of GEMM b (the accumulators of S' = S Phi^s are the entries of the next block's powers), as
+        // per-column-group partials that a tiny kernel adds up; only block 0 -- produced by the doubling prologue -- takes
+        // the streaming pass over its stack.  The scan of block b runs beside GEMM b + 1 on the side stream.  E, the
+        // partials and bsum / fsum are double-buffered by block parity.
         const bool overlap = !P->qmap && P->side != nullptr && nblocks > 1;
+        const bool fused = overlap && getenv("REACH_BFFPSV18_NO_FUSED_ABS") == nullptr;
         size_t sync_used = 0;
         auto sync_event = [&]() {
             if (sync_used == P->sync_evs.size()) {
@@ -557,7 +628,8 @@ void boxplan_run(BoxPlan* P) {
             double* fsum = par ? P->fsum1 : P->fsum;
             cudaStream_t ss = overlap ? P->side : st;
             if (overlap) {
-                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(st, evAbs[b - 1], 0));      // GEMM b overwrites the stack abs(b-1) read
+                // GEMM b overwrites the stack abs(b-1) read (unfused / block 0) and the partials combine(b-1) read (same parity as b+1) ...
+                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(st, evAbs[b - 1], 0));
                 if (b > 1) REACH_CUDA(cudaStreamWaitEvent(st, evScan[b - 2], 0));     // ... and the E buffer scan(b-2) read
             }
             cudaEvent_t e0 = next_event(), e1 = next_event();
@@ -565,6 +637,10 @@ void boxplan_run(BoxPlan* P) {
             if (!last) {
                 GemmEpilogue ep;
                 ep.C2 = Eb.p; ep.ldc2 = Eb.ld; ep.nsplit = n;
+                if (fused) {            // partials of block b + 1
+                    ep.w0 = P->r0; ep.w1 = m > 0 ? P->rpsi : nullptr;
+                    ep.part = P->part[(b + 1) & 1]; ep.ldpart = P->ldpart;
+                }
                 gemm_nt(ctx, s * Rp, n + m + 1, n, P->S[cur].p, P->S[cur].ld, P->BtAug.p, P->BtAug.ld, P->S[cur ^ 1].p,
                         P->S[cur ^ 1].ld, ep);
                 P->gemm_flops += 2.0 * (double)(s * nrows) * n * (double)(n + m + 1);
@@ -577,15 +653,20 @@ void boxplan_run(BoxPlan* P) {
             if (overlap) {
                 evG.push_back(sync_event());
                 REACH_CUDA(cudaEventRecord(evG[b], st));
-                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(ss, evG[b - 1], 0));        // S[cur] of this block is complete
+                if (b > 0) REACH_CUDA(cudaStreamWaitEvent(ss, evG[b - 1], 0));        // S[cur] / the partials of this block are complete
             }
-            const unsigned grid = (unsigned)ceil_div(cnt * Rp, 64);
-            if (m > 0)
-                abs_rowsums_kernel<true><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, P->rpsi,
-                                                               bsum, fsum);
-            else
-                abs_rowsums_kernel<false><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, nullptr,
-                                                                bsum, nullptr);
+            if (fused && b > 0) {
+                combine_partials_kernel<<<(unsigned)ceil_div(cnt * Rp, 256), 256, 0, ss>>>(cnt * Rp, (int)P->ngroups, P->part[b & 1],
+                                                                                          P->ldpart, m > 0 ? 1 : 0, bsum, fsum);
+            } else {
+                const unsigned grid = (unsigned)ceil_div(cnt * Rp, 64);
+                if (m > 0)
+                    abs_rowsums_kernel<true><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, P->rpsi,
+                                                                   bsum, fsum);
+                else
+                    abs_rowsums_kernel<false><<<grid, 256, 0, ss>>>(cnt * Rp, (int)n, P->S[cur].p, P->S[cur].ld, P->r0, nullptr,
+                                                                    bsum, nullptr);
+            }
             REACH_CUDA(cudaGetLastError());
             if (overlap) {
                 evAbs.push_back(sync_event());

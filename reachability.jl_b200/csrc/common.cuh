@@ -136,7 +136,17 @@ struct GemmEpilogue {
     double* C2 = nullptr;
     int64_t ldc2 = 0;
     int64_t nsplit = -1;
+    // gemm_nt only -- fused weighted abs-row-sums of the product's columns [0, nsplit) (the box radii |P_k| r0 and |P_k| rψ of
+    // BFFPSV18, reach_blocks.jl:191-193, 209-215, straight from the accumulators):
+    //   part[(2 q + w) * ldpart + row] = sum over the 8*WNT columns of column group q of |C[row, col]| * (w ? w1 : w0)[col],
+    // q = 0 .. gemm_nt_col_groups(N) - 1 in ascending column order; the caller adds the groups up in that order.
+    const double* w0 = nullptr;
+    const double* w1 = nullptr;     // may stay nullptr (only w0 sums are produced)
+    double* part = nullptr;
+    int64_t ldpart = 0;
 };
+// number of column groups gemm_nt produces partial abs-row-sums for (4 consumer warps per column tile)
+int64_t gemm_nt_col_groups(int64_t N);
 void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt,
              int64_t ldbt, double* C, int64_t ldc, const GemmEpilogue& ep = GemmEpilogue());
 // Y[n x Q] = P[n x K] * X[K x Q], all column-major; X and Y are generator matrices (columns contiguous, ld a

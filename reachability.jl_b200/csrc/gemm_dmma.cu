@@ -53,6 +53,10 @@ struct GemmParams {
     double* C2;      // columns >= nsplit are stored to C2[(col - nsplit) * ldc2 + row] (fused side products)
     int64_t ldc2;
     int nsplit;
+    const double* w0;   // fused weighted abs-row-sums (NT variant): see GemmEpilogue
+    const double* w1;
+    double* part;
+    int64_t ldpart;
     int* sched;      // sched[0] = dynamic tile counter, sched[1] = CTAs that finished fetching (both zero between launches)
 };
 
@@ -82,6 +86,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
     uint64_t* empty = full + STAGES;
     int* tile_ring = reinterpret_cast<int*>(empty + STAGES);   // tile id travelling with the first k-step of every tile
+    // fused abs-sum epilogue (NT variant): every consumer warp keeps the weights of ITS 8*WNT columns, [warp][w][column], fetched
+    // with cp.async at the start of the tile so that the epilogue finds them in shared memory without a CTA-wide barrier
+    double* wsm = reinterpret_cast<double*>(tile_ring + STAGES + (STAGES & 1));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -155,6 +162,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
             const int tile = tile_ring[it % STAGES];
             if (tile < 0) break;
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            if (!AKM && p.part) {
+                __syncwarp();                     // the previous tile's epilogue has read the warp's weights
+                if (lane < 8 * WNT) {
+                    const int col = tn * BN + wn * (8 * WNT) + lane;
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const double* wv = w ? p.w1 : p.w0;
+                        double* dst = wsm + (warp * 2 + w) * 32 + lane;
+                        if (wv != nullptr && col < p.nsplit)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(wv + col) : "memory");
+                        else
+                            *dst = 0.0;
+                    }
+                }
+            }
             double acc[8][WNT][2];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -211,6 +233,54 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const GemmParams 
                     }
                 }
             } else {
+            if (p.part) {
+                // Fused abs-sum epilogue: the warp holds a 64 x 8*WNT piece of P_k; every row's weighted abs-sum over these
+                // columns is a per-thread fma chain (ascending columns) followed by a butterfly over the quad.  One partial
+                // per (column group, row) leaves the SM instead of the 130 MB stack being re-read by a second kernel.
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();                     // this tile's weights (fetched by lanes 0 .. 8 WNT - 1) are visible to the warp
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    if ((w ? p.w1 : p.w0) == nullptr) continue;
+                    const double* wsrc = wsm + (warp * 2 + w) * 32 + 2 * t;
+                    double wc[WNT][2];
+#pragma unroll
+                    for (int j = 0; j < WNT; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(wsrc + j * 8);
+                        wc[j][0] = v.x; wc[j][1] = v.y;
+                    }
+                    double* pout = p.part + (int64_t)((tn * 4 + wn) * 2 + w) * p.ldpart;
+                    double sv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < WNT; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) sacc = fma(fabs(acc[i][j][e]), wc[j][e], sacc);
+                        sv[i] = sacc;
+                    }
+                    // reduce-scatter over the quad (6 shuffles instead of 16): lane t ends up with the sums of rows 2t, 2t+1
+                    double k4[4], k2[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double send = (t & 2) ? sv[k] : sv[4 + k];
+                        const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                        k4[k] = ((t & 2) ? sv[4 + k] : sv[k]) + recv;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double send = (t & 1) ? k4[k] : k4[2 + k];
+                        const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        k2[k] = ((t & 1) ? k4[2 + k] : k4[k]) + recv;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int row = row0 + (2 * t + k) * 8;
+                        if (row < p.M) pout[row] = k2[k];
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < WNT; ++j) {
 #pragma unroll
@@ -281,7 +351,7 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     constexpr int A_STAGE = AKM ? BM * BK : BK * PITCH_A;
     constexpr int B_STAGE = BK * (BN + 4) + (AKM ? 8 : 0);
     const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 2 * STAGES * sizeof(uint64_t) +
-                        STAGES * sizeof(int) + 1024;
+                        (STAGES + (STAGES & 1)) * sizeof(int) + CONSUMER_WARPS * 2 * 32 * sizeof(double) + 1024;
     static bool configured[64] = {false};      // function attributes are per device
     const int dev = ctx->device & 63;
     {
@@ -325,6 +395,19 @@ __global__ void transpose_kernel(int rows, int cols, const double* __restrict__ 
 
 }  // namespace
 
+// widest column tile (32 * WNT columns) that wastes the least padding
+static int nt_col_warp_tiles(int64_t N) {
+    int best = 4;
+    int64_t best_cols = round_up(N, 128);
+    for (int wnt = 3; wnt >= 2; --wnt) {
+        int64_t c = round_up(N, 32 * wnt);
+        if (c < best_cols) { best_cols = c; best = wnt; }
+    }
+    return best;
+}
+
+int64_t gemm_nt_col_groups(int64_t N) { return 4 * ceil_div(N, 32 * nt_col_warp_tiles(N)); }
+
 void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* Bt, int64_t ldbt,
              double* C, int64_t ldc, const GemmEpilogue& ep) {
     if (M <= 0 || N <= 0) return;
@@ -338,14 +421,10 @@ void gemm_nt(Ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t
     p.alpha = ep.alpha; p.diag = ep.diag;
     p.C2 = ep.C2; p.ldc2 = ep.ldc2;
     p.nsplit = (ep.C2 != nullptr && ep.nsplit >= 0) ? (int)ep.nsplit : (int)N;
+    p.w0 = ep.part ? ep.w0 : nullptr; p.w1 = ep.part ? ep.w1 : nullptr; p.part = ep.w0 ? ep.part : nullptr; p.ldpart = ep.ldpart;
+    REACH_REQUIRE(!p.part || (p.ldpart >= M && ep.alpha == 1.0), "gemm_nt: fused abs-row-sums need ldpart >= M and alpha == 1");
     p.tiles_m = (int)ceil_div(M, BM);
-    // widest column tile that wastes the least padding
-    int best = 4;
-    int64_t best_cols = round_up(N, 128);
-    for (int wnt = 3; wnt >= 2; --wnt) {
-        int64_t c = round_up(N, 32 * wnt);
-        if (c < best_cols) { best_cols = c; best = wnt; }
-    }
+    const int best = nt_col_warp_tiles(N);
     p.tiles_n = (int)ceil_div(N, 32 * best);
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof(dummy));
@@ -373,6 +452,7 @@ void gemm_left(Ctx* ctx, int64_t n, int64_t Q, int64_t K, const double* P, int64
     p.M = (int)Q; p.N = (int)n; p.ksteps = (int)ceil_div(K, BK);
     p.alpha = ep.alpha; p.diag = ep.diag;
     p.C2 = nullptr; p.ldc2 = 0; p.nsplit = (int)n;
+    p.w0 = p.w1 = nullptr; p.part = nullptr; p.ldpart = 0;
     p.tiles_m = (int)ceil_div(Q, BM);
     int best = 4;
     int64_t best_cols = round_up(n, 128);

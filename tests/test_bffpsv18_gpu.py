@@ -57,6 +57,35 @@ def test_random_systems_ragged_sizes(ctx, n, m, N):
     _check(ctx, _random_problem(100 + n, n, m), N)
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3, 5, 7, 12, 49, 64])
+@pytest.mark.parametrize("n,m,N", [(40, 2, 131), (130, 0, 101)])
+def test_any_stack_depth(ctx, n, m, N, depth, monkeypatch):
+    """The stacked power GEMM advances `depth` steps per launch; any depth works, not only powers of two (the first stack is
+    built by doubling with a partial last round, Phi^depth is the product of the squares at the set bits of depth), and with
+    more than one block the radii come out of the GEMM's fused abs-sum epilogue.  Same sets for every depth."""
+    monkeypatch.setenv("REACH_BFFPSV18_BLOCK", str(depth))
+    D = _random_problem(600 + n, n, m)
+    _check(ctx, D, N)
+    _check(ctx, D, N, rows=np.array([n - 1, 0, 3], dtype=np.int32))
+
+
+def test_fused_abs_sum_epilogue_equals_streaming_pass(ctx, monkeypatch):
+    """|P_k| r0 and |P_k| rpsi from the stacked GEMM's accumulators (fused epilogue, per-column-group partials) against the
+    separate streaming pass over the stack (REACH_BFFPSV18_NO_FUSED_ABS=1): same sets to rounding, each bit-reproducible."""
+    D = _random_problem(77, 200, 3)
+    N = 150
+    monkeypatch.setenv("REACH_BFFPSV18_BLOCK", "6")
+    Cf, Rf = _run(ctx, D, N)
+    Cf2, Rf2 = _run(ctx, D, N)
+    assert np.array_equal(Cf, Cf2) and np.array_equal(Rf, Rf2)
+    monkeypatch.setenv("REACH_BFFPSV18_NO_FUSED_ABS", "1")
+    Cu, Ru = _run(ctx, D, N)
+    assert np.array_equal(Cf, Cu)                      # centres never involve the abs-sums
+    assert_close(Rf, Ru, "radii: fused epilogue vs streaming pass")
+    Co, Ro = orc.bffpsv18_reach(D, N)
+    assert_close(Rf, Ro, "radii vs oracle")
+
+
 @pytest.mark.parametrize("N", [1, 2, 3])
 def test_tiny_step_counts(ctx, N):
     """N == 1 returns only X_1 = Xhat0[blocks] (reach.jl:87-90, reach_blocks.jl:152-158)."""
