@@ -36,6 +36,10 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# dram bytes (read + write) of the HBM-side GLGM06 kernels per flowpipe step at C2, from ncu --set full captures of one 64-step batch:
+# ell_left_score 340 MB + apply_r 452 MB + wbox_partial 38 MB + the small ones ~10 MB = 840 MB / 64 steps
+C2_REAL_BYTES_PER_STEP = 840.0e6 / 64
+C2_REAL_BYTES_SOURCE = "profiles/r01/ncu_glgm06_c2_v4_summary.txt"
 FP64_DMMA_PEAK_TFLOPS = 37.06   # measured on this pool's B200: tools/fp64_peak.cu -> profiles/r01/fp64_peak_b200.jsonl
 METRIC = "flowpipe steps/s (n=1006 BFFPSV18, n=270 GLGM06) at 1/2/4/8 B200 vs CPU"
 
@@ -125,6 +129,16 @@ def build_box_workload(name):
     D = orc.discretize_box(w.A, X0, w.delta, w.B, U, Phi=Phi, Phi2abs=P2)
     N = orc.n_steps_bffpsv18(w.T, w.delta)
     return w, D, N
+
+
+def box_workload_label(w, N):
+    """`config.workload` of a BFFPSV18 line -- the SAME string on the GPU arm and on the reference arm (`same_config`)."""
+    return (f"{w.name}: n={w.n}, m={w.m}, BFFPSV18 {len(w.partition)} blocks of dim {len(w.partition[0])}, delta={w.delta}, "
+            f"T={w.T}, N={N} reach sets")
+
+
+def zono_workload_label(w, N):
+    return f"{w.name}: n={w.n}, m={w.m}, GLGM06 max_order={w.max_order}, delta={w.delta}, T={w.T}, N={N} reach sets"
 
 
 def shard_rows(n, partition, rank, world):
@@ -261,9 +275,10 @@ def run_bffpsv18(args, rank, world, dist):
         plan.close()
         ctx.close()
     lazy_obj = None
-    if big and rank == 0 and world == 1:
+    rider = getattr(args, "rider", False)
+    if big and rank == 0 and world == 1 and not rider:
         lazy_obj = run_c4_lazy(w, dev, N)
-    if big and rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if big and rank == 0 and world == 1 and not args.no_cpu_baseline and not rider:
         args._c4_cpu = cpu_baseline_c4(w, D, N)
     if rank != 0:
         return None
@@ -275,8 +290,7 @@ def run_bffpsv18(args, rank, world, dist):
         "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: n={n}, m={m}, BFFPSV18 {len(w.partition)} blocks of dim "
-                               f"{len(w.partition[0])}, delta={w.delta}, T={w.T}, N={N} reach sets per bench step",
+        "config": {"workload": box_workload_label(w, N), "bench_step": "one complete flowpipe (all N reach sets)",
                    "rows_per_gpu": R, "parallelism": f"row-block sharding x{world}, Phi replicated" if world > 1 else "single GPU",
                    "l2": "256 MB L2 flush between timed iterations; " + ("Phi (953 MB) and the power stacks exceed L2" if big else
                                                                          "power stacks 2 x 132 MB exceed L2"),
@@ -525,18 +539,24 @@ def run_glgm06(args, rank, world, dist, e2e=True):
     red_s = tt["reduce_ms"] * 1e-3
     gemm_tf = tt["gemm_flops"] / (tt["gemm_ms"] * 1e-3) / 1e12 if tt["gemm_ms"] else None
     nbatches = int(tt["gemm_launches"])
-    numerics = {"kernel": "batched numerics of the two Girard reductions (wbox_partial, wseq, rank_r, apply_r, finalize_r, "
-                          "expand_diag; TMA-staged gather), side stream, in situ",
-                "bound": "hbm", "achieved": alg_bytes / red_s / 1e9 if red_s > 0 else None, "peak": hbm, "unit": "GB/s",
-                "frac": alg_bytes / red_s / 1e9 / hbm if red_s > 0 else None, "peak_source": hbm_src,
-                "kernel_ms_total": tt["reduce_ms"],
-                "algorithmic_bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
-                # dram bytes of the dominant numerics kernel, one 64-step launch of apply_r_kernel<8> (ncu --set full,
-                # profiles/r01/ncu_session4_kernels_summary.txt): 163.9 MB read + 288.8 MB written
-                "traffic": 452.7e6,
-                "note": "achieved counts SURVEY 8(d)'s ALGORITHMIC bytes (40.9 MB per step: score pass + gather pass + write of both "
-                        "reductions); the archive/reference design moves about a third of that (W is never rewritten, scores travel "
-                        "with the references, box generators are tags), so frac can exceed 1"}
+    # REAL traffic of the HBM-side kernels (generator map + scores + the batched numerics), dram__bytes_read.sum +
+    # dram__bytes_write.sum per 64-step batch from the `ncu --set full` captures (C2_REAL_BYTES_PER_STEP below), against the time
+    # those kernels take ALONE (the serialised diagnostics pass): in the pipelined run they overlap each other and the chain.
+    real_bytes = C2_REAL_BYTES_PER_STEP * flow_steps
+    hbm_side_ms = alone["gemm_ms"] + alone["numerics_ms"] if map_info["sparse_levels"] > 0 else alone["numerics_ms"]
+    real_gbs = real_bytes / (hbm_side_ms * 1e-3) / 1e9 if hbm_side_ms > 0 else None
+    numerics = {"kernel": "HBM-side kernels of a flowpipe: generator map fused with the Girard scores (ell_left_score) + batched numerics "
+                          "of the two reductions (wbox_partial, wseq, rank_r, apply_r [TMA-staged gather], finalize_r, expand_diag)",
+                "bound": "hbm", "achieved": real_gbs, "peak": hbm, "unit": "GB/s",
+                "frac": real_gbs / hbm if real_gbs else None, "peak_source": hbm_src,
+                "traffic": C2_REAL_BYTES_PER_STEP * 64, "traffic_unit": "bytes per 64-step batch (ncu dram read + write, " + C2_REAL_BYTES_SOURCE + ")",
+                "kernel_ms_alone": hbm_side_ms, "kernel_ms_total": tt["reduce_ms"],
+                "algorithmic": {"bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
+                                "gbs_by_survey_8d_bytes": alg_bytes / red_s / 1e9 if red_s > 0 else None,
+                                "note": "SURVEY 8(d) counts 40.9 MB per step (score pass + gather pass + write of both reductions); the "
+                                        "archive/reference design moves about a third of that (W is never rewritten, scores travel with "
+                                        "the references, box generators are tags) -- an algorithmic saving, not bandwidth"},
+                "note": "the flowpipe is NOT HBM-bound end to end: the selection chain (one CTA) is the critical path, see selection_chain"}
     chain = {"kernel": "chain_kernel (one persistent CTA on its own SM, key logic only)", "kernel_ms_total": tt["chain_ms"],
              "us_per_flowpipe_step": 1e3 * tt["chain_ms"] / (flow_steps * args.steps)}
     alone_obj = {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",
@@ -567,8 +587,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: n={n}, m={w.m}, GLGM06 max_order={r}, delta={w.delta}, T={w.T}, N={N} reach sets per "
-                               f"bench step, p0={p0}, pV={pV}, {pmax} generators per reach set",
+        "config": {"workload": zono_workload_label(w, N), "bench_step": "one complete flowpipe (all N reach sets)",
+                   "generators": f"p0={p0}, pV={pV}, {pmax} generators per reach set",
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (the column-sharded variant, sharding.run_sharded, "
                                                                      "exists but does not beat one GPU at n=270, DESIGN.md section 5)",
                    "l2": "256 MB L2 flush between timed iterations; the flowpipe written per iteration (11.7 GB) exceeds L2"},
@@ -596,6 +616,22 @@ def cpu_baseline_glgm06(target_s=12.0):
     return {"value": (n_cpu - 1) / t, "unit": "flowpipe steps/s", "cores": cpu_threads(), "kind": "port",
             "sample": f"first {n_cpu} of {N} reach sets of {w.name} (loop only, Omega0/V/Phi supplied), numpy+BLAS oracle port of "
                       "reach_inhomog! + reduce_order", "host_cpus": os.cpu_count()}
+
+
+def cpu_baseline_ensemble(w, cs, rs, N, members=24):
+    """C5 on the host: the oracle port of reach_homog! (GLGM06/reach.jl:5-24), one member after the other like the reference's
+    `solve` per split (single task; the 28 x 28 products are too small for BLAS threads to matter)."""
+    from oracle import reach_oracle as orc
+    Phi = orc.exp_Adelta(w.A, w.delta)
+    P2 = orc.Phi2(np.abs(w.A), w.delta)
+    zs = [orc.discretize_zonotope(w.A, orc.Box(cs[:, b], rs[:, b]), w.delta, rzg=False, Phi=Phi, Phi2abs=P2).Omega0 for b in range(members)]
+    t0 = time.perf_counter()
+    for z in zs:
+        orc.glgm06_reach_homog(z, Phi, N, rzg=False)
+    t = time.perf_counter() - t0
+    return {"value": members * (N - 1) / t, "unit": "ensemble member flowpipe steps/s", "cores": 1, "kind": "port",
+            "sample": f"{members} of the 4096 members, all {N} reach sets each (loop only, Omega0 and Phi supplied), numpy oracle port of "
+                      "reach_homog!, one member after the other like solve() per split", "host_cpus": os.cpu_count()}
 
 
 def run_ensemble(args, rank, world, dist):
@@ -655,13 +691,42 @@ def run_ensemble(args, rank, world, dist):
         lo, hi = ens.boxes(N)
         assert np.all(np.isfinite(lo)) and np.all(hi >= lo)
         ens.close()
+        # ---- end to end: the members' Omega0 from pinned host memory, the flowpipe, and the box hull of every member at every
+        #      step back in pinned host memory (the zonotopes themselves -- 19.7 GB per GPU -- stay in HBM)
+        e2e_obj = None
+        if not args.no_e2e:
+            hc0 = pinned((n, per_gpu)); hc0[:] = c0s
+            hG0 = pinned((n, p, per_gpu)); hG0[:] = G0s
+            hPhi = pinned((n, n)); hPhi[:] = Phi
+            hlo = pinned((n, per_gpu, N)); hhi = pinned((n, per_gpu, N))
+
+            def one_e2e():
+                e2 = ctx.ensemble(hPhi, hc0, hG0, N)
+                e2.run()
+                e2.boxes_all(hlo, hhi)
+                e2.close()
+
+            one_e2e()
+            e2e_steps = max(1, min(args.steps, 3))
+            _barrier(dist, world)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                one_e2e()
+            torch.cuda.synchronize()
+            e2e_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
+            e2e_obj = {"value": e2e_steps * (N - 1) * total / e2e_s, "unit": "ensemble member flowpipe steps/s",
+                       "h2d_bytes_per_step": 8 * (n * n + n * per_gpu * (p + 1)), "d2h_bytes_per_step": 16 * n * per_gpu * N,
+                       "steps": e2e_steps, "api": "reach_ensemble_create + reach_ensemble_run + reach_ensemble_boxes_all (pinned host "
+                       "buffers; box hull of every member at every step copied back)"}
         ctx.close()
     if rank != 0:
         return None
     hbm, hbm_src = _peaks()
     steps = N - 1
     bytes_per_step = 16.0 * n * (p + 1) * per_gpu                         # read + write of one ensemble step
-    achieved = bytes_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e9
+    real_bytes_per_step = 8.0 * n * (p + 1) * per_gpu                     # what the one-launch kernel moves: every slot is written once
+    achieved = real_bytes_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e9
     return {
         "metric": METRIC, "value": args.steps * steps * total / (ms * 1e-3), "unit": "ensemble member flowpipe steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -670,13 +735,66 @@ def run_ensemble(args, rank, world, dist):
                                f"homogeneous GLGM06, delta={w.delta}, N={N} reach sets per bench step",
                    "parallelism": f"members sharded x{world}, Phi replicated, no collective",
                    "l2": "256 MB L2 flush between timed iterations; the ensemble flowpipe (19.7 GB per GPU) exceeds L2"},
-        "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                     "kernel": "homog_small_dmma_kernel<4,7> (whole flowpipe in one launch; real traffic = the writes, half of the "
-                               "algorithmic read+write figure)", "launches": args.steps, "kernel_ms_total": kern_ms,
+        "e2e": e2e_obj, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": real_bytes_per_step * steps,
+                     "kernel": "homog_small_dmma_kernel<4,7> (whole flowpipe in one launch: every slot is written once and never "
+                               "re-read, so the REAL traffic is the writes -- that is what `achieved` counts)",
+                     "launches": args.steps, "kernel_ms_total": kern_ms,
                      "kernel_share_of_step": kern_ms / ms, "peak_source": hbm_src,
-                     "algorithmic_bytes_per_ensemble_step": bytes_per_step},
+                     "algorithmic_bytes_per_ensemble_step": bytes_per_step,
+                     "algorithmic_note": "SURVEY 8(d) counts read + write of every step (2x the real traffic): by that figure the "
+                                         "kernel moves %.0f GB/s" % (2 * achieved)},
+        **({} if getattr(args, "rider", False) or args.no_cpu_baseline or world > 1 else {"cpu_baseline": cpu_baseline_ensemble(w, wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])[0], wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])[1], N)}),
     }
+
+
+def c2_flat_scalars(c2):
+    """The C2 numbers as flat scalars for the end of the JSON line."""
+    roof = c2.get("roofline") or {}
+    chain = roof.get("selection_chain") or {}
+    dense = c2.get("dense_gemm_path") or {}
+    out = {"c2_value": c2.get("value"), "c2_unit": "flowpipe steps/s (n=270 GLGM06, N=2000)",
+           "c2_e2e": (c2.get("e2e") or {}).get("value"), "c2_e2e_projected": ((c2.get("e2e") or {}).get("projected") or {}).get("value"),
+           "c2_chain_us_per_step": chain.get("us_per_flowpipe_step"), "c2_real_hbm_frac": roof.get("frac"),
+           "c2_dense_value": dense.get("value"), "c2_dense_frac": (dense.get("roofline") or {}).get("frac"),
+           "c2_cpu_value": (c2.get("cpu_baseline") or {}).get("value")}
+    return {k: v for k, v in out.items() if v is not None}
+
+
+def run_inprocess_multi(rank, world, dist):
+    """Rider under --gpus N: ONE process (rank 0) drives all N GPUs through a multi-device context (reach_ctx_create_multi) and
+    the one-shot host-buffer call reach_bffpsv18_boxes -- what a single Julia task gets through one `ccall`.  The other ranks
+    wait at a barrier with their GPUs idle."""
+    import torch
+    import math
+    import reachability_jl_b200 as rb
+    from reachability_jl_b200 import workloads as wl
+    out = None
+    _barrier(dist, world)
+    if rank == 0:
+        w = wl.fom()
+        N = int(math.ceil(w.T / w.delta))
+        n, m = w.n, w.m
+        with rb.Context(list(range(world))) as ctx:
+            D = ctx.discretize_box(w.A, w.delta, w.c, w.r, w.B, w.cU, w.rU)
+            hPhi = pinned((n, n)); hPhi[:] = D["Phi"]
+            hMU = pinned((n, m)); hMU[:] = D["MU"]
+            hc = pinned((n, N)); hr = pinned((n, N))
+            rows = np.arange(n, dtype=np.int32)
+            call = lambda: ctx.bffpsv18_boxes_into(hPhi, D["c0"], D["r0"], N, hMU, D["cU"], D["rU"], D["rpsi"], rows, hc, hr)
+            call()
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                call()
+            dt = time.perf_counter() - t0
+        out = {"value": reps * (N - 1) / dt, "unit": "flowpipe steps/s", "devices": world, "steps": reps,
+               "api": "reach_ctx_create_multi + reach_bffpsv18_boxes: one process, one handle, rows sharded over the devices inside "
+                      "the library (host threads, no collective), pinned host buffers in and out",
+               "h2d_bytes_per_step": world * 8 * (n * n + n * m + 3 * n + 2 * m), "d2h_bytes_per_step": 16 * n * N}
+    _barrier(dist, world)
+    return out
 
 
 def _as_tensor(ptr, count, dev):
@@ -765,8 +883,7 @@ def run_reference_glgm06(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: n={w.n}, m={w.m}, GLGM06 max_order={w.max_order}, delta={w.delta}, T={w.T}, N={N}",
-                   "sample": sample},
+        "config": {"workload": zono_workload_label(w, N), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "flowpipe steps/s", "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "flowpipe steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -798,7 +915,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "flowpipe steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: n={w.n}, m={w.m}, BFFPSV18, delta={w.delta}, T={w.T}, N={N}", "sample": sample},
+        "config": {"workload": box_workload_label(w, N), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "flowpipe steps/s", "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "flowpipe steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -813,6 +930,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the second headline workload (C2 GLGM06) summary")
+    ap.add_argument("--no-riders", action="store_true", help="skip the C4 / C5 riders of the default line")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
@@ -838,18 +956,44 @@ def main():
         args.no_cpu_baseline = True
     else:
         out = run_bffpsv18(args, rank, world, dist)
+    flat = {}                       # flat scalars appended at the END of the line (they survive a truncated stdout tail)
+    primary_c3 = args.workload == "C3" and not args.flow_steps
+    if primary_c3 and not args.no_riders:
+        # ---- riders of the default line: the other configurations of BASELINE.json, each reduced to a few scalars ----------
+        # C4 (n = 10913, the configuration the 1 -> 8 GPU scaling target names): a truncated flowpipe of the same problem,
+        # all rows sharded like the main line; C5: the ensemble, members sharded (weak scaling)
+        r4 = run_bffpsv18(argparse.Namespace(**{**vars(args), "workload": "C4", "steps": 1, "warmup": 1, "flow_steps": 160,
+                                                "no_e2e": True, "no_cpu_baseline": True, "rider": True}), rank, world, dist)
+        r5 = run_ensemble(argparse.Namespace(**{**vars(args), "workload": "C5", "steps": 2, "warmup": 1, "flow_steps": 0,
+                                                "no_e2e": world > 1, "no_cpu_baseline": True, "rider": True}), rank, world, dist)
+        multi = run_inprocess_multi(rank, world, dist) if world > 1 else None
+        if out is not None:
+            out["riders"] = {"c4_mna5": {k: r4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling")},
+                             "c5_ensemble": {k: r5[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling", "e2e")}}
+            flat.update(c4_value=r4["value"], c4_unit="flowpipe steps/s (n=10913, first 160 reach sets, all rows)",
+                        c4_frac=r4["roofline"]["frac"], c5_value=r5["value"], c5_unit=r5["unit"],
+                        c5_real_hbm_frac=r5["roofline"]["frac"])
+            if r5.get("e2e"):
+                flat["c5_e2e"] = r5["e2e"]["value"]
+            if multi is not None:
+                out["riders"]["c3_one_process_multi_device"] = multi
+                flat["c3_one_process_multi_device_e2e"] = multi["value"]
     if out is not None:
         if args.flow_steps:
             out["config"]["truncated"] = f"PROFILING RUN: flowpipe truncated to {args.flow_steps} reach sets"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_glgm06() if args.workload == "C2" else cpu_baseline_for(args)
-        if world == 1 and args.workload == "C3" and not args.no_secondary and not args.flow_steps:
+        if world == 1 and primary_c3 and not args.no_secondary:
             # the metric names two configurations: the n=270 GLGM06 one rides along as a summary object
             sec = run_glgm06(args, rank, world, dist)
             keep = ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "gpu_launches", "generator_map", "dense_gemm_path")
             out["glgm06_c2"] = {k: sec[k] for k in keep if k in sec}
             if not args.no_cpu_baseline:
                 out["glgm06_c2"]["cpu_baseline"] = cpu_baseline_glgm06()
+            flat.update(c2_flat_scalars(out["glgm06_c2"]))
+        if args.workload == "C2":
+            flat.update(c2_flat_scalars(out))
+        out.update(flat)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -283,6 +283,8 @@ REACH_API int32_t reach_ensemble_run(reach_ensemble* e);
 REACH_API int32_t reach_ensemble_step(reach_ensemble* e, int64_t b, int64_t k, double* c, double* G);
 /* Box hull of every member at step k: lo/hi n x batch. */
 REACH_API int32_t reach_ensemble_boxes(reach_ensemble* e, int64_t k, double* lo, double* hi);
+/* Box hull of every member at EVERY step in one pass over the flowpipe: lo/hi n x batch x N (index i + n (b + batch (k-1))). */
+REACH_API int32_t reach_ensemble_boxes_all(reach_ensemble* e, double* lo, double* hi);
 REACH_API int32_t reach_ensemble_timing(reach_ensemble* e, double* run_ms, double* bytes_per_step);
 REACH_API void reach_ensemble_free(reach_ensemble* e);
 

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "reach_ensemble_run": [vp],
     "reach_ensemble_step": [vp, i64, i64, c_double_p, c_double_p],
     "reach_ensemble_boxes": [vp, i64, c_double_p, c_double_p],
+    "reach_ensemble_boxes_all": [vp, c_double_p, c_double_p],
     "reach_ensemble_timing": [vp, c_double_p, c_double_p],
     "reach_ensemble_free": [vp],
     "reach_dgemm_left": [vp, i64, i64, i64, c_double_p, i64, c_double_p, i64, c_double_p, i64, i32, c_double_p],

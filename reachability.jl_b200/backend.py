@@ -667,6 +667,15 @@ class Ensemble:
         self.ctx._check(self.ctx.lib.reach_ensemble_boxes(self._h, int(k), dptr(lo), dptr(hi)))
         return lo, hi
 
+    def boxes_all(self, lo=None, hi=None):
+        """Box hulls of every member at every step: (lo, hi), each (n, batch, N) Fortran arrays (caller-owned when given)."""
+        shape = (self.n, self.batch, self.N)
+        lo = np.zeros(shape, order="F") if lo is None else lo
+        hi = np.zeros(shape, order="F") if hi is None else hi
+        assert lo.shape == shape and hi.shape == shape and lo.flags.f_contiguous and hi.flags.f_contiguous
+        self.ctx._check(self.ctx.lib.reach_ensemble_boxes_all(self._h, dptr(lo), dptr(hi)))
+        return lo, hi
+
     def timing(self):
         a, b = C.c_double(), C.c_double()
         self.ctx._check(self.ctx.lib.reach_ensemble_timing(self._h, C.byref(a), C.byref(b)))

@@ -1134,6 +1134,32 @@ __global__ void __launch_bounds__(256) zono_box_kernel(int n, int ld, int p, int
     hi[(int64_t)b * n + i] = ci + s;
 }
 
+// Box hulls of EVERY member at EVERY step of an ensemble flowpipe in one pass (one warp per (member, step); lanes = rows, the
+// member's p generator columns are contiguous): lo / hi [i + n (b + batch (k - 1))].  Reads the flowpipe once.
+__global__ void __launch_bounds__(128) ensemble_boxes_all_kernel(int n, int ld, int p, int batch, int64_t N, int64_t q,
+                                                                 const double* __restrict__ Y, double* __restrict__ lo,
+                                                                 double* __restrict__ hi) {
+    const int64_t job = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (job >= (int64_t)batch * N) return;
+    const int64_t k = job / batch;
+    const int b = (int)(job - k * batch);
+    const double* slot = Y + k * q * ld;
+    const double* G = slot + (int64_t)b * p * ld;
+    const double* c = slot + ((int64_t)batch * p + b) * ld;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < n) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < p; ++j) s += fabs(G[(int64_t)j * ld + i]);
+            const double ci = c[i];
+            lo[(k * batch + b) * n + i] = ci - s;
+            hi[(k * batch + b) * n + i] = ci + s;
+        }
+    }
+}
+
 // ---- structurally sparse Phi: the generator map as a sparse product -------------------------------------------------------
 // Decoupled / block-diagonal systems (the ISS-shaped C2: 135 independent 2 x 2 modes) have a Phi = e^{A delta} with a handful of
 // non-zeros per row, and so have all its powers.  linear_map(Phi^w, Z) (GLGM06/reach.jl:16,48,54) is then an ELL sparse x
@@ -2716,6 +2742,27 @@ int32_t reach_ensemble_boxes(reach_ensemble* en, int64_t k, double* lo, double* 
     F->ctx->launches++;
     REACH_CUDA(cudaMemcpyAsync(lo, en->stage, cnt * 8, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaMemcpyAsync(hi, en->stage + cnt, cnt * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    return REACH_OK;
+    FP_END(en->ctx)
+}
+
+int32_t reach_ensemble_boxes_all(reach_ensemble* en, double* lo, double* hi) {
+    if (!en || !lo || !hi) return REACH_EINVAL;
+    FP_BEGIN(en->ctx)
+    Flowpipe* F = en->f;
+    require_ran(F);
+    cudaStream_t st = F->ctx->stream;
+    const size_t cnt = (size_t)F->n * en->batch * F->N;
+    DevScratch scr(F->ctx);
+    double* d = scr.get<double>(2 * cnt);
+    const int64_t jobs = en->batch * F->N;
+    ensemble_boxes_all_kernel<<<(unsigned)ceil_div(jobs * 32, 128), 128, 0, st>>>((int)F->n, (int)F->ld, (int)en->p, (int)en->batch,
+                                                                                 F->N, F->q, F->Hflow, d, d + cnt);
+    REACH_CUDA(cudaGetLastError());
+    F->ctx->launches++;
+    REACH_CUDA(cudaMemcpyAsync(lo, d, cnt * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaMemcpyAsync(hi, d + cnt, cnt * 8, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaStreamSynchronize(st));
     return REACH_OK;
     FP_END(en->ctx)

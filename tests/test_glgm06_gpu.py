@@ -220,6 +220,11 @@ def test_ensemble_homogeneous(ctx, n, p, batch, N):
         rad = np.abs(R[-1].G).sum(axis=1) if p else np.zeros(n)
         assert_close(lo[:, b], R[-1].c - rad, "lo")
         assert_close(hi[:, b], R[-1].c + rad, "hi")
+    # every member at every step in one pass (reach_ensemble_boxes_all): identical bits to the per-step query
+    LO, HI = ens.boxes_all()
+    for k in (1, 2, N):
+        lk, hk = ens.boxes(k)
+        assert np.array_equal(LO[:, :, k - 1], lk) and np.array_equal(HI[:, :, k - 1], hk)
     ens.close()
 
 
