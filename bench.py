@@ -726,6 +726,7 @@ def run_ensemble(args, rank, world, dist):
     steps = N - 1
     bytes_per_step = 16.0 * n * (p + 1) * per_gpu                         # read + write of one ensemble step
     real_bytes_per_step = 8.0 * n * (p + 1) * per_gpu                     # what the one-launch kernel moves: every slot is written once
+    flops_per_step = 2.0 * n * n * (p + 1) * per_gpu                      # 2 n^2 (p+1) batch
     achieved = real_bytes_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e9
     return {
         "metric": METRIC, "value": args.steps * steps * total / (ms * 1e-3), "unit": "ensemble member flowpipe steps/s",
@@ -736,15 +737,22 @@ def run_ensemble(args, rank, world, dist):
                    "parallelism": f"members sharded x{world}, Phi replicated, no collective",
                    "l2": "256 MB L2 flush between timed iterations; the ensemble flowpipe (19.7 GB per GPU) exceeds L2"},
         "e2e": e2e_obj, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+        # AI = 2 n^2 (p+1) flop / 8 n (p+1) B written = n / 4 = 7 flop/B against a machine balance of 37.06e12 / 6.55e12 = 5.7:
+        # the one-launch kernel is bound by the FP64 tensor pipe (DMMA m8n8k4: 28 rows occupy 32), not by HBM -- both are reported
+        "roofline": {"bound": "tensor", "achieved": flops_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e12,
+                     "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": flops_per_step * steps * args.steps / (kern_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
                      "traffic": real_bytes_per_step * steps,
-                     "kernel": "homog_small_dmma_kernel<4,7> (whole flowpipe in one launch: every slot is written once and never "
-                               "re-read, so the REAL traffic is the writes -- that is what `achieved` counts)",
-                     "launches": args.steps, "kernel_ms_total": kern_ms,
-                     "kernel_share_of_step": kern_ms / ms, "peak_source": hbm_src,
-                     "algorithmic_bytes_per_ensemble_step": bytes_per_step,
-                     "algorithmic_note": "SURVEY 8(d) counts read + write of every step (2x the real traffic): by that figure the "
-                                         "kernel moves %.0f GB/s" % (2 * achieved)},
+                     "kernel": "homog_small_dmma_kernel<4,7,NT> (whole flowpipe in ONE launch: Phi as DMMA A fragments in shared memory, "
+                               "one CTA per SM with 19 warps, every slot written once by a bulk copy shared -> global and never re-read)",
+                     "launches": args.steps, "kernel_ms_total": kern_ms, "kernel_share_of_step": kern_ms / ms,
+                     "algorithmic_flops_per_ensemble_step": flops_per_step,
+                     "executed_frac_with_m8_padding": flops_per_step * (32.0 / 28.0 if n == 28 else 1.0) * steps * args.steps / (kern_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                     "peak_source": "FP64 DMMA register-resident loop measured on this pool's B200 (profiles/r01/fp64_peak_b200.jsonl)",
+                     "hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": hbm_src,
+                             "note": "REAL traffic = the writes (8 n (p+1) B per member and step; nothing is re-read); SURVEY 8(d)'s "
+                                     "algorithmic read + write figure is twice that",
+                             "algorithmic_bytes_per_ensemble_step": bytes_per_step}},
         **({} if getattr(args, "rider", False) or args.no_cpu_baseline or world > 1 else {"cpu_baseline": cpu_baseline_ensemble(w, wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])[0], wl.split_box(w.c, w.r, [4, 4, 4, 4, 2, 2, 2, 2])[1], N)}),
     }
 
@@ -771,7 +779,12 @@ def run_inprocess_multi(rank, world, dist):
     import reachability_jl_b200 as rb
     from reachability_jl_b200 import workloads as wl
     out = None
-    _barrier(dist, world)
+    # the waiting ranks must leave their GPUs IDLE: an NCCL barrier is a kernel that spins on the device, and rank 0's work on
+    # that device would be time-sliced against it (two processes on one GPU) -- so this rider synchronises on the host (gloo)
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    host_group = dist.new_group(backend="gloo")
+    torch.cuda.synchronize()
+    dist.barrier(group=host_group)
     if rank == 0:
         w = wl.fom()
         N = int(math.ceil(w.T / w.delta))
@@ -793,7 +806,7 @@ def run_inprocess_multi(rank, world, dist):
                "api": "reach_ctx_create_multi + reach_bffpsv18_boxes: one process, one handle, rows sharded over the devices inside "
                       "the library (host threads, no collective), pinned host buffers in and out",
                "h2d_bytes_per_step": world * 8 * (n * n + n * m + 3 * n + 2 * m), "d2h_bytes_per_step": 16 * n * N}
-    _barrier(dist, world)
+    dist.barrier(group=host_group)
     return out
 
 
@@ -972,7 +985,7 @@ def main():
                              "c5_ensemble": {k: r5[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling", "e2e")}}
             flat.update(c4_value=r4["value"], c4_unit="flowpipe steps/s (n=10913, first 160 reach sets, all rows)",
                         c4_frac=r4["roofline"]["frac"], c5_value=r5["value"], c5_unit=r5["unit"],
-                        c5_real_hbm_frac=r5["roofline"]["frac"])
+                        c5_dmma_frac=r5["roofline"]["frac"], c5_real_hbm_frac=r5["roofline"]["hbm"]["frac"])
             if r5.get("e2e"):
                 flat["c5_e2e"] = r5["e2e"]["value"]
             if multi is not None:

@@ -1392,65 +1392,105 @@ __device__ __forceinline__ void dmma884_acc(double& c0, double& c1, double a, do
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int MT, int KT>
-__global__ void __launch_bounds__(128) homog_small_dmma_kernel(const double* __restrict__ Phi, int ldphi, int n, int ld, int64_t q,
-                                                               int64_t nsteps, double* __restrict__ Y) {
-    constexpr int P = 36;
-    __shared__ double tile[4][32 * P];
+// pitch (doubles) of a column in the shared-memory tiles: the smallest P >= ld with P mod 16 in {4, 12}, which makes both the
+// B-fragment loads (slot 12 g + t) and the accumulator stores (slot 8 t + g) conflict-free; P == ld (C5: 28) lets the
+// whole tile leave with ONE bulk copy
+static int homog_pitch(int ld, int kt) {
+    int P = std::max(ld, 4 * kt);       // a B fragment reads k = 0 .. 4 KT - 1 of its column: they must stay inside the column
+    while ((P & 15) != 4 && (P & 15) != 12) P += 2;
+    return P;
+}
+
+// MT x KT: m8 / k4 tiles covering the n x n matrix; NT: n8 column tiles per warp (a warp owns 8 NT consecutive columns).
+// Per step and warp: KT x NT fragment loads from the current tile, MT x NT x KT DMMAs, the accumulators go to the OTHER tile
+// of the warp's pair, and that tile leaves as a bulk copy shared -> global (TMA engine, SASS UBLKCP.G.S) issued by one lane --
+// no per-thread store instructions, no index arithmetic, and the next step's DMMAs start while the copy drains.
+__device__ __forceinline__ void dmma884_first(double& c0, double& c1, double a, double b) {       // D = A B (C = 0)
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// The kernel is bound by the DMMA pipe of each SM, not by HBM (AI = 7 flop/B against a machine balance of 5.7), so the SMs
+// must carry EQUAL work and every scheduler needs several warps to keep the pipe fed across the per-step epilogue: one CTA per
+// SM with W warps of 8 NT columns each, (W, NT) chosen on the host so that one wave of CTAs covers all columns with the least
+// slack (C5 on one GPU: 145 CTAs x 19 warps x 16 columns).  Phi lives in shared memory as m8n8k4 A fragments (pitch 36:
+// conflict-free), which keeps the kernel under 107 registers -- 19 warps per SM.  The warps never synchronise after the prologue.
+constexpr int HOMOG_PA = 36;
+template <int MT, int KT, int NT>
+__global__ void __launch_bounds__(640, 1) homog_small_dmma_kernel(const double* __restrict__ Phi, int ldphi, int n, int ld, int64_t q,
+                                                                  int64_t nsteps, double* __restrict__ Y, int P) {
+    extern __shared__ __align__(128) double hsm[];
+    constexpr int NC = 8 * NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int64_t col0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;
-    if (col0 >= q) return;
-    const int ncol = (int)min((int64_t)32, q - col0);
-    const int chunk = ncol * ld;
-    double* tr = tile[warp];
-    double a[MT][KT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-            const int row = 8 * mt + g, k = 4 * kt + t;
-            a[mt][kt] = (row < n && k < n) ? Phi[row + (int64_t)k * ldphi] : 0.0;
-        }
-    for (int idx = lane; idx < 32 * P; idx += 32) tr[idx] = 0.0;
+    double* const As = hsm;                                         // As[k * HOMOG_PA + row], 4 KT x 8 MT, zero-padded
+    for (int idx = threadIdx.x; idx < 4 * KT * HOMOG_PA; idx += blockDim.x) {
+        const int k = idx / HOMOG_PA, row = idx - k * HOMOG_PA;
+        As[idx] = (row < n && k < n) ? Phi[row + (int64_t)k * ldphi] : 0.0;
+    }
+    __syncthreads();
+    const int64_t col0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * NC;
+    if (col0 >= q) return;                                    // whole warps leave; nothing below synchronises the CTA
+    const int ncol = (int)min((int64_t)NC, q - col0);
+    double* const tiles = hsm + 4 * KT * HOMOG_PA + (size_t)(warp * 2) * NC * P;    // the warp's pair of tiles, NC * P doubles each
+    const int tile_doubles = NC * P;
+    const bool compact = (P == ld);
+    for (int idx = lane; idx < 2 * tile_doubles; idx += 32) tiles[idx] = 0.0;
     __syncwarp();
     {
         const double* src = Y + col0 * ld;
-        for (int idx = lane; idx < chunk; idx += 32) {
-            const int c = idx / ld, i = idx - c * ld;
-            if (i < n) tr[c * P + i] = src[idx];
-        }
+        for (int c = 0; c < ncol; ++c)
+            for (int i = lane; i < n; i += 32) tiles[c * P + i] = src[(int64_t)c * ld + i];
     }
     __syncwarp();
+    const double* const afrag = As + t * HOMOG_PA + g;
+    int cur = 0;
     for (int64_t step = 1; step <= nsteps; ++step) {
-        double d[MT][4][2];
+        const double* tin = tiles + cur * tile_doubles + g * P + t;
+        double* tout = tiles + (cur ^ 1) * tile_doubles;
+        double d[MT][NT][2];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int kt = 0; kt < KT; ++kt) {
+            double av[MT], bv[NT];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) d[mt][nt][0] = d[mt][nt][1] = 0.0;
+            for (int mt = 0; mt < MT; ++mt) av[mt] = afrag[4 * kt * HOMOG_PA + 8 * mt];
 #pragma unroll
-        for (int kt = 0; kt < KT; ++kt)
+            for (int nt = 0; nt < NT; ++nt) bv[nt] = tin[8 * nt * P + 4 * kt];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const double b = tr[(8 * nt + g) * P + 4 * kt + t];
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) dmma884_acc(d[mt][nt][0], d[mt][nt][1], a[mt][kt], b);
-            }
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (kt == 0) dmma884_first(d[mt][nt][0], d[mt][nt][1], av[mt], bv[nt]);
+                    else dmma884_acc(d[mt][nt][0], d[mt][nt][1], av[mt], bv[nt]);
+                }
+        }
+        // the bulk copy that left `tout` two steps ago has finished reading it (at most the previous step's copy is pending)
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = 8 * mt + g;
+            if (row < n) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                tr[(8 * nt + 2 * t) * P + 8 * mt + g] = d[mt][nt][0];
-                tr[(8 * nt + 2 * t + 1) * P + 8 * mt + g] = d[mt][nt][1];
+                for (int nt = 0; nt < NT; ++nt) {
+                    tout[(8 * nt + 2 * t) * P + row] = d[mt][nt][0];
+                    tout[(8 * nt + 2 * t + 1) * P + row] = d[mt][nt][1];
+                }
             }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes before the async-proxy read
         __syncwarp();
         double* dst = Y + (step * q + col0) * ld;
-        for (int idx = lane; idx < chunk; idx += 32) {
-            const int c = idx / ld, i = idx - c * ld;
-            dst[idx] = i < n ? tr[c * P + i] : 0.0;
+        if (compact) {
+            if (lane == 0) {
+                bulk_s2g(dst, tout, (uint32_t)(ncol * ld * 8));
+                bulk_commit();
+            }
+        } else if (lane < ncol) {
+            bulk_s2g(dst + (int64_t)lane * ld, tout + lane * P, (uint32_t)(ld * 8));
+            bulk_commit();
         }
-        __syncwarp();
+        cur ^= 1;
     }
+    bulk_wait0();
 }
 
 template <typename T>
@@ -1975,15 +2015,42 @@ void flowpipe_run(Flowpipe* F) {
     F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
     if (F->homog && !F->phi_host.empty() && N > 1) {
         const int nn = (int)n;
-        const unsigned grid = (unsigned)ceil_div(q, 128);
+        const int P = homog_pitch((int)ld, nn <= 8 ? 2 : nn <= 16 ? 4 : nn <= 24 ? 6 : nn <= 28 ? 7 : 8);
+        // (W warps per CTA, NT column tiles per warp): the fewest waves of one-CTA-per-SM, then the least slack in the last wave,
+        // then the most warps (latency hiding).  Budget: 65536 registers per SM at <= 107 per thread -> up to 19 warps.
+        const int kt_tiles = nn <= 8 ? 2 : nn <= 16 ? 4 : nn <= 24 ? 6 : nn <= 28 ? 7 : 8;
+        const size_t a_bytes = (size_t)4 * kt_tiles * HOMOG_PA * sizeof(double);
+        int bestW = 4, nt = 1;
+        double best_cost = 1e300;
+        for (int cand_nt = 1; cand_nt <= 4; ++cand_nt)
+            for (int W = 4; W <= 20; ++W) {          // __launch_bounds__(640): at most 20 warps, <= 102 registers
+                if (a_bytes + (size_t)W * 2 * 8 * cand_nt * P * sizeof(double) > 200 * 1024) continue;
+                const int64_t ctas = ceil_div(q, (int64_t)W * 8 * cand_nt);
+                const int64_t waves = ceil_div(ctas, ctx->sm_count);
+                const double cost = (double)waves * W * cand_nt + 1e-2 * waves - 1e-3 * W - 1e-4 * cand_nt;
+                if (cost < best_cost) { best_cost = cost; bestW = W; nt = cand_nt; }
+            }
+        const unsigned grid = (unsigned)ceil_div(q, (int64_t)bestW * 8 * nt), block = (unsigned)bestW * 32;
+        const size_t smem = a_bytes + (size_t)bestW * 2 * 8 * nt * P * sizeof(double);
+#define REACH_HOMOG_LAUNCH(MT, KT, NT)                                                                                          \
+    do {                                                                                                                       \
+        REACH_CUDA(cudaFuncSetAttribute(homog_small_dmma_kernel<MT, KT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        homog_small_dmma_kernel<MT, KT, NT><<<grid, block, smem, st>>>(F->Phi.p, (int)F->Phi.ld, nn, (int)ld, q, N - 1, F->Hflow, P); \
+    } while (0)
 #define REACH_HOMOG_DMMA(MT, KT)                                                                                               \
-    homog_small_dmma_kernel<MT, KT><<<grid, 128, 0, st>>>(F->Phi.p, (int)F->Phi.ld, nn, (int)ld, q, N - 1, F->Hflow)
+    do {                                                                                                                       \
+        if (nt == 4) REACH_HOMOG_LAUNCH(MT, KT, 4);                                                                            \
+        else if (nt == 3) REACH_HOMOG_LAUNCH(MT, KT, 3);                                                                       \
+        else if (nt == 2) REACH_HOMOG_LAUNCH(MT, KT, 2);                                                                       \
+        else REACH_HOMOG_LAUNCH(MT, KT, 1);                                                                                    \
+    } while (0)
         if (nn <= 8) REACH_HOMOG_DMMA(1, 2);
         else if (nn <= 16) REACH_HOMOG_DMMA(2, 4);
         else if (nn <= 24) REACH_HOMOG_DMMA(3, 6);
         else if (nn <= 28) REACH_HOMOG_DMMA(4, 7);
         else REACH_HOMOG_DMMA(4, 8);
 #undef REACH_HOMOG_DMMA
+#undef REACH_HOMOG_LAUNCH
         REACH_CUDA(cudaGetLastError());
         ctx->launches++;
         REACH_CUDA(cudaEventRecord(ctx->ev1, st));
