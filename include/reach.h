@@ -265,6 +265,11 @@ REACH_API int32_t reach_flowpipe_phase_ms(reach_flowpipe* fp, double* chain_ms, 
  * (HBM-bound) instead of the dense DMMA GEMM; the results are those of the dense product (the skipped terms are exact
  * zeros).  Detected at creation; the environment variable REACH_GLGM06_DENSE=1 forces the GEMM. */
 REACH_API int32_t reach_flowpipe_map_info(reach_flowpipe* fp, int32_t* sparse_levels, int32_t* nnz_per_row);
+/* How the Girard SELECTION of W ran in the last run: `batches` batches of steps, `parallel_batches` of them through the parallel
+ * selection chain (steady state: W full, no zero scores; every generator's fate over the batch is evaluated independently),
+ * the others through the sequential merge chain (growth phase, zero-generator removal still changing the box).  Same
+ * selections either way; REACH_CHAIN_SEQUENTIAL=1 forces the sequential chain. */
+REACH_API int32_t reach_flowpipe_chain_info(reach_flowpipe* fp, int64_t* parallel_batches, int64_t* batches);
 /* Diagnostics: serial != 0 makes the next runs issue everything on one stream (no overlap), so that the per-kernel
  * CUDA-event times of reach_flowpipe_timing / _phase_ms are those of each kernel running alone. */
 REACH_API int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial);

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "reach_flowpipe_timing": [vp, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p],
     "reach_flowpipe_phase_ms": [vp, c_double_p, c_double_p],
     "reach_flowpipe_map_info": [vp, c_int32_p, c_int32_p],
+    "reach_flowpipe_chain_info": [vp, c_int64_p, c_int64_p],
     "reach_flowpipe_set_serial": [vp, i32],
     "reach_flowpipe_free": [vp],
     "reach_reduce_order": [vp, i64, i64, c_double_p, c_double_p, i64, i64, i32, c_double_p, i64, c_int64_p, c_int32_p],

@@ -509,6 +509,12 @@ class Flowpipe:
         self.ctx._check(self.ctx.lib.reach_flowpipe_map_info(self._h, C.byref(a), C.byref(b)))
         return dict(sparse_levels=int(a.value), nnz_per_row=int(b.value))
 
+    def chain_info(self):
+        """dict(parallel_batches, batches): how many batches of the last run took the parallel selection chain."""
+        a, b = C.c_int64(), C.c_int64()
+        self.ctx._check(self.ctx.lib.reach_flowpipe_chain_info(self._h, C.byref(a), C.byref(b)))
+        return dict(parallel_batches=int(a.value), batches=int(b.value))
+
     def set_serial(self, serial: bool):
         """Diagnostics: run without stream overlap so that per-kernel times are those of each kernel alone."""
         self.ctx._check(self.ctx.lib.reach_flowpipe_set_serial(self._h, int(bool(serial))))

@@ -83,6 +83,9 @@ struct GP {
     int* ordS; int* cpsS; int* cntZ;   // by sorted rank: element index, its compact position; # zero scores per segment
     // ---- W chain state (sorted list) + per-step snapshots of the batch
     WEnt* wEnt; int* wCount;
+    WEnt* wEntAlt;              // the next W list while the parallel chain still reads the current one
+    int* fastFlag;              // batch-local: 1 = this batch took the parallel selection chain (chain_fast_kernel)
+    int* fastCount;             // [2]: batches that took the parallel chain / all batches (diagnostics)
     WEnt* snEnt; int* snCount;
     PlanW* planW; PlanR* planR;                 // [N+2]
     int* dlistW;                // [smax][capDisc] references of the generators boxed by the W reduction, sigma order
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
     __shared__ int s_pC[128], s_zC[128];
     __shared__ int s_nd;
     const int tid = threadIdx.x, cap = g.capW, pV = g.pV, lane = tid & 31, wid = tid >> 5;
+    if (g.fastFlag != nullptr && *g.fastFlag != 0) return;      // the parallel chain handled this batch (uniform over the CTA)
     // working set (shared memory, or global scratch when the W list is too long): the sorted list of W, double-buffered;
     // the input segment C_t of two consecutive steps in sorted order (score, element, compact position).
     WEnt* ebuf0 = SMEM ? reinterpret_cast<WEnt*>(chain_sm) : reinterpret_cast<WEnt*>(scr);
@@ -631,6 +635,189 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
     if (tid == 0) *g.wCount = pW;
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// PARALLEL CHAIN (steady state).  Once W is full -- n(r-1) dense generators plus the n box generators of the previous step --
+// and no mapped generator has score exactly 0, every step boxes the n box generators (score 0, always first) and the pC_t
+// lowest dense candidates of D_t ∪ C_t (D_t: the dense generators of W_{k-1}, C_t: the valid columns of P_{k-1} GV).  Under
+// Julia's stable sortperm the candidates are totally ordered by (score, age, column), ages never change, so whether and
+// when a generator is boxed is a pure function of counts:
+//     L_t(e)   = #candidates of step t that sort before e  = pos_t(e) + #{x in C_t : score_x < score_e}      (e in D_t)
+//     boxed at t  <=>  L_t(e) < pC_t ;  otherwise  pos_{t+1}(e) = L_t(e) - pC_t.
+// One warp per generator (the dense part of W at the start of the batch and every mapped column of the batch) evaluates its
+// whole life over the batch -- a binary search per step, a warp prefix sum -- and writes what the batched numerics read: its
+// entry in every per-step snapshot of W, its slot in the boxed list of the step that boxes it, and its place in the next W.
+// No step waits for another: 64 dependent merges on one CTA (3.9 us each at C2) become two launches.
+// chain_decide_kernel checks the preconditions on the device (the host never synchronises); when they do not hold (growth
+// phase, zero scores, zero-generator removal still shrinking the box) the sequential chain_kernel below runs instead.
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) chain_decide_kernel(GP g, int k0, int cnt, int force_sequential) {
+    const int lane = threadIdx.x, n = g.n, nkeep = (int)g.nkeep;
+    int ok = !force_sequential && nkeep >= 1 && cnt <= 128 && *g.wCount == (int)g.rn;
+    if (ok) {
+        for (int i = lane; i < n; i += 32) {
+            const WEnt w = g.wEnt[i];
+            ok &= (w.ref == tag_ref(k0 - 1, i, n)) && (w.key == 0.0) && (w.pos == nkeep + i);
+        }
+        if (lane == 0) {
+            const WEnt w = g.wEnt[n];                   // the lowest dense generator: a genuine generator with a positive score
+            ok &= (w.ref >= 0) && (w.key > 0.0);
+        }
+        for (int t = lane; t < cnt; t += 32) ok &= (g.cntS[2 * t + 1] >= 1) && (g.cntZ[2 * t + 1] == 0);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        *g.fastFlag = ok;
+        g.fastCount[0] += ok;
+        g.fastCount[1] += 1;
+    }
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(256) chain_fast_kernel(GP g, int k0, int cnt) {
+    if (*g.fastFlag == 0) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n = g.n, nkeep = (int)g.nkeep, pV = g.pV, rn = (int)g.rn;
+    if (warp >= nkeep + cnt * pV) return;
+    int b = -1, j = 0, cp = 0, ref;
+    double key;
+    if (warp < nkeep) {
+        const WEnt w = g.wEnt[n + warp];
+        key = w.key; ref = w.ref;
+    } else {
+        const int x = warp - nkeep;
+        b = x / pV; j = x - b * pV;
+        if (j >= g.cntS[2 * b + 1]) return;
+        const int base = b * g.q + g.p0;
+        key = g.skS[base + j]; ref = (int)(g.col0 + base + g.ordS[base + j]); cp = g.cpsS[base + j];
+    }
+    constexpr int U = 4;                                 // steps per lane: cnt <= 128
+    int delta[U], pc[U], incl[U];
+    int older_greater = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int t = lane + 32 * u;
+        delta[u] = 0; pc[u] = 0;
+        if (t < cnt) {
+            pc[u] = g.cntS[2 * t + 1];
+            const double* sk = g.skS + t * g.q + g.p0;
+            if (t > b) delta[u] = lower_bound(sk, pc[u], key) - pc[u];         // younger columns sort after e on a tie
+            else if (t < b) older_greater += pc[u] - upper_bound(sk, pc[u], key);   // older columns sort before e on a tie
+        }
+    }
+    // position from which the recurrence starts: P0 = pos at step t0
+    int t0 = 0, P0 = warp, entry_L = 0;
+    if (b >= 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) older_greater += __shfl_xor_sync(0xffffffffu, older_greater, o);
+        const int G = older_greater + (nkeep - upper_bound_ent(g.wEnt + n, nkeep, key));   // older generators that sort after e
+        entry_L = (nkeep - min(nkeep, G)) + j;           // candidates of step b that sort before e
+        t0 = b + 1;
+        int pcb = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v = __shfl_sync(0xffffffffu, pc[u], b & 31);
+            if (u == (b >> 5)) pcb = v;
+        }
+        P0 = entry_L - pcb;                              // pos_{b+1}(e) if it survives its first step
+    }
+    // inclusive prefix sums of delta over t = 0 .. cnt-1 (t = lane + 32 u: lanes first, then u)
+    int carry = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int v = delta[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += x;
+        }
+        incl[u] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    // first step that boxes e
+    int death = INT_MAX;
+    if (b >= 0 && P0 < 0) death = b;                     // boxed by the very reduction it enters
+    else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = lane + 32 * u;
+            if (t < cnt && t >= t0 && P0 + incl[u] < 0) death = min(death, t);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) death = min(death, __shfl_xor_sync(0xffffffffu, death, o));
+    }
+    if (b >= 0 && lane == 0) {                           // the step the column enters: its place in the merged order
+        if (death == b) g.dlistW[(int64_t)b * g.capDisc + n + entry_L] = ref;
+        if (RECORD) {
+            g.recOrdW[(int64_t)(k0 + b) * g.capListW + n + entry_L] = rn + cp;
+            g.recHW[(int64_t)(k0 + b) * g.capListW + rn + cp] = key;
+        }
+    }
+    if (death != b || b < 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = lane + 32 * u;
+            if (t < cnt && t >= t0 && t <= death) {
+                const int pos = P0 + incl[u] - delta[u];     // position among the dense generators of W_{k-1}, ascending
+                WEnt w;
+                w.key = key; w.ref = ref; w.pos = pos;
+                g.snEnt[(int64_t)t * g.capW + n + pos] = w;
+                const int L = pos + delta[u] + pc[u];
+                if (t == death) g.dlistW[(int64_t)t * g.capDisc + n + L] = ref;
+                if (RECORD) {
+                    g.recOrdW[(int64_t)(k0 + t) * g.capListW + n + L] = pos;
+                    g.recHW[(int64_t)(k0 + t) * g.capListW + pos] = key;
+                }
+            }
+        }
+        if (death == INT_MAX && lane == 0) {             // survives the batch: its place in the next W
+            WEnt w;
+            w.key = key; w.ref = ref; w.pos = P0 + carry;
+            g.wEntAlt[n + w.pos] = w;
+        }
+    }
+}
+
+// everything of the parallel chain that does not depend on scores: the box generators (references to the previous step's box
+// vector), the plans, and the hand-over of the next W
+template <bool RECORD>
+__global__ void __launch_bounds__(256) chain_fast_fill_kernel(GP g, int k0, int cnt) {
+    if (*g.fastFlag == 0) return;
+    const int n = g.n, nkeep = (int)g.nkeep, rn = (int)g.rn;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.y < (unsigned)cnt) {
+        const int t = blockIdx.y, k = k0 + t;
+        if (gid < n) {
+            const int i = gid;
+            WEnt w;
+            w.key = 0.0; w.ref = tag_ref(k - 1, i, n); w.pos = nkeep + i;
+            g.snEnt[(int64_t)t * g.capW + i] = w;
+            g.dlistW[(int64_t)t * g.capDisc + i] = w.ref;
+            g.tcnt[(int64_t)t * n + i] = 1;
+            g.tsrc[((int64_t)t * n + i) * 4] = k - 1;
+            if (RECORD) {
+                g.recOrdW[(int64_t)k * g.capListW + i] = nkeep + i;
+                g.recHW[(int64_t)k * g.capListW + nkeep + i] = 0.0;
+            }
+        }
+        if (gid == 0) {
+            const int pC = g.cntS[2 * t + 1];
+            g.snCount[t] = rn;
+            PlanW pl;
+            pl.mode = MODE_REDUCE; pl.pin = rn + pC; pl.m = n + pC; pl.pW = rn; pl.pC = pC; pl.nk = nkeep; pl.nd = n; pl.z = 0;
+            g.planW[k] = pl;
+        }
+    } else {                                             // last row of the grid: the next W (box generators of the last step first)
+        const int klast = k0 + cnt - 1;
+        if (gid < n) {
+            WEnt w;
+            w.key = 0.0; w.ref = tag_ref(klast, gid, n); w.pos = nkeep + gid;
+            g.wEnt[gid] = w;
+        } else if (gid < rn) {
+            g.wEnt[gid] = g.wEntAlt[gid];
+        }
+    }
+}
+
 static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st,
                          bool exclusive = false) {
     // exclusive: ask for so much shared memory that neither a GEMM CTA nor a numerics CTA fits next to the chain -- it
@@ -643,6 +830,28 @@ static void launch_chain(GP& g, int k0, int cnt, bool use_smem, size_t smem, dou
         if (g.record) chain_kernel<false, true><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
         else chain_kernel<false, false><<<1, CHAIN_THREADS, 0, st>>>(g, k0, cnt, scr);
     }
+}
+
+// Selection chain of steps [k0, k0 + cnt): the parallel chain when its preconditions hold (decided on the device), else the
+// sequential one -- both are enqueued, exactly one of them works.
+static int launch_chain_auto(GP& g, int k0, int cnt, bool use_smem, size_t smem, double* scr, cudaStream_t st, bool exclusive) {
+    const bool force_seq = getenv("REACH_CHAIN_SEQUENTIAL") != nullptr;      // diagnostics / A-B tests
+    chain_decide_kernel<<<1, 32, 0, st>>>(g, k0, cnt, force_seq ? 1 : 0);
+    int launches = 1;
+    if (!force_seq && cnt <= 128 && g.nkeep >= 1) {
+        const int64_t warps = g.nkeep + (int64_t)cnt * g.pV;
+        const dim3 fill_grid((unsigned)ceil_div(g.rn, 256), (unsigned)(cnt + 1));
+        if (g.record) {
+            chain_fast_kernel<true><<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(g, k0, cnt);
+            chain_fast_fill_kernel<true><<<fill_grid, 256, 0, st>>>(g, k0, cnt);
+        } else {
+            chain_fast_kernel<false><<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(g, k0, cnt);
+            chain_fast_fill_kernel<false><<<fill_grid, 256, 0, st>>>(g, k0, cnt);
+        }
+        launches += 2;
+    }
+    launch_chain(g, k0, cnt, use_smem, smem, scr, st, exclusive);
+    return launches + 1;
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -1684,6 +1893,8 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.Wd = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * ld));
             g.wEnt = (WEnt*)own(dalloc<WEnt>(ctx, g.capW));
             g.wCount = (int*)own(dalloc<int>(ctx, 1));
+            g.wEntAlt = (WEnt*)own(dalloc<WEnt>(ctx, g.capW));
+            g.fastCount = (int*)own(dalloc<int>(ctx, 2));
             g.planW = (PlanW*)own(dalloc<PlanW>(ctx, N + 2));
             g.planR = (PlanR*)own(dalloc<PlanR>(ctx, N + 2));
             g.cW = (double*)own(dalloc<double>(ctx, ld));
@@ -1715,6 +1926,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
                 h.cntZ = (int*)own(dalloc<int>(ctx, 2 * s + 8));
                 h.snEnt = (WEnt*)own(dalloc<WEnt>(ctx, (size_t)s * g.capW));
                 h.snCount = (int*)own(dalloc<int>(ctx, s));
+                h.fastFlag = (int*)own(dalloc<int>(ctx, 1));
                 h.dlistW = (int*)own(dalloc<int>(ctx, (size_t)s * g.capDisc));
                 h.tcnt = (int*)own(dalloc<int>(ctx, (size_t)s * n));
                 h.tsrc = (int*)own(dalloc<int>(ctx, (size_t)s * n * 4));
@@ -1881,7 +2093,7 @@ static void score_and_sort(Flowpipe* F, GP& g, int64_t slot0, int cnt, cudaStrea
 static void bind_set(GP& g, const GP& h) {
     g.hS = h.hS; g.skS = h.skS; g.rkS = h.rkS; g.cposS = h.cposS; g.cntS = h.cntS;
     g.ordS = h.ordS; g.cpsS = h.cpsS; g.cntZ = h.cntZ;
-    g.snEnt = h.snEnt; g.snCount = h.snCount; g.dlistW = h.dlistW; g.tcnt = h.tcnt; g.tsrc = h.tsrc;
+    g.snEnt = h.snEnt; g.snCount = h.snCount; g.fastFlag = h.fastFlag; g.dlistW = h.dlistW; g.tcnt = h.tcnt; g.tsrc = h.tsrc;
     g.orderR = h.orderR; g.partW = h.partW; g.partR = h.partR;
 }
 
@@ -1893,9 +2105,8 @@ static size_t numerics_smem(int64_t ld, int jb) {
 
 // selection chain of steps [k0, k0 + cnt) (their slots k-1 are in the archive already) ...
 static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) {
-    launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st, F->chain_exclusive);
+    F->ctx->launches += launch_chain_auto(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st, F->chain_exclusive);
     REACH_CUDA(cudaGetLastError());
-    F->ctx->launches += 1;
 }
 
 // ... and their batched numerics
@@ -2067,6 +2278,7 @@ void flowpipe_run(Flowpipe* F) {
         bind_set(g, F->gset[0]);
         // W_1 = V, cW_1 = cV (GLGM06/reach.jl:41-42)
         REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
+        REACH_CUDA(cudaMemsetAsync(g.fastCount, 0, 2 * sizeof(int), st));
         score_and_sort(F, g, 0, 1, st);
         init_w_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(g.pV, 256)), 256, 0, st>>>(g);
         REACH_CUDA(cudaGetLastError());
@@ -2275,6 +2487,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         g.col0 = 0;
         if (phase == 0) {
             F->next_batch = 0; F->pw = &F->Phi; F->sp = 0; F->shard_lvl = 0; F->ran = false;
+            REACH_CUDA(cudaMemsetAsync(g.fastCount, 0, 2 * sizeof(int), st));
             REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
             score_only(F, g, 0, 1, st);
         } else if (phase == 1) {
@@ -2302,7 +2515,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         score_only(F, g, B.have, cnt, st);
     } else if (phase == 1) {
         sort_only(F, g, cnt, st);
-        launch_chain(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st);
+        ctx->launches += launch_chain_auto(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st, false) - 1;
         if (it == 4) wbox_partial_kernel<4><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
         else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
         else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
@@ -2855,6 +3068,20 @@ int32_t reach_flowpipe_map_info(reach_flowpipe* fp, int32_t* sparse_levels, int3
     if (sparse_levels) *sparse_levels = fp->f->ell_levels;
     if (nnz_per_row) *nnz_per_row = fp->f->ell_levels ? fp->f->ell_width : 0;
     return REACH_OK;
+}
+
+int32_t reach_flowpipe_chain_info(reach_flowpipe* fp, int64_t* parallel_batches, int64_t* batches) {
+    if (!fp) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    int h[2] = {0, 0};
+    if (!fp->f->homog && fp->f->g.fastCount) {
+        REACH_CUDA(cudaMemcpyAsync(h, fp->f->g.fastCount, sizeof(h), cudaMemcpyDeviceToHost, fp->ctx->stream));
+        REACH_CUDA(cudaStreamSynchronize(fp->ctx->stream));
+    }
+    if (parallel_batches) *parallel_batches = h[0];
+    if (batches) *batches = h[1];
+    return REACH_OK;
+    FP_END(fp->ctx)
 }
 
 int32_t reach_flowpipe_set_serial(reach_flowpipe* fp, int32_t serial) {

@@ -81,9 +81,38 @@ def test_long_dense_flowpipes_every_step_and_selection(ctx, n, m, N, r, block, m
     Om = orc.reduce_order(D.Omega0, r)
     fp = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, RECORD).run()
     assert fp.map_info()["sparse_levels"] == 0
+    info = fp.chain_info()
+    assert info["batches"] >= 4 and info["parallel_batches"] >= info["batches"] - 8, info      # all but the growth phase
     worst = _stream_compare({f"dense n={n} block={block}": _fp_reader(fp)}, Om, D.V, D.Phi, N, r)
     assert max(worst.values()) <= 1.0
     fp.close()
+
+
+@pytest.mark.parametrize("n,m,N,r", [(33, 2, 420, 3), (96, 5, 330, 4)])
+def test_parallel_selection_chain_is_bit_identical_to_the_sequential_chain(ctx, n, m, N, r, monkeypatch):
+    """The parallel chain (every generator's fate over a batch evaluated independently from counts) and the sequential
+    merge chain (REACH_CHAIN_SEQUENTIAL=1) must take the same selections in the same order: every generator, box vector
+    and recorded sortperm agrees BIT FOR BIT."""
+    D = _dense_problem(900 + n, n, m)
+    Om = orc.reduce_order(D.Omega0, r)
+    fpar = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, RECORD).run()
+    assert fpar.chain_info()["parallel_batches"] >= 3
+    monkeypatch.setenv("REACH_CHAIN_SEQUENTIAL", "1")
+    fseq = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, RECORD).run()
+    monkeypatch.delenv("REACH_CHAIN_SEQUENTIAL")
+    assert fseq.chain_info()["parallel_batches"] == 0
+    p = fpar.ngens()
+    assert np.array_equal(p, fseq.ngens())
+    for k in range(1, N + 1):
+        ca, Ga = fpar.step(k, int(p[k - 1]))
+        cb, Gb = fseq.step(k, int(p[k - 1]))
+        assert np.array_equal(ca, cb) and np.array_equal(Ga, Gb), f"step {k}"
+        if k >= 2:
+            for which in (0, 1):
+                sa, sb = fpar.selection(k, which), fseq.selection(k, which)
+                assert sa["p_in"] == sb["p_in"] and sa["m"] == sb["m"] and np.array_equal(sa["ind"], sb["ind"]), (k, which)
+                assert np.array_equal(sa["h"], sb["h"])
+    fpar.close(); fseq.close()
 
 
 @pytest.mark.parametrize("rzg", [True, False])
@@ -132,6 +161,7 @@ def test_config_c2_full_length_every_step_sparse_and_dense_map(ctx, monkeypatch)
     assert N == 2000 and Om.ngens == 1084 and D.V.ngens == 273
     fs = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, RECORD).run()
     assert fs.map_info()["sparse_levels"] >= 1
+    assert fs.chain_info()["parallel_batches"] >= 25        # 38 batches; all but the growth phase take the parallel selection chain
     monkeypatch.setenv("REACH_GLGM06_DENSE", "1")
     fd = ctx.glgm06(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, RECORD).run()
     monkeypatch.delenv("REACH_GLGM06_DENSE")
