@@ -1047,7 +1047,46 @@ __device__ __forceinline__ WseqIn wseq_load(const GP& g, int k0, int t, int i) {
     }
     return w;
 }
+// Steady state (the parallel chain handled the batch): every step boxes exactly the n box generators of the previous step, so
+// d_k = base_k + |d_{k-1}| and the recurrences need no indirection.  One thread per row: the loads of 16 steps are independent
+// and issued together, the sums run in registers in the sequential kernel's order (identical bits).
+__global__ void __launch_bounds__(128) wseq_fast_kernel(GP g, int k0, int cnt) {
+    if (*g.fastFlag == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    double cw = g.cW[i];
+    double d = g.Wd[(int64_t)(k0 - 1) * g.ld + i];
+    constexpr int CH = 16;
+    for (int t0 = 0; t0 < cnt; t0 += CH) {
+        double base[CH], yc0[CH], ycV[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int t = t0 + u;
+            base[u] = 0.0; yc0[u] = 0.0; ycV[u] = 0.0;
+            if (t < cnt) {
+                for (int b = 0; b < NBW; ++b) base[u] += g.partW[((int64_t)t * NBW + b) * g.ld + i];
+                const double* yc = g.Y + (int64_t)(t * g.qloc + g.la + g.lc) * g.ld;
+                yc0[u] = yc[i];
+                ycV[u] = yc[g.ld + i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int t = t0 + u;
+            if (t < cnt) {
+                const int k = k0 + t;
+                g.Rc[(int64_t)(k - 1) * g.ld + i] = yc0[u] + cw;
+                cw += ycV[u];
+                d = base[u] + fabs(d);
+                g.Wd[(int64_t)k * g.ld + i] = d;
+            }
+        }
+    }
+    g.cW[i] = cw;
+}
+
 __global__ void __launch_bounds__(128) wseq_kernel(GP g, int k0, int cnt) {
+    if (g.fastFlag != nullptr && *g.fastFlag != 0) return;     // wseq_fast_kernel handled this batch
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     double cw = g.cW[i];
@@ -1447,10 +1486,25 @@ template <int W>
 __global__ void __launch_bounds__(1024) ell_left_score_kernel(GP g, int cnt, const int* __restrict__ idx,
                                                               const double* __restrict__ val, const double* __restrict__ X,
                                                               double* __restrict__ Yout) {
-    extern __shared__ __align__(16) double ycol[];          // ELL_GPB columns of ld doubles
+    // TMA-staged: the CTA's ELL_GPB input columns are contiguous in the archive, so ONE bulk copy (cp.async.bulk, SASS UBLKCP)
+    // brings them into shared memory, the threads gather from there (thread = state row, its ELL row in registers), and ONE
+    // bulk copy shared -> global writes the mapped columns while the warps compute their scores from the same tile.  No
+    // per-thread global load or store is left on the path; three CTAs per SM keep ~200 KB in flight.
+    extern __shared__ __align__(128) double esm[];          // [ELL_GPB * ld] input columns | [ELL_GPB * ld] mapped columns | mbarrier
     const int n = g.n, ld = g.ld;
+    double* xin = esm;
+    double* ycol = esm + ELL_GPB * ld;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ycol + ELL_GPB * ld);
     const int i = threadIdx.x;
     const int64_t Q = (int64_t)cnt * g.q;
+    const int64_t g0 = (int64_t)blockIdx.x * ELL_GPB;
+    const int ncols = (int)min((int64_t)ELL_GPB, Q - g0);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(ncols * ld * 8));
+        bulk_g2s(xin, X + g0 * ld, (uint32_t)(ncols * ld * 8), bar);
+    }
     int ji[W];
     double vi[W];
 #pragma unroll
@@ -1458,34 +1512,27 @@ __global__ void __launch_bounds__(1024) ell_left_score_kernel(GP g, int cnt, con
         ji[w] = i < n ? idx[i * ELL_MAX + w] : 0;
         vi[w] = i < n ? val[i * ELL_MAX + w] : 0.0;
     }
-    const int64_t g0 = (int64_t)blockIdx.x * ELL_GPB;
-    constexpr int U = W <= 2 ? 8 : (W <= 4 ? 4 : 2);
-#pragma unroll 1
-    for (int u0 = 0; u0 < ELL_GPB; u0 += U) {
-        double xv[U][W];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t gq = min(g0 + u0 + u, Q - 1);
-            const double* x = X + gq * ld;
-#pragma unroll
-            for (int w = 0; w < W; ++w) xv[u][w] = x[ji[w]];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
+    __syncthreads();                                         // the barrier is initialised before anyone polls it
+    mbar_wait(bar, 0);
+    if (i < ld) {
+#pragma unroll 4
+        for (int u = 0; u < ncols; ++u) {
             double acc = 0.0;
 #pragma unroll
-            for (int w = 0; w < W; ++w) acc = fma(vi[w], xv[u][w], acc);
-            const int64_t gq = g0 + u0 + u;
-            if (gq < Q && i < n) Yout[gq * ld + i] = acc;
-            if (i < ld) ycol[(u0 + u) * ld + i] = i < n ? acc : 0.0;       // pad rows are zero, as in the archive
+            for (int w = 0; w < W; ++w) acc = fma(vi[w], xin[u * ld + ji[w]], acc);
+            ycol[u * ld + i] = i < n ? acc : 0.0;            // pad rows are zero, as in the archive
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_s2g(Yout + g0 * ld, ycol, (uint32_t)(ncols * ld * 8));
+        bulk_commit();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int n2 = ld / 2;
-    for (int u = warp; u < ELL_GPB; u += nwarps) {
+    for (int u = warp; u < ncols; u += nwarps) {
         const int64_t gq = g0 + u;
-        if (gq >= Q) break;
         const int t = (int)(gq / g.q), c = (int)(gq - (int64_t)t * g.q);
         if (c >= g.p0 + g.pV) continue;                     // the two centre columns of a slot carry no score
         const double2* c2 = reinterpret_cast<const double2*>(ycol + u * ld);
@@ -1507,6 +1554,7 @@ __global__ void __launch_bounds__(1024) ell_left_score_kernel(GP g, int cnt, con
         const double asum = warp_sum(s), amax = warp_max(m);
         if (lane == 0) g.hS[t * g.q + c] = (g.strip && asum == 0.0) ? INFINITY : asum - amax;
     }
+    if (threadIdx.x == 0) bulk_wait0();                      // the tile has left shared memory before the CTA retires
 }
 
 // ---- projection of a zonotope flowpipe: M * R_k (project_reach.jl:18-99, linear map of every reach set) -----------
@@ -1937,9 +1985,11 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             int prio_lo = 0, prio_hi = 0;
             REACH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             REACH_CUDA(cudaStreamCreateWithPriority(&F->side, cudaStreamNonBlocking, prio_hi));      // the chain is the critical path
-            REACH_CUDA(cudaStreamCreateWithFlags(&F->side2, cudaStreamNonBlocking));
-            REACH_CUDA(cudaStreamCreateWithFlags(&F->side3, cudaStreamNonBlocking));
-            REACH_CUDA(cudaStreamCreateWithFlags(&F->side4, cudaStreamNonBlocking));
+            // the map / GEMM of later batches (main stream, lowest priority) is far ahead of the pipeline; everything downstream
+            // of it gets its CTAs scheduled first as SM slots free up
+            REACH_CUDA(cudaStreamCreateWithPriority(&F->side2, cudaStreamNonBlocking, prio_hi));
+            REACH_CUDA(cudaStreamCreateWithPriority(&F->side3, cudaStreamNonBlocking, prio_hi));
+            REACH_CUDA(cudaStreamCreateWithPriority(&F->side4, cudaStreamNonBlocking, prio_hi));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
             if (p0 > 0) REACH_CUDA(cudaMemsetAsync(g.Rg, 0, (size_t)p0 * ld * 8, st));
             if (g.la > 0)
@@ -1995,17 +2045,17 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
 static bool map_slots_scored(Flowpipe* F, int lvl, GP& g, int64_t slot0, int cnt, const double* Xp, double* Yp) {
     Ctx* ctx = F->ctx;
     const int64_t n = F->n, ld = F->ld;
-    const size_t smem = (size_t)ELL_GPB * ld * sizeof(double);
-    if (lvl >= F->ell_levels || F->nranks != 1 || smem > 96 * 1024) return false;
+    const size_t smem = (size_t)2 * ELL_GPB * ld * sizeof(double) + 16;
+    if (lvl >= F->ell_levels || F->nranks != 1 || smem > 200 * 1024) return false;
     g.Y = F->Hflow + slot0 * F->qloc * ld;
     g.col0 = slot0 * F->q;
     static bool attr[64] = {false};
     static std::mutex attr_mutex;
     std::lock_guard<std::mutex> attr_lock(attr_mutex);
     if (!attr[ctx->device & 63]) {
-        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        REACH_CUDA(cudaFuncSetAttribute(ell_left_score_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr[ctx->device & 63] = true;
     }
     const int* idx = F->ell_idx + (size_t)lvl * n * ELL_MAX;
@@ -2129,6 +2179,7 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
     else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     mark();
+    wseq_fast_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     mark();
     if (rank_st && rank_st != st) {
@@ -2522,6 +2573,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 2;
     } else if (phase == 2) {
+        wseq_fast_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
         rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
         const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
