@@ -770,6 +770,45 @@ def c2_flat_scalars(c2):
     return {k: v for k, v in out.items() if v is not None}
 
 
+def run_glgm06_column_sharded(rank, world, dist, reps=3):
+    """Rider under --gpus N: ONE C2 system with its generator columns sharded over the N ranks (reach_glgm06_create_sharded,
+    sharding.run_sharded): every rank maps, scores and gathers only its columns, the Girard selection runs replicated on the
+    all-reduced scores, three small NCCL all-reduces per batch of steps."""
+    import torch
+    import reachability_jl_b200 as rb
+    from reachability_jl_b200 import api, sharding, workloads as wl
+    w = wl.iss()
+    N = int(round(w.T / w.delta))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        ctx = rb.Context(dev, stream=stream.cuda_stream)
+        Phi, (c0, G0), V = api.discretize_zonotope(ctx, w.A, w.delta, w.c, w.r, w.B, (w.cU, w.rU))
+        G0red, _ = ctx.reduce_order(c0, G0, w.max_order)
+        fp = ctx.glgm06_sharded(Phi, c0, G0red, N, w.max_order, V[0], V[1], rank, world)
+        for _ in range(2):
+            sharding.run_sharded(fp, dist)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(reps):
+            sharding.run_sharded(fp, dist)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(dist, world, ev0.elapsed_time(ev1), dev)
+        p = fp.ngens()
+        fp.close()
+        ctx.close()
+    if rank != 0:
+        return None
+    return {"value": reps * (N - 1) / (ms * 1e-3), "unit": "flowpipe steps/s", "ms_per_flowpipe": ms / reps, "ranks": world,
+            "generators_per_reach_set": int(p.max()), "scaling": "strong",
+            "api": "reach_glgm06_create_sharded + reach_glgm06_shard_phase / _shard_buffer, NCCL sum all-reduces issued by "
+                   "sharding.run_sharded on the library's stream (no host synchronisation inside the flowpipe)",
+            "note": "at n = 270 the exchange is latency-bound (SURVEY 8e): this does not beat one GPU; it exists for large n * p"}
+
+
 def run_inprocess_multi(rank, world, dist):
     """Rider under --gpus N: ONE process (rank 0) drives all N GPUs through a multi-device context (reach_ctx_create_multi) and
     the one-shot host-buffer call reach_bffpsv18_boxes -- what a single Julia task gets through one `ccall`.  The other ranks
@@ -979,6 +1018,7 @@ def main():
                                                 "no_e2e": True, "no_cpu_baseline": True, "rider": True}), rank, world, dist)
         r5 = run_ensemble(argparse.Namespace(**{**vars(args), "workload": "C5", "steps": 2, "warmup": 1, "flow_steps": 0,
                                                 "no_e2e": world > 1, "no_cpu_baseline": True, "rider": True}), rank, world, dist)
+        shard = run_glgm06_column_sharded(rank, world, dist) if world > 1 else None
         multi = run_inprocess_multi(rank, world, dist) if world > 1 else None
         if out is not None:
             out["riders"] = {"c4_mna5": {k: r4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling")},
@@ -988,6 +1028,9 @@ def main():
                         c5_dmma_frac=r5["roofline"]["frac"], c5_real_hbm_frac=r5["roofline"]["hbm"]["frac"])
             if r5.get("e2e"):
                 flat["c5_e2e"] = r5["e2e"]["value"]
+            if shard is not None:
+                out["riders"]["c2_column_sharded"] = shard
+                flat["c2_column_sharded_value"] = shard["value"]
             if multi is not None:
                 out["riders"]["c3_one_process_multi_device"] = multi
                 flat["c3_one_process_multi_device_e2e"] = multi["value"]
