@@ -43,7 +43,7 @@ constexpr int MODE_UNCHANGED = 0;   // r*n >= p: reduce_order returns Z unchange
 constexpr int MODE_REDUCE = 1;
 constexpr int NBW = 4;              // box-sum chunks per step for the W reduction (wseq adds them up per row: keep it small)
 constexpr int NBR = 16;
-constexpr int COPY_CTAS = 48;       // copy CTAs per step of the R gather
+constexpr int COPY_CTAS = 8;        // CTAs per step that record the references of the kept generators of R_k
 constexpr int COPY_JB = 8;          // columns a warp resolves (one per lane) and then moves back to back
 constexpr int NUM_WARPS = 4;        // warps per CTA of the TMA-staged numerics kernels (wbox_partial, apply_r)
 constexpr int STAGE_BYTES = 16384;  // staging per warp: JB = min(8, STAGE_BYTES / column bytes) columns in flight
@@ -94,7 +94,10 @@ struct GP {
     double* partW; double* partR;               // [smax][NB*][ld]
     double* cW;
     // ---- flowpipe
-    double* Rg; int64_t slot; double* Rc; double* Rd; int* Rrow; int2* meta;
+    // R_k = [ kept generators, as REFERENCES in sortperm order (Rref) | box generators d[row] e_row (Rd, Rrow) ]: the reach sets
+    // are never copied into dense matrices by the time loop -- every generator already sits in the archive -- the dense
+    // n x p matrix of a reach set is materialised by the fetch / projection kernels (materialize_kernel) on demand
+    int* Rref; double* Rc; double* Rd; int* Rrow; int2* meta;
     // ---- selection records
     int* recOrdW; double* recHW; int* recOrdR; double* recHR;
 };
@@ -1235,50 +1238,15 @@ __global__ void __launch_bounds__(NUM_WARPS * 32) apply_r_kernel(GP g, int k0, i
         acc_reduce_store(g, a, stage_red(g, smem_raw, jb), g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
         return;
     }
-    double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
-    const int nwarps = (gridDim.x - NBR) * NUM_WARPS;
-    const int w0 = (blockIdx.x - NBR) * NUM_WARPS + warp;
+    // the kept generators of R_k: their references, in the order of the reduced zonotope (sortperm order)
+    int* rr = g.Rref + (int64_t)(k - 1) * g.capR;
     const int jobs = pl.mode == MODE_REDUCE ? pl.pin : g.p0 + pl.pW;
-    for (int j0 = w0 * jb; j0 < jobs; j0 += nwarps * jb) {
-        int ref = NO_JOB, dest = 0;
-        if (lane < jb) resolve_copy_job(g, pl, order, sn, t, j0 + lane, jobs, ref, dest);   // resolved in parallel
-        const double* src = (ref != NO_JOB && ref >= 0) ? col_ptr(g, ref) : nullptr;
-        const unsigned dense = stage_load(g, ws, src, lane);        // archive column -> stage (global -> shared bulk copy)
-        double tval = 0.0;
-        int trow = -1;
-        if (ref != NO_JOB && ref < 0) {
-            int kt;
-            tag_decode(ref, g.n, kt, trow);
-            tval = g.Wd[(int64_t)kt * g.ld + trow];
-        }
-        // box generators (one non-zero) and columns another rank owns (zeros here: the slabs of the ranks have disjoint
-        // support) are written with plain stores while the bulk loads are in flight
-        const unsigned other = __ballot_sync(0xffffffffu, ref != NO_JOB && src == nullptr);
-        for (unsigned rest = other; rest;) {
-            const int j = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const int r = __shfl_sync(0xffffffffu, ref, j), d = __shfl_sync(0xffffffffu, dest, j);
-            const double val = (r < 0 && g.rank == 0) ? __shfl_sync(0xffffffffu, tval, j) : 0.0;
-            const int it = r < 0 ? __shfl_sync(0xffffffffu, trow, j) : -1;
-            double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)d * g.ld);
-            for (int i = lane; i < n2; i += 32) {
-                double2 v = make_double2(0.0, 0.0);
-                if (2 * i == it) v.x = val;
-                if (2 * i + 1 == it) v.y = val;
-                d2[i] = v;
-            }
-        }
-        if (dense) {
-            stage_wait(ws);
-            if (src) {                                              // stage -> flowpipe slot (shared -> global bulk copy)
-                bulk_s2g(slot + (int64_t)dest * g.ld, ws.buf + (size_t)lane * g.ld, (uint32_t)(g.ld * 8));
-                bulk_commit();
-                bulk_wait_read0();
-            }
-            __syncwarp();
-        }
+    const int nthreads = (gridDim.x - NBR) * blockDim.x;
+    for (int job = (blockIdx.x - NBR) * blockDim.x + threadIdx.x; job < jobs; job += nthreads) {
+        int ref, dest;
+        resolve_copy_job(g, pl, order, sn, t, job, jobs, ref, dest);
+        if (ref != NO_JOB) rr[dest] = ref;
     }
-    bulk_wait0();
 }
 
 // Box vector, generator counts and (strip mode) the rows of the dense box generators of every R_k of the batch.
@@ -1314,38 +1282,39 @@ __global__ void __launch_bounds__(256) finalize_r_kernel(GP g, int k0) {
     if (tid == 0) g.meta[k - 1] = make_int2(pl.pin - pl.m, scan[255]);
 }
 
-// Dense box generators of the reach sets of steps [k0, k1): column nk + c of slot k is d[row_c] e_{row_c}.
-__global__ void __launch_bounds__(256) expand_diag_kernel(GP g, int k0, int k1) {
-    const int k = k0 + blockIdx.y;
-    if (k >= k1) return;
+// Dense generator matrices of the reach sets of steps [k0, k0 + cnt): slab t = pmax columns of leading dimension ldo (slab
+// stride `stride` doubles); column j < nk is the generator Rref[j] refers to (an archive column, or a box generator of W
+// whose value sits in the W box archive), the next nd columns are the box generators d[row] e_row of the reduction, the rest
+// is zero.  One warp per column.  A column-sharded rank materialises only what it owns (the others' columns are zero; the
+// replicated box generators belong to rank 0), so the slabs of the ranks sum to the reach set.
+__global__ void __launch_bounds__(256) materialize_kernel(GP g, int k0, int cnt, int pmax, double* __restrict__ out, int ldo,
+                                                          int64_t stride) {
+    const int t = blockIdx.y, k = k0 + t, col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= cnt || col >= pmax) return;
     const int2 mt = g.meta[k - 1];
     const int nk = mt.x, nd = mt.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n2 = g.ld / 2;
-    double* slot = g.Rg + (int64_t)(k - 1) * g.slot;
-    for (int c = blockIdx.x * 8 + warp; c < nd; c += gridDim.x * 8) {
-        const int row = g.Rrow[(int64_t)(k - 1) * g.n + c];
-        const double d = g.rank == 0 ? g.Rd[(int64_t)(k - 1) * g.ld + row] : 0.0;
-        double2* d2 = reinterpret_cast<double2*>(slot + (int64_t)(nk + c) * g.ld);
-        for (int i = lane; i < n2; i += 32) {
-            double2 v = make_double2(0.0, 0.0);
-            if (2 * i == row) v.x = d;
-            if (2 * i + 1 == row) v.y = d;
-            d2[i] = v;
+    double* dst = out + (int64_t)t * stride + (int64_t)col * ldo;
+    const double* src = nullptr;
+    int row = -1;
+    double val = 0.0;
+    if (col < nk) {
+        const int ref = g.Rref[(int64_t)(k - 1) * g.capR + col];
+        if (ref >= 0) {
+            src = col_ptr(g, ref);
+        } else {
+            int kt;
+            tag_decode(ref, g.n, kt, row);
+            val = g.rank == 0 ? g.Wd[(int64_t)kt * g.ld + row] : 0.0;
         }
+    } else if (col < nk + nd) {
+        row = g.Rrow[(int64_t)(k - 1) * g.n + (col - nk)];
+        val = g.rank == 0 ? g.Rd[(int64_t)(k - 1) * g.ld + row] : 0.0;
     }
-}
-
-// Reach sets of steps [k0, k0 + cnt) packed for the host: slab t = n x pmax doubles (leading dimension n), columns
-// beyond the set's generator count zeroed.  One warp per column.
-__global__ void __launch_bounds__(256) pack_slots_kernel(GP g, int k0, int cnt, int pmax, double* __restrict__ out) {
-    const int t = blockIdx.y, k = k0 + t, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (t >= cnt || warp >= pmax) return;
-    const int2 mt = g.meta[k - 1];
-    const int p = mt.x + mt.y;
-    const double* src = g.Rg + (int64_t)(k - 1) * g.slot + (int64_t)warp * g.ld;
-    double* dst = out + ((int64_t)t * pmax + warp) * g.n;
-    for (int i = lane; i < g.n; i += 32) dst[i] = warp < p ? src[i] : 0.0;
+    if (src) {
+        for (int i = lane; i < g.n; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < g.n; i += 32) dst[i] = i == row ? val : 0.0;
+    }
 }
 
 // Dense copy of the current W in logical order (box generators synthesised).  out: n x pW, leading dimension ldo.
@@ -1597,12 +1566,40 @@ __device__ __forceinline__ void proj_column(const double* __restrict__ col, cons
             for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
 }
 
-__global__ void __launch_bounds__(256) project_gens_kernel(ProjIn in, const double* __restrict__ Mt, double* __restrict__ out) {
+// `g` is only used when in.meta != nullptr (a reduced flowpipe: generators are references, see materialize_kernel)
+__global__ void __launch_bounds__(256) project_gens_kernel(ProjIn in, GP g, const double* __restrict__ Mt, double* __restrict__ out) {
     const int k = blockIdx.y, col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= in.N || col >= in.pmax) return;
     const int p = in.meta ? in.meta[k].x + in.meta[k].y : in.p_const;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (col < p) proj_column(in.G + (int64_t)k * in.slot + (int64_t)col * in.ld, Mt, in.n, in.q, lane, acc);
+    if (col < p && in.meta == nullptr) {
+        proj_column(in.G + (int64_t)k * in.slot + (int64_t)col * in.ld, Mt, in.n, in.q, lane, acc);
+    } else if (col < p) {
+        const int nk = in.meta[k].x;
+        const double* src = nullptr;
+        int row = -1;
+        double val = 0.0;
+        if (col < nk) {
+            const int ref = g.Rref[(int64_t)k * g.capR + col];
+            if (ref >= 0) {
+                src = col_ptr(g, ref);
+            } else {
+                int kt;
+                tag_decode(ref, g.n, kt, row);
+                val = g.rank == 0 ? g.Wd[(int64_t)kt * g.ld + row] : 0.0;
+            }
+        } else {
+            row = g.Rrow[(int64_t)k * g.n + (col - nk)];
+            val = g.rank == 0 ? g.Rd[(int64_t)k * g.ld + row] : 0.0;
+        }
+        if (src) {
+            proj_column(src, Mt, in.n, in.q, lane, acc);
+        } else if (row >= 0) {                      // M (val e_row) = val M[:, row]
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < in.q) acc[r] = Mt[(int64_t)r * (in.n + (in.n & 1)) + row] * val;
+        }
+    }
     if (lane < in.q) {
         const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
         out[((int64_t)k * in.pmax + col) * in.q + lane] = v;
@@ -1916,8 +1913,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             g.capListW = g.capW + (int)pV;
             g.capDisc = (int)std::max<int64_t>(g.capW + pV - g.nkeep, 0) + 8;
             g.smax = (int)s;
-            g.slot = ld * (int64_t)g.capR;
-            need += (double)N * (double)g.slot * 8.0;
+            need += (double)N * (double)g.capR * 4.0;          // the reach sets are generator references, not copies
             REACH_REQUIRE((double)N * (double)std::max<int64_t>(q, n) < 2.0e9, "glgm06: N * columns exceeds the 32-bit reference range");
         }
         if (need > 0.92 * (double)free_b) {
@@ -1952,7 +1948,7 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
                 g.recOrdR = (int*)own(dalloc<int>(ctx, (size_t)(N + 2) * g.capListR));
                 g.recHR = (double*)own(dalloc<double>(ctx, (size_t)(N + 2) * g.capListR));
             }
-            g.Rg = (double*)own(dalloc<double>(ctx, (size_t)N * g.slot, false));
+            g.Rref = (int*)own(dalloc<int>(ctx, (size_t)N * g.capR, false));
             g.Rc = (double*)own(dalloc<double>(ctx, (size_t)N * ld));
             g.Rd = (double*)own(dalloc<double>(ctx, (size_t)N * ld));
             g.Rrow = (int*)own(dalloc<int>(ctx, (size_t)N * n));
@@ -1991,10 +1987,12 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             REACH_CUDA(cudaStreamCreateWithPriority(&F->side3, cudaStreamNonBlocking, prio_hi));
             REACH_CUDA(cudaStreamCreateWithPriority(&F->side4, cudaStreamNonBlocking, prio_hi));
             // R_1 = Omega0 (GLGM06/reach.jl:39-40)
-            if (p0 > 0) REACH_CUDA(cudaMemsetAsync(g.Rg, 0, (size_t)p0 * ld * 8, st));
-            if (g.la > 0)
-                REACH_CUDA(cudaMemcpy2DAsync(g.Rg + (int64_t)g.a0 * ld, ld * 8, G0 + (int64_t)g.a0 * ldg0, ldg0 * 8, n * 8, g.la,
-                                             cudaMemcpyHostToDevice, st));
+            {       // R_1 = Omega0: the columns 0 .. p0-1 of archive slot 0
+                std::vector<int> iota((size_t)std::max<int64_t>(p0, 1));
+                for (int64_t j = 0; j < p0; ++j) iota[(size_t)j] = (int)j;
+                REACH_CUDA(cudaMemcpyAsync(g.Rref, iota.data(), sizeof(int) * (size_t)p0, cudaMemcpyHostToDevice, st));
+                REACH_CUDA(cudaStreamSynchronize(st));
+            }
             REACH_CUDA(cudaMemcpyAsync(g.Rc, c0, n * 8, cudaMemcpyHostToDevice, st));
             const int2 m1 = make_int2((int)p0, 0);
             REACH_CUDA(cudaMemcpyAsync(g.meta, &m1, sizeof(int2), cudaMemcpyHostToDevice, st));
@@ -2197,8 +2195,6 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
     mark();
     finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
     mark();
-    expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
-    mark();
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches += 6;
 }
@@ -2338,7 +2334,8 @@ void flowpipe_run(Flowpipe* F) {
             cudaEvent_t ev_init = next_event(F, ev_used);
             REACH_CUDA(cudaEventRecord(ev_init, st));
             REACH_CUDA(cudaStreamWaitEvent(F->cpy, ev_init, 0));
-            pack_slots_kernel<<<dim3((unsigned)ceil_div(F->sink_pmax, 8), 1u), 256, 0, F->cpy>>>(g, 1, 1, (int)F->sink_pmax, F->pack);
+            materialize_kernel<<<dim3((unsigned)ceil_div(F->sink_pmax, 8), 1u), 256, 0, F->cpy>>>(g, 1, 1, (int)F->sink_pmax, F->pack, (int)n,
+                                                                                                   n * F->sink_pmax);
             REACH_CUDA(cudaGetLastError());
             REACH_CUDA(cudaMemcpyAsync(F->sink_G, F->pack, (size_t)n * F->sink_pmax * 8, cudaMemcpyDeviceToHost, F->cpy));
         }
@@ -2409,7 +2406,7 @@ void flowpipe_run(Flowpipe* F) {
             if (F->sink_G) {        // stream this batch's reach sets to the host while the later batches are computed
                 REACH_CUDA(cudaStreamWaitEvent(F->cpy, e1, 0));
                 dim3 pg((unsigned)ceil_div(F->sink_pmax, 8), (unsigned)cnt);
-                pack_slots_kernel<<<pg, 256, 0, F->cpy>>>(g, (int)have + 1, (int)cnt, (int)F->sink_pmax, F->pack);
+                materialize_kernel<<<pg, 256, 0, F->cpy>>>(g, (int)have + 1, (int)cnt, (int)F->sink_pmax, F->pack, (int)n, n * F->sink_pmax);
                 REACH_CUDA(cudaGetLastError());
                 ctx->launches++;
                 REACH_CUDA(cudaMemcpyAsync(F->sink_G + have * n * F->sink_pmax, F->pack, (size_t)cnt * n * F->sink_pmax * 8,
@@ -2457,15 +2454,15 @@ void flowpipe_run(Flowpipe* F) {
         F->reduce_ms += t;
     }
     if (F->detail && !F->detail_ev.empty()) {
-        const char* names[6] = {"wbox_partial", "wseq", "rank_r", "apply_r", "finalize_r", "expand_diag"};
-        double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (size_t i = 0; i + 6 < F->detail_ev.size() + 0 && i + 6 < F->detail_ev.size() + 1; i += 7)
-            for (int j = 0; j < 6; ++j) {
+        const char* names[5] = {"wbox_partial", "wseq", "rank_r", "apply_r", "finalize_r"};
+        double acc[5] = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i + 5 < F->detail_ev.size(); i += 6)
+            for (int j = 0; j < 5; ++j) {
                 float t = 0;
                 cudaEventElapsedTime(&t, F->detail_ev[i + j], F->detail_ev[i + j + 1]);
                 acc[j] += t;
             }
-        for (int j = 0; j < 6; ++j) fprintf(stderr, "[reach detail] %-13s %8.3f ms in situ\n", names[j], acc[j]);
+        for (int j = 0; j < 5; ++j) fprintf(stderr, "[reach detail] %-13s %8.3f ms in situ\n", names[j], acc[j]);
         for (cudaEvent_t e : F->detail_ev) cudaEventDestroy(e);
         F->detail_ev.clear();
     }
@@ -2584,9 +2581,8 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         ctx->launches += 3;
     } else {
         finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
-        expand_diag_kernel<<<dim3(8, (unsigned)cnt), 256, 0, st>>>(g, k0, k0 + cnt);
         REACH_CUDA(cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 1;
         if (B.square_after) {
             DMat* spare[2] = {&F->PowA, &F->PowB};
             if (F->ell_levels == 0)
@@ -2713,18 +2709,33 @@ namespace {
 
 void require_ran(Flowpipe* F) { REACH_REQUIRE(F->ran, "flowpipe: call reach_glgm06_run first"); }
 
-// device pointer of reach set k (1-based): generators, centre, counts
-void locate(Flowpipe* F, int64_t k, const double** G, const double** c, int* p) {
-    REACH_REQUIRE(k >= 1 && k <= F->N, "flowpipe: step index out of range");
+// Reach sets [k0, k0 + cnt) (1-based) as dense generator matrices on the device: slab t = n x pmax, leading dimension n.
+// Homogeneous flowpipes are stored densely already (the archive IS the flowpipe); reduced ones are materialised from their
+// generator references.
+void materialize_steps(Flowpipe* F, int64_t k0, int64_t cnt, int64_t pmax, double* out, cudaStream_t st) {
+    const int64_t n = F->n;
     if (F->homog) {
-        const double* slot = F->Hflow + (k - 1) * F->q * F->ld;
-        *G = slot; *c = slot + F->p0 * F->ld; *p = (int)F->p0;
-    } else {
-        *G = F->g.Rg + (k - 1) * F->g.slot;
-        *c = F->g.Rc + (k - 1) * F->ld;
-        const int2 m = F->meta_host[k - 1];
-        *p = m.x + m.y;
+        for (int64_t t = 0; t < cnt; ++t)
+            REACH_CUDA(cudaMemcpy2DAsync(out + t * n * pmax, n * 8, F->Hflow + (k0 + t - 1) * F->q * F->ld, F->ld * 8, n * 8,
+                                         std::min<int64_t>(pmax, F->p0), cudaMemcpyDeviceToDevice, st));
+        return;
     }
+    GP g = F->g;
+    materialize_kernel<<<dim3((unsigned)ceil_div(pmax, 8), (unsigned)cnt), 256, 0, st>>>(g, (int)k0, (int)cnt, (int)pmax, out, (int)n,
+                                                                                          n * pmax);
+    REACH_CUDA(cudaGetLastError());
+    F->ctx->launches++;
+}
+
+int ngens_of(Flowpipe* F, int64_t k) {
+    REACH_REQUIRE(k >= 1 && k <= F->N, "flowpipe: step index out of range");
+    if (F->homog) return (int)F->p0;
+    const int2 m = F->meta_host[k - 1];
+    return m.x + m.y;
+}
+
+const double* center_of(Flowpipe* F, int64_t k) {
+    return F->homog ? F->Hflow + ((k - 1) * F->q + F->p0) * F->ld : F->g.Rc + (k - 1) * F->ld;
 }
 
 }  // namespace
@@ -2836,14 +2847,16 @@ int32_t reach_flowpipe_step(reach_flowpipe* fp, int64_t k, double* c, double* G,
     FP_BEGIN(fp->ctx)
     Flowpipe* F = fp->f;
     require_ran(F);
-    const double *dG, *dc;
-    int p;
-    locate(F, k, &dG, &dc, &p);
+    const int p = ngens_of(F, k);
     cudaStream_t st = F->ctx->stream;
-    if (c) REACH_CUDA(cudaMemcpyAsync(c, dc, F->n * 8, cudaMemcpyDeviceToHost, st));
+    if (c) REACH_CUDA(cudaMemcpyAsync(c, center_of(F, k), F->n * 8, cudaMemcpyDeviceToHost, st));
     if (G && p > 0) {
         REACH_REQUIRE(ldg >= F->n, "reach_flowpipe_step: ldg < n");
-        REACH_CUDA(cudaMemcpy2DAsync(G, ldg * 8, dG, F->ld * 8, F->n * 8, p, cudaMemcpyDeviceToHost, st));
+        DevScratch scr(F->ctx);
+        double* d = scr.get<double>((size_t)F->n * p);
+        materialize_steps(F, k, 1, p, d, st);
+        REACH_CUDA(cudaMemcpy2DAsync(G, ldg * 8, d, F->n * 8, F->n * 8, p, cudaMemcpyDeviceToHost, st));
+        REACH_CUDA(cudaStreamSynchronize(st));
     }
     REACH_CUDA(cudaStreamSynchronize(st));
     return REACH_OK;
@@ -2856,15 +2869,29 @@ int32_t reach_flowpipe_fetch(reach_flowpipe* fp, double* centers, double* G, int
     Flowpipe* F = fp->f;
     require_ran(F);
     cudaStream_t st = F->ctx->stream;
-    for (int64_t k = 1; k <= F->N; ++k) {
-        const double *dG, *dc;
-        int p;
-        locate(F, k, &dG, &dc, &p);
-        if (centers) REACH_CUDA(cudaMemcpyAsync(centers + (k - 1) * F->n, dc, F->n * 8, cudaMemcpyDeviceToHost, st));
-        if (G && p > 0) {
-            REACH_REQUIRE(p <= pmax, "reach_flowpipe_fetch: pmax smaller than a reach set's generator count");
-            REACH_CUDA(cudaMemcpy2DAsync(G + (k - 1) * F->n * pmax, F->n * 8, dG, F->ld * 8, F->n * 8, p,
-                                         cudaMemcpyDeviceToHost, st));
+    const int64_t n = F->n, N = F->N;
+    if (centers) {
+        if (F->homog) {
+            for (int64_t k = 1; k <= N; ++k)
+                REACH_CUDA(cudaMemcpyAsync(centers + (k - 1) * n, center_of(F, k), n * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            REACH_CUDA(cudaMemcpy2DAsync(centers, n * 8, F->g.Rc, F->ld * 8, n * 8, N, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (G) {
+        int64_t need = 0;
+        for (int64_t k = 1; k <= N; ++k) need = std::max<int64_t>(need, ngens_of(F, k));
+        REACH_REQUIRE(need <= pmax, "reach_flowpipe_fetch: pmax smaller than a reach set's generator count");
+        // whole slabs (columns beyond a set's count are zero), a chunk of steps at a time through a device staging buffer
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(256 << 20) / std::max<int64_t>(1, n * pmax * 8)));
+        DevScratch scr(F->ctx);
+        double* d = scr.get<double>((size_t)chunk * n * pmax);
+        for (int64_t k0 = 1; k0 <= N; k0 += chunk) {
+            const int64_t cnt = std::min(chunk, N - k0 + 1);
+            if (F->homog) REACH_CUDA(cudaMemsetAsync(d, 0, (size_t)cnt * n * pmax * 8, st));
+            materialize_steps(F, k0, cnt, pmax, d, st);
+            REACH_CUDA(cudaMemcpyAsync(G + (k0 - 1) * n * pmax, d, (size_t)cnt * n * pmax * 8, cudaMemcpyDeviceToHost, st));
+            REACH_CUDA(cudaStreamSynchronize(st));       // the staging buffer is reused by the next chunk
         }
     }
     REACH_CUDA(cudaStreamSynchronize(st));
@@ -2877,20 +2904,18 @@ int32_t reach_flowpipe_box(reach_flowpipe* fp, int64_t k, double* lo, double* hi
     FP_BEGIN(fp->ctx)
     Flowpipe* F = fp->f;
     require_ran(F);
-    const double *dG, *dc;
-    int p;
-    locate(F, k, &dG, &dc, &p);
+    const int p = ngens_of(F, k);
     cudaStream_t st = F->ctx->stream;
-    if (!F->stage) {
-        REACH_CUDA(cudaMalloc(&F->stage, 2 * F->n * 8));
-        F->owned.push_back(F->stage);
-    }
-    zono_box_kernel<<<dim3((unsigned)ceil_div(F->n, 256), 1), 256, 0, st>>>((int)F->n, (int)F->ld, p, 0, 1, dG, dc, 0,
-                                                                             F->stage, F->stage + F->n);
+    DevScratch scr(F->ctx);
+    double* d = scr.get<double>((size_t)F->n * std::max(p, 1));
+    double* stage = scr.get<double>((size_t)2 * F->n);
+    materialize_steps(F, k, 1, p, d, st);
+    zono_box_kernel<<<dim3((unsigned)ceil_div(F->n, 256), 1), 256, 0, st>>>((int)F->n, (int)F->n, p, 0, 1, d, center_of(F, k), 0, stage,
+                                                                             stage + F->n);
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches++;
-    REACH_CUDA(cudaMemcpyAsync(lo, F->stage, F->n * 8, cudaMemcpyDeviceToHost, st));
-    REACH_CUDA(cudaMemcpyAsync(hi, F->stage + F->n, F->n * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaMemcpyAsync(lo, stage, F->n * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaMemcpyAsync(hi, stage + F->n, F->n * 8, cudaMemcpyDeviceToHost, st));
     REACH_CUDA(cudaStreamSynchronize(st));
     return REACH_OK;
     FP_END(fp->ctx)
@@ -2923,10 +2948,10 @@ int32_t reach_flowpipe_project(reach_flowpipe* fp, int64_t q, const double* M, i
             in.G = F->Hflow; in.slot = F->q * F->ld; in.c = F->Hflow + F->p0 * F->ld; in.cstride = F->q * F->ld;
             in.meta = nullptr; in.p_const = (int)F->p0;
         } else {
-            in.G = F->g.Rg; in.slot = F->g.slot; in.c = F->g.Rc; in.cstride = F->ld; in.meta = F->g.meta; in.p_const = 0;
+            in.G = nullptr; in.slot = 0; in.c = F->g.Rc; in.cstride = F->ld; in.meta = F->g.meta; in.p_const = 0;
         }
         in.n = (int)n; in.ld = (int)F->ld; in.q = (int)q; in.pmax = (int)pmax; in.N = (int)N;
-        project_gens_kernel<<<dim3((unsigned)ceil_div(pmax, 8), (unsigned)N), 256, 0, st>>>(in, dM, dG);
+        project_gens_kernel<<<dim3((unsigned)ceil_div(pmax, 8), (unsigned)N), 256, 0, st>>>(in, F->g, dM, dG);
         REACH_CUDA(cudaGetLastError());
         project_box_kernel<<<(unsigned)N, 256, 0, st>>>(in, dM, dG, dcr, dcr + q * N);
         REACH_CUDA(cudaGetLastError());
