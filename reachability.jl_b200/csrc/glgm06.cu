@@ -1051,41 +1051,45 @@ __device__ __forceinline__ WseqIn wseq_load(const GP& g, int k0, int t, int i) {
     return w;
 }
 // Steady state (the parallel chain handled the batch): every step boxes exactly the n box generators of the previous step, so
-// d_k = base_k + |d_{k-1}| and the recurrences need no indirection.  One thread per row: the loads of 16 steps are independent
-// and issued together, the sums run in registers in the sequential kernel's order (identical bits).
-__global__ void __launch_bounds__(128) wseq_fast_kernel(GP g, int k0, int cnt) {
+// d_k = base_k + |d_{k-1}| and the recurrences need no indirection.  One WARP per row, lanes = steps: the loads of 32 steps are
+// issued at once (one round trip to memory instead of one per step), the sums then run lane by lane in the sequential
+// kernel's order (identical bits).
+__global__ void __launch_bounds__(256) wseq_fast_kernel(GP g, int k0, int cnt) {
     if (*g.fastFlag == 0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= g.n) return;
     double cw = g.cW[i];
     double d = g.Wd[(int64_t)(k0 - 1) * g.ld + i];
-    constexpr int CH = 16;
-    for (int t0 = 0; t0 < cnt; t0 += CH) {
-        double base[CH], yc0[CH], ycV[CH];
+    for (int t0 = 0; t0 < cnt; t0 += 32) {
+        const int t = t0 + lane;
+        double base = 0.0, yc0 = 0.0, ycV = 0.0;
+        if (t < cnt) {
+            double pb[NBW];
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int t = t0 + u;
-            base[u] = 0.0; yc0[u] = 0.0; ycV[u] = 0.0;
-            if (t < cnt) {
-                for (int b = 0; b < NBW; ++b) base[u] += g.partW[((int64_t)t * NBW + b) * g.ld + i];
-                const double* yc = g.Y + (int64_t)(t * g.qloc + g.la + g.lc) * g.ld;
-                yc0[u] = yc[i];
-                ycV[u] = yc[g.ld + i];
-            }
+            for (int b = 0; b < NBW; ++b) pb[b] = g.partW[((int64_t)t * NBW + b) * g.ld + i];
+            const double* yc = g.Y + (int64_t)(t * g.qloc + g.la + g.lc) * g.ld;
+            yc0 = yc[i];
+            ycV = yc[g.ld + i];
+#pragma unroll
+            for (int b = 0; b < NBW; ++b) base += pb[b];
         }
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int t = t0 + u;
-            if (t < cnt) {
-                const int k = k0 + t;
-                g.Rc[(int64_t)(k - 1) * g.ld + i] = yc0[u] + cw;
-                cw += ycV[u];
-                d = base[u] + fabs(d);
-                g.Wd[(int64_t)k * g.ld + i] = d;
-            }
+        double my_c = 0.0, my_d = 0.0;
+        const int m = min(32, cnt - t0);
+        for (int u = 0; u < m; ++u) {                       // the recurrences, in step order
+            const double bu = __shfl_sync(0xffffffffu, base, u), y0 = __shfl_sync(0xffffffffu, yc0, u),
+                         yV = __shfl_sync(0xffffffffu, ycV, u);
+            const double cu = y0 + cw;
+            cw += yV;
+            d = bu + fabs(d);
+            if (lane == u) { my_c = cu; my_d = d; }
+        }
+        if (t < cnt) {
+            const int k = k0 + t;
+            g.Rc[(int64_t)(k - 1) * g.ld + i] = my_c;
+            g.Wd[(int64_t)k * g.ld + i] = my_d;
         }
     }
-    g.cW[i] = cw;
+    if (lane == 0) g.cW[i] = cw;
 }
 
 __global__ void __launch_bounds__(128) wseq_kernel(GP g, int k0, int cnt) {
@@ -2177,7 +2181,7 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
     else if (it == 8) wbox_partial_kernel<8><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     else wbox_partial_kernel<16><<<dim3(NBW, (unsigned)cnt), NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
     mark();
-    wseq_fast_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
+    wseq_fast_kernel<<<(unsigned)ceil_div(F->n * 32, 256), 256, 0, st>>>(g, k0, cnt);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     mark();
     if (rank_st && rank_st != st) {
@@ -2570,7 +2574,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 2;
     } else if (phase == 2) {
-        wseq_fast_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
+        wseq_fast_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(g, k0, cnt);
         wseq_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(g, k0, cnt);
         rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
         const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
