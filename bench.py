@@ -36,10 +36,11 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-# dram bytes (read + write) of the HBM-side GLGM06 kernels per flowpipe step at C2, from ncu --set full captures of one 64-step batch:
-# ell_left_score 340 MB + apply_r 452 MB + wbox_partial 38 MB + the small ones ~10 MB = 840 MB / 64 steps
-C2_REAL_BYTES_PER_STEP = 840.0e6 / 64
-C2_REAL_BYTES_SOURCE = "profiles/r01/ncu_glgm06_c2_v4_summary.txt"
+# dram bytes (read + write) of the HBM-side GLGM06 kernels per flowpipe step at C2, from ncu --set full captures of one 64-step batch
+# (round 2: reach sets are generator references, nothing is copied into dense slots any more):
+# ell_left_score 335.2 MB + apply_r 72.0 MB + wbox_partial 38.2 MB + rank_r 3.8 + finalize_r 1.1 + sort / chain / wseq 2.0 = 452 MB / 64 steps
+C2_REAL_BYTES_PER_STEP = 452.3e6 / 64
+C2_REAL_BYTES_SOURCE = "profiles/r02/ncu_c2_summary.txt"
 FP64_DMMA_PEAK_TFLOPS = 37.06   # measured on this pool's B200: tools/fp64_peak.cu -> profiles/r01/fp64_peak_b200.jsonl
 METRIC = "flowpipe steps/s (n=1006 BFFPSV18, n=270 GLGM06) at 1/2/4/8 B200 vs CPU"
 
@@ -545,8 +546,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
     real_bytes = C2_REAL_BYTES_PER_STEP * flow_steps
     hbm_side_ms = alone["gemm_ms"] + alone["numerics_ms"] if map_info["sparse_levels"] > 0 else alone["numerics_ms"]
     real_gbs = real_bytes / (hbm_side_ms * 1e-3) / 1e9 if hbm_side_ms > 0 else None
-    numerics = {"kernel": "HBM-side kernels of a flowpipe: generator map fused with the Girard scores (ell_left_score) + batched numerics "
-                          "of the two reductions (wbox_partial, wseq, rank_r, apply_r [TMA-staged gather], finalize_r, expand_diag)",
+    numerics = {"kernel": "HBM-side kernels of a flowpipe: generator map fused with the Girard scores (ell_left_score, TMA-staged) + batched "
+                          "numerics of the two reductions (wbox_partial, wseq, rank_r, apply_r, finalize_r)",
                 "bound": "hbm", "achieved": real_gbs, "peak": hbm, "unit": "GB/s",
                 "frac": real_gbs / hbm if real_gbs else None, "peak_source": hbm_src,
                 "traffic": C2_REAL_BYTES_PER_STEP * 64, "traffic_unit": "bytes per 64-step batch (ncu dram read + write, " + C2_REAL_BYTES_SOURCE + ")",
@@ -554,10 +555,13 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                 "algorithmic": {"bytes_per_flowpipe_step": glgm06_algorithmic_bytes_per_step(n, p0, pV, r),
                                 "gbs_by_survey_8d_bytes": alg_bytes / red_s / 1e9 if red_s > 0 else None,
                                 "note": "SURVEY 8(d) counts 40.9 MB per step (score pass + gather pass + write of both reductions); the "
-                                        "archive/reference design moves about a third of that (W is never rewritten, scores travel with "
-                                        "the references, box generators are tags) -- an algorithmic saving, not bandwidth"},
-                "note": "the flowpipe is NOT HBM-bound end to end: the selection chain (one CTA) is the critical path, see selection_chain"}
-    chain = {"kernel": "chain_kernel (one persistent CTA on its own SM, key logic only)", "kernel_ms_total": tt["chain_ms"],
+                                        "archive/reference design moves 7.1 MB (W and R_k are never rewritten -- reach sets are lists of "
+                                        "generator references into the archive, scores travel with the references, box generators are "
+                                        "tags) -- an algorithmic saving, not bandwidth"},
+                "note": "in the pipelined run the HBM-side kernels share the GPU with the latency-bound ones (segment sort, selection "
+                        "chain, box recurrence); the dense n x p matrix of a reach set is materialised by the fetch / projection kernels"}
+    chain = {"kernel": "selection chain: chain_decide + chain_fast (parallel, one warp per generator) + chain_fast_fill in the steady state, "
+                       "chain_kernel (one persistent CTA, sequential merge) in the growth phase", "kernel_ms_total": tt["chain_ms"],
              "us_per_flowpipe_step": 1e3 * tt["chain_ms"] / (flow_steps * args.steps)}
     alone_obj = {"note": "one extra flowpipe with all kernels serialised on one stream (not timed into `value`)",
                  "map_ms": alone["gemm_ms"], "numerics_ms": alone["numerics_ms"], "chain_ms": alone["chain_ms"],

@@ -47,14 +47,16 @@ constexpr int COPY_CTAS = 8;        // CTAs per step that record the references 
 constexpr int COPY_JB = 8;          // columns a warp resolves (one per lane) and then moves back to back
 constexpr int NUM_WARPS = 4;        // warps per CTA of the TMA-staged numerics kernels (wbox_partial, apply_r)
 constexpr int STAGE_BYTES = 16384;  // staging per warp: JB = min(8, STAGE_BYTES / column bytes) columns in flight
-constexpr int MAX_IT = 16;          // double2 per lane: rows <= 32*2*16 = 1024
+constexpr int MAX_IT = 16;          // double2 per lane of a row WINDOW: the numerics kernels sweep the rows 1024 at a time
+constexpr int WIN_ROWS = 64 * MAX_IT;   // rows per window
+constexpr int CHAIN_MAX_IT = 64;    // the sequential selection chain keeps per-row state in shared memory: n <= 64 * 64 = 4096
 #ifndef REACH_CHAIN_THREADS
 #define REACH_CHAIN_THREADS 512
 #endif
 // threads of the single selection-chain CTA (it owns an SM in the pipelined run): C2 chain time 10.8 ms with 256 threads,
 // 9.7 ms with 512, 11.2 ms with 1024 (-DREACH_CHAIN_THREADS=... to rebuild)
 constexpr int CHAIN_THREADS = REACH_CHAIN_THREADS;
-constexpr int CHAIN_ROWS = 64 * MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
+constexpr int CHAIN_ROWS = 64 * CHAIN_MAX_IT / CHAIN_THREADS;   // rows per thread when a loop runs over the n rows
 
 struct PlanW { int mode, pin, m, pW, pC, nk, nd, z; };     // W reduction of step k  (GLGM06/reach.jl:54-55)
 struct PlanR { int mode, pin, m, pA, pW, pad0, pad1, pad2; };   // R reduction of step k  (:48-49)
@@ -353,8 +355,8 @@ __device__ unsigned long long g_chain_prof[8];
 template <bool SMEM, bool RECORD>
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) chain_kernel(GP g, int k0, int cnt, double* scr) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
-    __shared__ unsigned orm[2 * MAX_IT];
-    __shared__ int tc_s[64 * MAX_IT];          // per row: box generators boxed again in this step
+    __shared__ unsigned orm[2 * CHAIN_MAX_IT];
+    __shared__ int tc_s[64 * CHAIN_MAX_IT];    // per row: box generators boxed again in this step
     __shared__ int rows_s[CHAIN_ROWS * (CHAIN_THREADS / 32)];
     __shared__ int s_pC[128], s_zC[128];
     __shared__ int s_nd;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
         int* dl = g.dlistW + (int64_t)t * g.capDisc;
         CHAIN_TICK(0);
         // ---- A: the box generators of W (score 0, hence sigma = rank) that are boxed again ----
-        if (tid < 2 * MAX_IT) orm[tid] = 0u;
+        if (tid < 2 * CHAIN_MAX_IT) orm[tid] = 0u;
         for (int i = tid; i < g.n; i += CHAIN_THREADS) tc_s[i] = 0;
         if (tid == 0) {             // sentinels for the merge of this step
             const_cast<WEnt*>(ec)[pW] = WEnt{INFINITY, 0, 0};
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
             // Row-support union of the boxed generators.  The boxed box generators alone usually cover every row
             // (steady state); only otherwise are the dense ones located (binary search) and their masks fetched.
             if (wid == 0) {
-                int c = lane < g.nwords ? __popc(orm[lane]) : 0;
-                if (g.nwords > 32) c += (lane + 32 < g.nwords) ? __popc(orm[lane + 32]) : 0;
+                int c = 0;
+                for (int w = lane; w < g.nwords; w += 32) c += __popc(orm[w]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
                 if (lane == 0) s_nd = c;
@@ -480,16 +482,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_THREADS <= 256 ? 3 : 1) c
                             mk = g.maskAll + ((g.col0 / g.q + t) * (int64_t)pV + cOrd[jc]) * g.nwords4;
                     }
                     if (mk) {
-                        uint4 v[2 * MAX_IT / 4];
-#pragma unroll
-                        for (int u = 0; u < 2 * MAX_IT / 4; ++u)
-                            v[u] = u < nw4 ? reinterpret_cast<const uint4*>(mk)[u] : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int u = 0; u < 2 * MAX_IT / 4; ++u) {
-                            if (v[u].x) atomicOr(&orm[4 * u + 0], v[u].x);
-                            if (v[u].y) atomicOr(&orm[4 * u + 1], v[u].y);
-                            if (v[u].z) atomicOr(&orm[4 * u + 2], v[u].z);
-                            if (v[u].w) atomicOr(&orm[4 * u + 3], v[u].w);
+#pragma unroll 4
+                        for (int u = 0; u < nw4; ++u) {
+                            const uint4 v = reinterpret_cast<const uint4*>(mk)[u];
+                            if (v.x) atomicOr(&orm[4 * u + 0], v.x);
+                            if (v.y) atomicOr(&orm[4 * u + 1], v.y);
+                            if (v.z) atomicOr(&orm[4 * u + 2], v.z);
+                            if (v.w) atomicOr(&orm[4 * u + 3], v.w);
                         }
                     }
                 }
@@ -870,52 +869,31 @@ __device__ __forceinline__ void acc_zero(Acc<IT>& a) {
 #pragma unroll
     for (int i = 0; i < IT; ++i) a.v[i] = make_double2(0.0, 0.0);
 }
-// a += |column ref|  (dense archive column, or the single entry of a box generator when with_tags)
-template <int IT>
-__device__ __forceinline__ void acc_add(const GP& g, Acc<IT>& a, int ref, int lane, bool with_tags) {
-    const int n2 = g.ld / 2;
-    if (ref >= 0) {
-        const double2* c2 = reinterpret_cast<const double2*>(col_ptr(g, ref));
-        if (c2 == nullptr) return;                // another rank sums this generator (partials are all-reduced)
-#pragma unroll
-        for (int i = 0; i < IT; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < n2) {
-                const double2 v = c2[idx];
-                a.v[i].x += fabs(v.x);
-                a.v[i].y += fabs(v.y);
-            }
-        }
-    } else if (with_tags && g.rank == 0) {        // box generators are replicated: rank 0 accounts for them
-        int kt, it;
-        tag_decode(ref, g.n, kt, it);
-        const double val = fabs(g.Wd[(int64_t)kt * g.ld + it]);
-        const int idx = it >> 1;
-#pragma unroll
-        for (int i = 0; i < IT; ++i)
-            if (lane + 32 * i == idx) {
-                if (it & 1) a.v[i].y += val; else a.v[i].x += val;
-            }
-    }
-}
+// The rows are swept in WINDOWS of WIN_ROWS (one window for n <= 1024): an accumulator covers rows [rbase, rbase + wl).
+struct Win {
+    int rbase, wl;
+};
+__device__ __forceinline__ int win_pitch(const GP& g) { return min(g.ld, WIN_ROWS); }     // column pitch of the shared-memory stages
+__device__ __forceinline__ Win win_at(const GP& g, int rbase) { return Win{rbase, min(WIN_ROWS, g.ld - rbase)}; }
 // CTA-wide sum of the warps' accumulators in warp order -> out[0 .. ld)
 template <int IT>
-__device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc<IT>& a, double* red_s, double* __restrict__ out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n2 = g.ld / 2, nw = blockDim.x >> 5;
+__device__ __forceinline__ void acc_reduce_store(const GP& g, const Acc<IT>& a, double* red_s, double* __restrict__ out, const Win& win) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n2 = win.wl / 2, nw = blockDim.x >> 5, pitch = win_pitch(g);
 #pragma unroll
     for (int i = 0; i < IT; ++i) {
         const int idx = lane + 32 * i;
         if (idx < n2) {
-            red_s[warp * g.ld + 2 * idx] = a.v[i].x;
-            red_s[warp * g.ld + 2 * idx + 1] = a.v[i].y;
+            red_s[warp * pitch + 2 * idx] = a.v[i].x;
+            red_s[warp * pitch + 2 * idx + 1] = a.v[i].y;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < g.ld; i += blockDim.x) {
+    for (int i = threadIdx.x; i < win.wl; i += blockDim.x) {
         double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += red_s[w * g.ld + i];
-        out[i] = s;
+        for (int w = 0; w < nw; ++w) s += red_s[w * pitch + i];
+        out[win.rbase + i] = s;
     }
+    __syncthreads();        // the scratch is free for the next window
 }
 
 // ---- TMA-staged column access ------------------------------------------------------------------------------------
@@ -932,8 +910,8 @@ struct WarpStage {
 __device__ __forceinline__ WarpStage warp_stage_init(const GP& g, unsigned char* smem, int jb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpStage ws;
-    ws.buf = reinterpret_cast<double*>(smem) + (size_t)warp * jb * g.ld;
-    ws.bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * g.ld) + warp;
+    ws.buf = reinterpret_cast<double*>(smem) + (size_t)warp * jb * win_pitch(g);
+    ws.bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * win_pitch(g)) + warp;
     ws.phase = 0;
     if (lane == 0) mbar_init(ws.bar, 1);
     mbar_fence_init();
@@ -942,15 +920,15 @@ __device__ __forceinline__ WarpStage warp_stage_init(const GP& g, unsigned char*
 }
 // scratch of acc_reduce_store behind the stages and barriers
 __device__ __forceinline__ double* stage_red(const GP& g, unsigned char* smem, int jb) {
-    return reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * g.ld + NUM_WARPS;
+    return reinterpret_cast<double*>(smem) + (size_t)NUM_WARPS * jb * win_pitch(g) + NUM_WARPS;
 }
 // Lane j < jb holds column pointer `src` (or nullptr): start the bulk loads of the warp's group.  Returns the ballot.
-__device__ __forceinline__ unsigned stage_load(const GP& g, WarpStage& ws, const double* src, int lane) {
+__device__ __forceinline__ unsigned stage_load(const GP& g, WarpStage& ws, const double* src, int lane, const Win& win) {
     const unsigned dense = __ballot_sync(0xffffffffu, src != nullptr);
     if (dense) {
-        if (lane == 0) mbar_expect_tx(ws.bar, (uint32_t)(__popc(dense) * g.ld * 8));
+        if (lane == 0) mbar_expect_tx(ws.bar, (uint32_t)(__popc(dense) * win.wl * 8));
         __syncwarp();
-        if (src) bulk_g2s(ws.buf + (size_t)lane * g.ld, src, (uint32_t)(g.ld * 8), ws.bar);
+        if (src) bulk_g2s(ws.buf + (size_t)lane * win_pitch(g), src + win.rbase, (uint32_t)(win.wl * 8), ws.bar);
     }
     return dense;
 }
@@ -960,12 +938,12 @@ __device__ __forceinline__ void stage_wait(WarpStage& ws) {
 }
 // a += |staged column j| for every j of `dense`, in lane order
 template <int IT>
-__device__ __forceinline__ void acc_add_staged(const GP& g, Acc<IT>& a, const WarpStage& ws, unsigned dense, int lane) {
-    const int n2 = g.ld / 2;
+__device__ __forceinline__ void acc_add_staged(const GP& g, Acc<IT>& a, const WarpStage& ws, unsigned dense, int lane, const Win& win) {
+    const int n2 = win.wl / 2;
     for (unsigned rest = dense; rest;) {
         const int j = __ffs(rest) - 1;
         rest &= rest - 1;
-        const double2* c2 = reinterpret_cast<const double2*>(ws.buf + (size_t)j * g.ld);
+        const double2* c2 = reinterpret_cast<const double2*>(ws.buf + (size_t)j * win_pitch(g));
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
             const int idx = lane + 32 * i;
@@ -980,12 +958,13 @@ __device__ __forceinline__ void acc_add_staged(const GP& g, Acc<IT>& a, const Wa
 }
 // a += |box generator (tval at row trow)| of the lanes in `tags`, in lane order
 template <int IT>
-__device__ __forceinline__ void acc_add_tags(Acc<IT>& a, unsigned tags, double tval, int trow, int lane) {
+__device__ __forceinline__ void acc_add_tags(Acc<IT>& a, unsigned tags, double tval, int trow, int lane, const Win& win) {
     for (unsigned rest = tags; rest;) {
         const int j = __ffs(rest) - 1;
         rest &= rest - 1;
         const double val = fabs(__shfl_sync(0xffffffffu, tval, j));
-        const int it = __shfl_sync(0xffffffffu, trow, j);
+        const int it = __shfl_sync(0xffffffffu, trow, j) - win.rbase;
+        if (it < 0 || it >= win.wl) continue;           // the box generator's row lies in another window
         const int idx = it >> 1;
 #pragma unroll
         for (int i = 0; i < IT; ++i)
@@ -1003,26 +982,29 @@ __global__ void __launch_bounds__(NUM_WARPS * 32) wbox_partial_kernel(GP g, int 
     const PlanW pl = g.planW[k0 + t];
     double* out = g.partW + ((int64_t)t * NBW + b) * g.ld;
     WarpStage ws = warp_stage_init(g, smem_raw, jb);
-    Acc<IT> a;
-    acc_zero(a);
-    if (pl.mode == MODE_REDUCE) {
-        const int chunk = (pl.m + NBW - 1) / NBW;
-        const int lo = b * chunk, hi = min(pl.m, lo + chunk);
-        const int* dl = g.dlistW + (int64_t)t * g.capDisc;
-        const int wchunk = (chunk + NUM_WARPS - 1) / NUM_WARPS;
-        const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
-        for (int s0 = wlo; s0 < whi; s0 += jb) {
-            const int ref = (lane < jb && s0 + lane < whi) ? dl[s0 + lane] : -1;     // box generators are wseq's business
-            const double* src = ref >= 0 ? col_ptr(g, ref) : nullptr;   // nullptr: another rank sums it (partials are all-reduced)
-            const unsigned dense = stage_load(g, ws, src, lane);
-            if (dense) {
-                stage_wait(ws);
-                acc_add_staged(g, a, ws, dense, lane);
+    for (int rbase = 0; rbase < g.ld; rbase += WIN_ROWS) {
+        const Win win = win_at(g, rbase);
+        Acc<IT> a;
+        acc_zero(a);
+        if (pl.mode == MODE_REDUCE) {
+            const int chunk = (pl.m + NBW - 1) / NBW;
+            const int lo = b * chunk, hi = min(pl.m, lo + chunk);
+            const int* dl = g.dlistW + (int64_t)t * g.capDisc;
+            const int wchunk = (chunk + NUM_WARPS - 1) / NUM_WARPS;
+            const int wlo = lo + warp * wchunk, whi = min(hi, wlo + wchunk);
+            for (int s0 = wlo; s0 < whi; s0 += jb) {
+                const int ref = (lane < jb && s0 + lane < whi) ? dl[s0 + lane] : -1;     // box generators are wseq's business
+                const double* src = ref >= 0 ? col_ptr(g, ref) : nullptr;   // nullptr: another rank sums it (partials are all-reduced)
+                const unsigned dense = stage_load(g, ws, src, lane, win);
+                if (dense) {
+                    stage_wait(ws);
+                    acc_add_staged(g, a, ws, dense, lane, win);
+                }
             }
         }
+        __syncthreads();
+        acc_reduce_store(g, a, stage_red(g, smem_raw, jb), out, win);
     }
-    __syncthreads();
-    acc_reduce_store(g, a, stage_red(g, smem_raw, jb), out);
 }
 
 // Sequential over the steps of the batch, parallel over rows: W box vectors (dense partials + discarded box
@@ -1202,9 +1184,10 @@ __global__ void __launch_bounds__(NUM_WARPS * 32) apply_r_kernel(GP g, int k0, i
     const PlanR pl = g.planR[k];
     const int* order = g.orderR + (int64_t)t * g.capListR;
     const WEnt* sn = g.snEnt + (int64_t)t * g.capW;
-    const int n2 = g.ld / 2;
     WarpStage ws = warp_stage_init(g, smem_raw, jb);
     if (blockIdx.x < NBR) {
+      for (int rbase = 0; rbase < g.ld; rbase += WIN_ROWS) {
+        const Win win = win_at(g, rbase);
         Acc<IT> a;
         acc_zero(a);
         if (pl.mode == MODE_REDUCE) {
@@ -1221,7 +1204,7 @@ __global__ void __launch_bounds__(NUM_WARPS * 32) apply_r_kernel(GP g, int k0, i
                     ref = code < g.p0 ? (int)(g.col0 + t * g.q + code) : sn[code - g.p0].ref;
                 }
                 const double* src = (ref != NO_JOB && ref >= 0) ? col_ptr(g, ref) : nullptr;
-                const unsigned dense = stage_load(g, ws, src, lane);
+                const unsigned dense = stage_load(g, ws, src, lane, win);
                 double tval = 0.0;
                 int trow = -1;
                 const bool is_tag = ref != NO_JOB && ref < 0 && g.rank == 0;   // box generators are replicated: rank 0 accounts for them
@@ -1233,14 +1216,15 @@ __global__ void __launch_bounds__(NUM_WARPS * 32) apply_r_kernel(GP g, int k0, i
                 const unsigned tags = __ballot_sync(0xffffffffu, is_tag);
                 if (dense) {
                     stage_wait(ws);
-                    acc_add_staged(g, a, ws, dense, lane);
+                    acc_add_staged(g, a, ws, dense, lane, win);
                 }
-                acc_add_tags(a, tags, tval, trow, lane);
+                acc_add_tags(a, tags, tval, trow, lane, win);
             }
         }
         __syncthreads();
-        acc_reduce_store(g, a, stage_red(g, smem_raw, jb), g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld);
-        return;
+        acc_reduce_store(g, a, stage_red(g, smem_raw, jb), g.partR + ((int64_t)t * NBR + blockIdx.x) * g.ld, win);
+      }
+      return;
     }
     // the kept generators of R_k: their references, in the order of the reduced zonotope (sortperm order)
     int* rr = g.Rref + (int64_t)(k - 1) * g.capR;
@@ -1852,8 +1836,8 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
     REACH_REQUIRE(pV >= 0 && (pV == 0 || (GV && ldgv >= n)), "glgm06: bad input zonotope");
     if (!homog && max_order < 1)
         throw Error(REACH_EUNSUPPORTED, "glgm06: max_order < 1 (reduce_order never reduces; unbounded growth) is not supported");
-    if (!homog && n > 64 * MAX_IT)
-        throw Error(REACH_EUNSUPPORTED, "glgm06: inhomogeneous path supports n <= 1024 in this build");
+    if (!homog && n > 64 * CHAIN_MAX_IT)
+        throw Error(REACH_EUNSUPPORTED, "glgm06: inhomogeneous path supports n <= 4096 in this build");
     Flowpipe* F = new Flowpipe();
     try {
         F->ctx = ctx; F->n = n; F->p0 = p0; F->pV = pV; F->N = N; F->r = max_order; F->flags = flags;
@@ -2150,9 +2134,13 @@ static void bind_set(GP& g, const GP& h) {
 }
 
 // columns per warp stage and dynamic shared memory of the TMA-staged numerics kernels: stages | mbarriers | reduction scratch
-static int numerics_jb(int64_t ld) { return (int)std::max<int64_t>(1, std::min<int64_t>(COPY_JB, STAGE_BYTES / (ld * 8))); }
+static int numerics_jb(int64_t ld) {
+    const int64_t pitch = std::min<int64_t>(ld, WIN_ROWS);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(COPY_JB, STAGE_BYTES / (pitch * 8)));
+}
 static size_t numerics_smem(int64_t ld, int jb) {
-    return (size_t)NUM_WARPS * jb * ld * 8 + NUM_WARPS * sizeof(uint64_t) + (size_t)NUM_WARPS * ld * 8;
+    const int64_t pitch = std::min<int64_t>(ld, WIN_ROWS);
+    return (size_t)NUM_WARPS * jb * pitch * 8 + NUM_WARPS * sizeof(uint64_t) + (size_t)NUM_WARPS * pitch * 8;
 }
 
 // selection chain of steps [k0, k0 + cnt) (their slots k-1 are in the archive already) ...

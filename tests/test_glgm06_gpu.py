@@ -245,6 +245,31 @@ def test_long_w_list_uses_global_scratch(ctx):
     fp.close()
 
 
+@pytest.mark.parametrize("n,m,N,r,dense", [(1100, 2, 7, 2, True), (1500, 3, 6, 3, True), (1040, 2, 12, 2, False)])
+def test_state_dimension_above_1024(ctx, n, m, N, r, dense):
+    """GLGM06/reach.jl:30-62 has no limit on n.  The numerics kernels sweep the rows in windows of 1024, the sequential
+    selection chain keeps per-row state for up to 4096 rows; the structured case (decoupled modes, inputs entering two rows)
+    keeps zero-generator removal active with more than 32 mask words per generator."""
+    A, X0, B, U, delta = _problem(800 + n, n, m, dense=dense)
+    if not dense:
+        B = np.zeros((n, m)); B[1, 0] = 1.0; B[n // 2 | 1, 1] = -0.5
+        X0.r[n // 2:] = 0.0
+    D, Om, R, sels = _oracle(A, X0, B, U, delta, N, r, True)
+    fp = _device(ctx, D, Om, N, r, True)
+    _compare(fp, R, sels, N)
+    lo, hi = fp.box(N)
+    rad = np.abs(R[-1].G).sum(axis=1)
+    assert_close(lo, R[-1].c - rad, "box lo")
+    M = np.zeros((2, n)); M[0, n - 1] = 1.0; M[1] = np.random.default_rng(2).standard_normal(n)
+    Cp, Rp = fp.project(M)
+    assert_close(Rp[:, N - 1], np.abs(M @ R[-1].G).sum(axis=1), "projected radius")
+    fp.close()
+    from reachability_jl_b200 import ReachError
+    with pytest.raises(ReachError) as ei:               # the documented ceiling of this build
+        ctx.glgm06(np.eye(4100), np.zeros(4100), np.eye(4100), 3, 2, np.zeros(4100), np.eye(4100), 0)
+    assert ei.value.code == 3
+
+
 def test_config_c2_full_size_properties(ctx):
     """BASELINE.json configs[1] at full size (n = 270, max_order 10, N = 2000, 2700 generators per reach set, 11.7 GB):
     (a) the first 120 reach sets -- growth phase, first reductions, steady state -- equal the oracle's entry by entry;
