@@ -106,6 +106,16 @@ REACH_API int32_t reach_discretize_zonotope(reach_ctx* ctx, int64_t n, const dou
                                     double* c0, double* G0, int64_t ldg0, int64_t* p0, double* cV, double* GV, int64_t ldgv,
                                     int64_t* pV);
 
+/* Time-varying inputs (`VaryingInput`; discretize.jl:690-696 with lazy sets, :729-737 with zonotopes): for the K input boxes
+ * U_k = B * Box(cUs[:, k], rUs[:, k]) (B n x m, NULL with m == n: identity) the bloating terms
+ *   Eψ_k = sih(Φ₂(|A|, δ) * sih(A * U_k)),   radius rpsi[:, k] = Φ₂(|A|, δ) (|A B cU_k| + |A B| rU_k)      (n x K, ld ldrpsi),
+ * for all k at once (three thin DMMA GEMMs).  MU (may be NULL) receives δ B; the discretised input of step k is
+ * Ud[k] = MU * Box(cU_k, rU_k) ⊕ Box(0, rpsi[:, k]).  (The reference's reach kernels themselves take a ConstantInput only,
+ * reach_blocks.jl:137, GLGM06/reach.jl:32.) */
+REACH_API int32_t reach_discretize_inputs_box(reach_ctx* ctx, int64_t n, const double* A, int64_t lda, double delta, int64_t m,
+                                      const double* B, int64_t ldb, int64_t K, const double* cUs, int64_t ldcu,
+                                      const double* rUs, int64_t ldru, double* rpsi, int64_t ldrpsi, double* MU);
+
 /* ---- BFFPSV18: dense reach_blocks! (BFFPSV18/reach_blocks.jl:135-224) ---------------------------------- */
 /* One-shot host-buffer call = the method the shim adds for
  *   reach_blocks!(ϕ::Matrix{Float64}, Xhat0::Vector{<:Union{Interval,Hyperrectangle}}, U, ..., res)

@@ -294,6 +294,21 @@ def _bloating(A, Phi, X0: Box, delta, algorithm, B=None, U: Optional[Box] = None
     return Phi2abs, rE, rpsi
 
 
+def discretize_varying_inputs(A, delta: float, B, Us: Sequence[Box], Phi2abs=None):
+    """``VaryingInput`` branch of the interpolation models (discretize.jl:690-696 lazy, :729-737 zonotope): for every
+    input set ``Uk`` of the sequence, ``Eψk = sih(Phi2Aabs * sih(A * Uk))`` and ``Ud[k] = δ*Uk ⊕ Eψk``.  Returns the
+    list of radii of Eψk (centre 0); δB is shared by all k."""
+    A = np.asarray(A, dtype=np.float64)
+    if Phi2abs is None:
+        Phi2abs = Phi2(np.abs(A), delta)
+    AB = A @ B if B is not None else A
+    out = []
+    for Uk in Us:
+        s = np.abs(AB @ Uk.c) + np.abs(AB) @ Uk.r             # sih(A * Uk)
+        out.append(Phi2abs @ s)                               # sih(Phi2Aabs * ...): Φ₂(|A|) >= 0
+    return out
+
+
 def discretize_box(A, X0: Box, delta: float, B=None, U: Optional[Box] = None,
                    algorithm: str = "forward", Phi=None, Phi2abs=None) -> DiscreteBoxProblem:
     """``discretize(IVP, δ; algorithm="forward"|"backward", set_operations="lazy")`` followed by the box

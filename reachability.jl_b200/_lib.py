@@ -45,6 +45,8 @@ _SIGNATURES = {
     "reach_discretize_zonotope": [vp, i64, c_double_p, i64, f64, i32, c_double_p, c_double_p, i64, c_double_p, i64, c_double_p,
                                   c_double_p, i32, c_double_p, i64, c_double_p, c_double_p, i64, c_int64_p, c_double_p, c_double_p,
                                   i64, c_int64_p],
+    "reach_discretize_inputs_box": [vp, i64, c_double_p, i64, f64, i64, c_double_p, i64, i64, c_double_p, i64, c_double_p, i64,
+                                    c_double_p, i64, c_double_p],
     "reach_bffpsv18_boxes": _BOX_ARGS + [c_double_p, c_double_p, c_int64_p],
     "reach_bffpsv18_boxes_csc": [vp, i64, i64, c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p, i64, c_double_p, i64,
                                  c_double_p, c_double_p, c_double_p, i64, c_int32_p, i64, c_double_p, c_double_p, c_int64_p],

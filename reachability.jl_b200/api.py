@@ -172,6 +172,14 @@ class ConstantInput:
 
 
 @dataclass
+class VaryingInput:
+    """`VaryingInput(U_1, U_2, ...)` (MathematicalSystems): a sequence of input sets.  `discretize` bloats each of them
+    (discretize.jl:690-696, 729-737; `discretize_inputs` below); the reach kernels of both post operators take a
+    `ConstantInput` only (reach_blocks.jl:137, GLGM06/reach.jl:32), in the reference as here."""
+    Us: Sequence[Any]
+
+
+@dataclass
 class LinearContinuousSystem:
     A: np.ndarray
 
@@ -405,6 +413,9 @@ def _normalize(problem, keep_sparse=False):
     if isinstance(S, ConstrainedLinearControlContinuousSystem):
         if S.X is not None and not isinstance(S.X, Universe):
             raise ReachError(3, "state constraints (invariants) other than Universe are unsupported on the sm_100a path")
+        if isinstance(S.U, VaryingInput):
+            raise ReachError(3, "time-varying inputs: the reach kernels take a ConstantInput (the reference has no reach_blocks! / "
+                                "reach_inhomog! method for VaryingInput either); `discretize_inputs` bloats the sequence")
         U = S.U.U if isinstance(S.U, ConstantInput) else S.U
         if U is None:
             return A, None, None
@@ -600,6 +611,16 @@ def discretize_zonotope(ctx: Context, A, delta, c, r, B=None, U=None, algorithm=
                                 None if U is None else U[1], algorithm=algorithm, remove_zero_generators=remove_zero_generators)
     V = None if U is None else (D["cV"], D["GV"])
     return D["Phi"], (D["c0"], D["G0"]), V
+
+
+def discretize_inputs(ctx: Context, A, delta, B, U: "VaryingInput"):
+    """The `VaryingInput` branch of `discretize` (discretize.jl:690-696): returns (MU = δB, [(cU_k, rU_k, rpsi_k)]), i.e.
+    Ud[k] = MU * Box(cU_k, rU_k) ⊕ Box(0, rpsi_k) for every input set of the sequence, all k in one device call."""
+    boxes = [_as_box(Uk, "input set") for Uk in U.Us]
+    cUs = np.stack([b[0] for b in boxes], axis=1)
+    rUs = np.stack([b[1] for b in boxes], axis=1)
+    D = ctx.discretize_inputs_box(A, delta, B, cUs, rUs)
+    return D["MU"], [(cUs[:, k], rUs[:, k], D["rpsi"][:, k]) for k in range(len(boxes))]
 
 
 def _post_glgm06(op, problem, opts, ctx):

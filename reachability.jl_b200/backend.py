@@ -171,6 +171,22 @@ class Context:
         return dict(Phi=Phi, c0=c0, G0=np.asfortranarray(G0[:, :p0.value]), cV=cV,
                     GV=np.asfortranarray(GV[:, :pV.value]) if m else None)
 
+    def discretize_inputs_box(self, A, delta, B, cUs, rUs):
+        """`VaryingInput` discretisation (discretize.jl:690-696, 729-737): K input boxes (columns of cUs / rUs, m x K) through
+        B -> dict(rpsi (n, K), MU = δB (n, m)); step k's discretised input is MU * Box(cUs[:, k], rUs[:, k]) ⊕ Box(0, rpsi[:, k])."""
+        A = fmat(A)
+        n = A.shape[0]
+        cUs, rUs = fmat(cUs), fmat(rUs)
+        m, K = cUs.shape
+        assert rUs.shape == (m, K)
+        Bm = None if B is None else fmat(np.asarray(B, dtype=np.float64).reshape(n, -1))
+        assert (Bm is None and m == n) or Bm.shape == (n, m)
+        rpsi = np.zeros((n, K), order="F")
+        MU = np.zeros((n, m), order="F")
+        self._check(self.lib.reach_discretize_inputs_box(self._h, n, dptr(A), n, float(delta), m, dptr(Bm), n, K, dptr(cUs), m,
+                                                         dptr(rUs), m, dptr(rpsi), n, dptr(MU)))
+        return dict(rpsi=rpsi, MU=MU)
+
     # ---- BFFPSV18 --------------------------------------------------------------------------------------
     @staticmethod
     def _box_args(Phi, c0, r0, MU, cU, rU, rpsi, rows, N):

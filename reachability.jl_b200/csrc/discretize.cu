@@ -186,6 +186,13 @@ __global__ void axpy_vec_kernel(int n, const double* __restrict__ a, double alph
     if (i < n) y[i] = (a ? a[i] : 0.0) + alpha * b[i];
 }
 
+
+// Y = |X1| + X2 elementwise (n x K, leading dimension ld): the inner symmetric interval hull of K boxes at once
+__global__ void abs_add_kernel(int n, const double* __restrict__ X1, const double* __restrict__ X2, int64_t ld, double* __restrict__ Y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i < n) Y[(int64_t)k * ld + i] = fabs(X1[(int64_t)k * ld + i]) + X2[(int64_t)k * ld + i];
+}
+
 void launch2d(Ctx* ctx, int n, dim3& grid) { grid = dim3((unsigned)ceil_div(n, 256), (unsigned)n); (void)ctx; }
 
 }  // namespace
@@ -649,6 +656,66 @@ int32_t reach_discretize_zonotope(reach_ctx* h, int64_t n, const double* A, int6
         *pV = 0;
     }
     if (Phi) { REACH_REQUIRE(ldphi >= n, "reach_discretize_zonotope: ldphi"); dmat_download(ctx, d.dPhi, Phi, ldphi); }
+    REACH_CUDA(cudaStreamSynchronize(st));
+    return REACH_OK;
+    D_END(ctx)
+}
+
+
+// Time-varying inputs (VaryingInput branches of discretize.jl:690-696 / 729-737): for K input boxes U_k = B * Box(cU_k, rU_k)
+//     Eψ_k = sih(Φ₂(|A|, δ) * sih(A * U_k))      radius  rψ_k = Φ₂(|A|, δ) (|A B cU_k| + |A B| rU_k)
+// for all k at once: three thin GEMMs (A B CU, |A B| RU, Φ₂ S) on the DMMA kernel instead of K mat-vec sweeps.
+int32_t reach_discretize_inputs_box(reach_ctx* h, int64_t n, const double* A, int64_t lda, double delta, int64_t m, const double* B,
+                                    int64_t ldb, int64_t K, const double* cUs, int64_t ldcu, const double* rUs, int64_t ldru,
+                                    double* rpsi, int64_t ldrpsi, double* MU) {
+    if (!h) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    D_BEGIN(ctx)
+    REACH_REQUIRE(n > 0 && A && lda >= n && m > 0 && K > 0 && cUs && rUs && ldcu >= m && ldru >= m && rpsi && ldrpsi >= n,
+                  "reach_discretize_inputs_box: bad arguments");
+    REACH_REQUIRE(!B || ldb >= n, "reach_discretize_inputs_box: bad ldb");
+    REACH_REQUIRE(B || m == n, "reach_discretize_inputs_box: B == NULL means identity and needs m == n");
+    cudaStream_t st = ctx->stream;
+    DMatGuard gA(dmat_alloc(ctx, n, n)), gP2(dmat_alloc(ctx, n, n)), gB(dmat_alloc(ctx, n, m)), gAB(dmat_alloc(ctx, n, m)),
+        gABabs(dmat_alloc(ctx, n, m));
+    DMat &dA = gA.m, &dP2 = gP2.m, &dB = gB.m, &dAB = gAB.m, &dABabs = gABabs.m;
+    // generator layout for the thin operands: columns contiguous, ld a multiple of 4, >= 128 zeroed columns of slack
+    const int64_t lm = round_up(m, 4), ln = round_up(n, 4);
+    DevScratch scr(ctx);
+    double* dCU = scr.get<double>((size_t)(K + 128) * lm);
+    double* dRU = scr.get<double>((size_t)(K + 128) * lm);
+    double* dX1 = scr.get<double>((size_t)(K + 128) * ln);
+    double* dX2 = scr.get<double>((size_t)(K + 128) * ln);
+    double* dS = scr.get<double>((size_t)(K + 128) * ln);
+    double* dR = scr.get<double>((size_t)(K + 128) * ln);
+    for (double* p : {dCU, dRU}) REACH_CUDA(cudaMemsetAsync(p, 0, (size_t)(K + 128) * lm * 8, st));
+    for (double* p : {dX1, dX2, dS, dR}) REACH_CUDA(cudaMemsetAsync(p, 0, (size_t)(K + 128) * ln * 8, st));
+    dmat_upload(ctx, dA, A, lda);
+    if (B) {
+        dmat_upload(ctx, dB, B, ldb);
+    } else {
+        dim3 g2((unsigned)ceil_div(n, 256), (unsigned)n);
+        axpby_diag_kernel<<<g2, 256, 0, st>>>((int)n, 0.0, dA.p, dA.ld, 0.0, nullptr, 0, 1.0, dB.p, dB.ld);
+        ctx->launches++;
+    }
+    REACH_CUDA(cudaMemcpy2DAsync(dCU, lm * 8, cUs, ldcu * 8, m * 8, K, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(cudaMemcpy2DAsync(dRU, lm * 8, rUs, ldru * 8, m * 8, K, cudaMemcpyHostToDevice, st));
+    expm_family(ctx, n, dA.p, dA.ld, delta, true, nullptr, nullptr, &dP2);             // Φ₂(|A|, δ)                 :652
+    gemm_left(ctx, n, m, n, dA.p, dA.ld, dB.p, dB.ld, dAB.p, dAB.ld);                   // A * B
+    dim3 gm((unsigned)ceil_div(n, 256), (unsigned)m);
+    scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, dAB.p, dAB.ld, 1.0, 1, dABabs.p, dABabs.ld);      // |A B|
+    gemm_left(ctx, n, K, m, dAB.p, dAB.ld, dCU, lm, dX1, ln);                           // (A B) cU_k for every k
+    gemm_left(ctx, n, K, m, dABabs.p, dABabs.ld, dRU, lm, dX2, ln);                     // |A B| rU_k
+    abs_add_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)K), 256, 0, st>>>((int)n, dX1, dX2, ln, dS);   // sih(A * U_k)  :693,:731
+    gemm_left(ctx, n, K, n, dP2.p, dP2.ld, dS, ln, dR, ln);                             // outer sih: Φ₂(|A|) s_k >= 0
+    REACH_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    REACH_CUDA(cudaMemcpy2DAsync(rpsi, ldrpsi * 8, dR, ln * 8, n * 8, K, cudaMemcpyDeviceToHost, st));
+    if (MU) {
+        scale_copy_kernel<<<gm, 256, 0, st>>>((int)n, dB.p, dB.ld, delta, 0, dAB.p, dAB.ld);       // δ B
+        ctx->launches++;
+        dmat_download(ctx, dAB, MU, n);
+    }
     REACH_CUDA(cudaStreamSynchronize(st));
     return REACH_OK;
     D_END(ctx)

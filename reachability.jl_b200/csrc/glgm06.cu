@@ -2255,7 +2255,9 @@ void flowpipe_run(Flowpipe* F) {
         const char* e = getenv("REACH_CHAIN_EXCLUSIVE");
         F->chain_exclusive = F->chain_use_smem && (!e || atoi(e) != 0);
         const double t_gemm = 2.0 * (double)n * n * F->q / 37.0e12;
-        const double t_num = 8.0 * (double)ld * (2.0 * F->r * n + F->p0 + F->pV) * 1.25 / 4.0e12;
+        // HBM-side work per step since the reach sets are generator references: the score pass over the mapped generators and
+        // the box sums over the ~(p0 + pV + n) boxed generators of the two reductions
+        const double t_num = 8.0 * (double)ld * (2.0 * (F->p0 + F->pV) + n) / 4.0e12;
         int K = (int)(0.5 * ctx->sm_count * t_num / (t_gemm + t_num) + 0.5) + (F->chain_exclusive ? 1 : 0);
         K = std::max(F->chain_exclusive ? 2 : 0, std::min(K, ctx->sm_count / 2));
         const char* r = getenv("REACH_GEMM_RESERVE");

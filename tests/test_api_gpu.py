@@ -226,3 +226,17 @@ def test_project_reachset_option_projects_inside_solve():                   # BF
         for k in (0, 9):
             assert_close(set_of(got[k]).center, set_of(want[k]).center, "centre")
             assert_close(set_of(got[k]).radius, set_of(want[k]).radius, "radius")
+
+
+def test_varying_input_is_discretised_but_not_propagated():               # discretize.jl:690-696; reach_blocks.jl:137
+    from reachability_jl_b200 import api
+    ctx = api._context(0)
+    A = np.array([[-1.0, 0.5], [0.0, -2.0]])
+    B = np.array([[1.0], [0.5]])
+    U = api.VaryingInput([Interval(0.9, 1.1), Interval(-0.2, 0.4), Singleton([0.3])])
+    MU, seq = api.discretize_inputs(ctx, A, 0.05, B, U)
+    assert np.allclose(MU, 0.05 * B) and len(seq) == 3
+    assert np.all(seq[0][2] > 0) and np.all(seq[2][2] > 0)                 # E_psi_k bloats every step's input
+    with pytest.raises(ReachError) as ei:
+        solve(IVP(CLCCS(A, B, None, U), BallInf(np.zeros(2), 0.1)), Options(T=0.1))
+    assert ei.value.code == 3

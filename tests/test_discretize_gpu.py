@@ -115,3 +115,21 @@ def test_other_discretisation_models_then_flowpipe(ctx, n, m, alg):
     assert_close(R.T, Ro, "radii")
     if alg == "nobloating":
         assert np.array_equal(out["c0"], X0.c) and np.array_equal(out["r0"], X0.r)
+
+
+@pytest.mark.parametrize("n,m,K,identity_B", [(4, 2, 1, False), (17, 3, 9, False), (48, 1, 40, False), (12, 12, 5, True), (130, 4, 300, False)])
+def test_varying_inputs_discretisation(ctx, n, m, K, identity_B):
+    """`VaryingInput` (discretize.jl:690-696, 729-737): Eψk = sih(Φ₂(|A|, δ) sih(A Uk)) for a sequence of input boxes, all k at
+    once on the device vs the oracle's per-k loop; k = 1 agrees with the constant-input discretisation."""
+    g = np.random.default_rng(n + K)
+    A = _A(n + 1, n, 2.0)
+    B = None if identity_B else g.standard_normal((n, m))
+    cUs = g.standard_normal((m, K))
+    rUs = np.abs(g.standard_normal((m, K))) * 0.3
+    rUs[0, ::3] = 0.0
+    out = ctx.discretize_inputs_box(A, 0.02, B, cUs, rUs)
+    want = orc.discretize_varying_inputs(A, 0.02, B, [orc.Box(cUs[:, k], rUs[:, k]) for k in range(K)])
+    assert_close(out["rpsi"], np.stack(want, axis=1), "radii of E_psi_k")
+    assert_close(out["MU"], 0.02 * (np.eye(n) if B is None else B), "delta * B")
+    const = ctx.discretize_box(A, 0.02, np.zeros(n), np.zeros(n), B, cUs[:, 0], rUs[:, 0])
+    assert_close(out["rpsi"][:, 0], const["rpsi"], "k = 1 vs the ConstantInput discretisation")
