@@ -774,7 +774,7 @@ def c2_flat_scalars(c2):
     return {k: v for k, v in out.items() if v is not None}
 
 
-def run_glgm06_column_sharded(rank, world, dist, reps=3):
+def run_glgm06_column_sharded(rank, world, dist, reps=3, dense=False):
     """Rider under --gpus N: ONE C2 system with its generator columns sharded over the N ranks (reach_glgm06_create_sharded,
     sharding.run_sharded): every rank maps, scores and gathers only its columns, the Girard selection runs replicated on the
     all-reduced scores, three small NCCL all-reduces per batch of steps."""
@@ -789,7 +789,12 @@ def run_glgm06_column_sharded(rank, world, dist, reps=3):
         ctx = rb.Context(dev, stream=stream.cuda_stream)
         Phi, (c0, G0), V = api.discretize_zonotope(ctx, w.A, w.delta, w.c, w.r, w.B, (w.cU, w.rU))
         G0red, _ = ctx.reduce_order(c0, G0, w.max_order)
-        fp = ctx.glgm06_sharded(Phi, c0, G0red, N, w.max_order, V[0], V[1], rank, world)
+        if dense:            # the path of a dense Phi: linear_map(Phi^w, .) as the DMMA GEMM, which shards by columns
+            os.environ["REACH_GLGM06_DENSE"] = "1"
+        try:
+            fp = ctx.glgm06_sharded(Phi, c0, G0red, N, w.max_order, V[0], V[1], rank, world)
+        finally:
+            os.environ.pop("REACH_GLGM06_DENSE", None)
         for _ in range(2):
             sharding.run_sharded(fp, dist)
         torch.cuda.synchronize()
@@ -808,6 +813,7 @@ def run_glgm06_column_sharded(rank, world, dist, reps=3):
         return None
     return {"value": reps * (N - 1) / (ms * 1e-3), "unit": "flowpipe steps/s", "ms_per_flowpipe": ms / reps, "ranks": world,
             "generators_per_reach_set": int(p.max()), "scaling": "strong",
+            "generator_map": "DMMA GEMM (dense Phi path, REACH_GLGM06_DENSE=1)" if dense else "ELL sparse map (Phi of C2 has 2 non-zeros per row)",
             "api": "reach_glgm06_create_sharded + reach_glgm06_shard_phase / _shard_buffer, NCCL sum all-reduces issued by "
                    "sharding.run_sharded on the library's stream (no host synchronisation inside the flowpipe)",
             "note": "at n = 270 the exchange is latency-bound (SURVEY 8e): this does not beat one GPU; it exists for large n * p"}
@@ -1023,6 +1029,7 @@ def main():
         r5 = run_ensemble(argparse.Namespace(**{**vars(args), "workload": "C5", "steps": 2, "warmup": 1, "flow_steps": 0,
                                                 "no_e2e": world > 1, "no_cpu_baseline": True, "rider": True}), rank, world, dist)
         shard = run_glgm06_column_sharded(rank, world, dist) if world > 1 else None
+        shard_dense = run_glgm06_column_sharded(rank, world, dist, dense=True) if world > 1 else None
         multi = run_inprocess_multi(rank, world, dist) if world > 1 else None
         if out is not None:
             out["riders"] = {"c4_mna5": {k: r4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling")},
@@ -1035,6 +1042,11 @@ def main():
             if shard is not None:
                 out["riders"]["c2_column_sharded"] = shard
                 flat["c2_column_sharded_value"] = shard["value"]
+            if shard_dense is not None:
+                shard_dense["note"] = ("dense-Phi path: the DMMA GEMM (the dominant cost on one GPU, see c2_dense_value of the N=1 "
+                                       "line) shards by generator columns; compare with c2_dense_value, not with c2_value")
+                out["riders"]["c2_column_sharded_dense"] = shard_dense
+                flat["c2_column_sharded_dense_value"] = shard_dense["value"]
             if multi is not None:
                 out["riders"]["c3_one_process_multi_device"] = multi
                 flat["c3_one_process_multi_device_e2e"] = multi["value"]

@@ -55,6 +55,7 @@ struct DMat {
 struct Ctx {
     int device = 0;
     int sm_count = 148;
+    bool gemm_exclusive = false;    // the persistent GEMM asks for all of an SM's shared memory while gemm_reserve_sms > 0: a real SM partition
     int gemm_reserve_sms = 0;       // SMs the persistent GEMM leaves free (GLGM06 keeps one for its selection chain)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;

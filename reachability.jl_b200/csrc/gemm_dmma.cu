@@ -354,13 +354,15 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
                         (STAGES + (STAGES & 1)) * sizeof(int) + CONSUMER_WARPS * 2 * 32 * sizeof(double) + 1024;
     static bool configured[64] = {false};      // function attributes are per device
     const int dev = ctx->device & 63;
+    constexpr size_t SMEM_ALL = 227 * 1024;    // with the 1 KB the system reserves per CTA: the whole SM, nothing fits beside it
     {
         std::lock_guard<std::mutex> lock(g_config_mutex);     // contexts of several devices may run on their own host threads
         if (!configured[dev]) {
-            REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            REACH_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<WNT, AKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALL));
             configured[dev] = true;
         }
     }
+    const size_t smem_launch = (ctx->gemm_exclusive && ctx->gemm_reserve_sms > 0) ? SMEM_ALL : smem;
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = ctx->sm_count - ctx->gemm_reserve_sms > 0 ? ctx->sm_count - ctx->gemm_reserve_sms : 1;
     const int grid = tiles < sms ? tiles : sms;
@@ -373,7 +375,7 @@ void launch(Ctx* ctx, const GemmParams& p, const CUtensorMap& tmap) {
     }
     GemmParams q = p;
     q.sched = ctx->gemm_sched + 2 * (ctx->gemm_sched_next++ % SCHED_RING);
-    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem, ctx->stream>>>(q, tmap);
+    gemm_dmma_kernel<WNT, AKM><<<grid, THREADS, smem_launch, ctx->stream>>>(q, tmap);
     REACH_CUDA(cudaGetLastError());
     ctx->launches++;
 }

@@ -2150,10 +2150,13 @@ static void process_chain(Flowpipe* F, GP& g, int k0, int cnt, cudaStream_t st) 
 }
 
 // ... and their batched numerics
-// `rank_st` (optional): rank_r only needs the chain's snapshot, so it may run on its own stream next to wbox / wseq;
-// `rank_done` is then recorded there and awaited before apply_r.
-static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st, cudaStream_t rank_st = nullptr,
-                             cudaEvent_t rank_done = nullptr) {
+// `tail_st` (optional): a second stream for the R reduction of the batch.  Only the W box recurrence (wseq) is sequential from
+// batch to batch; the R sortperm needs nothing but the chain's snapshot, and the R gather (apply_r, finalize_r) needs the W
+// box vectors of its OWN batch (`w_done`, recorded on `st` after wseq).  With the two halves on two streams the R reduction of
+// batch b overlaps the W recurrence of batch b + 1 instead of queueing behind it (dense C2: the numerics stream was busy 15.4
+// of 17.3 ms, its latency-bound kernels slowed 4x by the GEMM next door).  Returns the stream on which the batch completes.
+static cudaStream_t process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStream_t st, cudaStream_t tail_st = nullptr,
+                                     cudaEvent_t w_done = nullptr) {
     const int jb = numerics_jb(F->ld);
     const size_t red_smem = numerics_smem(F->ld, jb);
     const int it = F->ld <= 256 ? 4 : (F->ld <= 512 ? 8 : 16);
@@ -2172,23 +2175,26 @@ static void process_numerics(Flowpipe* F, const GP& g, int k0, int cnt, cudaStre
     wseq_fast_kernel<<<(unsigned)ceil_div(F->n * 32, 256), 256, 0, st>>>(g, k0, cnt);
     wseq_kernel<<<(unsigned)ceil_div(F->n, 128), 128, 0, st>>>(g, k0, cnt);
     mark();
-    if (rank_st && rank_st != st) {
-        rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, rank_st>>>(g, k0);
-        REACH_CUDA(cudaEventRecord(rank_done, rank_st));
-        REACH_CUDA(cudaStreamWaitEvent(st, rank_done, 0));
+    cudaStream_t rs = st;
+    if (tail_st && tail_st != st) {
+        REACH_CUDA(cudaEventRecord(w_done, st));
+        rs = tail_st;
+        rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, rs>>>(g, k0);
+        REACH_CUDA(cudaStreamWaitEvent(rs, w_done, 0));
     } else {
         rank_r_kernel<<<dim3((unsigned)ceil_div(g.p0 + g.capW, 256), (unsigned)cnt), 256, 0, st>>>(g, k0);
     }
     mark();
     const dim3 ag(NBR + COPY_CTAS, (unsigned)cnt);
-    if (it == 4) apply_r_kernel<4><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
-    else if (it == 8) apply_r_kernel<8><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
-    else apply_r_kernel<16><<<ag, NUM_WARPS * 32, red_smem, st>>>(g, k0, jb);
+    if (it == 4) apply_r_kernel<4><<<ag, NUM_WARPS * 32, red_smem, rs>>>(g, k0, jb);
+    else if (it == 8) apply_r_kernel<8><<<ag, NUM_WARPS * 32, red_smem, rs>>>(g, k0, jb);
+    else apply_r_kernel<16><<<ag, NUM_WARPS * 32, red_smem, rs>>>(g, k0, jb);
     mark();
-    finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
+    finalize_r_kernel<<<(unsigned)cnt, 256, 0, rs>>>(g, k0);
     mark();
     REACH_CUDA(cudaGetLastError());
     F->ctx->launches += 6;
+    return rs;
 }
 
 static void set_kernel_attributes(Flowpipe* F) {
@@ -2242,7 +2248,7 @@ void flowpipe_run(Flowpipe* F) {
     struct ReserveGuard {       // one SM stays free for the selection chain while the GEMMs of later batches run
         Ctx* c; int old;
         ReserveGuard(Ctx* c_, int v) : c(c_), old(c_->gemm_reserve_sms) { c->gemm_reserve_sms = v; }
-        ~ReserveGuard() { c->gemm_reserve_sms = old; }
+        ~ReserveGuard() { c->gemm_reserve_sms = old; c->gemm_exclusive = false; }
     } reserve(ctx, 0);
     if (!F->homog && !F->serial) {
         // SM partition of the pipelined run.  The persistent GEMM is issue-bound, so kernels that share its SMs crawl (a
@@ -2262,6 +2268,8 @@ void flowpipe_run(Flowpipe* F) {
         K = std::max(F->chain_exclusive ? 2 : 0, std::min(K, ctx->sm_count / 2));
         const char* r = getenv("REACH_GEMM_RESERVE");
         ctx->gemm_reserve_sms = r ? atoi(r) : K;
+        const char* x = getenv("REACH_GEMM_EXCLUSIVE");
+        ctx->gemm_exclusive = x && atoi(x) != 0;
     }
     std::vector<std::pair<size_t, size_t>> chain_ev;
     F->detail = getenv("REACH_TIMING_DETAIL") != nullptr;
@@ -2389,13 +2397,14 @@ void flowpipe_run(Flowpipe* F) {
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             red_ev.push_back({ev_used - 2, ev_used - 1});
             REACH_CUDA(cudaEventRecord(e0, sNum));
-            if (F->serial || F->detail) {
+            cudaStream_t sDone = sNum;
+            if (F->serial || F->detail || getenv("REACH_NUMERICS_ONE_STREAM")) {
                 process_numerics(F, g, (int)have + 1, (int)cnt, sNum);
             } else {
                 REACH_CUDA(cudaStreamWaitEvent(F->side4, c1, 0));
-                process_numerics(F, g, (int)have + 1, (int)cnt, sNum, F->side4, next_event(F, ev_used));
+                sDone = process_numerics(F, g, (int)have + 1, (int)cnt, sNum, F->side4, next_event(F, ev_used));
             }
-            REACH_CUDA(cudaEventRecord(e1, sNum));
+            REACH_CUDA(cudaEventRecord(e1, sDone));
             ev_num.push_back(e1);
             if (F->sink_G) {        // stream this batch's reach sets to the host while the later batches are computed
                 REACH_CUDA(cudaStreamWaitEvent(F->cpy, e1, 0));

@@ -81,6 +81,29 @@ def iss(n_modes: int = 135, delta: float = 0.01, T: float = 20.0, seed: int = 27
     return Workload("C2-iss", A, c, r, B, cU, rU, delta, T, "GLGM06", max_order=max_order)
 
 
+def iss_mixed(n_modes: int = 512, delta: float = 0.01, T: float = 2.0, seed: int = 1024, max_order: int = 10) -> Workload:
+    """A large n * p GLGM06 case (what the generator-column sharding exists for): the lightly damped
+    modes of `iss` under a random orthogonal change of coordinates, so A -- and every power of Phi -- is DENSE and the
+    generator map is the DMMA GEMM.  n = 2 * n_modes (1024), three inputs, same reachable set as the decoupled modes up to
+    the rotation."""
+    g = _rng(seed)
+    w = np.exp(g.uniform(np.log(0.8), np.log(60.0), n_modes))
+    zeta = 0.005
+    n = 2 * n_modes
+    Am = np.zeros((n, n))
+    Am[:n_modes, n_modes:] = np.eye(n_modes)
+    Am[n_modes:, :n_modes] = -np.diag(w ** 2)
+    Am[n_modes:, n_modes:] = -np.diag(2 * zeta * w)
+    Q, _ = np.linalg.qr(g.standard_normal((n, n)))
+    A = Q @ Am @ Q.T
+    B = Q @ np.vstack([np.zeros((n_modes, 3)), g.normal(0.0, 1e-3, (n_modes, 3))])
+    c = np.zeros(n)
+    r = np.full(n, 1e-4)
+    cU = np.array([0.05, 0.9, 0.95])
+    rU = np.array([0.05, 0.1, 0.05])
+    return Workload(f"GLGM06-dense-n{n}", A, c, r, B, cU, rU, delta, T, "GLGM06", max_order=max_order)
+
+
 def fom(n_pairs: int = 500, delta: float = 0.003, T: float = 20.0, seed: int = 1006) -> Workload:
     """C3: FOM-shaped sparse stable system, n = 6 + 2*n_pairs (1006), one input, 2-D Hyperrectangle blocks."""
     g = _rng(seed)
