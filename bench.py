@@ -514,11 +514,14 @@ def run_glgm06(args, rank, world, dist, e2e=True):
 
             one_proj()
             one_proj()
-            proj_steps = 5                      # a solve + project call is ~25 ms: a few more of them than of the 1.3 s full fetch
+            proj_steps = 10                     # a solve + project call is ~11 ms: more of them than of the 1.3 s full fetch
             torch.cuda.synchronize()
+            proj_call_ms = []
             t0 = time.perf_counter()
             for _ in range(proj_steps):
+                tc = time.perf_counter()
                 one_proj()
+                proj_call_ms.append(round((time.perf_counter() - tc) * 1e3, 2))
             torch.cuda.synchronize()
             proj_s = _max_over_ranks(dist, world, time.perf_counter() - t0, dev)
             e2e_obj = {"value": world * e2e_steps * (N - 1) / e2e_s, "unit": "flowpipe steps/s",
@@ -527,7 +530,7 @@ def run_glgm06(args, rank, world, dist, e2e=True):
                        "api": "reach_glgm06_create + reach_glgm06_run_fetch (pinned host buffers; every zonotope of the "
                               "flowpipe copied back, batch by batch while later batches compute, as reach_inhomog! materialises them)",
                        "projected": {"value": world * proj_steps * (N - 1) / proj_s, "unit": "flowpipe steps/s", "steps": proj_steps,
-                                     "d2h_bytes_per_step": 2 * 2 * 8 * N,
+                                     "d2h_bytes_per_step": 2 * 2 * 8 * N, "call_ms": proj_call_ms,
                                      "api": "reach_glgm06_create + reach_glgm06_run + reach_flowpipe_project (solve + project(sol, vars): "
                                             "2-D boxes of every reach set computed on the device, only they are copied back)"}}
         ctx.close()
@@ -795,14 +798,18 @@ def run_glgm06_column_sharded(rank, world, dist, reps=3, dense=False):
             fp = ctx.glgm06_sharded(Phi, c0, G0red, N, w.max_order, V[0], V[1], rank, world)
         finally:
             os.environ.pop("REACH_GLGM06_DENSE", None)
+        # phases in order on one stream: at n = 270 the map of a batch is as short as its selection / box phases, and issuing it
+        # on a second stream (sharding.run_sharded(gemm_stream=...), what the n = 1024 rider does) measured slower on 2 GPUs
+        # (sparse map 165 k against 190 k steps/s, dense map 125 k against 127 k)
+        gemm_stream = None
         for _ in range(2):
-            sharding.run_sharded(fp, dist)
+            sharding.run_sharded(fp, dist, gemm_stream=gemm_stream)
         torch.cuda.synchronize()
         dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(reps):
-            sharding.run_sharded(fp, dist)
+            sharding.run_sharded(fp, dist, gemm_stream=gemm_stream)
         ev1.record(stream)
         torch.cuda.synchronize()
         ms = _max_over_ranks(dist, world, ev0.elapsed_time(ev1), dev)
@@ -817,6 +824,69 @@ def run_glgm06_column_sharded(rank, world, dist, reps=3, dense=False):
             "api": "reach_glgm06_create_sharded + reach_glgm06_shard_phase / _shard_buffer, NCCL sum all-reduces issued by "
                    "sharding.run_sharded on the library's stream (no host synchronisation inside the flowpipe)",
             "note": "at n = 270 the exchange is latency-bound (SURVEY 8e): this does not beat one GPU; it exists for large n * p"}
+
+
+def run_glgm06_large(rank, world, dist, reps=3):
+    """Rider: a large n * p GLGM06 system with a DENSE Phi (n = 1024, order 10, 4100 + 1027 mapped generators per step, 10240 per
+    reach set; workloads.iss_mixed) -- the regime the generator-column sharding of SURVEY.md section 8e exists for.  Rank 0
+    times the pipelined single-GPU engine (value, in-situ DMMA fraction of the generator map); under --gpus N all ranks then
+    run the SAME system column-sharded with the software-pipelined phase machine (phase 0 of batch b + 1 on a second stream)."""
+    import torch
+    import reachability_jl_b200 as rb
+    from reachability_jl_b200 import api, sharding, workloads as wl
+    w = wl.iss_mixed()
+    N = int(round(w.T / w.delta))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    stream = torch.cuda.Stream(device=dev)
+    out = None
+    with torch.cuda.stream(stream):
+        ctx = rb.Context(dev, stream=stream.cuda_stream)
+        Phi, (c0, G0), V = api.discretize_zonotope(ctx, w.A, w.delta, w.c, w.r, w.B, (w.cU, w.rU))
+        G0red, _ = ctx.reduce_order(c0, G0, w.max_order)
+        if rank == 0:
+            fp = ctx.glgm06(Phi, c0, G0red, N, w.max_order, V[0], V[1], 0)
+            fp.run()
+            best, t = 1e30, None
+            for _ in range(reps):
+                fp.run()
+                ti = fp.timing()
+                if ti["run_ms"] < best:
+                    best, t = ti["run_ms"], ti
+            pmax = int(fp.ngens().max())
+            fp.close()
+            tf = t["gemm_flops"] / (best * 1e-3) * 1e-12
+            out = {"value": (N - 1) / (best * 1e-3), "unit": "flowpipe steps/s", "ms_per_flowpipe": best,
+                   "config": {"workload": f"{w.name}: n={w.n}, m={w.m}, GLGM06 max_order={w.max_order}, delta={w.delta}, N={N} reach sets, "
+                                          f"p0={G0red.shape[1]}, pV={V[1].shape[1]}, {pmax} generators per reach set, dense Phi"},
+                   "roofline": {"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                "frac": tf / FP64_DMMA_PEAK_TFLOPS,
+                                "kernel": "gemm_dmma_kernel<.,true> in situ: flops of the generator map / whole-flowpipe time "
+                                          "(selection chain, scores and box sums overlapped on the SMs the GEMM leaves free)",
+                                "gemm_ms_in_situ": t["gemm_ms"], "numerics_ms_in_situ": t["numerics_ms"], "chain_ms_in_situ": t["chain_ms"]}}
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            fs = ctx.glgm06_sharded(Phi, c0, G0red, N, w.max_order, V[0], V[1], rank, world)
+            gs = torch.cuda.Stream(device=dev)
+            for _ in range(2):
+                sharding.run_sharded(fs, dist, gemm_stream=gs)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(reps):
+                sharding.run_sharded(fs, dist, gemm_stream=gs)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = _max_over_ranks(dist, world, ev0.elapsed_time(ev1), dev) / reps
+            fs.close()
+            if out is not None:
+                out["column_sharded"] = {"value": (N - 1) / (ms * 1e-3), "unit": "flowpipe steps/s", "ms_per_flowpipe": ms, "ranks": world,
+                                         "speedup_vs_one_gpu": out["ms_per_flowpipe"] / ms, "scaling": "strong",
+                                         "api": "reach_glgm06_create_sharded + reach_glgm06_shard_phase_on / _shard_buffer; "
+                                                "sharding.run_sharded(gemm_stream=...): three NCCL sum all-reduces per 64-step batch"}
+        ctx.close()
+    return out
 
 
 def run_inprocess_multi(rank, world, dist):
@@ -1031,6 +1101,7 @@ def main():
         shard = run_glgm06_column_sharded(rank, world, dist) if world > 1 else None
         shard_dense = run_glgm06_column_sharded(rank, world, dist, dense=True) if world > 1 else None
         multi = run_inprocess_multi(rank, world, dist) if world > 1 else None
+        large = run_glgm06_large(rank, world, dist)
         if out is not None:
             out["riders"] = {"c4_mna5": {k: r4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling")},
                              "c5_ensemble": {k: r5[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling", "e2e")}}
@@ -1047,6 +1118,12 @@ def main():
                                        "line) shards by generator columns; compare with c2_dense_value, not with c2_value")
                 out["riders"]["c2_column_sharded_dense"] = shard_dense
                 flat["c2_column_sharded_dense_value"] = shard_dense["value"]
+            if large is not None:
+                out["riders"]["glgm06_dense_n1024"] = large
+                flat.update(glgm06_n1024_dense_value=large["value"], glgm06_n1024_dense_frac=large["roofline"]["frac"])
+                if "column_sharded" in large:
+                    flat.update(glgm06_n1024_column_sharded_value=large["column_sharded"]["value"],
+                                glgm06_n1024_column_sharded_speedup=large["column_sharded"]["speedup_vs_one_gpu"])
             if multi is not None:
                 out["riders"]["c3_one_process_multi_device"] = multi
                 flat["c3_one_process_multi_device_e2e"] = multi["value"]

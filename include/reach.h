@@ -236,6 +236,14 @@ REACH_API int32_t reach_glgm06_shard_nbatches(reach_flowpipe* fp, int64_t* nbatc
 REACH_API int32_t reach_glgm06_shard_phase(reach_flowpipe* fp, int64_t batch, int32_t phase);
 REACH_API int32_t reach_glgm06_shard_buffer(reach_flowpipe* fp, int64_t batch, int32_t which, void** dev_ptr, int64_t* count,
                                   int32_t* dtype /* 0 = float64, 1 = int32 */);
+/* reach_glgm06_shard_phase with the phase's kernels issued on `cuda_stream` (a cudaStream_t of the caller) instead of the
+ * context's stream.  Phase 0 of batch b + 1 -- the map of the rank's own generator columns (the DMMA GEMM when Phi is dense)
+ * and their scores -- needs nothing of batch b but its archive slots, so the caller may issue it on a second stream BEFORE
+ * phases 1..3 of batch b and the two overlap on the device (sharding.run_sharded(..., gemm_stream=...)): the batch-local
+ * arrays exist three times, the library orders their reuse with events, and the buffers reach_glgm06_shard_buffer reports
+ * are those of the batch's own set.  Phase 0 may run at most two batches ahead of phases 1..3 (status 1 otherwise); the
+ * all-reduces of a phase must be ordered after it on the stream it was issued on. */
+REACH_API int32_t reach_glgm06_shard_phase_on(reach_flowpipe* fp, int64_t batch, int32_t phase, void* cuda_stream);
 /* run + fetch in one call, streamed: every batch of reach sets is copied to the host (layout of reach_flowpipe_fetch;
  * pinned buffers overlap best) while the later batches are still being computed.  This is the shape of
  * `reach_inhomog!(R, ...)` filling its caller-allocated vector (GLGM06/reach.jl:30-36). */

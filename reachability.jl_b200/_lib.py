@@ -76,6 +76,7 @@ _SIGNATURES = {
                                     i64, i64, i64, i32, i32, i32, C.POINTER(vp)],
     "reach_glgm06_shard_nbatches": [vp, c_int64_p],
     "reach_glgm06_shard_phase": [vp, i64, i32],
+    "reach_glgm06_shard_phase_on": [vp, i64, i32, vp],
     "reach_glgm06_shard_buffer": [vp, i64, i32, C.POINTER(vp), c_int64_p, c_int32_p],
     "reach_glgm06_run": [vp],
     "reach_glgm06_run_fetch": [vp, c_double_p, c_double_p, i64],

@@ -640,8 +640,13 @@ class ShardedFlowpipe(Flowpipe):
         self.ctx._check(self.ctx.lib.reach_glgm06_shard_nbatches(self._h, C.byref(v)))
         return int(v.value)
 
-    def phase(self, batch: int, phase: int):
-        self.ctx._check(self.ctx.lib.reach_glgm06_shard_phase(self._h, int(batch), int(phase)))
+    def phase(self, batch: int, phase: int, stream: Optional[int] = None):
+        """One phase of one batch; `stream` (a raw cudaStream_t) issues it there instead of on the context's stream
+        (reach_glgm06_shard_phase_on: phase 0 of batch b + 1 may overlap phases 1..3 of batch b)."""
+        if stream is None:
+            self.ctx._check(self.ctx.lib.reach_glgm06_shard_phase(self._h, int(batch), int(phase)))
+        else:
+            self.ctx._check(self.ctx.lib.reach_glgm06_shard_phase_on(self._h, int(batch), int(phase), C.c_void_p(int(stream))))
 
     def buffer(self, batch: int, which: int):
         """(device pointer, element count, numpy dtype string) of the buffer to sum-all-reduce, or None when empty."""

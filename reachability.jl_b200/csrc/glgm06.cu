@@ -1757,7 +1757,9 @@ struct Flowpipe {
     // column-sharded phase machine (reach_glgm06_shard_*): batches are processed in order, collectives in between
     struct Batch { int64_t have, cnt, w; bool square_after; };
     std::vector<Batch> sched;
-    int64_t next_batch = 0;
+    int64_t next_batch = 0;         // next batch whose phases 1..3 are due
+    int64_t next_p0 = 0;            // next batch whose phase 0 (map + scores) is due: may run ahead of next_batch on another stream
+    std::vector<cudaEvent_t> shard_done;    // phase 3 of batch b issued (orders the reuse of the batch-local array sets)
     const DMat* pw = nullptr;
     int sp = 0, shard_lvl = 0;
     GP g{};
@@ -1807,6 +1809,7 @@ void flowpipe_free(Flowpipe* F) {
     dmat_free(F->Phi); dmat_free(F->PowA); dmat_free(F->PowB);
     for (void* p : F->owned) ctx_free(F->ctx, p);
     for (cudaEvent_t e : F->evs) cudaEventDestroy(e);
+    for (cudaEvent_t e : F->shard_done) cudaEventDestroy(e);
     if (F->side) cudaStreamDestroy(F->side);
     if (F->side2) cudaStreamDestroy(F->side2);
     if (F->side3) cudaStreamDestroy(F->side3);
@@ -1849,6 +1852,13 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
         F->q = homog ? p0 + F->nc : p0 + pV + 2;
         const int64_t q = F->q;
         F->s = N > 2 ? pick_block(n, q, N) : 1;
+        if (!homog && N > 2) {
+            // inhomogeneous path: every batch costs ~12 launches (and, column-sharded, 4 all-reduces), so long batches pay even
+            // when the GEMM grid is full much earlier (n = 1024, N = 200: s = 4 / 16 / 64 -> 71.2 / 66.3 / 66.0 ms on one GPU,
+            // 52.8 / 40.4 / 37.6 ms column-sharded over two); bounded by ~1 GB of batch-local arrays (3 sets)
+            const int64_t cap = std::max<int64_t>(1, (int64_t)1e9 / (192 * std::max<int64_t>(1, max_order * n)));
+            while (F->s < 64 && F->s < N - 1 && F->s * 2 <= cap) F->s *= 2;
+        }
         if (getenv("REACH_GLGM06_BLOCK") && N > 2) {      // tuning knob, rounded down to a power of two
             int64_t want = std::max(1, std::min(128, atoi(getenv("REACH_GLGM06_BLOCK")))), pw2 = 1;
             while (pw2 * 2 <= want) pw2 *= 2;
@@ -2216,6 +2226,19 @@ static void set_kernel_attributes(Flowpipe* F) {
     done = true;
 }
 
+// SMs the persistent GEMM leaves to the selection chain and the HBM-bound numerics while they overlap it: balances t_gemm at
+// the DMMA peak against t_numerics at ~4 TB/s, scaled by 0.5 because the numerics CTAs that land next to GEMM CTAs still
+// contribute (C2: K = 33 gave 106 k steps/s against 89 k with K = 0 in round 1; the dynamic tile scheduler of the GEMM makes
+// any grid size free of wave quantisation).
+static int partition_reserve(const Flowpipe* F, int64_t q_gemm, int64_t gens_numerics, bool chain_exclusive) {
+    const double t_gemm = 2.0 * (double)F->n * F->n * q_gemm / 37.0e12;
+    // HBM-side work per step since the reach sets are generator references: the score pass over the mapped generators and
+    // the box sums over the ~(p0 + pV + n) boxed generators of the two reductions
+    const double t_num = 8.0 * (double)F->ld * (2.0 * gens_numerics + F->n) / 4.0e12;
+    int K = (int)(0.5 * F->ctx->sm_count * t_num / (t_gemm + t_num) + 0.5) + (chain_exclusive ? 1 : 0);
+    return std::max(chain_exclusive ? 2 : 0, std::min(K, F->ctx->sm_count / 2));
+}
+
 void flowpipe_run(Flowpipe* F) {
     Ctx* ctx = F->ctx;
     cudaStream_t st = ctx->stream;
@@ -2260,12 +2283,7 @@ void flowpipe_run(Flowpipe* F) {
         // makes any grid size free of wave quantisation.)  REACH_GEMM_RESERVE / REACH_CHAIN_EXCLUSIVE override (diagnostics).
         const char* e = getenv("REACH_CHAIN_EXCLUSIVE");
         F->chain_exclusive = F->chain_use_smem && (!e || atoi(e) != 0);
-        const double t_gemm = 2.0 * (double)n * n * F->q / 37.0e12;
-        // HBM-side work per step since the reach sets are generator references: the score pass over the mapped generators and
-        // the box sums over the ~(p0 + pV + n) boxed generators of the two reductions
-        const double t_num = 8.0 * (double)ld * (2.0 * (F->p0 + F->pV) + n) / 4.0e12;
-        int K = (int)(0.5 * ctx->sm_count * t_num / (t_gemm + t_num) + 0.5) + (F->chain_exclusive ? 1 : 0);
-        K = std::max(F->chain_exclusive ? 2 : 0, std::min(K, ctx->sm_count / 2));
+        const int K = partition_reserve(F, F->q, F->p0 + F->pV, F->chain_exclusive);
         const char* r = getenv("REACH_GEMM_RESERVE");
         ctx->gemm_reserve_sms = r ? atoi(r) : K;
         const char* x = getenv("REACH_GEMM_EXCLUSIVE");
@@ -2523,21 +2541,46 @@ int64_t flowpipe_shard_nbatches(Flowpipe* F) {
     return 1 + (int64_t)F->sched.size();
 }
 
-void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
+// `on` (optional): the CUDA stream the phase is issued on instead of the context's.  Phase 0 of batch b + 1 (the map of the
+// own columns and their scores -- the DMMA GEMM for a dense Phi) needs nothing of batch b but its slots, so a caller may issue
+// it on a second stream BEFORE phases 1..3 of batch b and the two overlap; the batch-local arrays exist NSET times and the
+// library orders their reuse with events (phase 0 of batch b waits for phase 3 of batch b - NSET, which must have been issued).
+void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase, cudaStream_t on) {
     REACH_REQUIRE(!F->homog, "glgm06: homogeneous flowpipes are not column-sharded");
     const int64_t nb = flowpipe_shard_nbatches(F);
     REACH_REQUIRE(b >= 0 && b < nb && phase >= 0 && phase < 4, "glgm06: bad batch / phase");
     Ctx* ctx = F->ctx;
+    struct StreamGuard {            // the GEMM / map launchers issue on the context's stream
+        Ctx* c; cudaStream_t old; int old_reserve;
+        StreamGuard(Ctx* c_, cudaStream_t s) : c(c_), old(c_->stream), old_reserve(c_->gemm_reserve_sms) { if (s) c->stream = s; }
+        ~StreamGuard() { c->stream = old; c->gemm_reserve_sms = old_reserve; }
+    } guard(ctx, on);
     cudaStream_t st = ctx->stream;
     const int64_t n = F->n, ld = F->ld, N = F->N;
     set_kernel_attributes(F);
+    if ((int64_t)F->shard_done.size() < nb) {
+        const size_t have_ev = F->shard_done.size();
+        F->shard_done.resize(nb);
+        for (size_t i = have_ev; i < (size_t)nb; ++i) REACH_CUDA(cudaEventCreateWithFlags(&F->shard_done[i], cudaEventDisableTiming));
+    }
     GP g = F->g;
-    bind_set(g, F->gset[0]);
+    const int si = (int)(b % Flowpipe::NSET);
+    bind_set(g, F->gset[si]);
+    if (phase == 0) {
+        REACH_REQUIRE(b == 0 || b == F->next_p0, "glgm06: phase 0 of the sharded batches must be issued in order");
+        if (b >= Flowpipe::NSET) {
+            REACH_REQUIRE(F->next_batch > b - Flowpipe::NSET,
+                          "glgm06: phase 0 of a batch may run at most NSET - 1 batches ahead of phases 1..3");
+            REACH_CUDA(cudaStreamWaitEvent(st, F->shard_done[b - Flowpipe::NSET], 0));
+        }
+    } else {
+        REACH_REQUIRE(b == F->next_batch && b < F->next_p0, "glgm06: sharded batches must be processed in order (phase 0 first)");
+    }
     if (b == 0) {
         g.Y = F->Hflow;
         g.col0 = 0;
         if (phase == 0) {
-            F->next_batch = 0; F->pw = &F->Phi; F->sp = 0; F->shard_lvl = 0; F->ran = false;
+            F->next_batch = 0; F->next_p0 = 1; F->pw = &F->Phi; F->sp = 0; F->shard_lvl = 0; F->ran = false;
             REACH_CUDA(cudaMemsetAsync(g.fastCount, 0, 2 * sizeof(int), st));
             REACH_CUDA(cudaMemcpyAsync(g.cW, F->Hflow + (int64_t)(g.la + g.lc + 1) * ld, n * 8, cudaMemcpyDeviceToDevice, st));
             score_only(F, g, 0, 1, st);
@@ -2548,11 +2591,11 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
             ctx->launches++;
         } else if (phase == 3) {
             F->next_batch = 1;
+            REACH_CUDA(cudaEventRecord(F->shard_done[0], st));
             if (N == 1) { F->meta_host.assign(1, make_int2((int)F->p0, 0)); F->ran = true; }
         }
         return;
     }
-    REACH_REQUIRE(b == F->next_batch, "glgm06: sharded batches must be processed in order");
     const Flowpipe::Batch& B = F->sched[b - 1];
     const int k0 = (int)B.have + 1, cnt = (int)B.cnt;
     g.Y = F->Hflow + B.have * F->qloc * ld;
@@ -2561,9 +2604,22 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
     const size_t red_smem = numerics_smem(ld, jb);
     const int it = ld <= 256 ? 4 : (ld <= 512 ? 8 : 16);
     if (phase == 0) {
+        if (on) {       // overlapped with phases 1..3 of the previous batch: leave them SMs (the chain runs replicated on every rank)
+            const char* r = getenv("REACH_GEMM_RESERVE");
+            ctx->gemm_reserve_sms = r ? atoi(r) : std::max(8, partition_reserve(F, F->qloc, (F->p0 + F->pV) / F->nranks + 1, false));
+        }
+        if (b >= 2 && F->sched[b - 2].square_after) {      // Phi^(2w) for this batch (doubling phase of the schedule)
+            DMat* spare[2] = {&F->PowA, &F->PowB};
+            if (F->ell_levels == 0)
+                gemm_left(ctx, n, n, n, F->pw->p, F->pw->ld, F->pw->p, F->pw->ld, spare[F->sp]->p, spare[F->sp]->ld);
+            F->pw = spare[F->sp];
+            F->sp ^= 1;
+            F->shard_lvl++;
+        }
         map_slots(F, F->shard_lvl, *F->pw, B.cnt * F->qloc, F->Hflow + (B.have - B.w) * F->qloc * ld,
                   F->Hflow + B.have * F->qloc * ld);
         score_only(F, g, B.have, cnt, st);
+        F->next_p0 = b + 1;
     } else if (phase == 1) {
         sort_only(F, g, cnt, st);
         ctx->launches += launch_chain_auto(g, k0, cnt, F->chain_use_smem != 0, F->chain_smem, F->scr, st, false) - 1;
@@ -2586,14 +2642,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
         finalize_r_kernel<<<(unsigned)cnt, 256, 0, st>>>(g, k0);
         REACH_CUDA(cudaGetLastError());
         ctx->launches += 1;
-        if (B.square_after) {
-            DMat* spare[2] = {&F->PowA, &F->PowB};
-            if (F->ell_levels == 0)
-                gemm_left(ctx, n, n, n, F->pw->p, F->pw->ld, F->pw->p, F->pw->ld, spare[F->sp]->p, spare[F->sp]->ld);
-            F->pw = spare[F->sp];
-            F->sp ^= 1;
-            F->shard_lvl++;
-        }
+        REACH_CUDA(cudaEventRecord(F->shard_done[b], st));
         F->next_batch = b + 1;
         if (b == nb - 1) {
             F->meta_host.resize(N);
@@ -2602,8 +2651,8 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
             F->ran = true;
         }
     }
-    // No host synchronisation: the phases and the caller's all-reduces are ordered on the context's stream (the caller
-    // issues the collectives on that stream, or synchronises it itself -- sharding.run_sharded does either).
+    // No host synchronisation: the phases and the caller's all-reduces are ordered on the stream(s) they are issued on (the
+    // caller issues the collectives on that stream, or synchronises it itself -- sharding.run_sharded does either).
 }
 
 // Device buffer the caller all-reduces (sum) after phase `which`-dependent: 0 scores, 1 row-support masks, 2 W box
@@ -2611,7 +2660,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase) {
 void flowpipe_shard_buffer(Flowpipe* F, int64_t b, int which, void** ptr, int64_t* count, int* dtype) {
     const int64_t nb = flowpipe_shard_nbatches(F);
     REACH_REQUIRE(b >= 0 && b < nb && which >= 0 && which < 4, "glgm06: bad batch / buffer");
-    const GP& h = F->gset[0];
+    const GP& h = F->gset[b % Flowpipe::NSET];
     const int64_t cnt = b == 0 ? 1 : F->sched[b - 1].cnt, slot0 = b == 0 ? 0 : F->sched[b - 1].have;
     *dtype = 0;
     if (which == 0) { *ptr = h.hS; *count = cnt * F->q; }
@@ -2784,7 +2833,15 @@ int32_t reach_glgm06_shard_nbatches(reach_flowpipe* fp, int64_t* nbatches) {
 int32_t reach_glgm06_shard_phase(reach_flowpipe* fp, int64_t batch, int32_t phase) {
     if (!fp) return REACH_EINVAL;
     FP_BEGIN(fp->ctx)
-    flowpipe_shard_phase(fp->f, batch, phase);
+    flowpipe_shard_phase(fp->f, batch, phase, nullptr);
+    return REACH_OK;
+    FP_END(fp->ctx)
+}
+
+int32_t reach_glgm06_shard_phase_on(reach_flowpipe* fp, int64_t batch, int32_t phase, void* cuda_stream) {
+    if (!fp) return REACH_EINVAL;
+    FP_BEGIN(fp->ctx)
+    flowpipe_shard_phase(fp->f, batch, phase, reinterpret_cast<cudaStream_t>(cuda_stream));
     return REACH_OK;
     FP_END(fp->ctx)
 }

@@ -98,7 +98,7 @@ def _device_tensor(ptr, count, typestr, device):
     return torch.as_tensor(a, device=device)
 
 
-def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None):
+def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None, gemm_stream=None):
     """Drive a column-sharded GLGM06 flowpipe: `engine` exposes nbatches(), phase(batch, phase) and
     buffer(batch, which) (backend.ShardedFlowpipe, or a mock on CPU); `as_tensor` turns what buffer() returns into a
     torch tensor aliasing the engine's memory (default: a zero-copy view of the device buffer).
@@ -107,7 +107,14 @@ def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None):
     stream=torch.cuda.current_stream().cuda_stream)``).  The NCCL all-reduces are then ordered against the phases on the
     device (torch makes the collective wait for the current stream and the current stream wait for the collective), and
     the host enqueues the whole flowpipe without a single synchronisation.  Default: detected from the engine's context;
-    otherwise the stream is synchronised around every collective."""
+    otherwise the stream is synchronised around every collective.
+
+    `gemm_stream` (a second ``torch.cuda.Stream``; needs `stream_ordered`): software pipeline across batches.  Phase 0 of batch
+    b + 1 -- the map of the rank's own generator columns (the DMMA GEMM for a dense Phi) and their scores -- is issued on
+    `gemm_stream` BEFORE phases 1..3 of batch b are issued on the current stream, so the dominant GEMM overlaps the selection
+    chain, the box sums and their all-reduces of the previous batch (reach_glgm06_shard_phase_on; the library orders the reuse
+    of its batch-local arrays).  The all-reduce of the scores of batch b + 1 is issued AFTER the collectives of batch b, so one
+    NCCL communicator keeps its collectives in an order that never makes batch b wait for the GEMM of batch b + 1."""
     import torch
     if as_tensor is None:
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -122,6 +129,34 @@ def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None):
         def sync():
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
+    if gemm_stream is not None:
+        if not stream_ordered:
+            raise ValueError("run_sharded: gemm_stream needs a context created on torch's current stream (stream_ordered)")
+        main = torch.cuda.current_stream()
+        nb = engine.nbatches()
+
+        def reduce_buffers(b, phase):
+            for which in SHARD_COLLECTIVES[phase]:
+                buf = engine.buffer(b, which)
+                if buf is not None:
+                    dist.all_reduce(as_tensor(buf), op=dist.ReduceOp.SUM)
+
+        gemm_stream.wait_stream(main)
+        engine.phase(0, 0, stream=gemm_stream.cuda_stream)
+        for b in range(nb):
+            with torch.cuda.stream(gemm_stream):
+                reduce_buffers(b, 0)                                    # scores / masks of batch b (its phase 0 is in flight)
+                ready = torch.cuda.Event()
+                ready.record(gemm_stream)
+                if b + 1 < nb:
+                    engine.phase(b + 1, 0, stream=gemm_stream.cuda_stream)     # overlaps everything below
+            main.wait_event(ready)
+            for phase in (1, 2, 3):
+                engine.phase(b, phase, stream=main.cuda_stream)
+                reduce_buffers(b, phase)
+        main.wait_stream(gemm_stream)
+        sync()
+        return engine
     for b in range(engine.nbatches()):
         for phase in range(4):
             engine.phase(b, phase)

@@ -31,3 +31,16 @@ def ctx(lib_path):
     c = rb.Context(int(os.environ.get("REACH_TEST_DEVICE", "0")))
     yield c
     c.close()
+
+
+@pytest.fixture()
+def ctx_on_torch_stream(lib_path):
+    """A `reach_ctx` that borrows a torch CUDA stream (reach_ctx_create_on_stream): what the stream-ordered multi-GPU driver
+    uses, so that torch / NCCL work and the library's kernels are ordered on the device."""
+    import torch
+    import reachability_jl_b200 as rb
+    dev = int(os.environ.get("REACH_TEST_DEVICE", "0"))
+    stream = torch.cuda.Stream(device=dev)
+    c = rb.Context(dev, stream=stream.cuda_stream)
+    yield c, stream
+    c.close()

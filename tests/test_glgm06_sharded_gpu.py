@@ -39,6 +39,41 @@ class _EmulatedRanks:
                         t.copy_(total)
                 torch.cuda.synchronize()
 
+    def _reduce(self, b, phase):
+        for which in sharding.SHARD_COLLECTIVES[phase]:
+            bufs = [e.buffer(b, which) for e in self.engines]
+            if bufs[0] is None:
+                assert all(x is None for x in bufs)
+                continue
+            ts = [sharding._device_tensor(p, c, d, self.dev) for (p, c, d) in bufs]
+            total = torch.stack(ts).sum(dim=0)
+            for t in ts:
+                t.copy_(total)
+
+    def run_pipelined(self):
+        """The order of sharding.run_sharded(..., gemm_stream=...): phase 0 of batch b + 1 on a second stream, issued before
+        phases 1..3 of batch b; the emulated collectives run on the stream of their phase, nothing synchronises the host."""
+        sg, sm = torch.cuda.Stream(), torch.cuda.Stream()
+        nb = self.engines[0].nbatches()
+        torch.cuda.synchronize()
+        for e in self.engines:
+            e.phase(0, 0, stream=sg.cuda_stream)
+        for b in range(nb):
+            with torch.cuda.stream(sg):
+                self._reduce(b, 0)
+                ready = torch.cuda.Event()
+                ready.record(sg)
+            if b + 1 < nb:
+                for e in self.engines:
+                    e.phase(b + 1, 0, stream=sg.cuda_stream)
+            sm.wait_event(ready)
+            with torch.cuda.stream(sm):
+                for phase in (1, 2, 3):
+                    for e in self.engines:
+                        e.phase(b, phase, stream=sm.cuda_stream)
+                    self._reduce(b, phase)
+        torch.cuda.synchronize()
+
     def step(self, k):
         p = self.engines[0].ngens()
         parts = [e.step(k, int(p[k - 1])) for e in self.engines]
@@ -123,4 +158,61 @@ def test_column_sharded_flowpipe_with_structurally_sparse_phi(ctx):
         assert_close(c, R[k - 1].c, f"centre {k}")
         assert_close(G, R[k - 1].G, f"generators {k}")
     for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("n,m,N,r", [(33, 2, 330, 3), (64, 5, 200, 4)])
+def test_pipelined_phase_order_equals_serial_phase_order(ctx, nranks, n, m, N, r):
+    """reach_glgm06_shard_phase_on: phase 0 of batch b + 1 issued on a second stream before phases 1..3 of batch b (>= 4 batches,
+    so every batch-local array set is reused) gives the bits of the in-order run, and repeats them when run again."""
+    A, X0, B, U = _problem(500 + n, n, m)
+    D = orc.discretize_zonotope(A, X0, 0.01, B, U)
+    Om = orc.reduce_order(D.Omega0, r)
+    mk = lambda: [ctx.glgm06_sharded(D.Phi, Om.c, Om.G, N, r, D.V.c, D.V.G, rk, nranks) for rk in range(nranks)]
+    ser, pip = _EmulatedRanks(mk()), _EmulatedRanks(mk())
+    ser.run()
+    pip.run_pipelined()
+    pip.run_pipelined()                  # a second run starts from scratch
+    p = ser.engines[0].ngens()
+    assert np.array_equal(p, pip.engines[0].ngens())
+    for k in sorted(set([1, 2, 3, 64, 65, 129, 200, N - 1, N]) & set(range(1, N + 1))):
+        cs, Gs = ser.step(k)
+        cp, Gp = pip.step(k)
+        assert np.array_equal(cs, cp) and np.array_equal(Gs, Gp), k
+    Ro = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, r)
+    c, G = pip.step(N)
+    assert G.shape == Ro[N - 1].G.shape
+    assert_close(c, Ro[N - 1].c, "pipelined sharded centre")
+    assert_close(G, Ro[N - 1].G, "pipelined sharded generators")
+    for e in ser.engines + pip.engines:
+        e.close()
+
+
+def test_run_sharded_with_a_gemm_stream_single_rank(ctx_on_torch_stream):
+    """sharding.run_sharded(..., gemm_stream=...) itself (one rank, no-op collective) against the oracle."""
+    ctx, stream = ctx_on_torch_stream
+
+    class _Solo:
+        class ReduceOp:
+            SUM = None
+
+        @staticmethod
+        def all_reduce(t, op=None):
+            return None
+
+    A, X0, B, U = _problem(77, 40, 3)
+    D = orc.discretize_zonotope(A, X0, 0.01, B, U)
+    Om = orc.reduce_order(D.Omega0, 3)
+    N = 280
+    with torch.cuda.stream(stream):
+        e = ctx.glgm06_sharded(D.Phi, Om.c, Om.G, N, 3, D.V.c, D.V.G, 0, 1)
+        sharding.run_sharded(e, _Solo, gemm_stream=torch.cuda.Stream())
+        p = e.ngens()
+        Ro = orc.glgm06_reach_inhomog(Om, D.V, D.Phi, N, 3)
+        for k in (1, 2, 100, 257, N):
+            c, G = e.step(k, int(p[k - 1]))
+            assert G.shape == Ro[k - 1].G.shape
+            assert_close(c, Ro[k - 1].c, f"centre {k}")
+            assert_close(G, Ro[k - 1].G, f"generators {k}")
         e.close()

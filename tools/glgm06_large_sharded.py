@@ -36,6 +36,9 @@ with rb.Context(dev, stream=stream.cuda_stream) as ctx:
             best = min(best, t["run_ms"])
         out["single_gpu"] = {"ms": best, "steps_per_s": (N - 1) / (best * 1e-3), "gemm_ms": t["gemm_ms"], "numerics_ms": t["numerics_ms"],
                              "chain_ms": t["chain_ms"], "gemm_tflops": t["gemm_flops"] / (best * 1e-3) * 1e-12, "map": fp.map_info()}
+        out["single_gpu"]["chain_info"] = fp.chain_info()
+        fp.set_serial(True); fp.run(); ts = fp.timing(); fp.set_serial(False)
+        out["single_gpu"]["alone"] = {k: ts[k] for k in ("run_ms", "gemm_ms", "numerics_ms", "chain_ms")}
         pmax = int(fp.ngens().max())
         ref_c, ref_G = fp.step(N, int(fp.ngens()[N - 1]))
         fp.close()
@@ -51,7 +54,8 @@ with rb.Context(dev, stream=stream.cuda_stream) as ctx:
             SUM = None
     d = dist if world > 1 else _Solo
     fs = ctx.glgm06_sharded(Phi, c0, G0red, N, order, V[0], V[1], rank, world)
-    sharding.run_sharded(fs, d)
+    gs = None if os.environ.get("SERIAL_PHASES") else torch.cuda.Stream(device=dev)
+    sharding.run_sharded(fs, d, gemm_stream=gs)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -59,7 +63,7 @@ with rb.Context(dev, stream=stream.cuda_stream) as ctx:
     reps = 3
     e0.record(stream)
     for _ in range(reps):
-        sharding.run_sharded(fs, d)
+        sharding.run_sharded(fs, d, gemm_stream=gs)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -67,7 +71,7 @@ with rb.Context(dev, stream=stream.cuda_stream) as ctx:
         tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    out["sharded"] = {"ms": ms, "steps_per_s": (N - 1) / (ms * 1e-3), "ranks": world}
+    out["sharded"] = {"ms": ms, "steps_per_s": (N - 1) / (ms * 1e-3), "ranks": world, "pipelined": gs is not None}
     # last reach set of the sharded run against the single-GPU engine (same library, bit-identical selections expected)
     p = fs.ngens()
     if world > 1:
