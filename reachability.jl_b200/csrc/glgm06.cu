@@ -22,8 +22,11 @@
 //    the discarded generators (fixed summation order, no float atomics), the R-side selection [Phi^k G0 | W_{k-1}]
 //    against the per-step snapshot of W, the gather of the kept generators into the flowpipe slots (columns staged through
 //    shared memory with bulk copies, TMA engine), centres, and the dense box generators.
-//  * PIPELINE.  Five streams: map of batch b+1 (main) | scores + segment order | selection chain of batch b (owns one SM) |
-//    R sortperm | numerics of batch b-1; the persistent GEMM leaves K SMs to the chain and the HBM-bound numerics.
+//  * PIPELINE.  Six streams: map of batch b+1 (main) | scores + segment order | selection chain of batch b | W box sums + W
+//    recurrence | R sortperm + R box sums of batch b-1; the persistent GEMM leaves K SMs to the chain and the HBM-bound numerics.
+//  * The reach sets themselves are stored as REFERENCES (kept generators) + box vector; dense matrices are materialised on
+//    demand (fetch / step / box / projection kernels).  The steady-state selection runs as a PARALLEL chain (one warp per
+//    generator, chain_fast_kernel), the sequential merge-path chain is the fallback.
 //  * SPARSE PHI.  When Phi (and the powers the run uses) has at most 8 non-zeros per row, the map is an ELL sparse product
 //    fused with the Girard scores instead of the GEMM (decoupled modes: the ISS-shaped C2).
 //  * All counts live on the device; the host enqueues the whole flowpipe without synchronising.
