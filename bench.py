@@ -360,6 +360,41 @@ def run_c4_lazy(w, dev, N, nrows=31):
             "api": "reach_sparse_create + reach_discretize_box_sparse + reach_bffpsv18_boxes_lazy (best of 3, CUDA events)"}
 
 
+def run_c4_lazy_sharded(rank, world, dist, N=160):
+    """Rider of the default line: C4 (n = 10913, sparse A) with `exp_method = "lazy"` and ALL rows of interest, the rows sharded
+    over the ranks (no exchange: every row of e^{k delta A} advances on its own).  Same boxes as the dense
+    DMMA recurrence of the `c4_mna5` rider (tests/test_lazy_sparse_gpu.py), 2 x 22 x nnz x rows flop per step instead of 2 n^2 rows."""
+    import scipy.sparse as sp
+    import torch
+    import reachability_jl_b200 as rb
+    from reachability_jl_b200 import workloads as wl
+    w = wl.mna5()
+    n = w.n
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    rows = np.array(shard_rows(n, w.partition, rank, world), dtype=np.int32)
+    with rb.Context(dev) as ctx:
+        S = ctx.sparse(sp.csc_matrix(w.A))
+        Ds = S.discretize_box(w.delta, w.c, w.r, w.B, w.cU, w.rU)
+        S.bffpsv18_boxes(w.delta, Ds["c0"], Ds["r0"], 8, Ds["MU"], Ds["cU"], Ds["rU"], Ds["rpsi"], rows)      # warm-up
+        _barrier(dist, world)
+        S.bffpsv18_boxes(w.delta, Ds["c0"], Ds["r0"], N, Ds["MU"], Ds["cU"], Ds["rU"], Ds["rpsi"], rows)
+        t = S.timing()
+        S.close()
+    ms = _max_over_ranks(dist, world, t["run_ms"], dev)
+    if rank != 0:
+        return None
+    return {"value": (N - 1) / (ms * 1e-3), "unit": "flowpipe steps/s", "ms_per_step": ms, "rows_per_gpu": int(len(rows)),
+            "reach_sets_timed": N, "scaling": "strong",
+            "config": {"workload": f"C4-mna5: n={n}, m={w.m}, BFFPSV18 {n} blocks of dim 1, delta={w.delta}, exp_method=lazy (sparse A, "
+                                   f"nnz={int(np.count_nonzero(w.A))}), first {N} reach sets, all rows",
+                       "parallelism": "single GPU" if world == 1 else f"rows sharded x{world}, sparse A replicated, no collective"},
+            "roofline": {"bound": "hbm", "achieved": t["bytes"] / (t["run_ms"] * 1e-3) / 1e9, "peak": _peaks()[0], "unit": "GB/s",
+                         "frac": t["bytes"] / (t["run_ms"] * 1e-3) / 1e9 / _peaks()[0],
+                         "kernel": "spmm_taylor_kernel (Horner terms of the action of e^{delta A^T} on 256-row panels; algorithmic "
+                                   "bytes 12 nnz + 24 n R per term, rank 0's rows; the panels are sized to stay in L2)"},
+            "api": "reach_sparse_create + reach_discretize_box_sparse + reach_bffpsv18_boxes_lazy (CUDA events inside the library, max over ranks)"}
+
+
 def build_zono_workload():
     """Discretised GLGM06 problem of config C2 (ISS-shaped, n=270, max_order 10) on the HOST, for the CPU legs only: Omega0
     (already reduce_order'ed, GLGM06/post.jl:20), V and Phi."""
@@ -1102,6 +1137,7 @@ def main():
         shard_dense = run_glgm06_column_sharded(rank, world, dist, dense=True) if world > 1 else None
         multi = run_inprocess_multi(rank, world, dist) if world > 1 else None
         large = run_glgm06_large(rank, world, dist)
+        lazy4 = run_c4_lazy_sharded(rank, world, dist)
         if out is not None:
             out["riders"] = {"c4_mna5": {k: r4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling")},
                              "c5_ensemble": {k: r5[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "scaling", "e2e")}}
@@ -1124,6 +1160,9 @@ def main():
                 if "column_sharded" in large:
                     flat.update(glgm06_n1024_column_sharded_value=large["column_sharded"]["value"],
                                 glgm06_n1024_column_sharded_speedup=large["column_sharded"]["speedup_vs_one_gpu"])
+            if lazy4 is not None:
+                out["riders"]["c4_lazy_expm_all_rows"] = lazy4
+                flat.update(c4_lazy_value=lazy4["value"], c4_lazy_frac=lazy4["roofline"]["frac"])
             if multi is not None:
                 out["riders"]["c3_one_process_multi_device"] = multi
                 flat["c3_one_process_multi_device_e2e"] = multi["value"]
