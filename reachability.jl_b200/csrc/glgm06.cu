@@ -1783,8 +1783,9 @@ struct Flowpipe {
     // batch-local arrays, NSET-fold buffered: with two sets the loop numerics(b-1) -> map(b+1) -> sort -> chain(b+1) ->
     // numerics(b+1) spans two batches and left a gap between consecutive chains (0.31 ms per batch at C2); with three sets it
     // spans three and the chain (0.25 ms per batch) runs back to back
-    static constexpr int NSET = 3;
-    GP gset[NSET];
+    static constexpr int NSET_MAX = 8;
+    int nset = 3;                   // sets in use (REACH_GLGM06_SETS, diagnostics)
+    GP gset[NSET_MAX];
     std::vector<void*> owned;
     std::vector<int2> meta_host;
     bool ran = false;
@@ -1959,7 +1960,8 @@ Flowpipe* flowpipe_create(Ctx* ctx, int64_t n, const double* Phi, int64_t ldphi,
             F->chain_smem = (size_t)g.capW * 32 + (size_t)(pV + 2) * 32 + (size_t)g.capDisc * 4 + 64;
             F->chain_use_smem = F->chain_smem <= 200 * 1024 ? 1 : 0;
             if (!F->chain_use_smem) F->scr = (double*)own(dalloc<double>(ctx, F->chain_smem / 8 + 8));
-            for (int b = 0; b < Flowpipe::NSET; ++b) {      // batch-local arrays, one set per batch in flight
+            if (const char* e = getenv("REACH_GLGM06_SETS")) F->nset = std::max(2, std::min(Flowpipe::NSET_MAX, atoi(e)));
+            for (int b = 0; b < F->nset; ++b) {      // batch-local arrays, one set per batch in flight
                 GP& h = F->gset[b];
                 h.hS = (double*)own(dalloc<double>(ctx, sq));
                 h.skS = (double*)own(dalloc<double>(ctx, sq));
@@ -2381,8 +2383,8 @@ void flowpipe_run(Flowpipe* F) {
         if (!F->homog && lvl < F->ell_levels && !F->serial) {
             // sparse Phi: the map also produces the scores, so it writes into this batch's array set and has to wait for the
             // numerics that last used it (two batches back)
-            bind_set(g, F->gset[bi % Flowpipe::NSET]);
-            if (bi >= Flowpipe::NSET) REACH_CUDA(cudaStreamWaitEvent(st, ev_num[bi - Flowpipe::NSET], 0));
+            bind_set(g, F->gset[bi % F->nset]);
+            if (bi >= F->nset) REACH_CUDA(cudaStreamWaitEvent(st, ev_num[bi - F->nset], 0));
             cudaEvent_t e0 = next_event(F, ev_used), e1 = next_event(F, ev_used);
             gemm_ev.push_back({ev_used - 2, ev_used - 1});
             REACH_CUDA(cudaEventRecord(e0, st));
@@ -2397,8 +2399,8 @@ void flowpipe_run(Flowpipe* F) {
             REACH_CUDA(cudaEventRecord(ev_gemm, st));
             // scores / segment order: after this batch's GEMM and after the numerics that last used this array set
             REACH_CUDA(cudaStreamWaitEvent(sSort, ev_gemm, 0));
-            if (bi >= Flowpipe::NSET) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - Flowpipe::NSET], 0));
-            bind_set(g, F->gset[bi % Flowpipe::NSET]);
+            if (bi >= F->nset) REACH_CUDA(cudaStreamWaitEvent(sSort, ev_num[bi - F->nset], 0));
+            bind_set(g, F->gset[bi % F->nset]);
             if (scored) {
                 g.Y = F->Hflow + have * F->qloc * ld;
                 g.col0 = have * F->q;
@@ -2567,14 +2569,14 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase, cudaStream_t on) {
         for (size_t i = have_ev; i < (size_t)nb; ++i) REACH_CUDA(cudaEventCreateWithFlags(&F->shard_done[i], cudaEventDisableTiming));
     }
     GP g = F->g;
-    const int si = (int)(b % Flowpipe::NSET);
+    const int si = (int)(b % F->nset);
     bind_set(g, F->gset[si]);
     if (phase == 0) {
         REACH_REQUIRE(b == 0 || b == F->next_p0, "glgm06: phase 0 of the sharded batches must be issued in order");
-        if (b >= Flowpipe::NSET) {
-            REACH_REQUIRE(F->next_batch > b - Flowpipe::NSET,
+        if (b >= F->nset) {
+            REACH_REQUIRE(F->next_batch > b - F->nset,
                           "glgm06: phase 0 of a batch may run at most NSET - 1 batches ahead of phases 1..3");
-            REACH_CUDA(cudaStreamWaitEvent(st, F->shard_done[b - Flowpipe::NSET], 0));
+            REACH_CUDA(cudaStreamWaitEvent(st, F->shard_done[b - F->nset], 0));
         }
     } else {
         REACH_REQUIRE(b == F->next_batch && b < F->next_p0, "glgm06: sharded batches must be processed in order (phase 0 first)");
@@ -2663,7 +2665,7 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase, cudaStream_t on) {
 void flowpipe_shard_buffer(Flowpipe* F, int64_t b, int which, void** ptr, int64_t* count, int* dtype) {
     const int64_t nb = flowpipe_shard_nbatches(F);
     REACH_REQUIRE(b >= 0 && b < nb && which >= 0 && which < 4, "glgm06: bad batch / buffer");
-    const GP& h = F->gset[b % Flowpipe::NSET];
+    const GP& h = F->gset[b % F->nset];
     const int64_t cnt = b == 0 ? 1 : F->sched[b - 1].cnt, slot0 = b == 0 ? 0 : F->sched[b - 1].have;
     *dtype = 0;
     if (which == 0) { *ptr = h.hS; *count = cnt * F->q; }
