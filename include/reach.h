@@ -133,12 +133,19 @@ REACH_API int32_t reach_bffpsv18_boxes(reach_ctx* ctx, int64_t n, const double* 
                              double* centers, double* radii, int64_t* steps_done);
 /* The sparse twin, reach_blocks!(ϕ::SparseMatrixCSC{Float64,Int}, ...) (reach_blocks.jl:47-132; `:assume_sparse`): Φ crosses the
  * ABI as its CSC fields (colptr n+1, rowval nnz, nzval nnz; 1-based Int64).  The sparse method computes the same sets as the
- * dense one (it only skips zero blocks) and Φ^k fills in, so the device scatters Φ into its dense layout and runs the same
- * DMMA recurrence; results are bit-identical to reach_bffpsv18_boxes on Matrix(Φ). */
+ * dense one -- it only skips the blocks of Φ^k that are zero.  Two device paths:
+ *  (a) the sparsity graph of Φ falls into connected components of at most 16 states (decoupled subsystems, block-diagonal up
+ *      to a permutation): every power of Φ keeps that pattern, so row l of Φ^k lives on the columns of its component and the
+ *      zero blocks are skipped for good -- one thread per row of interest runs the whole recurrence, w^2 fma per step instead
+ *      of 2 n^2 (same sets as the dense path to rounding: the sums run over the same non-zero terms in ascending order);
+ *  (b) anything else: Φ^k fills in, the device scatters Φ into its dense layout and runs the DMMA recurrence; results are
+ *      bit-identical to reach_bffpsv18_boxes on Matrix(Φ).
+ * reach_bffpsv18_csc_info reports which path served the last call on this context (largest component, 0 = path (b)). */
 REACH_API int32_t reach_bffpsv18_boxes_csc(reach_ctx* ctx, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
                                    const double* nzval, const double* c0, const double* r0, int64_t m, const double* MU,
                                    int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
                                    const int32_t* rows, int64_t N, double* centers, double* radii, int64_t* steps_done);
+REACH_API int32_t reach_bffpsv18_csc_info(reach_ctx* ctx, int64_t* max_component, int32_t* sparse_path);
 /* Same computation split into upload / device-resident run / download (what bench.py times as `value`). */
 REACH_API int32_t reach_boxplan_create(reach_ctx* ctx, int64_t n, const double* Phi, int64_t ldphi, const double* c0,
                              const double* r0, int64_t m, const double* MU, int64_t ldmu, const double* cU,

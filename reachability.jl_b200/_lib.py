@@ -50,6 +50,7 @@ _SIGNATURES = {
     "reach_bffpsv18_boxes": _BOX_ARGS + [c_double_p, c_double_p, c_int64_p],
     "reach_bffpsv18_boxes_csc": [vp, i64, i64, c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p, i64, c_double_p, i64,
                                  c_double_p, c_double_p, c_double_p, i64, c_int32_p, i64, c_double_p, c_double_p, c_int64_p],
+    "reach_bffpsv18_csc_info": [vp, c_int64_p, c_int32_p],
     "reach_boxplan_create": _BOX_ARGS + [C.POINTER(vp)],
     "reach_boxplan_run": [vp],
     "reach_boxplan_fetch": [vp, c_double_p, c_double_p],

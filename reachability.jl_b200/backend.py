@@ -247,6 +247,14 @@ class Context:
                                                       dptr(centers), dptr(radii), C.byref(done)))
         return centers, radii
 
+    def csc_info(self):
+        """Which device path served the last `bffpsv18_boxes_csc` call: dict(max_component, sparse_path) --
+        sparse_path is True when Φ was block-diagonal up to a permutation (components of <= 16 states) and the zero blocks
+        were skipped (reach_bffpsv18_csc_info)."""
+        a, b = C.c_int64(), C.c_int32()
+        self._check(self.lib.reach_bffpsv18_csc_info(self._h, C.byref(a), C.byref(b)))
+        return dict(max_component=int(a.value), sparse_path=bool(b.value))
+
     def boxplan(self, Phi, c0, r0, N, MU=None, cU=None, rU=None, rpsi=None, rows=None) -> "BoxPlan":
         return BoxPlan(self, Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
 

@@ -17,6 +17,8 @@
 #include "../../include/reach.h"
 #include <algorithm>
 #include <climits>
+#include <cstring>
+#include <vector>
 
 namespace reach {
 
@@ -359,6 +361,224 @@ int64_t choose_block(int64_t n, int64_t Rp, int64_t N, int64_t m, int sms) {
 }  // namespace
 
 void boxplan_destroy(BoxPlan* P);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Structurally sparse Phi (sparse `reach_blocks!`, reach_blocks.jl:47-132, option :assume_sparse).  The sparse method of
+// the reference skips the blocks of Phi^k that are zero.  When the sparsity graph of Phi falls into small connected
+// components (decoupled subsystems: block-diagonal up to a permutation), EVERY power of Phi has the same pattern, so row l of
+// P_k lives on the w <= 16 columns of its component and the whole recurrence of that row is
+//     p <- p * Phi[comp, comp]                       (w^2 fma per step instead of 2 n^2)
+// independent of every other row.  One thread per row of interest runs all N steps with p in registers; the sums run over
+// ascending column index like the dense GEMM's k loop (the skipped terms are exact zeros).  Anything else (a component larger
+// than BD_MAX) keeps the dense DMMA recurrence: Phi^k fills in and the zero blocks disappear after a few steps.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BD_MAX = 16;
+
+namespace {
+
+struct BdRow { int w, jr, mem_off; int64_t blk_off; };      // component width, position of the row in it, offsets of its members / block
+
+template <int W>
+__global__ void __launch_bounds__(128) blockdiag_boxes_kernel(int nrows, int m, int64_t N, int wlo, const BdRow* __restrict__ info,
+                                                              const int* __restrict__ members, const double* __restrict__ blocks,
+                                                              const int32_t* __restrict__ rows, const double* __restrict__ c0,
+                                                              const double* __restrict__ r0, const double* __restrict__ rpsi,
+                                                              const double* __restrict__ MU, int64_t ldmu,
+                                                              const double* __restrict__ cU, const double* __restrict__ rU,
+                                                              double* __restrict__ centers, double* __restrict__ radii) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nrows) return;
+    const BdRow ri = info[l];
+    if (ri.w <= wlo || ri.w > W) return;              // rows are served by the narrowest instantiation that holds their component
+    const int w = ri.w;
+    const int* mem = members + ri.mem_off;
+    const double* B = blocks + ri.blk_off;           // B[j * w + c] = Phi[mem[j], mem[c]]
+    double p[W], c0w[W], r0w[W], psw[W];
+    int col[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const bool on = j < w;
+        col[j] = on ? mem[j] : 0;
+        p[j] = on ? B[ri.jr * w + j] : 0.0;          // P_1[l, :] = Phi[row, :]
+        c0w[j] = on ? c0[col[j]] : 0.0;
+        r0w[j] = on ? r0[col[j]] : 0.0;
+        psw[j] = (on && m > 0) ? rpsi[col[j]] : 0.0;
+    }
+    const int row = rows[l];
+    // step 1: Xhat0[row]; What_1 = box(V)[row]  (reach_blocks.jl:152-158, 172-175)
+    centers[l] = c0[row];
+    radii[l] = r0[row];
+    double cw = 0.0, rw = 0.0;
+    for (int q = 0; q < m; ++q) {
+        const double mu = MU[(int64_t)q * ldmu + row];
+        cw += mu * cU[q];
+        rw += fabs(mu) * rU[q];
+    }
+    if (m > 0) rw += rpsi[row];
+    for (int64_t k = 1; k < N; ++k) {                // p = P_k[l, comp] yields reach set k + 1 (column k)
+        double a = 0.0, b = 0.0, f = 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            a = fma(p[j], c0w[j], a);
+            b = fma(fabs(p[j]), r0w[j], b);
+            f = fma(fabs(p[j]), psw[j], f);
+        }
+        centers[k * nrows + l] = a + cw;
+        radii[k * nrows + l] = b + rw;
+        if (k + 1 < N) {
+            if (m > 0) {
+                double dc = 0.0, dr = 0.0;
+                for (int u = 0; u < m; ++u) {
+                    double e = 0.0;
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                        if (j < w) e = fma(p[j], MU[(int64_t)u * ldmu + col[j]], e);
+                    dc += e * cU[u];
+                    dr += fabs(e) * rU[u];
+                }
+                cw += dc;
+                rw += dr + f;
+            }
+            double pn[W];
+#pragma unroll
+            for (int c = 0; c < W; ++c) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < W; ++j)
+                    if (j < w && c < w) acc = fma(p[j], B[j * w + c], acc);
+                pn[c] = acc;
+            }
+#pragma unroll
+            for (int c = 0; c < W; ++c) p[c] = pn[c];
+        }
+    }
+}
+
+}  // namespace
+
+// Connected components of the sparsity graph of Phi (CSC, 1-based): returns false as soon as one exceeds BD_MAX.
+bool blockdiag_analyse(int64_t n, const PhiCsc& csc, std::vector<int>& comp_of, std::vector<std::vector<int>>& comps) {
+    std::vector<int> parent(n), size(n, 1);
+    for (int64_t i = 0; i < n; ++i) parent[i] = (int)i;
+    auto find = [&](int x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    };
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t q = csc.colptr[j] - 1; q < csc.colptr[j + 1] - 1; ++q) {
+            if (csc.nzval[q] == 0.0) continue;
+            const int64_t i = csc.rowval[q] - 1;
+            REACH_REQUIRE(i >= 0 && i < n, "bffpsv18 (csc): row index out of range");
+            int a = find((int)i), b = find((int)j);
+            if (a == b) continue;
+            if (size[a] < size[b]) std::swap(a, b);
+            parent[b] = a;
+            size[a] += size[b];
+            if (size[a] > BD_MAX) return false;
+        }
+    comp_of.assign(n, -1);
+    comps.clear();
+    std::vector<int> id(n, -1);
+    for (int64_t i = 0; i < n; ++i) {                // ascending i => members of every component come out sorted
+        const int r = find((int)i);
+        if (id[r] < 0) { id[r] = (int)comps.size(); comps.emplace_back(); }
+        comp_of[i] = id[r];
+        comps[id[r]].push_back((int)i);
+    }
+    return true;
+}
+
+// The whole flowpipe of the rows of interest for a block-diagonal Phi; results straight into the caller's host arrays.
+// Returns false (nothing done) when Phi is not block-diagonal with components of at most BD_MAX states.
+bool boxes_blockdiag(Ctx* ctx, int64_t n, const PhiCsc& csc, const double* c0, const double* r0, int64_t m, const double* MU,
+                     int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows,
+                     int64_t N, double* centers, double* radii, int64_t* max_component) {
+    REACH_REQUIRE(n > 0 && c0 && r0 && csc.colptr && (csc.nnz == 0 || (csc.rowval && csc.nzval)), "bffpsv18 (csc): bad Phi/c0/r0");
+    REACH_REQUIRE(N >= 1 && nrows > 0 && nrows <= n && rows, "bffpsv18 (csc): bad N / rows");
+    if (!MU) m = 0;
+    if (m > 0) REACH_REQUIRE(cU && rU && rpsi && ldmu >= n, "bffpsv18: inputs need MU, cU, rU, rpsi");
+    for (int64_t i = 0; i < nrows; ++i) REACH_REQUIRE(rows[i] >= 0 && rows[i] < n, "bffpsv18: row index out of range");
+    std::vector<int> comp_of;
+    std::vector<std::vector<int>> comps;
+    if (!blockdiag_analyse(n, csc, comp_of, comps)) return false;
+    // members / dense blocks of the components that hold a row of interest
+    std::vector<int> mem_off(comps.size(), -1), members;
+    std::vector<int64_t> blk_off(comps.size(), -1);
+    std::vector<double> blocks;
+    std::vector<BdRow> info(nrows);
+    std::vector<int> pos(n, -1);
+    int maxw = 0;
+    for (int64_t l = 0; l < nrows; ++l) {
+        const int c = comp_of[rows[l]];
+        const std::vector<int>& mb = comps[c];
+        const int w = (int)mb.size();
+        maxw = std::max(maxw, w);
+        if (mem_off[c] < 0) {
+            mem_off[c] = (int)members.size();
+            blk_off[c] = (int64_t)blocks.size();
+            members.insert(members.end(), mb.begin(), mb.end());
+            blocks.resize(blocks.size() + (size_t)w * w, 0.0);
+            for (int j = 0; j < w; ++j) pos[mb[j]] = j;
+            double* Bk = blocks.data() + blk_off[c];
+            for (int cc = 0; cc < w; ++cc) {          // column mb[cc] of Phi
+                const int64_t col = mb[cc];
+                for (int64_t q = csc.colptr[col] - 1; q < csc.colptr[col + 1] - 1; ++q) {
+                    const int64_t i = csc.rowval[q] - 1;
+                    if (csc.nzval[q] != 0.0) Bk[(size_t)pos[i] * w + cc] = csc.nzval[q];
+                }
+            }
+        }
+        info[l] = BdRow{w, pos[rows[l]], mem_off[c], blk_off[c]};
+    }
+    if (max_component) *max_component = maxw;
+    DevScratch scr(ctx);
+    cudaStream_t st = ctx->stream;
+    auto up = [&](const void* src, size_t bytes) {
+        void* d = scr.get<unsigned char>(bytes ? bytes : 8);
+        if (bytes) REACH_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+        return d;
+    };
+    const BdRow* dinfo = (const BdRow*)up(info.data(), info.size() * sizeof(BdRow));
+    const int* dmem = (const int*)up(members.data(), members.size() * sizeof(int));
+    const double* dblk = (const double*)up(blocks.data(), blocks.size() * sizeof(double));
+    const int32_t* drows = (const int32_t*)up(rows, (size_t)nrows * sizeof(int32_t));
+    const double* dc0 = (const double*)up(c0, (size_t)n * 8);
+    const double* dr0 = (const double*)up(r0, (size_t)n * 8);
+    const double *dpsi = nullptr, *dMU = nullptr, *dcU = nullptr, *drU = nullptr;
+    std::vector<double> mu_packed;
+    if (m > 0) {
+        dpsi = (const double*)up(rpsi, (size_t)n * 8);
+        mu_packed.resize((size_t)n * m);
+        for (int64_t u = 0; u < m; ++u) std::memcpy(&mu_packed[(size_t)u * n], MU + u * ldmu, (size_t)n * 8);
+        dMU = (const double*)up(mu_packed.data(), mu_packed.size() * 8);
+        dcU = (const double*)up(cU, (size_t)m * 8);
+        drU = (const double*)up(rU, (size_t)m * 8);
+    }
+    double* dC = scr.get<double>((size_t)nrows * N);
+    double* dR = scr.get<double>((size_t)nrows * N);
+    const unsigned grid = (unsigned)ceil_div(nrows, 128);
+    REACH_CUDA(cudaEventRecord(ctx->ev0, st));
+#define REACH_BD_LAUNCH(W, WLO)                                                                                                     \
+    if (maxw > WLO) {                                                                                                               \
+        blockdiag_boxes_kernel<W><<<grid, 128, 0, st>>>((int)nrows, (int)m, N, WLO, dinfo, dmem, dblk, drows, dc0, dr0, dpsi, dMU, n, \
+                                                        dcU, drU, dC, dR);                                                          \
+        ctx->launches++;                                                                                                            \
+    }
+    REACH_BD_LAUNCH(2, 0)
+    REACH_BD_LAUNCH(4, 2)
+    REACH_BD_LAUNCH(8, 4)
+    REACH_BD_LAUNCH(16, 8)
+#undef REACH_BD_LAUNCH
+    REACH_CUDA(cudaGetLastError());
+    REACH_CUDA(cudaEventRecord(ctx->ev1, st));
+    REACH_CUDA(cudaMemcpyAsync(centers, dC, (size_t)nrows * N * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaMemcpyAsync(radii, dR, (size_t)nrows * N * 8, cudaMemcpyDeviceToHost, st));
+    REACH_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    REACH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->t_loop_ms = ms;
+    return true;
+}
 
 // Φ given as Julia's SparseMatrixCSC fields (1-based Int64): scattered into the zero-filled dense device matrix.  The sparse
 // reach_blocks! (reach_blocks.jl:47-132) computes the same sets as the dense one -- it only skips blocks that are zero --

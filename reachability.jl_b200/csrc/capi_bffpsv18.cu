@@ -20,6 +20,9 @@ void boxplan_attach_map(BoxPlan* P, int64_t q, const double* M, int64_t ldm, int
                         bool check, double bound, bool eager);
 void boxplan_fetch_map(BoxPlan* P, double* centers, double* radii, int64_t* violation);
 Ctx* ctx_of(reach_ctx* h);
+bool boxes_blockdiag(Ctx* ctx, int64_t n, const PhiCsc& csc, const double* c0, const double* r0, int64_t m, const double* MU,
+                     int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows, const int32_t* rows,
+                     int64_t N, double* centers, double* radii, int64_t* max_component);
 }  // namespace reach
 
 using namespace reach;
@@ -161,6 +164,14 @@ int32_t reach_bffpsv18_boxes(reach_ctx* h, int64_t n, const double* Phi, int64_t
     GUARD_END(ctx)
 }
 
+int32_t reach_bffpsv18_csc_info(reach_ctx* h, int64_t* max_component, int32_t* sparse_path) {
+    if (!h || !max_component || !sparse_path) return REACH_EINVAL;
+    Ctx* ctx = ctx_of(h);
+    *max_component = ctx->csc_max_component;
+    *sparse_path = ctx->csc_sparse_path;
+    return REACH_OK;
+}
+
 int32_t reach_bffpsv18_boxes_csc(reach_ctx* h, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
                                  const double* nzval, const double* c0, const double* r0, int64_t m, const double* MU,
                                  int64_t ldmu, const double* cU, const double* rU, const double* rpsi, int64_t nrows,
@@ -170,6 +181,16 @@ int32_t reach_bffpsv18_boxes_csc(reach_ctx* h, int64_t n, int64_t nnz, const int
     GUARD_BEGIN(ctx)
     REACH_REQUIRE(centers && radii, "reach_bffpsv18_boxes_csc: output buffers required");
     const PhiCsc csc{nnz, colptr, rowval, nzval};
+    // decoupled subsystems: Phi (and every power of it) is block-diagonal up to a permutation -> the zero blocks are skipped
+    // for good (reach_blocks.jl:47-132); REACH_BFFPSV18_CSC_DENSE=1 keeps the dense DMMA recurrence (A/B tests)
+    ctx->csc_max_component = 0;
+    ctx->csc_sparse_path = 0;
+    if (!getenv("REACH_BFFPSV18_CSC_DENSE") && colptr && rows &&
+        boxes_blockdiag(ctx, n, csc, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii, &ctx->csc_max_component)) {
+        ctx->csc_sparse_path = 1;
+        if (steps_done) *steps_done = N;
+        return REACH_OK;
+    }
     const std::vector<Ctx*> cs = ctxs_of(h);
     if (cs.size() > 1 && nrows > 1 && rows) {
         boxes_multi(cs, n, nullptr, 0, &csc, c0, r0, m, MU, ldmu, cU, rU, rpsi, nrows, rows, N, centers, radii);

@@ -63,6 +63,8 @@ struct Ctx {
     uint32_t gemm_sched_next = 0;
     std::string last_error;
     // launch accounting (bench.py "gpu_launches") and per-phase timings
+    int64_t csc_max_component = 0;  // last reach_bffpsv18_boxes_csc call: largest connected component of Phi's sparsity graph (0: not block-diagonal)
+    int csc_sparse_path = 0;        // ... and whether the block-diagonal recurrence served it
     uint64_t launches = 0;
     double t_discretize_ms = 0, t_loop_ms = 0, t_h2d_ms = 0, t_d2h_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

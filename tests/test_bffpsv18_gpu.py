@@ -239,9 +239,27 @@ def test_config_c4_mna5_full_dimension(ctx):
     assert np.all(full_r >= 0)
 
 
-def test_sparse_csc_phi_is_bit_identical_to_dense(ctx):
-    """reach_blocks!(ϕ::SparseMatrixCSC, ...) (reach_blocks.jl:47-132): same sets as the dense method; the device scatters the
-    CSC fields into its dense layout, so the results equal those of Matrix(Φ) bit for bit."""
+def _block_diagonal_phi(g, n, max_block, permute=True):
+    """Φ that is block-diagonal up to a random permutation of the states: blocks of 1 .. max_block states."""
+    Phi = np.zeros((n, n))
+    i = 0
+    sizes = []
+    while i < n:
+        w = int(min(n - i, g.integers(1, max_block + 1)))
+        Phi[i:i + w, i:i + w] = g.standard_normal((w, w)) * (0.9 / np.sqrt(w))
+        sizes.append(w)
+        i += w
+    if permute:
+        perm = g.permutation(n)
+        Phi = Phi[np.ix_(perm, perm)]
+    return Phi, max(sizes)
+
+
+@pytest.mark.parametrize("dense_csc", [True, False])
+def test_sparse_csc_phi_is_bit_identical_to_dense(ctx, dense_csc, monkeypatch):
+    """reach_blocks!(ϕ::SparseMatrixCSC, ...) (reach_blocks.jl:47-132): same sets as the dense method.  Path (b) of the sparse
+    twin scatters the CSC fields into the dense layout, so the results equal those of Matrix(Φ) bit for bit: taken by a Φ whose
+    sparsity graph is connected, and forced for a block-diagonal one with REACH_BFFPSV18_CSC_DENSE=1."""
     import scipy.sparse as sp
     g = np.random.default_rng(5)
     n, N = 41, 30
@@ -249,14 +267,82 @@ def test_sparse_csc_phi_is_bit_identical_to_dense(ctx):
     for i in range(0, n - 1, 2):                      # block-diagonal Φ stays sparse under powers
         Phi[i:i + 2, i:i + 2] = g.standard_normal((2, 2)) * 0.6
     Phi[-1, -1] = 0.5
+    if dense_csc:
+        monkeypatch.setenv("REACH_BFFPSV18_CSC_DENSE", "1")
+    else:
+        Phi[np.arange(n - 1), np.arange(1, n)] += 0.01           # a chain couples everything: one component of 41 states
     c0, r0 = g.standard_normal(n), np.abs(g.standard_normal(n))
     MU = g.standard_normal((n, 2)) * 0.1
     cU, rU, rpsi = g.standard_normal(2), np.abs(g.standard_normal(2)), np.abs(g.standard_normal(n)) * 0.01
     rows = np.array([0, 1, 7, 40], dtype=np.int32)
     Cd, Rd = ctx.bffpsv18_boxes(Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
     Cs, Rs = ctx.bffpsv18_boxes_csc(sp.csc_matrix(Phi), c0, r0, N, MU, cU, rU, rpsi, rows)
+    assert not ctx.csc_info()["sparse_path"]
     assert np.array_equal(Cs, Cd) and np.array_equal(Rs, Rd)
     P = orc.DiscreteBoxProblem(Phi, c0, r0, MU, cU, rU, rpsi, None, None)
     Co, Ro = orc.bffpsv18_reach(P, N, rows)
     assert_close(Cs.T, Co, "centres")
     assert_close(Rs.T, Ro, "radii")
+
+
+@pytest.mark.parametrize("n,max_block,m,N,subset", [(41, 2, 2, 60, True), (97, 4, 0, 130, False), (150, 8, 3, 90, True),
+                                                    (203, 16, 1, 75, False), (64, 1, 2, 40, False)])
+def test_block_diagonal_csc_phi_skips_the_zero_blocks(ctx, n, max_block, m, N, subset):
+    """Path (a) of the sparse twin (reach_blocks.jl:47-132 skips zero blocks): decoupled subsystems scattered by a random
+    permutation of the states.  Every row of Φ^k lives on its component, the recurrence costs w^2 fma per row and step; the sets
+    equal the oracle's and the dense DMMA path's."""
+    import scipy.sparse as sp
+    g = np.random.default_rng(1000 + n)
+    Phi, wmax = _block_diagonal_phi(g, n, max_block)
+    c0, r0 = g.standard_normal(n), np.abs(g.standard_normal(n))
+    MU = g.standard_normal((n, m)) * 0.1 if m else None
+    cU = g.standard_normal(m) if m else None
+    rU = np.abs(g.standard_normal(m)) if m else None
+    rpsi = np.abs(g.standard_normal(n)) * 0.01 if m else None
+    rows = np.sort(g.choice(n, size=max(3, n // 5), replace=False)).astype(np.int32) if subset else None
+    Cs, Rs = ctx.bffpsv18_boxes_csc(sp.csc_matrix(Phi), c0, r0, N, MU, cU, rU, rpsi, rows)
+    info = ctx.csc_info()
+    assert info["sparse_path"] and 1 <= info["max_component"] <= wmax
+    P = orc.DiscreteBoxProblem(Phi, c0, r0, MU, cU, rU, rpsi, None, None)
+    Co, Ro = orc.bffpsv18_reach(P, N, rows)
+    assert_close(Cs.T, Co, "centres (block-diagonal path)")
+    assert_close(Rs.T, Ro, "radii (block-diagonal path)")
+    Cd, Rd = ctx.bffpsv18_boxes(Phi, c0, r0, N, MU, cU, rU, rpsi, rows)
+    assert_close(Cs, Cd, "centres vs the dense device path")
+    assert_close(Rs, Rd, "radii vs the dense device path")
+    assert np.all(Rs >= 0)
+
+
+def test_block_diagonal_path_needs_small_components(ctx):
+    """One component of 17 states is beyond the block-diagonal path: the sparse twin falls back to the dense recurrence."""
+    import scipy.sparse as sp
+    g = np.random.default_rng(17)
+    n = 40
+    Phi, _ = _block_diagonal_phi(g, n, 3, permute=False)
+    Phi[:17, :17] += np.diag(np.full(16, 0.01), 1)              # chain over the first 17 states
+    c0, r0 = g.standard_normal(n), np.abs(g.standard_normal(n))
+    Cs, Rs = ctx.bffpsv18_boxes_csc(sp.csc_matrix(Phi), c0, r0, 25)
+    assert not ctx.csc_info()["sparse_path"]
+    Cd, Rd = ctx.bffpsv18_boxes(Phi, c0, r0, 25)
+    assert np.array_equal(Cs, Cd) and np.array_equal(Rs, Rd)
+
+
+def test_iss_shaped_modes_under_bffpsv18_full_length(ctx):
+    """The decoupled modes of the ISS-shaped C2 system under BFFPSV18 (1-D blocks, N = 2000): Φ = e^{Aδ} is 135 components of
+    two states, so the sparse twin runs the whole flowpipe in one launch; prefix against the oracle, every step against the
+    dense device path."""
+    import scipy.sparse as sp
+    from reachability_jl_b200 import workloads as wl
+    w = wl.iss()
+    D = orc.discretize_box(w.A, orc.Box(w.c, w.r), w.delta, w.B, orc.Box(w.cU, w.rU))
+    N = 2000
+    Phi = np.where(np.abs(D.Phi) > 0, D.Phi, 0.0)
+    Cs, Rs = ctx.bffpsv18_boxes_csc(sp.csc_matrix(Phi), D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi)
+    info = ctx.csc_info()
+    assert info["sparse_path"] and info["max_component"] == 2
+    Co, Ro = orc.bffpsv18_reach(D, 150)
+    assert_close(Cs[:, :150].T, Co, "centres")
+    assert_close(Rs[:, :150].T, Ro, "radii")
+    Cd, Rd = ctx.bffpsv18_boxes(Phi, D.c0, D.r0, N, D.MU, D.cU, D.rU, D.rpsi)
+    assert_close(Cs, Cd, "centres vs the dense device path, all 2000 steps")
+    assert_close(Rs, Rd, "radii vs the dense device path, all 2000 steps")
