@@ -171,6 +171,63 @@ function inputs_of(U::Union{ConstantInput,Nothing}, n::Int)
     return (size(MU, 2), MU, cU, rU, rψ)
 end
 
+# regroup the rows of (centers, radii) into the blocks' set types and fill the caller's `res` (store!, reach_blocks.jl:41-44)
+function fill_box_result!(res, C, R, blocks, sizes, opts, dimensions, δ, N)
+    t0, t1 = 0.0, δ
+    for k in 1:N
+        arr = Vector{LazySet{Float64}}(undef, length(blocks)); o = 0
+        for (i, b) in enumerate(blocks)
+            len = Int(sizes[i])
+            T = opts isa Union{AbstractVector, Dict} ? opts[b] : opts
+            arr[i] = T === Interval ? Interval(C[o+1, k] - R[o+1, k], C[o+1, k] + R[o+1, k]) :
+                                      Hyperrectangle(C[o+1:o+len, k], R[o+1:o+len, k])
+            o += len
+        end
+        res[k] = SparseReachSet(CartesianProductArray(arr), t0, t1, dimensions)
+        t0 = t1; t1 += δ
+    end
+    return res
+end
+
+# ---- reach_blocks.jl:47-132 -- the sparse twin (a `SparseMatrixCSC` ϕ, e.g. exp_method = "pade"): same 15 positional
+#      arguments.  The CSC fields cross the ABI as they are; a ϕ of decoupled subsystems skips its zero blocks on the device
+#      (reach_bffpsv18_boxes_csc), everything else computes the same sets through the dense method.
+function reach_blocks!(ϕ::SparseMatrixCSC{Float64, Int64},
+                       Xhat0::Vector{<:LazySet{Float64}},
+                       U::Union{ConstantInput, Nothing},
+                       overapproximate::Function,
+                       overapproximate_inputs::Function,
+                       n::Int,
+                       N::Union{Int, Nothing},
+                       output_function::Union{Function, Nothing},
+                       blocks::AbstractVector{Int},
+                       partition::AbstractVector{<:Union{AbstractVector{Int}, Int}},
+                       dimensions::Vector{Int},
+                       δ::Float64,
+                       termination::Function,
+                       progress_meter::Union{Progress, Nothing},
+                       res::Vector{<:AbstractReachSet}
+                       )::Tuple{Int, Bool}
+    box0 = boxof(Xhat0)
+    if output_function !== nothing || N === nothing || box0 === nothing || !box_blocks(overapproximate) ||
+       !plain_termination(termination)
+        return reach_blocks!(Matrix{Float64}(ϕ), Xhat0, U, overapproximate, overapproximate_inputs, n, N, output_function,
+                             blocks, partition, dimensions, δ, termination, progress_meter, res)
+    end
+    ctx = context()
+    c0, r0 = box0
+    m, MU, cU, rU, rψ = inputs_of(U, n)
+    rows = Int32.(dimensions .- 1); nr = length(rows)
+    sizes = Int32[length(partition[b]) for b in blocks]
+    C = Matrix{Float64}(undef, nr, N); R = Matrix{Float64}(undef, nr, N); done = Ref{Int64}(0)
+    check(ctx, ccall((:reach_bffpsv18_boxes_csc, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        ctx.handle, n, nnz(ϕ), ϕ.colptr, ϕ.rowval, ϕ.nzval, c0, r0, m, MU, n, cU, rU, rψ, nr, rows, N, C, R, done))
+    fill_box_result!(res, C, R, blocks, sizes, captured(overapproximate, :block_options_iter), dimensions, δ, N)
+    return N, false
+end
+
 # ---- reach_blocks.jl:135-224 -- the registry's "explicit_blocks" function for a dense Φ; same 15 positional arguments ------
 function reach_blocks!(ϕ::Matrix{Float64},
                        Xhat0::Vector{<:LazySet{Float64}},
@@ -212,19 +269,7 @@ function reach_blocks!(ϕ::Matrix{Float64},
             (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64},
              Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
             ctx.handle, n, ϕ, n, c0, r0, m, MU, n, cU, rU, rψ, nr, rows, N, C, R, done))
-        opts = captured(overapproximate, :block_options_iter)
-        for k in 1:N       # regroup the rows into the blocks' set types (store!, reach_blocks.jl:41-44)
-            arr = Vector{LazySet{Float64}}(undef, length(blocks)); o = 0
-            for (i, b) in enumerate(blocks)
-                len = Int(sizes[i])
-                T = opts isa Union{AbstractVector, Dict} ? opts[b] : opts
-                arr[i] = T === Interval ? Interval(C[o+1, k] - R[o+1, k], C[o+1, k] + R[o+1, k]) :
-                                          Hyperrectangle(C[o+1:o+len, k], R[o+1:o+len, k])
-                o += len
-            end
-            res[k] = SparseReachSet(CartesianProductArray(arr), t0, t1, dimensions)
-            t0 = t1; t1 += δ
-        end
+        fill_box_result!(res, C, R, blocks, sizes, captured(overapproximate, :block_options_iter), dimensions, δ, N)
     else                   # reach.jl:73-82: the stored set is box_approximation(M * CPA(Xhat_k)); blocks stay lazy
         Mfull = output_matrix(output_function); Mout = Mfull[:, dimensions]; q = size(Mout, 1)
         C = Matrix{Float64}(undef, q, N); R = Matrix{Float64}(undef, q, N)

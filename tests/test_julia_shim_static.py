@@ -43,7 +43,8 @@ def test_every_ccall_matches_the_ctypes_signature():
         assert {"Int32": C.c_int32, "Cvoid": None, "Cstring": C.c_char_p}[ret] is restype, f"{name}: return type"
     for needed in ("reach_ctx_create_multi", "reach_expm", "reach_phi12", "reach_discretize_zonotope", "reach_bffpsv18_boxes",
                    "reach_bffpsv18_output_map", "reach_bffpsv18_check", "reach_glgm06_create", "reach_glgm06_run_fetch",
-                   "reach_reduce_order", "reach_flowpipe_project", "reach_sparse_create", "reach_bffpsv18_boxes_lazy"):
+                   "reach_reduce_order", "reach_flowpipe_project", "reach_sparse_create", "reach_bffpsv18_boxes_lazy",
+                   "reach_bffpsv18_boxes_csc"):
         assert needed in seen, f"the shim no longer binds {needed}"
 
 
