@@ -307,10 +307,10 @@ def run_bffpsv18(args, rank, world, dist):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (M=16128, N=1008, K=1006) from the
-                     # `ncu --set full` capture profiles/r01/ncu_gemm_dmma_c3_raw_summary.txt: 138.8 MB + 93.2 MB
-                     # (algorithmic: 130 MB stack read + 8 MB Phi^s + 130 MB stack write, part of which stays in L2)
-                     "traffic": 232.0e6 if (w.n == 1006 and world == 1) else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch (21 stacked row blocks: M=21168,
+                     # N=1008, K=1006) from the `ncu --set full` capture profiles/r02/ncu_c3_power_gemm_final.txt: 182.4 MB +
+                     # 146.3 MB (algorithmic: 171 MB stack read + 8 MB Phi^s + 171 MB stack write, part of which stays in L2)
+                     "traffic": 328.7e6 if (w.n == 1006 and world == 1) else None,
                      "kernel": "gemm_dmma_kernel (stacked power GEMM S·[Phi^s | dB | c0])",
                      "launches": int(gemm_launches), "kernel_ms_total": gemm_ms,
                      "kernel_share_of_step": gemm_ms / ms,
