@@ -523,9 +523,7 @@ def _post_bffpsv18(op, problem, opts, ctx):
     types = _block_set_types(op, partition)
     if op["discretization"] not in ("forward", "backward", "firstorder", "nobloating"):
         raise ValueError(f"the algorithm {op['discretization']} is unknown")          # discretize.jl:121
-    if op["exp_method"] not in ("base", "sm100a", "lazy"):
-        if op["exp_method"] == "pade":
-            raise ReachError(3, "exp_method 'pade' is unsupported on the sm_100a path")
+    if op["exp_method"] not in ("base", "sm100a", "lazy", "pade"):
         raise ValueError(f"the exponentiation method {op['exp_method']} is unknown")    # ArgumentError, discretize.jl:158
     c, r = _as_box(problem.x0, "initial set")
     N = int(math.ceil(T / delta))                                          # reach.jl:54
@@ -576,7 +574,14 @@ def _post_bffpsv18(op, problem, opts, ctx):
         def make(i):
             return ReachSet(Hyperrectangle(C[:, i], R[:, i]), float(t0[i]), float(t1[i]))     # reach.jl:82
         return ReachSolution([Flowpipe(_LazyReachSets(N, make))], opts, dict(centers=C, radii=R))
-    C, R = ctx.bffpsv18_boxes(D["Phi"], D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
+    if op["exp_method"] == "pade":
+        # `padm(A*δ)` (discretize.jl:155-156, Expokit's Padé approximant for a sparse A): the same matrix e^{Aδ} to rounding --
+        # the device computes it with its own scaling-and-squaring scheme -- used in SPARSE form, i.e. through the sparse twin
+        # of reach_blocks! (reach_blocks.jl:47-132): decoupled subsystems skip their zero blocks on the device
+        import scipy.sparse as sp
+        C, R = ctx.bffpsv18_boxes_csc(sp.csc_matrix(D["Phi"]), D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
+    else:
+        C, R = ctx.bffpsv18_boxes(D["Phi"], D["c0"], D["r0"], N, D["MU"], D["cU"], D["rU"], D["rpsi"], rows)
     return _box_solution(C, R, N, delta, partition, blocks, dims, types, opts, D)
 
 

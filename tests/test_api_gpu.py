@@ -240,3 +240,28 @@ def test_varying_input_is_discretised_but_not_propagated():               # disc
     with pytest.raises(ReachError) as ei:
         solve(IVP(CLCCS(A, B, None, U), BallInf(np.zeros(2), 0.1)), Options(T=0.1))
     assert ei.value.code == 3
+
+
+def test_pade_exp_method_runs_the_sparse_twin():                            # BFFPSV18(:exp_method => "pade"), discretize.jl:155-156
+    """`padm(A*δ)` keeps ϕ sparse, so the reference takes reach_blocks!(ϕ::SparseMatrixCSC, ...) (reach_blocks.jl:47-132); the
+    mirror routes the flowpipe through reach_bffpsv18_boxes_csc: decoupled subsystems skip their zero blocks, same sets."""
+    import scipy.sparse as sp
+    g = np.random.default_rng(8)
+    n = 14
+    Ad = np.zeros((n, n))
+    for i in range(0, n, 2):                       # seven decoupled damped oscillators, states interleaved by a permutation
+        w = g.uniform(1.0, 6.0)
+        Ad[i:i + 2, i:i + 2] = [[-0.1, w], [-w, -0.1]]
+    perm = g.permutation(n)
+    Ad = Ad[np.ix_(perm, perm)]
+    Bd = g.standard_normal((n, 1))
+    prob = lambda Amat: IVP(CLCCS(Amat, Bd, None, Interval(0.9, 1.1)), BallInf(np.ones(n), 0.05))
+    op = lambda method: BFFPSV18(δ=0.02, vars=[1, 4, 13], exp_method=method)
+    from reachability_jl_b200 import api
+    dense = solve(prob(Ad), Options(T=0.6), op=op("base"))
+    pade = solve(prob(sp.csc_matrix(Ad)), Options(T=0.6), op=op("pade"))
+    info = api._context(0).csc_info()
+    assert info["sparse_path"] and info["max_component"] == 2
+    assert_close(pade.arrays["centers"], dense.arrays["centers"], "centres")
+    assert_close(pade.arrays["radii"], dense.arrays["radii"], "radii")
+    assert len(pade.flowpipes[0].reachsets) == 30 and dim(set_of(pade.flowpipes[0].reachsets[7])) == 3
