@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(GP g) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { g.cntS[t * 2 + seg] = nvalid; g.cntZ[t * 2 + seg] = nzero; }
 }
 
-// Same result as sort_segments_kernel for segments of up to 4096 generators: bitonic sort of (score, index) pairs in
+// Same result as sort_segments_kernel for segments of up to BITONIC_MAX generators: bitonic sort of (score, index) pairs in
 // shared memory, one CTA per (step, segment).  O(len log^2 len) instead of O(len^2).
-constexpr int BITONIC_MAX = 4096;
+constexpr int BITONIC_MAX = 16384;      // 12 B per element of dynamic shared memory: 192 KB (n = 1024 has p0 = 4n + m + 1 = 4100 generators)
 __global__ void __launch_bounds__(512) sort_segments_bitonic_kernel(GP g, int P) {
     extern __shared__ __align__(16) unsigned char bsm[];
     double* kk = reinterpret_cast<double*>(bsm);            // [P] scores

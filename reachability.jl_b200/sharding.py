@@ -135,22 +135,31 @@ def run_sharded(engine, dist, as_tensor=None, sync=None, stream_ordered=None, ge
         main = torch.cuda.current_stream()
         nb = engine.nbatches()
 
-        def reduce_buffers(b, phase):
+        def reduce_buffers(b, phase, async_op=False):
+            works = []
             for which in SHARD_COLLECTIVES[phase]:
                 buf = engine.buffer(b, which)
                 if buf is not None:
-                    dist.all_reduce(as_tensor(buf), op=dist.ReduceOp.SUM)
+                    w = dist.all_reduce(as_tensor(buf), op=dist.ReduceOp.SUM, async_op=async_op)
+                    if async_op and w is not None:
+                        works.append(w)
+            return works
 
         gemm_stream.wait_stream(main)
         engine.phase(0, 0, stream=gemm_stream.cuda_stream)
         for b in range(nb):
             with torch.cuda.stream(gemm_stream):
-                reduce_buffers(b, 0)                                    # scores / masks of batch b (its phase 0 is in flight)
+                # scores / masks of batch b (its phase 0 is in flight on gemm_stream).  ASYNC: the collective waits for
+                # gemm_stream, but gemm_stream does not wait for the collective -- NCCL runs its collectives in issue order, so a
+                # blocking all-reduce here would hold the GEMM of batch b + 1 back until phases 1..3 of batch b - 1 are through
+                works = reduce_buffers(b, 0, async_op=True)
                 ready = torch.cuda.Event()
-                ready.record(gemm_stream)
+                ready.record(gemm_stream)                               # the kernels of phase 0 of batch b
                 if b + 1 < nb:
                     engine.phase(b + 1, 0, stream=gemm_stream.cuda_stream)     # overlaps everything below
             main.wait_event(ready)
+            for w in works:
+                w.wait()                                                # the MAIN stream waits for the all-reduced scores
             for phase in (1, 2, 3):
                 engine.phase(b, phase, stream=main.cuda_stream)
                 reduce_buffers(b, phase)

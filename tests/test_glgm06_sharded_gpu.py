@@ -198,7 +198,7 @@ def test_run_sharded_with_a_gemm_stream_single_rank(ctx_on_torch_stream):
             SUM = None
 
         @staticmethod
-        def all_reduce(t, op=None):
+        def all_reduce(t, op=None, async_op=False):
             return None
 
     A, X0, B, U = _problem(77, 40, 3)

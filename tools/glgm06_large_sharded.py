@@ -48,7 +48,7 @@ with rb.Context(dev, stream=stream.cuda_stream) as ctx:
 
     class _Solo:            # world 1: the sharded engine with one rank (no collectives)
         @staticmethod
-        def all_reduce(t, op=None):
+        def all_reduce(t, op=None, async_op=False):
             return None
         class ReduceOp:
             SUM = None
