@@ -2611,7 +2611,11 @@ void flowpipe_shard_phase(Flowpipe* F, int64_t b, int phase, cudaStream_t on) {
     if (phase == 0) {
         if (on) {       // overlapped with phases 1..3 of the previous batch: leave them SMs (the chain runs replicated on every rank)
             const char* r = getenv("REACH_GEMM_RESERVE");
-            ctx->gemm_reserve_sms = r ? atoi(r) : std::max(8, partition_reserve(F, F->qloc, (F->p0 + F->pV) / F->nranks + 1, false));
+            // the selection, the segment sort and the R ranks run REPLICATED on every rank while the GEMM shrinks with the number
+            // of ranks, so their share of the SMs has to grow with it (n = 1024, 8 GPUs, N = 600: K = 8 / 16 / 32 -> 37.9 / 33.9 /
+            // 33.0 ms per flowpipe)
+            const int k_rep = std::min(48, 8 + 3 * F->nranks);
+            ctx->gemm_reserve_sms = r ? atoi(r) : std::max(k_rep, partition_reserve(F, F->qloc, (F->p0 + F->pV) / F->nranks + 1, false));
         }
         if (b >= 2 && F->sched[b - 2].square_after) {      // Phi^(2w) for this batch (doubling phase of the schedule)
             DMat* spare[2] = {&F->PowA, &F->PowB};
