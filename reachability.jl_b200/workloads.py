@@ -81,7 +81,7 @@ def iss(n_modes: int = 135, delta: float = 0.01, T: float = 20.0, seed: int = 27
     return Workload("C2-iss", A, c, r, B, cU, rU, delta, T, "GLGM06", max_order=max_order)
 
 
-def iss_mixed(n_modes: int = 512, delta: float = 0.01, T: float = 2.0, seed: int = 1024, max_order: int = 10) -> Workload:
+def iss_mixed(n_modes: int = 512, delta: float = 0.01, T: float = 6.0, seed: int = 1024, max_order: int = 10) -> Workload:
     """A large n * p GLGM06 case (what the generator-column sharding exists for): the lightly damped
     modes of `iss` under a random orthogonal change of coordinates, so A -- and every power of Phi -- is DENSE and the
     generator map is the DMMA GEMM.  n = 2 * n_modes (1024), three inputs, same reachable set as the decoupled modes up to
