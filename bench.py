@@ -613,7 +613,8 @@ def run_glgm06(args, rank, world, dist, e2e=True):
         # structurally sparse Phi: no GEMM on the path; the HBM-bound numerics are the dominant kernels by bytes, the selection
         # chain is the critical path by latency
         map_obj = {"kind": "ell_sparse", "nnz_per_row": map_info["nnz_per_row"], "launches": nbatches,
-                   "kernel": "ell_left_kernel (Phi^w in ELL form, thread per state row, 16 generators per CTA)",
+                   "kernel": "ell_left_score_kernel (Phi^w in ELL form, thread per state row, 16 generators per CTA staged with one bulk copy in "
+                             "and one out, Girard scores and row-support masks fused)",
                    "kernel_ms_total": tt["gemm_ms"], "algorithmic_gbs": map_bytes / (tt["gemm_ms"] * 1e-3) / 1e9 if tt["gemm_ms"] else None,
                    "note": "Phi of this workload (decoupled modes) and its powers have 2 non-zeros per row; detected at creation, "
                            "results equal the dense GEMM's (tests/test_glgm06_gpu.py::test_sparse_phi_map_equals_dense_gemm); "
