@@ -348,14 +348,21 @@ int64_t choose_block(int64_t n, int64_t Rp, int64_t N, int64_t m, int sms) {
     // ... then ANY depth in [s0, 2 s0] (not only powers of two): the persistent GEMM hands out equal tiles, so the launch
     // takes ceil(tiles / SMs) waves -- pick the depth whose last wave is fullest and whose row padding is smallest
     // (C3: s = 16 -> 1008 tiles = 6.8 waves, 97.3 % of the tile slots used; s = 49 -> 3088 tiles = 20.9 waves, 99.3 %)
+    // A depth that is not a power of two costs extra n^3 products for Phi^s and extra underfilled launches while the stack is
+    // built, which matters when few rows are left per GPU (C3 on 8 GPUs: 126 rows, s0 = 128 already fills 98.8 % of its tile
+    // slots): leave s0 only for a gain of more than 2 %.
     int64_t best = s0;
     double best_eff = 0.0;
-    for (int64_t s = s0; s <= 2 * s0 && s <= N - 1 && s <= 1024 && bytes_per_block * (double)s <= 24e9; ++s) {
+    auto eff_of = [&](int64_t s) {
         const int64_t tiles = ceil_div(s * Rp, 128) * tiles_n;
-        const double eff = (double)(s * Rp) / 128.0 * (double)tiles_n / (double)(ceil_div(tiles, sms) * sms);
+        return (double)(s * Rp) / 128.0 * (double)tiles_n / (double)(ceil_div(tiles, sms) * sms);
+    };
+    const double eff0 = eff_of(s0);
+    for (int64_t s = s0; s <= 2 * s0 && s <= N - 1 && s <= 1024 && bytes_per_block * (double)s <= 24e9; ++s) {
+        const double eff = eff_of(s);
         if (eff > best_eff + 1e-3) { best_eff = eff; best = s; }
     }
-    return best;
+    return best_eff > eff0 + 0.02 ? best : s0;
 }
 
 }  // namespace
